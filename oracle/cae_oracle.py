@@ -1,0 +1,290 @@
+"""CPU oracle for hot path 1 (convolutional autoencoder / PS-VAE).  TEST INFRASTRUCTURE ONLY.
+
+This is a plain-PyTorch fp32 (or fp64) restatement of what the reference computes for the CAE
+path, written functionally over a reference-named ``state_dict``.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may import
+it; the product (``behavenet_b200``) never does.
+
+Pinning: the restatement is checked against the UNMODIFIED reference classes
+(``behavenet.models.AE`` / ``PSVAE`` imported from /root/reference) by
+``oracle/gen_golden.py`` -- which also writes the committed fixtures under ``tests/golden/`` --
+and against the closed forms of the reference's own ``tests/test_fitting/test_losses.py``
+(re-stated in ``tests/test_oracle_cae.py``).
+
+Reference lines followed (all under /root/reference/behavenet):
+  encoder forward   models/aes.py:181-218   (ZeroPad2d -> Conv2d -> LeakyReLU(0.05), flatten C,H,W)
+  decoder forward   models/aes.py:432-488   (FF -> view(C0,H0,W0) -> ConvT -> crop -> LeakyReLU .. Sigmoid)
+  AE.loss           models/aes.py:722-773   (<=200-frame chunks, per-chunk mean loss + backward)
+  PS encoder        models/vaes.py:1319-1363
+  PSVAE.forward     models/vaes.py:571-601 ; reparameterize 17-35 (std = exp(logvar))
+  PSVAE.loss        models/vaes.py:603-729
+  losses            fitting/losses.py:36-59 (mse) 62-96 (gaussian_ll) 130-147 (kl) 284-372 (decomposed kl)
+"""
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LN2PI = math.log(2 * math.pi)
+LEAK = 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# losses (fitting/losses.py)
+# ------------------------------------------------------------------------------------------------
+
+def mse(y_pred, y_true, masks=None):
+    """losses.py:36-59 -- mean over ALL elements of (diff^2 * mask)."""
+    d = (y_pred - y_true) ** 2
+    if masks is not None:
+        d = d * masks
+    return d.mean()
+
+
+def gaussian_ll(y_pred, y_mean, masks=None, std=1):
+    """losses.py:62-96 -- sum over dims, mean over batch, fixed std."""
+    n_dims = int(np.prod(y_pred.shape[1:]))
+    d = (y_pred - y_mean) ** 2
+    if masks is not None:
+        d = d * masks
+    per_frame = d.reshape(d.shape[0], -1).sum(1)
+    ll = -(0.5 * LN2PI + 0.5 * math.log(std ** 2)) * n_dims - (0.5 / std ** 2) * per_frame
+    return ll.mean()
+
+
+def gaussian_ll_to_mse(ll, n_dims, gaussian_std=1, mse_std=1):
+    """losses.py:99-127."""
+    v = float(ll) + (0.5 * LN2PI + 0.5 * math.log(gaussian_std ** 2)) * n_dims
+    v *= -(gaussian_std ** 2) / 0.5
+    v /= n_dims
+    return v / (mse_std ** 2)
+
+
+def kl_div_to_std_normal(mu, logvar):
+    """losses.py:130-147."""
+    return (0.5 * (logvar.exp() - logvar + mu ** 2 - 1).sum(1)).mean()
+
+
+def decomposed_kl(z, mu, logvar):
+    """losses.py:284-351 -- minibatch estimators (index-code MI, total correlation, dim-wise KL)."""
+    # [j, i, l]: log q(z_j,l | x_i)
+    lq = -0.5 * (torch.exp(-logvar)[None] * (z[:, None] - mu[None]) ** 2 + logvar[None] + LN2PI)
+    joint = lq.sum(2)                                   # (j, i)
+    log_qz = torch.logsumexp(joint, dim=1)              # log sum_i prod_l
+    log_qz_diag = torch.diagonal(joint)                 # log q(z_j | x_j)
+    log_qz_prod = torch.logsumexp(lq, dim=1).sum(1)     # sum_l log sum_i
+    log_pz = (-0.5 * (z ** 2 + LN2PI)).sum(1)
+    return ((log_qz_diag - log_qz).mean(), (log_qz - log_qz_prod).mean(),
+            (log_qz_prod - log_pz).mean())
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder / decoder (models/aes.py)
+# ------------------------------------------------------------------------------------------------
+
+def n_conv_layers(hparams):
+    return len(hparams['ae_encoding_n_channels'])
+
+
+def encoder_features(sd, hparams, x, prefix='encoding.'):
+    """Conv stack of ConvAEEncoder.forward (aes.py:181-214); returns flattened (N, C*H*W)."""
+    for i in range(n_conv_layers(hparams)):
+        x0, x1 = hparams['ae_encoding_x_padding'][i]
+        y0, y1 = hparams['ae_encoding_y_padding'][i]
+        s = hparams['ae_encoding_stride_size'][i]
+        # symmetric: Conv2d(padding=(y0,x0)); asymmetric: ZeroPad2d((x0,x1,y0,y1)) + padding 0
+        # (aes.py:141-155) -- numerically the same explicit zero pad
+        x = F.pad(x, (x0, x1, y0, y1))
+        x = F.conv2d(x, sd[prefix + 'encoder.conv%i.weight' % i],
+                     sd[prefix + 'encoder.conv%i.bias' % i], stride=s)
+        x = F.leaky_relu(x, LEAK)
+    return x.reshape(x.shape[0], -1)
+
+
+def encode(sd, hparams, x, prefix='encoding.'):
+    """ConvAEEncoder.forward -> z   (or (mu, logvar) if hparams['variational'])."""
+    h = encoder_features(sd, hparams, x, prefix)
+    z = F.linear(h, sd[prefix + 'FF.weight'], sd[prefix + 'FF.bias'])
+    if hparams.get('variational', False):
+        return z, F.linear(h, sd[prefix + 'logvar.weight'], sd[prefix + 'logvar.bias'])
+    return z
+
+
+def decode(sd, hparams, z, prefix='decoding.'):
+    """ConvAEDecoder.forward (aes.py:432-488)."""
+    c0, h0, w0 = hparams['ae_decoding_starting_dim']
+    x = F.linear(z, sd[prefix + 'FF.weight'], sd[prefix + 'FF.bias']).view(-1, c0, h0, w0)
+    n = len(hparams['ae_decoding_n_channels'])
+    for i in range(n):
+        x0, x1 = hparams['ae_decoding_x_padding'][i]
+        y0, y1 = hparams['ae_decoding_y_padding'][i]
+        s = hparams['ae_decoding_stride_size'][i]
+        # symmetric pads go in as ConvTranspose2d(padding=...), asymmetric as a crop afterwards
+        # (aes.py:404-418, 467-470): both are "full transposed conv, then crop"
+        x = F.conv_transpose2d(x, sd[prefix + 'decoder.convtranspose%i.weight' % i],
+                               sd[prefix + 'decoder.convtranspose%i.bias' % i], stride=s)
+        x = x[:, :, y0:x.shape[2] - y1, x0:x.shape[3] - x1]
+        x = torch.sigmoid(x) if i == n - 1 else F.leaky_relu(x, LEAK)
+    return x
+
+
+def ae_forward(sd, hparams, x):
+    """AE.forward (aes.py:695-720) -> (x_hat, z)."""
+    z = encode(sd, hparams, x)
+    return decode(sd, hparams, z), z
+
+
+def _chunks(n, chunk_size):
+    return [(b, min(b + chunk_size, n)) for b in range(0, n, chunk_size)]
+
+
+def ae_loss(sd, hparams, x, masks=None, chunk_size=200, want_grads=True):
+    """AE.loss (aes.py:722-773): returns ({'loss': float}, {name: grad}) with the reference's
+    chunk semantics (each chunk back-propagates its own mean)."""
+    params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
+    total = 0.0
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in = x[b:e]
+        x_hat, _ = ae_forward(params, hparams, x_in)
+        loss = mse(x_in, x_hat, None if masks is None else masks[b:e])
+        if want_grads:
+            loss.backward()
+        total += loss.item() * (e - b)
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return {'loss': total / x.shape[0]}, grads
+
+
+# ------------------------------------------------------------------------------------------------
+# PS-VAE (models/vaes.py)
+# ------------------------------------------------------------------------------------------------
+
+def psvae_forward(sd, hparams, x, eps=None, use_mean=False):
+    """PSVAE.forward (vaes.py:571-601) with the reparameterisation noise injected.
+
+    Returns (x_hat, z, mu, logvar, y_hat).  ``eps`` replaces ``torch.randn_like`` in
+    ``reparameterize`` (vaes.py:33-35; std = exp(logvar), reproduced as is).
+    """
+    n_labels = hparams['n_labels']
+    h = encoder_features(sd, hparams, x)
+    pre = F.linear(h, sd['encoding.FF.weight'], sd['encoding.FF.bias'])
+    y = F.linear(pre, sd['encoding.A.weight'])
+    w = F.linear(pre, sd['encoding.B.weight'])
+    logvar = F.linear(h, sd['encoding.logvar.weight'], sd['encoding.logvar.bias'])
+    mu = torch.cat([y, w], 1)
+    z = mu if use_mean else eps * torch.exp(logvar) + mu
+    x_hat = decode(sd, hparams, z)
+    y_hat = y * sd['encoding.D.weight'] + sd['encoding.D.bias']      # DiagLinear, base.py:70-103
+    assert y_hat.shape[1] == n_labels
+    return x_hat, z, mu, logvar, y_hat
+
+
+def psvae_loss(sd, hparams, x, labels, eps, masks=None, labels_masks=None, alpha=None, beta=None,
+               kl_anneal=1.0, chunk_size=200, want_grads=True):
+    """PSVAE.loss (vaes.py:603-729) for fixed (alpha, beta, kl-anneal) weights.
+
+    Returns (loss dict, grads).  'label_r2' is omitted (sklearn, CPU-side in the reference too,
+    vaes.py:711-718); 'loss_data_mse' reproduces the running-sum quirk of vaes.py:705-706.
+    """
+    alpha = hparams['ps_vae.alpha'] if alpha is None else alpha
+    beta = hparams['ps_vae.beta'] if beta is None else beta
+    nl = hparams['n_labels']
+    frozen = ('encoding.A.weight', 'encoding.B.weight')
+    params = {k: v.detach().clone().requires_grad_(want_grads and k not in frozen)
+              for k, v in sd.items()}
+    keys = ['loss', 'loss_data_ll', 'loss_label_ll', 'loss_zs_kl', 'loss_zu_mi', 'loss_zu_tc',
+            'loss_zu_dwkl']
+    vals = {k: 0.0 for k in keys}
+    vals['loss_data_mse'] = 0.0
+    n_pix = int(np.prod(x.shape[1:]))
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in, y_in = x[b:e], labels[b:e]
+        x_hat, z, mu, logvar, y_hat = psvae_forward(params, hparams, x_in, eps[b:e])
+        t = {}
+        t['loss_data_ll'] = gaussian_ll(x_in, x_hat, None if masks is None else masks[b:e])
+        t['loss_label_ll'] = gaussian_ll(
+            y_in, y_hat, None if labels_masks is None else labels_masks[b:e])
+        t['loss_zs_kl'] = kl_div_to_std_normal(mu[:, :nl], logvar[:, :nl])
+        t['loss_zu_mi'], t['loss_zu_tc'], t['loss_zu_dwkl'] = decomposed_kl(
+            z[:, nl:], mu[:, nl:], logvar[:, nl:])
+        t['loss'] = (-t['loss_data_ll'] - alpha * t['loss_label_ll'] + t['loss_zs_kl']
+                     + kl_anneal * t['loss_zu_mi'] + beta * t['loss_zu_tc']
+                     + kl_anneal * t['loss_zu_dwkl'])
+        if want_grads:
+            t['loss'].backward()
+        bs = e - b
+        for k in keys:
+            vals[k] += t[k].item() * bs
+        vals['loss_data_mse'] += gaussian_ll_to_mse(vals['loss_data_ll'] / bs, n_pix) * bs
+    for k in vals:
+        vals[k] /= x.shape[0]
+    vals['alpha'], vals['beta'] = alpha, beta
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return vals, grads
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic parameters with the reference's shapes/names (torch default inits)
+# ------------------------------------------------------------------------------------------------
+
+def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class='ae',
+                 n_labels=0, arch=None):
+    """hparams dict as the reference's grid-search mains assemble it (ae_grid_search.py:20-30)."""
+    from behavenet_b200.models.ae_model_architecture_generator import (
+        load_default_arch, get_handcrafted_dims)
+    hp = load_default_arch() if arch is None else dict(arch)
+    hp['ae_batch_norm'] = False
+    hp['ae_input_dim'] = [n_input_channels, y_pixels, x_pixels]
+    hp['n_input_channels'], hp['y_pixels'], hp['x_pixels'] = n_input_channels, y_pixels, x_pixels
+    hp['n_ae_latents'] = n_ae_latents
+    hp = get_handcrafted_dims(hp, symmetric=True)
+    hp['model_class'] = model_class
+    hp['model_type'] = 'conv'
+    hp['fit_sess_io_layers'] = False
+    if model_class == 'ps-vae':
+        hp.update({'n_labels': n_labels, 'ps_vae.alpha': 1000, 'ps_vae.beta': 10,
+                   'ps_vae.anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
+    return hp
+
+
+def init_state_dict(hparams, seed=0, dtype=torch.float32):
+    """Random parameters with the reference's names/shapes, drawn
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like torch's default Conv2d/ConvTranspose2d/Linear
+    initialisers, from a private generator under ``seed``."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def uniform(shape, bound):
+        return ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+
+    def put(name, w_shape, fan_in, n_bias):
+        sd[name + '.weight'] = uniform(w_shape, 1 / math.sqrt(fan_in))
+        sd[name + '.bias'] = uniform((n_bias,), 1 / math.sqrt(fan_in))
+
+    c_in = hparams['ae_input_dim'][0]
+    for i, c in enumerate(hparams['ae_encoding_n_channels']):
+        k = hparams['ae_encoding_kernel_size'][i]
+        put('encoding.encoder.conv%i' % i, (c, c_in, k, k), c_in * k * k, c)
+        c_in = c
+    feat = c_in * hparams['ae_encoding_y_dim'][-1] * hparams['ae_encoding_x_dim'][-1]
+    L = hparams['n_ae_latents']
+    put('encoding.FF', (L, feat), feat, L)
+    if hparams.get('variational', False):
+        put('encoding.logvar', (L, feat), feat, L)
+    if hparams.get('model_class') == 'ps-vae':
+        nl = hparams['n_labels']
+        q, _ = torch.linalg.qr(torch.randn(L, L, generator=g, dtype=torch.float64))
+        sd['encoding.A.weight'] = q[:nl].to(dtype).contiguous()
+        sd['encoding.B.weight'] = q[nl:].to(dtype).contiguous()
+        sd['encoding.D.weight'] = uniform((nl,), 1 / math.sqrt(nl))
+        sd['encoding.D.bias'] = uniform((nl,), 1 / math.sqrt(nl))
+    c0, h0, w0 = hparams['ae_decoding_starting_dim']
+    put('decoding.FF', (c0 * h0 * w0, L), L, c0 * h0 * w0)
+    c_in = c0
+    for i, c in enumerate(hparams['ae_decoding_n_channels']):
+        k = hparams['ae_decoding_kernel_size'][i]
+        # torch computes ConvTranspose2d fan_in from weight.size(1) = out channels
+        put('decoding.decoder.convtranspose%i' % i, (c_in, c, k, k), c * k * k, c)
+        c_in = c
+    return sd

@@ -1,0 +1,186 @@
+"""Generate the committed golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the authoring container only (needs /root/reference):
+
+    python oracle/gen_golden.py
+
+* CAE / PS-VAE: imports ``behavenet.models.AE`` / ``PSVAE`` from /root/reference (with a stub for
+  the absent ``commentjson`` module, which the reference only uses to read arch json files),
+  loads the seeded parameters of ``oracle.cae_oracle.init_state_dict`` into them, runs
+  ``forward`` and ``loss`` on seeded inputs and stores inputs' seeds + outputs.  It also asserts
+  that the oracle restatement (oracle/cae_oracle.py) reproduces the reference to fp32 round-off,
+  which is what pins the oracle.
+* ARHMM: ``ssm`` is not available, so the fixture holds the restated oracle's own outputs on a
+  small seeded problem (regression fixture, parity unpinned -- see oracle/arhmm_oracle.py).
+
+The fixtures are small .npz files (a few hundred KB in total).
+"""
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+sys.modules.setdefault('commentjson', types.ModuleType('commentjson'))
+
+from oracle import cae_oracle as co          # noqa: E402
+from oracle import arhmm_oracle as ao        # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+# (name, C, H, W, latents, batch, model_class, n_labels, chunk_size)
+CAE_CASES = [
+    ('c1_ae_32x32x1_l8_b32', 1, 32, 32, 8, 32, 'ae', 0, 200),
+    ('ae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'ae', 0, 4),          # integration-test geometry, 2 chunks
+    ('ae_128x128x1_l12_b3', 1, 128, 128, 12, 3, 'ae', 0, 200),   # C2 geometry, tiny batch
+    ('psvae_128x128x2_l16_b5', 2, 128, 128, 16, 5, 'ps-vae', 4, 3),  # C3 geometry, 2 chunks
+    ('psvae_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'ps-vae', 3, 200),
+]
+
+
+def synth_inputs(case):
+    name, c, h, w, L, b, mc, nl, chunk = case
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(b, c, h, w, generator=g)
+    out = {'x': x}
+    if mc == 'ps-vae':
+        out['labels'] = torch.randn(b, nl, generator=g)
+        out['eps'] = torch.randn(b, L, generator=g)
+    out['masks'] = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
+    return out
+
+
+def run_reference(case):
+    from behavenet.models import AE, PSVAE
+    import behavenet.models.vaes as vaes
+    name, c, h, w, L, b, mc, nl, chunk = case
+    hp = co.make_hparams(c, h, w, L, mc, nl)
+    sd = co.init_state_dict(hp, seed=0)
+    inp = synth_inputs(case)
+    res = {}
+    hp_ref = dict(hp)
+    if mc == 'ae':
+        model = AE(hp_ref)
+        model.load_state_dict(sd)
+        model.eval()
+        with torch.no_grad():
+            x_hat, z = model(inp['x'])
+        res['x_hat'], res['z'] = x_hat, z
+        for tag, m in (('', None), ('_masked', inp['masks'])):
+            model.zero_grad()
+            data = {'images': inp['x'][None]}
+            if m is not None:
+                data['masks'] = m[None]
+            loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+            res['loss' + tag] = torch.tensor(loss['loss'], dtype=torch.float64)
+            for k, p in model.named_parameters():
+                res['grad%s.%s' % (tag, k)] = p.grad.clone()
+        # pin the restatement
+        xo, zo = co.ae_forward(sd, hp, inp['x'])
+        assert torch.allclose(xo, x_hat, atol=1e-6), name
+        assert torch.allclose(zo, z, atol=1e-5), name
+        lo, go = co.ae_loss(sd, hp, inp['x'], None, chunk)
+        assert abs(lo['loss'] - float(res['loss'])) < 1e-7, name
+        for k, gref in go.items():
+            assert torch.allclose(gref, res['grad.' + k], atol=1e-6, rtol=1e-4), (name, k)
+    else:
+        model = PSVAE(hp_ref)
+        model.load_state_dict(sd)
+        model.eval()
+        eps_all = inp['eps']
+        # inject eps into reparameterize (vaes.py:33-35 draws torch.randn_like)
+        state = {'pos': 0}
+        orig = torch.randn_like
+
+        def fake_randn_like(t, *a, **k):
+            n = t.shape[0]
+            e = eps_all[state['pos']:state['pos'] + n]
+            state['pos'] += n
+            return e.to(t.dtype)
+        vaes.torch.randn_like = fake_randn_like
+        try:
+            with torch.no_grad():
+                state['pos'] = 0
+                x_hat, z, mu, logvar, y_hat = model(inp['x'])
+            res.update(x_hat=x_hat, z=z, mu=mu, logvar=logvar, y_hat=y_hat)
+            model.curr_epoch = 1
+            model.zero_grad()
+            state['pos'] = 0
+            data = {'images': inp['x'][None], 'labels': inp['labels'][None]}
+            loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+        finally:
+            vaes.torch.randn_like = orig
+        for k, v in loss.items():
+            res['loss.' + k] = torch.tensor(float(v), dtype=torch.float64)
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                res['grad.' + k] = p.grad.clone()
+        # pin the restatement
+        o = co.psvae_forward(sd, hp, inp['x'], inp['eps'])
+        for a, bref in zip(o, (x_hat, z, mu, logvar, y_hat)):
+            assert torch.allclose(a, bref, atol=2e-5), name
+        lo, go = co.psvae_loss(sd, hp, inp['x'], inp['labels'], inp['eps'], chunk_size=chunk)
+        for k in lo:
+            ref = float(res['loss.' + k])
+            assert abs(lo[k] - ref) <= 1e-5 * max(1.0, abs(ref)), (name, k, lo[k], ref)
+        for k, gref in go.items():
+            gr = res['grad.' + k]
+            assert torch.allclose(gref, gr, atol=1e-4 * float(gr.abs().max()) + 1e-7), (name, k)
+    return res
+
+
+def compact(res, big_limit=4096):
+    """Store small tensors whole; for big ones store a strided sample + fp64 checksums."""
+    out = {}
+    for k, v in res.items():
+        a = v.detach().cpu().numpy()
+        if a.size <= big_limit:
+            out[k] = a
+        else:
+            flat = a.reshape(-1)
+            idx = np.linspace(0, flat.size - 1, 2048).astype(np.int64)
+            out[k + '#idx'] = idx
+            out[k + '#val'] = flat[idx]
+            out[k + '#sum'] = np.array([flat.astype(np.float64).sum(),
+                                        np.abs(flat.astype(np.float64)).sum()])
+            out[k + '#shape'] = np.array(a.shape)
+    return out
+
+
+def gen_arhmm():
+    p = ao.synth_params(K=4, D=3, lags=2, seed=3, mix=0.05)
+    rng = np.random.RandomState(7)
+    lengths = [40, 3, 17, 1, 64]
+    xs = [ao.sample(p, T, rng)[1].astype(np.float32) for T in lengths]
+    out = {'lengths': np.array(lengths), 'x': np.concatenate(xs, 0),
+           'log_pi0': p.log_pi0, 'log_Ps': p.log_Ps, 'As': p.As, 'bs': p.bs, 'Sigmas': p.Sigmas,
+           'lags': np.array(p.lags)}
+    ez, ezz, lz, zs, lls = [], [], [], [], []
+    for x in xs:
+        ll = ao.ar_log_likelihoods(x, p.As, p.bs, p.Sigmas, p.lags)
+        g, j, n = ao.expected_states(p.log_pi0, p.log_Ps, ll)
+        ez.append(g); ezz.append(j); lz.append(n); lls.append(ll)
+        zs.append(ao.viterbi(p.log_pi0, p.log_Ps, ll))
+    out.update(Ez=np.concatenate(ez, 0), Ezz=np.stack(ezz), logZ=np.array(lz),
+               z=np.concatenate(zs), ll=np.concatenate(lls, 0))
+    np.savez_compressed(os.path.join(GOLD, 'arhmm_k4_d3_l2.npz'), **out)
+    print('arhmm fixture written')
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    for case in CAE_CASES:
+        res = run_reference(case)
+        np.savez_compressed(os.path.join(GOLD, case[0] + '.npz'), **compact(res))
+        print('wrote', case[0], {k: tuple(v.shape) for k, v in list(res.items())[:3]})
+    gen_arhmm()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,688 @@
+// Hot path 2: ARHMM E-step (forward-backward), log-likelihood and Viterbi on sm_100a.
+//
+// What the reference reaches through ssm (fitting/arhmm_grid_search.py:170-204, fitting/eval.py:167):
+//   hmm.fit(method='em') E-step  -> bn_arhmm_estep   (gamma, sum_t xi_t, log normaliser per trial)
+//   hmm.log_likelihood           -> bn_arhmm_estep with NULL Ez/Ezz (forward pass only)
+//   hmm.most_likely_states       -> bn_arhmm_viterbi
+//
+// Two kernels per call, by design (hard parts 1 and 7):
+//   1. emission kernel: embarrassingly parallel over timesteps.  The AR Gaussian log-density is
+//      folded into one whitened affine map per state, y = W_k [x_t, x_{t-1..t-L}, 1] with
+//      W_k = chol(Sigma_k)^-1 [I, -A_k, -b_k] (built on the host in fp64), ll = c_k - |y|^2 / 2.
+//      Each thread owns TS timesteps, W_k^T is broadcast from shared memory as float4, the x tile
+//      is staged once per block with coalesced loads.  Output: per-step max m_t and scaled
+//      likelihoods exp(ll - m_t) in (0, 1]  (fp32) -- or raw fp64 ll for Viterbi.
+//   2. scan kernel: KP lanes per trial (KP = K rounded up to a power of two, so a warp carries
+//      32/KP trials); lane k keeps column/row k of the transition matrix in registers; the
+//      matrix-vector step is KP shuffles + FMAs, the normaliser a log2(KP)-step shuffle
+//      reduction.  Messages are per-step NORMALISED probabilities in fp32 (fp32 log-space
+//      messages miss the 1e-5 posterior tolerance, scaled ones meet it); the log normaliser is
+//      accumulated in fp64.  alpha_hat is written into the Ez buffer by the forward sweep and
+//      overwritten in place with gamma by the backward sweep (same thread, same address).
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/behavenet_b200.h"
+#include "bn_common.cuh"
+
+namespace {
+
+constexpr double LN2PI = 1.8378770664093453;
+
+struct BlobHeader {
+  int K, D, lags, DP, J, KP;
+  int pad_[2];
+  // offsets in bytes from blob start
+  long long off_pi0_f, off_P_f, off_W_f, off_c_f;
+  long long off_logpi0_d, off_logP_d, off_W_d, off_c_d;
+  long long total;
+};
+
+int round_dp(int D) { return (D + 3) & ~3; }
+int round_kp(int K) { int kp = 2; while (kp < K) kp <<= 1; return kp; }
+
+BlobHeader blob_layout(int K, int D, int lags) {
+  BlobHeader h;
+  memset(&h, 0, sizeof(h));
+  h.K = K; h.D = D; h.lags = lags; h.DP = round_dp(D); h.J = D * (lags + 1) + 1; h.KP = round_kp(K);
+  long long o = 256;
+  auto take = [&](long long bytes) { long long r = o; o += (bytes + 255) & ~255LL; return r; };
+  h.off_pi0_f = take(4LL * h.KP);
+  h.off_P_f = take(4LL * h.KP * h.KP);
+  h.off_W_f = take(4LL * K * h.J * h.DP);       // [k][j][i] (i fastest, padded to DP)
+  h.off_c_f = take(4LL * (K + 1));               // c_k, then c_init
+  h.off_logpi0_d = take(8LL * h.KP);
+  h.off_logP_d = take(8LL * h.KP * h.KP);
+  h.off_W_d = take(8LL * K * h.J * h.DP);
+  h.off_c_d = take(8LL * (K + 1));
+  h.total = o;
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// emission kernel
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+struct EmitArgs {
+  const unsigned char* blob;
+  const float* x;
+  const long long* offsets;
+  int K, D, lags, J;
+  float* Bsc;      // (total_T, K) scaled likelihoods   [real == float]
+  float* mx;       // (total_T) per-step max            [real == float]
+  double* ll;      // (total_T, K) raw log-likelihoods  [real == double]
+};
+
+template <typename real, int DP, int TS>
+__global__ void __launch_bounds__(128) emission_kernel(const EmitArgs<real> a) {
+  constexpr int TILE = 128 * TS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(a.blob);
+  const int K = a.K, D = a.D, L = a.lags, J = a.J;
+  const int XS = D | 1;                         // odd row stride: conflict-free column reads
+  real* Wsm = reinterpret_cast<real*>(smem_raw);                    // K * J * DP
+  real* csm = Wsm + (size_t)K * J * DP;                             // K + 1 (+pad)
+  float* xs = reinterpret_cast<float*>(csm + ((K + 1 + 3) & ~3));   // (TILE + L) * XS
+  float* outs = xs + (size_t)(TILE + L) * XS;                       // TILE * (K + 1)   [float path]
+
+  const int trial = blockIdx.x;
+  const long long beg = a.offsets[trial], end = a.offsets[trial + 1];
+  const int T = (int)(end - beg);
+  const int t0 = blockIdx.y * TILE;
+  if (t0 >= T) return;
+  const int tid = threadIdx.x;
+  {
+    const real* Wg = reinterpret_cast<const real*>(a.blob + (sizeof(real) == 4 ? hd->off_W_f : hd->off_W_d));
+    const real* cg = reinterpret_cast<const real*>(a.blob + (sizeof(real) == 4 ? hd->off_c_f : hd->off_c_d));
+    for (int i = tid; i < K * J * DP; i += 128) Wsm[i] = Wg[i];
+    for (int i = tid; i < K + 1; i += 128) csm[i] = cg[i];
+    // x rows t0-L .. t0+TILE-1 of this trial (rows before the trial start are never used)
+    const int nrows = min(TILE, T - t0) + L;
+    const float* xg = a.x + (beg + t0 - L) * D;
+    for (int i = tid; i < nrows * D; i += 128) {
+      int r = i / D, c = i - r * D;
+      xs[r * XS + c] = (t0 - L + r >= 0) ? __ldg(xg + i) : 0.f;
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int s = 0; s < TS; ++s) {
+    const int tl = tid + 128 * s;
+    const int t = t0 + tl;
+    if (t >= T) continue;
+    const float* xr = xs + (size_t)(tl + L) * XS;    // row of x_t; x_{t-l} is l rows above
+    real llk_max = (real)-INFINITY;
+    if (t < L) {
+      // initial segment: N(0, I) for every state (ssm mu_init = 0, Sigma_init = I)
+      real q = 0;
+      for (int d = 0; d < D; ++d) q += (real)xr[d] * (real)xr[d];
+      real v = csm[K] - (real)0.5 * q;
+      if (sizeof(real) == 4) {
+        for (int k = 0; k < K; ++k) outs[tl * (K + 1) + k] = 1.f;
+        a.mx[beg + t] = (float)v;
+      } else {
+        for (int k = 0; k < K; ++k) a.ll[(beg + t) * K + k] = (double)v;
+      }
+      continue;
+    }
+    for (int k = 0; k < K; ++k) {
+      real acc[DP];
+#pragma unroll
+      for (int i = 0; i < DP; ++i) acc[i] = 0;
+      const real* Wk = Wsm + (size_t)k * J * DP;
+      // psi = [x_t, x_{t-1}, ..., x_{t-L}, 1]
+      for (int l = 0; l <= L; ++l) {
+        const float* xl = xr - (size_t)l * XS;
+        for (int d = 0; d < D; ++d) {
+          const real p = (real)xl[d];
+          const real* wj = Wk + (size_t)(l * D + d) * DP;
+#pragma unroll
+          for (int i = 0; i < DP; ++i) acc[i] = fma(p, wj[i], acc[i]);
+        }
+      }
+      {
+        const real* wj = Wk + (size_t)(J - 1) * DP;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) acc[i] += wj[i];
+      }
+      real q = 0;
+#pragma unroll
+      for (int i = 0; i < DP; ++i) q = fma(acc[i], acc[i], q);
+      real v = csm[k] - (real)0.5 * q;
+      if (sizeof(real) == 4) {
+        outs[tl * (K + 1) + k] = (float)v;
+        llk_max = v > llk_max ? v : llk_max;
+      } else {
+        a.ll[(beg + t) * K + k] = (double)v;
+      }
+    }
+    if (sizeof(real) == 4) {
+      for (int k = 0; k < K; ++k) outs[tl * (K + 1) + k] = expf(outs[tl * (K + 1) + k] - (float)llk_max);
+      a.mx[beg + t] = (float)llk_max;
+    }
+  }
+  if (sizeof(real) == 4) {
+    __syncthreads();
+    const int nrows = min(TILE, T - t0);
+    float* og = a.Bsc + (beg + t0) * K;
+    for (int i = tid; i < nrows * K; i += 128) {
+      int r = i / K, c = i - r * K;
+      og[i] = outs[r * (K + 1) + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward-backward scan
+// ------------------------------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = KP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, KP);
+  return v;
+}
+
+struct ScanArgs {
+  const unsigned char* blob;
+  const float* Bsc;
+  const float* mx;
+  const long long* offsets;
+  int n_trials, K;
+  float* Ez;      // nullable
+  float* Ezz;     // nullable
+  double* logZ;   // nullable
+};
+
+template <int KP>
+__global__ void __launch_bounds__(128) scan_kernel(const ScanArgs a) {
+  constexpr int GPW = 32 / KP;                     // trials per warp
+  const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(a.blob);
+  const float* Pg = reinterpret_cast<const float*>(a.blob + hd->off_P_f);     // KP x KP, zero padded
+  const float* pi0g = reinterpret_cast<const float*>(a.blob + hd->off_pi0_f);
+  const int lane = threadIdx.x & 31;
+  const int k = lane % KP;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int trial = warp_global * GPW + lane / KP;
+  const bool active = trial < a.n_trials;
+  const int K = a.K;
+  const bool kvalid = k < K;
+  const long long beg = active ? a.offsets[trial] : 0;
+  const int T = active ? (int)(a.offsets[trial + 1] - beg) : 0;
+  // all lanes of a warp iterate to the longest trial in the warp so shuffles stay convergent
+  int Tmax = T;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+  if (Tmax == 0) return;
+
+  float Pcol[KP], Prow[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    Pcol[j] = Pg[j * KP + k];
+    Prow[j] = Pg[k * KP + j];
+  }
+  const bool want_post = a.Ez != nullptr;
+  const float* Bp = a.Bsc + beg * K + k;
+  const float* mp = a.mx + beg;
+  float* Ep = want_post ? a.Ez + beg * K + k : nullptr;
+
+  // ---------------- forward
+  double logZ = 0.0;
+  float alpha = 0.f;
+  {
+    float b = (T > 0 && kvalid) ? __ldg(Bp) : 0.f;
+    alpha = pi0g[k] * b;
+    float c = group_sum<KP>(alpha);
+    float inv = c > 0.f ? 1.f / c : 0.f;
+    alpha *= inv;
+    if (T > 0) {
+      logZ += (double)logf(c) + (double)__ldg(mp);
+      if (want_post && kvalid) Ep[0] = alpha;
+    }
+  }
+  float bnext = (T > 1 && kvalid) ? __ldg(Bp + K) : 0.f;
+  float mnext = T > 1 ? __ldg(mp + 1) : 0.f;
+  for (int t = 1; t < Tmax; ++t) {
+    const bool on = t < T;
+    const float b = bnext;
+    const float m = mnext;
+    if (t + 1 < T) {
+      bnext = kvalid ? __ldg(Bp + (long long)(t + 1) * K) : 0.f;
+      mnext = __ldg(mp + t + 1);
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KP; j += 2) {
+      s0 = fmaf(__shfl_sync(0xffffffffu, alpha, j, KP), Pcol[j], s0);
+      s1 = fmaf(__shfl_sync(0xffffffffu, alpha, j + 1, KP), Pcol[j + 1], s1);
+    }
+    float an = (s0 + s1) * b;
+    float c = group_sum<KP>(an);
+    if (on) {
+      float inv = c > 0.f ? 1.f / c : 0.f;
+      alpha = an * inv;
+      logZ += (double)logf(c) + (double)m;
+      if (want_post && kvalid) Ep[(long long)t * K] = alpha;
+    }
+  }
+  if (active && k == 0 && a.logZ) a.logZ[trial] = logZ;
+  if (!want_post && a.Ezz == nullptr) return;
+
+  // ---------------- backward (lane j = k owns row j of P)
+  float X[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) X[j] = 0.f;
+  float beta = 1.f;       // beta_hat_{t+1}(k)
+  // gamma_{T-1} = alpha_hat_{T-1}: already in place
+  for (int t = Tmax - 2; t >= 0; --t) {
+    const bool on = t + 1 < T;       // this trial has a step t+1
+    float bn = (on && kvalid) ? __ldg(Bp + (long long)(t + 1) * K) : 0.f;
+    float w = (on && kvalid && want_post) ? Ep[(long long)t * K] : 0.f;    // alpha_hat_t(j)
+    float v = bn * beta;             // lane k: B_{t+1}(k) beta_hat_{t+1}(k)
+    float u0 = 0.f, u1 = 0.f;
+    float vk[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) vk[j] = __shfl_sync(0xffffffffu, v, j, KP);
+#pragma unroll
+    for (int j = 0; j < KP; j += 2) {
+      u0 = fmaf(Prow[j], vk[j], u0);
+      u1 = fmaf(Prow[j + 1], vk[j + 1], u1);
+    }
+    float u = u0 + u1;
+    float d = group_sum<KP>(w * u);
+    if (on) {
+      float inv = d > 0.f ? 1.f / d : 0.f;
+      float wi = w * inv;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) X[j] = fmaf(wi, vk[j], X[j]);
+      beta = u * inv;
+      if (kvalid && want_post) Ep[(long long)t * K] = w * beta;
+    }
+  }
+  if (active && kvalid && a.Ezz) {
+    float* out = a.Ezz + ((long long)trial * K + k) * K;
+    for (int j = 0; j < K; ++j) out[j] = X[j] * Prow[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Viterbi (fp64 max-sum, backward recursion like ssm.messages.viterbi)
+// ------------------------------------------------------------------------------------------------
+struct VitArgs {
+  const unsigned char* blob;
+  const double* ll;
+  const long long* offsets;
+  int n_trials, K;
+  unsigned char* args;   // (total_T, K)
+  int* z;
+};
+
+__device__ __forceinline__ double shfl_d(double v, int src, int width) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src, width);
+  hi = __shfl_sync(0xffffffffu, hi, src, width);
+  return __hiloint2double(hi, lo);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(128) viterbi_kernel(const VitArgs a) {
+  constexpr int GPW = 32 / KP;
+  const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(a.blob);
+  const double* lPg = reinterpret_cast<const double*>(a.blob + hd->off_logP_d);   // KP x KP, -inf padded
+  const double* lpi = reinterpret_cast<const double*>(a.blob + hd->off_logpi0_d);
+  const int lane = threadIdx.x & 31;
+  const int k = lane % KP;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int trial = warp_global * GPW + lane / KP;
+  const bool active = trial < a.n_trials;
+  const int K = a.K;
+  const bool kvalid = k < K;
+  const long long beg = active ? a.offsets[trial] : 0;
+  const int T = active ? (int)(a.offsets[trial + 1] - beg) : 0;
+  int Tmax = T;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+  if (Tmax == 0) return;
+  double lrow[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) lrow[j] = lPg[k * KP + j];
+  const double* llp = a.ll + beg * K + k;
+  unsigned char* ap = a.args + beg * K + k;
+  double score = 0.0;          // scores[T-1] = 0
+  for (int t = Tmax - 2; t >= 0; --t) {
+    const bool on = t + 1 < T;
+    double s = (on && kvalid) ? score + llp[(long long)(t + 1) * K] : -INFINITY;
+    double best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      double v = lrow[j] + shfl_d(s, j, KP);
+      if (v > best) { best = v; arg = j; }
+    }
+    if (on) {
+      score = best;
+      if (kvalid) ap[(long long)(t + 1) * K] = (unsigned char)arg;
+    }
+  }
+  // z_0 = argmax_j scores_0(j) + log pi0_j + ll_0(j), first index on ties
+  double s0 = (T > 0 && kvalid) ? score + lpi[k] + llp[0] : -INFINITY;
+  double best = -INFINITY;
+  int arg = 0;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    double v = shfl_d(s0, j, KP);
+    if (v > best) { best = v; arg = j; }
+  }
+  __syncwarp();
+  if (active && k == 0 && T > 0) {
+    int zt = arg;
+    a.z[beg] = zt;
+    const unsigned char* ag = a.args + beg * K;
+    for (int t = 1; t < T; ++t) {
+      zt = ag[(long long)t * K + zt];
+      a.z[beg + t] = zt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AR sufficient statistics for the M-step (fp64 accumulation)
+// ------------------------------------------------------------------------------------------------
+struct StatArgs {
+  const float* x;
+  const long long* offsets;
+  const float* Ez;
+  int n_trials, K, D, lags, Q;   // Q = D*lags + 1 + D
+  double* stats;                 // (K, Q, Q)
+  double* counts;                // (K)
+};
+
+__global__ void __launch_bounds__(256) ar_stats_kernel(const StatArgs a) {
+  // each block owns a strided subset of trials and a private (K, Q, Q) fp64 accumulator in
+  // shared memory; one atomic flush per block at the end.
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TT = 64;
+  const int K = a.K, D = a.D, L = a.lags, Q = a.Q;
+  const int PS = Q | 1;
+  double* acc = reinterpret_cast<double*>(smem_raw);              // K*Q*Q
+  double* cnt = acc + (size_t)K * Q * Q;                          // K
+  float* phi = reinterpret_cast<float*>(cnt + ((K + 1) & ~1));    // TT * PS
+  float* gam = phi + (size_t)TT * PS;                             // TT * K
+  const int tid = threadIdx.x;
+  const int items = K * Q * Q;
+  for (int i = tid; i < items + K; i += 256) acc[i] = 0.0;
+  __syncthreads();
+  for (int trial = blockIdx.x; trial < a.n_trials; trial += gridDim.x) {
+    const long long beg = a.offsets[trial];
+    const int T = (int)(a.offsets[trial + 1] - beg);
+    for (int t0 = L; t0 < T; t0 += TT) {
+      const int nt = min(TT, T - t0);
+      for (int i = tid; i < nt * Q; i += 256) {
+        int r = i / Q, q = i - r * Q;
+        int t = t0 + r;
+        float v;
+        if (q < D * L) { int l = q / D, d = q - l * D; v = __ldg(a.x + (beg + t - l - 1) * D + d); }
+        else if (q == D * L) v = 1.f;
+        else v = __ldg(a.x + (beg + t) * D + (q - D * L - 1));
+        phi[r * PS + q] = v;
+      }
+      for (int i = tid; i < nt * K; i += 256) gam[i] = __ldg(a.Ez + (beg + t0) * K + i);
+      __syncthreads();
+      for (int it = tid; it < items; it += 256) {
+        int k = it / (Q * Q);
+        int rem = it - k * Q * Q;
+        int p = rem / Q, q = rem - p * Q;
+        if (q < p) continue;                       // upper triangle only; mirrored on the host
+        float s = 0.f;
+        for (int r = 0; r < nt; ++r) s = fmaf(gam[r * K + k] * phi[r * PS + p], phi[r * PS + q], s);
+        acc[it] += (double)s;
+      }
+      if (tid < K) {
+        float s = 0.f;
+        for (int r = 0; r < nt; ++r) s += gam[r * K + tid];
+        cnt[tid] += (double)s;
+      }
+      __syncthreads();
+    }
+  }
+  for (int it = tid; it < items; it += 256) {
+    int rem = it % (Q * Q);
+    int p = rem / Q, q = rem - p * Q;
+    if (q >= p && acc[it] != 0.0) atomicAdd(a.stats + it, acc[it]);
+  }
+  if (tid < K && cnt[tid] != 0.0) atomicAdd(a.counts + tid, cnt[tid]);
+}
+
+struct WsLayoutH {
+  size_t Bsc, mx, ll, args, total;
+};
+WsLayoutH hmm_ws(int K, long long total_T, int fp64) {
+  WsLayoutH w;
+  size_t o = 0;
+  auto take = [&](size_t b) { size_t r = o; o += (b + 255) & ~(size_t)255; return r; };
+  w.Bsc = take((size_t)total_T * K * 4);
+  w.mx = take((size_t)total_T * 4);
+  w.ll = fp64 ? take((size_t)total_T * K * 8) : 0;
+  w.args = fp64 ? take((size_t)total_T * K) : 0;
+  w.total = o;
+  return w;
+}
+
+template <typename real, int DP, int TS>
+int launch_emission_t(const EmitArgs<real>& a, int n_trials, int max_T, cudaStream_t st) {
+  constexpr int TILE = 128 * TS;
+  const int XS = a.D | 1;
+  size_t smem = sizeof(real) * ((size_t)a.K * a.J * DP + ((a.K + 1 + 3) & ~3)) +
+                4 * ((size_t)(TILE + a.lags) * XS + (sizeof(real) == 4 ? (size_t)TILE * (a.K + 1) : 0));
+  if (smem > 227 * 1024) BN_FAIL("arhmm emission: K=%d D=%d lags=%d needs %zu B of shared memory", a.K, a.D, a.lags, smem);
+  auto kern = emission_kernel<real, DP, TS>;
+  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_trials, bn_cdiv(max_T, TILE));
+  kern<<<grid, 128, smem, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+template <typename real, int TS>
+int launch_emission(const EmitArgs<real>& a, int n_trials, int max_T, cudaStream_t st) {
+  switch (round_dp(a.D)) {
+    case 4: return launch_emission_t<real, 4, TS>(a, n_trials, max_T, st);
+    case 8: return launch_emission_t<real, 8, TS>(a, n_trials, max_T, st);
+    case 12: return launch_emission_t<real, 12, TS>(a, n_trials, max_T, st);
+    case 16: return launch_emission_t<real, 16, TS>(a, n_trials, max_T, st);
+    case 20: return launch_emission_t<real, 20, TS>(a, n_trials, max_T, st);
+    case 24: return launch_emission_t<real, 24, TS>(a, n_trials, max_T, st);
+    case 28: return launch_emission_t<real, 28, TS>(a, n_trials, max_T, st);
+    case 32: return launch_emission_t<real, 32, TS>(a, n_trials, max_T, st);
+    default: BN_FAIL("arhmm: observation dim D=%d > 32 unsupported", a.D);
+  }
+}
+
+int check_dims(int K, int D, int lags) {
+  if (K < 1 || K > 32) BN_FAIL("arhmm: K=%d outside [1, 32]", K);
+  if (D < 1 || D > 32) BN_FAIL("arhmm: D=%d outside [1, 32]", D);
+  if (lags < 0 || lags > 8) BN_FAIL("arhmm: lags=%d outside [0, 8]", lags);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t bn_arhmm_params_bytes(int K, int D, int lags) {
+  if (check_dims(K, D, lags)) return 0;
+  return (size_t)blob_layout(K, D, lags).total;
+}
+
+extern "C" int bn_arhmm_pack_params(int K, int D, int lags, const double* log_pi0, const double* log_Ps,
+                                    const double* As, const double* bs, const double* Sigmas,
+                                    void* h_blob) {
+  BN_TRY(check_dims(K, D, lags));
+  if (!log_pi0 || !log_Ps || !As || !bs || !Sigmas || !h_blob) BN_FAIL("bn_arhmm_pack_params: null argument");
+  BlobHeader h = blob_layout(K, D, lags);
+  unsigned char* blob = (unsigned char*)h_blob;
+  memset(blob, 0, (size_t)h.total);
+  memcpy(blob, &h, sizeof(h));
+  const int KP = h.KP, DP = h.DP, J = h.J;
+  float* pi0f = (float*)(blob + h.off_pi0_f);
+  float* Pf = (float*)(blob + h.off_P_f);
+  float* Wf = (float*)(blob + h.off_W_f);
+  float* cf = (float*)(blob + h.off_c_f);
+  double* lpid = (double*)(blob + h.off_logpi0_d);
+  double* lPd = (double*)(blob + h.off_logP_d);
+  double* Wd = (double*)(blob + h.off_W_d);
+  double* cd = (double*)(blob + h.off_c_d);
+  for (int j = 0; j < KP; ++j) {
+    lpid[j] = j < K ? log_pi0[j] : -INFINITY;
+    pi0f[j] = j < K ? (float)exp(log_pi0[j]) : 0.f;
+    for (int k = 0; k < KP; ++k) {
+      bool ok = j < K && k < K;
+      lPd[j * KP + k] = ok ? log_Ps[j * K + k] : -INFINITY;
+      Pf[j * KP + k] = ok ? (float)exp(log_Ps[j * K + k]) : 0.f;
+    }
+  }
+  std::vector<double> Lc(D * D), Li(D * D), M(D * (size_t)J);
+  for (int k = 0; k < K; ++k) {
+    const double* S = Sigmas + (size_t)k * D * D;
+    // Cholesky S = Lc Lc^T
+    std::fill(Lc.begin(), Lc.end(), 0.0);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double s = S[i * D + j];
+        for (int q = 0; q < j; ++q) s -= Lc[i * D + q] * Lc[j * D + q];
+        if (i == j) {
+          if (!(s > 0.0)) BN_FAIL("arhmm: Sigma[%d] is not positive definite", k);
+          Lc[i * D + i] = sqrt(s);
+        } else {
+          Lc[i * D + j] = s / Lc[j * D + j];
+        }
+      }
+    // Li = Lc^-1 (lower triangular)
+    std::fill(Li.begin(), Li.end(), 0.0);
+    for (int c = 0; c < D; ++c)
+      for (int i = c; i < D; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+        for (int q = c; q < i; ++q) s -= Lc[i * D + q] * Li[q * D + c];
+        Li[i * D + c] = s / Lc[i * D + i];
+      }
+    // M = [I, -A_k, -b_k] (D x J);  W = Li M
+    const double* A = As + (size_t)k * D * D * lags;
+    const double* b = bs + (size_t)k * D;
+    std::fill(M.begin(), M.end(), 0.0);
+    for (int i = 0; i < D; ++i) {
+      M[(size_t)i * J + i] = 1.0;
+      for (int c = 0; c < D * lags; ++c) M[(size_t)i * J + D + c] = -A[(size_t)i * D * lags + c];
+      M[(size_t)i * J + J - 1] = -b[i];
+    }
+    double logdet = 0.0;
+    for (int i = 0; i < D; ++i) logdet += log(Lc[i * D + i]);
+    cd[k] = -0.5 * D * LN2PI - logdet;
+    cf[k] = (float)cd[k];
+    for (int j = 0; j < J; ++j)
+      for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+        for (int q = 0; q <= i; ++q) s += Li[i * D + q] * M[(size_t)q * J + j];
+        Wd[((size_t)k * J + j) * DP + i] = s;
+        Wf[((size_t)k * J + j) * DP + i] = (float)s;
+      }
+  }
+  cd[K] = -0.5 * D * LN2PI;
+  cf[K] = (float)cd[K];
+  return 0;
+}
+
+extern "C" size_t bn_arhmm_workspace_bytes(int K, int D, int lags, int64_t total_T, int n_trials, int fp64) {
+  (void)D; (void)lags; (void)n_trials;
+  return hmm_ws(K, total_T, fp64).total;
+}
+
+template <int KP>
+static int launch_scan(const ScanArgs& a, cudaStream_t st) {
+  constexpr int GPW = 32 / KP;
+  int warps = bn_cdiv(a.n_trials, GPW);
+  scan_kernel<KP><<<bn_cdiv(warps, 4), 128, 0, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+template <int KP>
+static int launch_vit(const VitArgs& a, cudaStream_t st) {
+  constexpr int GPW = 32 / KP;
+  int warps = bn_cdiv(a.n_trials, GPW);
+  viterbi_kernel<KP><<<bn_cdiv(warps, 4), 128, 0, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+extern "C" int bn_arhmm_estep(int K, int D, int lags, const void* d_blob, const float* d_x,
+                              const int64_t* d_offsets, int n_trials, int64_t total_T, int max_T,
+                              void* d_ws, float* d_Ez, float* d_Ezz, double* d_logZ, void* stream) {
+  BN_TRY(check_dims(K, D, lags));
+  if (!d_blob || !d_x || !d_offsets || !d_ws) BN_FAIL("bn_arhmm_estep: null argument");
+  if (d_Ezz && !d_Ez) BN_FAIL("bn_arhmm_estep: d_Ezz requires d_Ez (alpha_hat is staged there)");
+  if (n_trials <= 0 || total_T <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  WsLayoutH w = hmm_ws(K, total_T, 0);
+  unsigned char* ws = (unsigned char*)d_ws;
+  EmitArgs<float> e;
+  e.blob = (const unsigned char*)d_blob; e.x = d_x; e.offsets = (const long long*)d_offsets;
+  e.K = K; e.D = D; e.lags = lags; e.J = D * (lags + 1) + 1;
+  e.Bsc = (float*)(ws + w.Bsc); e.mx = (float*)(ws + w.mx); e.ll = nullptr;
+  BN_TRY((launch_emission<float, 2>(e, n_trials, max_T, st)));
+  ScanArgs s;
+  s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
+  s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ;
+  switch (round_kp(K)) {
+    case 2: return launch_scan<2>(s, st);
+    case 4: return launch_scan<4>(s, st);
+    case 8: return launch_scan<8>(s, st);
+    case 16: return launch_scan<16>(s, st);
+    default: return launch_scan<32>(s, st);
+  }
+}
+
+extern "C" int bn_arhmm_viterbi(int K, int D, int lags, const void* d_blob, const float* d_x,
+                                const int64_t* d_offsets, int n_trials, int64_t total_T, int max_T,
+                                void* d_ws, int32_t* d_z, void* stream) {
+  BN_TRY(check_dims(K, D, lags));
+  if (!d_blob || !d_x || !d_offsets || !d_ws || !d_z) BN_FAIL("bn_arhmm_viterbi: null argument");
+  if (n_trials <= 0 || total_T <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  WsLayoutH w = hmm_ws(K, total_T, 1);
+  unsigned char* ws = (unsigned char*)d_ws;
+  EmitArgs<double> e;
+  e.blob = (const unsigned char*)d_blob; e.x = d_x; e.offsets = (const long long*)d_offsets;
+  e.K = K; e.D = D; e.lags = lags; e.J = D * (lags + 1) + 1;
+  e.Bsc = nullptr; e.mx = nullptr; e.ll = (double*)(ws + w.ll);
+  BN_TRY((launch_emission<double, 1>(e, n_trials, max_T, st)));
+  VitArgs v;
+  v.blob = e.blob; v.ll = e.ll; v.offsets = e.offsets; v.n_trials = n_trials; v.K = K;
+  v.args = ws + w.args; v.z = d_z;
+  switch (round_kp(K)) {
+    case 2: return launch_vit<2>(v, st);
+    case 4: return launch_vit<4>(v, st);
+    case 8: return launch_vit<8>(v, st);
+    case 16: return launch_vit<16>(v, st);
+    default: return launch_vit<32>(v, st);
+  }
+}
+
+extern "C" int bn_arhmm_ar_stats(int K, int D, int lags, const float* d_x, const int64_t* d_offsets,
+                                 int n_trials, int64_t total_T, const float* d_Ez, double* d_stats,
+                                 double* d_counts, void* stream) {
+  BN_TRY(check_dims(K, D, lags));
+  if (!d_x || !d_offsets || !d_Ez || !d_stats || !d_counts) BN_FAIL("bn_arhmm_ar_stats: null argument");
+  if (n_trials <= 0 || total_T <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  StatArgs a;
+  a.x = d_x; a.offsets = (const long long*)d_offsets; a.Ez = d_Ez; a.n_trials = n_trials;
+  a.K = K; a.D = D; a.lags = lags; a.Q = D * lags + 1 + D; a.stats = d_stats; a.counts = d_counts;
+  const int PS = a.Q | 1;
+  size_t smem = 8 * ((size_t)K * a.Q * a.Q + ((K + 1) & ~1)) + 4 * ((size_t)64 * PS + (size_t)64 * K);
+  if (smem > 227 * 1024) BN_FAIL("arhmm ar_stats: K=%d D=%d lags=%d needs %zu B of shared memory", K, D, lags, smem);
+  BN_CUDA(cudaFuncSetAttribute(ar_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = n_trials < 296 ? n_trials : 296;
+  ar_stats_kernel<<<grid, 256, smem, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}

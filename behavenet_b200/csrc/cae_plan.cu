@@ -1,0 +1,362 @@
+// Plan object + C ABI for hot path 1 (convolutional autoencoder).  See include/behavenet_b200.h.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/behavenet_b200.h"
+#include "cae_kernels.cuh"
+
+thread_local char g_bn_err[512] = "";
+std::atomic<long long> g_bn_launches{0};
+static std::atomic<int> g_tc_mode{1};
+
+extern "C" int bn_abi_version(void) { return BN_ABI_VERSION; }
+extern "C" const char* bn_last_error(void) { return g_bn_err; }
+extern "C" int64_t bn_launch_count(void) { return (int64_t)g_bn_launches.load(); }
+extern "C" int bn_set_tensor_core_mode(int mode) {
+  g_tc_mode.store(mode ? 1 : 0);
+  return 0;
+}
+extern "C" int bn_get_tensor_core_mode(void) { return g_tc_mode.load(); }
+
+struct bn_cae_plan {
+  bn_cae_desc d;
+  int nl;
+  ConvGeom enc[BN_MAX_LAYERS], dec[BN_MAX_LAYERS];
+  std::vector<TapClass> h_tables;
+  std::vector<int> enc_f, enc_d, dec_f, dec_d;   // table start indices
+  TapClass* d_tables;
+  size_t packed_floats, off_heads;
+  size_t enc_sz[BN_MAX_LAYERS + 1];   // per-frame floats: [0] input, [i+1] output of enc layer i
+  size_t dec_sz[BN_MAX_LAYERS + 1];   // [0] h0, [i+1] output of dec layer i
+  size_t max_act;
+  int feat_c, feat_h, feat_w;
+};
+
+namespace {
+
+size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
+
+struct WsLayout {
+  size_t enc_act[BN_MAX_LAYERS + 1];
+  size_t dec_act[BN_MAX_LAYERS + 1];
+  size_t dpre_last, zcopy, gA, gB, partial, partial_floats, total;
+};
+
+WsLayout ws_layout(const bn_cae_plan* p, int n) {
+  WsLayout w;
+  size_t o = 0;
+  w.enc_act[0] = 0;
+  for (int i = 1; i <= p->nl; ++i) { w.enc_act[i] = o; o += align64((size_t)n * p->enc_sz[i]); }
+  for (int i = 0; i <= p->nl; ++i) { w.dec_act[i] = o; o += align64((size_t)n * p->dec_sz[i]); }
+  w.dpre_last = o; o += align64((size_t)n * p->dec_sz[p->nl]);
+  w.zcopy = o; o += align64((size_t)n * p->d.n_latents);
+  w.gA = o; o += align64((size_t)n * p->max_act);
+  w.gB = o; o += align64((size_t)n * p->max_act);
+  size_t pf = 0;
+  for (int i = 0; i < p->nl; ++i) {
+    pf = std::max(pf, bn_wgrad_partial_floats(p->enc[i], n));
+    pf = std::max(pf, bn_wgrad_partial_floats(p->dec[i], n));
+  }
+  w.partial = o; w.partial_floats = pf; o += align64(pf);
+  w.total = o;
+  return w;
+}
+
+void build_classes(ConvGeom& g, std::vector<TapClass>& tab, int& i_f, int& i_d) {
+  // fprop-form class: every small-image pixel gathers k*k taps from the big image
+  TapClass c;
+  memset(&c, 0, sizeof(c));
+  c.Hm = g.Hs; c.Wm = g.Ws; c.oy0 = 0; c.ox0 = 0; c.ntaps = g.k * g.k;
+  for (int ky = 0; ky < g.k; ++ky)
+    for (int kx = 0; kx < g.k; ++kx) {
+      int t = ky * g.k + kx;
+      c.dy[t] = (signed char)(ky - g.pt);
+      c.dx[t] = (signed char)(kx - g.pl);
+      c.wt[t] = (unsigned char)t;
+    }
+  i_f = (int)tab.size();
+  tab.push_back(c);
+  // dgrad-form classes: big-image pixels with the same residue mod stride share a tap list;
+  // big[y] receives small[(y + pt - ky) / s] * W[ky] whenever the division is exact
+  i_d = (int)tab.size();
+  g.n_dgrad = 0; g.dgrad_maxM = 0; g.dgrad_maxtaps = 0;
+  for (int y0 = 0; y0 < g.s; ++y0)
+    for (int x0 = 0; x0 < g.s; ++x0) {
+      if (y0 >= g.Hb || x0 >= g.Wb) continue;
+      TapClass d;
+      memset(&d, 0, sizeof(d));
+      d.Hm = (g.Hb - y0 + g.s - 1) / g.s;
+      d.Wm = (g.Wb - x0 + g.s - 1) / g.s;
+      d.oy0 = y0; d.ox0 = x0;
+      int nt = 0;
+      for (int ky = (y0 + g.pt) % g.s; ky < g.k; ky += g.s)
+        for (int kx = (x0 + g.pl) % g.s; kx < g.k; kx += g.s) {
+          d.dy[nt] = (signed char)((y0 + g.pt - ky) / g.s);
+          d.dx[nt] = (signed char)((x0 + g.pl - kx) / g.s);
+          d.wt[nt] = (unsigned char)(ky * g.k + kx);
+          ++nt;
+        }
+      d.ntaps = nt;
+      tab.push_back(d);
+      g.n_dgrad++;
+      g.dgrad_maxM = std::max(g.dgrad_maxM, d.Hm * d.Wm);
+      g.dgrad_maxtaps = std::max(g.dgrad_maxtaps, nt);
+    }
+}
+
+int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const float* bias, float* out,
+              int Ho, int Wo, int Co, const float* dact, int table_idx, int nclasses, int maxM, int gs,
+              int os, int n, int act, cudaStream_t st) {
+  const TapClass* dcls = p->d_tables + table_idx;
+  if (g_tc_mode.load()) {
+    int r = bn_launch_igemm_tc(in, w, bias, out, Ho, Wo, Co, dact, dcls, p->h_tables.data() + table_idx,
+                               nclasses, maxM, gs, os, n, act, st);
+    if (r <= 0) return r;
+  }
+  return bn_launch_igemm(in, w, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n, act, st);
+}
+
+int run_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
+              size_t partial_floats, float* grad, cudaStream_t st) {
+  if (!grad) return 0;
+  if (g_tc_mode.load()) {
+    int r = bn_launch_wgrad_tc(big, small, g, n, partial, partial_floats, grad, st);
+    if (r <= 0) return r;
+  }
+  return bn_launch_wgrad(big, small, g, n, partial, partial_floats, grad, st);
+}
+
+ImgView input_view(const bn_cae_plan* p, const float* x) {
+  // frames arrive NCHW (data_generator.py:258-263); with one channel that is already NHWC
+  if (p->d.in_c == 1) return nhwc_view(x, p->d.in_h, p->d.in_w, 1);
+  return nchw_view(x, p->d.in_h, p->d.in_w, p->d.in_c);
+}
+
+}  // namespace
+
+extern "C" int bn_cae_plan_create(const bn_cae_desc* desc, bn_cae_plan** out) {
+  if (!desc || !out) BN_FAIL("bn_cae_plan_create: null argument");
+  const bn_cae_desc& d = *desc;
+  if (d.n_layers < 1 || d.n_layers > BN_MAX_LAYERS) BN_FAIL("n_layers=%d out of range", d.n_layers);
+  if (d.n_heads < 1 || d.n_heads > 2) BN_FAIL("n_heads=%d", d.n_heads);
+  if (d.n_latents < 1) BN_FAIL("n_latents=%d", d.n_latents);
+  bn_cae_plan* p = new bn_cae_plan();
+  p->d = d;
+  p->nl = d.n_layers;
+  p->d_tables = nullptr;
+  int H = d.in_h, W = d.in_w, C = d.in_c;
+  p->enc_sz[0] = (size_t)H * W * C;
+  size_t off = 0;
+  for (int i = 0; i < p->nl; ++i) {
+    ConvGeom& g = p->enc[i];
+    g.Hb = H; g.Wb = W; g.Cb = C;
+    g.Hs = d.enc_h[i]; g.Ws = d.enc_w[i]; g.Cs = d.enc_c[i];
+    g.k = d.enc_k[i]; g.s = d.enc_s[i]; g.pt = d.enc_pt[i]; g.pl = d.enc_pl[i];
+    if (g.k * g.k > BN_MAX_TAPS || g.k < 1 || g.s < 1) { delete p; BN_FAIL("enc layer %d: kernel %d / stride %d unsupported", i, g.k, g.s); }
+    int eh = (H + d.enc_pt[i] + d.enc_pb[i] - g.k) / g.s + 1;
+    int ew = (W + d.enc_pl[i] + d.enc_pr[i] - g.k) / g.s + 1;
+    if (eh != g.Hs || ew != g.Ws) { delete p; BN_FAIL("enc layer %d: dims (%d,%d) inconsistent with padding (expect %d,%d)", i, g.Hs, g.Ws, eh, ew); }
+    g.p_w = 2 * i; g.p_b = 2 * i + 1;
+    g.off_wf = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    g.off_wd = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    H = g.Hs; W = g.Ws; C = g.Cs;
+    p->enc_sz[i + 1] = (size_t)H * W * C;
+  }
+  p->feat_c = C; p->feat_h = H; p->feat_w = W;
+  p->off_heads = off; off += align64((size_t)d.n_heads * d.n_latents * C * H * W);
+  H = d.dec_h0; W = d.dec_w0; C = d.dec_c0;
+  p->dec_sz[0] = (size_t)H * W * C;
+  for (int i = 0; i < p->nl; ++i) {
+    ConvGeom& g = p->dec[i];
+    g.Hs = H; g.Ws = W; g.Cs = C;
+    g.Hb = d.dec_h[i]; g.Wb = d.dec_w[i]; g.Cb = d.dec_c[i];
+    g.k = d.dec_k[i]; g.s = d.dec_s[i]; g.pt = d.dec_pt[i]; g.pl = d.dec_pl[i];
+    if (g.k * g.k > BN_MAX_TAPS || g.k < 1 || g.s < 1) { delete p; BN_FAIL("dec layer %d: kernel %d / stride %d unsupported", i, g.k, g.s); }
+    int eh = (H - 1) * g.s + g.k - d.dec_pt[i] - d.dec_pb[i];
+    int ew = (W - 1) * g.s + g.k - d.dec_pl[i] - d.dec_pr[i];
+    if (eh != g.Hb || ew != g.Wb) { delete p; BN_FAIL("dec layer %d: dims (%d,%d) inconsistent with crop (expect %d,%d)", i, g.Hb, g.Wb, eh, ew); }
+    g.p_w = 2 * p->nl + 6 + 2 * i; g.p_b = g.p_w + 1;
+    g.off_wf = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    g.off_wd = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    H = g.Hb; W = g.Wb; C = g.Cb;
+    p->dec_sz[i + 1] = (size_t)H * W * C;
+  }
+  if (H != d.in_h || W != d.in_w || C != d.in_c) { delete p; BN_FAIL("decoder output (%d,%d,%d) != input (%d,%d,%d)", C, H, W, d.in_c, d.in_h, d.in_w); }
+  if (C > 4) { delete p; BN_FAIL("n_input_channels=%d > 4 has no fused output-layer kernel", C); }
+  p->packed_floats = off;
+  p->max_act = 0;
+  for (int i = 0; i <= p->nl; ++i) p->max_act = std::max(p->max_act, std::max(p->enc_sz[i], p->dec_sz[i]));
+  p->enc_f.resize(p->nl); p->enc_d.resize(p->nl); p->dec_f.resize(p->nl); p->dec_d.resize(p->nl);
+  for (int i = 0; i < p->nl; ++i) build_classes(p->enc[i], p->h_tables, p->enc_f[i], p->enc_d[i]);
+  for (int i = 0; i < p->nl; ++i) build_classes(p->dec[i], p->h_tables, p->dec_f[i], p->dec_d[i]);
+  cudaError_t e = cudaMalloc(&p->d_tables, p->h_tables.size() * sizeof(TapClass));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(p->d_tables, p->h_tables.data(), p->h_tables.size() * sizeof(TapClass), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->d_tables) cudaFree(p->d_tables);
+    delete p;
+    BN_FAIL("plan tables: %s", cudaGetErrorString(e));
+  }
+  for (int i = 0; i < p->nl; ++i) {
+    p->enc[i].d_fprop = p->d_tables + p->enc_f[i]; p->enc[i].d_dgrad = p->d_tables + p->enc_d[i];
+    p->dec[i].d_fprop = p->d_tables + p->dec_f[i]; p->dec[i].d_dgrad = p->d_tables + p->dec_d[i];
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" void bn_cae_plan_destroy(bn_cae_plan* p) {
+  if (!p) return;
+  if (p->d_tables) cudaFree(p->d_tables);
+  delete p;
+}
+
+extern "C" size_t bn_cae_packed_bytes(const bn_cae_plan* p) { return p ? p->packed_floats * sizeof(float) : 0; }
+
+extern "C" size_t bn_cae_workspace_bytes(const bn_cae_plan* p, int n) {
+  if (!p || n <= 0) return 0;
+  return ws_layout(p, n).total * sizeof(float);
+}
+
+extern "C" int bn_cae_pack_params(bn_cae_plan* p, const float* const* P, void* d_packed, void* stream) {
+  if (!p || !P || !d_packed) BN_FAIL("bn_cae_pack_params: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* pk = (float*)d_packed;
+  for (int i = 0; i < p->nl; ++i) {
+    const ConvGeom& g = p->enc[i];
+    if (P[g.p_w])
+      BN_TRY(bn_launch_pack_conv(P[g.p_w], g.Cs, g.Cb, g.k * g.k, pk + g.off_wf, pk + g.off_wd, st));
+    const ConvGeom& h = p->dec[i];
+    if (P[h.p_w])
+      BN_TRY(bn_launch_pack_conv(P[h.p_w], h.Cs, h.Cb, h.k * h.k, pk + h.off_wf, pk + h.off_wd, st));
+  }
+  const int n2 = 2 * p->nl;
+  if (P[n2]) {
+    if (p->d.n_heads == 2 && !P[n2 + 2]) BN_FAIL("bn_cae_pack_params: logvar head weight missing");
+    BN_TRY(bn_launch_pack_heads(P[n2], p->d.n_heads == 2 ? P[n2 + 2] : nullptr, p->d.n_latents, p->feat_c,
+                                p->feat_h, p->feat_w, pk + p->off_heads, st));
+  }
+  return 0;
+}
+
+extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const float* const* P,
+                             const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream) {
+  if (!p || !d_x || !P || !d_packed || !d_ws || !d_mu) BN_FAIL("bn_cae_encode: null argument");
+  if (p->d.n_heads == 2 && !d_logvar) BN_FAIL("bn_cae_encode: logvar output required for a variational encoder");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* pk = (const float*)d_packed;
+  float* ws = (float*)d_ws;
+  WsLayout L = ws_layout(p, n);
+  ImgView in = input_view(p, d_x);
+  for (int i = 0; i < p->nl; ++i) {
+    const ConvGeom& g = p->enc[i];
+    float* out = ws + L.enc_act[i + 1];
+    BN_TRY(run_igemm(p, in, pk + g.off_wf, P[g.p_b], out, g.Hs, g.Ws, g.Cs, nullptr, p->enc_f[i], 1,
+                     g.Hs * g.Ws, g.s, 1, n, BN_ACT_LEAKY, st));
+    in = nhwc_view(out, g.Hs, g.Ws, g.Cs);
+  }
+  const int n2 = 2 * p->nl;
+  BN_TRY(bn_launch_heads_fwd(ws + L.enc_act[p->nl], pk + p->off_heads, P[n2 + 1],
+                             p->d.n_heads == 2 ? P[n2 + 3] : nullptr, n, p->d.n_latents, p->d.n_heads,
+                             p->feat_c * p->feat_h * p->feat_w, d_mu, d_logvar, st));
+  return 0;
+}
+
+extern "C" int bn_cae_decode(bn_cae_plan* p, int n, const float* d_z, const float* const* P,
+                             const void* d_packed, void* d_ws, float* d_xhat, const float* d_target,
+                             const float* d_mask, int chunk_size, int frame_offset, int n_total,
+                             float grad_coef, double* d_sse, void* stream) {
+  if (!p || !d_z || !P || !d_packed || !d_ws) BN_FAIL("bn_cae_decode: null argument");
+  if (d_target && !d_sse) BN_FAIL("bn_cae_decode: d_sse required with d_target");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* pk = (const float*)d_packed;
+  float* ws = (float*)d_ws;
+  WsLayout L = ws_layout(p, n);
+  const int n2 = 2 * p->nl;
+  BN_CUDA(cudaMemcpyAsync(ws + L.zcopy, d_z, (size_t)n * p->d.n_latents * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  BN_TRY(bn_launch_decff_fwd(d_z, P[n2 + 4], P[n2 + 5], n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
+                             p->d.dec_w0, ws + L.dec_act[0], st));
+  for (int i = 0; i + 1 < p->nl; ++i) {
+    const ConvGeom& g = p->dec[i];
+    ImgView in = nhwc_view(ws + L.dec_act[i], g.Hs, g.Ws, g.Cs);
+    BN_TRY(run_igemm(p, in, pk + g.off_wd, P[g.p_b], ws + L.dec_act[i + 1], g.Hb, g.Wb, g.Cb, nullptr,
+                     p->dec_d[i], g.n_dgrad, g.dgrad_maxM, 1, g.s, n, BN_ACT_LEAKY, st));
+  }
+  const ConvGeom& g = p->dec[p->nl - 1];
+  BN_TRY(bn_launch_thin_dgrad(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
+                              d_xhat, d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
+                              ws + L.dpre_last, st));
+  return 0;
+}
+
+extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, const float* const* P,
+                                 const void* d_packed, void* d_ws, float* const* G, float* d_dz,
+                                 void* stream) {
+  if (!p || !P || !d_packed || !d_ws || !G) BN_FAIL("bn_cae_decode_bwd: null argument");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* pk = (const float*)d_packed;
+  float* ws = (float*)d_ws;
+  WsLayout L = ws_layout(p, n);
+  const int n2 = 2 * p->nl;
+  const ConvGeom& gl = p->dec[p->nl - 1];
+  if (d_dxhat)
+    BN_TRY(bn_launch_sigmoid_bwd(d_dxhat, ws + L.dec_act[p->nl], ws + L.dpre_last, n, gl.Cb, gl.Hb, gl.Wb, st));
+  float* gcur = ws + L.dpre_last;
+  float* pp[2] = {ws + L.gA, ws + L.gB};
+  int flip = 0;
+  for (int i = p->nl - 1; i >= 0; --i) {
+    const ConvGeom& g = p->dec[i];
+    ImgView big = nhwc_view(gcur, g.Hb, g.Wb, g.Cb);
+    const float* small = ws + L.dec_act[i];
+    BN_TRY(run_wgrad(big, small, g, n, ws + L.partial, L.partial_floats, G[g.p_w], st));
+    BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
+    float* out = pp[flip];
+    flip ^= 1;
+    BN_TRY(run_igemm(p, big, pk + g.off_wf, nullptr, out, g.Hs, g.Ws, g.Cs, i > 0 ? small : nullptr,
+                     p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st));
+    gcur = out;
+  }
+  BN_TRY(bn_launch_decff_bwd(ws + L.zcopy, P[n2 + 4], gcur, n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
+                             p->d.dec_w0, d_dz, G[n2 + 4], G[n2 + 5], st));
+  return 0;
+}
+
+extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const float* d_dmu,
+                                 const float* d_dlogvar, const float* const* P, const void* d_packed,
+                                 void* d_ws, float* const* G, void* stream) {
+  if (!p || !d_x || !P || !d_packed || !d_ws || !G) BN_FAIL("bn_cae_encode_bwd: null argument");
+  if (!d_dmu && !d_dlogvar) BN_FAIL("bn_cae_encode_bwd: no upstream gradient");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* pk = (const float*)d_packed;
+  float* ws = (float*)d_ws;
+  WsLayout L = ws_layout(p, n);
+  const int n2 = 2 * p->nl;
+  float* pp[2] = {ws + L.gA, ws + L.gB};
+  int flip = 0;
+  float* gcur = pp[flip];
+  flip ^= 1;
+  BN_TRY(bn_launch_heads_bwd(ws + L.enc_act[p->nl], pk + p->off_heads, d_dmu, d_dlogvar, n, p->d.n_latents,
+                             p->feat_c, p->feat_h, p->feat_w, gcur, G[n2], G[n2 + 1],
+                             p->d.n_heads == 2 ? G[n2 + 2] : nullptr, p->d.n_heads == 2 ? G[n2 + 3] : nullptr, st));
+  for (int i = p->nl - 1; i >= 0; --i) {
+    const ConvGeom& g = p->enc[i];
+    ImgView big = i == 0 ? input_view(p, d_x) : nhwc_view(ws + L.enc_act[i], g.Hb, g.Wb, g.Cb);
+    BN_TRY(run_wgrad(big, gcur, g, n, ws + L.partial, L.partial_floats, G[g.p_w], st));
+    BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hs * g.Ws, g.Cs, G[g.p_b], st));
+    if (i > 0) {
+      float* out = pp[flip];
+      flip ^= 1;
+      ImgView in = nhwc_view(gcur, g.Hs, g.Ws, g.Cs);
+      BN_TRY(run_igemm(p, in, pk + g.off_wd, nullptr, out, g.Hb, g.Wb, g.Cb, ws + L.enc_act[i], p->enc_d[i],
+                       g.n_dgrad, g.dgrad_maxM, 1, g.s, n, BN_ACT_NONE, st));
+      gcur = out;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,254 @@
+// PS-VAE latent block: subspace projections, reparameterisation, label / KL / decomposed-KL
+// loss terms and their gradients, for one reference chunk (<= 200 frames in every caller).
+//
+// Reference: models/vaes.py:571-601 (forward), 669-696 (loss terms), 17-35 (reparameterize);
+// fitting/losses.py:62-96 (gaussian_ll), 130-147 (kl_div_to_std_normal), 284-372 (decomposed_kl).
+//
+// The tensors are tiny (n x 16); the kernels favour determinism and simplicity over speed: every
+// output element is produced by exactly one thread, in a fixed summation order.
+#include <math.h>
+
+#include "../../include/behavenet_b200.h"
+#include "bn_common.cuh"
+
+namespace {
+
+constexpr float LN2PI_F = 1.8378770664093453f;
+
+struct LatArgs {
+  int n, L, nl;
+  const float *pre, *logvar, *A, *B, *Dw, *Db, *eps, *labels, *lmask;
+  float alpha, beta, klw;
+  float *mu, *z, *yhat;
+  double* terms;
+  float *gmu, *glv, *gz, *gDw, *gDb;
+  float* log_qz;   // (n)
+  float* lse;      // (n, du)
+};
+
+// K0: projections + reparameterisation + supervised terms.  One thread per (frame, latent dim).
+__global__ void latent_fwd_kernel(const LatArgs a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n * a.L) return;
+  int f = i / a.L, d = i - f * a.L;
+  const float* row = d < a.nl ? a.A + (size_t)d * a.L : a.B + (size_t)(d - a.nl) * a.L;
+  const float* p = a.pre + (size_t)f * a.L;
+  float m = 0.f;
+  for (int c = 0; c < a.L; ++c) m = fmaf(__ldg(row + c), __ldg(p + c), m);
+  float lv = a.logvar[i];
+  float z = a.eps ? fmaf(a.eps[i], expf(lv), m) : m;
+  a.mu[i] = m;
+  a.z[i] = z;
+  if (d < a.nl) {
+    float yh = fmaf(m, a.Dw[d], a.Db[d]);
+    a.yhat[(size_t)f * a.nl + d] = yh;
+    float gy = 0.f;
+    if (a.labels) {
+      float diff = yh - a.labels[(size_t)f * a.nl + d];
+      float mk = a.lmask ? a.lmask[(size_t)f * a.nl + d] : 1.f;
+      atomicAdd(a.terms + 0, (double)(diff * diff * mk));
+      gy = a.alpha * diff * mk / (float)a.n;           // d(-alpha * label_ll)/d yhat
+      if (a.gDw) atomicAdd(a.gDw + d, gy * m);
+      if (a.gDb) atomicAdd(a.gDb + d, gy);
+    }
+    // supervised-latent KL to N(0,1): 0.5 * (exp(lv) - lv + mu^2 - 1)
+    atomicAdd(a.terms + 1, (double)(0.5f * (expf(lv) - lv + m * m - 1.f)));
+    if (a.gmu) {
+      a.gmu[i] = gy * a.Dw[d] + m / (float)a.n;
+      a.glv[i] = 0.5f * (expf(lv) - 1.f) / (float)a.n;
+      a.gz[i] = 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ float lq_elem(float z, float mu, float lv) {
+  float d = z - mu;
+  return -0.5f * (expf(-lv) * d * d + lv + LN2PI_F);
+}
+
+// K1: one block per sample j: log q(z_j) and per-dimension log-sum-exps over the chunk.
+__global__ void __launch_bounds__(128) dkl_rows_kernel(const LatArgs a) {
+  __shared__ float red[128];
+  __shared__ float zj[64];
+  const int j = blockIdx.x, tid = threadIdx.x;
+  const int du = a.L - a.nl;
+  if (tid < du) zj[tid] = a.z[(size_t)j * a.L + a.nl + tid];
+  __syncthreads();
+  auto block_max = [&](float v) {
+    red[tid] = v;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) { if (tid < o) red[tid] = fmaxf(red[tid], red[tid + o]); __syncthreads(); }
+    float r = red[0];
+    __syncthreads();
+    return r;
+  };
+  auto block_sum = [&](float v) {
+    red[tid] = v;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    float r = red[0];
+    __syncthreads();
+    return r;
+  };
+  // joint over dims
+  float mx = -INFINITY;
+  for (int i = tid; i < a.n; i += 128) {
+    float s = 0.f;
+    for (int l = 0; l < du; ++l)
+      s += lq_elem(zj[l], a.mu[(size_t)i * a.L + a.nl + l], a.logvar[(size_t)i * a.L + a.nl + l]);
+    mx = fmaxf(mx, s);
+  }
+  mx = block_max(mx);
+  float se = 0.f, diag = 0.f;
+  for (int i = tid; i < a.n; i += 128) {
+    float s = 0.f;
+    for (int l = 0; l < du; ++l)
+      s += lq_elem(zj[l], a.mu[(size_t)i * a.L + a.nl + l], a.logvar[(size_t)i * a.L + a.nl + l]);
+    se += expf(s - mx);
+    if (i == j) diag = s;
+  }
+  se = block_sum(se);
+  diag = block_sum(diag);
+  const float log_qz = mx + logf(se);
+  float prod = 0.f;
+  for (int l = 0; l < du; ++l) {
+    float m2 = -INFINITY;
+    for (int i = tid; i < a.n; i += 128)
+      m2 = fmaxf(m2, lq_elem(zj[l], a.mu[(size_t)i * a.L + a.nl + l], a.logvar[(size_t)i * a.L + a.nl + l]));
+    m2 = block_max(m2);
+    float s2 = 0.f;
+    for (int i = tid; i < a.n; i += 128)
+      s2 += expf(lq_elem(zj[l], a.mu[(size_t)i * a.L + a.nl + l], a.logvar[(size_t)i * a.L + a.nl + l]) - m2);
+    s2 = block_sum(s2);
+    float v = m2 + logf(s2);
+    if (tid == 0) a.lse[(size_t)j * du + l] = v;
+    prod += v;
+  }
+  if (tid == 0) {
+    a.log_qz[j] = log_qz;
+    float lpz = 0.f;
+    for (int l = 0; l < du; ++l) lpz += -0.5f * (zj[l] * zj[l] + LN2PI_F);
+    atomicAdd(a.terms + 2, (double)(diag - log_qz));
+    atomicAdd(a.terms + 3, (double)(log_qz - prod));
+    atomicAdd(a.terms + 4, (double)(prod - lpz));
+  }
+}
+
+// K2: gradients.  role 0: thread per (j, l) -> gz ; role 1: thread per (i, l) -> gmu, glv.
+// Coefficient on lq[j,i,l]:  G = (a * [i == j] + c * p_ji - c * q_jil) / n,
+//   a = kl_w, c = beta - kl_w, p_ji = softmax_i(joint[j, :]), q_jil = softmax_i(lq[j, :, l]).
+__global__ void dkl_grad_kernel(const LatArgs a) {
+  const int du = a.L - a.nl;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n * du) return;
+  const int role = blockIdx.y;
+  const int me = idx / du, l = idx - me * du;
+  const float ca = a.klw, cc = a.beta - a.klw, invn = 1.f / (float)a.n;
+  float g0 = 0.f, g1 = 0.f;
+  for (int other = 0; other < a.n; ++other) {
+    const int j = role == 0 ? me : other;
+    const int i = role == 0 ? other : me;
+    const float* zr = a.z + (size_t)j * a.L + a.nl;
+    const float* mr = a.mu + (size_t)i * a.L + a.nl;
+    const float* lr = a.logvar + (size_t)i * a.L + a.nl;
+    float joint = 0.f;
+    for (int q = 0; q < du; ++q) joint += lq_elem(zr[q], mr[q], lr[q]);
+    float p = expf(joint - a.log_qz[j]);
+    float lql = lq_elem(zr[l], mr[l], lr[l]);
+    float qq = expf(lql - a.lse[(size_t)j * du + l]);
+    float G = ((i == j ? ca : 0.f) + cc * p - cc * qq) * invn;
+    float w = expf(-lr[l]);
+    float dlt = zr[l] - mr[l];
+    if (role == 0) {
+      g0 = fmaf(G, -w * dlt, g0);
+    } else {
+      g0 = fmaf(G, w * dlt, g0);
+      g1 = fmaf(G, 0.5f * (w * dlt * dlt - 1.f), g1);
+    }
+  }
+  size_t o = (size_t)me * a.L + a.nl + l;
+  if (role == 0) {
+    a.gz[o] = g0 + ca * invn * a.z[o];      // - a * log p(z): d/dz = + a z
+  } else {
+    a.gmu[o] = g0;
+    a.glv[o] = g1;
+  }
+}
+
+__global__ void latent_bwd_kernel(int n, int L, int nl, const float* A, const float* B,
+                                  const float* eps, const float* logvar, const float* gz_dec,
+                                  const float* gmu_p, const float* glv_p, const float* gz_p,
+                                  float* gpre, float* glogvar) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * L) return;
+  int f = i / L, c = i - f * L;
+  // glogvar for (f, c)
+  {
+    float gz = (gz_p ? gz_p[i] : 0.f) + (gz_dec ? gz_dec[i] : 0.f);
+    float e = eps ? eps[i] * expf(logvar[i]) : 0.f;
+    glogvar[i] = (glv_p ? glv_p[i] : 0.f) + gz * e;
+  }
+  // gpre[f, c] = sum_d M[d, c] * (gmu_part[f, d] + gz[f, d])
+  float s = 0.f;
+  for (int d = 0; d < L; ++d) {
+    size_t o = (size_t)f * L + d;
+    float g = (gmu_p ? gmu_p[o] : 0.f) + (gz_p ? gz_p[o] : 0.f) + (gz_dec ? gz_dec[o] : 0.f);
+    float m = d < nl ? A[(size_t)d * L + c] : B[(size_t)(d - nl) * L + c];
+    s = fmaf(m, g, s);
+  }
+  gpre[i] = s;
+}
+
+}  // namespace
+
+extern "C" size_t bn_psvae_latent_workspace_bytes(int n, int n_latents) {
+  if (n <= 0 || n_latents <= 0) return 0;
+  return (size_t)n * (n_latents + 1) * sizeof(float);
+}
+
+extern "C" int bn_psvae_latent(int n, int L, int nl, const float* d_pre, const float* d_logvar,
+                               const float* d_A, const float* d_B, const float* d_Dw, const float* d_Db,
+                               const float* d_eps, const float* d_labels, const float* d_labels_mask,
+                               float alpha, float beta, float kl_w, void* d_ws, float* d_mu, float* d_z,
+                               float* d_yhat, double* d_terms, float* d_gmu_part, float* d_glogvar_part,
+                               float* d_gz_part, float* d_gDw, float* d_gDb, void* stream) {
+  if (n <= 0) return 0;
+  if (L < 1 || nl < 0 || nl > L) BN_FAIL("bn_psvae_latent: n_latents=%d n_labels=%d", L, nl);
+  if (L - nl > 64) BN_FAIL("bn_psvae_latent: more than 64 unsupervised latents");
+  if (!d_pre || !d_logvar || !d_A || (!d_B && L > nl) || !d_Dw || !d_Db || !d_mu || !d_z || !d_yhat || !d_terms)
+    BN_FAIL("bn_psvae_latent: null argument");
+  const bool grads = d_gmu_part && d_glogvar_part && d_gz_part;
+  if (grads && !d_ws) BN_FAIL("bn_psvae_latent: workspace required");
+  cudaStream_t st = (cudaStream_t)stream;
+  LatArgs a;
+  a.n = n; a.L = L; a.nl = nl; a.pre = d_pre; a.logvar = d_logvar; a.A = d_A; a.B = d_B; a.Dw = d_Dw;
+  a.Db = d_Db; a.eps = d_eps; a.labels = d_labels; a.lmask = d_labels_mask; a.alpha = alpha;
+  a.beta = beta; a.klw = kl_w; a.mu = d_mu; a.z = d_z; a.yhat = d_yhat; a.terms = d_terms;
+  a.gmu = grads ? d_gmu_part : nullptr; a.glv = d_glogvar_part; a.gz = d_gz_part; a.gDw = d_gDw; a.gDb = d_gDb;
+  a.log_qz = (float*)d_ws;
+  a.lse = d_ws ? (float*)d_ws + n : nullptr;
+  latent_fwd_kernel<<<bn_cdiv((long long)n * L, 128), 128, 0, st>>>(a);
+  BN_LAUNCHED();
+  const int du = L - nl;
+  if (du > 0 && d_ws) {
+    dkl_rows_kernel<<<n, 128, 0, st>>>(a);
+    BN_LAUNCHED();
+    if (grads) {
+      dkl_grad_kernel<<<dim3(bn_cdiv((long long)n * du, 128), 2), 128, 0, st>>>(a);
+      BN_LAUNCHED();
+    }
+  }
+  return 0;
+}
+
+extern "C" int bn_psvae_latent_bwd(int n, int L, int nl, const float* d_A, const float* d_B,
+                                   const float* d_eps, const float* d_logvar, const float* d_gz_dec,
+                                   const float* d_gmu_part, const float* d_glogvar_part,
+                                   const float* d_gz_part, float* d_gpre, float* d_glogvar, void* stream) {
+  if (n <= 0) return 0;
+  if (!d_A || (!d_B && L > nl) || !d_logvar || !d_gpre || !d_glogvar) BN_FAIL("bn_psvae_latent_bwd: null argument");
+  latent_bwd_kernel<<<bn_cdiv((long long)n * L, 128), 128, 0, (cudaStream_t)stream>>>(
+      n, L, nl, d_A, d_B, d_eps, d_logvar, d_gz_dec, d_gmu_part, d_glogvar_part, d_gz_part, d_gpre, d_glogvar);
+  BN_LAUNCHED();
+  return 0;
+}

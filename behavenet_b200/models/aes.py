@@ -1,0 +1,313 @@
+"""Convolutional autoencoder with the reference's object protocol, computed by sm_100a kernels.
+
+Drop-in for ``behavenet.models.aes.{ConvAEEncoder, ConvAEDecoder, AE}`` (reference
+``behavenet/models/aes.py:17-218, 221-488, 616-773``): same constructor (``hparams`` dict), same
+``forward`` / ``loss`` / ``encoding`` / ``decoding`` signatures and tuple arities, same
+``state_dict`` names and tensor layouts (checkpoints are interchangeable), same exceptions for
+invalid hparams.  The ``nn.Conv2d`` / ``nn.ConvTranspose2d`` / ``nn.Linear`` submodules exist only
+as parameter containers (so names, shapes and default initialisation are torch's own); their
+``forward`` is never called -- all arithmetic runs in ``libbehavenet_b200.so`` and there is no
+eager fallback: inputs on the CPU raise.
+"""
+
+import numpy as np
+import torch
+from torch import nn
+
+from behavenet_b200 import _lib, parallel
+from behavenet_b200.models.base import BaseModule, BaseModel
+from behavenet_b200.models._engine import CaeDriver, Runtime, EncodeFn, DecodeFn
+
+__all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'load_pretrained_ae']
+
+
+class ConvAEEncoder(BaseModule):
+    """Convolutional encoder (reference aes.py:17-218)."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = hparams
+        self.encoder = None
+        self.build_model()
+
+    def __str__(self):
+        s = 'Encoder architecture:\n'
+        i = -1
+        for i, module in enumerate(self.encoder):
+            s += '    {:02d}: {}\n'.format(i, module)
+        s += '    {:02d}: {}\n'.format(i + 1, self.FF)
+        return s
+
+    def build_model(self):
+        """Parameter containers named like the reference's (aes.py:55-125)."""
+        hp = self.hparams
+        self._driver = CaeDriver(hp)        # raises NotImplementedError for unsupported variants
+        self._rt = Runtime()
+        self.encoder = nn.ModuleList()
+        c_in = hp['ae_input_dim'][0]
+        for i, c_out in enumerate(hp['ae_encoding_n_channels']):
+            x0, x1 = hp['ae_encoding_x_padding'][i]
+            y0, y1 = hp['ae_encoding_y_padding'][i]
+            if x0 == x1 and y0 == y1:
+                padding = (y0, x0)
+            else:
+                self.encoder.add_module('zero_pad%i' % i, nn.ZeroPad2d((x0, x1, y0, y1)))
+                padding = 0
+            self.encoder.add_module('conv%i' % i, nn.Conv2d(
+                in_channels=c_in, out_channels=c_out, kernel_size=hp['ae_encoding_kernel_size'][i],
+                stride=hp['ae_encoding_stride_size'][i], padding=padding))
+            self.encoder.add_module('relu%i' % i, nn.LeakyReLU(0.05))
+            c_in = c_out
+        last_conv_size = c_in * hp['ae_encoding_y_dim'][-1] * hp['ae_encoding_x_dim'][-1]
+        self.FF = nn.Linear(last_conv_size, hp['n_ae_latents'])
+        if hp.get('variational', False):
+            self.logvar = nn.Linear(last_conv_size, hp['n_ae_latents'])
+
+    def _conv_modules(self):
+        return [m for m in self.encoder if isinstance(m, nn.Conv2d)]
+
+    def kernel_params(self):
+        """Parameters in the order of the C parameter table (encoder side)."""
+        ps = []
+        for m in self._conv_modules():
+            ps += [m.weight, m.bias]
+        ps += [self.FF.weight, self.FF.bias]
+        if self.hparams.get('variational', False):
+            ps += [self.logvar.weight, self.logvar.bias]
+        else:
+            ps += [None, None]
+        return ps
+
+    def _heads(self, x):
+        x = CaeDriver._check_input(x, 'encoder input', self._driver.img)
+        if x.requires_grad:
+            raise NotImplementedError('gradients with respect to input frames are not computed')
+        ps = self.kernel_params()
+        if self.hparams.get('variational', False):
+            return EncodeFn.apply(self, x, *ps)
+        return EncodeFn.apply(self, x, *ps[:-2])
+
+    def forward(self, x, dataset=None):
+        """(z, pool_idx, output_size) -- or (mu, logvar, pool_idx, output_size) if variational
+        (reference aes.py:181-218).  The pool lists are empty: there is no max-pooling path."""
+        out = self._heads(x)
+        if self.hparams.get('variational', False):
+            return out[0], out[1], [], []
+        return out, [], []
+
+
+class ConvAEDecoder(BaseModule):
+    """Convolutional decoder (reference aes.py:221-488)."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = hparams
+        self.decoder = None
+        self.build_model()
+
+    def __str__(self):
+        s = 'Decoder architecture:\n'
+        s += '    {:02d}: {}\n'.format(0, self.FF)
+        for i, module in enumerate(self.decoder):
+            s += '    {:02d}: {}\n'.format(i + 1, module)
+        return s
+
+    def build_model(self):
+        hp = self.hparams
+        if hp.get('ae_padding_type', 'same') not in ('same', 'valid'):
+            raise ValueError('"%s" is not a valid padding type' % hp['ae_padding_type'])
+        self._driver = CaeDriver(hp)
+        self._rt = Runtime()
+        c0, h0, w0 = hp['ae_decoding_starting_dim']
+        self.FF = nn.Linear(hp['hidden_layer_size'], c0 * h0 * w0)
+        self.decoder = nn.ModuleList()
+        self.conv_t_pads = {}
+        c_in = c0
+        n = len(hp['ae_decoding_n_channels'])
+        for i, c_out in enumerate(hp['ae_decoding_n_channels']):
+            x0, x1 = hp['ae_decoding_x_padding'][i]
+            y0, y1 = hp['ae_decoding_y_padding'][i]
+            name = 'convtranspose%i' % i
+            if x0 == x1 and y0 == y1:
+                padding = (y0, x0)
+                self.conv_t_pads[name] = None
+            else:
+                padding = 0
+                self.conv_t_pads[name] = [x0, x1, y0, y1]
+            self.decoder.add_module(name, nn.ConvTranspose2d(
+                in_channels=c_in, out_channels=c_out,
+                kernel_size=(hp['ae_decoding_kernel_size'][i],) * 2,
+                stride=(hp['ae_decoding_stride_size'][i],) * 2, padding=padding, output_padding=0))
+            if i == n - 1:
+                self.decoder.add_module('sigmoid%i' % i, nn.Sigmoid())
+            else:
+                self.decoder.add_module('relu%i' % i, nn.LeakyReLU(0.05))
+            c_in = c_out
+
+    def _conv_modules(self):
+        return [m for m in self.decoder if isinstance(m, nn.ConvTranspose2d)]
+
+    def kernel_params(self):
+        ps = [self.FF.weight, self.FF.bias]
+        for m in self._conv_modules():
+            ps += [m.weight, m.bias]
+        return ps
+
+    def forward(self, x, pool_idx=None, target_output_size=None, dataset=None):
+        """x_hat of shape (n, C, H, W) (reference aes.py:432-488)."""
+        x = CaeDriver._check_input(x, 'decoder input', (self._driver.L,))
+        return DecodeFn.apply(self, x, *self.kernel_params())
+
+
+class AE(BaseModel):
+    """Convolutional autoencoder (reference aes.py:616-773)."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = hparams
+        self.model_type = self.hparams['model_type']
+        self.img_size = (
+            self.hparams['n_input_channels'], self.hparams['y_pixels'], self.hparams['x_pixels'])
+        self.encoding = None
+        self.decoding = None
+        # True: shard every batch over the ranks of behavenet_b200.parallel (one process per GPU)
+        self.data_parallel = False
+        self.build_model()
+
+    def __str__(self):
+        s = '\nAutoencoder architecture\n'
+        s += '------------------------\n'
+        s += self.encoding.__str__()
+        s += self.decoding.__str__()
+        return s + '\n'
+
+    def build_model(self):
+        self.hparams['hidden_layer_size'] = self.hparams['n_ae_latents']
+        if self.model_type == 'conv':
+            self.encoding = ConvAEEncoder(self.hparams)
+            self.decoding = ConvAEDecoder(self.hparams)
+        elif self.model_type == 'linear':
+            raise NotImplementedError('linear autoencoders have no B200 kernel path')
+        else:
+            raise ValueError('"%s" is an invalid model_type' % self.model_type)
+        self._driver = self.encoding._driver
+        self._rt = Runtime()
+
+    def forward(self, x, dataset=None, **kwargs):
+        """(x_hat, z) (reference aes.py:695-720)."""
+        z, pool_idx, outsize = self.encoding(x, dataset=dataset)
+        y = self.decoding(z, pool_idx, outsize, dataset=dataset)
+        return y, z
+
+    # -- fused training step -----------------------------------------------------------------
+    def _kernel_params(self):
+        return self.encoding.kernel_params() + self.decoding.kernel_params()
+
+    def _extra_trainable(self):
+        """Trainable parameters that are not in the C parameter table (PS-VAE label head)."""
+        return []
+
+    def _grad_table(self, params):
+        """.grad tensors to accumulate into (autograd semantics: created as zeros if absent).
+        Freshly created gradients are views of one flat buffer so that a data-parallel run needs
+        a single all-reduce."""
+        everything = [p for p in params if p is not None] + self._extra_trainable()
+        missing = [p for p in everything if p.requires_grad and p.grad is None]
+        if missing:
+            total = sum(p.numel() for p in missing)
+            flat = torch.zeros(total, dtype=torch.float32, device=missing[0].device)
+            o = 0
+            for p in missing:
+                p.grad = flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+            self._rt.bufs['flat_grad'] = flat
+            self._rt.bufs['flat_grad_ptrs'] = [p.grad.data_ptr() for p in missing]
+        return [None if (p is None or not p.requires_grad) else p.grad for p in params]
+
+    def _shard(self, n):
+        """Contiguous frame range of this rank (data-parallel) -> (begin, end)."""
+        if not (self.data_parallel and parallel.enabled()):
+            return 0, n
+        return parallel.shard_range(n)
+
+    def _allreduce(self, params, extra):
+        """One NCCL all-reduce of the flat gradient (+ one of the loss partial sums)."""
+        flat = self._rt.bufs.get('flat_grad')
+        ptrs = self._rt.bufs.get('flat_grad_ptrs')
+        everything = [p for p in params if p is not None] + self._extra_trainable()
+        live = [p.grad.data_ptr() for p in everything if p.requires_grad]
+        if flat is not None and ptrs == live:
+            parallel.all_reduce_sum(flat)
+        else:
+            for p in everything:
+                if p.requires_grad:
+                    parallel.all_reduce_sum(p.grad)
+        parallel.all_reduce_sum(extra)
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200):
+        """MSE loss (+ gradients) with the reference's chunk semantics (aes.py:722-773): the batch
+        is treated as ceil(n / chunk_size) chunks, each contributing the gradient of its own mean
+        squared error; the returned value is the frame-weighted mean of the chunk losses.
+
+        One fused pass: encoder kernels -> decoder kernels with the squared error and its
+        gradient computed in the last layer's epilogue -> backward kernels accumulating into
+        ``.grad``.  A single device->host read of the per-chunk sums ends the call.
+        """
+        x = data['images'][0]
+        m = data['masks'][0] if 'masks' in data else None
+        drv, rt = self._driver, self._rt
+        x = drv._check_input(x, "data['images'][0]", drv.img)
+        if m is not None:
+            m = drv._check_input(m.to(torch.float32), "data['masks'][0]", drv.img)
+        n_total = x.shape[0]
+        n_chunks = int(np.ceil(n_total / chunk_size))
+        beg, end = self._shard(n_total)
+        n = end - beg
+        params = self._kernel_params()
+        device = x.device
+        sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
+        if n > 0:
+            xs = x[beg:end]
+            ms = None if m is None else m[beg:end]
+            packed = drv.packed(rt, params, device)
+            ws = drv.workspace(rt, n, device)
+            z, _ = drv.encode(xs, params, packed, ws, False)
+            numel = float(np.prod(drv.img))
+            drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms,
+                       chunk_size=chunk_size, frame_offset=beg, n_total=n_total,
+                       grad_coef=2.0 / numel, sse=sse)
+            if accumulate_grad:
+                grads = self._grad_table(params)
+                dz = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+                drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
+        elif accumulate_grad:
+            self._grad_table(params)
+        if self.data_parallel and parallel.enabled():
+            if accumulate_grad:
+                self._allreduce(params, sse)
+            else:
+                parallel.all_reduce_sum(sse)
+        numel = float(np.prod(drv.img))
+        loss_val = float(sse.sum().item()) / (numel * n_total)
+        return {'loss': loss_val}
+
+
+def load_pretrained_ae(model, hparams):
+    """Load pretrained weights into ``model`` (reference aes.py:1220-1274): FF layers are dropped
+    when the latent count differs, everything else must match."""
+    import os
+    if hparams.get('pretrained_weights_path') is None or hparams['pretrained_weights_path'] == '':
+        return model
+    path = hparams['pretrained_weights_path']
+    if not os.path.exists(path):
+        raise FileNotFoundError('pretrained weights %s do not exist' % path)
+    loaded = torch.load(path, map_location=lambda storage, loc: storage)
+    own = model.state_dict()
+    if loaded['encoding.FF.weight'].shape == own['encoding.FF.weight'].shape:
+        model.load_state_dict(loaded, strict=False)
+    else:
+        print('warning: number of latents differ; pretrained FF layers are skipped')
+        for k in ['encoding.FF.weight', 'encoding.FF.bias', 'decoding.FF.weight', 'decoding.FF.bias']:
+            loaded.pop(k, None)
+        model.load_state_dict(loaded, strict=False)
+    return model

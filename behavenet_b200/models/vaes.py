@@ -1,0 +1,345 @@
+"""Partitioned-subspace VAE with the reference's object protocol on sm_100a kernels.
+
+Drop-in for ``behavenet.models.vaes.{reparameterize, ConvAEPSEncoder, PSVAE}`` (reference
+``behavenet/models/vaes.py:17-35, 1276-1363, 506-846``).  The conv stacks run on the same kernels
+as the AE; the latent block (orthogonal A/B projections, diagonal label head D, reparameterisation,
+label log-likelihood, KL and decomposed-KL terms and all of their gradients) is one fused C call
+per reference chunk (``bn_psvae_latent``), and the pixel log-likelihood is fused into the last
+decoder layer's epilogue.
+"""
+
+import numpy as np
+import torch
+from torch import nn
+
+from behavenet_b200 import _lib, parallel
+from behavenet_b200.models.aes import AE, ConvAEDecoder, ConvAEEncoder
+from behavenet_b200.models.base import DiagLinear
+from behavenet_b200.models._engine import CaeDriver
+
+__all__ = ['reparameterize', 'PSVAE', 'ConvAEPSEncoder']
+
+LN2PI = float(np.log(2 * np.pi))
+
+
+def reparameterize(mu, logvar, eps=None):
+    """Sample eps * exp(logvar) + mu (reference vaes.py:17-35; note std = exp(logvar)).
+
+    ``eps`` (optional) injects the noise, for bit-reproducible comparisons with the reference.
+    """
+    if eps is None:
+        eps = torch.randn_like(mu)
+    return eps * torch.exp(logvar) + mu
+
+
+class _LatentFn(torch.autograd.Function):
+    """Differentiable PS-VAE latent block outside ``loss`` (forward / plotting helpers):
+    (pre, logvar, A, B, Dw, Db, eps) -> (mu, z, y_hat).  Backward chains through the same C call
+    that ``PSVAE.loss`` uses, with all loss weights zero."""
+
+    @staticmethod
+    def forward(ctx, pre, logvar, A, B, Dw, Db, eps):
+        n, L = pre.shape
+        nl = A.shape[0]
+        dev = pre.device
+        mu = torch.empty(n, L, device=dev)
+        z = torch.empty(n, L, device=dev)
+        yhat = torch.empty(n, nl, device=dev)
+        terms = torch.zeros(5, dtype=torch.float64, device=dev)
+        _lib.check(_lib.lib().bn_psvae_latent(
+            n, L, nl, pre.data_ptr(), logvar.data_ptr(), A.data_ptr(), _lib.ptr(B), Dw.data_ptr(),
+            Db.data_ptr(), _lib.ptr(eps), None, None, 0.0, 0.0, 0.0, None, mu.data_ptr(),
+            z.data_ptr(), yhat.data_ptr(), terms.data_ptr(), None, None, None, None, None,
+            _lib.stream_ptr()), 'bn_psvae_latent')
+        ctx.save_for_backward(logvar, A, B, Dw, eps, mu)
+        return mu, z, yhat
+
+    @staticmethod
+    def backward(ctx, gmu, gz, gy):
+        logvar, A, B, Dw, eps, mu = ctx.saved_tensors
+        n, L = logvar.shape
+        nl = A.shape[0]
+        dev = logvar.device
+        gmu_part = torch.zeros(n, L, device=dev) if gmu is None else gmu.contiguous().clone()
+        gDw = gDb = None
+        if gy is not None:
+            gmu_part[:, :nl] += gy * Dw
+            gDw = (gy * mu[:, :nl]).sum(0)
+            gDb = gy.sum(0)
+        gz_dec = None if gz is None else gz.contiguous()
+        gpre = torch.empty(n, L, device=dev)
+        glv = torch.empty(n, L, device=dev)
+        _lib.check(_lib.lib().bn_psvae_latent_bwd(
+            n, L, nl, A.data_ptr(), _lib.ptr(B), _lib.ptr(eps), logvar.data_ptr(), _lib.ptr(gz_dec),
+            gmu_part.data_ptr(), None, None, gpre.data_ptr(), glv.data_ptr(), _lib.stream_ptr()),
+            'bn_psvae_latent_bwd')
+        return gpre, glv, None, None, gDw, gDb, None
+
+
+class ConvAEPSEncoder(ConvAEEncoder):
+    """Encoder that separates the label-related subspace (reference vaes.py:1276-1363)."""
+
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        n_latents = self.hparams['n_ae_latents']
+        n_labels = self.hparams['n_labels']
+        self.A = nn.Linear(n_latents, n_labels, bias=False)
+        self.B = nn.Linear(n_latents, n_latents - n_labels, bias=False)
+        self.D = DiagLinear(n_labels, bias=True)
+        # frozen orthogonal projections, drawn from numpy's global RNG like the reference
+        # (vaes.py:1294-1302)
+        from scipy.stats import ortho_group
+        m = ortho_group.rvs(dim=n_latents).astype('float32')
+        with torch.no_grad():
+            self.A.weight = nn.Parameter(torch.from_numpy(m[:n_labels, :]), requires_grad=False)
+            self.B.weight = nn.Parameter(torch.from_numpy(m[n_labels:, :]), requires_grad=False)
+
+    def __str__(self):
+        s = 'Encoder architecture:\n'
+        i = -1
+        for i, module in enumerate(self.encoder):
+            s += '    {:02d}: {}\n'.format(i, module)
+        s += '    {:02d}: {}\n'.format(i + 1, self.FF)
+        s += '    {:02d}: {} (to constrained latents)\n'.format(i + 1, self.A)
+        s += '    {:02d}: {} (to unconstrained latents)\n'.format(i + 1, self.B)
+        s += '    {:02d}: {} (constrained latents to labels)\n'.format(i + 1, self.D)
+        return s
+
+    def forward(self, x, dataset=None):
+        """(y, w, logvar, pool_idx, output_size) (reference vaes.py:1319-1363): ``logvar`` comes
+        from the flattened conv features, y / w are the A / B projections of the FF output."""
+        pre, logvar = self._heads(x)
+        n_labels = self.hparams['n_labels']
+        mu, _, _ = _LatentFn.apply(pre, logvar, self.A.weight, self.B.weight, self.D.weight,
+                                   self.D.bias, None)
+        return mu[:, :n_labels], mu[:, n_labels:], logvar, [], []
+
+
+class PSVAE(AE):
+    """Partitioned subspace variational autoencoder (reference vaes.py:506-846)."""
+
+    def __init__(self, hparams):
+        if hparams['model_type'] == 'linear':
+            raise NotImplementedError
+        if hparams['n_ae_latents'] < hparams['n_labels']:
+            raise ValueError('PS-VAE model must contain at least as many latents as labels')
+        self.n_latents = hparams['n_ae_latents']
+        self.n_labels = hparams['n_labels']
+        hparams['variational'] = True
+        super().__init__(hparams)
+        # annealing tables indexed by curr_epoch (reference vaes.py:536-553)
+        anneal_epochs = self.hparams.get('ps_vae.anneal_epochs', 0)
+        self.curr_epoch = 0
+        beta = hparams['ps_vae.beta']
+        tail = np.ones(hparams['max_n_epochs'] + 1)
+        if anneal_epochs > 0:
+            self.beta_vals = np.append(np.linspace(0, beta, anneal_epochs), beta * tail)
+            self.kl_anneal_vals = np.append(np.linspace(0, 1, anneal_epochs), tail)
+        else:
+            self.beta_vals = beta * tail
+            self.kl_anneal_vals = tail
+
+    def build_model(self):
+        self.hparams['hidden_layer_size'] = self.hparams['n_ae_latents']
+        if self.model_type == 'conv':
+            self.encoding = ConvAEPSEncoder(self.hparams)
+            self.decoding = ConvAEDecoder(self.hparams)
+        elif self.model_type == 'linear':
+            raise NotImplementedError
+        else:
+            raise ValueError('"%s" is an invalid model_type' % self.model_type)
+        from behavenet_b200.models._engine import Runtime
+        self._driver = self.encoding._driver
+        self._rt = Runtime()
+
+    def _extra_trainable(self):
+        return [self.encoding.D.weight, self.encoding.D.bias]
+
+    def forward(self, x, dataset=None, use_mean=False, eps=None, **kwargs):
+        """(x_hat, z, mu, logvar, y_hat) (reference vaes.py:571-601).  ``eps`` optionally injects
+        the reparameterisation noise."""
+        enc = self.encoding
+        pre, logvar = enc._heads(x)
+        if use_mean:
+            noise = None
+        else:
+            noise = torch.randn_like(pre) if eps is None else eps.to(pre.device).contiguous()
+        mu, z, y_hat = _LatentFn.apply(pre, logvar, enc.A.weight, enc.B.weight, enc.D.weight,
+                                       enc.D.bias, noise)
+        x_hat = self.decoding(z, [], [], dataset=dataset)
+        return x_hat, z, mu, logvar, y_hat
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200, eps=None):
+        """Decomposed-ELBO loss of the PS-VAE with the reference's chunk semantics
+        (reference vaes.py:603-729).  Returns the same dict of python floats.
+
+        Conv stacks run once over the whole (rank-local) batch; the latent block runs once per
+        reference chunk because the MI / TC / DWKL estimators are pairwise over the chunk
+        (losses.py:321-351).  ``eps`` (n, n_latents) optionally injects the sampling noise.
+        """
+        x = data['images'][0]
+        y = data['labels'][0]
+        m = data['masks'][0] if 'masks' in data else None
+        nm = data['labels_masks'][0] if 'labels_masks' in data else None
+        drv, rt, enc = self._driver, self._rt, self.encoding
+        x = drv._check_input(x, "data['images'][0]", drv.img)
+        y = drv._check_input(y.to(torch.float32), "data['labels'][0]", (self.n_labels,))
+        if m is not None:
+            m = drv._check_input(m.to(torch.float32), "data['masks'][0]", drv.img)
+        if nm is not None:
+            nm = drv._check_input(nm.to(torch.float32), "data['labels_masks'][0]", (self.n_labels,))
+        n_total = x.shape[0]
+        chunks = [(b, min(b + chunk_size, n_total)) for b in range(0, n_total, chunk_size)]
+        n_chunks = len(chunks)
+        L, nl = self.n_latents, self.n_labels
+        alpha = self.hparams['ps_vae.alpha']
+        beta = self.beta_vals[self.curr_epoch]
+        kl = self.kl_anneal_vals[self.curr_epoch]
+        device = x.device
+        if self.data_parallel and parallel.enabled():
+            # whole chunks per rank: the pairwise estimators need a chunk's frames together
+            cb, ce = parallel.shard_range(n_chunks)
+            my_chunks = list(range(cb, ce))
+        else:
+            my_chunks = list(range(n_chunks))
+        beg = chunks[my_chunks[0]][0] if my_chunks else 0
+        end = chunks[my_chunks[-1]][1] if my_chunks else 0
+        n = end - beg
+        params = self._kernel_params()
+        # per chunk: [sse_pixels] ; [label sumsq, zs_kl, mi, tc, dwkl]
+        sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
+        terms = torch.zeros(n_chunks, 5, dtype=torch.float64, device=device)
+        y_hat_all = torch.zeros(n_total, nl, dtype=torch.float32, device=device)
+        lib = _lib.lib()
+        if n > 0:
+            xs = x[beg:end]
+            ms = None if m is None else m[beg:end]
+            if eps is None:
+                eps_s = torch.randn(n, L, dtype=torch.float32, device=device)
+            else:
+                eps_s = eps.to(device=device, dtype=torch.float32)[beg:end].contiguous()
+            packed = drv.packed(rt, params, device)
+            ws = drv.workspace(rt, n, device)
+            pre, logvar = drv.encode(xs, params, packed, ws, True)
+            mu = torch.empty(n, L, device=device)
+            z = torch.empty(n, L, device=device)
+            gmu_p = torch.empty(n, L, device=device)
+            glv_p = torch.empty(n, L, device=device)
+            gz_p = torch.empty(n, L, device=device)
+            D = enc.D
+            grads = self._grad_table(params) if accumulate_grad else None
+            lws = torch.empty(lib.bn_psvae_latent_workspace_bytes(chunk_size, L), dtype=torch.uint8,
+                              device=device)
+            for c in my_chunks:
+                b, e = chunks[c][0] - beg, chunks[c][1] - beg
+                sl = slice(b, e)
+                _lib.check(lib.bn_psvae_latent(
+                    e - b, L, nl, pre[sl].data_ptr(), logvar[sl].data_ptr(), enc.A.weight.data_ptr(),
+                    _lib.ptr(enc.B.weight) if L > nl else None, D.weight.data_ptr(), D.bias.data_ptr(),
+                    eps_s[sl].data_ptr(), y[beg + b:beg + e].data_ptr(),
+                    None if nm is None else nm[beg + b:beg + e].data_ptr(),
+                    float(alpha), float(beta), float(kl), lws.data_ptr(), mu[sl].data_ptr(),
+                    z[sl].data_ptr(), y_hat_all[beg + b:beg + e].data_ptr(), terms[c].data_ptr(),
+                    gmu_p[sl].data_ptr(), glv_p[sl].data_ptr(), gz_p[sl].data_ptr(),
+                    D.weight.grad.data_ptr() if accumulate_grad and D.weight.requires_grad else None,
+                    D.bias.grad.data_ptr() if accumulate_grad and D.bias.requires_grad else None,
+                    _lib.stream_ptr()), 'bn_psvae_latent')
+            # pixel log-likelihood fused in the decoder epilogue: d(-ll)/dxhat = (xhat - x) m / len
+            drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms,
+                       chunk_size=chunk_size, frame_offset=beg, n_total=n_total, grad_coef=1.0,
+                       sse=sse)
+            if accumulate_grad:
+                gz_dec = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+                gpre = torch.empty(n, L, device=device)
+                glv = torch.empty(n, L, device=device)
+                _lib.check(lib.bn_psvae_latent_bwd(
+                    n, L, nl, enc.A.weight.data_ptr(), _lib.ptr(enc.B.weight) if L > nl else None,
+                    eps_s.data_ptr(), logvar.data_ptr(), gz_dec.data_ptr(), gmu_p.data_ptr(),
+                    glv_p.data_ptr(), gz_p.data_ptr(), gpre.data_ptr(), glv.data_ptr(),
+                    _lib.stream_ptr()), 'bn_psvae_latent_bwd')
+                drv.encode_bwd(xs, gpre, glv, params, packed, ws, grads)
+        elif accumulate_grad:
+            self._grad_table(params)
+        if self.data_parallel and parallel.enabled():
+            stats = torch.cat([sse[:, None], terms], 1)
+            if accumulate_grad:
+                self._allreduce(params, stats)
+            else:
+                parallel.all_reduce_sum(stats)
+            parallel.all_reduce_sum(y_hat_all)
+            sse, terms = stats[:, 0], stats[:, 1:]
+        # ---- one device->host read, then the reference's bookkeeping (vaes.py:700-729)
+        host = torch.cat([sse[:, None], terms], 1).cpu().numpy()
+        n_pix = float(np.prod(drv.img))
+        keys = ['loss', 'loss_data_ll', 'loss_label_ll', 'loss_zs_kl', 'loss_zu_mi', 'loss_zu_tc',
+                'loss_zu_dwkl']
+        vals = {k: 0.0 for k in keys}
+        vals['loss_data_mse'] = 0.0
+        for c, (b, e) in enumerate(chunks):
+            bs = e - b
+            t = {}
+            t['loss_data_ll'] = -0.5 * LN2PI * n_pix - 0.5 * host[c, 0] / bs
+            t['loss_label_ll'] = -0.5 * LN2PI * nl - 0.5 * host[c, 1] / bs
+            t['loss_zs_kl'] = host[c, 2] / bs
+            t['loss_zu_mi'] = host[c, 3] / bs
+            t['loss_zu_tc'] = host[c, 4] / bs
+            t['loss_zu_dwkl'] = host[c, 5] / bs
+            t['loss'] = (-t['loss_data_ll'] - alpha * t['loss_label_ll'] + t['loss_zs_kl']
+                         + kl * t['loss_zu_mi'] + beta * t['loss_zu_tc'] + kl * t['loss_zu_dwkl'])
+            for k in keys:
+                vals[k] += t[k] * bs
+            # the reference converts the RUNNING sum (vaes.py:705-706); reproduced as is
+            llc = vals['loss_data_ll'] / bs + 0.5 * LN2PI * n_pix
+            vals['loss_data_mse'] += (llc * -2.0 / n_pix) * bs
+        for k in vals:
+            vals[k] /= n_total
+        vals['alpha'] = alpha
+        vals['beta'] = beta
+        # variance-weighted R^2 on the host, as the reference does with sklearn (vaes.py:709-718)
+        from sklearn.metrics import r2_score
+        y_np = y.cpu().numpy()
+        yh_np = y_hat_all.cpu().numpy()
+        if nm is not None:
+            n_np = nm.cpu().numpy()
+            vals['label_r2'] = r2_score(y_np[n_np == 1], yh_np[n_np == 1],
+                                        multioutput='variance_weighted')
+        else:
+            vals['label_r2'] = r2_score(y_np, yh_np, multioutput='variance_weighted')
+        return vals
+
+    # -- helpers used by the reference's plotting code (vaes.py:731-846); tiny tensors ----------
+    def get_predicted_labels(self, x, dataset=None, use_mean=True):
+        y, w, logvar, _, _ = self.encoding(x, dataset=dataset)
+        if not use_mean:
+            y = reparameterize(y, logvar[:, :self.n_labels])
+        return self.encoding.D(y)
+
+    def get_transformed_latents(self, inputs, dataset=None, as_numpy=True):
+        if not isinstance(inputs, torch.Tensor):
+            inputs = torch.Tensor(inputs)
+        dev = self.encoding.D.weight.device
+        inputs = inputs.to(dev)
+        if inputs.dim() == 2:
+            y_og, w_og = inputs[:, :self.n_labels], inputs[:, self.n_labels:]
+        elif inputs.dim() == 4:
+            y_og, w_og, _, _, _ = self.encoding(inputs, dataset=dataset)
+        else:
+            raise ValueError('"inputs" must be 2 or 4-dimensional tensor')
+        y_new = self.encoding.D(y_og)
+        latents = torch.cat([y_new, w_og], axis=1)
+        return latents.cpu().detach().numpy() if as_numpy else latents
+
+    def get_inverse_transformed_latents(self, inputs, dataset=None, as_numpy=True):
+        if not isinstance(inputs, torch.Tensor):
+            inputs = torch.Tensor(inputs)
+        dev = self.encoding.D.weight.device
+        inputs = inputs.to(dev)
+        if inputs.dim() == 2:
+            y_og, w_og = inputs[:, :self.n_labels], inputs[:, self.n_labels:]
+        elif inputs.dim() == 4:
+            y_og, w_og, _, _, _ = self.encoding(inputs, dataset=dataset)
+        else:
+            raise ValueError('"inputs" must be 2 or 4-dimensional tensor')
+        y_new = (y_og - self.encoding.D.bias) / self.encoding.D.weight
+        latents = torch.cat([y_new, w_og], axis=1)
+        return latents.cpu().detach().numpy() if as_numpy else latents

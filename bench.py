@@ -1,0 +1,375 @@
+"""Benchmark of the two hot paths on synthetic data of BASELINE.json's shapes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Headline workload (N GPUs, weak scaling): config C2 -- CAE 128x128x1, 12 latents, 256 frames per
+GPU, one ``AE.loss(data, accumulate_grad=True)`` call per step (forward + fused MSE + backward over
+all reference chunks, plus the gradient all-reduce when N > 1), frames resident in HBM.
+The same JSON line carries an ``arhmm`` object for config C4 (K=16, lag 2, D=12, 2048 trials x 1000
+steps per GPU, one E-step per step).
+
+``--impl reference`` times the CPU oracle port of the reference path (oracle/) on the host cores.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work
+CAE_C2_TRAIN_GFLOP_PER_FRAME = 2.078
+ARHMM_BYTES_PER_TIMESTEP = 113.0
+CAE_BATCH_PER_GPU = 256
+ARHMM_TRIALS_PER_GPU, ARHMM_T, ARHMM_K, ARHMM_D, ARHMM_LAGS = 2048, 1000, 16, 12, 2
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [v.strip() for v in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(np.max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_cae(device):
+    import copy
+    from behavenet_b200.models import AE
+    from oracle import cae_oracle as co          # only for the seeded synthetic parameters
+    hp = co.make_hparams(1, 128, 128, 12)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.to(device)
+    return model, hp
+
+
+def timed(fn, steps, warmup, flush=None):
+    """CUDA-event timing of ``steps`` calls after ``warmup`` calls; returns list of ms per step."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(steps):
+        if flush is not None:
+            flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return ms
+
+
+def dist_max(value, device):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        t = torch.tensor([value], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return value
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def run_ours(args):
+    from behavenet_b200 import _lib, parallel
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        parallel.init('nccl')
+    peaks, peak_src = measured_peaks()
+    lib = _lib.lib()
+    lib.bn_set_tensor_core_mode(1)
+
+    # ---------------- CAE (C2) : weak scaling, 256 frames per GPU
+    model, hp = make_cae(device)
+    model.data_parallel = world > 1
+    B = CAE_BATCH_PER_GPU * world
+    g = torch.Generator().manual_seed(0)
+    x_host = torch.rand(B, 1, 128, 128, generator=g).pin_memory()
+    x_dev = x_host.to(device)
+    data = {'images': x_dev[None]}
+    opt = torch.optim.Adam(model.get_parameters(), lr=1e-4, amsgrad=True)
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def flush():
+        l2_flush.zero_()
+
+    def step():
+        opt.zero_grad()
+        model.loss(data, accumulate_grad=True)
+
+    def step_e2e():
+        opt.zero_grad()
+        xd = x_host.to(device, non_blocking=True)
+        model.loss({'images': xd[None]}, accumulate_grad=True)      # ends with the loss readback
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    launches0 = _lib.launch_count()
+    if rank == 0:
+        sampler.start()
+    # timed region: exactly K steps, barrier + synchronize on both sides
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    total_ms = dist_max(e0.elapsed_time(e1), device)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    cae_value = B / (ms_per_step * 1e-3)
+    # per-step distribution with an L2 flush between steps (inputs are 16.8 MB/GPU < L2)
+    ms_flushed = timed(step, max(3, min(args.steps, 10)), 0, flush)
+    opt_ms = timed(lambda: opt.step(), 3, 1)
+    e2e_ms = timed(step_e2e, max(3, min(args.steps, 10)), 2)
+    e2e_ms = dist_max(float(np.median(e2e_ms)), device)
+
+    tf = cae_value * CAE_C2_TRAIN_GFLOP_PER_FRAME * 1e-3 / world         # TFLOP/s per GPU
+    tf32_peak = peaks.get('tf32_tflops', peaks['bf16_tflops_sustained'] / 2.0)
+
+    # ---------------- ARHMM (C4): weak scaling, 2048 trials per GPU
+    from behavenet_b200.ssm import HMM
+    from oracle import arhmm_oracle as ao         # synthetic parameters / data generator only
+    p = ao.synth_params(ARHMM_K, ARHMM_D, ARHMM_LAGS, seed=0)
+    hmm = HMM(ARHMM_K, ARHMM_D, observations='ar', observation_kwargs={'lags': ARHMM_LAGS})
+    hmm.init_state_distn.log_pi0, hmm.transitions.log_Ps = p.log_pi0, p.log_Ps
+    hmm.observations.As, hmm.observations.bs, hmm.observations.Sigmas = p.As, p.bs, p.Sigmas
+    X = ao.sample_batch(p, ARHMM_TRIALS_PER_GPU, ARHMM_T, seed=rank)
+    trials = [X[i] for i in range(X.shape[0])]
+    st = hmm._stage(trials)
+    n_ts = ARHMM_TRIALS_PER_GPU * ARHMM_T
+
+    def estep():
+        Ez, Ezz, logZ = hmm._run_estep(st, True)
+        if world > 1:
+            stats = torch.cat([Ezz.sum(0).double().reshape(-1), logZ.sum().reshape(1)])
+            parallel.all_reduce_sum(stats)
+
+    for _ in range(max(3, args.warmup)):
+        estep()
+    torch.cuda.synchronize()
+    barrier()
+    h0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        estep()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    hmm_ms = dist_max(e0.elapsed_time(e1), device) / args.steps
+    hmm_launches = _lib.launch_count() - h0
+    hmm_value = n_ts * world / (hmm_ms * 1e-3)
+
+    def estep_e2e():
+        hmm.clear_cache()
+        s2 = hmm._stage(trials)                       # host -> device copy of the latents
+        Ez, Ezz, logZ = hmm._run_estep(s2, True)
+        return float(logZ.sum().item()), Ezz.sum(0).cpu()
+    hmm_e2e = float(np.median(timed(estep_e2e, 3, 1)))
+
+    if rank != 0:
+        return
+    cpu = cpu_baselines(hp) if world == 1 else None
+    hbm_achieved = hmm_value / world * ARHMM_BYTES_PER_TIMESTEP / 1e9
+    line = {
+        'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
+        'value': cae_value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 accumulate)' if lib.bn_get_tensor_core_mode() else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'C2: CAE 128x128x1, 12 latents, batch=256 per GPU, AE.loss fwd+bwd, '
+                               'default 5-layer arch', 'global_batch': B,
+                   'l2': 'inputs 16.8 MB/GPU < L2; ms_per_step_l2_flushed reports the flushed timing',
+                   'parallelism': 'dp%d' % world},
+        'ms_per_step_l2_flushed': float(np.median(ms_flushed)),
+        'optimizer_step_ms': float(np.median(opt_ms)),
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'e2e': {'value': B / (e2e_ms * 1e-3), 'unit': 'frames/s',
+                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 16},
+        'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                     'frac': tf / tf32_peak, 'traffic': None,
+                     'note': 'whole-step algorithmic FLOPs (%.3f GFLOP/frame) / step time, per GPU; '
+                             'peak = TF32 dense = %s' % (CAE_C2_TRAIN_GFLOP_PER_FRAME,
+                                                          'measured' if 'tf32_tflops' in peaks else
+                                                          'half of the %s bf16 sustained peak' % peak_src)},
+        'arhmm': {
+            'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
+            'value': hmm_value, 'unit': 'timesteps/s', 'ms_per_step': hmm_ms,
+            'gpu_launches': int(hmm_launches), 'dtype': 'f32 (scaled messages), f64 log-normaliser',
+            'e2e': {'value': n_ts / (hmm_e2e * 1e-3), 'unit': 'timesteps/s',
+                    'h2d_bytes_per_step': int(n_ts * ARHMM_D * 4),
+                    'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4)},
+            'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
+                         'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': None,
+                         'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out '
+                                 '+ per-trial outputs), whole E-step time; peak %s' % peak_src},
+        },
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu['cae']
+        line['arhmm']['cpu_baseline'] = cpu['arhmm']
+    print(json.dumps(line))
+
+
+def cpu_cae_step(hp, batch, threads):
+    from oracle import cae_oracle as co
+    torch.set_num_threads(threads)
+    sd = co.init_state_dict(hp, seed=0)
+    x = torch.rand(batch, 1, 128, 128, generator=torch.Generator().manual_seed(0))
+    co.ae_loss(sd, hp, x[:32])                 # warm-up
+    t0 = time.perf_counter()
+    co.ae_loss(sd, hp, x)
+    return time.perf_counter() - t0
+
+
+def cpu_baselines(hp):
+    """Oracle port of the reference paths on this box's host cores (bounded samples)."""
+    from oracle import arhmm_oracle as ao
+    cores = os.cpu_count() or 1
+    dt = cpu_cae_step(hp, 256, cores)
+    cae = {'value': 256 / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+           'sample': 'one AE.loss-equivalent step (oracle/cae_oracle.ae_loss, torch eager fp32, '
+                     'chunks 200+56) on the full 256-frame batch, after a 32-frame warm-up'}
+    p = ao.synth_params(ARHMM_K, ARHMM_D, ARHMM_LAGS, seed=0)
+    X = ao.sample_batch(p, 16, ARHMM_T, seed=0)
+    ao.e_step(p, [X[0]])                        # numba compile
+    t0 = time.perf_counter()
+    ao.e_step(p, [X[i] for i in range(16)])
+    dt = time.perf_counter() - t0
+    hm = {'value': 16 * ARHMM_T / dt, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
+          'sample': '16 of the 2048 trials x 1000 steps, oracle/arhmm_oracle.e_step (numpy emissions '
+                    '+ numba fp64 log-space messages, python loop over trials = ssm execution model)'}
+    return {'cae': cae, 'arhmm': hm}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU path (oracle port; the reference is pure Python /
+    PyTorch eager and /root/reference does not exist on the GPU box).  Rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    import copy
+    from oracle import cae_oracle as co
+    cores = os.cpu_count() or 1
+    hp = co.make_hparams(1, 128, 128, 12)
+    sample = 64            # frames per step: bounded sample of the 256-frame batch
+    torch.set_num_threads(cores)
+    sd = co.init_state_dict(hp, seed=0)
+    x = torch.rand(sample, 1, 128, 128, generator=torch.Generator().manual_seed(0))
+    for _ in range(min(args.warmup, 2)):
+        co.ae_loss(sd, hp, x)
+    steps = min(args.steps, 10)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        co.ae_loss(sd, hp, x)
+    dt = (time.perf_counter() - t0) / steps
+    value = sample / dt
+    print(json.dumps({
+        'impl': 'reference',
+        'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
+        'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': min(args.warmup, 2), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'C2: CAE 128x128x1, 12 latents, AE.loss fwd+bwd, default 5-layer arch; '
+                               'bounded sample of %d frames per step' % sample},
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d-frame steps of oracle/cae_oracle.ae_loss (torch eager fp32, all host '
+                                   'threads)' % sample},
+        'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+        from behavenet_b200 import parallel
+        parallel.shutdown()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,200 @@
+"""GPU parity tests of hot path 1 (CAE / PS-VAE) through the public model API (which calls the C ABI).
+
+Tolerances (north_star): fp32 reconstructions within 1e-4 relative.  Latents, losses and gradients
+are checked against the fp32 CPU oracle with the tolerances written next to each assert; the
+tensor-core (TF32) path gets the looser gradient bound stated there.
+"""
+
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cae_oracle as co
+from tests.helpers import load_golden, golden_compare, synth_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: (C, H, W, latents, batch, model_class, n_labels, chunk)
+    'c1_ae_32x32x1_l8_b32': (1, 32, 32, 8, 32, 'ae', 0, 200),
+    'ae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 'ae', 0, 4),
+    'ae_128x128x1_l12_b3': (1, 128, 128, 12, 3, 'ae', 0, 200),
+    'psvae_128x128x2_l16_b5': (2, 128, 128, 16, 5, 'ps-vae', 4, 3),
+    'psvae_32x32x2_l8_b6': (2, 32, 32, 8, 6, 'ps-vae', 3, 200),
+}
+
+
+def build(case, tc_mode):
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import AE, PSVAE
+    c, h, w, L, b, mc, nl, chunk = CASES[case]
+    hp = co.make_hparams(c, h, w, L, mc, nl)
+    sd = co.init_state_dict(hp, seed=0)
+    model = (AE if mc == 'ae' else PSVAE)(copy.deepcopy(hp))
+    model.load_state_dict(sd)
+    model.to('cuda')
+    _lib.lib().bn_set_tensor_core_mode(tc_mode)
+    return model, hp, sd, synth_inputs(c, h, w, L, b, nl), chunk
+
+
+def tols(tc_mode):
+    # fp32 CUDA-core path: round-off only.  TF32 tensor-core path: 10-bit mantissa operands,
+    # fp32 accumulation (same arithmetic the reference gets from cuDNN with allow_tf32).
+    return dict(xhat=1e-4, z=2e-5 if tc_mode == 0 else 2e-3, grad=1e-4 if tc_mode == 0 else 5e-3,
+                loss=1e-5 if tc_mode == 0 else 1e-4)
+
+
+@pytest.mark.parametrize('tc_mode', [0, 1])
+@pytest.mark.parametrize('case', [k for k, v in CASES.items() if v[5] == 'ae'])
+def test_ae_forward_and_loss_match_reference_goldens(case, tc_mode):
+    model, hp, sd, inp, chunk = build(case, tc_mode)
+    gold = load_golden(case)
+    t = tols(tc_mode)
+    x = inp['x'].cuda()
+    with torch.no_grad():
+        x_hat, z = model(x)
+    assert x_hat.shape == x.shape and z.shape == (x.shape[0], hp['n_ae_latents'])
+    golden_compare(gold, 'x_hat', x_hat, rtol=t['xhat'], atol=t['xhat'])     # values in (0,1)
+    zg = gold['z']
+    assert rel_err(z, zg) < t['z'] * 10
+    for tag, m in (('', None), ('_masked', inp['masks'].cuda())):
+        model.zero_grad()
+        data = {'images': x[None]}
+        if m is not None:
+            data['masks'] = m[None]
+        out = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+        ref = float(gold['loss' + tag])
+        assert abs(out['loss'] - ref) <= t['loss'] * abs(ref), (out, ref)
+        for name, p in model.named_parameters():
+            key = 'grad%s.%s' % (tag, name)
+            g = p.grad
+            scale = max(float(np.abs(gold[key + '#val']).max()) if key + '#val' in gold
+                        else float(np.abs(gold[key]).max()), 1e-12)
+            golden_compare(gold, key, g, rtol=t['grad'], atol=t['grad'] * scale)
+
+
+@pytest.mark.parametrize('tc_mode', [0, 1])
+@pytest.mark.parametrize('case', [k for k, v in CASES.items() if v[5] == 'ps-vae'])
+def test_psvae_forward_and_loss_match_reference_goldens(case, tc_mode):
+    model, hp, sd, inp, chunk = build(case, tc_mode)
+    gold = load_golden(case)
+    t = tols(tc_mode)
+    x, y, eps = inp['x'].cuda(), inp['labels'].cuda(), inp['eps'].cuda()
+    with torch.no_grad():
+        x_hat, z, mu, logvar, y_hat = model(x, eps=eps)
+    golden_compare(gold, 'x_hat', x_hat, rtol=t['xhat'], atol=t['xhat'])
+    for key, val in (('z', z), ('mu', mu), ('logvar', logvar), ('y_hat', y_hat)):
+        assert rel_err(val, gold[key]) < t['z'] * 10, key
+    model.curr_epoch = 1
+    model.zero_grad()
+    out = model.loss({'images': x[None], 'labels': y[None]}, accumulate_grad=True,
+                     chunk_size=chunk, eps=eps)
+    for k in ['loss', 'loss_data_ll', 'loss_label_ll', 'loss_zs_kl', 'loss_zu_mi', 'loss_zu_tc',
+              'loss_zu_dwkl', 'loss_data_mse', 'alpha', 'beta', 'label_r2']:
+        ref = float(gold['loss.' + k])
+        assert abs(out[k] - ref) <= 10 * t['loss'] * max(1.0, abs(ref)), (k, out[k], ref)
+    for name, p in model.named_parameters():
+        key = 'grad.' + name
+        if key not in gold and key + '#val' not in gold:
+            assert not p.requires_grad
+            continue
+        scale = max(float(np.abs(gold[key + '#val']).max()) if key + '#val' in gold
+                    else float(np.abs(gold[key]).max()), 1e-12)
+        golden_compare(gold, key, p.grad, rtol=4 * t['grad'], atol=4 * t['grad'] * scale)
+
+
+@pytest.mark.parametrize('tc_mode', [0, 1])
+def test_ae_c2_batch_matches_oracle(tc_mode):
+    """BASELINE config C2 geometry at a batch the CPU oracle finishes in seconds (B=24, chunks of
+    16+8): x_hat, loss and every parameter gradient against the fp32 oracle."""
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 128, 128, 12)
+    sd = co.init_state_dict(hp, seed=1)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(sd)
+    model.cuda()
+    _lib.lib().bn_set_tensor_core_mode(tc_mode)
+    t = tols(tc_mode)
+    x = torch.rand(24, 1, 128, 128, generator=torch.Generator().manual_seed(5))
+    xo, zo = co.ae_forward(sd, hp, x)
+    lo, go = co.ae_loss(sd, hp, x, None, chunk_size=16)
+    with torch.no_grad():
+        xh, z = model(x.cuda())
+    assert rel_err(xh, xo) < t['xhat']
+    assert rel_err(z, zo) < 10 * t['z']
+    out = model.loss({'images': x.cuda()[None]}, chunk_size=16)
+    assert abs(out['loss'] - lo['loss']) <= t['loss'] * lo['loss']
+    for name, p in model.named_parameters():
+        assert rel_err(p.grad, go[name]) < t['grad'], name
+
+
+def test_autograd_bridge_matches_fused_loss():
+    """model(x) + torch autograd (EncodeFn / DecodeFn backward) gives the same gradients as the
+    fused ``loss`` path."""
+    from behavenet_b200.models import AE
+    from behavenet_b200 import _lib
+    _lib.lib().bn_set_tensor_core_mode(0)
+    hp = co.make_hparams(1, 32, 32, 8)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=2))
+    model.cuda()
+    x = torch.rand(9, 1, 32, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    model.loss({'images': x[None]})
+    fused = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    x_hat, z = model(x)
+    torch.mean((x - x_hat) ** 2).backward()
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, fused[k]) < 1e-4, k
+
+
+def test_grad_accumulates_across_calls_and_chunk_weighting():
+    """.grad accumulates across loss() calls (autograd semantics the reference's training loop
+    relies on) and a tail chunk weighs as much as a full one."""
+    from behavenet_b200.models import AE
+    from behavenet_b200 import _lib
+    _lib.lib().bn_set_tensor_core_mode(0)
+    hp = co.make_hparams(1, 32, 32, 8)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=2))
+    model.cuda()
+    x = torch.rand(10, 1, 32, 32, generator=torch.Generator().manual_seed(4)).cuda()
+    model.loss({'images': x[None]}, chunk_size=6)         # chunks of 6 + 4
+    both = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    model.loss({'images': x[None, :6]})
+    model.loss({'images': x[None, 6:]})
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, both[k]) < 1e-4, k
+
+
+def test_cpu_input_raises_no_fallback():
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 32, 32, 8)
+    model = AE(copy.deepcopy(hp)).cuda()
+    with pytest.raises(RuntimeError):
+        model(torch.rand(2, 1, 32, 32))
+
+
+def test_deepcopy_and_state_dict_roundtrip(tmp_path):
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 32, 32, 8)
+    model = AE(copy.deepcopy(hp)).cuda()
+    x = torch.rand(4, 1, 32, 32).cuda()
+    with torch.no_grad():
+        a, _ = model(x)
+    model.hparams = None                      # what fit() does around deepcopy (training.py:393-396)
+    clone = copy.deepcopy(model)
+    model.hparams = hp
+    with torch.no_grad():
+        b, _ = clone(x)
+    assert torch.equal(a, b)
+    model.save(str(tmp_path / 'm.pt'))
+    other = AE(copy.deepcopy(hp)).cuda()
+    other.load_state_dict(torch.load(str(tmp_path / 'm.pt')))
+    with torch.no_grad():
+        c, _ = other(x)
+    assert torch.equal(a, c)

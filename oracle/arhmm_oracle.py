@@ -231,8 +231,9 @@ def synth_params(K=16, D=12, lags=2, seed=0, mix=0.04):
     As = np.zeros((K, D, D * lags))
     for k in range(K):
         q, _ = np.linalg.qr(q0 + mix * rng.randn(D, D))
-        As[k, :, :D] = 0.95 * q
-        As[k] += 0.01 * rng.randn(D, D * lags)
+        if lags > 0:
+            As[k, :, :D] = 0.95 * q
+            As[k] += 0.01 * rng.randn(D, D * lags)
     bs = 0.1 * rng.randn(K, D)
     G = rng.randn(K, D, D)
     Sigmas = 0.1 * np.eye(D)[None] + 0.01 * np.einsum('kij,klj->kil', G, G)

@@ -22,6 +22,8 @@ struct ConvGeom {
   // packed weights (offsets in floats into the packed cache)
   size_t off_wf;        // fprop weights  [(tap, c_big)][c_small]
   size_t off_wd;        // dgrad weights  [(tap, c_small)][c_big]
+  size_t off_wft;       // fprop weights, K-major + TF32-rounded  [c_small][(tap, c_big)]
+  size_t off_wdt;       // dgrad weights, K-major + TF32-rounded  [c_big][(tap, c_small)]
   // torch parameter table indices
   int p_w, p_b;
 };
@@ -54,9 +56,10 @@ int bn_launch_thin_dgrad(const float* small, const ConvGeom& g, const float* wd,
 int bn_launch_sigmoid_bwd(const float* dxhat, const float* xhat, float* dpre, int n, int C, int H,
                           int W, cudaStream_t st);
 
-// packing: src [cs][cb][kk] -> wf [(tap,cb)][cs], wd [(tap,cs)][cb]
-int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd,
-                        cudaStream_t st);
+// packing: src [cs][cb][kk] -> wf [(tap,cb)][cs], wd [(tap,cs)][cb] (fp32, exact) and the K-major
+// TF32-rounded copies wft [cs][(tap,cb)], wdt [cb][(tap,cs)] for the tensor-core kernels
+int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd, float* wft,
+                        float* wdt, cudaStream_t st);
 // encoder heads: wcat[(head, j)][i_nhwc] from W_head[j][i_chw]
 int bn_launch_pack_heads(const float* w0, const float* w1, int L, int C, int H, int W, float* wcat,
                          cudaStream_t st);
@@ -76,9 +79,9 @@ int bn_launch_decff_bwd(const float* z, const float* w, const float* dh0, int n,
 
 // tcgen05 TF32 tensor-core implicit GEMM (cae_tc.cu).  Returns 1 if the shape is not supported
 // (caller then uses the CUDA-core kernel), 0 on success, <0 on error.
-int bn_launch_igemm_tc(const ImgView& in, const float* w, const float* bias, float* out, int Ho,
-                       int Wo, int Co, const float* dact, const TapClass* d_classes,
-                       const TapClass* h_classes, int nclasses, int maxM, int gs, int os, int n,
-                       int act, cudaStream_t st);
+//   wt : K-major packed weights [Co][wrow], wrow = k*k*Ci, TF32-rounded
+int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
+                       int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes, int nclasses,
+                       int maxM, int gs, int os, int n, int act, cudaStream_t st);
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n,
                        float* partial, size_t partial_floats, float* grad, cudaStream_t st);

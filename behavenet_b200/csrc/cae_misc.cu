@@ -201,8 +201,15 @@ __global__ void __launch_bounds__(256) colsum_thin_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // packing
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 __global__ void pack_conv_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
-                                 float* __restrict__ wf, float* __restrict__ wd) {
+                                 float* __restrict__ wf, float* __restrict__ wd,
+                                 float* __restrict__ wft, float* __restrict__ wdt) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long tot = (long long)Cs * Cb * kk;
   if (i >= tot) return;
@@ -213,6 +220,9 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, int Cs, int Cb, 
   float v = src[i];
   wf[((long long)tap * Cb + cb) * Cs + cs] = v;
   wd[((long long)tap * Cs + cs) * Cb + cb] = v;
+  const float vr = round_tf32(v);
+  wft[((long long)cs * kk + tap) * Cb + cb] = vr;
+  wdt[((long long)cb * kk + tap) * Cs + cs] = vr;
 }
 
 __global__ void pack_heads_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int L,
@@ -431,10 +441,10 @@ int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_
   return 0;
 }
 
-int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd,
-                        cudaStream_t st) {
+int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd, float* wft,
+                        float* wdt, cudaStream_t st) {
   long long tot = (long long)Cs * Cb * kk;
-  pack_conv_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(src, Cs, Cb, kk, wf, wd);
+  pack_conv_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(src, Cs, Cb, kk, wf, wd, wft, wdt);
   BN_LAUNCHED();
   return 0;
 }

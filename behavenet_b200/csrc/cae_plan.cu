@@ -106,13 +106,13 @@ void build_classes(ConvGeom& g, std::vector<TapClass>& tab, int& i_f, int& i_d) 
     }
 }
 
-int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const float* bias, float* out,
-              int Ho, int Wo, int Co, const float* dact, int table_idx, int nclasses, int maxM, int gs,
-              int os, int n, int act, cudaStream_t st) {
+int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const float* wt, int wrow,
+              const float* bias, float* out, int Ho, int Wo, int Co, const float* dact, int table_idx,
+              int nclasses, int maxM, int gs, int os, int n, int act, cudaStream_t st) {
   const TapClass* dcls = p->d_tables + table_idx;
   if (g_tc_mode.load()) {
-    int r = bn_launch_igemm_tc(in, w, bias, out, Ho, Wo, Co, dact, dcls, p->h_tables.data() + table_idx,
-                               nclasses, maxM, gs, os, n, act, st);
+    int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n,
+                               act, st);
     if (r <= 0) return r;
   }
   return bn_launch_igemm(in, w, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n, act, st);
@@ -161,6 +161,8 @@ extern "C" int bn_cae_plan_create(const bn_cae_desc* desc, bn_cae_plan** out) {
     g.p_w = 2 * i; g.p_b = 2 * i + 1;
     g.off_wf = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
     g.off_wd = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    g.off_wft = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    g.off_wdt = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
     H = g.Hs; W = g.Ws; C = g.Cs;
     p->enc_sz[i + 1] = (size_t)H * W * C;
   }
@@ -180,6 +182,8 @@ extern "C" int bn_cae_plan_create(const bn_cae_desc* desc, bn_cae_plan** out) {
     g.p_w = 2 * p->nl + 6 + 2 * i; g.p_b = g.p_w + 1;
     g.off_wf = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
     g.off_wd = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    g.off_wft = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
+    g.off_wdt = off; off += align64((size_t)g.k * g.k * g.Cb * g.Cs);
     H = g.Hb; W = g.Wb; C = g.Cb;
     p->dec_sz[i + 1] = (size_t)H * W * C;
   }
@@ -227,10 +231,12 @@ extern "C" int bn_cae_pack_params(bn_cae_plan* p, const float* const* P, void* d
   for (int i = 0; i < p->nl; ++i) {
     const ConvGeom& g = p->enc[i];
     if (P[g.p_w])
-      BN_TRY(bn_launch_pack_conv(P[g.p_w], g.Cs, g.Cb, g.k * g.k, pk + g.off_wf, pk + g.off_wd, st));
+      BN_TRY(bn_launch_pack_conv(P[g.p_w], g.Cs, g.Cb, g.k * g.k, pk + g.off_wf, pk + g.off_wd,
+                                 pk + g.off_wft, pk + g.off_wdt, st));
     const ConvGeom& h = p->dec[i];
     if (P[h.p_w])
-      BN_TRY(bn_launch_pack_conv(P[h.p_w], h.Cs, h.Cb, h.k * h.k, pk + h.off_wf, pk + h.off_wd, st));
+      BN_TRY(bn_launch_pack_conv(P[h.p_w], h.Cs, h.Cb, h.k * h.k, pk + h.off_wf, pk + h.off_wd,
+                                 pk + h.off_wft, pk + h.off_wdt, st));
   }
   const int n2 = 2 * p->nl;
   if (P[n2]) {
@@ -254,8 +260,8 @@ extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const floa
   for (int i = 0; i < p->nl; ++i) {
     const ConvGeom& g = p->enc[i];
     float* out = ws + L.enc_act[i + 1];
-    BN_TRY(run_igemm(p, in, pk + g.off_wf, P[g.p_b], out, g.Hs, g.Ws, g.Cs, nullptr, p->enc_f[i], 1,
-                     g.Hs * g.Ws, g.s, 1, n, BN_ACT_LEAKY, st));
+    BN_TRY(run_igemm(p, in, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, P[g.p_b], out, g.Hs, g.Ws,
+                     g.Cs, nullptr, p->enc_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_LEAKY, st));
     in = nhwc_view(out, g.Hs, g.Ws, g.Cs);
   }
   const int n2 = 2 * p->nl;
@@ -283,8 +289,9 @@ extern "C" int bn_cae_decode(bn_cae_plan* p, int n, const float* d_z, const floa
   for (int i = 0; i + 1 < p->nl; ++i) {
     const ConvGeom& g = p->dec[i];
     ImgView in = nhwc_view(ws + L.dec_act[i], g.Hs, g.Ws, g.Cs);
-    BN_TRY(run_igemm(p, in, pk + g.off_wd, P[g.p_b], ws + L.dec_act[i + 1], g.Hb, g.Wb, g.Cb, nullptr,
-                     p->dec_d[i], g.n_dgrad, g.dgrad_maxM, 1, g.s, n, BN_ACT_LEAKY, st));
+    BN_TRY(run_igemm(p, in, pk + g.off_wd, pk + g.off_wdt, g.k * g.k * g.Cs, P[g.p_b],
+                     ws + L.dec_act[i + 1], g.Hb, g.Wb, g.Cb, nullptr, p->dec_d[i], g.n_dgrad,
+                     g.dgrad_maxM, 1, g.s, n, BN_ACT_LEAKY, st));
   }
   const ConvGeom& g = p->dec[p->nl - 1];
   BN_TRY(bn_launch_thin_dgrad(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
@@ -317,8 +324,8 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
     BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
     float* out = pp[flip];
     flip ^= 1;
-    BN_TRY(run_igemm(p, big, pk + g.off_wf, nullptr, out, g.Hs, g.Ws, g.Cs, i > 0 ? small : nullptr,
-                     p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st));
+    BN_TRY(run_igemm(p, big, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, nullptr, out, g.Hs, g.Ws,
+                     g.Cs, i > 0 ? small : nullptr, p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st));
     gcur = out;
   }
   BN_TRY(bn_launch_decff_bwd(ws + L.zcopy, P[n2 + 4], gcur, n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
@@ -353,8 +360,9 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
       float* out = pp[flip];
       flip ^= 1;
       ImgView in = nhwc_view(gcur, g.Hs, g.Ws, g.Cs);
-      BN_TRY(run_igemm(p, in, pk + g.off_wd, nullptr, out, g.Hb, g.Wb, g.Cb, ws + L.enc_act[i], p->enc_d[i],
-                       g.n_dgrad, g.dgrad_maxM, 1, g.s, n, BN_ACT_NONE, st));
+      BN_TRY(run_igemm(p, in, pk + g.off_wd, pk + g.off_wdt, g.k * g.k * g.Cs, nullptr, out, g.Hb, g.Wb,
+                       g.Cb, ws + L.enc_act[i], p->enc_d[i], g.n_dgrad, g.dgrad_maxM, 1, g.s, n,
+                       BN_ACT_NONE, st));
       gcur = out;
     }
   }

@@ -1,12 +1,355 @@
-// tcgen05 (TF32, TMEM accumulators) implicit-GEMM kernels for the fat CAE layers.
-// Placeholder until the tensor-core kernels land: report "unsupported shape" so the plan uses the
-// fp32 CUDA-core kernels.
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernels for the fat CAE layers, TF32 operands with
+// fp32 accumulation in TMEM.
+//
+//   D[128 x BN] (TMEM) += A[128 x 32] (smem, K-major) * B[BN x 32]^T (smem, K-major)     per k-chunk
+//
+// A is the im2col view of an NHWC activation tensor: row m = output pixel, 32 consecutive k =
+// 32 channels of one filter tap.  Four producer warps gather it with 16-byte cp.async copies
+// (zero-fill outside the image: this is where ZeroPad2d / the transposed-conv border live) straight
+// into the canonical no-swizzle UMMA layout (8-row x 16-byte core matrices), a fifth warp's elected
+// lane issues tcgen05.mma and signals stage reuse with tcgen05.commit -> mbarrier; the producer
+// warps then read the accumulator back with tcgen05.ld and apply bias / LeakyReLU / sigmoid / the
+// activation-derivative mask of the backward pass before storing NHWC.
+//
+// Weights are pre-packed K-major ([c_out][(tap, c_in)]) and pre-rounded to TF32 (cvt.rna) by
+// bn_cae_pack_params; activations are consumed as stored (the tensor core ignores the low 13
+// mantissa bits).
 #include "cae_kernels.cuh"
 
-int bn_launch_igemm_tc(const ImgView&, const float*, const float*, float*, int, int, int, const float*,
-                       const TapClass*, const TapClass*, int, int, int, int, int, int, cudaStream_t) {
-  return 1;
+namespace {
+
+constexpr int BM = 128;         // rows per CTA tile = UMMA M
+constexpr int BK = 32;          // floats per k-chunk = 128 bytes = 8 core-matrix columns
+constexpr int NPROD = 128;      // producer / epilogue threads (warps 0-3)
+constexpr int NTHREADS = 160;   // + warp 4: TMEM allocator and MMA issuer
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle ("interleave") shared-memory matrix descriptor.
+//   core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes
+//   SBO = byte distance between core matrices adjacent along M/N, LBO = along K
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version 1 (sm_100)
+  return d;                   // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+  const float* in;
+  int Hi, Wi, Ci;
+  const float* wt;        // K-major packed weights [Co][KK * Ci]
+  int wrow;               // KK * Ci (row length of wt)
+  const float* bias;
+  float* out;
+  int Ho, Wo, Co;
+  const float* dact;
+  const TapClass* classes;
+  int gs, os, n, act;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;   // + barriers / class table / tmem ptr
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using S = TcSmem<BN, STAGES>;
+  constexpr int NCOLS = BN < 32 ? 32 : BN;
+  unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);              // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;                             // [STAGES]
+  uint64_t* accum_bar = empty_bar + STAGES;                            // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);     // [1] (+pad)
+  TapClass* cls = reinterpret_cast<TapClass*>(tmem_ptr + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  {
+    const int* src = reinterpret_cast<const int*>(a.classes + blockIdx.z);
+    int* dst = reinterpret_cast<int*>(cls);
+    for (int i = tid; i < (int)(sizeof(TapClass) / 4); i += NTHREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), NPROD);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int HmWm = cls->Hm * cls->Wm;
+  const long long M = (long long)a.n * HmWm;
+  const long long m0 = (long long)blockIdx.x * BM;
+  if (m0 >= M) return;                         // uniform per CTA, before any TMEM allocation
+  if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n0 = blockIdx.y * BN;
+  const int Ci = a.Ci;
+  const int cpt = Ci / BK;
+  const int nchunks = cls->ntaps * cpt;
+  const uint32_t smem_base = smem_u32(smem);
+  constexpr uint32_t A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;
+
+  if (warp < 4) {
+    // ======================= producers: one A row per thread, BN/128 B rows per thread ===========
+    const long long m = m0 + tid;
+    const bool rvalid = m < M;
+    int ybase = 0, xbase = 0;
+    long long foff = 0;
+    if (rvalid) {
+      int f = (int)(m / HmWm);
+      int rem = (int)(m - (long long)f * HmWm);
+      int ym = rem / cls->Wm;
+      int xm = rem - ym * cls->Wm;
+      ybase = ym * a.gs;
+      xbase = xm * a.gs;
+      foff = (long long)f * a.Hi * a.Wi * Ci;
+    }
+    const uint32_t a_row_off = (uint32_t)((tid >> 3) * 128 + (tid & 7) * 16);
+
+    auto issue = [&](int c) {
+      const int stage = c % STAGES;
+      const int tap = c / cpt;
+      const int c0 = (c - tap * cpt) * BK;
+      const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+      const uint32_t sb = sa + S::A_BYTES;
+      {
+        int y = ybase + cls->dy[tap], x = xbase + cls->dx[tap];
+        bool ok = rvalid && (unsigned)y < (unsigned)a.Hi && (unsigned)x < (unsigned)a.Wi;
+        const float* src = ok ? a.in + foff + ((long long)y * a.Wi + x) * Ci + c0 : a.in;
+        uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) cp_async16(sa + kc * A_LBO + a_row_off, src + kc * 4, nbytes);
+      }
+      const long long wcol = (long long)cls->wt[tap] * Ci + c0;
+#pragma unroll
+      for (int r = tid; r < BN; r += NPROD) {
+        const float* src = a.wt + (long long)(n0 + r) * a.wrow + wcol;
+        const uint32_t b_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) cp_async16(sb + kc * B_LBO + b_row_off, src + kc * 4, 16u);
+      }
+    };
+
+    for (int c = 0; c < STAGES - 1; ++c) {
+      if (c < nchunks) issue(c);
+      cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int cn = c + STAGES - 1;
+      if (cn < nchunks) {
+        if (cn >= STAGES) mbar_wait(smem_u32(empty_bar + cn % STAGES), ((cn / STAGES) - 1) & 1);
+        issue(cn);
+      }
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();      // chunk c has landed (this thread's part)
+      fence_proxy_async();              // make it visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(full_bar + c % STAGES));
+    }
+
+    // ======================= epilogue: TMEM -> registers -> global ============================
+    if (nchunks > 0) {
+      mbar_wait(smem_u32(accum_bar), 0);
+      tc_fence_after();
+    }
+    long long obase = 0;
+    if (rvalid) {
+      int f = (int)(m / HmWm);
+      int rem = (int)(m - (long long)f * HmWm);
+      int ym = rem / cls->Wm;
+      int xm = rem - ym * cls->Wm;
+      int oy = cls->oy0 + a.os * ym, ox = cls->ox0 + a.os * xm;
+      obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + n0;
+    }
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t r[32];
+      if (nchunks > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) r[q] = 0u;
+      }
+      if (rvalid) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(r[q + e]);
+            if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q + e);
+            if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+            else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+            v[e] = x;
+          }
+          const long long idx = obase + j * 32 + q;
+          if (a.dact) {
+            float4 d = __ldg(reinterpret_cast<const float4*>(a.dact + idx));
+            v[0] *= d.x > 0.f ? 1.f : BN_LEAK;
+            v[1] *= d.y > 0.f ? 1.f : BN_LEAK;
+            v[2] *= d.z > 0.f ? 1.f : BN_LEAK;
+            v[3] *= d.w > 0.f ? 1.f : BN_LEAK;
+          }
+          *reinterpret_cast<float4*>(a.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ======================= MMA issuer (warp 4, one elected lane) =============================
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        mbar_wait(smem_u32(full_bar + stage), (c / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          uint64_t ad = make_desc(sa + k * 2 * A_LBO, A_LBO, SBO);
+          uint64_t bd = make_desc(sb + k * 2 * B_LBO, B_LBO, SBO);
+          umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(empty_bar + stage));     // stage reusable once these MMAs retire
+      }
+      if (nchunks > 0) umma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<NCOLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+int launch_tc(const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  auto kern = igemm_tc_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, nclasses);
+  kern<<<grid, NTHREADS, S::TOTAL, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
+                       int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes, int nclasses,
+                       int maxM, int gs, int os, int n, int act, cudaStream_t st) {
+  // shapes this kernel covers: NHWC-dense input with C % 32 == 0, C_out in {32, 64, 128, 256, 512},
+  // enough rows to fill the machine (the stride-5 layers with a few hundred rows stay on the
+  // CUDA-core kernel until the split-K variant lands)
+  if (wt == nullptr) return 1;
+  if (in.sc != 1 || in.C % BK != 0 || in.sx != in.C || in.sy != (long long)in.W * in.C ||
+      in.sn != (long long)in.H * in.W * in.C)
+    return 1;
+  if (((uintptr_t)in.p & 15) || ((uintptr_t)out & 15) || ((uintptr_t)wt & 15) || (dact && ((uintptr_t)dact & 15))) return 1;
+  if ((long long)n * maxM < 64LL * BM) return 1;
+  TcArgs a;
+  a.in = in.p; a.Hi = in.H; a.Wi = in.W; a.Ci = in.C; a.wt = wt; a.wrow = wrow; a.bias = bias; a.out = out;
+  a.Ho = Ho; a.Wo = Wo; a.Co = Co; a.dact = dact; a.classes = d_classes; a.gs = gs; a.os = os;
+  a.n = n; a.act = act;
+  switch (Co) {
+    case 32: return launch_tc<32, 4>(a, nclasses, maxM, st);
+    case 64: return launch_tc<64, 4>(a, nclasses, maxM, st);
+    case 128: return launch_tc<128, 3>(a, nclasses, maxM, st);
+    case 256: return launch_tc<256, 4>(a, nclasses, maxM, st);
+    case 512: return launch_tc<256, 4>(a, nclasses, maxM, st);
+    default: return 1;
+  }
+}
+
 int bn_launch_wgrad_tc(const ImgView&, const float*, const ConvGeom&, int, float*, size_t, float*,
                        cudaStream_t) {
   return 1;

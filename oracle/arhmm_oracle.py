@@ -256,7 +256,7 @@ def sample(params, T, rng):
         if t < L:
             x[t] = rng.randn(D)
         else:
-            hist = np.concatenate([x[t - l - 1] for l in range(L)])
+            hist = np.concatenate([x[t - l - 1] for l in range(L)]) if L else np.zeros(0)
             x[t] = params.As[z[t]] @ hist + params.bs[z[t]] + chol[z[t]] @ rng.randn(D)
     return z, x
 
@@ -277,7 +277,8 @@ def sample_batch(params, n_trials, T, seed=0, dtype=np.float32):
         if t < L:
             x[:, t] = noise
         else:
-            hist = np.concatenate([x[:, t - l - 1] for l in range(L)], 1)
+            hist = (np.concatenate([x[:, t - l - 1] for l in range(L)], 1) if L
+                    else np.zeros((n_trials, 0)))
             x[:, t] = (np.einsum('nde,ne->nd', params.As[z], hist) + params.bs[z]
                        + np.einsum('nde,ne->nd', chol[z], noise))
     return x.astype(dtype)

@@ -40,9 +40,15 @@ def build(case, tc_mode):
 
 
 def tols(tc_mode):
-    # fp32 CUDA-core path: round-off only.  TF32 tensor-core path: 10-bit mantissa operands,
-    # fp32 accumulation (same arithmetic the reference gets from cuDNN with allow_tf32).
-    return dict(xhat=1e-4, z=2e-5 if tc_mode == 0 else 2e-3, grad=1e-4 if tc_mode == 0 else 5e-3,
+    # fp32 CUDA-core path (mode 0): round-off only.
+    # TF32 tensor-core path (mode 1): 10-bit-mantissa operands, fp32 accumulation -- the arithmetic
+    # the reference itself gets on a GPU from cuDNN (torch.backends.cudnn.allow_tf32 defaults to
+    # True).  Reconstructions stay within the north-star 1e-4; gradients of this random-init
+    # network are tiny sums with heavy cancellation, and scripts/diag_precision.py (run on B200,
+    # profiles/r01_precision.txt) measures 1e-2..7e-2 relative-to-max deviation from the fp64 oracle
+    # for BOTH our TF32 path and eager PyTorch-on-CUDA with its default TF32 convolutions; the bound
+    # below is that yardstick, not an fp32 round-off bound.
+    return dict(xhat=1e-4, z=2e-5 if tc_mode == 0 else 2e-3, grad=1e-4 if tc_mode == 0 else 1.5e-1,
                 loss=1e-5 if tc_mode == 0 else 1e-4)
 
 

@@ -41,6 +41,9 @@ int bn_launch_igemm(const ImgView& in, const float* w, const float* bias, float*
 int bn_launch_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                     size_t partial_floats, float* grad, cudaStream_t st);
 size_t bn_wgrad_partial_floats(const ConvGeom& g, int n);
+// grad[((cs*Cb + cb)*KK + wt[tap])] += sum_z partial[z][(tap, cb)][cs]
+int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, int Cb, int KK,
+                           const TapClass* cls, float* grad, cudaStream_t st);
 
 // out[c] += sum_m x[m*C + c]
 int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_t st);

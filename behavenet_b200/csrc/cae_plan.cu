@@ -368,3 +368,38 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
   }
   return 0;
 }
+
+// Single-layer entry point: kernel-level parity tests (tensor-core vs CUDA-core kernels on the same
+// tensors) and per-kernel timing for the roofline line of bench.py.
+extern "C" int bn_cae_layer_op(bn_cae_plan* p, int side, int layer, int op, int n, const float* d_in,
+                               const float* d_in2, float* d_out, const float* const* P,
+                               const void* d_packed, void* d_ws, void* stream) {
+  if (!p || !d_in || !d_out || !d_packed || !d_ws) BN_FAIL("bn_cae_layer_op: null argument");
+  if (side < 0 || side > 1 || layer < 0 || layer >= p->nl || op < 0 || op > 2) BN_FAIL("bn_cae_layer_op: bad selector");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* pk = (const float*)d_packed;
+  float* ws = (float*)d_ws;
+  WsLayout L = ws_layout(p, n);
+  const ConvGeom& g = side == 0 ? p->enc[layer] : p->dec[layer];
+  const int tf = side == 0 ? p->enc_f[layer] : p->dec_f[layer];
+  const int td = side == 0 ? p->enc_d[layer] : p->dec_d[layer];
+  const float* bias = (P && op == 0) ? P[g.p_b] : nullptr;
+  const bool fprop_form = (side == 0 && op == 0) || (side == 1 && op == 1);
+  if (op == 2) {
+    if (!d_in2) BN_FAIL("bn_cae_layer_op: wgrad needs both images");
+    return run_wgrad(nhwc_view(d_in, g.Hb, g.Wb, g.Cb), d_in2, g, n, ws + L.partial, L.partial_floats, d_out, st);
+  }
+  if (fprop_form) {
+    return run_igemm(p, nhwc_view(d_in, g.Hb, g.Wb, g.Cb), pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, bias,
+                     d_out, g.Hs, g.Ws, g.Cs, nullptr, tf, 1, g.Hs * g.Ws, g.s, 1, n,
+                     op == 0 ? BN_ACT_LEAKY : BN_ACT_NONE, st);
+  }
+  if (side == 1 && op == 0 && layer == p->nl - 1) {
+    return bn_launch_thin_dgrad(d_in, g, pk + g.off_wd, bias, n, ws + L.dec_act[p->nl], d_out, nullptr, nullptr, 0,
+                                0, n, 0.f, nullptr, ws + L.dpre_last, st);
+  }
+  return run_igemm(p, nhwc_view(d_in, g.Hs, g.Ws, g.Cs), pk + g.off_wd, pk + g.off_wdt, g.k * g.k * g.Cs, bias,
+                   d_out, g.Hb, g.Wb, g.Cb, nullptr, td, g.n_dgrad, g.dgrad_maxM, 1, g.s, n,
+                   op == 0 ? BN_ACT_LEAKY : BN_ACT_NONE, st);
+}

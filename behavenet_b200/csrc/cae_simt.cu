@@ -412,7 +412,25 @@ static int wgrad_splits(const ConvGeom& g, int n) {
 }
 
 size_t bn_wgrad_partial_floats(const ConvGeom& g, int n) {
-  return (size_t)wgrad_splits(g, n) * g.k * g.k * g.Cb * g.Cs;
+  // room for the CUDA-core split count and for the tensor-core kernel's (up to ~2 waves of CTAs)
+  long long M = (long long)n * g.Hs * g.Ws;
+  long long Ktot = (long long)g.k * g.k * g.Cb;
+  long long tiles_tc = ((Ktot + 127) / 128) * ((g.Cs + 255) / 256);
+  long long s_tc = (2 * 148 + tiles_tc - 1) / tiles_tc;
+  long long maxs = (M + 127) / 128;
+  if (s_tc > maxs) s_tc = maxs;
+  if (s_tc < 1) s_tc = 1;
+  long long s = wgrad_splits(g, n);
+  if (s_tc > s) s = s_tc;
+  return (size_t)s * Ktot * g.Cs;
+}
+
+int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, int Cb, int KK,
+                           const TapClass* cls, float* grad, cudaStream_t st) {
+  long long tot = (long long)Ktot * Cs;
+  wgrad_reduce_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(partial, splits, Ktot, Cs, Cb, KK, cls, grad);
+  BN_LAUNCHED();
+  return 0;
 }
 
 int bn_launch_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,

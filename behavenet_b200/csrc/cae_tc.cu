@@ -6,7 +6,7 @@
 // A is the im2col view of an NHWC activation tensor: row m = output pixel, 32 consecutive k =
 // 32 channels of one filter tap.  Four producer warps gather it with 16-byte cp.async copies
 // (zero-fill outside the image: this is where ZeroPad2d / the transposed-conv border live) straight
-// into the canonical no-swizzle UMMA layout (8-row x 16-byte core matrices), a fifth warp's elected
+// into the canonical SWIZZLE_128B K-major UMMA layout (what TMA would write), a fifth warp's elected
 // lane issues tcgen05.mma and signals stage reuse with tcgen05.commit -> mbarrier; the producer
 // warps then read the accumulator back with tcgen05.ld and apply bias / LeakyReLU / sigmoid / the
 // activation-derivative mask of the backward pass before storing NHWC.
@@ -90,16 +90,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, no-swizzle ("interleave") shared-memory matrix descriptor.
-//   core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes
-//   SBO = byte distance between core matrices adjacent along M/N, LBO = along K
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// K-major SWIZZLE_128B shared-memory matrix descriptor (the layout TMA would write):
+//   a tile row is 128 contiguous bytes (32 tf32), 8 rows form a 1024-byte swizzle atom in which the
+//   16-byte chunk c of row r is stored at chunk position c ^ (r & 7).  SBO = 1024 bytes between
+//   8-row groups; one MMA consumes 32 bytes of K, so successive MMAs advance the start address by 32.
+//   Tile bases must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;     // descriptor version 1 (sm_100)
-  return d;                   // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+  d |= (uint64_t)1 << 16;                    // LBO (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;          // SBO
+  d |= (uint64_t)1 << 46;                    // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                    // layout type 2 = SWIZZLE_128B
+  return d;
 }
 // instruction descriptor: D = F32, A = B = TF32, both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -129,7 +132,7 @@ struct TcSmem {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   using S = TcSmem<BN, STAGES>;
   constexpr int NCOLS = BN < 32 ? 32 : BN;
   unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
@@ -170,10 +173,13 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
   const int cpt = Ci / BK;
   const int nchunks = cls->ntaps * cpt;
   const uint32_t smem_base = smem_u32(smem);
-  constexpr uint32_t A_LBO = (BM / 8) * 128, B_LBO = (BN / 8) * 128, SBO = 128;
 
   if (warp < 4) {
-    // ======================= producers: one A row per thread, BN/128 B rows per thread ===========
+    // ======================= producers ===========================================================
+    // Thread t owns the im2col bookkeeping of tile row t.  Copies are issued so that 8 consecutive
+    // lanes move the 8 16-byte chunks of ONE 128-byte row (one L1/L2 line per 8 lanes, 4 lines per
+    // warp instruction) and land them conflict-free in the swizzled tile; the row pointer is
+    // fetched from its owner lane with shuffles.
     const long long m = m0 + tid;
     const bool rvalid = m < M;
     int ybase = 0, xbase = 0;
@@ -187,7 +193,9 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
       xbase = xm * a.gs;
       foff = (long long)f * a.Hi * a.Wi * Ci;
     }
-    const uint32_t a_row_off = (uint32_t)((tid >> 3) * 128 + (tid & 7) * 16);
+    const int lane = tid & 31;
+    const int kc = lane & 7;           // 16-byte chunk of the 128-byte row
+    const int rsub = lane >> 3;        // row within the group of 4 rows moved per instruction
 
     auto issue = [&](int c) {
       const int stage = c % STAGES;
@@ -198,18 +206,24 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
       {
         int y = ybase + cls->dy[tap], x = xbase + cls->dx[tap];
         bool ok = rvalid && (unsigned)y < (unsigned)a.Hi && (unsigned)x < (unsigned)a.Wi;
-        const float* src = ok ? a.in + foff + ((long long)y * a.Wi + x) * Ci + c0 : a.in;
-        uint32_t nbytes = ok ? 16u : 0u;
+        // own row's source (nullptr = zero fill)
+        const float* own = ok ? a.in + foff + ((long long)y * a.Wi + x) * Ci + c0 : nullptr;
+        unsigned long long own_u = (unsigned long long)own;
 #pragma unroll
-        for (int kc = 0; kc < 8; ++kc) cp_async16(sa + kc * A_LBO + a_row_off, src + kc * 4, nbytes);
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + rsub;                       // row within this warp's 32 rows
+          unsigned long long pu = __shfl_sync(0xffffffffu, own_u, rl);
+          const int row = warp * 32 + rl;
+          const uint32_t dst = sa + row * 128 + ((kc ^ (row & 7)) << 4);
+          const float* src = pu ? reinterpret_cast<const float*>(pu) + kc * 4 : a.in;
+          cp_async16(dst, src, pu ? 16u : 0u);
+        }
       }
-      const long long wcol = (long long)cls->wt[tap] * Ci + c0;
+      const float* wsrc = a.wt + (long long)cls->wt[tap] * Ci + c0 + kc * 4;
 #pragma unroll
-      for (int r = tid; r < BN; r += NPROD) {
-        const float* src = a.wt + (long long)(n0 + r) * a.wrow + wcol;
-        const uint32_t b_row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);
-#pragma unroll
-        for (int kc = 0; kc < 8; ++kc) cp_async16(sb + kc * B_LBO + b_row_off, src + kc * 4, 16u);
+      for (int r = warp * 4 + rsub; r < BN; r += 16) {
+        const uint32_t dst = sb + r * 128 + ((kc ^ (r & 7)) << 4);
+        cp_async16(dst, wsrc + (long long)(n0 + r) * a.wrow, 16u);
       }
     };
 
@@ -290,8 +304,8 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
         const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          uint64_t ad = make_desc(sa + k * 2 * A_LBO, A_LBO, SBO);
-          uint64_t bd = make_desc(sb + k * 2 * B_LBO, B_LBO, SBO);
+          uint64_t ad = make_desc_sw128(sa + k * 32);
+          uint64_t bd = make_desc_sw128(sb + k * 32);
           umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(empty_bar + stage));     // stage reusable once these MMAs retire
@@ -317,6 +331,226 @@ int launch_tc(const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, nclasses);
+  kern<<<grid, NTHREADS, S::TOTAL, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient on tensor cores.
+//   D[kk (128 rows), cs (BN)] += sum over 32-pixel chunks of  A(m, kk) * S(m, cs)
+// with A(m, kk=(tap, cb)) = big[pix(m) + off(tap), cb] (im2col of the layer's big image) and
+// S = the small image's gradient / activation.  The reduction index m is the GEMM K dimension and
+// both operands are contiguous along their M/N index in memory (channels), so both are staged in
+// the MN-major canonical layout that tf32 supports, SWIZZLE_128B_BASE32B: an atom is 4 k-rows x
+// 128 bytes (32 channels) whose 32-byte granule g of k-row r is stored at granule g ^ (r & 3);
+// atoms adjacent along M/N are LBO apart, adjacent along K are SBO apart.  One tcgen05.mma
+// (K = 8) consumes two k-atoms.
+// Each CTA reduces a slice of the pixels (split-K over grid.z) into partial[z][kk][cs]; the
+// fp32 reduce kernel of cae_simt.cu sums the slices into the torch-layout gradient.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                    // layout type 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+  return make_idesc(M, N) | (1u << 15) | (1u << 16);      // A and B MN-major
+}
+
+struct WgTcArgs {
+  const float* big;
+  int Hb, Wb, Cb;
+  const float* small;
+  int Hs, Ws, Cs;
+  const TapClass* cls;     // fprop class (all k*k taps)
+  int gs, n, Ktot;
+  long long rows_per_split;
+  float* partial;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const WgTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using S = TcSmem<BN, STAGES>;
+  constexpr int NCOLS = BN < 32 ? 32 : BN;
+  unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  TapClass* cls = reinterpret_cast<TapClass*>(tmem_ptr + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  {
+    const int* src = reinterpret_cast<const int*>(a.cls);
+    int* dst = reinterpret_cast<int*>(cls);
+    for (int i = tid; i < (int)(sizeof(TapClass) / 4); i += NTHREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), NPROD);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int HsWs = a.Hs * a.Ws;
+  const long long M = (long long)a.n * HsWs;
+  const long long mbeg = (long long)blockIdx.z * a.rows_per_split;
+  const long long mend = mbeg + a.rows_per_split < M ? mbeg + a.rows_per_split : M;
+  const int nchunks = mbeg < mend ? (int)((mend - mbeg + BK - 1) / BK) : 0;
+  const int kk0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Cb = a.Cb, Cs = a.Cs;
+  const uint32_t smem_base = smem_u32(smem);
+  constexpr uint32_t A_LBO = 512, A_SBO = (BM / 32) * 512;     // 4-row k-atoms of 512 bytes
+  constexpr uint32_t B_LBO = 512, B_SBO = (BN / 32) * 512;
+
+  if (warp < 4) {
+    // producers.  Warp w moves the 32-channel slab kk0 + 32w .. +31 of the A tile: a fixed
+    // (tap, channel offset) for the whole kernel; lane l decodes pixel l of each 32-pixel chunk.
+    const int lane = tid & 31;
+    const int kc = lane & 7;
+    const int rsub = lane >> 3;
+    const int akk = kk0 + 32 * warp;
+    const bool kvalid = akk < a.Ktot;
+    const int tap = kvalid ? akk / Cb : 0;
+    const int cb0 = akk - tap * Cb;
+    const int dy = cls->dy[tap], dx = cls->dx[tap];
+
+    auto issue = [&](int c) {
+      const int stage = c % STAGES;
+      const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+      const uint32_t sb = sa + S::A_BYTES;
+      const long long mc = mbeg + (long long)c * BK;
+      // lane l: source of pixel mc + l for this warp's channel slab
+      unsigned long long own_u = 0;
+      {
+        long long m = mc + lane;
+        if (kvalid && m < mend) {
+          int f = (int)(m / HsWs);
+          int rem = (int)(m - (long long)f * HsWs);
+          int ym = rem / a.Ws;
+          int xm = rem - ym * a.Ws;
+          int y = ym * a.gs + dy, x = xm * a.gs + dx;
+          if ((unsigned)y < (unsigned)a.Hb && (unsigned)x < (unsigned)a.Wb)
+            own_u = (unsigned long long)(a.big + (((long long)f * a.Hb + y) * a.Wb + x) * Cb + cb0);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int px = 4 * i + rsub;                            // pixel (k row) within the chunk
+        unsigned long long pu = __shfl_sync(0xffffffffu, own_u, px);
+        const uint32_t dst = sa + (px >> 2) * A_SBO + warp * A_LBO + (px & 3) * 128 +
+                             ((((kc >> 1) ^ (px & 3)) << 5) | ((kc & 1) << 4));
+        const float* src = pu ? reinterpret_cast<const float*>(pu) + kc * 4 : a.big;
+        cp_async16(dst, src, pu ? 16u : 0u);
+      }
+      // S tile: rows (pixel, 32-channel slab j)
+#pragma unroll
+      for (int q = warp * 4 + rsub; q < 32 * (BN / 32); q += 16) {
+        const int px = q & 31, j = q >> 5;
+        const long long m = mc + px;
+        const bool ok = m < mend;
+        const uint32_t dst = sb + (px >> 2) * B_SBO + j * B_LBO + (px & 3) * 128 +
+                             ((((kc >> 1) ^ (px & 3)) << 5) | ((kc & 1) << 4));
+        const float* src = ok ? a.small + m * Cs + n0 + 32 * j + kc * 4 : a.small;
+        cp_async16(dst, src, ok ? 16u : 0u);
+      }
+    };
+
+    for (int c = 0; c < STAGES - 1; ++c) {
+      if (c < nchunks) issue(c);
+      cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int cn = c + STAGES - 1;
+      if (cn < nchunks) {
+        if (cn >= STAGES) mbar_wait(smem_u32(empty_bar + cn % STAGES), ((cn / STAGES) - 1) & 1);
+        issue(cn);
+      }
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();
+      fence_proxy_async();
+      mbar_arrive(smem_u32(full_bar + c % STAGES));
+    }
+    if (nchunks > 0) {
+      mbar_wait(smem_u32(accum_bar), 0);
+      tc_fence_after();
+    }
+    // epilogue: row kk of the partial slice, 32 columns at a time
+    const int kk = kk0 + tid;
+    float* prow = a.partial + ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t r[32];
+      if (nchunks > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) r[q] = 0u;
+      }
+      if (kk < a.Ktot) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(prow + j * 32 + q) =
+              make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
+                          __uint_as_float(r[q + 3]));
+      }
+    }
+    tc_fence_before();
+  } else {
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc_mn(BM, BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        mbar_wait(smem_u32(full_bar + stage), (c / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          uint64_t ad = make_desc_mn_sw128(sa + k * 2 * A_SBO, A_LBO, A_SBO);
+          uint64_t bd = make_desc_mn_sw128(sb + k * 2 * B_SBO, B_LBO, B_SBO);
+          umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(empty_bar + stage));
+      }
+      if (nchunks > 0) umma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<NCOLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+int launch_wgrad_tc(const WgTcArgs& a, int splits, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  auto kern = wgrad_tc_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  dim3 grid(bn_cdiv(a.Ktot, BM), a.Cs / BN, splits);
   kern<<<grid, NTHREADS, S::TOTAL, st>>>(a);
   BN_LAUNCHED();
   return 0;
@@ -350,7 +584,46 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   }
 }
 
-int bn_launch_wgrad_tc(const ImgView&, const float*, const ConvGeom&, int, float*, size_t, float*,
-                       cudaStream_t) {
-  return 1;
+int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
+                       size_t partial_floats, float* grad, cudaStream_t st) {
+  if (n <= 0 || grad == nullptr) return 0;
+  if (big.sc != 1 || big.C % 32 != 0 || big.sx != big.C || big.sy != (long long)big.W * big.C ||
+      big.sn != (long long)big.H * big.W * big.C)
+    return 1;
+  if (((uintptr_t)big.p & 15) || ((uintptr_t)small & 15) || ((uintptr_t)partial & 15)) return 1;
+  const int Cs = g.Cs;
+  int bn;
+  switch (Cs) {
+    case 32: bn = 32; break;
+    case 64: bn = 64; break;
+    case 128: bn = 128; break;
+    case 256: case 512: bn = 256; break;
+    default: return 1;
+  }
+  const int Ktot = g.k * g.k * g.Cb;
+  const long long M = (long long)n * g.Hs * g.Ws;
+  if (M < 256) return 1;
+  long long tiles = (long long)bn_cdiv(Ktot, BM) * (Cs / bn);
+  long long splits = (2 * 148 + tiles - 1) / tiles;
+  long long maxs = (M + 127) / 128;
+  if (splits > maxs) splits = maxs;
+  long long cap = (long long)(partial_floats / ((size_t)Ktot * Cs));
+  if (splits > cap) splits = cap;
+  if (splits < 1) return 1;
+  long long rps = (M + splits - 1) / splits;
+  rps = (rps + BK - 1) / BK * BK;
+  splits = (M + rps - 1) / rps;
+  WgTcArgs a;
+  a.big = big.p; a.Hb = big.H; a.Wb = big.W; a.Cb = big.C; a.small = small; a.Hs = g.Hs; a.Ws = g.Ws;
+  a.Cs = Cs; a.cls = g.d_fprop; a.gs = g.s; a.n = n; a.Ktot = Ktot; a.rows_per_split = rps;
+  a.partial = partial;
+  int r;
+  switch (bn) {
+    case 32: r = launch_wgrad_tc<32, 4>(a, (int)splits, st); break;
+    case 64: r = launch_wgrad_tc<64, 4>(a, (int)splits, st); break;
+    case 128: r = launch_wgrad_tc<128, 3>(a, (int)splits, st); break;
+    default: r = launch_wgrad_tc<256, 4>(a, (int)splits, st); break;
+  }
+  if (r) return r;
+  return bn_launch_wgrad_reduce(partial, (int)splits, Ktot, Cs, g.Cb, g.k * g.k, g.d_fprop, grad, st);
 }

@@ -124,6 +124,17 @@ int bn_cae_encode_bwd(bn_cae_plan* plan, int n, const float* d_x, const float* d
                       const float* d_dlogvar, const float* const* d_params, const void* d_packed,
                       void* d_ws, float* const* d_grads, void* stream);
 
+/* Run ONE layer operation of the plan on caller tensors (NHWC fp32): kernel-level parity tests of
+ * the tensor-core kernels against the CUDA-core kernels, and per-kernel timing for bench.py.
+ *   side: 0 = encoder layer `layer` (Conv2d), 1 = decoder layer `layer` (ConvTranspose2d)
+ *   op:   0 = forward (bias + the layer's activation), 1 = backward-data (no activation mask),
+ *         2 = weight gradient (d_in = big image, d_in2 = small image, d_out = torch-layout gradient,
+ *             ACCUMULATES)
+ * "big"/"small" are the conv-input-side / conv-output-side images of the layer. */
+int bn_cae_layer_op(bn_cae_plan* plan, int side, int layer, int op, int n, const float* d_in,
+                    const float* d_in2, float* d_out, const float* const* d_params,
+                    const void* d_packed, void* d_ws, void* stream);
+
 /* PS-VAE latent block (vaes.py:571-601, 669-696; losses.py:130-147, 284-372), one reference chunk
  * of n frames at a time (the MI/TC/DWKL estimators are pairwise over the chunk).
  * Inputs: d_pre (n, L) = FF output, d_logvar (n, L), frozen orthogonal d_A (n_labels, L) /

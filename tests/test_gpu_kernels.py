@@ -1,0 +1,90 @@
+"""Kernel-level GPU tests: every tcgen05 (TF32) layer kernel against the fp32 CUDA-core kernel on
+the SAME tensors, with data that is exactly representable in TF32 (multiples of 1/16 with small
+magnitude) so that products are exact and the two paths may only differ by fp32 summation order
+(tolerance 2e-5 relative to the output's max).  Shapes are the fat layers of config C2/C3."""
+
+import copy
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import cae_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+def _exact(shape, gen, scale=16, span=8):
+    return (torch.randint(-span, span + 1, shape, generator=gen).float() / scale)
+
+
+def _setup(n_ch=1, n=32):
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(n_ch, 128, 128, 12)
+    model = AE(copy.deepcopy(hp))
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(_exact(p.shape, g, scale=64, span=8))
+    model.cuda()
+    drv, rt = model._driver, model._rt
+    params = model._kernel_params()
+    packed = drv.packed(rt, params, torch.device('cuda', 0))
+    ws = drv.workspace(rt, n, torch.device('cuda', 0))
+    return _lib, model, drv, params, packed, ws, hp
+
+
+def _dims(hp, side, layer):
+    if side == 0:
+        cb = hp['ae_input_dim'][0] if layer == 0 else hp['ae_encoding_n_channels'][layer - 1]
+        hb = hp['ae_input_dim'][1] if layer == 0 else hp['ae_encoding_y_dim'][layer - 1]
+        wb = hp['ae_input_dim'][2] if layer == 0 else hp['ae_encoding_x_dim'][layer - 1]
+        return (hb, wb, cb), (hp['ae_encoding_y_dim'][layer], hp['ae_encoding_x_dim'][layer],
+                              hp['ae_encoding_n_channels'][layer])
+    c0, h0, w0 = hp['ae_decoding_starting_dim']
+    cs = c0 if layer == 0 else hp['ae_decoding_n_channels'][layer - 1]
+    hs = h0 if layer == 0 else hp['ae_decoding_y_dim'][layer - 1]
+    wsm = w0 if layer == 0 else hp['ae_decoding_x_dim'][layer - 1]
+    return ((hp['ae_decoding_y_dim'][layer], hp['ae_decoding_x_dim'][layer],
+             hp['ae_decoding_n_channels'][layer]), (hs, wsm, cs))
+
+
+def _run(lib, drv, params, packed, ws, side, layer, op, n, a, b, out, mode):
+    lib.lib().bn_set_tensor_core_mode(mode)
+    lib.check(lib.lib().bn_cae_layer_op(
+        drv.plan(a.device), side, layer, op, n, a.data_ptr(), None if b is None else b.data_ptr(),
+        out.data_ptr(), drv.table(params), packed.data_ptr(), ws.data_ptr(), lib.stream_ptr()),
+        'bn_cae_layer_op')
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('side,layer', [(0, 1), (0, 2), (0, 3), (0, 4), (1, 0), (1, 1), (1, 2), (1, 3)])
+@pytest.mark.parametrize('op', [0, 1, 2])
+def test_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op):
+    n = 32
+    lib, model, drv, params, packed, ws, hp = _setup(n=n)
+    big, small = _dims(hp, side, layer)
+    g = torch.Generator().manual_seed(100 * side + 10 * layer + op)
+    xb = _exact((n,) + big, g).cuda()
+    xs = _exact((n,) + small, g).cuda()
+    fprop_form = (side == 0 and op == 0) or (side == 1 and op == 1)
+    if op == 2:
+        wshape = params[2 * layer].shape if side == 0 else params[2 * drv.n_layers + 6 + 2 * layer].shape
+        outs = []
+        for mode in (0, 1):
+            out = torch.zeros(wshape, device='cuda')
+            _run(lib, drv, params, packed, ws, side, layer, 2, n, xb, xs, out, mode)
+            outs.append(out)
+    else:
+        src = xb if fprop_form else xs
+        oshape = (n,) + (small if fprop_form else big)
+        outs = []
+        for mode in (0, 1):
+            out = torch.full(oshape, float('nan'), device='cuda')
+            _run(lib, drv, params, packed, ws, side, layer, op, n, src, None, out, mode)
+            outs.append(out)
+    ref, tc = outs
+    assert torch.isfinite(tc).all()
+    err = float((tc - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err

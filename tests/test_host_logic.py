@@ -1,0 +1,198 @@
+"""CPU tests of the host-side mirror of the reference interfaces (no kernels are launched):
+model construction / state_dict protocol, unsupported-variant errors, HMM host logic (M-step,
+permute, pickling), sharding arithmetic, and the world-size-2 gloo path of the collectives."""
+
+import copy
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import arhmm_oracle as ao
+from oracle import cae_oracle as co
+from tests.helpers import load_golden
+
+
+def test_ae_state_dict_protocol_matches_reference_names():
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 128, 128, 12)
+    model = AE(copy.deepcopy(hp))
+    gold = load_golden('ae_128x128x1_l12_b3')
+    ref_names = sorted({k[5:].split('#')[0] for k in gold if k.startswith('grad.')})
+    assert sorted(model.state_dict().keys()) == ref_names
+    sd = co.init_state_dict(hp)
+    model.load_state_dict(sd)                      # shapes identical to the reference's
+    assert model.hparams['hidden_layer_size'] == 12
+    assert sum(p.numel() for p in model.parameters()) == 8758285     # SURVEY.md probe
+    assert len(list(model.get_parameters())) == 24
+    assert 'Encoder architecture' in str(model) and 'Decoder architecture' in str(model)
+    assert model.decoding.conv_t_pads['convtranspose0'] is None
+    assert model.decoding.conv_t_pads['convtranspose1'] == [1, 2, 1, 2]
+    copy.deepcopy(model)
+    pickle.loads(pickle.dumps(model))
+
+
+def test_psvae_protocol():
+    from behavenet_b200.models import PSVAE
+    np.random.seed(0)
+    hp = co.make_hparams(2, 32, 32, 8, 'ps-vae', 3)
+    model = PSVAE(copy.deepcopy(hp))
+    assert model.hparams['variational'] is True
+    names = set(model.state_dict().keys())
+    for k in ['encoding.A.weight', 'encoding.B.weight', 'encoding.D.weight', 'encoding.D.bias',
+              'encoding.logvar.weight', 'encoding.FF.weight', 'decoding.FF.weight']:
+        assert k in names
+    assert not model.encoding.A.weight.requires_grad and not model.encoding.B.weight.requires_grad
+    m = torch.cat([model.encoding.A.weight, model.encoding.B.weight], 0)
+    assert torch.allclose(m @ m.T, torch.eye(8), atol=1e-5)           # orthogonal, frozen
+    assert model.beta_vals.shape == (hp['max_n_epochs'] + 1,)
+    hp2 = co.make_hparams(2, 32, 32, 2, 'ps-vae', 3)
+    with pytest.raises(ValueError):
+        PSVAE(hp2)
+    hp3 = dict(co.make_hparams(2, 32, 32, 8, 'ps-vae', 3))
+    hp3['ps_vae.anneal_epochs'] = 4
+    model3 = PSVAE(hp3)
+    assert model3.beta_vals[0] == 0 and model3.kl_anneal_vals[3] == 1
+
+
+@pytest.mark.parametrize('key,val', [('ae_batch_norm', True), ('fit_sess_io_layers', True),
+                                     ('ae_decoding_last_FF_layer', True), ('ae_padding_type', 'valid')])
+def test_unsupported_variants_raise_instead_of_falling_back(key, val):
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 32, 32, 8)
+    hp[key] = val
+    with pytest.raises(NotImplementedError):
+        AE(hp)
+
+
+def test_invalid_model_type_and_linear():
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 32, 32, 8)
+    hp['model_type'] = 'linear'
+    with pytest.raises(NotImplementedError):
+        AE(hp)
+    hp['model_type'] = 'bogus'
+    with pytest.raises((ValueError, NotImplementedError)):
+        AE(hp)
+
+
+def test_cpu_tensors_are_rejected():
+    from behavenet_b200.models import AE
+    model = AE(co.make_hparams(1, 32, 32, 8))
+    with pytest.raises(RuntimeError):
+        model(torch.rand(2, 1, 32, 32))
+    with pytest.raises(RuntimeError):
+        model.loss({'images': torch.rand(1, 2, 1, 32, 32)})
+
+
+def test_hmm_m_step_matches_oracle_given_oracle_expectations():
+    """Host M-step logic: feed the oracle's E-step outputs through the product's M-step (as
+    Gram statistics) and compare with the oracle's M-step."""
+    from behavenet_b200.ssm import HMM
+    for transitions, kw in (('stationary', None), ('sticky', {'kappa': 5.0})):
+        p = ao.synth_params(3, 2, 2, seed=2, mix=0.3)
+        rng = np.random.RandomState(0)
+        xs = [ao.sample(p, T, rng)[1] for T in (80, 60)]
+        exps = ao.e_step(p, xs)
+        hmm = HMM(3, 2, observations='ar', observation_kwargs={'lags': 2}, transitions=transitions,
+                  transition_kwargs=kw)
+        hmm.observations.As, hmm.observations.bs, hmm.observations.Sigmas = p.As.copy(), p.bs.copy(), p.Sigmas.copy()
+        Sxx, Sxy, Syy, Sn = ao.ar_sufficient_stats(p, xs, exps)
+        P = 2 * 2 + 1
+        stats = np.zeros((3, P + 2, P + 2))
+        stats[:, :P, :P], stats[:, :P, P:], stats[:, P:, P:] = Sxx, Sxy, Syy
+        stats[:, P:, :P] = np.transpose(Sxy, (0, 2, 1))
+        hmm.observations.m_step(stats, Sn)
+        hmm.transitions.m_step(sum(e[1] for e in exps))
+        hmm.init_state_distn.m_step(sum(e[0][0] for e in exps))
+        ref = ao.m_step(p, xs, exps, transitions=transitions, kappa=5.0)
+        used = Sn > 1          # states with < 1 expected count are re-seeded from a used one (ssm)
+        assert used.sum() >= 2
+        np.testing.assert_allclose(hmm.observations.As[used], ref.As[used], atol=1e-10)
+        np.testing.assert_allclose(hmm.observations.bs[used], ref.bs[used], atol=1e-10)
+        np.testing.assert_allclose(hmm.observations.Sigmas[used], ref.Sigmas[used], atol=1e-10)
+        np.testing.assert_allclose(hmm.transitions.log_Ps, ref.log_Ps, atol=1e-10)
+        np.testing.assert_allclose(hmm.init_state_distn.log_pi0, ref.log_pi0, atol=1e-10)
+
+
+def test_hmm_construction_permute_pickle_and_errors():
+    from behavenet_b200.ssm import HMM
+    np.random.seed(1)
+    hmm = HMM(4, 3, observations='ar', observation_kwargs={'lags': 2}, transitions='sticky',
+              transition_kwargs={'kappa': 100})
+    assert hmm.observations.As.shape == (4, 3, 6) and hmm.observations.lags == 2
+    P = hmm.transitions.transition_matrix
+    np.testing.assert_allclose(P.sum(1), 1, atol=1e-12)
+    before = (hmm.observations.bs.copy(), hmm.transitions.log_Ps.copy())
+    perm = np.array([2, 0, 3, 1])
+    hmm.permute(perm)
+    np.testing.assert_array_equal(hmm.observations.bs, before[0][perm])
+    np.testing.assert_array_equal(hmm.transitions.log_Ps, before[1][np.ix_(perm, perm)])
+    hmm.hparams = {'a': 1}
+    clone = pickle.loads(pickle.dumps(hmm))
+    np.testing.assert_array_equal(clone.observations.As, hmm.observations.As)
+    assert clone.hparams == {'a': 1}
+    for bad in (dict(observations='robust_ar'), dict(transitions='recurrent'), dict(M=2)):
+        with pytest.raises(NotImplementedError):
+            HMM(4, 3, **bad)
+    z, x = hmm.sample(20)
+    assert z.shape == (20,) and x.shape == (20, 3)
+
+
+def test_shard_range_covers_everything_once():
+    from behavenet_b200 import parallel
+    for n in (0, 1, 7, 256, 2048, 5292):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from behavenet_b200 import parallel
+    from behavenet_b200.models import AE
+    assert parallel.init('gloo')
+    assert parallel.world_size() == world and parallel.rank() == rank
+    hp = co.make_hparams(1, 32, 32, 8)
+    torch.manual_seed(0)
+    model = AE(hp)
+    model.data_parallel = True
+    params = model._kernel_params()
+    # fabricate rank-dependent gradients in the flat buffer the fused loss path would fill
+    grads = model._grad_table(params)
+    for i, g in enumerate(g for g in grads if g is not None):
+        g.fill_(float(rank + 1) * (i + 1))
+    sse = torch.tensor([1.0 + rank, 10.0], dtype=torch.float64)
+    lo, hi = model._shard(10)
+    model._allreduce(params, sse)
+    tot = sum(r + 1 for r in range(world))
+    ok = all(torch.all(g == tot * (i + 1)) for i, g in enumerate(g for g in grads if g is not None))
+    ok = ok and sse.tolist() == [sum(1.0 + r for r in range(world)), 10.0 * world]
+    # second path: gradients that are NOT views of the flat buffer
+    model.zero_grad()
+    for p in model.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    model._allreduce(params, sse)
+    ok = ok and all(torch.all(p.grad == tot) for p in model.parameters())
+    q.put((rank, ok, (lo, hi)))
+    parallel.shutdown()
+
+
+def test_world_size_2_gloo_allreduce_and_sharding():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1]
+    assert res[0][2] == (0, 5) and res[1][2] == (5, 10)

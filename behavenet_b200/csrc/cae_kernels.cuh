@@ -55,6 +55,17 @@ int bn_launch_thin_dgrad(const float* small, const ConvGeom& g, const float* wd,
                          const float* mask, int chunk_size, int frame_offset, int n_total,
                          float grad_coef, double* sse, float* dpre, cudaStream_t st);
 
+// Shared-memory-tiled fast paths for kernel-5 / stride-2 thin layers (cae_thin.cu).  Each returns 1
+// when the geometry is not covered (caller falls back to the general kernels).
+int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* bias, float* out,
+                         const float* dact, int act, int n, cudaStream_t st);
+int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
+                         size_t partial_floats, float* grad, cudaStream_t st);
+int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd, const float* bias, int n,
+                          float* xhat_ws, float* xhat_user, const float* target, const float* mask,
+                          int chunk_size, int frame_offset, int n_total, float grad_coef, double* sse,
+                          float* dpre, cudaStream_t st);
+
 // dpre[n,y,x,c] = dxhat[n,c,y,x] * xhat * (1 - xhat)
 int bn_launch_sigmoid_bwd(const float* dxhat, const float* xhat, float* dpre, int n, int C, int H,
                           int W, cudaStream_t st);
@@ -83,8 +94,10 @@ int bn_launch_decff_bwd(const float* z, const float* w, const float* dh0, int n,
 // tcgen05 TF32 tensor-core implicit GEMM (cae_tc.cu).  Returns 1 if the shape is not supported
 // (caller then uses the CUDA-core kernel), 0 on success, <0 on error.
 //   wt : K-major packed weights [Co][wrow], wrow = k*k*Ci, TF32-rounded
+//   split_buf : scratch for the split-K variant (few output tiles, long reduction); may be NULL
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes, int nclasses,
-                       int maxM, int gs, int os, int n, int act, cudaStream_t st);
+                       int maxM, int maxtaps, int gs, int os, int n, int act, float* split_buf,
+                       size_t split_floats, cudaStream_t st);
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n,
                        float* partial, size_t partial_floats, float* grad, cudaStream_t st);

@@ -106,13 +106,20 @@ void build_classes(ConvGeom& g, std::vector<TapClass>& tab, int& i_f, int& i_d) 
     }
 }
 
+// scratch of the current C-ABI call (the workspace's split-K partial region), used by the
+// tensor-core split-K variant; set by every entry point after it lays out the workspace
+thread_local float* t_split_buf = nullptr;
+thread_local size_t t_split_floats = 0;
+
 int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const float* wt, int wrow,
               const float* bias, float* out, int Ho, int Wo, int Co, const float* dact, int table_idx,
               int nclasses, int maxM, int gs, int os, int n, int act, cudaStream_t st) {
   const TapClass* dcls = p->d_tables + table_idx;
   if (g_tc_mode.load()) {
-    int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n,
-                               act, st);
+    int maxtaps = 0;
+    for (int c = 0; c < nclasses; ++c) maxtaps = std::max(maxtaps, p->h_tables[table_idx + c].ntaps);
+    int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, maxtaps, gs, os,
+                               n, act, t_split_buf, t_split_floats, st);
     if (r <= 0) return r;
   }
   return bn_launch_igemm(in, w, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n, act, st);
@@ -121,6 +128,10 @@ int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const flo
 int run_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
               size_t partial_floats, float* grad, cudaStream_t st) {
   if (!grad) return 0;
+  if (g.Cb <= 4) {
+    int r = bn_launch_thin_wgrad(big, small, g, n, partial, partial_floats, grad, st);
+    if (r <= 0) return r;
+  }
   if (g_tc_mode.load()) {
     int r = bn_launch_wgrad_tc(big, small, g, n, partial, partial_floats, grad, st);
     if (r <= 0) return r;
@@ -256,12 +267,17 @@ extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const floa
   const float* pk = (const float*)d_packed;
   float* ws = (float*)d_ws;
   WsLayout L = ws_layout(p, n);
+  t_split_buf = ws + L.partial;
+  t_split_floats = L.partial_floats;
   ImgView in = input_view(p, d_x);
   for (int i = 0; i < p->nl; ++i) {
     const ConvGeom& g = p->enc[i];
     float* out = ws + L.enc_act[i + 1];
-    BN_TRY(run_igemm(p, in, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, P[g.p_b], out, g.Hs, g.Ws,
-                     g.Cs, nullptr, p->enc_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_LEAKY, st));
+    int thin = g.Cb <= 4 ? bn_launch_thin_fprop(in, g, pk + g.off_wf, P[g.p_b], out, nullptr, BN_ACT_LEAKY, n, st) : 1;
+    if (thin < 0) return thin;
+    if (thin > 0)
+      BN_TRY(run_igemm(p, in, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, P[g.p_b], out, g.Hs, g.Ws,
+                       g.Cs, nullptr, p->enc_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_LEAKY, st));
     in = nhwc_view(out, g.Hs, g.Ws, g.Cs);
   }
   const int n2 = 2 * p->nl;
@@ -282,6 +298,8 @@ extern "C" int bn_cae_decode(bn_cae_plan* p, int n, const float* d_z, const floa
   const float* pk = (const float*)d_packed;
   float* ws = (float*)d_ws;
   WsLayout L = ws_layout(p, n);
+  t_split_buf = ws + L.partial;
+  t_split_floats = L.partial_floats;
   const int n2 = 2 * p->nl;
   BN_CUDA(cudaMemcpyAsync(ws + L.zcopy, d_z, (size_t)n * p->d.n_latents * sizeof(float), cudaMemcpyDeviceToDevice, st));
   BN_TRY(bn_launch_decff_fwd(d_z, P[n2 + 4], P[n2 + 5], n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
@@ -294,9 +312,14 @@ extern "C" int bn_cae_decode(bn_cae_plan* p, int n, const float* d_z, const floa
                      g.dgrad_maxM, 1, g.s, n, BN_ACT_LEAKY, st));
   }
   const ConvGeom& g = p->dec[p->nl - 1];
-  BN_TRY(bn_launch_thin_dgrad(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
-                              d_xhat, d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
-                              ws + L.dpre_last, st));
+  int fast = bn_launch_thin_dgrad5(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
+                                   d_xhat, d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
+                                   ws + L.dpre_last, st);
+  if (fast < 0) return fast;
+  if (fast > 0)
+    BN_TRY(bn_launch_thin_dgrad(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
+                                d_xhat, d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
+                                ws + L.dpre_last, st));
   return 0;
 }
 
@@ -309,6 +332,8 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
   const float* pk = (const float*)d_packed;
   float* ws = (float*)d_ws;
   WsLayout L = ws_layout(p, n);
+  t_split_buf = ws + L.partial;
+  t_split_floats = L.partial_floats;
   const int n2 = 2 * p->nl;
   const ConvGeom& gl = p->dec[p->nl - 1];
   if (d_dxhat)
@@ -324,8 +349,12 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
     BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
     float* out = pp[flip];
     flip ^= 1;
-    BN_TRY(run_igemm(p, big, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, nullptr, out, g.Hs, g.Ws,
-                     g.Cs, i > 0 ? small : nullptr, p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st));
+    int thin = g.Cb <= 4 ? bn_launch_thin_fprop(big, g, pk + g.off_wf, nullptr, out, i > 0 ? small : nullptr,
+                                                BN_ACT_NONE, n, st) : 1;
+    if (thin < 0) return thin;
+    if (thin > 0)
+      BN_TRY(run_igemm(p, big, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, nullptr, out, g.Hs, g.Ws,
+                       g.Cs, i > 0 ? small : nullptr, p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st));
     gcur = out;
   }
   BN_TRY(bn_launch_decff_bwd(ws + L.zcopy, P[n2 + 4], gcur, n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
@@ -343,6 +372,8 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
   const float* pk = (const float*)d_packed;
   float* ws = (float*)d_ws;
   WsLayout L = ws_layout(p, n);
+  t_split_buf = ws + L.partial;
+  t_split_floats = L.partial_floats;
   const int n2 = 2 * p->nl;
   float* pp[2] = {ws + L.gA, ws + L.gB};
   int flip = 0;
@@ -381,6 +412,8 @@ extern "C" int bn_cae_layer_op(bn_cae_plan* p, int side, int layer, int op, int 
   const float* pk = (const float*)d_packed;
   float* ws = (float*)d_ws;
   WsLayout L = ws_layout(p, n);
+  t_split_buf = ws + L.partial;
+  t_split_floats = L.partial_floats;
   const ConvGeom& g = side == 0 ? p->enc[layer] : p->dec[layer];
   const int tf = side == 0 ? p->enc_f[layer] : p->dec_f[layer];
   const int td = side == 0 ? p->enc_d[layer] : p->dec_d[layer];

@@ -120,6 +120,8 @@ struct TcArgs {
   const float* dact;
   const TapClass* classes;
   int gs, os, n, act;
+  int ksplit;             // > 1: single-class op whose k-chunks are split over grid.z
+  float* split_out;       // [ksplit][M][Co] raw partial sums (bias / activation applied by the reducer)
 };
 
 template <int BN, int STAGES>
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   {
-    const int* src = reinterpret_cast<const int*>(a.classes + blockIdx.z);
+    const int* src = reinterpret_cast<const int*>(a.classes + (a.ksplit > 1 ? 0 : blockIdx.z));
     int* dst = reinterpret_cast<int*>(cls);
     for (int i = tid; i < (int)(sizeof(TapClass) / 4); i += NTHREADS) dst[i] = src[i];
   }
@@ -171,7 +173,14 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
   const int n0 = blockIdx.y * BN;
   const int Ci = a.Ci;
   const int cpt = Ci / BK;
-  const int nchunks = cls->ntaps * cpt;
+  // k-chunk range of this CTA (all of them, or one split-K slice)
+  int cbeg = 0, nchunks = cls->ntaps * cpt;
+  if (a.ksplit > 1) {
+    const int per = (nchunks + a.ksplit - 1) / a.ksplit;
+    cbeg = blockIdx.z * per;
+    const int cend = cbeg + per < nchunks ? cbeg + per : nchunks;
+    nchunks = cend > cbeg ? cend - cbeg : 0;
+  }
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp < 4) {
@@ -199,8 +208,8 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
 
     auto issue = [&](int c) {
       const int stage = c % STAGES;
-      const int tap = c / cpt;
-      const int c0 = (c - tap * cpt) * BK;
+      const int tap = (cbeg + c) / cpt;
+      const int c0 = (cbeg + c - tap * cpt) * BK;
       const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
       const uint32_t sb = sa + S::A_BYTES;
       {
@@ -267,7 +276,13 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      if (rvalid) {
+      if (rvalid && a.ksplit > 1) {
+        float* po = a.split_out + ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(po + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                                           __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+      } else if (rvalid) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
           float v[4];
@@ -330,10 +345,34 @@ int launch_tc(const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, nclasses);
+  dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, a.ksplit > 1 ? a.ksplit : nclasses);
   kern<<<grid, NTHREADS, S::TOTAL, st>>>(a);
   BN_LAUNCHED();
   return 0;
+}
+
+// out[i] = act(bias[i % Co] + sum_z part[z][i]) * lrelu'(dact[i])
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long total, int Co,
+                                     const float* __restrict__ bias, const float* __restrict__ dact, int act,
+                                     float* __restrict__ out) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= total) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(part + (long long)z * total + i));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  float v[4] = {s.x, s.y, s.z, s.w};
+  const int c = (int)(i % Co);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float x = v[e] + (bias ? __ldg(bias + c + e) : 0.f);
+    if (act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+    else if (act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+    if (dact) x *= __ldg(dact + i + e) > 0.f ? 1.f : BN_LEAK;
+    v[e] = x;
+  }
+  *reinterpret_cast<float4*>(out + i) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 
@@ -560,7 +599,8 @@ int launch_wgrad_tc(const WgTcArgs& a, int splits, cudaStream_t st) {
 
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes, int nclasses,
-                       int maxM, int gs, int os, int n, int act, cudaStream_t st) {
+                       int maxM, int maxtaps, int gs, int os, int n, int act, float* split_buf,
+                       size_t split_floats, cudaStream_t st) {
   // shapes this kernel covers: NHWC-dense input with C % 32 == 0, C_out in {32, 64, 128, 256, 512},
   // enough rows to fill the machine (the stride-5 layers with a few hundred rows stay on the
   // CUDA-core kernel until the split-K variant lands)
@@ -569,19 +609,38 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
       in.sn != (long long)in.H * in.W * in.C)
     return 1;
   if (((uintptr_t)in.p & 15) || ((uintptr_t)out & 15) || ((uintptr_t)wt & 15) || (dact && ((uintptr_t)dact & 15))) return 1;
-  if ((long long)n * maxM < 64LL * BM) return 1;
+  const int bn = Co >= 256 ? 256 : Co;
+  if (Co != 32 && Co != 64 && Co != 128 && Co != 256 && Co != 512) return 1;
+  const long long M = (long long)n * maxM;
+  const long long ctas = (long long)bn_cdiv(M, BM) * (Co / bn) * nclasses;
+  const int nchunks = maxtaps * (in.C / BK);
+  int ksplit = 1;
+  if (ctas < 64 && nclasses == 1 && os == 1 && split_buf != nullptr && nchunks >= 16) {
+    // few output tiles but a long reduction (the stride-5 layers): split the taps over grid.z
+    ksplit = (int)((148 + ctas - 1) / ctas);
+    if (ksplit > nchunks / 4) ksplit = nchunks / 4;
+    if (ksplit > 32) ksplit = 32;
+    while (ksplit > 1 && (size_t)ksplit * M * Co > split_floats) --ksplit;
+  }
+  if (ctas * ksplit < 24) return 1;            // too little work to fill the machine: CUDA-core kernel
   TcArgs a;
+  a.ksplit = ksplit;
+  a.split_out = split_buf;
   a.in = in.p; a.Hi = in.H; a.Wi = in.W; a.Ci = in.C; a.wt = wt; a.wrow = wrow; a.bias = bias; a.out = out;
   a.Ho = Ho; a.Wo = Wo; a.Co = Co; a.dact = dact; a.classes = d_classes; a.gs = gs; a.os = os;
   a.n = n; a.act = act;
+  int r;
   switch (Co) {
-    case 32: return launch_tc<32, 4>(a, nclasses, maxM, st);
-    case 64: return launch_tc<64, 4>(a, nclasses, maxM, st);
-    case 128: return launch_tc<128, 3>(a, nclasses, maxM, st);
-    case 256: return launch_tc<256, 4>(a, nclasses, maxM, st);
-    case 512: return launch_tc<256, 4>(a, nclasses, maxM, st);
-    default: return 1;
+    case 32: r = launch_tc<32, 4>(a, nclasses, maxM, st); break;
+    case 64: r = launch_tc<64, 4>(a, nclasses, maxM, st); break;
+    case 128: r = launch_tc<128, 3>(a, nclasses, maxM, st); break;
+    default: r = launch_tc<256, 4>(a, nclasses, maxM, st); break;
   }
+  if (r || ksplit == 1) return r;
+  const long long total = M * Co;          // fprop-form output is linear in (m, co)
+  splitk_reduce_kernel<<<bn_cdiv(total / 4, 256), 256, 0, st>>>(split_buf, ksplit, total, Co, bias, dact, act, out);
+  BN_LAUNCHED();
+  return 0;
 }
 
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,

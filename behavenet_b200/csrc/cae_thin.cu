@@ -1,0 +1,357 @@
+// Shared-memory-tiled kernels for the thin first / last layers of the default architecture
+// (kernel 5, stride 2, 1-4 image channels <-> 32k feature channels).  These layers carry < 2 % of
+// the FLOPs but move the largest activations (64x64x32 per frame); they are HBM-bound, so the
+// im2col duplication of the implicit-GEMM kernels (6.25x re-reads through L2) is what has to go:
+// every input element is staged ONCE per tile in shared memory and the 25 taps read it from there.
+//
+//   thin_fprop_kernel  : thin image -> fat image   (encoder conv0 forward; last convT backward-data)
+//   thin_wgrad_kernel  : weight gradient of the same geometry (conv0.weight, convtranspose{last}.weight)
+//   thin_dgrad5_kernel : fat image -> thin image + sigmoid + fused reconstruction loss
+//                        (last ConvTranspose2d forward, aes.py:463-470 + losses.py:36-96)
+// Lane = feature channel in the first two (coalesced 128-byte rows per pixel, taps read by
+// broadcast LDS.128); lane = output pixel of one stride-residue class in the third.
+#include "cae_kernels.cuh"
+
+namespace {
+
+constexpr int TH = 8, TW = 32;             // small-image tile per block (fprop / wgrad)
+constexpr int PROWS = 2 * (TH - 1) + 5;    // 19 patch rows
+constexpr int PCOLS = 72;                  // 2*(TW-1)+5 = 67 used, padded for 16-byte LDS
+
+struct ThinGeo {
+  ImgView big;          // thin image (C <= 4), any strides
+  int Hs, Ws, Cs;       // fat image
+  int pt, pl, n;
+};
+
+template <int CB>
+__device__ __forceinline__ void load_patch(float (*patch)[PROWS][PCOLS], const ThinGeo& g, int f, int y0,
+                                           int x0, int tid) {
+  for (int i = tid; i < CB * PROWS * PCOLS; i += 256) {
+    int c = i / (PROWS * PCOLS);
+    int rem = i - c * PROWS * PCOLS;
+    int r = rem / PCOLS, col = rem - r * PCOLS;
+    int y = 2 * y0 - g.pt + r, x = 2 * x0 - g.pl + col;
+    float v = 0.f;
+    if ((unsigned)y < (unsigned)g.big.H && (unsigned)x < (unsigned)g.big.W)
+      v = __ldg(g.big.p + (long long)f * g.big.sn + (long long)y * g.big.sy + (long long)x * g.big.sx +
+                (long long)c * g.big.sc);
+    patch[c][r][col] = v;
+  }
+}
+
+template <int CB>
+__global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         float* __restrict__ out,
+                                                         const float* __restrict__ dact, int act,
+                                                         int tiles_x) {
+  __shared__ __align__(16) float patch[CB][PROWS][PCOLS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  const int c = blockIdx.z * 32 + lane;
+  load_patch<CB>(patch, g, f, y0, x0, tid);
+  float wr[25 * CB];
+#pragma unroll
+  for (int i = 0; i < 25 * CB; ++i) wr[i] = __ldg(w + (long long)i * g.Cs + c);    // [(tap, cb)][cs]
+  const float b = bias ? __ldg(bias + c) : 0.f;
+  __syncthreads();
+  const int oy = y0 + warp;
+  if (oy >= g.Hs) return;
+#pragma unroll 2
+  for (int j = 0; j < TW / 2; ++j) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+      for (int cb = 0; cb < CB; ++cb) {
+        const float4 v0 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j]);
+        const float4 v1 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j + 4]);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const float wv = wr[(ky * 5 + kx) * CB + cb];
+          a0 = fmaf(v[kx], wv, a0);
+          a1 = fmaf(v[kx + 2], wv, a1);
+        }
+      }
+    }
+    const int ox = x0 + 2 * j;
+    float r[2] = {a0 + b, a1 + b};
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (ox + e >= g.Ws) continue;
+      float x = r[e];
+      if (act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+      const long long idx = (((long long)f * g.Hs + oy) * g.Ws + ox + e) * g.Cs + c;
+      if (dact) x *= __ldg(dact + idx) > 0.f ? 1.f : BN_LEAK;
+      out[idx] = x;
+    }
+  }
+}
+
+template <int CB>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinGeo g, const float* __restrict__ small,
+                                                         float* __restrict__ partial, int tiles_x,
+                                                         int tiles_per_frame, long long total_tiles) {
+  // persistent: each block walks tiles blockIdx.x, +gridDim.x, ...; lane = small-image channel
+  __shared__ __align__(16) float patch[CB][PROWS][PCOLS];
+  extern __shared__ __align__(16) float red[];          // [8][25*CB][32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.y * 32 + lane;
+  float acc[25 * CB];
+#pragma unroll
+  for (int i = 0; i < 25 * CB; ++i) acc[i] = 0.f;
+  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int f = (int)(t / tiles_per_frame);
+    const int tt = (int)(t - (long long)f * tiles_per_frame);
+    const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    __syncthreads();
+    load_patch<CB>(patch, g, f, y0, x0, tid);
+    __syncthreads();
+    const int oy = y0 + warp;
+    if (oy < g.Hs) {
+      const float* srow = small + (((long long)f * g.Hs + oy) * g.Ws + x0) * g.Cs + c;
+#pragma unroll 2
+      for (int j = 0; j < TW / 2; ++j) {
+        const int ox = x0 + 2 * j;
+        const float s0 = ox < g.Ws ? __ldg(srow + (long long)(2 * j) * g.Cs) : 0.f;
+        const float s1 = ox + 1 < g.Ws ? __ldg(srow + (long long)(2 * j + 1) * g.Cs) : 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+          for (int cb = 0; cb < CB; ++cb) {
+            const float4 v0 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j]);
+            const float4 v1 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j + 4]);
+            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+              float& a = acc[(ky * 5 + kx) * CB + cb];
+              a = fmaf(v[kx], s0, a);
+              a = fmaf(v[kx + 2], s1, a);
+            }
+          }
+        }
+      }
+    }
+  }
+  // cross-warp reduction, then this block's slice of the partial buffer [(tap, cb)][Cs]
+#pragma unroll
+  for (int i = 0; i < 25 * CB; ++i) red[(warp * 25 * CB + i) * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int i = warp; i < 25 * CB; i += 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[(q * 25 * CB + i) * 32 + lane];
+    partial[((long long)blockIdx.x * 25 * CB + i) * g.Cs + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// last decoder layer, kernel 5 / stride 2 fast path
+// ------------------------------------------------------------------------------------------------
+struct Dg5Args {
+  const float* small;
+  int Hs, Ws, Cs, Hb, Wb, pt, pl, n;
+  const float* wd;        // [(tap, cs)][cb]
+  const float* bias;
+  float* xhat_ws;
+  float* xhat_user;
+  const float* target;
+  const float* mask;
+  int chunk_size, frame_offset, n_total;
+  float coef;
+  double* sse;
+  float* dpre;
+};
+
+constexpr int DT = 16;      // output tile edge
+constexpr int DP = 10;      // input patch edge: (DT + 4) / 2
+
+template <int CB>
+__global__ void __launch_bounds__(256) thin_dgrad5_kernel(const Dg5Args a, int tiles_x) {
+  extern __shared__ __align__(16) float sm[];
+  const int Cs = a.Cs, PS = Cs + 4;                    // padded pixel stride: conflict-free LDS.128
+  float* patch = sm;                                   // [DP*DP][PS]
+  float* wsm = sm + DP * DP * PS;                      // [25][CB][Cs]
+  __shared__ double sse_sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = blockIdx.y;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * DT, x0 = tx * DT;
+  // patch origin: smallest input row/col any pixel of the tile can touch
+  const int iy0 = (y0 + a.pt - 3) >> 1, ix0 = (x0 + a.pl - 3) >> 1;      // = ceil((y0 + pt - 4) / 2)
+  for (int i = tid; i < DP * DP * (Cs / 4); i += 256) {
+    int p = i / (Cs / 4), q = i - p * (Cs / 4);
+    int pr = p / DP, pc = p - pr * DP;
+    int iy = iy0 + pr, ix = ix0 + pc;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)iy < (unsigned)a.Hs && (unsigned)ix < (unsigned)a.Ws)
+      v = __ldg(reinterpret_cast<const float4*>(a.small + (((long long)f * a.Hs + iy) * a.Ws + ix) * Cs) + q);
+    *reinterpret_cast<float4*>(patch + p * PS + q * 4) = v;
+  }
+  for (int i = tid; i < 25 * CB * Cs; i += 256) {
+    int tap = i / (CB * Cs);
+    int rem = i - tap * CB * Cs;
+    int cb = rem / Cs, ci = rem - cb * Cs;
+    wsm[i] = __ldg(a.wd + ((long long)tap * Cs + ci) * CB + cb);
+  }
+  if (tid == 0) sse_sm = 0.0;
+  __syncthreads();
+  // warp -> stride-residue class (uniform tap list), lane -> pixel of that class
+  const int cls = warp >> 1;
+  const int py = cls >> 1, px = cls & 1;
+  const int yy = (warp & 1) * 4 + (lane >> 3), xx = lane & 7;
+  const int y = y0 + 2 * yy + py, x = x0 + 2 * xx + px;
+  const bool valid = y < a.Hb && x < a.Wb;
+  float acc[CB];
+#pragma unroll
+  for (int c = 0; c < CB; ++c) acc[c] = 0.f;
+  const int ky0 = (py + a.pt) & 1, kx0 = (px + a.pl) & 1;       // y0, x0 are even
+  for (int ky = ky0; ky < 5; ky += 2) {
+    const int pr = ((y0 + py + a.pt - ky) >> 1) + yy - iy0;
+    for (int kx = kx0; kx < 5; kx += 2) {
+      const int pc = ((x0 + px + a.pl - kx) >> 1) + xx - ix0;
+      const float* ip = patch + (pr * DP + pc) * PS;
+      const float* wp = wsm + (ky * 5 + kx) * CB * Cs;
+      for (int q = 0; q < Cs; q += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(ip + q);
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+          const float4 wv = *reinterpret_cast<const float4*>(wp + c * Cs + q);
+          acc[c] = fmaf(v.x, wv.x, acc[c]);
+          acc[c] = fmaf(v.y, wv.y, acc[c]);
+          acc[c] = fmaf(v.z, wv.z, acc[c]);
+          acc[c] = fmaf(v.w, wv.w, acc[c]);
+        }
+      }
+    }
+  }
+  double my_sse = 0.0;
+  if (valid) {
+    const int chunk = (f + a.frame_offset) / a.chunk_size;
+    const int len = min(a.chunk_size, a.n_total - chunk * a.chunk_size);
+    const float gsc = a.coef / (float)len;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      float v = acc[c] + (a.bias ? __ldg(a.bias + c) : 0.f);
+      v = 1.f / (1.f + expf(-v));
+      const long long inchw = (((long long)f * CB + c) * a.Hb + y) * a.Wb + x;
+      a.xhat_ws[inchw] = v;
+      if (a.xhat_user) a.xhat_user[inchw] = v;
+      if (a.target) {
+        const float d = v - __ldg(a.target + inchw);
+        const float m = a.mask ? __ldg(a.mask + inchw) : 1.f;
+        my_sse += (double)(d * d * m);
+        a.dpre[(((long long)f * a.Hb + y) * a.Wb + x) * CB + c] = gsc * d * m * v * (1.f - v);
+      }
+    }
+  }
+  if (a.target) {
+    // a block lies inside one frame, hence inside one chunk
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_sse += __shfl_xor_sync(0xffffffffu, my_sse, o);
+    if (lane == 0 && my_sse != 0.0) atomicAdd(&sse_sm, my_sse);
+    __syncthreads();
+    if (tid == 0 && sse_sm != 0.0) atomicAdd(a.sse + (f + a.frame_offset) / a.chunk_size, sse_sm);
+  }
+}
+
+bool fast_geom(const ConvGeom& g) { return g.k == 5 && g.s == 2 && g.Cb >= 1 && g.Cb <= 4 && g.Cs % 32 == 0; }
+
+}  // namespace
+
+int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* bias, float* out,
+                         const float* dact, int act, int n, cudaStream_t st) {
+  if (!fast_geom(g) || n <= 0) return 1;
+  ThinGeo t;
+  t.big = big; t.Hs = g.Hs; t.Ws = g.Ws; t.Cs = g.Cs; t.pt = g.pt; t.pl = g.pl; t.n = n;
+  const int tiles_x = bn_cdiv(g.Ws, TW), tiles_y = bn_cdiv(g.Hs, TH);
+  dim3 grid(tiles_x * tiles_y, n, g.Cs / 32);
+  if (n > 65535) return 1;
+  switch (g.Cb) {
+    case 1: thin_fprop_kernel<1><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
+    case 2: thin_fprop_kernel<2><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
+    case 3: thin_fprop_kernel<3><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
+    default: thin_fprop_kernel<4><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
+  }
+  BN_LAUNCHED();
+  return 0;
+}
+
+template <int CB>
+static int launch_thin_wgrad(const ThinGeo& t, const float* small, float* partial, int blocks, int tiles_x,
+                             int tiles_per_frame, long long total, int cgroups, cudaStream_t st) {
+  size_t smem = (size_t)8 * 25 * CB * 32 * sizeof(float);
+  auto kern = thin_wgrad_kernel<CB>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<dim3(blocks, cgroups), 256, smem, st>>>(t, small, partial, tiles_x, tiles_per_frame, total);
+  BN_LAUNCHED();
+  return 0;
+}
+
+int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
+                         size_t partial_floats, float* grad, cudaStream_t st) {
+  if (!fast_geom(g) || n <= 0 || grad == nullptr) return grad == nullptr ? 0 : 1;
+  ThinGeo t;
+  t.big = big; t.Hs = g.Hs; t.Ws = g.Ws; t.Cs = g.Cs; t.pt = g.pt; t.pl = g.pl; t.n = n;
+  const int tiles_x = bn_cdiv(g.Ws, TW), tiles_y = bn_cdiv(g.Hs, TH);
+  const int tpf = tiles_x * tiles_y;
+  const long long total = (long long)tpf * n;
+  const int Ktot = 25 * g.Cb;
+  long long blocks = total < 2 * 148 ? total : 2 * 148;
+  long long cap = (long long)(partial_floats / ((size_t)Ktot * g.Cs));
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) return 1;
+  int r;
+  switch (g.Cb) {
+    case 1: r = launch_thin_wgrad<1>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
+    case 2: r = launch_thin_wgrad<2>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
+    case 3: r = launch_thin_wgrad<3>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
+    default: r = launch_thin_wgrad<4>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
+  }
+  if (r) return r;
+  return bn_launch_wgrad_reduce(partial, (int)blocks, Ktot, g.Cs, g.Cb, 25, g.d_fprop, grad, st);
+}
+
+template <int CB>
+static int launch_dgrad5(const Dg5Args& a, dim3 grid, int tiles_x, size_t smem, cudaStream_t st) {
+  auto kern = thin_dgrad5_kernel<CB>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  kern<<<grid, 256, smem, st>>>(a, tiles_x);
+  BN_LAUNCHED();
+  return 0;
+}
+
+int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd, const float* bias, int n,
+                          float* xhat_ws, float* xhat_user, const float* target, const float* mask,
+                          int chunk_size, int frame_offset, int n_total, float grad_coef, double* sse,
+                          float* dpre, cudaStream_t st) {
+  if (!(g.k == 5 && g.s == 2 && g.Cb >= 1 && g.Cb <= 4 && g.Cs % 4 == 0) || n <= 0 || n > 65535) return 1;
+  size_t smem = ((size_t)DP * DP * (g.Cs + 4) + (size_t)25 * g.Cb * g.Cs) * sizeof(float);
+  if (smem > 96 * 1024) return 1;
+  Dg5Args a;
+  a.small = small; a.Hs = g.Hs; a.Ws = g.Ws; a.Cs = g.Cs; a.Hb = g.Hb; a.Wb = g.Wb; a.pt = g.pt; a.pl = g.pl;
+  a.n = n; a.wd = wd; a.bias = bias; a.xhat_ws = xhat_ws; a.xhat_user = xhat_user; a.target = target;
+  a.mask = mask; a.n_total = n_total > 0 ? n_total : n; a.frame_offset = frame_offset;
+  a.chunk_size = chunk_size > 0 ? chunk_size : a.n_total; a.coef = grad_coef; a.sse = sse; a.dpre = dpre;
+  const int tiles_x = bn_cdiv(g.Wb, DT), tiles_y = bn_cdiv(g.Hb, DT);
+  dim3 grid(tiles_x * tiles_y, n);
+  switch (g.Cb) {
+    case 1: return launch_dgrad5<1>(a, grid, tiles_x, smem, st);
+    case 2: return launch_dgrad5<2>(a, grid, tiles_x, smem, st);
+    case 3: return launch_dgrad5<3>(a, grid, tiles_x, smem, st);
+    default: return launch_dgrad5<4>(a, grid, tiles_x, smem, st);
+  }
+}

@@ -46,10 +46,27 @@ def tols(tc_mode):
     # True).  Reconstructions stay within the north-star 1e-4; gradients of this random-init
     # network are tiny sums with heavy cancellation, and scripts/diag_precision.py (run on B200,
     # profiles/r01_precision.txt) measures 1e-2..7e-2 relative-to-max deviation from the fp64 oracle
-    # for BOTH our TF32 path and eager PyTorch-on-CUDA with its default TF32 convolutions; the bound
-    # below is that yardstick, not an fp32 round-off bound.
-    return dict(xhat=1e-4, z=2e-5 if tc_mode == 0 else 2e-3, grad=1e-4 if tc_mode == 0 else 1.5e-1,
+    # for BOTH our TF32 path and eager PyTorch-on-CUDA with its default TF32 convolutions (up to
+    # 1.2e-1 on the 7-frame 64x48 case for both); the mode-1 bound below is that yardstick, not an
+    # fp32 round-off bound.  What proves the tensor-core kernels themselves is
+    # tests/test_gpu_kernels.py: <= 2e-5 against the CUDA-core kernels on TF32-exact data.
+    return dict(xhat=1e-4, z=2e-5 if tc_mode == 0 else 2e-3, grad=1e-4 if tc_mode == 0 else 2.5e-1,
                 loss=1e-5 if tc_mode == 0 else 1e-4)
+
+
+def compare_grad(gold, key, g, tc_mode, t, factor=1.0):
+    scale = max(float(np.abs(gold[key + '#val']).max()) if key + '#val' in gold
+                else float(np.abs(gold[key]).max()), 1e-12)
+    if tc_mode == 0:
+        golden_compare(gold, key, g, rtol=factor * t['grad'], atol=factor * t['grad'] * scale)
+    else:   # norm-wise relative error on the stored entries
+        a = g.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        if key in gold:
+            ref = gold[key].reshape(-1).astype(np.float64)
+        else:
+            a, ref = a[gold[key + '#idx']], gold[key + '#val'].astype(np.float64)
+        err = np.linalg.norm(a - ref) / max(np.linalg.norm(ref), 1e-30)
+        assert err < t['grad'], (key, err)
 
 
 @pytest.mark.parametrize('tc_mode', [0, 1])
@@ -74,11 +91,7 @@ def test_ae_forward_and_loss_match_reference_goldens(case, tc_mode):
         ref = float(gold['loss' + tag])
         assert abs(out['loss'] - ref) <= t['loss'] * abs(ref), (out, ref)
         for name, p in model.named_parameters():
-            key = 'grad%s.%s' % (tag, name)
-            g = p.grad
-            scale = max(float(np.abs(gold[key + '#val']).max()) if key + '#val' in gold
-                        else float(np.abs(gold[key]).max()), 1e-12)
-            golden_compare(gold, key, g, rtol=t['grad'], atol=t['grad'] * scale)
+            compare_grad(gold, 'grad%s.%s' % (tag, name), p.grad, tc_mode, t)
 
 
 @pytest.mark.parametrize('tc_mode', [0, 1])
@@ -106,9 +119,7 @@ def test_psvae_forward_and_loss_match_reference_goldens(case, tc_mode):
         if key not in gold and key + '#val' not in gold:
             assert not p.requires_grad
             continue
-        scale = max(float(np.abs(gold[key + '#val']).max()) if key + '#val' in gold
-                    else float(np.abs(gold[key]).max()), 1e-12)
-        golden_compare(gold, key, p.grad, rtol=4 * t['grad'], atol=4 * t['grad'] * scale)
+        compare_grad(gold, key, p.grad, tc_mode, t, factor=4.0)
 
 
 @pytest.mark.parametrize('tc_mode', [0, 1])

@@ -18,10 +18,10 @@ def _exact(shape, gen, scale=16, span=8):
     return (torch.randint(-span, span + 1, shape, generator=gen).float() / scale)
 
 
-def _setup(n_ch=1, n=32):
+def _setup(n_ch=1, n=32, h=128, w=128):
     from behavenet_b200 import _lib
     from behavenet_b200.models import AE
-    hp = co.make_hparams(n_ch, 128, 128, 12)
+    hp = co.make_hparams(n_ch, h, w, 12)
     model = AE(copy.deepcopy(hp))
     g = torch.Generator().manual_seed(0)
     with torch.no_grad():
@@ -59,11 +59,14 @@ def _run(lib, drv, params, packed, ws, side, layer, op, n, a, b, out, mode):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize('geom', [(32, 128, 128), (7, 64, 48), (50, 96, 80)])
 @pytest.mark.parametrize('side,layer', [(0, 1), (0, 2), (0, 3), (0, 4), (1, 0), (1, 1), (1, 2), (1, 3)])
 @pytest.mark.parametrize('op', [0, 1, 2])
-def test_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op):
-    n = 32
-    lib, model, drv, params, packed, ws, hp = _setup(n=n)
+def test_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op, geom):
+    """geom = (frames, H, W): the C2 shape, the integration-test shape with ragged tiles (rows and
+    reduction lengths that are not multiples of the tile sizes), and a mid-size odd shape."""
+    n, h, w = geom
+    lib, model, drv, params, packed, ws, hp = _setup(n=n, h=h, w=w)
     big, small = _dims(hp, side, layer)
     g = torch.Generator().manual_seed(100 * side + 10 * layer + op)
     xb = _exact((n,) + big, g).cuda()

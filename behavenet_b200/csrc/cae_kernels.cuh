@@ -96,8 +96,8 @@ int bn_launch_decff_bwd(const float* z, const float* w, const float* dh0, int n,
 //   wt : K-major packed weights [Co][wrow], wrow = k*k*Ci, TF32-rounded
 //   split_buf : scratch for the split-K variant (few output tiles, long reduction); may be NULL
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
-                       int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes, int nclasses,
-                       int maxM, int maxtaps, int gs, int os, int n, int act, float* split_buf,
-                       size_t split_floats, cudaStream_t st);
+                       int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
+                       const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
+                       int act, float* split_buf, size_t split_floats, cudaStream_t st);
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n,
                        float* partial, size_t partial_floats, float* grad, cudaStream_t st);

@@ -118,8 +118,8 @@ int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const flo
   if (g_tc_mode.load()) {
     int maxtaps = 0;
     for (int c = 0; c < nclasses; ++c) maxtaps = std::max(maxtaps, p->h_tables[table_idx + c].ntaps);
-    int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, maxtaps, gs, os,
-                               n, act, t_split_buf, t_split_floats, st);
+    int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, p->h_tables.data() + table_idx,
+                               nclasses, maxM, maxtaps, gs, os, n, act, t_split_buf, t_split_floats, st);
     if (r <= 0) return r;
   }
   return bn_launch_igemm(in, w, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n, act, st);

@@ -14,6 +14,14 @@
 // Weights are pre-packed K-major ([c_out][(tap, c_in)]) and pre-rounded to TF32 (cvt.rna) by
 // bn_cae_pack_params; activations are consumed as stored (the tensor core ignores the low 13
 // mantissa bits).
+#include <cuda.h>
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
 #include "cae_kernels.cuh"
 
 namespace {
@@ -351,6 +359,285 @@ int launch_tc(const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA-fed variant of the implicit GEMM (fprop form and dgrad form with <= 4 residue classes).
+// The whole producer side collapses to ONE thread issuing two bulk-tensor copies per k-chunk:
+//   * A: cp.async.bulk.tensor.4d ... im2col -- the TMA unit walks 128 consecutive output pixels of
+//     the NHWC activation (wrapping over rows and frames inside the bounding box that encodes the
+//     padding), fetches 32 channels at the filter-tap offset, zero-fills out-of-image taps and
+//     writes the SWIZZLE_128B tile the MMA descriptors expect;
+//   * B: a plain 2-D tile of the K-major weights.
+// Completion is signalled on the stage's mbarrier by transaction bytes (complete_tx).
+// ------------------------------------------------------------------------------------------------
+struct alignas(64) TmaSet {
+  CUtensorMap a[4];     // one im2col map per residue class
+  CUtensorMap b;        // weights [Co][KK*Ci]
+  int lw[4], lh[4];     // bounding-box lower corner per class (tensor coordinates of base pixel 0)
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w,
+                                              int h, int n, uint16_t offw, uint16_t offh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(offw), "h"(offh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_constant__ TmaSet tm, const TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using S = TcSmem<BN, STAGES>;
+  constexpr int NCOLS = BN < 32 ? 32 : BN;
+  unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  TapClass* cls = reinterpret_cast<TapClass*>(tmem_ptr + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int cls_idx = a.ksplit > 1 ? 0 : blockIdx.z;
+  {
+    const int* src = reinterpret_cast<const int*>(a.classes + cls_idx);
+    int* dst = reinterpret_cast<int*>(cls);
+    for (int i = tid; i < (int)(sizeof(TapClass) / 4); i += NTHREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int HmWm = cls->Hm * cls->Wm;
+  const long long M = (long long)a.n * HmWm;
+  const long long m0 = (long long)blockIdx.x * BM;
+  if (m0 >= M) return;
+  if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n0 = blockIdx.y * BN;
+  const int Ci = a.Ci;
+  const int cpt = Ci / BK;
+  int cbeg = 0, nchunks = cls->ntaps * cpt;
+  if (a.ksplit > 1) {
+    const int per = (nchunks + a.ksplit - 1) / a.ksplit;
+    cbeg = blockIdx.z * per;
+    const int cend = cbeg + per < nchunks ? cbeg + per : nchunks;
+    nchunks = cend > cbeg ? cend - cbeg : 0;
+  }
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp < 4) {
+    if (tid == 0) {
+      // ======================= TMA producer (one thread) =========================================
+      const int f0 = (int)(m0 / HmWm);
+      const int rem0 = (int)(m0 - (long long)f0 * HmWm);
+      const int ym0 = rem0 / cls->Wm, xm0 = rem0 - ym0 * cls->Wm;
+      const int lw = tm.lw[cls_idx], lh = tm.lh[cls_idx];
+      const int w0 = lw + xm0 * a.gs, h0 = lh + ym0 * a.gs;
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        if (c >= STAGES) mbar_wait(smem_u32(empty_bar + stage), ((c / STAGES) - 1) & 1);
+        const int tap = (cbeg + c) / cpt;
+        const int c0 = (cbeg + c - tap * cpt) * BK;
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t bar = smem_u32(full_bar + stage);
+        mbar_expect_tx(bar, (uint32_t)S::STAGE_BYTES);
+        tma_im2col_4d(sa, &tm.a[cls_idx], bar, c0, w0, h0, f0, (uint16_t)(cls->dx[tap] - lw),
+                      (uint16_t)(cls->dy[tap] - lh));
+        tma_tile_2d(sb, &tm.b, bar, cls->wt[tap] * Ci + c0, n0);
+      }
+    }
+    __syncwarp();
+    // ======================= epilogue ============================================================
+    const long long m = m0 + tid;
+    const bool rvalid = m < M;
+    if (nchunks > 0) {
+      mbar_wait(smem_u32(accum_bar), 0);
+      tc_fence_after();
+    }
+    long long obase = 0;
+    if (rvalid) {
+      int f = (int)(m / HmWm);
+      int rem = (int)(m - (long long)f * HmWm);
+      int ym = rem / cls->Wm;
+      int xm = rem - ym * cls->Wm;
+      int oy = cls->oy0 + a.os * ym, ox = cls->ox0 + a.os * xm;
+      obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + n0;
+    }
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t r[32];
+      if (nchunks > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) r[q] = 0u;
+      }
+      if (rvalid && a.ksplit > 1) {
+        float* po = a.split_out + ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32;
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(po + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                                           __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+      } else if (rvalid) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(r[q + e]);
+            if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q + e);
+            if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+            else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+            v[e] = x;
+          }
+          const long long idx = obase + j * 32 + q;
+          if (a.dact) {
+            float4 d = __ldg(reinterpret_cast<const float4*>(a.dact + idx));
+            v[0] *= d.x > 0.f ? 1.f : BN_LEAK;
+            v[1] *= d.y > 0.f ? 1.f : BN_LEAK;
+            v[2] *= d.z > 0.f ? 1.f : BN_LEAK;
+            v[3] *= d.w > 0.f ? 1.f : BN_LEAK;
+          }
+          *reinterpret_cast<float4*>(a.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        mbar_wait(smem_u32(full_bar + stage), (c / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          uint64_t ad = make_desc_sw128(sa + k * 32);
+          uint64_t bd = make_desc_sw128(sb + k * 32);
+          umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(empty_bar + stage));
+      }
+      if (nchunks > 0) umma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<NCOLS>(tmem_base);
+  }
+}
+
+// ---- host side: tensor-map encoding through the driver entry points (no link-time libcuda) ------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_tma_state = 0;      // 0 unknown, 1 available, -1 unavailable
+// BN_TMA=0 in the environment selects the cp.async producers instead (A/B tests)
+std::mutex g_tma_mutex;
+
+bool tma_available() {
+  std::lock_guard<std::mutex> lk(g_tma_mutex);
+  if (g_tma_state == 0) {
+    const char* env = getenv("BN_TMA");
+    if (env && env[0] == '0') {
+      g_tma_state = -1;
+      return false;
+    }
+    void* f1 = nullptr;
+    void* f2 = nullptr;
+    cudaDriverEntryPointQueryResult q1, q2;
+    cudaError_t e1 = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q1);
+    cudaError_t e2 = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q2);
+    if (e1 == cudaSuccess && e2 == cudaSuccess && f1 && f2 && q1 == cudaDriverEntryPointSuccess &&
+        q2 == cudaDriverEntryPointSuccess) {
+      g_encode_tiled = (EncodeTiledFn)f1;
+      g_encode_im2col = (EncodeIm2colFn)f2;
+      g_tma_state = 1;
+    } else {
+      g_tma_state = -1;
+      cudaGetLastError();
+    }
+  }
+  return g_tma_state == 1;
+}
+
+// im2col map over an NHWC fp32 image: `count_w x count_h` base pixels per frame starting at
+// (lw, lh) with traversal stride `ts`; box = 32 channels x `pixels` base pixels
+bool encode_im2col(CUtensorMap* map, const float* p, int N, int H, int W, int C, int lw, int lh, int count_w,
+                   int count_h, int ts, int pixels, CUtensorMapSwizzle swz) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  // number of base pixels along w: (W + upper - lower - 1) / ts + 1 == count_w
+  int lower[2] = {lw, lh};
+  int upper[2] = {(count_w - 1) * ts + lw + 1 - W, (count_h - 1) * ts + lh + 1 - H};
+  for (int i = 0; i < 2; ++i)
+    if (lower[i] < -128 || lower[i] > 127 || upper[i] < -128 || upper[i] > 127) return false;
+  cuuint32_t estr[4] = {1, (cuuint32_t)ts, (cuuint32_t)ts, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p, gdim, gstr, lower, upper, 32,
+                               (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool encode_tiled_2d(CUtensorMap* map, const float* p, long long rows, long long cols, int box_cols, int box_rows,
+                     CUtensorMapSwizzle swz) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+int launch_tma(const TmaSet& tm, const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  auto kern = igemm_tma_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, a.ksplit > 1 ? a.ksplit : nclasses);
+  kern<<<grid, NTHREADS, S::TOTAL, st>>>(tm, a);
+  BN_LAUNCHED();
+  return 0;
+}
+
 // out[i] = act(bias[i % Co] + sum_z part[z][i]) * lrelu'(dact[i])
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long total, int Co,
                                      const float* __restrict__ bias, const float* __restrict__ dact, int act,
@@ -597,10 +884,54 @@ int launch_wgrad_tc(const WgTcArgs& a, int splits, cudaStream_t st) {
 
 }  // namespace
 
+namespace {
+
+struct TmaKey {
+  const void* in;
+  const void* wt;
+  const void* cls;
+  int n, H, W, C, gs, nclasses, Co, wrow;
+  bool operator==(const TmaKey& o) const {
+    return in == o.in && wt == o.wt && cls == o.cls && n == o.n && H == o.H && W == o.W && C == o.C &&
+           gs == o.gs && nclasses == o.nclasses && Co == o.Co && wrow == o.wrow;
+  }
+};
+std::vector<std::pair<TmaKey, TmaSet>> g_tma_cache;
+
+// Tensor maps of one op (cached: activations live at stable workspace addresses across steps)
+const TmaSet* get_tma_set(const ImgView& in, const float* wt, int wrow, int Co, int bn, const TapClass* d_classes,
+                          const TapClass* h_classes, int nclasses, int gs, int n) {
+  if (nclasses > 4 || !tma_available()) return nullptr;
+  TmaKey key{in.p, wt, d_classes, n, in.H, in.W, in.C, gs, nclasses, Co, wrow};
+  std::lock_guard<std::mutex> lk(g_tma_mutex);
+  for (auto& kv : g_tma_cache)
+    if (kv.first == key) return &kv.second;
+  TmaSet tm;
+  memset(&tm, 0, sizeof(tm));
+  for (int c = 0; c < nclasses; ++c) {
+    const TapClass& k = h_classes[c];
+    if (k.ntaps == 0 || k.Hm == 0 || k.Wm == 0) continue;
+    int lw = 127, lh = 127;
+    for (int t = 0; t < k.ntaps; ++t) {
+      lw = k.dx[t] < lw ? k.dx[t] : lw;
+      lh = k.dy[t] < lh ? k.dy[t] : lh;
+    }
+    tm.lw[c] = lw; tm.lh[c] = lh;
+    if (!encode_im2col(&tm.a[c], in.p, n, in.H, in.W, in.C, lw, lh, k.Wm, k.Hm, gs, BM, CU_TENSOR_MAP_SWIZZLE_128B))
+      return nullptr;
+  }
+  if (!encode_tiled_2d(&tm.b, wt, Co, wrow, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B)) return nullptr;
+  if (g_tma_cache.size() >= 256) g_tma_cache.clear();
+  g_tma_cache.emplace_back(key, tm);
+  return &g_tma_cache.back().second;
+}
+
+}  // namespace
+
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
-                       int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes, int nclasses,
-                       int maxM, int maxtaps, int gs, int os, int n, int act, float* split_buf,
-                       size_t split_floats, cudaStream_t st) {
+                       int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
+                       const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
+                       int act, float* split_buf, size_t split_floats, cudaStream_t st) {
   // shapes this kernel covers: NHWC-dense input with C % 32 == 0, C_out in {32, 64, 128, 256, 512},
   // enough rows to fill the machine (the stride-5 layers with a few hundred rows stay on the
   // CUDA-core kernel until the split-K variant lands)
@@ -630,11 +961,22 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   a.Ho = Ho; a.Wo = Wo; a.Co = Co; a.dact = dact; a.classes = d_classes; a.gs = gs; a.os = os;
   a.n = n; a.act = act;
   int r;
-  switch (Co) {
-    case 32: r = launch_tc<32, 4>(a, nclasses, maxM, st); break;
-    case 64: r = launch_tc<64, 4>(a, nclasses, maxM, st); break;
-    case 128: r = launch_tc<128, 3>(a, nclasses, maxM, st); break;
-    default: r = launch_tc<256, 4>(a, nclasses, maxM, st); break;
+  const TmaSet* tm = get_tma_set(in, wt, wrow, Co, bn, d_classes, h_classes, nclasses, gs, n);
+  if (tm) {
+    TmaSet local = *tm;      // copied into the kernel parameter space (__grid_constant__)
+    switch (Co) {
+      case 32: r = launch_tma<32, 4>(local, a, nclasses, maxM, st); break;
+      case 64: r = launch_tma<64, 4>(local, a, nclasses, maxM, st); break;
+      case 128: r = launch_tma<128, 3>(local, a, nclasses, maxM, st); break;
+      default: r = launch_tma<256, 4>(local, a, nclasses, maxM, st); break;
+    }
+  } else {
+    switch (Co) {
+      case 32: r = launch_tc<32, 4>(a, nclasses, maxM, st); break;
+      case 64: r = launch_tc<64, 4>(a, nclasses, maxM, st); break;
+      case 128: r = launch_tc<128, 3>(a, nclasses, maxM, st); break;
+      default: r = launch_tc<256, 4>(a, nclasses, maxM, st); break;
+    }
   }
   if (r || ksplit == 1) return r;
   const long long total = M * Co;          // fprop-form output is linear in (m, co)

@@ -867,6 +867,158 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const WgTcArgs a) {
   }
 }
 
+// TMA-fed weight gradient: one thread issues, per 32-pixel chunk, one im2col copy per 32-channel
+// slab of the A tile (each slab = one filter tap x 32 channels) and one 2-D copy per 32-channel slab
+// of the small image; both land as 32 rows x 128 bytes with the 32-byte-atom 128B swizzle, i.e. the
+// MN-major canonical layout with LBO = 4096 (next slab) and SBO = 512 (next 4 pixels).
+struct alignas(64) WgTmaSet {
+  CUtensorMap a;      // im2col over the big image, 32 pixels x 32 channels per copy
+  CUtensorMap s;      // small image as a [M][Cs] matrix, 32 rows x 32 channels per copy
+  int lw, lh;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_constant__ WgTmaSet tm, const WgTcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using S = TcSmem<BN, STAGES>;
+  constexpr int NCOLS = BN < 32 ? 32 : BN;
+  unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  TapClass* cls = reinterpret_cast<TapClass*>(tmem_ptr + 2);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  {
+    const int* src = reinterpret_cast<const int*>(a.cls);
+    int* dst = reinterpret_cast<int*>(cls);
+    for (int i = tid; i < (int)(sizeof(TapClass) / 4); i += NTHREADS) dst[i] = src[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full_bar + s), 1);
+      mbar_init(smem_u32(empty_bar + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int HsWs = a.Hs * a.Ws;
+  const long long M = (long long)a.n * HsWs;
+  const long long mbeg = (long long)blockIdx.z * a.rows_per_split;
+  const long long mend = mbeg + a.rows_per_split < M ? mbeg + a.rows_per_split : M;
+  const int nchunks = mbeg < mend ? (int)((mend - mbeg + BK - 1) / BK) : 0;
+  const int kk0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Cb = a.Cb, Cs = a.Cs;
+  const uint32_t smem_base = smem_u32(smem);
+  constexpr uint32_t SLAB = 32 * 128;                 // 32 pixels x 32 channels
+  constexpr uint32_t LBO = SLAB, SBO = 512;
+
+  if (warp < 4) {
+    if (tid == 0) {
+      // valid 32-channel slabs of this M-tile (the last tile of Ktot = 25*Cb may be short)
+      int nslab = (a.Ktot - kk0 + 31) / 32;
+      nslab = nslab > BM / 32 ? BM / 32 : nslab;
+      const uint32_t bytes = (uint32_t)(nslab * SLAB + (BN / 32) * SLAB);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        if (c >= STAGES) mbar_wait(smem_u32(empty_bar + stage), ((c / STAGES) - 1) & 1);
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t bar = smem_u32(full_bar + stage);
+        const long long mc = mbeg + (long long)c * BK;
+        const int f = (int)(mc / HsWs);
+        const int rem = (int)(mc - (long long)f * HsWs);
+        const int ym = rem / a.Ws, xm = rem - ym * a.Ws;
+        const int w0 = tm.lw + xm * a.gs, h0 = tm.lh + ym * a.gs;
+        mbar_expect_tx(bar, bytes);
+        for (int j = 0; j < nslab; ++j) {
+          const int akk = kk0 + 32 * j;
+          const int tap = akk / Cb;
+          const int cb0 = akk - tap * Cb;
+          tma_im2col_4d(sa + j * SLAB, &tm.a, bar, cb0, w0, h0, f, (uint16_t)(cls->dx[tap] - tm.lw),
+                        (uint16_t)(cls->dy[tap] - tm.lh));
+        }
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) tma_tile_2d(sb + j * SLAB, &tm.s, bar, n0 + 32 * j, (int)mc);
+      }
+    }
+    __syncwarp();
+    if (nchunks > 0) {
+      mbar_wait(smem_u32(accum_bar), 0);
+      tc_fence_after();
+    }
+    const int kk = kk0 + tid;
+    float* prow = a.partial + ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+#pragma unroll 1
+    for (int j = 0; j < BN / 32; ++j) {
+      uint32_t r[32];
+      if (nchunks > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) r[q] = 0u;
+      }
+      if (kk < a.Ktot) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          *reinterpret_cast<float4*>(prow + j * 32 + q) =
+              make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
+                          __uint_as_float(r[q + 3]));
+      }
+    }
+    tc_fence_before();
+  } else {
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc = make_idesc_mn(BM, BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        mbar_wait(smem_u32(full_bar + stage), (c / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          uint64_t ad = make_desc_mn_sw128(sa + k * 2 * SBO, LBO, SBO);
+          uint64_t bd = make_desc_mn_sw128(sb + k * 2 * SBO, LBO, SBO);
+          umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(empty_bar + stage));
+      }
+      if (nchunks > 0) umma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<NCOLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+int launch_wgrad_tma(const WgTmaSet& tm, const WgTcArgs& a, int splits, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  auto kern = wgrad_tma_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  dim3 grid(bn_cdiv(a.Ktot, BM), a.Cs / BN, splits);
+  kern<<<grid, NTHREADS, S::TOTAL, st>>>(tm, a);
+  BN_LAUNCHED();
+  return 0;
+}
+
 template <int BN, int STAGES>
 int launch_wgrad_tc(const WgTcArgs& a, int splits, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
@@ -985,6 +1137,39 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   return 0;
 }
 
+namespace {
+
+struct WgKey {
+  const void* big;
+  const void* small;
+  int n, H, W, C, Hs, Ws, Cs, k, s, pt, pl;
+  bool operator==(const WgKey& o) const {
+    return big == o.big && small == o.small && n == o.n && H == o.H && W == o.W && C == o.C && Hs == o.Hs &&
+           Ws == o.Ws && Cs == o.Cs && k == o.k && s == o.s && pt == o.pt && pl == o.pl;
+  }
+};
+std::vector<std::pair<WgKey, WgTmaSet>> g_wg_cache;
+
+const WgTmaSet* get_wgrad_tma_set(const ImgView& big, const float* small, const ConvGeom& g, int n, long long M) {
+  if (!tma_available()) return nullptr;
+  WgKey key{big.p, small, n, big.H, big.W, big.C, g.Hs, g.Ws, g.Cs, g.k, g.s, g.pt, g.pl};
+  std::lock_guard<std::mutex> lk(g_tma_mutex);
+  for (auto& kv : g_wg_cache)
+    if (kv.first == key) return &kv.second;
+  WgTmaSet tm;
+  memset(&tm, 0, sizeof(tm));
+  tm.lw = -g.pl; tm.lh = -g.pt;
+  if (!encode_im2col(&tm.a, big.p, n, big.H, big.W, big.C, tm.lw, tm.lh, g.Ws, g.Hs, g.s, BK,
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+    return nullptr;
+  if (!encode_tiled_2d(&tm.s, small, M, g.Cs, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return nullptr;
+  if (g_wg_cache.size() >= 256) g_wg_cache.clear();
+  g_wg_cache.emplace_back(key, tm);
+  return &g_wg_cache.back().second;
+}
+
+}  // namespace
+
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                        size_t partial_floats, float* grad, cudaStream_t st) {
   if (n <= 0 || grad == nullptr) return 0;
@@ -1019,6 +1204,18 @@ int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g
   a.Cs = Cs; a.cls = g.d_fprop; a.gs = g.s; a.n = n; a.Ktot = Ktot; a.rows_per_split = rps;
   a.partial = partial;
   int r;
+  const WgTmaSet* tm = get_wgrad_tma_set(big, small, g, n, M);
+  if (tm) {
+    WgTmaSet local = *tm;
+    switch (bn) {
+      case 32: r = launch_wgrad_tma<32, 4>(local, a, (int)splits, st); break;
+      case 64: r = launch_wgrad_tma<64, 4>(local, a, (int)splits, st); break;
+      case 128: r = launch_wgrad_tma<128, 3>(local, a, (int)splits, st); break;
+      default: r = launch_wgrad_tma<256, 4>(local, a, (int)splits, st); break;
+    }
+    if (r) return r;
+    return bn_launch_wgrad_reduce(partial, (int)splits, Ktot, Cs, g.Cb, g.k * g.k, g.d_fprop, grad, st);
+  }
   switch (bn) {
     case 32: r = launch_wgrad_tc<32, 4>(a, (int)splits, st); break;
     case 64: r = launch_wgrad_tc<64, 4>(a, (int)splits, st); break;

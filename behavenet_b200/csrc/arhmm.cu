@@ -90,14 +90,24 @@ __global__ void __launch_bounds__(128) emission_kernel(const EmitArgs<real> a) {
   const int trial = blockIdx.x;
   const long long beg = a.offsets[trial], end = a.offsets[trial + 1];
   const int T = (int)(end - beg);
-  const int t0 = blockIdx.y * TILE;
-  if (t0 >= T) return;
+  if ((int)blockIdx.y * TILE >= T) return;
   const int tid = threadIdx.x;
   {
+    // the whitened parameters are staged ONCE per block and reused for all of its time tiles
     const real* Wg = reinterpret_cast<const real*>(a.blob + (sizeof(real) == 4 ? hd->off_W_f : hd->off_W_d));
     const real* cg = reinterpret_cast<const real*>(a.blob + (sizeof(real) == 4 ? hd->off_c_f : hd->off_c_d));
-    for (int i = tid; i < K * J * DP; i += 128) Wsm[i] = Wg[i];
+    if ((K * J * DP * (int)sizeof(real)) % 16 == 0) {
+      const int4* src = reinterpret_cast<const int4*>(Wg);
+      int4* dst = reinterpret_cast<int4*>(Wsm);
+      for (int i = tid; i < K * J * DP * (int)sizeof(real) / 16; i += 128) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < K * J * DP; i += 128) Wsm[i] = Wg[i];
+    }
     for (int i = tid; i < K + 1; i += 128) csm[i] = cg[i];
+  }
+  for (int t0 = blockIdx.y * TILE; t0 < T; t0 += gridDim.y * TILE) {
+  __syncthreads();      // previous tile's x / out staging is no longer read
+  {
     // x rows t0-L .. t0+TILE-1 of this trial (rows before the trial start are never used)
     const int nrows = min(TILE, T - t0) + L;
     const float* xg = a.x + (beg + t0 - L) * D;
@@ -108,60 +118,93 @@ __global__ void __launch_bounds__(128) emission_kernel(const EmitArgs<real> a) {
   }
   __syncthreads();
 
+  // Register tile: KG states x TS timesteps x DP whitened residual components per thread.  Every
+  // W row (DP values, one broadcast LDS.128 per 4) is reused for TS timesteps and every psi value
+  // (one conflict-free LDS) for KG states, so the loop is FMA-bound instead of LDS-bound.
+  constexpr int REGW = (int)(sizeof(real) / 4);
+  constexpr int KG0 = 96 / (TS * DP * REGW);
+  constexpr int KG = KG0 < 1 ? 1 : (KG0 > 4 ? 4 : KG0);
+  constexpr int VEC = 16 / (int)sizeof(real);          // elements per 16-byte shared load
+  struct alignas(16) Vec { real v[VEC]; };
+  real vmax[TS];
+#pragma unroll
+  for (int s = 0; s < TS; ++s) vmax[s] = (real)-INFINITY;
+  for (int kg = 0; kg < K; kg += KG) {
+    real acc[KG][TS][DP];
+#pragma unroll
+    for (int g = 0; g < KG; ++g)
+#pragma unroll
+      for (int s = 0; s < TS; ++s)
+#pragma unroll
+        for (int i = 0; i < DP; ++i) acc[g][s][i] = 0;
+    const real* Wg[KG];
+#pragma unroll
+    for (int g = 0; g < KG; ++g) Wg[g] = Wsm + (size_t)min(kg + g, K - 1) * J * DP;
+    int l = 0, d = 0;
+    for (int j = 0; j < J - 1; ++j) {
+      real p[TS];
+#pragma unroll
+      for (int s = 0; s < TS; ++s) p[s] = (real)xs[(size_t)(tid + 128 * s + L - l) * XS + d];
+#pragma unroll
+      for (int g = 0; g < KG; ++g) {
+        const Vec* wr = reinterpret_cast<const Vec*>(Wg[g] + (size_t)j * DP);
+#pragma unroll
+        for (int i4 = 0; i4 < DP / VEC; ++i4) {
+          const Vec w = wr[i4];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e)
+#pragma unroll
+            for (int s = 0; s < TS; ++s) acc[g][s][i4 * VEC + e] = fma(p[s], w.v[e], acc[g][s][i4 * VEC + e]);
+        }
+      }
+      if (++d == D) { d = 0; ++l; }
+    }
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+      const int k = kg + g;
+      const real* wb = Wg[g] + (size_t)(J - 1) * DP;
+#pragma unroll
+      for (int s = 0; s < TS; ++s) {
+        real q = 0;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) {
+          const real y = acc[g][s][i] + wb[i];
+          q = fma(y, y, q);
+        }
+        const real v = csm[min(k, K - 1)] - (real)0.5 * q;
+        const int tl = tid + 128 * s;
+        const int t = t0 + tl;
+        if (k < K && t < T && t >= L) {
+          if (sizeof(real) == 4) {
+            outs[tl * (K + 1) + k] = (float)v;
+            vmax[s] = v > vmax[s] ? v : vmax[s];
+          } else {
+            a.ll[(beg + t) * K + k] = (double)v;
+          }
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int s = 0; s < TS; ++s) {
     const int tl = tid + 128 * s;
     const int t = t0 + tl;
     if (t >= T) continue;
-    const float* xr = xs + (size_t)(tl + L) * XS;    // row of x_t; x_{t-l} is l rows above
-    real llk_max = (real)-INFINITY;
     if (t < L) {
       // initial segment: N(0, I) for every state (ssm mu_init = 0, Sigma_init = I)
+      const float* xr = xs + (size_t)(tl + L) * XS;
       real q = 0;
-      for (int d = 0; d < D; ++d) q += (real)xr[d] * (real)xr[d];
-      real v = csm[K] - (real)0.5 * q;
+      for (int dd = 0; dd < D; ++dd) q += (real)xr[dd] * (real)xr[dd];
+      const real v = csm[K] - (real)0.5 * q;
       if (sizeof(real) == 4) {
         for (int k = 0; k < K; ++k) outs[tl * (K + 1) + k] = 1.f;
         a.mx[beg + t] = (float)v;
       } else {
         for (int k = 0; k < K; ++k) a.ll[(beg + t) * K + k] = (double)v;
       }
-      continue;
-    }
-    for (int k = 0; k < K; ++k) {
-      real acc[DP];
-#pragma unroll
-      for (int i = 0; i < DP; ++i) acc[i] = 0;
-      const real* Wk = Wsm + (size_t)k * J * DP;
-      // psi = [x_t, x_{t-1}, ..., x_{t-L}, 1]
-      for (int l = 0; l <= L; ++l) {
-        const float* xl = xr - (size_t)l * XS;
-        for (int d = 0; d < D; ++d) {
-          const real p = (real)xl[d];
-          const real* wj = Wk + (size_t)(l * D + d) * DP;
-#pragma unroll
-          for (int i = 0; i < DP; ++i) acc[i] = fma(p, wj[i], acc[i]);
-        }
-      }
-      {
-        const real* wj = Wk + (size_t)(J - 1) * DP;
-#pragma unroll
-        for (int i = 0; i < DP; ++i) acc[i] += wj[i];
-      }
-      real q = 0;
-#pragma unroll
-      for (int i = 0; i < DP; ++i) q = fma(acc[i], acc[i], q);
-      real v = csm[k] - (real)0.5 * q;
-      if (sizeof(real) == 4) {
-        outs[tl * (K + 1) + k] = (float)v;
-        llk_max = v > llk_max ? v : llk_max;
-      } else {
-        a.ll[(beg + t) * K + k] = (double)v;
-      }
-    }
-    if (sizeof(real) == 4) {
-      for (int k = 0; k < K; ++k) outs[tl * (K + 1) + k] = expf(outs[tl * (K + 1) + k] - (float)llk_max);
-      a.mx[beg + t] = (float)llk_max;
+    } else if (sizeof(real) == 4) {
+      for (int k = 0; k < K; ++k) outs[tl * (K + 1) + k] = expf(outs[tl * (K + 1) + k] - (float)vmax[s]);
+      a.mx[beg + t] = (float)vmax[s];
     }
   }
   if (sizeof(real) == 4) {
@@ -173,6 +216,7 @@ __global__ void __launch_bounds__(128) emission_kernel(const EmitArgs<real> a) {
       og[i] = outs[r * (K + 1) + c];
     }
   }
+  }   // time-tile loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -194,6 +238,7 @@ struct ScanArgs {
   float* Ez;      // nullable
   float* Ezz;     // nullable
   double* logZ;   // nullable
+  float* cinv;    // (total_T) workspace: 1 / c_t of the forward sweep, reused by the backward sweep
 };
 
 template <int KP>
@@ -229,81 +274,171 @@ __global__ void __launch_bounds__(128) scan_kernel(const ScanArgs a) {
   float* Ep = want_post ? a.Ez + beg * K + k : nullptr;
 
   // ---------------- forward
+  // Lazily normalised recursion.  The state a_t carried on the serial chain is
+  //     a_t(k) = [sum_j a_{t-1}(j) P(j,k)] * b_t(k) / S_{t-1},     S_{t-1} = sum_j a_{t-1}(j),
+  // so sum_k a_t(k) = c_t (the per-step normaliser) and alpha_hat_t = a_t / S_t.  Each step the KP
+  // lanes of a trial exchange their state through a 2 x 32-float shared-memory slot (one STS, four
+  // broadcast LDS.128 per lane -- cheaper and shorter than KP shuffles), so every lane has all
+  // a_{t-1}(j) and S_{t-1} is a LOCAL sum: no cross-lane reduction sits between two steps.
+  // 1 / c_t is kept (a.cinv) so that the backward sweep needs no reduction at all.
+  __shared__ __align__(16) float xch[4][2][32];
+  const int wib = threadIdx.x >> 5;
+  const int gbase = (lane / KP) * KP;
+  constexpr int PF = 8;
   double logZ = 0.0;
-  float alpha = 0.f;
-  {
-    float b = (T > 0 && kvalid) ? __ldg(Bp) : 0.f;
-    alpha = pi0g[k] * b;
-    float c = group_sum<KP>(alpha);
-    float inv = c > 0.f ? 1.f / c : 0.f;
-    alpha *= inv;
-    if (T > 0) {
-      logZ += (double)logf(c) + (double)__ldg(mp);
-      if (want_post && kvalid) Ep[0] = alpha;
-    }
+  float acur = 0.f;                 // a_t(k)
+  float m0 = 0.f;
+  if (Tmax > 0) {
+    const float b0 = (T > 0 && kvalid) ? __ldg(Bp) : 0.f;
+    acur = pi0g[k] * b0;
+    if (T > 0) m0 = __ldg(mp);
   }
-  float bnext = (T > 1 && kvalid) ? __ldg(Bp + K) : 0.f;
-  float mnext = T > 1 ? __ldg(mp + 1) : 0.f;
-  for (int t = 1; t < Tmax; ++t) {
-    const bool on = t < T;
-    const float b = bnext;
-    const float m = mnext;
-    if (t + 1 < T) {
-      bnext = kvalid ? __ldg(Bp + (long long)(t + 1) * K) : 0.f;
-      mnext = __ldg(mp + t + 1);
+  logZ += (double)m0;
+  float* cip = a.cinv + beg;
+  int par = 0;
+  auto exchange = [&](float mine, float (&v)[KP]) {
+    xch[wib][par][lane] = mine;
+    __syncwarp();
+    if (KP >= 4) {
+#pragma unroll
+      for (int j = 0; j < KP; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&xch[wib][par][gbase + j]);
+        v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) v[j] = xch[wib][par][gbase + j];
     }
-    float s0 = 0.f, s1 = 0.f;
+    par ^= 1;
+  };
+  // steps every trial of this warp has (no per-step conditionals, prefetched inputs) ...
+  int Tmin = active ? T : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) Tmin = min(Tmin, __shfl_xor_sync(0xffffffffu, Tmin, o));
+  // one step of the forward recursion: consumes a_{t-1}, finalises step t-1, produces a_t
+  auto fwd_step = [&](int t, float b, float m, bool has_prev, bool has_cur, float& lsum) {
+    float v[KP];
+    exchange(acur, v);
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int j = 0; j < KP; j += 2) {
-      s0 = fmaf(__shfl_sync(0xffffffffu, alpha, j, KP), Pcol[j], s0);
-      s1 = fmaf(__shfl_sync(0xffffffffu, alpha, j + 1, KP), Pcol[j + 1], s1);
+      s0 = fmaf(v[j], Pcol[j], s0);
+      s1 = fmaf(v[j + 1], Pcol[j + 1], s1);
+      q0 += v[j];
+      q1 += v[j + 1];
     }
-    float an = (s0 + s1) * b;
-    float c = group_sum<KP>(an);
-    if (on) {
-      float inv = c > 0.f ? 1.f / c : 0.f;
-      alpha = an * inv;
-      logZ += (double)logf(c) + (double)m;
-      if (want_post && kvalid) Ep[(long long)t * K] = alpha;
+    const float S = q0 + q1;                       // = c_{t-1}
+    const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+    if (has_prev) {
+      lsum += __logf(S);
+      if (want_post && kvalid) Ep[(long long)(t - 1) * K] = acur * inv;
+      if (want_post && k == 0) cip[t - 1] = inv;
     }
+    if (has_cur) {
+      acur = (s0 + s1) * b * inv;
+      lsum += m;
+    }
+  };
+  int t = 1;
+  if (Tmin > 1) {
+    float bq[PF], mq[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int tt = min(1 + i, Tmin - 1);
+      bq[i] = kvalid ? __ldg(Bp + (long long)tt * K) : 0.f;
+      mq[i] = __ldg(mp + tt);
+    }
+    for (; t + PF <= Tmin; t += PF) {
+      float nb[PF], nm[PF];
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int tt = min(t + PF + i, Tmin - 1);
+        nb[i] = kvalid ? __ldg(Bp + (long long)tt * K) : 0.f;
+        nm[i] = __ldg(mp + tt);
+      }
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < PF; ++i) fwd_step(t + i, bq[i], mq[i], true, true, lsum);
+      logZ += (double)lsum;
+#pragma unroll
+      for (int i = 0; i < PF; ++i) { bq[i] = nb[i]; mq[i] = nm[i]; }
+    }
+  }
+  // ... and the ragged remainder (trial ends inside the warp's range), one checked step at a time
+  for (; t <= Tmax; ++t) {
+    const bool cur = t < T;
+    const float b = (cur && kvalid) ? __ldg(Bp + (long long)t * K) : 0.f;
+    const float m = cur ? __ldg(mp + t) : 0.f;
+    float lsum = 0.f;
+    fwd_step(t, b, m, t - 1 < T, cur, lsum);
+    logZ += (double)lsum;
   }
   if (active && k == 0 && a.logZ) a.logZ[trial] = logZ;
   if (!want_post && a.Ezz == nullptr) return;
 
   // ---------------- backward (lane j = k owns row j of P)
+  // Scaled with the forward normalisers: beta_hat_t(j) = sum_k P(j,k) b_{t+1}(k) beta_hat_{t+1}(k) / c_{t+1},
+  // which makes gamma_t = alpha_hat_t * beta_hat_t and xi_t(j,k) = alpha_hat_t(j) P(j,k) v_k exactly
+  // normalised -- no reduction and no division in this sweep.
   float X[KP];
 #pragma unroll
   for (int j = 0; j < KP; ++j) X[j] = 0.f;
   float beta = 1.f;       // beta_hat_{t+1}(k)
-  // gamma_{T-1} = alpha_hat_{T-1}: already in place
-  for (int t = Tmax - 2; t >= 0; --t) {
-    const bool on = t + 1 < T;       // this trial has a step t+1
-    float bn = (on && kvalid) ? __ldg(Bp + (long long)(t + 1) * K) : 0.f;
-    float w = (on && kvalid && want_post) ? Ep[(long long)t * K] : 0.f;    // alpha_hat_t(j)
-    float v = bn * beta;             // lane k: B_{t+1}(k) beta_hat_{t+1}(k)
-    float u0 = 0.f, u1 = 0.f;
+  auto bwd_step = [&](int t, float bc, float w, bool on) {
     float vk[KP];
-#pragma unroll
-    for (int j = 0; j < KP; ++j) vk[j] = __shfl_sync(0xffffffffu, v, j, KP);
+    exchange(bc * beta, vk);                       // v_k = b_{t+1}(k) beta_hat_{t+1}(k) / c_{t+1}
+    float u0 = 0.f, u1 = 0.f;
 #pragma unroll
     for (int j = 0; j < KP; j += 2) {
       u0 = fmaf(Prow[j], vk[j], u0);
       u1 = fmaf(Prow[j + 1], vk[j + 1], u1);
     }
-    float u = u0 + u1;
-    float d = group_sum<KP>(w * u);
     if (on) {
-      float inv = d > 0.f ? 1.f / d : 0.f;
-      float wi = w * inv;
+      beta = u0 + u1;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) X[j] = fmaf(wi, vk[j], X[j]);
-      beta = u * inv;
-      if (kvalid && want_post) Ep[(long long)t * K] = w * beta;
+      for (int j = 0; j < KP; ++j) X[j] = fmaf(w, vk[j], X[j]);
+      if (kvalid) Ep[(long long)t * K] = w * beta;
+    }
+  };
+  // ragged head (some trials of the warp are shorter): checked steps
+  int tb = Tmax - 2;
+  for (; tb >= 0 && tb + 1 >= Tmin; --tb) {
+    const bool on = tb + 1 < T;
+    const float bc = (on && kvalid) ? __ldg(Bp + (long long)(tb + 1) * K) * cip[tb + 1] : 0.f;
+    const float w = (on && kvalid) ? Ep[(long long)tb * K] : 0.f;
+    bwd_step(tb, bc, w, on);
+  }
+  // uniform part: every trial has steps tb and tb+1
+  if (tb >= 0) {
+    float bq[PF], wq[PF];
+    auto fetch = [&](int t0, float (&bb)[PF], float (&ww)[PF]) {
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int tt = max(t0 - i, 0);
+        bb[i] = kvalid ? __ldg(Bp + (long long)(tt + 1) * K) * cip[tt + 1] : 0.f;
+        ww[i] = kvalid ? Ep[(long long)tt * K] : 0.f;
+      }
+    };
+    fetch(tb, bq, wq);
+    for (; tb - PF + 1 >= 0; tb -= PF) {
+      float nb[PF], nw[PF];
+      fetch(tb - PF, nb, nw);
+#pragma unroll
+      for (int i = 0; i < PF; ++i) bwd_step(tb - i, bq[i], wq[i], true);
+#pragma unroll
+      for (int i = 0; i < PF; ++i) { bq[i] = nb[i]; wq[i] = nw[i]; }
+    }
+    for (; tb >= 0; --tb) {
+      const float bc = kvalid ? __ldg(Bp + (long long)(tb + 1) * K) * cip[tb + 1] : 0.f;
+      const float w = kvalid ? Ep[(long long)tb * K] : 0.f;
+      bwd_step(tb, bc, w, true);
     }
   }
   if (active && kvalid && a.Ezz) {
     float* out = a.Ezz + ((long long)trial * K + k) * K;
-    for (int j = 0; j < K; ++j) out[j] = X[j] * Prow[j];
+#pragma unroll
+    for (int j = 0; j < KP; ++j)
+      if (j < K) out[j] = X[j] * Prow[j];        // compile-time indices keep X / Prow in registers
   }
 }
 
@@ -456,7 +591,7 @@ __global__ void __launch_bounds__(256) ar_stats_kernel(const StatArgs a) {
 }
 
 struct WsLayoutH {
-  size_t Bsc, mx, ll, args, total;
+  size_t Bsc, mx, cinv, ll, args, total;
 };
 WsLayoutH hmm_ws(int K, long long total_T, int fp64) {
   WsLayoutH w;
@@ -464,6 +599,7 @@ WsLayoutH hmm_ws(int K, long long total_T, int fp64) {
   auto take = [&](size_t b) { size_t r = o; o += (b + 255) & ~(size_t)255; return r; };
   w.Bsc = take((size_t)total_T * K * 4);
   w.mx = take((size_t)total_T * 4);
+  w.cinv = take((size_t)total_T * 4);
   w.ll = fp64 ? take((size_t)total_T * K * 8) : 0;
   w.args = fp64 ? take((size_t)total_T * K) : 0;
   w.total = o;
@@ -479,7 +615,12 @@ int launch_emission_t(const EmitArgs<real>& a, int n_trials, int max_T, cudaStre
   if (smem > 227 * 1024) BN_FAIL("arhmm emission: K=%d D=%d lags=%d needs %zu B of shared memory", a.K, a.D, a.lags, smem);
   auto kern = emission_kernel<real, DP, TS>;
   BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(n_trials, bn_cdiv(max_T, TILE));
+  // one block per trial walks all of its time tiles (parameters staged once) when there are enough
+  // trials to fill the machine; otherwise the time tiles are spread over grid.y as well
+  int tiles = bn_cdiv(max_T, TILE);
+  int gy = n_trials >= 2 * 148 ? 1 : bn_cdiv(2 * 148, n_trials);
+  if (gy > tiles) gy = tiles;
+  dim3 grid(n_trials, gy);
   kern<<<grid, 128, smem, st>>>(a);
   BN_LAUNCHED();
   return 0;
@@ -631,7 +772,7 @@ extern "C" int bn_arhmm_estep(int K, int D, int lags, const void* d_blob, const 
   BN_TRY((launch_emission<float, 2>(e, n_trials, max_T, st)));
   ScanArgs s;
   s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
-  s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ;
+  s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.cinv = (float*)(ws + w.cinv);
   switch (round_kp(K)) {
     case 2: return launch_scan<2>(s, st);
     case 4: return launch_scan<4>(s, st);

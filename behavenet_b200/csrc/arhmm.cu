@@ -20,46 +20,17 @@
 //      accumulated in fp64.  alpha_hat is written into the Ez buffer by the forward sweep and
 //      overwritten in place with gamma by the backward sweep (same thread, same address).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
 
 #include "../../include/behavenet_b200.h"
-#include "bn_common.cuh"
+#include "arhmm_common.cuh"
 
 namespace {
 
 constexpr double LN2PI = 1.8378770664093453;
-
-struct BlobHeader {
-  int K, D, lags, DP, J, KP;
-  int pad_[2];
-  // offsets in bytes from blob start
-  long long off_pi0_f, off_P_f, off_W_f, off_c_f;
-  long long off_logpi0_d, off_logP_d, off_W_d, off_c_d;
-  long long total;
-};
-
-int round_dp(int D) { return (D + 3) & ~3; }
-int round_kp(int K) { int kp = 2; while (kp < K) kp <<= 1; return kp; }
-
-BlobHeader blob_layout(int K, int D, int lags) {
-  BlobHeader h;
-  memset(&h, 0, sizeof(h));
-  h.K = K; h.D = D; h.lags = lags; h.DP = round_dp(D); h.J = D * (lags + 1) + 1; h.KP = round_kp(K);
-  long long o = 256;
-  auto take = [&](long long bytes) { long long r = o; o += (bytes + 255) & ~255LL; return r; };
-  h.off_pi0_f = take(4LL * h.KP);
-  h.off_P_f = take(4LL * h.KP * h.KP);
-  h.off_W_f = take(4LL * K * h.J * h.DP);       // [k][j][i] (i fastest, padded to DP)
-  h.off_c_f = take(4LL * (K + 1));               // c_k, then c_init
-  h.off_logpi0_d = take(8LL * h.KP);
-  h.off_logP_d = take(8LL * h.KP * h.KP);
-  h.off_W_d = take(8LL * K * h.J * h.DP);
-  h.off_c_d = take(8LL * (K + 1));
-  h.total = o;
-  return h;
-}
 
 // ------------------------------------------------------------------------------------------------
 // emission kernel
@@ -443,6 +414,298 @@ __global__ void __launch_bounds__(128) scan_kernel(const ScanArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward-backward scan, meet-in-the-middle form.
+//
+// The serial chain of the E-step is 2T dependent steps when the backward sweep waits for the forward
+// one.  Here a trial is owned by TWO lane groups in two different warps of the same block: the
+// forward group sweeps t = 0 .. T-1, the backward group t = T-1 .. 0, concurrently, each with its own
+// lazy normalisation.  Until they cross at h = T/2 each stores its message (alpha_hat into the Ez
+// buffer, beta_tilde into the workspace); after one block-level barrier each finds the other's message
+// already in memory and finishes the posteriors on the fly:
+//     gamma_t    = alpha_hat_t * beta_t / G_t,                  G_t = sum_k alpha_hat_t(k) beta_t(k)
+//     xi_t(j,k)  = alpha_hat_t(j) P(j,k) b_{t+1}(k) beta_{t+1}(k) / (G_t D_t)        (backward group, t < h)
+//                = alpha_hat_t(j) P(j,k) b_{t+1}(k) beta_{t+1}(k) / (c_{t+1} G_{t+1})  (forward group, t >= h)
+// (D_t, c_t = the local normalisers).  G_t is a KP-lane shuffle reduction that does not feed the
+// recursion, so it stays off the dependent chain; the chain itself is T steps of
+// STS -> LDS.128 x KP/4 -> KP FMAs.  No third pass, no extra HBM traffic beyond one message array.
+// ------------------------------------------------------------------------------------------------
+struct Scan2Args {
+  const unsigned char* blob;
+  const float* Bsc;
+  const float* mx;
+  const long long* offsets;
+  int n_trials, K;
+  float* Ez;      // nullable (then forward only: log normalisers)
+  float* Ezz;     // nullable
+  double* logZ;   // nullable
+  float* beta;    // (total_T, K) workspace
+};
+
+template <int PF, class In, class Load, class Step>
+__device__ __forceinline__ void run_range(int t0, int n, int dir, Load load, Step step) {
+  int done = 0;
+  if (n >= PF) {
+    In q[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) q[i] = load(t0 + dir * i);
+    for (; done + 2 * PF <= n; done += PF) {
+      In nq[PF];
+#pragma unroll
+      for (int i = 0; i < PF; ++i) nq[i] = load(t0 + dir * (done + PF + i));
+#pragma unroll
+      for (int i = 0; i < PF; ++i) step(t0 + dir * (done + i), q[i]);
+#pragma unroll
+      for (int i = 0; i < PF; ++i) q[i] = nq[i];
+    }
+#pragma unroll
+    for (int i = 0; i < PF; ++i) step(t0 + dir * (done + i), q[i]);
+    done += PF;
+  }
+  for (; done < n; ++done) step(t0 + dir * done, load(t0 + dir * done));
+}
+
+struct ScanIn { float b, m, x; };
+
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): the scan is issue-bound, so two lanes per instruction
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b),
+                     uc = *reinterpret_cast<unsigned long long*>(&c), ud;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+  return *reinterpret_cast<float2*>(&ud);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), ud;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+  return *reinterpret_cast<float2*>(&ud);
+}
+
+template <int KP, bool POST>
+__global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan2Args a) {
+  constexpr int GPW = 32 / KP;                     // trials per warp
+  constexpr int H2 = KP / 2;                       // packed pairs per message
+  constexpr int PF = 8;                            // prefetch depth of the first halves
+  constexpr int PF2 = 4;                           // second halves carry more live state
+  const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(a.blob);
+  const float* Pg = reinterpret_cast<const float*>(a.blob + hd->off_P_f);     // KP x KP, zero padded
+  const float* pi0g = reinterpret_cast<const float*>(a.blob + hd->off_pi0_f);
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int k = lane % KP;
+  const int grp = lane / KP;
+  // POST: warps 0,1 run the forward sweeps of trial sets 0,1 of this block, warps 2,3 the backward
+  // sweeps of the same sets.  !POST (log-likelihood only): four forward warps.
+  const bool is_bwd = POST && wib >= 2;
+  const int set = POST ? (wib & 1) : wib;
+  const int trial = (blockIdx.x * (POST ? 2 : 4) + set) * GPW + grp;
+  const bool active = trial < a.n_trials;
+  const int K = a.K;
+  const bool kvalid = k < K && active;
+  const long long beg = active ? a.offsets[trial] : 0;
+  const int T = active ? (int)(a.offsets[trial + 1] - beg) : 0;
+  const int h = T / 2;
+  const unsigned gmask = KP == 32 ? 0xffffffffu : (((1u << KP) - 1u) << (grp * KP));
+
+  __shared__ __align__(16) float xch[4][2][32];
+  __shared__ float xz[2][GPW][KP][KP + 1];
+  const int gbase = grp * KP;
+  int par = 0;
+  auto exchange = [&](float mine, float2 (&v)[H2]) {
+    xch[wib][par][lane] = mine;
+    __syncwarp(gmask);
+    if (KP >= 4) {
+#pragma unroll
+      for (int j = 0; j < KP; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&xch[wib][par][gbase + j]);
+        v[j / 2] = make_float2(q.x, q.y);
+        v[j / 2 + 1] = make_float2(q.z, q.w);
+      }
+    } else {
+      v[0] = *reinterpret_cast<const float2*>(&xch[wib][par][gbase]);
+    }
+    par ^= 1;
+  };
+  auto gsum = [&](float v) {
+#pragma unroll
+    for (int o = KP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, KP);
+    return v;
+  };
+  auto pair_barrier = [&]() {
+    __syncwarp();
+    if (POST) asm volatile("bar.sync %0, 64;" ::"r"(1 + set) : "memory");
+  };
+  // dot(v, p) and sum(v) of a packed message
+  auto dot_sum = [&](const float2 (&v)[H2], const float2 (&p)[H2], float& dot, float& sum) {
+    float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < H2; ++j) {
+      s = ffma2(v[j], p[j], s);
+      q = fadd2(q, v[j]);
+    }
+    dot = s.x + s.y;
+    sum = q.x + q.y;
+  };
+
+  const float* Bp = a.Bsc + beg * K + k;
+  const float* mp = a.mx + beg;
+  float* Ep = POST ? a.Ez + beg * K + k : nullptr;
+  float* Bt = POST ? a.beta + beg * K + k : nullptr;
+
+  if (!is_bwd) {
+    // =============================== forward group (lane k owns column k of P)
+    float2 Pcol[H2];
+#pragma unroll
+    for (int j = 0; j < H2; ++j) Pcol[j] = make_float2(Pg[(2 * j) * KP + k], Pg[(2 * j + 1) * KP + k]);
+    double logZ = 0.0;
+    float acur = 0.f, bprev = 0.f;
+    if (T > 0) {
+      bprev = kvalid ? __ldg(Bp) : 0.f;
+      acur = pi0g[k] * bprev;
+      logZ = (double)__ldg(mp);
+    }
+    // first half: t = 1 .. h; finalises alpha_hat_{t-1}, produces a_t
+    auto load1 = [&](int t) {
+      ScanIn in;
+      in.b = kvalid ? __ldg(Bp + t * K) : 0.f;
+      in.m = __ldg(mp + t);
+      in.x = 0.f;
+      return in;
+    };
+    auto step1 = [&](int t, const ScanIn& in) {
+      float2 v[H2];
+      exchange(acur, v);
+      float dot, S;                                  // S = c_{t-1}
+      dot_sum(v, Pcol, dot, S);
+      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      logZ += (double)(__logf(S) + in.m);            // fp64 accumulation, off the dependent chain
+      if (POST && kvalid) Ep[(t - 1) * K] = acur * inv;
+      acur = dot * in.b * inv;
+      bprev = in.b;
+    };
+    const int n1 = POST ? h : (T > 0 ? T - 1 : 0);
+    run_range<PF, ScanIn>(1, n1, 1, load1, step1);
+    if (!POST) {
+      // finalise the last step: log c_{T-1}
+      if (T > 0) {
+        float2 v[H2];
+        exchange(acur, v);
+        float dot, S;
+        dot_sum(v, Pcol, dot, S);
+        logZ += (double)__logf(S);
+      }
+      if (active && k == 0 && a.logZ) a.logZ[trial] = logZ;
+      return;
+    }
+    pair_barrier();
+    // second half: t = h+1 .. T; finalises step t-1 into gamma_{t-1} and xi_{t-2}; t == T has no a_t
+    float2 X[H2], vprev[H2];
+#pragma unroll
+    for (int j = 0; j < H2; ++j) { X[j] = make_float2(0.f, 0.f); vprev[j] = make_float2(0.f, 0.f); }
+    float invprev = 0.f;
+    auto load2 = [&](int t) {
+      ScanIn in;
+      const bool cur = t < T;
+      in.b = (cur && kvalid) ? __ldg(Bp + t * K) : 0.f;
+      in.m = cur ? __ldg(mp + t) : 0.f;
+      in.x = kvalid ? Bt[(t - 1) * K] : 0.f;                      // beta_tilde_{t-1}(k)
+      return in;
+    };
+    auto step2 = [&](int t, const ScanIn& in) {
+      float2 v[H2];
+      exchange(acur, v);
+      float dot, S;
+      dot_sum(v, Pcol, dot, S);
+      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      logZ += (double)(__logf(S) + in.m);
+      const float ab = acur * inv * in.x;
+      const float G = gsum(ab);
+      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
+      if (kvalid) Ep[(t - 1) * K] = ab * rG;
+      const float w = bprev * in.x * inv * rG * invprev;          // 0 on the first step (invprev = 0)
+      const float2 w2 = make_float2(w, w);
+#pragma unroll
+      for (int j = 0; j < H2; ++j) {
+        X[j] = ffma2(vprev[j], w2, X[j]);
+        vprev[j] = v[j];
+      }
+      invprev = inv;
+      acur = dot * in.b * inv;
+      bprev = in.b;
+    };
+    run_range<PF2, ScanIn>(h + 1, T - h, 1, load2, step2);
+    if (active && k == 0 && a.logZ) a.logZ[trial] = logZ;
+    pair_barrier();                                  // backward group's xi rows are in xz
+    if (kvalid && a.Ezz) {
+      float* out = a.Ezz + (long long)trial * K * K + k;
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        if (j < K) {
+          const float xj = (j & 1) ? X[j / 2].y : X[j / 2].x;
+          const float pj = (j & 1) ? Pcol[j / 2].y : Pcol[j / 2].x;
+          out[(long long)j * K] = pj * (xj + xz[set][grp][j][k]);
+        }
+    }
+  } else {
+    // =============================== backward group (lane j = k owns row j of P)
+    float2 Prow[H2];
+#pragma unroll
+    for (int j = 0; j < H2; ++j) Prow[j] = make_float2(Pg[k * KP + 2 * j], Pg[k * KP + 2 * j + 1]);
+    float beta = 1.f;                                // beta_tilde_{t+1}(j)
+    if (T > 0 && kvalid) Bt[(T - 1) * K] = 1.f;
+    auto load1 = [&](int t) {
+      ScanIn in;
+      in.b = kvalid ? __ldg(Bp + (t + 1) * K) : 0.f;
+      in.m = 0.f;
+      in.x = 0.f;
+      return in;
+    };
+    auto step1 = [&](int t, const ScanIn& in) {
+      float2 vk[H2];
+      exchange(in.b * beta, vk);
+      float u, Dn;
+      dot_sum(vk, Prow, u, Dn);
+      const float rD = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
+      beta = u * rD;
+      if (kvalid) Bt[t * K] = beta;
+    };
+    run_range<PF, ScanIn>(T - 2, max(T - 1 - h, 0), -1, load1, step1);      // t = T-2 .. h
+    pair_barrier();
+    float2 X[H2];
+#pragma unroll
+    for (int j = 0; j < H2; ++j) X[j] = make_float2(0.f, 0.f);
+    auto load2 = [&](int t) {
+      ScanIn in;
+      in.b = kvalid ? __ldg(Bp + (t + 1) * K) : 0.f;
+      in.m = 0.f;
+      in.x = kvalid ? Ep[t * K] : 0.f;                            // alpha_hat_t(j)
+      return in;
+    };
+    auto step2 = [&](int t, const ScanIn& in) {
+      float2 vk[H2];
+      exchange(in.b * beta, vk);
+      float u, Dn;
+      dot_sum(vk, Prow, u, Dn);
+      const float rD = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
+      beta = u * rD;
+      const float ab = in.x * beta;
+      const float G = gsum(ab);
+      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
+      if (kvalid) Ep[t * K] = ab * rG;
+      const float w = in.x * rD * rG;
+      const float2 w2 = make_float2(w, w);
+#pragma unroll
+      for (int j = 0; j < H2; ++j) X[j] = ffma2(vk[j], w2, X[j]);
+    };
+    run_range<PF2, ScanIn>(h - 1, h, -1, load2, step2);                       // t = h-1 .. 0
+#pragma unroll
+    for (int j = 0; j < H2; ++j) {
+      xz[set][grp][k][2 * j] = X[j].x;
+      xz[set][grp][k][2 * j + 1] = X[j].y;
+    }
+    pair_barrier();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Viterbi (fp64 max-sum, backward recursion like ssm.messages.viterbi)
 // ------------------------------------------------------------------------------------------------
 struct VitArgs {
@@ -591,7 +854,7 @@ __global__ void __launch_bounds__(256) ar_stats_kernel(const StatArgs a) {
 }
 
 struct WsLayoutH {
-  size_t Bsc, mx, cinv, ll, args, total;
+  size_t Bsc, mx, beta, ll, args, total;
 };
 WsLayoutH hmm_ws(int K, long long total_T, int fp64) {
   WsLayoutH w;
@@ -599,7 +862,7 @@ WsLayoutH hmm_ws(int K, long long total_T, int fp64) {
   auto take = [&](size_t b) { size_t r = o; o += (b + 255) & ~(size_t)255; return r; };
   w.Bsc = take((size_t)total_T * K * 4);
   w.mx = take((size_t)total_T * 4);
-  w.cinv = take((size_t)total_T * 4);
+  w.beta = take((size_t)total_T * K * 4);      // backward messages of the second half of every trial
   w.ll = fp64 ? take((size_t)total_T * K * 8) : 0;
   w.args = fp64 ? take((size_t)total_T * K) : 0;
   w.total = o;
@@ -628,7 +891,7 @@ int launch_emission_t(const EmitArgs<real>& a, int n_trials, int max_T, cudaStre
 
 template <typename real, int TS>
 int launch_emission(const EmitArgs<real>& a, int n_trials, int max_T, cudaStream_t st) {
-  switch (round_dp(a.D)) {
+  switch (bn_round_dp(a.D)) {
     case 4: return launch_emission_t<real, 4, TS>(a, n_trials, max_T, st);
     case 8: return launch_emission_t<real, 8, TS>(a, n_trials, max_T, st);
     case 12: return launch_emission_t<real, 12, TS>(a, n_trials, max_T, st);
@@ -652,7 +915,7 @@ int check_dims(int K, int D, int lags) {
 
 extern "C" size_t bn_arhmm_params_bytes(int K, int D, int lags) {
   if (check_dims(K, D, lags)) return 0;
-  return (size_t)blob_layout(K, D, lags).total;
+  return (size_t)bn_blob_layout(K, D, lags).total;
 }
 
 extern "C" int bn_arhmm_pack_params(int K, int D, int lags, const double* log_pi0, const double* log_Ps,
@@ -660,7 +923,7 @@ extern "C" int bn_arhmm_pack_params(int K, int D, int lags, const double* log_pi
                                     void* h_blob) {
   BN_TRY(check_dims(K, D, lags));
   if (!log_pi0 || !log_Ps || !As || !bs || !Sigmas || !h_blob) BN_FAIL("bn_arhmm_pack_params: null argument");
-  BlobHeader h = blob_layout(K, D, lags);
+  BlobHeader h = bn_blob_layout(K, D, lags);
   unsigned char* blob = (unsigned char*)h_blob;
   memset(blob, 0, (size_t)h.total);
   memcpy(blob, &h, sizeof(h));
@@ -729,6 +992,35 @@ extern "C" int bn_arhmm_pack_params(int K, int D, int lags, const double* log_pi
   }
   cd[K] = -0.5 * D * LN2PI;
   cf[K] = (float)cd[K];
+  // TF32 hi / lo split of W for the tensor-core emission kernel: W = hi + lo to ~2^-22 relative, both
+  // exactly representable in TF32.  Row n = k*DP + i, column kt = b*DP + d for x_{t-b}[d] and
+  // (lags+1)*DP for the bias; stored as 8x(16-byte) core matrices, K-adjacent cores NT/8*128 bytes apart.
+  {
+    float* Whi = (float*)(blob + h.off_W_hi);
+    float* Wlo = (float*)(blob + h.off_W_lo);
+    auto tf32 = [](double v) {
+      float f = (float)v;
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      u = (u + 0x1000u) & 0xFFFFE000u;        // round to nearest (ties away), 10 explicit mantissa bits
+      memcpy(&f, &u, 4);
+      return f;
+    };
+    for (int k = 0; k < K; ++k)
+      for (int j = 0; j < J; ++j) {
+        int kt;
+        if (j == J - 1) kt = (lags + 1) * DP;
+        else { int b = j / D, d = j - b * D; kt = b * DP + d; }
+        for (int i = 0; i < D; ++i) {
+          const double w = Wd[((size_t)k * J + j) * DP + i];
+          const int n = k * DP + i;
+          const size_t o = (size_t)(kt / 4) * (h.NT / 8 * 32) + (size_t)(n / 8) * 32 + (n % 8) * 4 + kt % 4;
+          const float hi = tf32(w);
+          Whi[o] = hi;
+          Wlo[o] = tf32(w - (double)hi);
+        }
+      }
+  }
   return 0;
 }
 
@@ -742,6 +1034,18 @@ static int launch_scan(const ScanArgs& a, cudaStream_t st) {
   constexpr int GPW = 32 / KP;
   int warps = bn_cdiv(a.n_trials, GPW);
   scan_kernel<KP><<<bn_cdiv(warps, 4), 128, 0, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+template <int KP>
+static int launch_scan2(const Scan2Args& a, cudaStream_t st) {
+  constexpr int GPW = 32 / KP;
+  if (a.Ez) {
+    scan2_kernel<KP, true><<<bn_cdiv(a.n_trials, 2 * GPW), 128, 0, st>>>(a);
+  } else {
+    scan2_kernel<KP, false><<<bn_cdiv(a.n_trials, 4 * GPW), 128, 0, st>>>(a);
+  }
   BN_LAUNCHED();
   return 0;
 }
@@ -769,16 +1073,34 @@ extern "C" int bn_arhmm_estep(int K, int D, int lags, const void* d_blob, const 
   e.blob = (const unsigned char*)d_blob; e.x = d_x; e.offsets = (const long long*)d_offsets;
   e.K = K; e.D = D; e.lags = lags; e.J = D * (lags + 1) + 1;
   e.Bsc = (float*)(ws + w.Bsc); e.mx = (float*)(ws + w.mx); e.ll = nullptr;
-  BN_TRY((launch_emission<float, 2>(e, n_trials, max_T, st)));
-  ScanArgs s;
+  int tc = 1;
+  if (bn_get_tensor_core_mode())
+    tc = bn_launch_emission_tc(e.blob, d_x, e.offsets, K, D, lags, n_trials, max_T, e.Bsc, e.mx, st);
+  if (tc < 0) return tc;
+  if (tc > 0) BN_TRY((launch_emission<float, 2>(e, n_trials, max_T, st)));
+  static const bool legacy_scan = [] { const char* e = getenv("BN_SCAN"); return e && e[0] == '1'; }();
+  if (legacy_scan) {
+    // sequential forward-then-backward kernel (kept for A/B timing: BN_SCAN=1)
+    ScanArgs s;
+    s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
+    s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.cinv = (float*)(ws + w.beta);
+    switch (bn_round_kp(K)) {
+      case 2: return launch_scan<2>(s, st);
+      case 4: return launch_scan<4>(s, st);
+      case 8: return launch_scan<8>(s, st);
+      case 16: return launch_scan<16>(s, st);
+      default: return launch_scan<32>(s, st);
+    }
+  }
+  Scan2Args s;
   s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
-  s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.cinv = (float*)(ws + w.cinv);
-  switch (round_kp(K)) {
-    case 2: return launch_scan<2>(s, st);
-    case 4: return launch_scan<4>(s, st);
-    case 8: return launch_scan<8>(s, st);
-    case 16: return launch_scan<16>(s, st);
-    default: return launch_scan<32>(s, st);
+  s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.beta = (float*)(ws + w.beta);
+  switch (bn_round_kp(K)) {
+    case 2: return launch_scan2<2>(s, st);
+    case 4: return launch_scan2<4>(s, st);
+    case 8: return launch_scan2<8>(s, st);
+    case 16: return launch_scan2<16>(s, st);
+    default: return launch_scan2<32>(s, st);
   }
 }
 
@@ -799,7 +1121,7 @@ extern "C" int bn_arhmm_viterbi(int K, int D, int lags, const void* d_blob, cons
   VitArgs v;
   v.blob = e.blob; v.ll = e.ll; v.offsets = e.offsets; v.n_trials = n_trials; v.K = K;
   v.args = ws + w.args; v.z = d_z;
-  switch (round_kp(K)) {
+  switch (bn_round_kp(K)) {
     case 2: return launch_vit<2>(v, st);
     case 4: return launch_vit<4>(v, st);
     case 8: return launch_vit<8>(v, st);

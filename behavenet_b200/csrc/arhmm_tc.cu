@@ -1,0 +1,324 @@
+// ARHMM emission log-likelihoods on the 5th-gen tensor cores (tcgen05), fp32-accurate via the
+// 3xTF32 split.
+//
+// The AR Gaussian log-density of every state is one whitened affine map (arhmm.cu):
+//     y_k = W_k psi_t,   psi_t = [x_t, x_{t-1}, .., x_{t-L}, 1],   ll_t(k) = c_k - |y_k|^2 / 2,
+// i.e. a (timesteps x KT) x (KT x K*D) GEMM followed by per-state sums of squares.  On the FP32
+// pipe that GEMM is ~13.6 kFLOP per timestep and bounds the whole E-step; here a CTA turns 128
+// consecutive timesteps of a trial into one UMMA tile:
+//     D[128 x NT] (TMEM, fp32) = psi_lo * W_hi^T + psi_hi * W_lo^T + psi_hi * W_hi^T
+// with psi split on the fly (cvt.rna.tf32 and the exact remainder) and W split on the host in
+// fp64.  Each dropped term (lo * lo) is below 2^-22 relative, so the result carries fp32-level error
+// and the posteriors keep the 1e-5 parity bound of the CUDA-core kernel.
+//
+// Operands are K-major in the no-swizzle canonical layout: 8-row x 16-byte core matrices, cores
+// adjacent along M/N 128 bytes apart (SBO), cores adjacent along K one whole column of cores apart
+// (LBO) -- thread r writes the four floats of k-chunk c of its row at c*LBO + r*16, a fully
+// coalesced 2 KB store per chunk.  Warps 0-3 build psi, wait for the accumulator, read their TMEM
+// lane quarter back with tcgen05.ld and reduce per state; warp 4 allocates TMEM and issues the
+// MMAs.  Two CTAs per SM overlap one tile's MMAs with the other's epilogue.
+#include "arhmm_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace bn_tc;
+
+constexpr int TM = 128;          // timesteps per tile = UMMA M
+constexpr int NTHREADS = 160;
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor
+__device__ __forceinline__ uint64_t make_desc_k_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;        // descriptor version 1 (sm_100)
+  return d;                      // layout type 0 = no swizzle
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__host__ __device__ constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
+
+struct EmitTcArgs {
+  const unsigned char* blob;
+  const float* x;
+  const long long* offsets;
+  int K, D, lags, n_trials;
+  float* Bsc;
+  float* mx;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs a) {
+  constexpr int SC = DP * 32 / gcd_c(DP, 32);      // columns per epilogue super-chunk (whole states, whole 32-col loads)
+  constexpr int SPC = SC / DP;                     // states per super-chunk
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(a.blob);
+  const int K = a.K, D = a.D, L = a.lags;
+  const int NT = hd->NT, KT = hd->KT;
+  const uint32_t A_LBO = TM * 16, B_LBO = (uint32_t)NT * 16;
+  // smem: W_hi | W_lo | psi_hi | psi_lo | c | barriers
+  float* Bhi = reinterpret_cast<float*>(smem);
+  float* Blo = Bhi + (size_t)NT * KT;
+  float* Ahi = Blo + (size_t)NT * KT;
+  float* Alo = Ahi + (size_t)TM * KT;
+  float* csm = Alo + (size_t)TM * KT;                        // K + 1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(csm + ((K + 1 + 3) & ~3));   // full, accum
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+  const uint32_t full_bar = smem_u32(bars), accum_bar = smem_u32(bars + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  {
+    const int4* s0 = reinterpret_cast<const int4*>(a.blob + hd->off_W_hi);
+    const int4* s1 = reinterpret_cast<const int4*>(a.blob + hd->off_W_lo);
+    int4* d0 = reinterpret_cast<int4*>(Bhi);
+    int4* d1 = reinterpret_cast<int4*>(Blo);
+    const int n16 = NT * KT / 4;
+    for (int i = tid; i < n16; i += NTHREADS) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
+    const float* cg = reinterpret_cast<const float*>(a.blob + hd->off_c_f);
+    for (int i = tid; i < K + 1; i += NTHREADS) csm[i] = cg[i];
+  }
+  if (tid == 0) {
+    mbar_init(full_bar, 128 + L);        // 128 row owners + L halo lanes of warp 4
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc<256>(smem_u32(tmem_ptr));
+  fence_proxy_async();             // W tiles (generic-proxy stores) -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  uint32_t phase = 0;
+
+  // Row r of the psi tile is timestep t0 + r; x_t feeds row r (block 0), row r+1 (block 1), .. so every
+  // x row is split into hi / lo ONCE by its owner thread and scattered to the L+1 rows that use it.
+  // The first L rows of a tile also need x_{t0-1} .. x_{t0-L}: lanes 0..L-1 of warp 4 own those.
+  auto load_x = [&](long long beg, int T, int ts, float4 (&v)[DP / 4]) {
+    const bool ok = ts >= 0 && ts < T;
+    const float* xr = a.x + (beg + (ok ? ts : 0)) * D;
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+      v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        if (D == DP) {
+          v[c] = __ldg(reinterpret_cast<const float4*>(xr) + c);
+        } else {
+          float e[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) e[q] = 4 * c + q < D ? __ldg(xr + 4 * c + q) : 0.f;
+          v[c] = make_float4(e[0], e[1], e[2], e[3]);
+        }
+      }
+    }
+  };
+  // scatter x_{t0 + r0} (hi / lo) to rows r0 + b, b = 0..L, that exist in this tile
+  auto scatter_x = [&](int r0, const float4 (&v)[DP / 4]) {
+#pragma unroll
+    for (int c = 0; c < DP / 4; ++c) {
+      const float4 h = make_float4(tf32_rna(v[c].x), tf32_rna(v[c].y), tf32_rna(v[c].z), tf32_rna(v[c].w));
+      const float4 l = make_float4(tf32_rna(v[c].x - h.x), tf32_rna(v[c].y - h.y), tf32_rna(v[c].z - h.z),
+                                   tf32_rna(v[c].w - h.w));
+      for (int b = 0; b <= L; ++b) {
+        const int row = r0 + b;
+        if (row < 0 || row >= TM) continue;
+        const size_t off = (size_t)(b * (DP / 4) + c) * A_LBO + row * 16;
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Ahi) + off) = h;
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Alo) + off) = l;
+      }
+    }
+  };
+  const bool halo_lane = warp == 4 && (tid & 31) < L;      // owns x_{t0 - 1 - lane}
+  const int my_r0 = warp < 4 ? tid : -1 - (tid & 31);
+
+  // work list of this CTA: (trial, t0) pairs in a fixed order known to every warp
+  int trial = blockIdx.x;
+  int t0 = blockIdx.y * TM;
+  long long beg = 0;
+  int T = 0;
+  auto advance = [&]() {             // move to the next non-empty tile; false when the list is exhausted
+    while (trial < a.n_trials) {
+      beg = a.offsets[trial];
+      T = (int)(a.offsets[trial + 1] - beg);
+      if (t0 < T) return true;
+      trial += gridDim.x;
+      t0 = blockIdx.y * TM;
+    }
+    return false;
+  };
+  auto step_tile = [&]() { t0 += gridDim.y * TM; };
+
+  bool have = advance();
+  float4 xv[DP / 4];
+  if (have && (warp < 4 || halo_lane)) load_x(beg, T, t0 + my_r0, xv);
+  while (have) {
+    const long long cbeg = beg;
+    const int cT = T, ct0 = t0;
+    if (warp < 4 || halo_lane) scatter_x(my_r0, xv);
+    if (warp < 4) {
+      for (int kc = (L + 1) * (DP / 4); kc < KT / 4; ++kc) {
+        const float one = kc == (L + 1) * (DP / 4) ? 1.f : 0.f;      // bias column, then zero padding
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Ahi) + (size_t)kc * A_LBO + tid * 16) =
+            make_float4(one, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(Alo) + (size_t)kc * A_LBO + tid * 16) =
+            make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();               // this thread's TMEM reads of the previous tile are complete
+    if (warp < 4 || halo_lane) mbar_arrive(full_bar);
+    // next tile's x rows are fetched while the tensor core works on this one
+    step_tile();
+    have = advance();
+    float qinit = 0.f;
+    if (warp < 4 && ct0 + tid < L) {
+      // initial segment: N(0, I) for every state (ssm mu_init = 0, Sigma_init = I)
+#pragma unroll
+      for (int c = 0; c < DP / 4; ++c)
+        qinit += xv[c].x * xv[c].x + xv[c].y * xv[c].y + xv[c].z * xv[c].z + xv[c].w * xv[c].w;
+    }
+    if (have && (warp < 4 || halo_lane)) load_x(beg, T, t0 + my_r0, xv);
+
+    if (warp < 4) {
+      // ---------------- epilogue
+      const int t = ct0 + tid;
+      mbar_wait(accum_bar, phase);
+      tc_fence_after();
+      float vmax = -INFINITY;
+      float vals[32];                       // K <= 32 log-likelihoods of this row
+#pragma unroll
+      for (int k = 0; k < 32; ++k) vals[k] = -INFINITY;
+#pragma unroll
+      for (int sc = 0; sc < (32 + SPC - 1) / SPC; ++sc) {
+        if (sc * SPC < K) {
+          uint32_t r[SC / 32][32];
+#pragma unroll
+          for (int c32 = 0; c32 < SC / 32; ++c32)
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + sc * SC + c32 * 32, r[c32]);
+          tmem_ld_wait();
+          float q[SPC];
+#pragma unroll
+          for (int s = 0; s < SPC; ++s) q[s] = 0.f;
+#pragma unroll
+          for (int c32 = 0; c32 < SC / 32; ++c32)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float y = __uint_as_float(r[c32][e]);
+              q[(c32 * 32 + e) / DP] = fmaf(y, y, q[(c32 * 32 + e) / DP]);
+            }
+#pragma unroll
+          for (int s = 0; s < SPC; ++s) {
+            const int k = sc * SPC + s;
+            if (k < 32 && k < K) {
+              vals[k] = csm[k] - 0.5f * q[s];
+              vmax = fmaxf(vmax, vals[k]);
+            }
+          }
+        }
+      }
+      if (t < cT) {
+        const bool init = t < L;
+        float* og = a.Bsc + (cbeg + t) * K;
+        a.mx[cbeg + t] = init ? csm[K] - 0.5f * qinit : vmax;
+        if ((K & 3) == 0) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            if (k < K)
+              *reinterpret_cast<float4*>(og + k) =
+                  init ? make_float4(1.f, 1.f, 1.f, 1.f)
+                       : make_float4(__expf(vals[k] - vmax), __expf(vals[k + 1] - vmax), __expf(vals[k + 2] - vmax),
+                                     __expf(vals[k + 3] - vmax));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k < K) og[k] = init ? 1.f : __expf(vals[k] - vmax);
+        }
+      }
+    } else if ((tid & 31) == 0) {
+      // ---------------- MMA issuer
+      mbar_wait(full_bar, phase);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(TM, NT);
+      const uint32_t ahi = smem_u32(Ahi), alo = smem_u32(Alo), bhi = smem_u32(Bhi), blo = smem_u32(Blo);
+      const int ksteps = KT / 8;
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t pa = pass == 0 ? alo : ahi;       // small terms first
+        const uint32_t pb = pass == 1 ? blo : bhi;
+        for (int s = 0; s < ksteps; ++s) {
+          const uint64_t ad = make_desc_k_nosw(pa + s * 2 * A_LBO, A_LBO, 128);
+          const uint64_t bd = make_desc_k_nosw(pb + s * 2 * B_LBO, B_LBO, 128);
+          umma_tf32(tmem_base, ad, bd, idesc, (pass | s) != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(accum_bar);
+    }
+    if (warp == 4) {
+      // the halo lanes rewrite rows of the psi tile in the next iteration: not before this tile's
+      // MMAs have retired (and never more than one tile ahead of the row owners)
+      __syncwarp();
+      mbar_wait(accum_bar, phase);
+    }
+    phase ^= 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+template <int DP>
+int launch(const EmitTcArgs& a, int NT, int KT, int max_T, cudaStream_t st) {
+  constexpr int SC = DP * 32 / gcd_c(DP, 32);
+  constexpr int SPC = SC / DP;
+  if (((a.K + SPC - 1) / SPC) * SC > 256) return 1;       // epilogue super-chunks must stay inside the allocation
+  size_t smem = 4 * (2 * (size_t)NT * KT + 2 * (size_t)TM * KT + ((a.K + 1 + 3) & ~3)) + 64;
+  if (smem > 113 * 1024) return 1;                        // two CTAs per SM
+  auto kern = emission_tc_kernel<DP>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    configured = true;
+  }
+  const int slots = 2 * 148;
+  int gx = a.n_trials < slots ? a.n_trials : slots;
+  int tiles = bn_cdiv(max_T, TM);
+  int gy = a.n_trials >= slots ? 1 : bn_cdiv(slots, a.n_trials);
+  if (gy > tiles) gy = tiles;
+  kern<<<dim3(gx, gy), NTHREADS, smem, st>>>(a);
+  BN_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+int bn_launch_emission_tc(const unsigned char* d_blob, const float* d_x, const long long* d_offsets, int K, int D,
+                          int lags, int n_trials, int max_T, float* d_Bsc, float* d_mx, cudaStream_t st) {
+  const BlobHeader h = bn_blob_layout(K, D, lags);
+  if (h.NT > 256 || h.NT < 16) return 1;
+  if (((uintptr_t)d_x & 15) != 0) return 1;
+  EmitTcArgs a;
+  a.blob = d_blob; a.x = d_x; a.offsets = d_offsets; a.K = K; a.D = D; a.lags = lags; a.n_trials = n_trials;
+  a.Bsc = d_Bsc; a.mx = d_mx;
+  switch (h.DP) {
+    case 4: return launch<4>(a, h.NT, h.KT, max_T, st);
+    case 8: return launch<8>(a, h.NT, h.KT, max_T, st);
+    case 12: return launch<12>(a, h.NT, h.KT, max_T, st);
+    case 16: return launch<16>(a, h.NT, h.KT, max_T, st);
+    case 20: return launch<20>(a, h.NT, h.KT, max_T, st);
+    case 24: return launch<24>(a, h.NT, h.KT, max_T, st);
+    case 28: return launch<28>(a, h.NT, h.KT, max_T, st);
+    case 32: return launch<32>(a, h.NT, h.KT, max_T, st);
+    default: return 1;
+  }
+}

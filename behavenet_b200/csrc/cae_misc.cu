@@ -293,9 +293,13 @@ __global__ void heads_bwd_data_kernel(const float* __restrict__ feat, const floa
   dpre[i] = s * (feat[i] > 0.f ? 1.f : BN_LEAK);
 }
 
-__global__ void heads_bwd_w_kernel(const float* __restrict__ feat, const float* __restrict__ dmu,
-                                   const float* __restrict__ dlv, int n, int L, int HJ, int C, int H,
-                                   int W, float* __restrict__ gw0, float* __restrict__ gw1) {
+// dW_head[j][i_chw] += sum_f dhead[f][j] * feat[f][i_nhwc].  The frame reduction is split over
+// grid.y (one atomicAdd per split) and unrolled into four independent chains: the old one-thread
+// 256-long dependent chain was pure latency.
+__global__ void __launch_bounds__(256) heads_bwd_w_kernel(const float* __restrict__ feat, const float* __restrict__ dmu,
+                                                          const float* __restrict__ dlv, int n, int L, int HJ, int C, int H,
+                                                          int W, int fper, float* __restrict__ gw0,
+                                                          float* __restrict__ gw1) {
   long long F = (long long)C * H * W;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)HJ * F) return;
@@ -304,27 +308,38 @@ __global__ void heads_bwd_w_kernel(const float* __restrict__ feat, const float* 
   float* g = hj < L ? gw0 : gw1;
   if (!g) return;
   if ((hj < L && !dmu) || (hj >= L && !dlv)) return;
-  float s = 0.f;
-  for (int f = 0; f < n; ++f) s = fmaf(head_grad(dmu, dlv, f, hj, L), __ldg(feat + (long long)f * F + inhwc), s);
+  const int f0 = blockIdx.y * fper, f1 = min(n, f0 + fper);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  int f = f0;
+  for (; f + 4 <= f1; f += 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      s[q] = fmaf(head_grad(dmu, dlv, f + q, hj, L), __ldg(feat + (long long)(f + q) * F + inhwc), s[q]);
+  }
+  for (; f < f1; ++f) s[0] = fmaf(head_grad(dmu, dlv, f, hj, L), __ldg(feat + (long long)f * F + inhwc), s[0]);
   int c = (int)(inhwc % C);
   long long pix = inhwc / C;
   int x = (int)(pix % W);
   int y = (int)(pix / W);
   int j = hj < L ? hj : hj - L;
-  g[(long long)j * F + ((long long)c * H + y) * W + x] += s;
+  atomicAdd(g + (long long)j * F + ((long long)c * H + y) * W + x, (s[0] + s[1]) + (s[2] + s[3]));
 }
 
-__global__ void heads_bwd_b_kernel(const float* __restrict__ dmu, const float* __restrict__ dlv,
-                                   int n, int L, int HJ, float* __restrict__ gb0,
-                                   float* __restrict__ gb1) {
-  int hj = blockIdx.x * blockDim.x + threadIdx.x;
-  if (hj >= HJ) return;
+// db_head[j] += sum_f dhead[f][j]: one block per output, frames strided over the threads
+__global__ void __launch_bounds__(128) heads_bwd_b_kernel(const float* __restrict__ dmu, const float* __restrict__ dlv,
+                                                          int n, int L, int HJ, float* __restrict__ gb0,
+                                                          float* __restrict__ gb1) {
+  __shared__ float red[4];
+  const int hj = blockIdx.x;
   float* g = hj < L ? gb0 : gb1;
   if (!g) return;
   if ((hj < L && !dmu) || (hj >= L && !dlv)) return;
   float s = 0.f;
-  for (int f = 0; f < n; ++f) s += head_grad(dmu, dlv, f, hj, L);
-  g[hj < L ? hj : hj - L] += s;
+  for (int f = threadIdx.x; f < n; f += 128) s += head_grad(dmu, dlv, f, hj, L);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) g[hj < L ? hj : hj - L] += (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,39 +368,71 @@ __global__ void decff_fwd_kernel(const float* __restrict__ z, const float* __res
   h0[i] = s;
 }
 
+// dz[f][j] = sum_i dh0[f][i_nhwc] * W[i_chw][j]: one block per frame, thread t owns features t, t+256, ..
+// and all L outputs (W rows are contiguous in j), then a block reduction per output.
+template <int LMAX>
 __global__ void __launch_bounds__(256) decff_bwd_z_kernel(const float* __restrict__ w,
                                                           const float* __restrict__ dh0, int n, int L,
-                                                          int C, int H, int W, float* __restrict__ dz) {
-  int warp = (blockIdx.x * 256 + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= n * L) return;
-  int f = warp / L, j = warp - f * L;
-  long long F = (long long)C * H * W;
-  float s = 0.f;
-  for (long long i = lane; i < F; i += 32)
-    s = fmaf(__ldg(dh0 + (long long)f * F + i), __ldg(w + nhwc_to_chw(i, C, H, W) * L + j), s);
-  s = warp_sum(s);
-  if (lane == 0) dz[(long long)f * L + j] = s;
+                                                          int C, int H, int W, int j0, float* __restrict__ dz) {
+  __shared__ float red[8][LMAX];
+  const int f = blockIdx.x;
+  const long long F = (long long)C * H * W;
+  float acc[LMAX];
+#pragma unroll
+  for (int j = 0; j < LMAX; ++j) acc[j] = 0.f;
+  for (long long i = threadIdx.x; i < F; i += 256) {
+    const float d = __ldg(dh0 + (long long)f * F + i);
+    const float* wp = w + nhwc_to_chw(i, C, H, W) * L + j0;
+#pragma unroll
+    for (int j = 0; j < LMAX; ++j)
+      if (j0 + j < L) acc[j] = fmaf(d, __ldg(wp + j), acc[j]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < LMAX; ++j) {
+    const float s = warp_sum(acc[j]);
+    if (lane == 0) red[warp][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < LMAX && j0 + threadIdx.x < L) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x];
+    dz[(long long)f * L + j0 + threadIdx.x] = s;
+  }
 }
 
-__global__ void decff_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ dh0, int n,
-                                   int L, int C, int H, int W, float* __restrict__ gw,
-                                   float* __restrict__ gb) {
+// dW[i_chw][j] += sum_f dh0[f][i_nhwc] z[f][j], db[i_chw] += sum_f dh0[f][i_nhwc]; frames split over
+// grid.y (atomic accumulate), four independent chains per thread
+__global__ void __launch_bounds__(256) decff_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ dh0, int n,
+                                                          int L, int C, int H, int W, int fper, float* __restrict__ gw,
+                                                          float* __restrict__ gb) {
   long long F = (long long)C * H * W;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over F * (L + 1)
   if (i >= F * (L + 1)) return;
   long long inhwc = i / (L + 1);
   int j = (int)(i - inhwc * (L + 1));
   long long ichw = nhwc_to_chw(inhwc, C, H, W);
-  float s = 0.f;
+  const int f0 = blockIdx.y * fper, f1 = min(n, f0 + fper);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  int f = f0;
   if (j < L) {
     if (!gw) return;
-    for (int f = 0; f < n; ++f) s = fmaf(__ldg(dh0 + (long long)f * F + inhwc), __ldg(z + (long long)f * L + j), s);
-    gw[ichw * L + j] += s;
+    for (; f + 4 <= f1; f += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        s[q] = fmaf(__ldg(dh0 + (long long)(f + q) * F + inhwc), __ldg(z + (long long)(f + q) * L + j), s[q]);
+    }
+    for (; f < f1; ++f) s[0] = fmaf(__ldg(dh0 + (long long)f * F + inhwc), __ldg(z + (long long)f * L + j), s[0]);
+    atomicAdd(gw + ichw * L + j, (s[0] + s[1]) + (s[2] + s[3]));
   } else {
     if (!gb) return;
-    for (int f = 0; f < n; ++f) s += __ldg(dh0 + (long long)f * F + inhwc);
-    gb[ichw] += s;
+    for (; f + 4 <= f1; f += 4) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += __ldg(dh0 + (long long)(f + q) * F + inhwc);
+    }
+    for (; f < f1; ++f) s[0] += __ldg(dh0 + (long long)f * F + inhwc);
+    atomicAdd(gb + ichw, (s[0] + s[1]) + (s[2] + s[3]));
   }
 }
 
@@ -474,9 +521,11 @@ int bn_launch_heads_bwd(const float* feat, const float* wcat, const float* dmu, 
   int HJ = dlogvar ? 2 * L : L;
   heads_bwd_data_kernel<<<bn_cdiv((long long)n * F, 256), 256, 0, st>>>(feat, wcat, dmu, dlogvar, n, L, HJ, F, dpre_feat);
   BN_LAUNCHED();
-  heads_bwd_w_kernel<<<bn_cdiv((long long)HJ * F, 256), 256, 0, st>>>(feat, dmu, dlogvar, n, L, HJ, C, H, W, gw0, gw1);
+  const int fsplit = n >= 64 ? 8 : 1, fper = bn_cdiv(n, fsplit);
+  heads_bwd_w_kernel<<<dim3(bn_cdiv((long long)HJ * F, 256), fsplit), 256, 0, st>>>(feat, dmu, dlogvar, n, L, HJ, C, H, W,
+                                                                                   fper, gw0, gw1);
   BN_LAUNCHED();
-  heads_bwd_b_kernel<<<bn_cdiv(HJ, 64), 64, 0, st>>>(dmu, dlogvar, n, L, HJ, gb0, gb1);
+  heads_bwd_b_kernel<<<HJ, 128, 0, st>>>(dmu, dlogvar, n, L, HJ, gb0, gb1);
   BN_LAUNCHED();
   return 0;
 }
@@ -494,11 +543,19 @@ int bn_launch_decff_bwd(const float* z, const float* w, const float* dh0, int n,
                         int W, float* dz, float* gw, float* gb, cudaStream_t st) {
   if (n <= 0) return 0;
   if (dz) {
-    decff_bwd_z_kernel<<<bn_cdiv((long long)n * L * 32, 256), 256, 0, st>>>(w, dh0, n, L, C, H, W, dz);
-    BN_LAUNCHED();
+    if (L <= 16) {
+      decff_bwd_z_kernel<16><<<n, 256, 0, st>>>(w, dh0, n, L, C, H, W, 0, dz);
+      BN_LAUNCHED();
+    } else {
+      for (int j0 = 0; j0 < L; j0 += 32) {
+        decff_bwd_z_kernel<32><<<n, 256, 0, st>>>(w, dh0, n, L, C, H, W, j0, dz);
+        BN_LAUNCHED();
+      }
+    }
   }
   long long F = (long long)C * H * W;
-  decff_bwd_w_kernel<<<bn_cdiv(F * (L + 1), 256), 256, 0, st>>>(z, dh0, n, L, C, H, W, gw, gb);
+  const int fsplit = n >= 64 ? 8 : 1, fper = bn_cdiv(n, fsplit);
+  decff_bwd_w_kernel<<<dim3(bn_cdiv(F * (L + 1), 256), fsplit), 256, 0, st>>>(z, dh0, n, L, C, H, W, fper, gw, gb);
   BN_LAUNCHED();
   return 0;
 }

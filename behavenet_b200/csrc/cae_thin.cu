@@ -24,129 +24,200 @@ struct ThinGeo {
   int pt, pl, n;
 };
 
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous (cp.async, zero-filled outside the image) copy of one tile's input patch
 template <int CB>
-__device__ __forceinline__ void load_patch(float (*patch)[PROWS][PCOLS], const ThinGeo& g, int f, int y0,
-                                           int x0, int tid) {
+__device__ __forceinline__ void issue_patch(float (*patch)[PROWS][PCOLS], const ThinGeo& g, int f, int y0,
+                                            int x0, int tid) {
   for (int i = tid; i < CB * PROWS * PCOLS; i += 256) {
     int c = i / (PROWS * PCOLS);
     int rem = i - c * PROWS * PCOLS;
     int r = rem / PCOLS, col = rem - r * PCOLS;
     int y = 2 * y0 - g.pt + r, x = 2 * x0 - g.pl + col;
-    float v = 0.f;
-    if ((unsigned)y < (unsigned)g.big.H && (unsigned)x < (unsigned)g.big.W)
-      v = __ldg(g.big.p + (long long)f * g.big.sn + (long long)y * g.big.sy + (long long)x * g.big.sx +
-                (long long)c * g.big.sc);
-    patch[c][r][col] = v;
+    const bool ok = (unsigned)y < (unsigned)g.big.H && (unsigned)x < (unsigned)g.big.W;
+    const float* src = ok ? g.big.p + (long long)f * g.big.sn + (long long)y * g.big.sy + (long long)x * g.big.sx +
+                                (long long)c * g.big.sc
+                          : g.big.p;
+    cp_async4(&patch[c][r][col], src, ok);
   }
 }
 
+struct TileIter {
+  int tiles_x, tiles_per_frame;
+  long long total;
+  __device__ __forceinline__ void decode(long long t, int& f, int& y0, int& x0) const {
+    f = (int)(t / tiles_per_frame);
+    const int tt = (int)(t - (long long)f * tiles_per_frame);
+    const int ty = tt / tiles_x;
+    y0 = ty * TH;
+    x0 = (tt - ty * tiles_x) * TW;
+  }
+};
+
+// Persistent blocks: the 25*CB weights of this lane's channel stay in registers for the whole kernel,
+// the next tile's patch streams in with cp.async while the current one is computed, and the
+// activation-derivative mask of a half row is fetched before the FMAs that precede its use.
 template <int CB>
 __global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          float* __restrict__ out,
                                                          const float* __restrict__ dact, int act,
-                                                         int tiles_x) {
-  __shared__ __align__(16) float patch[CB][PROWS][PCOLS];
+                                                         const TileIter it) {
+  extern __shared__ __align__(16) float thin_sm[];
+  typedef float (*Patch)[PROWS][PCOLS];
+  Patch patch[2] = {reinterpret_cast<Patch>(thin_sm), reinterpret_cast<Patch>(thin_sm + CB * PROWS * PCOLS)};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int f = blockIdx.y;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int y0 = ty * TH, x0 = tx * TW;
-  const int c = blockIdx.z * 32 + lane;
-  load_patch<CB>(patch, g, f, y0, x0, tid);
+  const int c = blockIdx.y * 32 + lane;
   float wr[25 * CB];
 #pragma unroll
   for (int i = 0; i < 25 * CB; ++i) wr[i] = __ldg(w + (long long)i * g.Cs + c);    // [(tap, cb)][cs]
   const float b = bias ? __ldg(bias + c) : 0.f;
-  __syncthreads();
-  const int oy = y0 + warp;
-  if (oy >= g.Hs) return;
-#pragma unroll 2
-  for (int j = 0; j < TW / 2; ++j) {
-    float a0 = 0.f, a1 = 0.f;
+  long long t = blockIdx.x;
+  int f, y0, x0;
+  if (t < it.total) {
+    it.decode(t, f, y0, x0);
+    issue_patch<CB>(patch[0], g, f, y0, x0, tid);
+  }
+  cp_commit();
+  for (int buf = 0; t < it.total; t += gridDim.x, buf ^= 1) {
+    it.decode(t, f, y0, x0);
+    const long long tn = t + gridDim.x;
+    if (tn < it.total) {
+      int fn, yn, xn;
+      it.decode(tn, fn, yn, xn);
+      issue_patch<CB>(patch[buf ^ 1], g, fn, yn, xn, tid);
+    }
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();
+    const int oy = y0 + warp;
+    if (oy < g.Hs) {
+      const long long rowbase = (((long long)f * g.Hs + oy) * g.Ws + x0) * g.Cs + c;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float d[TW / 2];
+        if (dact) {
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
+          for (int e = 0; e < TW / 2; ++e)
+            d[e] = x0 + half * (TW / 2) + e < g.Ws ? __ldg(dact + rowbase + (long long)(half * (TW / 2) + e) * g.Cs) : 1.f;
+        }
 #pragma unroll
-      for (int cb = 0; cb < CB; ++cb) {
-        const float4 v0 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j]);
-        const float4 v1 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j + 4]);
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        for (int jj = 0; jj < TW / 4; ++jj) {
+          const int j = half * (TW / 4) + jj;
+          float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-          const float wv = wr[(ky * 5 + kx) * CB + cb];
-          a0 = fmaf(v[kx], wv, a0);
-          a1 = fmaf(v[kx + 2], wv, a1);
+          for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) {
+              const float4 v0 = *reinterpret_cast<const float4*>(&patch[buf][cb][2 * warp + ky][4 * j]);
+              const float4 v1 = *reinterpret_cast<const float4*>(&patch[buf][cb][2 * warp + ky][4 * j + 4]);
+              const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) {
+                const float wv = wr[(ky * 5 + kx) * CB + cb];
+                a0 = fmaf(v[kx], wv, a0);
+                a1 = fmaf(v[kx + 2], wv, a1);
+              }
+            }
+          }
+          float r[2] = {a0 + b, a1 + b};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int xo = 2 * j + e;
+            if (x0 + xo >= g.Ws) continue;
+            float x = r[e];
+            if (act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+            if (dact) x *= d[2 * jj + e] > 0.f ? 1.f : BN_LEAK;
+            out[rowbase + (long long)xo * g.Cs] = x;
+          }
         }
       }
     }
-    const int ox = x0 + 2 * j;
-    float r[2] = {a0 + b, a1 + b};
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (ox + e >= g.Ws) continue;
-      float x = r[e];
-      if (act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-      const long long idx = (((long long)f * g.Hs + oy) * g.Ws + ox + e) * g.Cs + c;
-      if (dact) x *= __ldg(dact + idx) > 0.f ? 1.f : BN_LEAK;
-      out[idx] = x;
-    }
+    __syncthreads();       // patch[buf] is refilled by the next iteration's prefetch
   }
 }
 
 template <int CB>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinGeo g, const float* __restrict__ small,
-                                                         float* __restrict__ partial, int tiles_x,
-                                                         int tiles_per_frame, long long total_tiles) {
+                                                         float* __restrict__ partial, const TileIter it) {
   // persistent: each block walks tiles blockIdx.x, +gridDim.x, ...; lane = small-image channel
-  __shared__ __align__(16) float patch[CB][PROWS][PCOLS];
-  extern __shared__ __align__(16) float red[];          // [8][25*CB][32]
+  extern __shared__ __align__(16) float thin_sm[];
+  typedef float (*Patch)[PROWS][PCOLS];
+  Patch patch[2] = {reinterpret_cast<Patch>(thin_sm), reinterpret_cast<Patch>(thin_sm + CB * PROWS * PCOLS)};
+  float* red = thin_sm + 2 * CB * PROWS * PCOLS;          // [8][25*CB][32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.y * 32 + lane;
   float acc[25 * CB];
 #pragma unroll
   for (int i = 0; i < 25 * CB; ++i) acc[i] = 0.f;
-  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-    const int f = (int)(t / tiles_per_frame);
-    const int tt = (int)(t - (long long)f * tiles_per_frame);
-    const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-    const int y0 = ty * TH, x0 = tx * TW;
-    __syncthreads();
-    load_patch<CB>(patch, g, f, y0, x0, tid);
-    __syncthreads();
+  long long t = blockIdx.x;
+  int f, y0, x0;
+  if (t < it.total) {
+    it.decode(t, f, y0, x0);
+    issue_patch<CB>(patch[0], g, f, y0, x0, tid);
+  }
+  cp_commit();
+  for (int buf = 0; t < it.total; t += gridDim.x, buf ^= 1) {
+    it.decode(t, f, y0, x0);
+    const long long tn = t + gridDim.x;
+    if (tn < it.total) {
+      int fn, yn, xn;
+      it.decode(tn, fn, yn, xn);
+      issue_patch<CB>(patch[buf ^ 1], g, fn, yn, xn, tid);
+    }
+    cp_commit();
     const int oy = y0 + warp;
+    // this warp's row of the small image: fetched before waiting for the patch
+    float s[TW];
     if (oy < g.Hs) {
       const float* srow = small + (((long long)f * g.Hs + oy) * g.Ws + x0) * g.Cs + c;
-#pragma unroll 2
+#pragma unroll
+      for (int e = 0; e < TW; ++e) s[e] = x0 + e < g.Ws ? __ldg(srow + (long long)e * g.Cs) : 0.f;
+    }
+    cp_wait<1>();
+    __syncthreads();
+    if (oy < g.Hs) {
+#pragma unroll
       for (int j = 0; j < TW / 2; ++j) {
-        const int ox = x0 + 2 * j;
-        const float s0 = ox < g.Ws ? __ldg(srow + (long long)(2 * j) * g.Cs) : 0.f;
-        const float s1 = ox + 1 < g.Ws ? __ldg(srow + (long long)(2 * j + 1) * g.Cs) : 0.f;
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
           for (int cb = 0; cb < CB; ++cb) {
-            const float4 v0 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j]);
-            const float4 v1 = *reinterpret_cast<const float4*>(&patch[cb][2 * warp + ky][4 * j + 4]);
+            const float4 v0 = *reinterpret_cast<const float4*>(&patch[buf][cb][2 * warp + ky][4 * j]);
+            const float4 v1 = *reinterpret_cast<const float4*>(&patch[buf][cb][2 * warp + ky][4 * j + 4]);
             const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int kx = 0; kx < 5; ++kx) {
               float& a = acc[(ky * 5 + kx) * CB + cb];
-              a = fmaf(v[kx], s0, a);
-              a = fmaf(v[kx + 2], s1, a);
+              a = fmaf(v[kx], s[2 * j], a);
+              a = fmaf(v[kx + 2], s[2 * j + 1], a);
             }
           }
         }
       }
     }
+    __syncthreads();
   }
   // cross-warp reduction, then this block's slice of the partial buffer [(tap, cb)][Cs]
 #pragma unroll
   for (int i = 0; i < 25 * CB; ++i) red[(warp * 25 * CB + i) * 32 + lane] = acc[i];
   __syncthreads();
   for (int i = warp; i < 25 * CB; i += 8) {
-    float s = 0.f;
+    float sum = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s += red[(q * 25 * CB + i) * 32 + lane];
-    partial[((long long)blockIdx.x * 25 * CB + i) * g.Cs + c] = s;
+    for (int q = 0; q < 8; ++q) sum += red[(q * 25 * CB + i) * 32 + lane];
+    partial[((long long)blockIdx.x * 25 * CB + i) * g.Cs + c] = sum;
   }
 }
 
@@ -168,85 +239,113 @@ struct Dg5Args {
   float* dpre;
 };
 
-constexpr int DT = 16;      // output tile edge
-constexpr int DP = 10;      // input patch edge: (DT + 4) / 2
+constexpr int DT = 16;      // small-image tile edge: a thread owns one small pixel = a 2x2 output quad
+constexpr int DP = DT + 2;  // input patch edge (3x3 neighbourhood)
 
-template <int CB>
+// Thread = one small-image pixel and its 2x2 quad of output pixels (the four stride-residue classes).
+// The quad's 25 taps read only the 3x3 small-pixel neighbourhood, so every neighbour vector is
+// fetched from shared memory ONCE per 4 channels and reused by all taps / classes that touch it
+// (9 lane-strided + 25 broadcast LDS.128 per 100*CB FMAs: FMA-bound instead of LDS-bound).
+// PTO / PLO = parity of the crop offsets: they fix which taps belong to which class at compile time.
+template <int CB, int PTO, int PLO>
 __global__ void __launch_bounds__(256) thin_dgrad5_kernel(const Dg5Args a, int tiles_x) {
   extern __shared__ __align__(16) float sm[];
   const int Cs = a.Cs, PS = Cs + 4;                    // padded pixel stride: conflict-free LDS.128
   float* patch = sm;                                   // [DP*DP][PS]
   float* wsm = sm + DP * DP * PS;                      // [25][CB][Cs]
   __shared__ double sse_sm;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int f = blockIdx.y;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int y0 = ty * DT, x0 = tx * DT;
-  // patch origin: smallest input row/col any pixel of the tile can touch
-  const int iy0 = (y0 + a.pt - 3) >> 1, ix0 = (x0 + a.pl - 3) >> 1;      // = ceil((y0 + pt - 4) / 2)
+  const int sy0 = ty * DT, sx0 = tx * DT;              // small-pixel origin of the tile
+  // output pixel (2*ys + py, 2*xs + px) gathers small pixel (ys + (py + pt - ky) / 2, ..) for the
+  // taps with ky = (py + pt) mod 2 (+2, +4): offsets span [(pt - PTO) / 2 - 1 - .., ..]; with
+  // dy(py, ky) = (py + PTO - ky) / 2 in {-2..1} relative to the shifted origin ys + (pt - PTO) / 2
+  const int shy = (a.pt - PTO) >> 1, shx = (a.pl - PLO) >> 1;
+  const int iy0 = sy0 + shy - 1, ix0 = sx0 + shx - 1;  // patch origin (neighbour offsets -1..+1 -> rows 0..2)
   for (int i = tid; i < DP * DP * (Cs / 4); i += 256) {
-    int p = i / (Cs / 4), q = i - p * (Cs / 4);
-    int pr = p / DP, pc = p - pr * DP;
-    int iy = iy0 + pr, ix = ix0 + pc;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((unsigned)iy < (unsigned)a.Hs && (unsigned)ix < (unsigned)a.Ws)
-      v = __ldg(reinterpret_cast<const float4*>(a.small + (((long long)f * a.Hs + iy) * a.Ws + ix) * Cs) + q);
-    *reinterpret_cast<float4*>(patch + p * PS + q * 4) = v;
+    const int p = i / (Cs / 4), q = i - p * (Cs / 4);
+    const int pr = p / DP, pc = p - pr * DP;
+    const int iy = iy0 + pr, ix = ix0 + pc;
+    const bool ok = (unsigned)iy < (unsigned)a.Hs && (unsigned)ix < (unsigned)a.Ws;
+    cp_async16(patch + p * PS + q * 4, ok ? a.small + (((long long)f * a.Hs + iy) * a.Ws + ix) * Cs + q * 4 : a.small, ok);
   }
+  cp_commit();
   for (int i = tid; i < 25 * CB * Cs; i += 256) {
-    int tap = i / (CB * Cs);
-    int rem = i - tap * CB * Cs;
-    int cb = rem / Cs, ci = rem - cb * Cs;
+    const int tap = i / (CB * Cs);
+    const int rem = i - tap * CB * Cs;
+    const int cb = rem / Cs, ci = rem - cb * Cs;
     wsm[i] = __ldg(a.wd + ((long long)tap * Cs + ci) * CB + cb);
   }
   if (tid == 0) sse_sm = 0.0;
+  cp_wait<0>();
   __syncthreads();
-  // warp -> stride-residue class (uniform tap list), lane -> pixel of that class
-  const int cls = warp >> 1;
-  const int py = cls >> 1, px = cls & 1;
-  const int yy = (warp & 1) * 4 + (lane >> 3), xx = lane & 7;
-  const int y = y0 + 2 * yy + py, x = x0 + 2 * xx + px;
-  const bool valid = y < a.Hb && x < a.Wb;
-  float acc[CB];
+  const int yy = tid >> 4, xx = tid & 15;
+  float acc[2][2][CB];
 #pragma unroll
-  for (int c = 0; c < CB; ++c) acc[c] = 0.f;
-  const int ky0 = (py + a.pt) & 1, kx0 = (px + a.pl) & 1;       // y0, x0 are even
-  for (int ky = ky0; ky < 5; ky += 2) {
-    const int pr = ((y0 + py + a.pt - ky) >> 1) + yy - iy0;
-    for (int kx = kx0; kx < 5; kx += 2) {
-      const int pc = ((x0 + px + a.pl - kx) >> 1) + xx - ix0;
-      const float* ip = patch + (pr * DP + pc) * PS;
-      const float* wp = wsm + (ky * 5 + kx) * CB * Cs;
-      for (int q = 0; q < Cs; q += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(ip + q);
+  for (int py = 0; py < 2; ++py)
 #pragma unroll
-        for (int c = 0; c < CB; ++c) {
-          const float4 wv = *reinterpret_cast<const float4*>(wp + c * Cs + q);
-          acc[c] = fmaf(v.x, wv.x, acc[c]);
-          acc[c] = fmaf(v.y, wv.y, acc[c]);
-          acc[c] = fmaf(v.z, wv.z, acc[c]);
-          acc[c] = fmaf(v.w, wv.w, acc[c]);
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int c = 0; c < CB; ++c) acc[py][px][c] = 0.f;
+  for (int q = 0; q < Cs; q += 4) {
+#pragma unroll
+    for (int ny = 0; ny < 3; ++ny) {
+#pragma unroll
+      for (int nx = 0; nx < 3; ++nx) {
+        const float4 v = *reinterpret_cast<const float4*>(patch + ((yy + ny) * DP + xx + nx) * PS + q);
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+#pragma unroll
+          for (int ky = (py + PTO) & 1; ky < 5; ky += 2) {
+            if ((py + PTO - ky) / 2 + 1 != ny || (py + PTO - ky) % 2 != 0) continue;   // compile-time after unrolling
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+#pragma unroll
+              for (int kx = (px + PLO) & 1; kx < 5; kx += 2) {
+                if ((px + PLO - kx) / 2 + 1 != nx || (px + PLO - kx) % 2 != 0) continue;
+                const float* wp = wsm + (ky * 5 + kx) * CB * Cs + q;
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                  const float4 wv = *reinterpret_cast<const float4*>(wp + c * Cs);
+                  float s = acc[py][px][c];
+                  s = fmaf(v.x, wv.x, s);
+                  s = fmaf(v.y, wv.y, s);
+                  s = fmaf(v.z, wv.z, s);
+                  s = fmaf(v.w, wv.w, s);
+                  acc[py][px][c] = s;
+                }
+              }
+            }
+          }
         }
       }
     }
   }
   double my_sse = 0.0;
-  if (valid) {
-    const int chunk = (f + a.frame_offset) / a.chunk_size;
-    const int len = min(a.chunk_size, a.n_total - chunk * a.chunk_size);
-    const float gsc = a.coef / (float)len;
+  const int chunk = (f + a.frame_offset) / a.chunk_size;
+  const int len = min(a.chunk_size, a.n_total - chunk * a.chunk_size);
+  const float gsc = a.coef / (float)len;
 #pragma unroll
-    for (int c = 0; c < CB; ++c) {
-      float v = acc[c] + (a.bias ? __ldg(a.bias + c) : 0.f);
-      v = 1.f / (1.f + expf(-v));
-      const long long inchw = (((long long)f * CB + c) * a.Hb + y) * a.Wb + x;
-      a.xhat_ws[inchw] = v;
-      if (a.xhat_user) a.xhat_user[inchw] = v;
-      if (a.target) {
-        const float d = v - __ldg(a.target + inchw);
-        const float m = a.mask ? __ldg(a.mask + inchw) : 1.f;
-        my_sse += (double)(d * d * m);
-        a.dpre[(((long long)f * a.Hb + y) * a.Wb + x) * CB + c] = gsc * d * m * v * (1.f - v);
+  for (int py = 0; py < 2; ++py) {
+    const int y = 2 * (sy0 + yy) + py;
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const int x = 2 * (sx0 + xx) + px;
+      if (y >= a.Hb || x >= a.Wb) continue;
+#pragma unroll
+      for (int c = 0; c < CB; ++c) {
+        float v = acc[py][px][c] + (a.bias ? __ldg(a.bias + c) : 0.f);
+        v = 1.f / (1.f + expf(-v));
+        const long long inchw = (((long long)f * CB + c) * a.Hb + y) * a.Wb + x;
+        a.xhat_ws[inchw] = v;
+        if (a.xhat_user) a.xhat_user[inchw] = v;
+        if (a.target) {
+          const float d = v - __ldg(a.target + inchw);
+          const float m = a.mask ? __ldg(a.mask + inchw) : 1.f;
+          my_sse += (double)(d * d * m);
+          a.dpre[(((long long)f * a.Hb + y) * a.Wb + x) * CB + c] = gsc * d * m * v * (1.f - v);
+        }
       }
     }
   }
@@ -256,7 +355,7 @@ __global__ void __launch_bounds__(256) thin_dgrad5_kernel(const Dg5Args a, int t
     for (int o = 16; o > 0; o >>= 1) my_sse += __shfl_xor_sync(0xffffffffu, my_sse, o);
     if (lane == 0 && my_sse != 0.0) atomicAdd(&sse_sm, my_sse);
     __syncthreads();
-    if (tid == 0 && sse_sm != 0.0) atomicAdd(a.sse + (f + a.frame_offset) / a.chunk_size, sse_sm);
+    if (tid == 0 && sse_sm != 0.0) atomicAdd(a.sse + chunk, sse_sm);
   }
 }
 

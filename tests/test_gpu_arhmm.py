@@ -159,3 +159,61 @@ def test_reference_call_sequence_runs():
     z, x = hmm.sample(50)
     assert z.shape == (50,) and x.shape == (50, 6)
     assert hmm.transitions.transition_matrix.shape == (4, 4)
+
+
+@pytest.mark.parametrize('K,D,lags', [(16, 12, 2), (5, 7, 3), (32, 4, 1), (3, 16, 0)])
+def test_cuda_core_and_tensor_core_emissions_agree(K, D, lags):
+    """bn_set_tensor_core_mode(0) keeps the E-step on the fp32 CUDA-core emission kernel; mode 1 (default)
+    uses the tcgen05 3xTF32 kernel.  Both must meet the oracle tolerance and agree with each other."""
+    from behavenet_b200 import _lib
+    p = ao.synth_params(K, D, lags, seed=3 * K + D, mix=0.05)
+    if lags == 0:
+        p.As = np.zeros((K, D, 0))
+    rng = np.random.RandomState(4)
+    xs = [ao.sample(p, T, rng)[1].astype(np.float32) for T in (300, 129, 5)]
+    out = {}
+    try:
+        for mode in (0, 1):
+            _lib.lib().bn_set_tensor_core_mode(mode)
+            check_against_oracle(p, xs)
+            hmm = make_hmm(p)
+            out[mode] = [hmm.expected_states(x) for x in xs]
+    finally:
+        _lib.lib().bn_set_tensor_core_mode(1)
+    for (g0, j0, l0), (g1, j1, l1) in zip(out[0], out[1]):
+        assert np.abs(g0 - g1).max() < 1e-5
+        assert abs(l0 - l1) <= 1e-6 * abs(l0) + 1e-4
+
+
+def test_many_ragged_trials_batched():
+    """600 ragged trials in ONE launch: every emission CTA walks several trials and time tiles, scan warps
+    carry trials of different lengths.  Batched results must equal the per-trial oracle (subset) and the
+    CUDA-core emission path (all trials)."""
+    import torch
+    from behavenet_b200 import _lib
+    K, D, lags = 6, 4, 2
+    p = ao.synth_params(K, D, lags, seed=21, mix=0.05)
+    rng = np.random.RandomState(5)
+    lens = rng.randint(1, 400, size=600)
+    lens[:4] = [1, 2, 3, 399]
+    xs = [ao.sample(p, int(T), rng)[1].astype(np.float32) for T in lens]
+    hmm = make_hmm(p)
+    st = hmm._stage(xs)
+    out = {}
+    try:
+        for mode in (0, 1):
+            _lib.lib().bn_set_tensor_core_mode(mode)
+            Ez, Ezz, logZ = hmm._run_estep(st, True)
+            torch.cuda.synchronize()
+            out[mode] = (Ez.cpu().numpy(), Ezz.cpu().numpy(), logZ.cpu().numpy())
+    finally:
+        _lib.lib().bn_set_tensor_core_mode(1)
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-5
+    assert np.abs(out[0][2] - out[1][2]).max() < 1e-3
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for i in list(range(8)) + [77, 300, 599]:
+        g, j, lz = ao.e_step(p, [xs[i]])[0]
+        for mode in (0, 1):
+            assert np.abs(out[mode][0][off[i]:off[i + 1]] - g).max() < 1e-5
+            assert np.abs(out[mode][1][i] - j).max() < 1e-5 * max(1, lens[i])
+            assert abs(out[mode][2][i] - lz) <= 1e-6 * abs(lz) + 1e-4

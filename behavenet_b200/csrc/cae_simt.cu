@@ -366,19 +366,65 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgArgs a) {
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Ktot, int Cs,
-                                    int Cb, int KK, const TapClass* __restrict__ cls,
-                                    float* __restrict__ grad) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long tot = (long long)Ktot * Cs;
-  if (idx >= tot) return;
-  int kk = (int)(idx / Cs);
-  int cs = (int)(idx - (long long)kk * Cs);
-  int tap = kk / Cb;
-  int cb = kk - tap * Cb;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += partial[(long long)z * tot + idx];
-  grad[((long long)cs * Cb + cb) * KK + cls->wt[tap]] += s;
+// grad[cs][cb][wt[tap]] += sum_z partial[z][(tap, cb)][cs].  The partial slices are cs-fastest, the
+// torch gradient is tap-fastest: a block owns 32 cs x 32 consecutive (cb, tap) output positions, its
+// warps read the matching partial rows (128 contiguous bytes of cs each, 8 loads in flight per lane)
+// and the brick is transposed through shared memory so the read-modify-write runs are 128 bytes too.
+// Few-output layers (the thin first / last layer has 800 outputs but ~300 slices) spread the slices
+// over grid.z and finish with atomicAdd; everything else is a deterministic +=.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Ktot,
+                                                           int Cs, int Cb, int KK, const TapClass* __restrict__ cls,
+                                                           float* __restrict__ grad) {
+  __shared__ float tile[32][33];
+  __shared__ unsigned char inv[BN_MAX_TAPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < KK) inv[cls->wt[tid]] = (unsigned char)tid;
+  __syncthreads();
+  const int cs = blockIdx.x * 32 + lane;
+  const int o0 = blockIdx.y * 32;
+  const int nout = Cb * KK;
+  const long long tot = (long long)Ktot * Cs;
+  const int zper = (splits + gridDim.z - 1) / gridDim.z;
+  const int z0 = blockIdx.z * zper, z1 = min(splits, z0 + zper);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* p[4];
+  bool ok[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int o = o0 + warp * 4 + r;
+    ok[r] = o < nout && cs < Cs;
+    const int cb = ok[r] ? o / KK : 0;
+    const int tap = ok[r] ? inv[o - cb * KK] : 0;
+    p[r] = partial + ((long long)tap * Cb + cb) * Cs + (cs < Cs ? cs : 0);
+  }
+  int z = z0;
+  for (; z + 2 <= z1; z += 2) {
+    float v[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      v[2 * r] = ok[r] ? __ldg(p[r] + (long long)z * tot) : 0.f;
+      v[2 * r + 1] = ok[r] ? __ldg(p[r] + (long long)(z + 1) * tot) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s[r] += v[2 * r] + v[2 * r + 1];
+  }
+  for (; z < z1; ++z)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) s[r] += ok[r] ? __ldg(p[r] + (long long)z * tot) : 0.f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tile[lane][warp * 4 + r] = s[r];
+  __syncthreads();
+  // 8 warps x 4 cs rows; lane = output position
+  const int o = o0 + lane;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = blockIdx.x * 32 + warp * 4 + r;
+    if (c < Cs && o < nout) {
+      float* g = grad + (long long)c * nout + o;
+      if (gridDim.z > 1) atomicAdd(g, tile[warp * 4 + r][lane]);
+      else *g += tile[warp * 4 + r][lane];
+    }
+  }
 }
 
 }  // namespace
@@ -427,8 +473,11 @@ size_t bn_wgrad_partial_floats(const ConvGeom& g, int n) {
 
 int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, int Cb, int KK,
                            const TapClass* cls, float* grad, cudaStream_t st) {
-  long long tot = (long long)Ktot * Cs;
-  wgrad_reduce_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(partial, splits, Ktot, Cs, Cb, KK, cls, grad);
+  const int gx = bn_cdiv(Cs, 32), gy = bn_cdiv((long long)Cb * KK, 32);
+  int gz = 2 * 148 / (gx * gy);
+  if (gz > splits / 4) gz = splits / 4;
+  if (gz < 1) gz = 1;
+  wgrad_reduce_kernel<<<dim3(gx, gy, gz), 256, 0, st>>>(partial, splits, Ktot, Cs, Cb, KK, cls, grad);
   BN_LAUNCHED();
   return 0;
 }
@@ -451,9 +500,5 @@ int bn_launch_wgrad(const ImgView& big, const float* small, const ConvGeom& g, i
   if (vec) wgrad_kernel<true><<<grid, 256, 0, st>>>(a);
   else wgrad_kernel<false><<<grid, 256, 0, st>>>(a);
   BN_LAUNCHED();
-  long long tot = (long long)Ktot * g.Cs;
-  wgrad_reduce_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(partial, splits, Ktot, g.Cs, g.Cb, g.k * g.k,
-                                                          g.d_fprop, grad);
-  BN_LAUNCHED();
-  return 0;
+  return bn_launch_wgrad_reduce(partial, splits, Ktot, g.Cs, g.Cb, g.k * g.k, g.d_fprop, grad, st);
 }

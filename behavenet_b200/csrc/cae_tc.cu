@@ -35,6 +35,7 @@ constexpr int NPROD = 128;      // producer / epilogue threads (warps 0-3)
 constexpr int NTHREADS = 160;   // + warp 4: TMEM allocator and MMA issuer
 
 
+__device__ __forceinline__ uint64_t make_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes);
 // K-major SWIZZLE_128B shared-memory matrix descriptor (the layout TMA would write):
 //   a tile row is 128 contiguous bytes (32 tf32), 8 rows form a 1024-byte swizzle atom in which the
 //   16-byte chunk c of row r is stored at chunk position c ^ (r & 7).  SBO = 1024 bytes between
@@ -47,6 +48,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;          // SBO
   d |= (uint64_t)1 << 46;                    // descriptor version 1 (sm_100)
   d |= (uint64_t)2 << 61;                    // layout type 2 = SWIZZLE_128B
+  return d;
+}
+// same layout with an explicit stride between 8-row groups (rows of an image tile whose pitch is not 8 pixels)
+__device__ __forceinline__ uint64_t make_desc_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 
@@ -207,6 +218,9 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
       int oy = cls->oy0 + a.os * ym, ox = cls->ox0 + a.os * xm;
       obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + n0;
     }
+    // all MMAs have retired, so the pipeline stages are free: reuse them as the transposition tiles
+    float* tile = reinterpret_cast<float*>(smem) + warp * 1024;
+    const int elane = tid & 31;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       uint32_t r[32];
@@ -217,34 +231,22 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      if (rvalid && a.ksplit > 1) {
-        float* po = a.split_out + ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32;
+      float v[32];
+      if (a.ksplit > 1) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<float4*>(po + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
-                                                           __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
-      } else if (rvalid) {
+        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+        const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
+        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, v, tile, elane);
+      } else {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(r[q + e]);
-            if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q + e);
-            if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-            else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-            v[e] = x;
-          }
-          const long long idx = obase + j * 32 + q;
-          if (a.dact) {
-            float4 d = __ldg(reinterpret_cast<const float4*>(a.dact + idx));
-            v[0] *= d.x > 0.f ? 1.f : BN_LEAK;
-            v[1] *= d.y > 0.f ? 1.f : BN_LEAK;
-            v[2] *= d.z > 0.f ? 1.f : BN_LEAK;
-            v[3] *= d.w > 0.f ? 1.f : BN_LEAK;
-          }
-          *reinterpret_cast<float4*>(a.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int q = 0; q < 32; ++q) {
+          float x = __uint_as_float(r[q]);
+          if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q);
+          if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+          else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+          v[q] = x;
         }
+        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
       }
     }
     tc_fence_before();
@@ -417,6 +419,9 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
       int oy = cls->oy0 + a.os * ym, ox = cls->ox0 + a.os * xm;
       obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + n0;
     }
+    // all MMAs have retired, so the pipeline stages are free: reuse them as the transposition tiles
+    float* tile = reinterpret_cast<float*>(smem) + warp * 1024;
+    const int elane = tid & 31;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       uint32_t r[32];
@@ -427,34 +432,22 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      if (rvalid && a.ksplit > 1) {
-        float* po = a.split_out + ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32;
+      float v[32];
+      if (a.ksplit > 1) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<float4*>(po + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
-                                                           __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
-      } else if (rvalid) {
+        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+        const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
+        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, v, tile, elane);
+      } else {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(r[q + e]);
-            if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q + e);
-            if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-            else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-            v[e] = x;
-          }
-          const long long idx = obase + j * 32 + q;
-          if (a.dact) {
-            float4 d = __ldg(reinterpret_cast<const float4*>(a.dact + idx));
-            v[0] *= d.x > 0.f ? 1.f : BN_LEAK;
-            v[1] *= d.y > 0.f ? 1.f : BN_LEAK;
-            v[2] *= d.z > 0.f ? 1.f : BN_LEAK;
-            v[3] *= d.w > 0.f ? 1.f : BN_LEAK;
-          }
-          *reinterpret_cast<float4*>(a.out + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int q = 0; q < 32; ++q) {
+          float x = __uint_as_float(r[q]);
+          if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q);
+          if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+          else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+          v[q] = x;
         }
+        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
       }
     }
     tc_fence_before();
@@ -752,7 +745,8 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const WgTcArgs a) {
     }
     // epilogue: row kk of the partial slice, 32 columns at a time
     const int kk = kk0 + tid;
-    float* prow = a.partial + ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+    const long long prow_idx = ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+    float* tile = reinterpret_cast<float*>(smem) + warp * 1024;      // pipeline stages are idle now
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       uint32_t r[32];
@@ -763,13 +757,10 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const WgTcArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      if (kk < a.Ktot) {
+      float v[32];
 #pragma unroll
-        for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<float4*>(prow + j * 32 + q) =
-              make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
-                          __uint_as_float(r[q + 3]));
-      }
+      for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, v, tile, tid & 31);
     }
     tc_fence_before();
   } else {
@@ -889,7 +880,8 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
       tc_fence_after();
     }
     const int kk = kk0 + tid;
-    float* prow = a.partial + ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+    const long long prow_idx = ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+    float* tile = reinterpret_cast<float*>(smem) + warp * 1024;      // pipeline stages are idle now
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       uint32_t r[32];
@@ -900,13 +892,10 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      if (kk < a.Ktot) {
+      float v[32];
 #pragma unroll
-        for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<float4*>(prow + j * 32 + q) =
-              make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]),
-                          __uint_as_float(r[q + 3]));
-      }
+      for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, v, tile, tid & 31);
     }
     tc_fence_before();
   } else {
@@ -1011,6 +1000,347 @@ const TmaSet* get_tma_set(const ImgView& in, const float* wt, int wrow, int Co, 
   return &g_tma_cache.back().second;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Halo-resident transposed convolution (dgrad form, stride 2: ConvTranspose2d forward and Conv2d
+// backward-data of the fat layers).
+//
+// The im2col kernels above are bound by L2 -> SM bandwidth, not by the tensor pipe: every small-image
+// pixel is fetched once per filter tap (25x for the four stride-residue classes together).  Here a CTA
+// owns a 16 x 8 block of small-image pixels of one frame and ALL FOUR residue classes of the 32 x 16
+// output pixels they produce.  The (16+2)-row x 16-pixel input halo of a 32-channel chunk is staged
+// ONCE by a single tiled TMA copy (zero fill outside the image = the transposed-conv border) as
+// 128-byte pixel rows in the SWIZZLE_128B K-major layout, so the A operand of filter tap (dy, dx) is
+// the same buffer at row offset (dy - lo_y) * 16 + (dx - lo_x): 8 consecutive pixels of an image row
+// are one swizzle atom, the next tile row is SBO = 16 rows = 2048 bytes further.  No data moves per
+// tap; 25 taps x 4 k-steps of tcgen05.mma read the halo in place into four TMEM accumulators (one
+// per class).  Only the weights stream: one TMA tile (NB x 32 floats) per (tap, chunk).
+// A-side traffic drops from 25 fetches per small pixel to 2.25.
+//
+// The shifted window starts on a 128-byte row that is not a multiple of 8 rows: the descriptor's
+// base-offset field carries (row & 7) so that the 128B-swizzle phase matches what TMA wrote.
+// ------------------------------------------------------------------------------------------------
+constexpr int HALO_W = 10, HALO_H = 18;                 // box: (8 + 2) pixels x (16 + 2) rows
+constexpr int HALO_ABYTES = HALO_W * HALO_H * 128;      // one 32-channel chunk: 23040 bytes
+constexpr int HALO_ASTRIDE = (HALO_ABYTES + 1023) / 1024 * 1024;
+constexpr int HALO_THREADS = 192;                       // warps 0-3 epilogue, 4 MMA, 5 TMA producer
+constexpr int HALO_MAXG = 12;
+
+__device__ __forceinline__ void tma_tile_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h,
+                                            int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+
+// One MMA group = one halo window (tap offset) shared by `ncls` residue classes whose accumulators
+// sit in adjacent TMEM column blocks col0 .. col0 + ncls - 1: a single tcgen05.mma of N = ncls * NB
+// against the stacked weight tiles of those classes.  Small-N MMAs are bound by the 4 KB A-operand
+// fetch, not by the tensor pipe, so sharing the window between classes is what makes them efficient.
+struct HaloGroup {
+  unsigned short row_off;    // window offset in halo rows (pixels)
+  unsigned char col0, ncls;
+  unsigned char wt[4];       // weight tap index per stacked class
+};
+
+struct HaloArgs {
+  TcArgs a;
+  int lo_y, lo_x;            // smallest tap offset over all classes
+  int tiles_x;               // 8-pixel column blocks per frame
+  int ngroups;
+  int dbg;                   // experiment switches (BN_HALO_DBG): 1 no stores, 2 no MMAs, 4 no weight loads, 8 no bias/act
+  int pos[4];                // TMEM column block of class c
+  int Hm[4], Wm[4], oy0[4], ox0[4];
+  HaloGroup g[HALO_MAXG];
+};
+
+struct alignas(64) HaloMaps {
+  CUtensorMap a;       // NHWC input, box 32 ch x 10 px x 18 rows x 1 frame
+  CUtensorMap b;       // K-major weights, box 32 x NB
+};
+
+template <int NB, int NST>
+struct HaloSmem {
+  static constexpr int B_TILE = NB * 128;
+  static constexpr int B_BYTES = 4 * B_TILE;                          // up to four stacked class tiles
+  static constexpr int OFF_A = NST * B_BYTES;                         // multiple of 1024
+  static constexpr int OFF_BAR = OFF_A + 2 * HALO_ASTRIDE;
+  static constexpr int TOTAL = OFF_BAR + 8 * (2 * NST + 5) + 32;
+};
+
+template <int NB, int NST>
+__global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_constant__ HaloMaps maps,
+                                                                  const __grid_constant__ HaloArgs h) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using S = HaloSmem<NB, NST>;
+  constexpr int NCOLS = 4 * NB;                      // 128 or 256 TMEM columns: one accumulator per class
+  const TcArgs& a = h.a;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* b_empty = b_full + NST;
+  uint64_t* a_full = b_empty + NST;       // [2]
+  uint64_t* a_empty = a_full + 2;         // [2]
+  uint64_t* accum_bar = a_empty + 2;      // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(smem_u32(b_full + s), 1);
+      mbar_init(smem_u32(b_empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(a_full + s), 1);
+      mbar_init(smem_u32(a_empty + s), 1);
+    }
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int Ci = a.Ci;
+  const int nchunk = Ci / BK;
+  const int f = blockIdx.y;
+  const int by = blockIdx.x / h.tiles_x, bx = blockIdx.x - by * h.tiles_x;
+  const int ym0 = by * 16, xm0 = bx * 8;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp < 4) {
+    // ======================= epilogue ============================================================
+    mbar_wait(smem_u32(accum_bar), 0);
+    tc_fence_after();
+    const int ym = ym0 + (tid >> 3), xm = xm0 + (tid & 7);
+    float* tile = reinterpret_cast<float*>(smem) + warp * 1024;      // the weight ring is idle now
+    const int elane = tid & 31;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
+      const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
+      const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
+#pragma unroll 1
+      for (int j = 0; j < NB / 32; ++j) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + h.pos[c] * NB + j * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float x = __uint_as_float(r[q]);
+          if (a.bias) x += __ldg(a.bias + j * 32 + q);
+          if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+          else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+          v[q] = x;
+        }
+        if (!(h.dbg & 1)) warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ======================= MMA issuer ==========================================================
+    if ((tid & 31) == 0) {
+      int i = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        mbar_wait(smem_u32(a_full + (c & 1)), (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t abuf = smem_base + S::OFF_A + (c & 1) * HALO_ASTRIDE;
+        for (int gi = 0; gi < h.ngroups; ++gi, ++i) {
+          const int stage = i % NST;
+          mbar_wait(smem_u32(b_full + stage), (i / NST) & 1);
+          tc_fence_after();
+          const uint32_t sb = smem_base + stage * S::B_BYTES;
+          const HaloGroup g = h.g[gi];
+          const uint32_t idesc = make_idesc(BM, g.ncls * NB);
+          const uint32_t acc = tmem_base + g.col0 * NB;
+          const uint32_t arow = abuf + g.row_off * 128;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            // the 128B swizzle is a function of the shared-memory ADDRESS bits, so a window that starts
+            // on any 128-byte row of the TMA-written halo needs no descriptor base offset
+            const uint64_t ad = make_desc_sw128_sbo(arow + k * 32, HALO_W * 128);
+            const uint64_t bd = make_desc_sw128(sb + k * 32);
+            if (!(h.dbg & 2)) umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit(smem_u32(b_empty + stage));
+        }
+        umma_commit(smem_u32(a_empty + (c & 1)));
+      }
+      umma_commit(smem_u32(accum_bar));
+    }
+    __syncwarp();
+  } else {
+    // ======================= TMA producer: halo chunks and weight tiles ==========================
+    if ((tid & 31) == 0) {
+      auto load_halo = [&](int c) {
+        if (c >= 2) mbar_wait(smem_u32(a_empty + (c & 1)), ((c >> 1) - 1) & 1);
+        const uint32_t bar = smem_u32(a_full + (c & 1));
+        mbar_expect_tx(bar, (uint32_t)HALO_ABYTES);
+        tma_tile_4d(smem_base + S::OFF_A + (c & 1) * HALO_ASTRIDE, &maps.a, bar, c * BK, xm0 + h.lo_x, ym0 + h.lo_y, f);
+      };
+      load_halo(0);
+      if (nchunk > 1) load_halo(1);
+      int i = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        for (int gi = 0; gi < h.ngroups; ++gi, ++i) {
+          const int stage = i % NST;
+          if (i >= NST) mbar_wait(smem_u32(b_empty + stage), ((i / NST) - 1) & 1);
+          const uint32_t bar = smem_u32(b_full + stage);
+          const HaloGroup g = h.g[gi];
+          mbar_expect_tx(bar, (uint32_t)((h.dbg & 4) ? S::B_TILE : g.ncls * S::B_TILE));
+          for (int j = 0; j < ((h.dbg & 4) ? 1 : g.ncls); ++j)
+            tma_tile_2d(smem_base + stage * S::B_BYTES + j * S::B_TILE, &maps.b, bar, g.wt[j] * Ci + c * BK, 0);
+        }
+        if (c + 2 < nchunk) load_halo(c + 2);      // its buffer is released by the MMAs of chunk c
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<NCOLS>(tmem_base);
+  }
+}
+
+struct HaloKey {
+  const void* in;
+  const void* wt;
+  int n, H, W, C, Co, wrow;
+  bool operator==(const HaloKey& o) const {
+    return in == o.in && wt == o.wt && n == o.n && H == o.H && W == o.W && C == o.C && Co == o.Co && wrow == o.wrow;
+  }
+};
+std::vector<std::pair<HaloKey, HaloMaps>> g_halo_cache;
+
+bool encode_tiled_4d(CUtensorMap* map, const float* p, int N, int H, int W, int C, int bc, int bw, int bh) {
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p, gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int NB, int NST>
+int launch_halo(const HaloMaps& maps, const HaloArgs& h, int tiles, cudaStream_t st) {
+  using S = HaloSmem<NB, NST>;
+  auto kern = dgrad_halo_kernel<NB, NST>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  kern<<<dim3(tiles, h.a.n), HALO_THREADS, S::TOTAL, st>>>(maps, h);
+  BN_LAUNCHED();
+  return 0;
+}
+
+// returns 1 when the op does not have the stride-2 four-class shape this kernel covers
+int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("BN_HALO"); return e && e[0] == '0'; }();
+  if (off || nclasses != 4 || a.gs != 1 || a.os != 2 || a.ksplit > 1) return 1;
+  if (a.Co != 32 && a.Co != 64) return 1;
+  if (a.n > 65535 || !tma_available()) return 1;
+  int lo_y = 127, lo_x = 127, hi_y = -128, hi_x = -128, Hm = 0, Wm = 0, ntaps = 0;
+  for (int c = 0; c < 4; ++c) {
+    const TapClass& k = hc[c];
+    if (k.ntaps < 1) return 1;
+    ntaps += k.ntaps;
+    Hm = k.Hm > Hm ? k.Hm : Hm;
+    Wm = k.Wm > Wm ? k.Wm : Wm;
+    for (int t = 0; t < k.ntaps; ++t) {
+      lo_y = k.dy[t] < lo_y ? k.dy[t] : lo_y; hi_y = k.dy[t] > hi_y ? k.dy[t] : hi_y;
+      lo_x = k.dx[t] < lo_x ? k.dx[t] : lo_x; hi_x = k.dx[t] > hi_x ? k.dx[t] : hi_x;
+    }
+  }
+  if (hi_y - lo_y > HALO_H - 16 || hi_x - lo_x > HALO_W - 8) return 1;
+  // small images would leave most of the 16 x 8 block empty: the im2col kernel packs frames instead
+  if (Hm < 16 || Wm < 8) return 1;
+
+  HaloArgs h;
+  memset(&h, 0, sizeof(h));
+  h.a = a; h.lo_y = lo_y; h.lo_x = lo_x; h.tiles_x = bn_cdiv(Wm, 8);
+  for (int c = 0; c < 4; ++c) { h.Hm[c] = hc[c].Hm; h.Wm[c] = hc[c].Wm; h.oy0[c] = hc[c].oy0; h.ox0[c] = hc[c].ox0; }
+  // windows: tap offsets -> the set of classes that use them (at most one tap per class and window)
+  const int nwy = hi_y - lo_y + 1, nwx = hi_x - lo_x + 1;
+  int wmask[9] = {0}, wtap[9][4];
+  for (int c = 0; c < 4; ++c)
+    for (int t = 0; t < hc[c].ntaps; ++t) {
+      const int w = (hc[c].dy[t] - lo_y) * nwx + (hc[c].dx[t] - lo_x);
+      if (wmask[w] & (1 << c)) return 1;
+      wmask[w] |= 1 << c;
+      wtap[w][c] = hc[c].wt[t];
+    }
+  // TMEM order of the classes: a permutation that makes every window's class set contiguous, and
+  // puts a window that covers all four classes first (its MMA initialises every accumulator)
+  int perm[4] = {0, 1, 2, 3}, best[4] = {-1, -1, -1, -1};
+  const int perms[24][4] = {{0,1,2,3},{0,1,3,2},{0,2,1,3},{0,2,3,1},{0,3,1,2},{0,3,2,1},{1,0,2,3},{1,0,3,2},
+                            {1,2,0,3},{1,2,3,0},{1,3,0,2},{1,3,2,0},{2,0,1,3},{2,0,3,1},{2,1,0,3},{2,1,3,0},
+                            {2,3,0,1},{2,3,1,0},{3,0,1,2},{3,0,2,1},{3,1,0,2},{3,1,2,0},{3,2,0,1},{3,2,1,0}};
+  (void)perm;
+  int full = -1;
+  for (int w = 0; w < nwy * nwx; ++w)
+    if (wmask[w] == 15) { full = w; break; }
+  if (full < 0) return 1;
+  for (int pi = 0; pi < 24 && best[0] < 0; ++pi) {
+    bool ok = true;
+    for (int w = 0; w < nwy * nwx && ok; ++w) {
+      if (!wmask[w]) continue;
+      int lo = 4, hi = -1, cnt = 0;
+      for (int c = 0; c < 4; ++c)
+        if (wmask[w] & (1 << c)) { lo = perms[pi][c] < lo ? perms[pi][c] : lo; hi = perms[pi][c] > hi ? perms[pi][c] : hi; ++cnt; }
+      ok = hi - lo + 1 == cnt;
+    }
+    if (ok) for (int c = 0; c < 4; ++c) best[c] = perms[pi][c];
+  }
+  if (best[0] < 0) return 1;
+  for (int c = 0; c < 4; ++c) h.pos[c] = best[c];
+  int ng = 0;
+  auto add_group = [&](int w) {
+    HaloGroup g;
+    memset(&g, 0, sizeof(g));
+    g.row_off = (unsigned short)((w / nwx) * HALO_W + (w % nwx));
+    int lo = 4, cnt = 0;
+    for (int c = 0; c < 4; ++c)
+      if (wmask[w] & (1 << c)) { lo = best[c] < lo ? best[c] : lo; ++cnt; }
+    g.col0 = (unsigned char)lo; g.ncls = (unsigned char)cnt;
+    for (int c = 0; c < 4; ++c)
+      if (wmask[w] & (1 << c)) g.wt[best[c] - lo] = (unsigned char)wtap[w][c];
+    h.g[ng++] = g;
+  };
+  add_group(full);
+  for (int w = 0; w < nwy * nwx; ++w)
+    if (wmask[w] && w != full) add_group(w);
+  h.ngroups = ng;
+  (void)ntaps;
+  { const char* e = getenv("BN_HALO_DBG"); h.dbg = e ? atoi(e) : 0; }
+
+  const HaloMaps* hm = nullptr;
+  {
+    HaloKey key{a.in, a.wt, a.n, a.Hi, a.Wi, a.Ci, a.Co, a.wrow};
+    std::lock_guard<std::mutex> lk(g_tma_mutex);
+    for (auto& kv : g_halo_cache)
+      if (kv.first == key) hm = &kv.second;
+    if (!hm) {
+      HaloMaps m;
+      memset(&m, 0, sizeof(m));
+      if (!encode_tiled_4d(&m.a, a.in, a.n, a.Hi, a.Wi, a.Ci, BK, HALO_W, HALO_H)) return 1;
+      if (!encode_tiled_2d(&m.b, a.wt, a.Co, a.wrow, BK, a.Co, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (g_halo_cache.size() >= 256) g_halo_cache.clear();
+      g_halo_cache.emplace_back(key, m);
+      hm = &g_halo_cache.back().second;
+    }
+  }
+  const int tiles = h.tiles_x * bn_cdiv(Hm, 16);
+  HaloMaps local = *hm;
+  if (a.Co == 32) return launch_halo<32, 3>(local, h, tiles, st);
+  return launch_halo<64, 2>(local, h, tiles, st);
+}
+
 }  // namespace
 
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
@@ -1045,7 +1375,8 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   a.in = in.p; a.Hi = in.H; a.Wi = in.W; a.Ci = in.C; a.wt = wt; a.wrow = wrow; a.bias = bias; a.out = out;
   a.Ho = Ho; a.Wo = Wo; a.Co = Co; a.dact = dact; a.classes = d_classes; a.gs = gs; a.os = os;
   a.n = n; a.act = act;
-  int r;
+  int r = try_dgrad_halo(a, h_classes, nclasses, st);
+  if (r <= 0) return r;
   const TmaSet* tm = get_tma_set(in, wt, wrow, Co, bn, d_classes, h_classes, nclasses, gs, n);
   if (tm) {
     TmaSet local = *tm;      // copied into the kernel parameter space (__grid_constant__)
@@ -1123,7 +1454,11 @@ int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g
   const long long M = (long long)n * g.Hs * g.Ws;
   if (M < 256) return 1;
   long long tiles = (long long)bn_cdiv(Ktot, BM) * (Cs / bn);
-  long long splits = (2 * 148 + tiles - 1) / tiles;
+  // one full wave and no more: the CTAs are long-running (each walks its whole pixel slice), so a
+  // grid that exceeds the resident slots by a handful of CTAs doubles the kernel time
+  const long long slots = 148LL * (bn == 256 ? 1 : 2);      // 192 KB of stages per CTA at BN = 256, 96 KB otherwise
+  long long splits = slots / tiles;
+  if (splits < 1) splits = 1;
   long long maxs = (M + 127) / 128;
   if (splits > maxs) splits = maxs;
   long long cap = (long long)(partial_floats / ((size_t)Ktot * Cs));
@@ -1158,3 +1493,4 @@ int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g
   if (r) return r;
   return bn_launch_wgrad_reduce(partial, (int)splits, Ktot, Cs, g.Cb, g.k * g.k, g.d_fprop, grad, st);
 }
+

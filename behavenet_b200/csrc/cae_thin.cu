@@ -85,16 +85,28 @@ __global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const 
   const float b = bias ? __ldg(bias + c) : 0.f;
   long long t = blockIdx.x;
   int f, y0, x0;
+  // activation-derivative mask of half a row (16 pixels of this lane's channel), fetched half a tile
+  // ahead of its use: dq[0] / dq[1] alternate between "being loaded" and "being consumed"
+  float dq[2][TW / 2];
+  auto load_mask = [&](float (&d)[TW / 2], int ff, int yy0, int xx0, int half) {
+    const int oy = yy0 + warp;
+    const long long rb = (((long long)ff * g.Hs + oy) * g.Ws + xx0) * g.Cs + c;
+#pragma unroll
+    for (int e = 0; e < TW / 2; ++e)
+      d[e] = (oy < g.Hs && xx0 + half * (TW / 2) + e < g.Ws) ? __ldg(dact + rb + (long long)(half * (TW / 2) + e) * g.Cs)
+                                                            : 1.f;
+  };
   if (t < it.total) {
     it.decode(t, f, y0, x0);
     issue_patch<CB>(patch[0], g, f, y0, x0, tid);
+    if (dact) load_mask(dq[0], f, y0, x0, 0);
   }
   cp_commit();
   for (int buf = 0; t < it.total; t += gridDim.x, buf ^= 1) {
     it.decode(t, f, y0, x0);
     const long long tn = t + gridDim.x;
+    int fn = 0, yn = 0, xn = 0;
     if (tn < it.total) {
-      int fn, yn, xn;
       it.decode(tn, fn, yn, xn);
       issue_patch<CB>(patch[buf ^ 1], g, fn, yn, xn, tid);
     }
@@ -102,16 +114,14 @@ __global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const 
     cp_wait<1>();
     __syncthreads();
     const int oy = y0 + warp;
-    if (oy < g.Hs) {
-      const long long rowbase = (((long long)f * g.Hs + oy) * g.Ws + x0) * g.Cs + c;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float d[TW / 2];
-        if (dact) {
+    const long long rowbase = (((long long)f * g.Hs + oy) * g.Ws + x0) * g.Cs + c;
 #pragma unroll
-          for (int e = 0; e < TW / 2; ++e)
-            d[e] = x0 + half * (TW / 2) + e < g.Ws ? __ldg(dact + rowbase + (long long)(half * (TW / 2) + e) * g.Cs) : 1.f;
-        }
+    for (int half = 0; half < 2; ++half) {
+      if (dact) {
+        if (half == 0) load_mask(dq[1], f, y0, x0, 1);
+        else if (tn < it.total) load_mask(dq[0], fn, yn, xn, 0);
+      }
+      if (oy < g.Hs) {
 #pragma unroll
         for (int jj = 0; jj < TW / 4; ++jj) {
           const int j = half * (TW / 4) + jj;
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const 
             if (x0 + xo >= g.Ws) continue;
             float x = r[e];
             if (act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-            if (dact) x *= d[2 * jj + e] > 0.f ? 1.f : BN_LEAK;
+            if (dact) x *= dq[half][2 * jj + e] > 0.f ? 1.f : BN_LEAK;
             out[rowbase + (long long)xo * g.Cs] = x;
           }
         }
@@ -262,7 +272,9 @@ __global__ void __launch_bounds__(256) thin_dgrad5_kernel(const Dg5Args a, int t
   // taps with ky = (py + pt) mod 2 (+2, +4): offsets span [(pt - PTO) / 2 - 1 - .., ..]; with
   // dy(py, ky) = (py + PTO - ky) / 2 in {-2..1} relative to the shifted origin ys + (pt - PTO) / 2
   const int shy = (a.pt - PTO) >> 1, shx = (a.pl - PLO) >> 1;
-  const int iy0 = sy0 + shy - 1, ix0 = sx0 + shx - 1;  // patch origin (neighbour offsets -1..+1 -> rows 0..2)
+  // neighbour offsets: odd crop -> dy in {-1, 0, 1}, even crop -> dy in {-2, -1, 0}; patch row = dy + OY
+  constexpr int OY = PTO ? 1 : 2, OX = PLO ? 1 : 2;
+  const int iy0 = sy0 + shy - OY, ix0 = sx0 + shx - OX;
   for (int i = tid; i < DP * DP * (Cs / 4); i += 256) {
     const int p = i / (Cs / 4), q = i - p * (Cs / 4);
     const int pr = p / DP, pc = p - pr * DP;
@@ -298,12 +310,12 @@ __global__ void __launch_bounds__(256) thin_dgrad5_kernel(const Dg5Args a, int t
         for (int py = 0; py < 2; ++py) {
 #pragma unroll
           for (int ky = (py + PTO) & 1; ky < 5; ky += 2) {
-            if ((py + PTO - ky) / 2 + 1 != ny || (py + PTO - ky) % 2 != 0) continue;   // compile-time after unrolling
+            if ((py + PTO - ky) / 2 + OY != ny) continue;         // compile-time after unrolling
 #pragma unroll
             for (int px = 0; px < 2; ++px) {
 #pragma unroll
               for (int kx = (px + PLO) & 1; kx < 5; kx += 2) {
-                if ((px + PLO - kx) / 2 + 1 != nx || (px + PLO - kx) % 2 != 0) continue;
+                if ((px + PLO - kx) / 2 + OX != nx) continue;
                 const float* wp = wsm + (ky * 5 + kx) * CB * Cs + q;
 #pragma unroll
                 for (int c = 0; c < CB; ++c) {
@@ -363,35 +375,50 @@ bool fast_geom(const ConvGeom& g) { return g.k == 5 && g.s == 2 && g.Cb >= 1 && 
 
 }  // namespace
 
+template <int CB>
+static int launch_thin_fprop(const ThinGeo& t, const float* wf, const float* bias, float* out, const float* dact,
+                             int act, const TileIter& it, int cgroups, cudaStream_t st) {
+  const size_t smem = (size_t)2 * CB * PROWS * PCOLS * sizeof(float);
+  auto kern = thin_fprop_kernel<CB>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  long long blocks = it.total < 2 * 148 ? it.total : 2 * 148;      // two resident blocks per SM (128 registers x 256 threads)
+  kern<<<dim3((unsigned)blocks, cgroups), 256, smem, st>>>(t, wf, bias, out, dact, act, it);
+  BN_LAUNCHED();
+  return 0;
+}
+
 int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* bias, float* out,
                          const float* dact, int act, int n, cudaStream_t st) {
   if (!fast_geom(g) || n <= 0) return 1;
   ThinGeo t;
   t.big = big; t.Hs = g.Hs; t.Ws = g.Ws; t.Cs = g.Cs; t.pt = g.pt; t.pl = g.pl; t.n = n;
-  const int tiles_x = bn_cdiv(g.Ws, TW), tiles_y = bn_cdiv(g.Hs, TH);
-  dim3 grid(tiles_x * tiles_y, n, g.Cs / 32);
-  if (n > 65535) return 1;
+  TileIter it;
+  it.tiles_x = bn_cdiv(g.Ws, TW);
+  it.tiles_per_frame = it.tiles_x * bn_cdiv(g.Hs, TH);
+  it.total = (long long)it.tiles_per_frame * n;
   switch (g.Cb) {
-    case 1: thin_fprop_kernel<1><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
-    case 2: thin_fprop_kernel<2><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
-    case 3: thin_fprop_kernel<3><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
-    default: thin_fprop_kernel<4><<<grid, 256, 0, st>>>(t, wf, bias, out, dact, act, tiles_x); break;
+    case 1: return launch_thin_fprop<1>(t, wf, bias, out, dact, act, it, g.Cs / 32, st);
+    case 2: return launch_thin_fprop<2>(t, wf, bias, out, dact, act, it, g.Cs / 32, st);
+    case 3: return launch_thin_fprop<3>(t, wf, bias, out, dact, act, it, g.Cs / 32, st);
+    default: return launch_thin_fprop<4>(t, wf, bias, out, dact, act, it, g.Cs / 32, st);
   }
-  BN_LAUNCHED();
-  return 0;
 }
 
 template <int CB>
-static int launch_thin_wgrad(const ThinGeo& t, const float* small, float* partial, int blocks, int tiles_x,
-                             int tiles_per_frame, long long total, int cgroups, cudaStream_t st) {
-  size_t smem = (size_t)8 * 25 * CB * 32 * sizeof(float);
+static int launch_thin_wgrad(const ThinGeo& t, const float* small, float* partial, int blocks, const TileIter& it,
+                             int cgroups, cudaStream_t st) {
+  const size_t smem = ((size_t)2 * CB * PROWS * PCOLS + (size_t)8 * 25 * CB * 32) * sizeof(float);
   auto kern = thin_wgrad_kernel<CB>;
   static bool configured = false;
   if (!configured) {
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<dim3(blocks, cgroups), 256, smem, st>>>(t, small, partial, tiles_x, tiles_per_frame, total);
+  kern<<<dim3(blocks, cgroups), 256, smem, st>>>(t, small, partial, it);
   BN_LAUNCHED();
   return 0;
 }
@@ -401,31 +428,32 @@ int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom&
   if (!fast_geom(g) || n <= 0 || grad == nullptr) return grad == nullptr ? 0 : 1;
   ThinGeo t;
   t.big = big; t.Hs = g.Hs; t.Ws = g.Ws; t.Cs = g.Cs; t.pt = g.pt; t.pl = g.pl; t.n = n;
-  const int tiles_x = bn_cdiv(g.Ws, TW), tiles_y = bn_cdiv(g.Hs, TH);
-  const int tpf = tiles_x * tiles_y;
-  const long long total = (long long)tpf * n;
+  TileIter it;
+  it.tiles_x = bn_cdiv(g.Ws, TW);
+  it.tiles_per_frame = it.tiles_x * bn_cdiv(g.Hs, TH);
+  it.total = (long long)it.tiles_per_frame * n;
   const int Ktot = 25 * g.Cb;
-  long long blocks = total < 2 * 148 ? total : 2 * 148;
+  long long blocks = it.total < 2 * 148 ? it.total : 2 * 148;
   long long cap = (long long)(partial_floats / ((size_t)Ktot * g.Cs));
   if (blocks > cap) blocks = cap;
   if (blocks < 1) return 1;
   int r;
   switch (g.Cb) {
-    case 1: r = launch_thin_wgrad<1>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
-    case 2: r = launch_thin_wgrad<2>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
-    case 3: r = launch_thin_wgrad<3>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
-    default: r = launch_thin_wgrad<4>(t, small, partial, (int)blocks, tiles_x, tpf, total, g.Cs / 32, st); break;
+    case 1: r = launch_thin_wgrad<1>(t, small, partial, (int)blocks, it, g.Cs / 32, st); break;
+    case 2: r = launch_thin_wgrad<2>(t, small, partial, (int)blocks, it, g.Cs / 32, st); break;
+    case 3: r = launch_thin_wgrad<3>(t, small, partial, (int)blocks, it, g.Cs / 32, st); break;
+    default: r = launch_thin_wgrad<4>(t, small, partial, (int)blocks, it, g.Cs / 32, st); break;
   }
   if (r) return r;
   return bn_launch_wgrad_reduce(partial, (int)blocks, Ktot, g.Cs, g.Cb, 25, g.d_fprop, grad, st);
 }
 
-template <int CB>
+template <int CB, int PTO, int PLO>
 static int launch_dgrad5(const Dg5Args& a, dim3 grid, int tiles_x, size_t smem, cudaStream_t st) {
-  auto kern = thin_dgrad5_kernel<CB>;
+  auto kern = thin_dgrad5_kernel<CB, PTO, PLO>;
   static bool configured = false;
   if (!configured) {
-    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
   kern<<<grid, 256, smem, st>>>(a, tiles_x);
@@ -433,24 +461,38 @@ static int launch_dgrad5(const Dg5Args& a, dim3 grid, int tiles_x, size_t smem, 
   return 0;
 }
 
+template <int CB>
+static int launch_dgrad5_p(const Dg5Args& a, dim3 grid, int tiles_x, size_t smem, cudaStream_t st) {
+  switch ((a.pt & 1) * 2 + (a.pl & 1)) {
+    case 0: return launch_dgrad5<CB, 0, 0>(a, grid, tiles_x, smem, st);
+    case 1: return launch_dgrad5<CB, 0, 1>(a, grid, tiles_x, smem, st);
+    case 2: return launch_dgrad5<CB, 1, 0>(a, grid, tiles_x, smem, st);
+    default: return launch_dgrad5<CB, 1, 1>(a, grid, tiles_x, smem, st);
+  }
+}
+
 int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd, const float* bias, int n,
                           float* xhat_ws, float* xhat_user, const float* target, const float* mask,
                           int chunk_size, int frame_offset, int n_total, float grad_coef, double* sse,
                           float* dpre, cudaStream_t st) {
   if (!(g.k == 5 && g.s == 2 && g.Cb >= 1 && g.Cb <= 4 && g.Cs % 4 == 0) || n <= 0 || n > 65535) return 1;
+  if (g.pt < 0 || g.pl < 0 || g.pt > 4 || g.pl > 4) return 1;
+  // every output pixel must be covered by a small pixel of the tile grid
+  if (g.Hb > 2 * g.Hs + 2 || g.Wb > 2 * g.Ws + 2) return 1;
   size_t smem = ((size_t)DP * DP * (g.Cs + 4) + (size_t)25 * g.Cb * g.Cs) * sizeof(float);
-  if (smem > 96 * 1024) return 1;
+  if (smem > 100 * 1024) return 1;
   Dg5Args a;
   a.small = small; a.Hs = g.Hs; a.Ws = g.Ws; a.Cs = g.Cs; a.Hb = g.Hb; a.Wb = g.Wb; a.pt = g.pt; a.pl = g.pl;
   a.n = n; a.wd = wd; a.bias = bias; a.xhat_ws = xhat_ws; a.xhat_user = xhat_user; a.target = target;
   a.mask = mask; a.n_total = n_total > 0 ? n_total : n; a.frame_offset = frame_offset;
   a.chunk_size = chunk_size > 0 ? chunk_size : a.n_total; a.coef = grad_coef; a.sse = sse; a.dpre = dpre;
-  const int tiles_x = bn_cdiv(g.Wb, DT), tiles_y = bn_cdiv(g.Hb, DT);
+  // tiles of DT x DT small pixels = 2*DT x 2*DT output pixels
+  const int tiles_x = bn_cdiv(bn_cdiv(g.Wb, 2), DT), tiles_y = bn_cdiv(bn_cdiv(g.Hb, 2), DT);
   dim3 grid(tiles_x * tiles_y, n);
   switch (g.Cb) {
-    case 1: return launch_dgrad5<1>(a, grid, tiles_x, smem, st);
-    case 2: return launch_dgrad5<2>(a, grid, tiles_x, smem, st);
-    case 3: return launch_dgrad5<3>(a, grid, tiles_x, smem, st);
-    default: return launch_dgrad5<4>(a, grid, tiles_x, smem, st);
+    case 1: return launch_dgrad5_p<1>(a, grid, tiles_x, smem, st);
+    case 2: return launch_dgrad5_p<2>(a, grid, tiles_x, smem, st);
+    case 3: return launch_dgrad5_p<3>(a, grid, tiles_x, smem, st);
+    default: return launch_dgrad5_p<4>(a, grid, tiles_x, smem, st);
   }
 }

@@ -200,6 +200,11 @@ class AE(BaseModel):
         return y, z
 
     # -- fused training step -----------------------------------------------------------------
+    def invalidate_packed(self):
+        """Force the next call to re-pack the GEMM-ordered weight copies (what an optimizer step does
+        implicitly by bumping the parameter versions)."""
+        self._rt.packed_key = None
+
     def _kernel_params(self):
         return self.encoding.kernel_params() + self.decoding.kernel_params()
 

@@ -12,6 +12,7 @@ steps per GPU, one E-step per step).
 """
 
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -41,20 +42,23 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler runs from
+    before the warm-up, every row carries nvidia-smi's own timestamp, and only rows inside
+    [mark_start, mark_stop] are summarised."""
 
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -65,30 +69,50 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark_start(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_stop(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        parsed = []
         for r in self.rows:
             f = [v.strip() for v in r.split(',')]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f')
+                parsed.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+        inside = [q for q in parsed if self.t0 is not None and self.t0 <= q[0] <= self.t1]
+        # nvidia-smi's sampling period is coarser than a short timed region: fall back to the rows
+        # closest to it (the GPU is under the same load during warm-up and the follow-up loops)
+        where = 'timed region'
+        if len(inside) < 2:
+            inside = [q for q in parsed if self.t0 is not None and
+                      abs((q[0] - self.t0).total_seconds()) < 1.0 + (self.t1 - self.t0).total_seconds()]
+            where = 'timed region +-1 s (region shorter than the sampling period)'
+        sm = [q[1] for q in inside]
+        mx = [q[2] for q in inside]
+        reasons = set()
+        for q in inside:
+            for n, v in zip(names, q[3]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': float(np.max(mx)) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'window': where, 'reasons': sorted(reasons)}
 
 
 def make_cae(device):
@@ -221,29 +245,35 @@ def run_ours(args):
 
     def step():
         opt.zero_grad()
+        # a training step follows an optimizer step: the GEMM-ordered weight copies are stale and are
+        # re-packed inside the timed call (the optimizer itself is timed separately)
+        model.invalidate_packed()
         model.loss(data, accumulate_grad=True)
 
     def step_e2e():
         opt.zero_grad()
+        model.invalidate_packed()
         xd = x_host.to(device, non_blocking=True)
         model.loss({'images': xd[None]}, accumulate_grad=True)      # ends with the loss readback
 
     sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     barrier()
     launches0 = _lib.launch_count()
-    if rank == 0:
-        sampler.start()
     # timed region: exactly K steps, barrier + synchronize on both sides
     torch.cuda.synchronize()
+    sampler.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_stop()
     barrier()
     total_ms = dist_max(e0.elapsed_time(e1), device)
     launches = _lib.launch_count() - launches0
@@ -428,7 +458,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     args = ap.parse_args()

@@ -506,9 +506,12 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
   const unsigned gmask = KP == 32 ? 0xffffffffu : (((1u << KP) - 1u) << (grp * KP));
 
   __shared__ __align__(16) float xch[4][2][32];
+  __shared__ __align__(16) float xg[4][2][32];
   __shared__ float xz[2][GPW][KP][KP + 1];
   const int gbase = grp * KP;
   int par = 0;
+  // all-gather of one float per lane inside the KP-lane group (double-buffered by parity: a lane is
+  // at most one step ahead of its group)
   auto exchange = [&](float mine, float2 (&v)[H2]) {
     xch[wib][par][lane] = mine;
     __syncwarp(gmask);
@@ -524,10 +527,29 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     }
     par ^= 1;
   };
-  auto gsum = [&](float v) {
+  // same, plus the group SUM of a second float: the posterior normaliser G travels with the message
+  // instead of through a 4-deep shuffle butterfly, so it never lengthens the in-order critical path
+  auto exchange2 = [&](float mine, float gval, float2 (&v)[H2], float& G) {
+    xch[wib][par][lane] = mine;
+    xg[wib][par][lane] = gval;
+    __syncwarp(gmask);
+    float2 acc = make_float2(0.f, 0.f);
+    if (KP >= 4) {
 #pragma unroll
-    for (int o = KP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o, KP);
-    return v;
+      for (int j = 0; j < KP; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&xch[wib][par][gbase + j]);
+        v[j / 2] = make_float2(q.x, q.y);
+        v[j / 2 + 1] = make_float2(q.z, q.w);
+        const float4 e = *reinterpret_cast<const float4*>(&xg[wib][par][gbase + j]);
+        acc = fadd2(acc, make_float2(e.x, e.y));
+        acc = fadd2(acc, make_float2(e.z, e.w));
+      }
+    } else {
+      v[0] = *reinterpret_cast<const float2*>(&xch[wib][par][gbase]);
+      acc = *reinterpret_cast<const float2*>(&xg[wib][par][gbase]);
+    }
+    G = acc.x + acc.y;
+    par ^= 1;
   };
   auto pair_barrier = [&]() {
     __syncwarp();
@@ -555,14 +577,21 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     float2 Pcol[H2];
 #pragma unroll
     for (int j = 0; j < H2; ++j) Pcol[j] = make_float2(Pg[(2 * j) * KP + k], Pg[(2 * j + 1) * KP + k]);
+    // The message on the serial chain is a_t = (P^T a_{t-1}) b_t / S_{t-1} with S_{t-1} = sum_j a_{t-1}(j)
+    // taken from the SAME exchange (a local sum: every lane holds the whole vector), so sum_k a_t(k)
+    // = c_t stays in [min P, 1].  (Scaling by the older S_{t-2} would take the reciprocal off the
+    // chain but obeys L_t = log c_t + L_{t-1} - L_{t-2}, a marginally stable recurrence whose
+    // random-walk growth overflows fp32 within ~1000 steps.)  gamma and xi are normalised explicitly
+    // by G, and log Z = sum_t (log S_t + m_t).
     double logZ = 0.0;
     float acur = 0.f, bprev = 0.f;
+    float rcur = 1.f;                 // scale that produced acur
     if (T > 0) {
       bprev = kvalid ? __ldg(Bp) : 0.f;
       acur = pi0g[k] * bprev;
       logZ = (double)__ldg(mp);
     }
-    // first half: t = 1 .. h; finalises alpha_hat_{t-1}, produces a_t
+    // first half: t = 1 .. h; stores the (unnormalised) a_{t-1}, produces a_t
     auto load1 = [&](int t) {
       ScanIn in;
       in.b = kvalid ? __ldg(Bp + t * K) : 0.f;
@@ -573,18 +602,19 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     auto step1 = [&](int t, const ScanIn& in) {
       float2 v[H2];
       exchange(acur, v);
-      float dot, S;                                  // S = c_{t-1}
+      float dot, S;                                  // S = S_{t-1}
       dot_sum(v, Pcol, dot, S);
+      if (POST && kvalid) Ep[(t - 1) * K] = acur;
       const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
       logZ += (double)(__logf(S) + in.m);            // fp64 accumulation, off the dependent chain
-      if (POST && kvalid) Ep[(t - 1) * K] = acur * inv;
       acur = dot * in.b * inv;
+      rcur = inv;
       bprev = in.b;
     };
     const int n1 = POST ? h : (T > 0 ? T - 1 : 0);
     run_range<PF, ScanIn>(1, n1, 1, load1, step1);
     if (!POST) {
-      // finalise the last step: log c_{T-1}
+      // finalise the last step: log S_{T-1}
       if (T > 0) {
         float2 v[H2];
         exchange(acur, v);
@@ -600,7 +630,6 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     float2 X[H2], vprev[H2];
 #pragma unroll
     for (int j = 0; j < H2; ++j) { X[j] = make_float2(0.f, 0.f); vprev[j] = make_float2(0.f, 0.f); }
-    float invprev = 0.f;
     auto load2 = [&](int t) {
       ScanIn in;
       const bool cur = t < T;
@@ -611,24 +640,24 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     };
     auto step2 = [&](int t, const ScanIn& in) {
       float2 v[H2];
-      exchange(acur, v);
+      const float ab = acur * in.x;
+      float G;                                       // sum_k a_{t-1}(k) beta_{t-1}(k)
+      exchange2(acur, ab, v, G);
       float dot, S;
       dot_sum(v, Pcol, dot, S);
-      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
-      logZ += (double)(__logf(S) + in.m);
-      const float ab = acur * inv * in.x;
-      const float G = gsum(ab);
       const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
       if (kvalid) Ep[(t - 1) * K] = ab * rG;
-      const float w = bprev * in.x * inv * rG * invprev;          // 0 on the first step (invprev = 0)
+      const float w = bprev * in.x * rcur * rG;      // xi_{t-2}: vprev is all-zero on the first step
       const float2 w2 = make_float2(w, w);
 #pragma unroll
       for (int j = 0; j < H2; ++j) {
         X[j] = ffma2(vprev[j], w2, X[j]);
         vprev[j] = v[j];
       }
-      invprev = inv;
+      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      logZ += (double)(__logf(S) + in.m);            // in.m = 0 on the last step (t == T)
       acur = dot * in.b * inv;
+      rcur = inv;
       bprev = in.b;
     };
     run_range<PF2, ScanIn>(h + 1, T - h, 1, load2, step2);
@@ -663,39 +692,54 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
       exchange(in.b * beta, vk);
       float u, Dn;
       dot_sum(vk, Prow, u, Dn);
-      const float rD = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
-      beta = u * rD;
+      beta = u * (Dn > 0.f ? __fdividef(1.f, Dn) : 0.f);
       if (kvalid) Bt[t * K] = beta;
     };
     run_range<PF, ScanIn>(T - 2, max(T - 1 - h, 0), -1, load1, step1);      // t = T-2 .. h
     pair_barrier();
-    float2 X[H2];
+    // second half: t = h-1 .. 0.  gamma_t / xi_t need G_t = sum_j a_t(j) beta_t(j), which exists only
+    // at the END of step t: it rides along with the next step's message, so step t is finalised
+    // one iteration later (and t = 0 by a trailing exchange).
+    float2 X[H2], vkp[H2];
 #pragma unroll
-    for (int j = 0; j < H2; ++j) X[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < H2; ++j) { X[j] = make_float2(0.f, 0.f); vkp[j] = make_float2(0.f, 0.f); }
+    float al_p = 0.f, ab_p = 0.f, rho_p = 0.f;
     auto load2 = [&](int t) {
       ScanIn in;
       in.b = kvalid ? __ldg(Bp + (t + 1) * K) : 0.f;
       in.m = 0.f;
-      in.x = kvalid ? Ep[t * K] : 0.f;                            // alpha_hat_t(j)
+      in.x = kvalid ? Ep[t * K] : 0.f;                            // a_t(j) stored by the forward group
       return in;
+    };
+    auto finalise = [&](int tp, float G) {
+      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
+      if (kvalid) Ep[tp * K] = ab_p * rG;
+      const float w = al_p * rho_p * rG;
+      const float2 w2 = make_float2(w, w);
+#pragma unroll
+      for (int j = 0; j < H2; ++j) X[j] = ffma2(vkp[j], w2, X[j]);
     };
     auto step2 = [&](int t, const ScanIn& in) {
       float2 vk[H2];
-      exchange(in.b * beta, vk);
+      float G;
+      exchange2(in.b * beta, ab_p, vk, G);
+      if (t + 1 < h) finalise(t + 1, G);
       float u, Dn;
       dot_sum(vk, Prow, u, Dn);
-      const float rD = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
-      beta = u * rD;
-      const float ab = in.x * beta;
-      const float G = gsum(ab);
-      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
-      if (kvalid) Ep[t * K] = ab * rG;
-      const float w = in.x * rD * rG;
-      const float2 w2 = make_float2(w, w);
+      rho_p = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
+      beta = u * rho_p;
+      al_p = in.x;
+      ab_p = in.x * beta;
 #pragma unroll
-      for (int j = 0; j < H2; ++j) X[j] = ffma2(vk[j], w2, X[j]);
+      for (int j = 0; j < H2; ++j) vkp[j] = vk[j];
     };
     run_range<PF2, ScanIn>(h - 1, h, -1, load2, step2);                       // t = h-1 .. 0
+    if (h > 0) {
+      float2 vk[H2];
+      float G;
+      exchange2(0.f, ab_p, vk, G);
+      finalise(0, G);
+    }
 #pragma unroll
     for (int j = 0; j < H2; ++j) {
       xz[set][grp][k][2 * j] = X[j].x;

@@ -1,0 +1,91 @@
+"""Encode-only path: latents for the ARHMM (reference ``behavenet/fitting/eval.py:6-118`` export_latents).
+
+``encode_trials`` is the B200 form of the reference loop ``model.encoding(data['images'][0])`` per
+trial (eval.py:74-98): the encoder is frame-independent, so whole groups of trials go through ONE
+launch sequence, uint8 video is scaled by 1/255 on the device (data_generator.py:258-263 does it on
+the host), and the latents stay in HBM so that ``HMM.stage_device`` can feed the E-step without a
+host round trip (config C5).  ``export_latents`` keeps the reference's call signature and pickle
+format for callers that want files.
+"""
+
+import numpy as np
+
+
+def _latents_of(model, frames):
+    out = model.encoding(frames, dataset=None)
+    if model.hparams.get('model_class') == 'ps-vae':
+        import torch
+        return torch.cat([out[0], out[1]], dim=1)          # eval.py:75-76
+    return out[0]
+
+
+def encode_trials(model, trials, frames_per_launch=4096, device=None):
+    """Latent means of a list of trials.
+
+    trials: list of (T_i, C, H, W) arrays / tensors, uint8 (0..255) or float32 (0..1), host or device.
+    Returns (latents, lengths): a (sum T_i, n_latents) CUDA float32 tensor and the list of T_i.
+    """
+    import torch
+    if device is None:
+        device = next(model.parameters()).device
+    lengths = [int(t.shape[0]) for t in trials]
+    total = int(sum(lengths))
+    L = int(model.hparams['n_ae_latents'])
+    lat = torch.empty(total, L, dtype=torch.float32, device=device)
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        o = 0
+        group, gsize = [], 0
+
+        def flush():
+            nonlocal o, group, gsize
+            if not group:
+                return
+            parts = []
+            for t in group:
+                t = t if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t))
+                t = t.to(device, non_blocking=True)
+                parts.append(t.float().div_(255.0) if t.dtype == torch.uint8 else t.float())
+            x = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+            lat[o:o + x.shape[0]] = _latents_of(model, x)
+            o += x.shape[0]
+            group, gsize = [], 0
+
+        for t in trials:
+            if gsize and gsize + t.shape[0] > frames_per_launch:
+                flush()
+            group.append(t)
+            gsize += int(t.shape[0])
+        flush()
+    model.train(was_training)
+    return lat, lengths
+
+
+def export_latents(data_generator, model, filename=None):
+    """Reference-compatible export (eval.py:6-118): one pickle per dataset with
+    ``{'latents': [per-trial arrays, gap trials empty], 'trials': dataset.batch_idxs}``."""
+    import os
+    import pickle
+    import torch
+    model.eval()
+    latents = [[np.array([]) for _ in range(ds.n_trials)] for ds in data_generator.datasets]
+    with torch.no_grad():
+        for dtype in ['train', 'val', 'test']:
+            data_generator.reset_iterators(dtype)
+            for _ in range(data_generator.n_tot_batches[dtype]):
+                data, sess = data_generator.next_batch(dtype)
+                y = data['images'][0]
+                idx = data['batch_idx'].item() if hasattr(data['batch_idx'], 'item') else int(data['batch_idx'])
+                latents[sess][idx] = _latents_of(model, y).cpu().numpy()
+    filenames = []
+    for sess, ds in enumerate(data_generator.datasets):
+        if filename is None:
+            sess_id = '%s_%s_%s_%s_latents.pkl' % (ds.lab, ds.expt, ds.animal, ds.session)
+            fname = os.path.join(model.hparams['expt_dir'], 'version_%i' % model.version, sess_id)
+        else:
+            fname = filename
+        with open(fname, 'wb') as f:
+            pickle.dump({'latents': latents[sess], 'trials': ds.batch_idxs}, f)
+        filenames.append(fname)
+    return filenames

@@ -264,16 +264,24 @@ class AE(BaseModel):
         x = drv._check_input(x, "data['images'][0]", drv.img)
         if m is not None:
             m = drv._check_input(m.to(torch.float32), "data['masks'][0]", drv.img)
-        n_total = x.shape[0]
+        if 'shard' in data:
+            # data-parallel callers that stage only their own frames: data['shard'] = (first frame,
+            # frames in the whole batch); chunk membership still follows the whole batch
+            beg, n_total = int(data['shard'][0]), int(data['shard'][1])
+            end = beg + x.shape[0]
+            local = True
+        else:
+            n_total = x.shape[0]
+            beg, end = self._shard(n_total)
+            local = False
         n_chunks = int(np.ceil(n_total / chunk_size))
-        beg, end = self._shard(n_total)
         n = end - beg
         params = self._kernel_params()
         device = x.device
         sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
         if n > 0:
-            xs = x[beg:end]
-            ms = None if m is None else m[beg:end]
+            xs = x if local else x[beg:end]
+            ms = None if m is None else (m if local else m[beg:end])
             packed = drv.packed(rt, params, device)
             ws = drv.workspace(rt, n, device)
             z, _ = drv.encode(xs, params, packed, ws, False)

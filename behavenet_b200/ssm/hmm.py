@@ -225,6 +225,26 @@ class _Staged:
         self.offsets_host = off
         self.offsets = torch.from_numpy(off).to(device)
 
+    @classmethod
+    def from_device(cls, x, lengths):
+        """Stage trials that already live on the GPU (e.g. encoder latents, config C5): ``x`` is the
+        (sum T_i, D) fp32 concatenation, ``lengths`` the per-trial T_i.  No host round trip."""
+        import torch
+        self = cls.__new__(cls)
+        lens = [int(v) for v in lengths]
+        self.n = len(lens)
+        self.lengths = lens
+        self.total = int(sum(lens))
+        self.max_T = max(lens) if lens else 0
+        if x.dim() != 2 or x.shape[0] != self.total or x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError('expected a CUDA float32 tensor of shape (%d, D)' % self.total)
+        self.x = x.contiguous()
+        off = np.zeros(self.n + 1, np.int64)
+        off[1:] = np.cumsum(lens)
+        self.offsets_host = off
+        self.offsets = torch.from_numpy(off).to(x.device)
+        return self
+
 
 class HMM:
     """ssm.HMM look-alike (see module docstring)."""
@@ -309,6 +329,16 @@ class HMM:
 
     def clear_cache(self):
         self.__dict__.pop('_cache', None)
+
+    def stage_device(self, x, lengths):
+        """Device-resident trials for the E-step (see ``_Staged.from_device``)."""
+        if x.shape[1] != self.D:
+            raise ValueError('data must have shape (T, %d), got %s' % (self.D, tuple(x.shape)))
+        return _Staged.from_device(x, lengths)
+
+    def expected_states_device(self, staged):
+        """E-step over device-resident trials: (Ez (sum T, K), Ezz (n, K, K), logZ (n)) as CUDA tensors."""
+        return self._run_estep(staged, True)
 
     def _blob(self, device):
         import torch

@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 # algorithmic work
 CAE_C2_TRAIN_GFLOP_PER_FRAME = 2.078
 ARHMM_BYTES_PER_TIMESTEP = 113.0
+# dram__bytes_read + write per launch of the dominant kernel (profiles/r01_f_ncu_full.txt)
+HALO_KERNEL_TRAFFIC_BYTES = None
 CAE_BATCH_PER_GPU = 256
 ARHMM_TRIALS_PER_GPU, ARHMM_T, ARHMM_K, ARHMM_D, ARHMM_LAGS = 2048, 1000, 16, 12, 2
 
@@ -144,22 +146,36 @@ def timed(fn, steps, warmup, flush=None):
     return ms
 
 
-def time_dominant_kernel(model, device, iters=20):
-    """The kernel with the largest share of the step (profiles/r01_*launches*): the tcgen05
-    implicit-GEMM forward of encoder layer 1 (32->64 channels, 64x64 -> 32x32, k5 s2) on 256 frames,
-    timed alone through bn_cae_layer_op."""
+def time_layer_kernel(model, device, side, layer, op, name, traffic_bytes, iters=20):
+    """One layer kernel timed alone through bn_cae_layer_op (CUDA events on the launch stream, after
+    warm-up): side 0/1 = encoder/decoder layer, op 0/1 = forward / backward-data."""
     from behavenet_b200 import _lib
     drv, rt = model._driver, model._rt
+    hp = model.hparams
     n = CAE_BATCH_PER_GPU
     params = model._kernel_params()
     packed = drv.packed(rt, params, device)
     ws = drv.workspace(rt, n, device)
-    a = torch.rand(n, 64, 64, 32, device=device)
-    out = torch.empty(n, 32, 32, 64, device=device)
+    if side == 0:
+        cb, hb, wb = ((hp['ae_input_dim'][0], hp['ae_input_dim'][1], hp['ae_input_dim'][2]) if layer == 0 else
+                      (hp['ae_encoding_n_channels'][layer - 1], hp['ae_encoding_y_dim'][layer - 1],
+                       hp['ae_encoding_x_dim'][layer - 1]))
+        cs, hs, wsm = (hp['ae_encoding_n_channels'][layer], hp['ae_encoding_y_dim'][layer],
+                       hp['ae_encoding_x_dim'][layer])
+    else:
+        c0, h0, w0 = hp['ae_decoding_starting_dim']
+        cs, hs, wsm = ((c0, h0, w0) if layer == 0 else
+                       (hp['ae_decoding_n_channels'][layer - 1], hp['ae_decoding_y_dim'][layer - 1],
+                        hp['ae_decoding_x_dim'][layer - 1]))
+        cb, hb, wb = (hp['ae_decoding_n_channels'][layer], hp['ae_decoding_y_dim'][layer],
+                      hp['ae_decoding_x_dim'][layer])
+    fprop_form = (side == 0 and op == 0) or (side == 1 and op == 1)
+    src = torch.rand((n, hb, wb, cb) if fprop_form else (n, hs, wsm, cs), device=device)
+    out = torch.empty((n, hs, wsm, cs) if fprop_form else (n, hb, wb, cb), device=device)
     lib = _lib.lib()
 
     def run():
-        _lib.check(lib.bn_cae_layer_op(drv.plan(device), 0, 1, 0, n, a.data_ptr(), None, out.data_ptr(),
+        _lib.check(lib.bn_cae_layer_op(drv.plan(device), side, layer, op, n, src.data_ptr(), None, out.data_ptr(),
                                        drv.table(params), packed.data_ptr(), ws.data_ptr(),
                                        _lib.stream_ptr()), 'bn_cae_layer_op')
     for _ in range(5):
@@ -172,10 +188,18 @@ def time_dominant_kernel(model, device, iters=20):
     e1.record()
     e1.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters
-    gflop = 2.0 * (n * 32 * 32) * 64 * (25 * 32) * 1e-9
-    return {'kernel': 'igemm_tc_kernel<64,4> (encoder conv1 forward, M=262144 N=64 K=800)', 'us': us,
-            'gflop': gflop, 'tflops': gflop / us * 1e3, 'launches': iters,
-            'traffic_bytes': 51.6e6}
+    gflop = 2.0 * n * hs * wsm * cs * 25 * cb * 1e-9
+    return {'kernel': name, 'us': us, 'gflop': gflop, 'tflops': gflop / us * 1e3, 'launches': iters,
+            'traffic_bytes': traffic_bytes}
+
+
+def time_dominant_kernel(model, device):
+    """The kernel with the largest share of the step in the committed launch list
+    (profiles/r01_f_launches_summary.txt): the halo-resident tcgen05 transposed convolution of decoder
+    layer 3 (64 -> 32 channels, 32x32 -> 64x64, k5 s2, 256 frames)."""
+    return time_layer_kernel(model, device, 1, 3, 0,
+                             'dgrad_halo_kernel<32,3> (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])',
+                             HALO_KERNEL_TRAFFIC_BYTES)
 
 
 def measure_cublas_tf32(device):
@@ -250,11 +274,15 @@ def run_ours(args):
         model.invalidate_packed()
         model.loss(data, accumulate_grad=True)
 
+    lo, hi = parallel.shard_range(B, world, rank)
+    x_shard_host = x_host[lo:hi].clone().pin_memory()       # this rank's frames only
+
     def step_e2e():
         opt.zero_grad()
         model.invalidate_packed()
-        xd = x_host.to(device, non_blocking=True)
-        model.loss({'images': xd[None]}, accumulate_grad=True)      # ends with the loss readback
+        xd = x_shard_host.to(device, non_blocking=True)
+        # ends with the loss readback (one D2H of the per-chunk sums)
+        model.loss({'images': xd[None], 'shard': (lo, B)}, accumulate_grad=True)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -292,6 +320,8 @@ def run_ours(args):
     tf32_peak_burst = peaks['bf16_tflops'] / 2.0
     tf32_peak_sust = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']) / 2.0
     dom = time_dominant_kernel(model, device)
+    dom2 = time_layer_kernel(model, device, 0, 1, 0,
+                             'igemm_tma_kernel<64,4> (encoder conv1 forward, M=262144 N=64 K=800)', 51.7e6)
     cublas_tf32 = measure_cublas_tf32(device) if rank == 0 else None
 
     # ---------------- ARHMM (C4): weak scaling, 2048 trials per GPU
@@ -354,7 +384,7 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'e2e': {'value': B / (e2e_ms * 1e-3), 'unit': 'frames/s',
-                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 16},
+                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 16 * world},
         'roofline': {'bound': 'tensor', 'achieved': dom['tflops'], 'peak': tf32_peak_burst,
                      'unit': 'TFLOP/s', 'frac': dom['tflops'] / tf32_peak_burst,
                      'traffic': dom['traffic_bytes'],
@@ -362,12 +392,15 @@ def run_ours(args):
                      'note': 'dominant kernel timed alone with CUDA events on the launch stream (%d '
                              'launches after warm-up); peak = TF32 dense = half of the %s bf16 burst '
                              'peak (MEASURED_PEAKS.json has no TF32 entry); traffic = dram read+write '
-                             'bytes per launch from profiles/r01_c_ncu_full_tc_kernels.txt'
+                             'bytes per launch from profiles/r01_f_ncu_full.txt'
                              % (dom['launches'], peak_src)},
         'step_roofline': {'bound': 'tensor', 'achieved': tf, 'peak': tf32_peak_sust, 'unit': 'TFLOP/s',
                           'frac': tf / tf32_peak_sust,
                           'note': 'whole step: %.3f GFLOP/frame algorithmic / step time, per GPU; peak = '
                                   'half of the %s bf16 sustained peak' % (CAE_C2_TRAIN_GFLOP_PER_FRAME, peak_src)},
+        'kernel_rooflines': [{'kernel': d['kernel'], 'us': d['us'], 'tflops': d['tflops'],
+                              'frac': d['tflops'] / tf32_peak_burst, 'traffic': d['traffic_bytes']}
+                             for d in (dom, dom2)],
         'cublas_tf32_tflops_here': cublas_tf32,
         'arhmm': {
             'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
@@ -385,7 +418,8 @@ def run_ours(args):
     if cpu is not None:
         line['cpu_baseline'] = cpu['cae']
         line['arhmm']['cpu_baseline'] = cpu['arhmm']
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + '\n')
+    _OUT.flush()
 
 
 def cpu_cae_step(hp, batch, threads):
@@ -432,19 +466,30 @@ def run_reference(args):
     torch.set_num_threads(cores)
     sd = co.init_state_dict(hp, seed=0)
     x = torch.rand(sample, 1, 128, 128, generator=torch.Generator().manual_seed(0))
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):
         co.ae_loss(sd, hp, x)
-    steps = min(args.steps, 10)
+    steps = args.steps
     t0 = time.perf_counter()
     for _ in range(steps):
         co.ae_loss(sd, hp, x)
     dt = (time.perf_counter() - t0) / steps
     value = sample / dt
-    print(json.dumps({
+    # ARHMM E-step of the same reference arm: ssm's execution model (python loop over trials, fp64)
+    from oracle import arhmm_oracle as ao
+    p = ao.synth_params(ARHMM_K, ARHMM_D, ARHMM_LAGS, seed=0)
+    X = ao.sample_batch(p, 16, ARHMM_T, seed=0)
+    ao.e_step(p, [X[0]])                        # numba compile
+    reps = max(1, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ao.e_step(p, [X[i] for i in range(16)])
+    hdt = (time.perf_counter() - t0) / reps
+    hvalue = 16 * ARHMM_T / hdt
+    _OUT.write(json.dumps({
         'impl': 'reference',
         'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
         'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': min(args.warmup, 2), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'C2: CAE 128x128x1, 12 latents, AE.loss fwd+bwd, default 5-layer arch; '
                                'bounded sample of %d frames per step' % sample},
@@ -452,10 +497,29 @@ def run_reference(args):
                          'sample': '%d-frame steps of oracle/cae_oracle.ae_loss (torch eager fp32, all host '
                                    'threads)' % sample},
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+        'arhmm': {'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12)', 'value': hvalue,
+                  'unit': 'timesteps/s', 'ms_per_step': hdt * 1e3, 'dtype': 'f64',
+                  'cpu_baseline': {'value': hvalue, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
+                                   'sample': '16 of the 2048 trials x 1000 steps per step, '
+                                             'oracle/arhmm_oracle.e_step'},
+                  'e2e': {'value': hvalue, 'unit': 'timesteps/s', 'h2d_bytes_per_step': 0,
+                          'd2h_bytes_per_step': 0}},
+    }) + '\n')
+    _OUT.flush()
+
+
+def _claim_stdout():
+    """NCCL / torchrun helpers may print to fd 1; the driver expects ONE JSON line there.  Route fd 1
+    to stderr for the whole run and return a writer on the original stdout for the final line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
 
 
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)

@@ -217,3 +217,12 @@ def test_many_ragged_trials_batched():
             assert np.abs(out[mode][0][off[i]:off[i + 1]] - g).max() < 1e-5
             assert np.abs(out[mode][1][i] - j).max() < 1e-5 * max(1, lens[i])
             assert abs(out[mode][2][i] - lz) <= 1e-6 * abs(lz) + 1e-4
+
+
+def test_long_trials_stay_normalised():
+    """5000-step trials: any drift of the message scale (a lagged / marginally stable normalisation)
+    would overflow fp32 long before the end."""
+    p = ao.synth_params(8, 6, 2, seed=9, mix=0.05)
+    rng = np.random.RandomState(6)
+    xs = [ao.sample(p, T, rng)[1].astype(np.float32) for T in (5000, 4097)]
+    check_against_oracle(p, xs)

@@ -215,3 +215,37 @@ def test_deepcopy_and_state_dict_roundtrip(tmp_path):
     with torch.no_grad():
         c, _ = other(x)
     assert torch.equal(a, c)
+
+
+def test_c5_encode_then_estep_pipeline():
+    """Config C5 in miniature: uint8 two-camera trials -> encoder latents kept on the device -> ARHMM
+    E-step, against the oracle chain (CPU encoder restatement -> fp64 E-step)."""
+    import numpy as np
+    from behavenet_b200.fitting.eval import encode_trials
+    from behavenet_b200.ssm import HMM
+    from oracle import arhmm_oracle as ao
+    hp = co.make_hparams(2, 128, 128, 12)
+    sd = co.init_state_dict(hp, seed=0)
+    from behavenet_b200.models import AE
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(sd)
+    model.cuda()
+    g = torch.Generator().manual_seed(3)
+    lens = [37, 5, 64, 20]
+    trials = [torch.randint(0, 256, (T, 2, 128, 128), generator=g, dtype=torch.uint8) for T in lens]
+    lat, lengths = encode_trials(model, trials, frames_per_launch=64)
+    assert lengths == lens and lat.shape == (sum(lens), 12) and lat.is_cuda
+    ref = torch.cat([co.encode(sd, hp, t.float() / 255.0) for t in trials], 0)
+    err = float((lat.cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 2e-3, err                      # TF32 conv contractions
+    p = ao.synth_params(4, 12, 1, seed=2, mix=0.05)
+    hmm = HMM(4, 12, observations='ar', observation_kwargs={'lags': 1})
+    hmm.init_state_distn.log_pi0, hmm.transitions.log_Ps = p.log_pi0, p.log_Ps
+    hmm.observations.As, hmm.observations.bs, hmm.observations.Sigmas = p.As, p.bs, p.Sigmas
+    st = hmm.stage_device(lat, lengths)
+    Ez, Ezz, logZ = hmm.expected_states_device(st)
+    xs = np.split(lat.cpu().numpy(), np.cumsum(lens)[:-1])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for i, (gam, jnt, lz) in enumerate(ao.e_step(p, xs)):
+        assert np.abs(Ez[off[i]:off[i + 1]].cpu().numpy() - gam).max() < 1e-5
+        assert abs(float(logZ[i]) - lz) <= 1e-6 * abs(lz) + 1e-4

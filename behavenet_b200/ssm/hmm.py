@@ -215,11 +215,13 @@ class _Staged:
         self.lengths = lens
         self.total = int(sum(lens))
         self.max_T = max(lens) if lens else 0
+        # one pass over the host arrays straight into pinned memory, then one async H2D copy
+        pinned = torch.empty((self.total, D), dtype=torch.float32).pin_memory() if self.total else \
+            torch.empty((0, D), dtype=torch.float32)
         if self.total:
-            host = np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1, D) for d in datas], 0)
-        else:
-            host = np.zeros((0, D), np.float32)
-        self.x = torch.from_numpy(np.ascontiguousarray(host)).to(device)
+            np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1, D) for d in datas], 0, out=pinned.numpy())
+        self.x = pinned.to(device, non_blocking=True)
+        self._pinned = pinned          # keeps the staging buffer alive until the copy has been consumed
         off = np.zeros(self.n + 1, np.int64)
         off[1:] = np.cumsum(lens)
         self.offsets_host = off

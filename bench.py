@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 CAE_C2_TRAIN_GFLOP_PER_FRAME = 2.078
 ARHMM_BYTES_PER_TIMESTEP = 113.0
 # dram__bytes_read + write per launch of the dominant kernel (profiles/r01_f_ncu_full.txt)
-HALO_KERNEL_TRAFFIC_BYTES = None
+HALO_KERNEL_TRAFFIC_BYTES = 144.2e6
 CAE_BATCH_PER_GPU = 256
 ARHMM_TRIALS_PER_GPU, ARHMM_T, ARHMM_K, ARHMM_D, ARHMM_LAGS = 2048, 1000, 16, 12, 2
 
@@ -410,9 +410,12 @@ def run_ours(args):
                     'h2d_bytes_per_step': int(n_ts * ARHMM_D * 4),
                     'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4)},
             'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
-                         'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': None,
+                         'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': 588.4e6,
                          'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out '
-                                 '+ per-trial outputs), whole E-step time; peak %s' % peak_src},
+                                 '+ per-trial outputs), whole E-step time (emission + scan kernels); peak %s; '
+                                 'traffic = dram read+write of the dominant kernel (scan2_kernel, 0.31 of the 0.57 ms; '
+                                 'emission_tc_kernel adds 187 MB), profiles/r01_f_ncu_full.txt; the binding limits '
+                                 'are the T-step serial chain and the 3-pass emission GEMM, not HBM' % peak_src},
         },
     }
     if cpu is not None:

@@ -52,7 +52,7 @@ SIGNATURES = {
     'bn_cae_encode_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'bn_cae_layer_op': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'bn_psvae_latent_workspace_bytes': (_sz, [_i, _i]),
-    'bn_psvae_latent': (_i, [_i, _i, _i] + [_vp] * 9 + [_f, _f, _f] + [_vp] * 11),
+    'bn_psvae_latent': (_i, [_i, _i, _i] + [_vp] * 9 + [_f, _f, _f, _f] + [_vp] * 11),
     'bn_psvae_latent_bwd': (_i, [_i, _i, _i] + [_vp] * 11),
     'bn_arhmm_params_bytes': (_sz, [_i, _i, _i]),
     'bn_arhmm_pack_params': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -79,7 +79,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.bn_abi_version() != 1:
+        if handle.bn_abi_version() != 2:
             raise NativeLibraryError('ABI version mismatch')
         _lib = handle
     return _lib

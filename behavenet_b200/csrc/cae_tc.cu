@@ -1048,7 +1048,8 @@ struct HaloArgs {
   int lo_y, lo_x;            // smallest tap offset over all classes
   int tiles_x;               // 8-pixel column blocks per frame
   int ngroups;
-  int dbg;                   // experiment switches (BN_HALO_DBG): 1 no stores, 2 no MMAs, 4 no weight loads, 8 no bias/act
+  int tiles_per_frame;
+  long long total_tiles;     // tiles_per_frame * frames
   int pos[4];                // TMEM column block of class c
   int Hm[4], Wm[4], oy0[4], ox0[4];
   HaloGroup g[HALO_MAXG];
@@ -1059,28 +1060,40 @@ struct alignas(64) HaloMaps {
   CUtensorMap b;       // K-major weights, box 32 x NB
 };
 
-template <int NB, int NST>
+template <int NB, int NST, bool PERSIST>
 struct HaloSmem {
   static constexpr int B_TILE = NB * 128;
   static constexpr int B_BYTES = 4 * B_TILE;                          // up to four stacked class tiles
   static constexpr int OFF_A = NST * B_BYTES;                         // multiple of 1024
-  static constexpr int OFF_BAR = OFF_A + 2 * HALO_ASTRIDE;
-  static constexpr int TOTAL = OFF_BAR + 8 * (2 * NST + 5) + 32;
+  // 4 warps x 4 KB transposition tiles: their own region when the weight ring keeps streaming under
+  // the epilogue (persistent), aliased onto the (then idle) ring when a CTA owns a single tile
+  static constexpr int OFF_EPI = PERSIST ? OFF_A + 2 * HALO_ASTRIDE : 0;
+  static constexpr int OFF_BAR = OFF_A + 2 * HALO_ASTRIDE + (PERSIST ? 4 * 4096 : 0);
+  static constexpr int TOTAL = OFF_BAR + 8 * (2 * NST + 8) + 32;
 };
 
-template <int NB, int NST>
+// PERSIST: a CTA walks tiles blockIdx.x, +gridDim.x, .. (tile = 16 x 8 small pixels of one frame).
+// Three roles run the same tile sequence decoupled by mbarriers: the TMA thread streams halo chunks
+// (2 buffers) and weight-tile groups (NST-deep ring) without ever draining between tiles, the MMA
+// thread accumulates tile i into TMEM buffer i & 1, and the four epilogue warps drain buffer i & 1
+// while the MMAs of tile i + 1 fill the other one.  Barrier / TMEM setup is paid once per CTA.
+// !PERSIST (NB = 64: two accumulator sets would take all 512 TMEM columns and leave one CTA per SM,
+// which measured slower): one tile per CTA, one accumulator set, two CTAs per SM overlap each other.
+template <int NB, int NST, bool PERSIST>
 __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_constant__ HaloMaps maps,
                                                                   const __grid_constant__ HaloArgs h) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  using S = HaloSmem<NB, NST>;
-  constexpr int NCOLS = 4 * NB;                      // 128 or 256 TMEM columns: one accumulator per class
+  using S = HaloSmem<NB, NST, PERSIST>;
+  constexpr int ACC_COLS = 4 * NB;                   // one accumulator per class
+  constexpr int NCOLS = (PERSIST ? 2 : 1) * ACC_COLS;
   const TcArgs& a = h.a;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* b_empty = b_full + NST;
   uint64_t* a_full = b_empty + NST;       // [2]
   uint64_t* a_empty = a_full + 2;         // [2]
-  uint64_t* accum_bar = a_empty + 2;      // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = a_empty + 2;       // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -1092,8 +1105,9 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(a_full + s), 1);
       mbar_init(smem_u32(a_empty + s), 1);
+      mbar_init(smem_u32(acc_full + s), 1);
+      mbar_init(smem_u32(acc_empty + s), 128);
     }
-    mbar_init(smem_u32(accum_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
@@ -1103,100 +1117,124 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
   const int Ci = a.Ci;
   const int nchunk = Ci / BK;
-  const int f = blockIdx.y;
-  const int by = blockIdx.x / h.tiles_x, bx = blockIdx.x - by * h.tiles_x;
-  const int ym0 = by * 16, xm0 = bx * 8;
   const uint32_t smem_base = smem_u32(smem);
+  const long long total = h.total_tiles;
 
   if (warp < 4) {
     // ======================= epilogue ============================================================
-    mbar_wait(smem_u32(accum_bar), 0);
-    tc_fence_after();
-    const int ym = ym0 + (tid >> 3), xm = xm0 + (tid & 7);
-    float* tile = reinterpret_cast<float*>(smem) + warp * 1024;      // the weight ring is idle now
+    float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
     const int elane = tid & 31;
+    int ti = 0;
+    for (long long T = blockIdx.x; T < total; T += gridDim.x, ++ti) {
+      const int f = (int)(T / h.tiles_per_frame);
+      const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+      const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+      const int ym = by * 16 + (tid >> 3), xm = bx * 8 + (tid & 7);
+      const int buf = PERSIST ? (ti & 1) : 0;
+      mbar_wait(smem_u32(acc_full + buf), (ti >> 1) & 1);
+      tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
-      const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
-      const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
+      for (int c = 0; c < 4; ++c) {
+        const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
+        const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
+        const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
 #pragma unroll 1
-      for (int j = 0; j < NB / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + h.pos[c] * NB + j * 32, r);
-        tmem_ld_wait();
-        float v[32];
+        for (int j = 0; j < NB / 32; ++j) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * ACC_COLS + h.pos[c] * NB + j * 32, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          float x = __uint_as_float(r[q]);
-          if (a.bias) x += __ldg(a.bias + j * 32 + q);
-          if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-          else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-          v[q] = x;
+          for (int q = 0; q < 32; ++q) {
+            float x = __uint_as_float(r[q]);
+            if (a.bias) x += __ldg(a.bias + j * 32 + q);
+            if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
+            else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
+            v[q] = x;
+          }
+          warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
         }
-        if (!(h.dbg & 1)) warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
       }
+      tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
+      mbar_arrive(smem_u32(acc_empty + buf));
     }
-    tc_fence_before();
   } else if (warp == 4) {
     // ======================= MMA issuer ==========================================================
     if ((tid & 31) == 0) {
-      int i = 0;
-      for (int c = 0; c < nchunk; ++c) {
-        mbar_wait(smem_u32(a_full + (c & 1)), (c >> 1) & 1);
-        tc_fence_after();
-        const uint32_t abuf = smem_base + S::OFF_A + (c & 1) * HALO_ASTRIDE;
-        for (int gi = 0; gi < h.ngroups; ++gi, ++i) {
-          const int stage = i % NST;
-          mbar_wait(smem_u32(b_full + stage), (i / NST) & 1);
+      int ai = 0, bi = 0, ti = 0;
+      for (long long T = blockIdx.x; T < total; T += gridDim.x, ++ti) {
+        const int buf = PERSIST ? (ti & 1) : 0;
+        if (ti >= 2) {
+          mbar_wait(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
           tc_fence_after();
-          const uint32_t sb = smem_base + stage * S::B_BYTES;
-          const HaloGroup g = h.g[gi];
-          const uint32_t idesc = make_idesc(BM, g.ncls * NB);
-          const uint32_t acc = tmem_base + g.col0 * NB;
-          const uint32_t arow = abuf + g.row_off * 128;
-#pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // the 128B swizzle is a function of the shared-memory ADDRESS bits, so a window that starts
-            // on any 128-byte row of the TMA-written halo needs no descriptor base offset
-            const uint64_t ad = make_desc_sw128_sbo(arow + k * 32, HALO_W * 128);
-            const uint64_t bd = make_desc_sw128(sb + k * 32);
-            if (!(h.dbg & 2)) umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
-          }
-          umma_commit(smem_u32(b_empty + stage));
         }
-        umma_commit(smem_u32(a_empty + (c & 1)));
+        for (int c = 0; c < nchunk; ++c, ++ai) {
+          const int slot = ai & 1;
+          mbar_wait(smem_u32(a_full + slot), (ai >> 1) & 1);
+          tc_fence_after();
+          const uint32_t abuf = smem_base + S::OFF_A + slot * HALO_ASTRIDE;
+          for (int gi = 0; gi < h.ngroups; ++gi, ++bi) {
+            const int stage = bi % NST;
+            mbar_wait(smem_u32(b_full + stage), (bi / NST) & 1);
+            tc_fence_after();
+            const uint32_t sb = smem_base + stage * S::B_BYTES;
+            const HaloGroup g = h.g[gi];
+            const uint32_t idesc = make_idesc(BM, g.ncls * NB);
+            const uint32_t acc = tmem_base + buf * ACC_COLS + g.col0 * NB;
+            const uint32_t arow = abuf + g.row_off * 128;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              // the 128B swizzle is a function of the shared-memory ADDRESS bits, so a window that
+              // starts on any 128-byte row of the TMA-written halo needs no descriptor base offset
+              const uint64_t ad = make_desc_sw128_sbo(arow + k * 32, HALO_W * 128);
+              const uint64_t bd = make_desc_sw128(sb + k * 32);
+              umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
+            }
+            umma_commit(smem_u32(b_empty + stage));
+          }
+          umma_commit(smem_u32(a_empty + slot));
+        }
+        umma_commit(smem_u32(acc_full + buf));
       }
-      umma_commit(smem_u32(accum_bar));
     }
     __syncwarp();
   } else {
-    // ======================= TMA producer: halo chunks and weight tiles ==========================
+    // ======================= TMA producer: halo chunks and weight-tile groups ====================
     if ((tid & 31) == 0) {
-      auto load_halo = [&](int c) {
-        if (c >= 2) mbar_wait(smem_u32(a_empty + (c & 1)), ((c >> 1) - 1) & 1);
-        const uint32_t bar = smem_u32(a_full + (c & 1));
+      int ai = 0, bi = 0;
+      // chunk sequence number q -> (tile, chunk); the halo of chunk q + 1 is requested before the
+      // weight tiles of chunk q so that it lands while chunk q is being multiplied
+      auto load_halo = [&](long long T, int c, int q) {
+        const int slot = q & 1;
+        if (q >= 2) mbar_wait(smem_u32(a_empty + slot), ((q >> 1) - 1) & 1);
+        const int f = (int)(T / h.tiles_per_frame);
+        const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+        const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+        const uint32_t bar = smem_u32(a_full + slot);
         mbar_expect_tx(bar, (uint32_t)HALO_ABYTES);
-        tma_tile_4d(smem_base + S::OFF_A + (c & 1) * HALO_ASTRIDE, &maps.a, bar, c * BK, xm0 + h.lo_x, ym0 + h.lo_y, f);
+        tma_tile_4d(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a, bar, c * BK, bx * 8 + h.lo_x, by * 16 + h.lo_y, f);
       };
-      load_halo(0);
-      if (nchunk > 1) load_halo(1);
-      int i = 0;
-      for (int c = 0; c < nchunk; ++c) {
-        for (int gi = 0; gi < h.ngroups; ++gi, ++i) {
-          const int stage = i % NST;
-          if (i >= NST) mbar_wait(smem_u32(b_empty + stage), ((i / NST) - 1) & 1);
-          const uint32_t bar = smem_u32(b_full + stage);
-          const HaloGroup g = h.g[gi];
-          mbar_expect_tx(bar, (uint32_t)((h.dbg & 4) ? S::B_TILE : g.ncls * S::B_TILE));
-          for (int j = 0; j < ((h.dbg & 4) ? 1 : g.ncls); ++j)
-            tma_tile_2d(smem_base + stage * S::B_BYTES + j * S::B_TILE, &maps.b, bar, g.wt[j] * Ci + c * BK, 0);
+      if ((long long)blockIdx.x < total) load_halo(blockIdx.x, 0, 0);
+      for (long long T = blockIdx.x; T < total; T += gridDim.x) {
+        for (int c = 0; c < nchunk; ++c, ++ai) {
+          // next chunk in sequence
+          if (c + 1 < nchunk) load_halo(T, c + 1, ai + 1);
+          else if (T + gridDim.x < total) load_halo(T + gridDim.x, 0, ai + 1);
+          for (int gi = 0; gi < h.ngroups; ++gi, ++bi) {
+            const int stage = bi % NST;
+            if (bi >= NST) mbar_wait(smem_u32(b_empty + stage), ((bi / NST) - 1) & 1);
+            const uint32_t bar = smem_u32(b_full + stage);
+            const HaloGroup g = h.g[gi];
+            mbar_expect_tx(bar, (uint32_t)(g.ncls * S::B_TILE));
+            for (int j = 0; j < g.ncls; ++j)
+              tma_tile_2d(smem_base + stage * S::B_BYTES + j * S::B_TILE, &maps.b, bar, g.wt[j] * Ci + c * BK, 0);
+          }
         }
-        if (c + 2 < nchunk) load_halo(c + 2);      // its buffer is released by the MMAs of chunk c
       }
     }
     __syncwarp();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
@@ -1225,16 +1263,21 @@ bool encode_tiled_4d(CUtensorMap* map, const float* p, int N, int H, int W, int 
   return r == CUDA_SUCCESS;
 }
 
-template <int NB, int NST>
-int launch_halo(const HaloMaps& maps, const HaloArgs& h, int tiles, cudaStream_t st) {
-  using S = HaloSmem<NB, NST>;
-  auto kern = dgrad_halo_kernel<NB, NST>;
+template <int NB, int NST, bool PERSIST>
+int launch_halo(const HaloMaps& maps, const HaloArgs& h, cudaStream_t st) {
+  using S = HaloSmem<NB, NST, PERSIST>;
+  auto kern = dgrad_halo_kernel<NB, NST, PERSIST>;
   static bool configured = false;
   if (!configured) {
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  kern<<<dim3(tiles, h.a.n), HALO_THREADS, S::TOTAL, st>>>(maps, h);
+  static_assert(2 * (S::TOTAL + 1024) <= 227 * 1024, "two CTAs per SM");
+  static_assert(2 * (PERSIST ? 2 : 1) * 4 * NB <= 512, "TMEM columns of two resident CTAs");
+  long long grid = PERSIST ? 2 * 148 : h.total_tiles;
+  if (grid > h.total_tiles) grid = h.total_tiles;
+  if (!PERSIST && grid > 0x7fffffffLL) return 1;
+  kern<<<(unsigned)grid, HALO_THREADS, S::TOTAL, st>>>(maps, h);
   BN_LAUNCHED();
   return 0;
 }
@@ -1244,7 +1287,7 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream
   static const bool off = [] { const char* e = getenv("BN_HALO"); return e && e[0] == '0'; }();
   if (off || nclasses != 4 || a.gs != 1 || a.os != 2 || a.ksplit > 1) return 1;
   if (a.Co != 32 && a.Co != 64) return 1;
-  if (a.n > 65535 || !tma_available()) return 1;
+  if (!tma_available()) return 1;
   int lo_y = 127, lo_x = 127, hi_y = -128, hi_x = -128, Hm = 0, Wm = 0, ntaps = 0;
   for (int c = 0; c < 4; ++c) {
     const TapClass& k = hc[c];
@@ -1317,7 +1360,7 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream
     if (wmask[w] && w != full) add_group(w);
   h.ngroups = ng;
   (void)ntaps;
-  { const char* e = getenv("BN_HALO_DBG"); h.dbg = e ? atoi(e) : 0; }
+
 
   const HaloMaps* hm = nullptr;
   {
@@ -1335,10 +1378,11 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream
       hm = &g_halo_cache.back().second;
     }
   }
-  const int tiles = h.tiles_x * bn_cdiv(Hm, 16);
+  h.tiles_per_frame = h.tiles_x * bn_cdiv(Hm, 16);
+  h.total_tiles = (long long)h.tiles_per_frame * a.n;
   HaloMaps local = *hm;
-  if (a.Co == 32) return launch_halo<32, 3>(local, h, tiles, st);
-  return launch_halo<64, 2>(local, h, tiles, st);
+  if (a.Co == 32) return launch_halo<32, 3, true>(local, h, st);
+  return launch_halo<64, 2, false>(local, h, st);
 }
 
 }  // namespace

@@ -18,7 +18,7 @@ constexpr float LN2PI_F = 1.8378770664093453f;
 struct LatArgs {
   int n, L, nl;
   const float *pre, *logvar, *A, *B, *Dw, *Db, *eps, *labels, *lmask;
-  float alpha, beta, klw;
+  float alpha, beta, klw, kls;
   float *mu, *z, *yhat;
   double* terms;
   float *gmu, *glv, *gz, *gDw, *gDb;
@@ -54,8 +54,8 @@ __global__ void latent_fwd_kernel(const LatArgs a) {
     // supervised-latent KL to N(0,1): 0.5 * (exp(lv) - lv + mu^2 - 1)
     atomicAdd(a.terms + 1, (double)(0.5f * (expf(lv) - lv + m * m - 1.f)));
     if (a.gmu) {
-      a.gmu[i] = gy * a.Dw[d] + m / (float)a.n;
-      a.glv[i] = 0.5f * (expf(lv) - 1.f) / (float)a.n;
+      a.gmu[i] = gy * a.Dw[d] + a.kls * m / (float)a.n;
+      a.glv[i] = a.kls * 0.5f * (expf(lv) - 1.f) / (float)a.n;
       a.gz[i] = 0.f;
     }
   }
@@ -209,13 +209,15 @@ extern "C" size_t bn_psvae_latent_workspace_bytes(int n, int n_latents) {
 extern "C" int bn_psvae_latent(int n, int L, int nl, const float* d_pre, const float* d_logvar,
                                const float* d_A, const float* d_B, const float* d_Dw, const float* d_Db,
                                const float* d_eps, const float* d_labels, const float* d_labels_mask,
-                               float alpha, float beta, float kl_w, void* d_ws, float* d_mu, float* d_z,
+                               float alpha, float beta, float kl_w, float kl_s_w, void* d_ws, float* d_mu,
+                               float* d_z,
                                float* d_yhat, double* d_terms, float* d_gmu_part, float* d_glogvar_part,
                                float* d_gz_part, float* d_gDw, float* d_gDb, void* stream) {
   if (n <= 0) return 0;
   if (L < 1 || nl < 0 || nl > L) BN_FAIL("bn_psvae_latent: n_latents=%d n_labels=%d", L, nl);
   if (L - nl > 64) BN_FAIL("bn_psvae_latent: more than 64 unsupervised latents");
-  if (!d_pre || !d_logvar || !d_A || (!d_B && L > nl) || !d_Dw || !d_Db || !d_mu || !d_z || !d_yhat || !d_terms)
+  if (!d_pre || !d_logvar || (nl > 0 && (!d_A || !d_Dw || !d_Db || !d_yhat)) || (!d_B && L > nl) || !d_mu || !d_z ||
+      !d_terms)
     BN_FAIL("bn_psvae_latent: null argument");
   const bool grads = d_gmu_part && d_glogvar_part && d_gz_part;
   if (grads && !d_ws) BN_FAIL("bn_psvae_latent: workspace required");
@@ -223,7 +225,7 @@ extern "C" int bn_psvae_latent(int n, int L, int nl, const float* d_pre, const f
   LatArgs a;
   a.n = n; a.L = L; a.nl = nl; a.pre = d_pre; a.logvar = d_logvar; a.A = d_A; a.B = d_B; a.Dw = d_Dw;
   a.Db = d_Db; a.eps = d_eps; a.labels = d_labels; a.lmask = d_labels_mask; a.alpha = alpha;
-  a.beta = beta; a.klw = kl_w; a.mu = d_mu; a.z = d_z; a.yhat = d_yhat; a.terms = d_terms;
+  a.beta = beta; a.klw = kl_w; a.kls = kl_s_w; a.mu = d_mu; a.z = d_z; a.yhat = d_yhat; a.terms = d_terms;
   a.gmu = grads ? d_gmu_part : nullptr; a.glv = d_glogvar_part; a.gz = d_gz_part; a.gDw = d_gDw; a.gDb = d_gDb;
   a.log_qz = (float*)d_ws;
   a.lse = d_ws ? (float*)d_ws + n : nullptr;
@@ -246,7 +248,8 @@ extern "C" int bn_psvae_latent_bwd(int n, int L, int nl, const float* d_A, const
                                    const float* d_gmu_part, const float* d_glogvar_part,
                                    const float* d_gz_part, float* d_gpre, float* d_glogvar, void* stream) {
   if (n <= 0) return 0;
-  if (!d_A || (!d_B && L > nl) || !d_logvar || !d_gpre || !d_glogvar) BN_FAIL("bn_psvae_latent_bwd: null argument");
+  if ((!d_A && nl > 0) || (!d_B && L > nl) || !d_logvar || !d_gpre || !d_glogvar)
+    BN_FAIL("bn_psvae_latent_bwd: null argument");
   latent_bwd_kernel<<<bn_cdiv((long long)n * L, 128), 128, 0, (cudaStream_t)stream>>>(
       n, L, nl, d_A, d_B, d_eps, d_logvar, d_gz_dec, d_gmu_part, d_glogvar_part, d_gz_part, d_gpre, d_glogvar);
   BN_LAUNCHED();

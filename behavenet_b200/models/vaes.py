@@ -17,7 +17,7 @@ from behavenet_b200.models.aes import AE, ConvAEDecoder, ConvAEEncoder
 from behavenet_b200.models.base import DiagLinear
 from behavenet_b200.models._engine import CaeDriver
 
-__all__ = ['reparameterize', 'PSVAE', 'ConvAEPSEncoder']
+__all__ = ['reparameterize', 'VAE', 'BetaTCVAE', 'PSVAE', 'ConvAEPSEncoder']
 
 LN2PI = float(np.log(2 * np.pi))
 
@@ -48,7 +48,7 @@ class _LatentFn(torch.autograd.Function):
         terms = torch.zeros(5, dtype=torch.float64, device=dev)
         _lib.check(_lib.lib().bn_psvae_latent(
             n, L, nl, pre.data_ptr(), logvar.data_ptr(), A.data_ptr(), _lib.ptr(B), Dw.data_ptr(),
-            Db.data_ptr(), _lib.ptr(eps), None, None, 0.0, 0.0, 0.0, None, mu.data_ptr(),
+            Db.data_ptr(), _lib.ptr(eps), None, None, 0.0, 0.0, 0.0, 1.0, None, mu.data_ptr(),
             z.data_ptr(), yhat.data_ptr(), terms.data_ptr(), None, None, None, None, None,
             _lib.stream_ptr()), 'bn_psvae_latent')
         ctx.save_for_backward(logvar, A, B, Dw, eps, mu)
@@ -113,6 +113,191 @@ class ConvAEPSEncoder(ConvAEEncoder):
         mu, _, _ = _LatentFn.apply(pre, logvar, self.A.weight, self.B.weight, self.D.weight,
                                    self.D.bias, None)
         return mu[:, :n_labels], mu[:, n_labels:], logvar, [], []
+
+
+class VAE(AE):
+    """Variational autoencoder / beta-VAE (reference vaes.py:38-208): ``-ll + beta * KL``.
+
+    The conv stacks run on the AE kernels; the latent block is the PS-VAE C call with every latent
+    in the "supervised" slice (A = I, no labels), whose analytic KL weight carries ``vae.beta``."""
+
+    def __init__(self, hparams):
+        if hparams['model_type'] == 'linear':
+            raise NotImplementedError
+        hparams['variational'] = True
+        super().__init__(hparams)
+        anneal_epochs = self.hparams.get('vae.beta_anneal_epochs', 0)
+        self.curr_epoch = 0  # must be modified by training script
+        tail = np.ones(hparams['max_n_epochs'] + 1)
+        if anneal_epochs > 0:
+            self.beta_vals = np.append(np.linspace(0, hparams['vae.beta'], anneal_epochs), tail)
+        else:
+            self.beta_vals = hparams['vae.beta'] * tail
+
+    def forward(self, x, dataset=None, use_mean=False, eps=None, **kwargs):
+        """(x_hat, z, mu, logvar) (reference vaes.py:102-129); ``eps`` optionally injects the noise."""
+        mu, logvar, pool_idx, outsize = self.encoding(x, dataset=dataset)
+        z = mu if use_mean else reparameterize(mu, logvar, None if eps is None else eps.to(mu.device))
+        x_hat = self.decoding(z, pool_idx, outsize, dataset=dataset)
+        return x_hat, z, mu, logvar
+
+    # -- latent-block configuration: (n "supervised" dims, alpha, beta_tc, kl_w, kl_s_w) ----------
+    def _latent_weights(self):
+        L = self.hparams['n_ae_latents']
+        return L, 0.0, 0.0, 0.0, float(self.beta_vals[self.curr_epoch])
+
+    def _identity(self, device):
+        L = self.hparams['n_ae_latents']
+        buf = self._rt.bufs.get('eye')
+        if buf is None or buf[0].device != device:
+            buf = (torch.eye(L, device=device), torch.ones(L, device=device), torch.zeros(L, device=device))
+            self._rt.bufs['eye'] = buf
+        return buf
+
+    def _elbo_pass(self, data, accumulate_grad, chunk_size, eps):
+        """Shared fused pass of the VAE family: per reference chunk the pixel sum of squares and the
+        latent terms [unused, analytic KL, MI, TC, DWKL] (sums over the chunk's frames), gradients
+        accumulated into ``.grad``.  Returns (host array (n_chunks, 6), chunks)."""
+        x = data['images'][0]
+        m = data['masks'][0] if 'masks' in data else None
+        drv, rt = self._driver, self._rt
+        x = drv._check_input(x, "data['images'][0]", drv.img)
+        if m is not None:
+            m = drv._check_input(m.to(torch.float32), "data['masks'][0]", drv.img)
+        n_total = x.shape[0]
+        chunks = [(b, min(b + chunk_size, n_total)) for b in range(0, n_total, chunk_size)]
+        n_chunks = len(chunks)
+        L = self.hparams['n_ae_latents']
+        nl, alpha, beta, kl, kls = self._latent_weights()
+        device = x.device
+        if self.data_parallel and parallel.enabled():
+            cb, ce = parallel.shard_range(n_chunks)      # whole chunks: the estimators are per chunk
+            my_chunks = list(range(cb, ce))
+        else:
+            my_chunks = list(range(n_chunks))
+        beg = chunks[my_chunks[0]][0] if my_chunks else 0
+        end = chunks[my_chunks[-1]][1] if my_chunks else 0
+        n = end - beg
+        params = self._kernel_params()
+        sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
+        terms = torch.zeros(n_chunks, 5, dtype=torch.float64, device=device)
+        lib = _lib.lib()
+        if n > 0:
+            xs = x[beg:end]
+            ms = None if m is None else m[beg:end]
+            if eps is None:
+                eps_s = torch.randn(n, L, dtype=torch.float32, device=device)
+            else:
+                eps_s = eps.to(device=device, dtype=torch.float32)[beg:end].contiguous()
+            eye, ones, zeros = self._identity(device)
+            packed = drv.packed(rt, params, device)
+            ws = drv.workspace(rt, n, device)
+            pre, logvar = drv.encode(xs, params, packed, ws, True)
+            mu = torch.empty(n, L, device=device)
+            z = torch.empty(n, L, device=device)
+            gmu_p = torch.empty(n, L, device=device)
+            glv_p = torch.empty(n, L, device=device)
+            gz_p = torch.zeros(n, L, device=device)
+            yhat = torch.empty(max(n * nl, 1), device=device)
+            grads = self._grad_table(params) if accumulate_grad else None
+            lws = torch.empty(lib.bn_psvae_latent_workspace_bytes(chunk_size, L), dtype=torch.uint8, device=device)
+            A = eye.data_ptr() if nl > 0 else None
+            B = eye.data_ptr() if nl < L else None
+            for c in my_chunks:
+                b, e = chunks[c][0] - beg, chunks[c][1] - beg
+                sl = slice(b, e)
+                _lib.check(lib.bn_psvae_latent(
+                    e - b, L, nl, pre[sl].data_ptr(), logvar[sl].data_ptr(), A, B,
+                    ones.data_ptr() if nl > 0 else None, zeros.data_ptr() if nl > 0 else None,
+                    eps_s[sl].data_ptr(), None, None, float(alpha), float(beta), float(kl), float(kls),
+                    lws.data_ptr(), mu[sl].data_ptr(), z[sl].data_ptr(), yhat.data_ptr() if nl > 0 else None,
+                    terms[c].data_ptr(), gmu_p[sl].data_ptr(), glv_p[sl].data_ptr(), gz_p[sl].data_ptr(),
+                    None, None, _lib.stream_ptr()), 'bn_psvae_latent')
+            drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms, chunk_size=chunk_size,
+                       frame_offset=beg, n_total=n_total, grad_coef=1.0, sse=sse)
+            if accumulate_grad:
+                gz_dec = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+                gpre = torch.empty(n, L, device=device)
+                glv = torch.empty(n, L, device=device)
+                _lib.check(lib.bn_psvae_latent_bwd(
+                    n, L, nl, A, B, eps_s.data_ptr(), logvar.data_ptr(), gz_dec.data_ptr(), gmu_p.data_ptr(),
+                    glv_p.data_ptr(), gz_p.data_ptr(), gpre.data_ptr(), glv.data_ptr(), _lib.stream_ptr()),
+                    'bn_psvae_latent_bwd')
+                drv.encode_bwd(xs, gpre, glv, params, packed, ws, grads)
+        elif accumulate_grad:
+            self._grad_table(params)
+        stats = torch.cat([sse[:, None], terms], 1)
+        if self.data_parallel and parallel.enabled():
+            if accumulate_grad:
+                self._allreduce(params, stats)
+            else:
+                parallel.all_reduce_sum(stats)
+        return stats.cpu().numpy(), chunks        # the one device->host read of the call
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200, eps=None):
+        """ELBO loss with the reference's chunk semantics (vaes.py:131-208); same dict of floats."""
+        host, chunks = self._elbo_pass(data, accumulate_grad, chunk_size, eps)
+        beta = self.beta_vals[self.curr_epoch]
+        n_pix = float(np.prod(self._driver.img))
+        n_total = chunks[-1][1]
+        vals = {'loss': 0.0, 'loss_ll': 0.0, 'loss_kl': 0.0, 'loss_mse': 0.0}
+        for c, (b, e) in enumerate(chunks):
+            bs = e - b
+            ll = -0.5 * LN2PI * n_pix - 0.5 * host[c, 0] / bs
+            klv = host[c, 2] / bs
+            vals['loss'] += (-ll + beta * klv) * bs
+            vals['loss_ll'] += ll * bs
+            vals['loss_kl'] += klv * bs
+            vals['loss_mse'] += ((ll + 0.5 * LN2PI * n_pix) * -2.0 / n_pix) * bs
+        for k in vals:
+            vals[k] /= n_total
+        vals['beta'] = beta
+        return vals
+
+
+class BetaTCVAE(VAE):
+    """beta-TC-VAE (reference vaes.py:367-503): ``-ll + kl * MI + beta * TC + kl * DWKL`` with the
+    minibatch estimators of losses.py:284-372 over every latent (B = I, no supervised slice)."""
+
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        anneal_epochs = self.hparams.get('beta_tcvae.beta_anneal_epochs', 0)
+        self.curr_epoch = 0
+        beta = hparams['beta_tcvae.beta']
+        tail = np.ones(hparams['max_n_epochs'] + 1)
+        if anneal_epochs > 0:
+            self.beta_vals = np.append(np.linspace(0, beta, anneal_epochs), beta * tail)
+            self.kl_anneal_vals = np.append(np.linspace(0, 1, anneal_epochs), tail)
+        else:
+            self.beta_vals = beta * tail
+            self.kl_anneal_vals = tail
+
+    def _latent_weights(self):
+        return 0, 0.0, float(self.beta_vals[self.curr_epoch]), float(self.kl_anneal_vals[self.curr_epoch]), 0.0
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200, eps=None):
+        host, chunks = self._elbo_pass(data, accumulate_grad, chunk_size, eps)
+        beta = self.beta_vals[self.curr_epoch]
+        kl = self.kl_anneal_vals[self.curr_epoch]
+        n_pix = float(np.prod(self._driver.img))
+        n_total = chunks[-1][1]
+        keys = ['loss', 'loss_ll', 'loss_mi', 'loss_tc', 'loss_dwkl']
+        vals = {k: 0.0 for k in keys}
+        vals['loss_mse'] = 0.0
+        for c, (b, e) in enumerate(chunks):
+            bs = e - b
+            t = {'loss_ll': -0.5 * LN2PI * n_pix - 0.5 * host[c, 0] / bs, 'loss_mi': host[c, 3] / bs,
+                 'loss_tc': host[c, 4] / bs, 'loss_dwkl': host[c, 5] / bs}
+            t['loss'] = -t['loss_ll'] + kl * t['loss_mi'] + beta * t['loss_tc'] + kl * t['loss_dwkl']
+            for k in keys:
+                vals[k] += t[k] * bs
+            # the reference converts the RUNNING sum (vaes.py:490-491); reproduced as is
+            llc = vals['loss_ll'] / bs + 0.5 * LN2PI * n_pix
+            vals['loss_mse'] += (llc * -2.0 / n_pix) * bs
+        for k in vals:
+            vals[k] /= n_total
+        vals['beta'] = beta
+        return vals
 
 
 class PSVAE(AE):
@@ -238,7 +423,7 @@ class PSVAE(AE):
                     _lib.ptr(enc.B.weight) if L > nl else None, D.weight.data_ptr(), D.bias.data_ptr(),
                     eps_s[sl].data_ptr(), y[beg + b:beg + e].data_ptr(),
                     None if nm is None else nm[beg + b:beg + e].data_ptr(),
-                    float(alpha), float(beta), float(kl), lws.data_ptr(), mu[sl].data_ptr(),
+                    float(alpha), float(beta), float(kl), 1.0, lws.data_ptr(), mu[sl].data_ptr(),
                     z[sl].data_ptr(), y_hat_all[beg + b:beg + e].data_ptr(), terms[c].data_ptr(),
                     gmu_p[sl].data_ptr(), glv_p[sl].data_ptr(), gz_p[sl].data_ptr(),
                     D.weight.grad.data_ptr() if accumulate_grad and D.weight.requires_grad else None,

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define BN_MAX_LAYERS 8
-#define BN_ABI_VERSION 1
+#define BN_ABI_VERSION 2
 
 int bn_abi_version(void);
 const char* bn_last_error(void);
@@ -144,14 +144,14 @@ int bn_cae_layer_op(bn_cae_plan* plan, int side, int layer, int op, int n, const
  * Outputs: d_mu, d_z (n, L), d_yhat (n, n_labels); d_terms[5] doubles that ACCUMULATE sums over
  * the chunk's frames of {sum_d (y - yhat)^2 mask, zs_kl, index-code MI, total correlation,
  * dimension-wise KL}; and the partial gradients of
- *     -alpha * label_ll + zs_kl + kl_w * MI + beta * TC + kl_w * DWKL        (chunk means)
+ *     -alpha * label_ll + kl_s_w * zs_kl + kl_w * MI + beta * TC + kl_w * DWKL        (chunk means)
  * with respect to mu / logvar / z taken as independent variables: d_gmu_part, d_glogvar_part,
  * d_gz_part (n, L).  D's gradients accumulate (+=) into d_gDw / d_gDb (may be NULL). */
 size_t bn_psvae_latent_workspace_bytes(int n, int n_latents);
 int bn_psvae_latent(int n, int n_latents, int n_labels, const float* d_pre, const float* d_logvar,
                     const float* d_A, const float* d_B, const float* d_Dw, const float* d_Db,
                     const float* d_eps, const float* d_labels, const float* d_labels_mask,
-                    float alpha, float beta, float kl_w, void* d_ws, float* d_mu, float* d_z,
+                    float alpha, float beta, float kl_w, float kl_s_w, void* d_ws, float* d_mu, float* d_z,
                     float* d_yhat, double* d_terms, float* d_gmu_part, float* d_glogvar_part,
                     float* d_gz_part, float* d_gDw, float* d_gDb, void* stream);
 

@@ -225,6 +225,72 @@ def psvae_loss(sd, hparams, x, labels, eps, masks=None, labels_masks=None, alpha
 
 
 # ------------------------------------------------------------------------------------------------
+# VAE / beta-TC-VAE (models/vaes.py:38-208, 367-503)
+# ------------------------------------------------------------------------------------------------
+
+def vae_forward(sd, hparams, x, eps=None, use_mean=False):
+    """VAE.forward (vaes.py:102-129) -> (x_hat, z, mu, logvar); noise injected like psvae_forward."""
+    mu, logvar = encode(sd, hparams, x)
+    z = mu if use_mean else eps * torch.exp(logvar) + mu
+    return decode(sd, hparams, z), z, mu, logvar
+
+
+def vae_loss(sd, hparams, x, eps, masks=None, beta=None, chunk_size=200, want_grads=True):
+    """VAE.loss (vaes.py:131-208): -ll + beta * KL per chunk."""
+    beta = hparams['vae.beta'] if beta is None else beta
+    params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
+    vals = {'loss': 0.0, 'loss_ll': 0.0, 'loss_kl': 0.0, 'loss_mse': 0.0}
+    n_pix = int(np.prod(x.shape[1:]))
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in = x[b:e]
+        x_hat, _, mu, logvar = vae_forward(params, hparams, x_in, eps[b:e])
+        ll = gaussian_ll(x_in, x_hat, None if masks is None else masks[b:e])
+        kl = kl_div_to_std_normal(mu, logvar)
+        loss = -ll + beta * kl
+        if want_grads:
+            loss.backward()
+        bs = e - b
+        vals['loss'] += loss.item() * bs
+        vals['loss_ll'] += ll.item() * bs
+        vals['loss_kl'] += kl.item() * bs
+        vals['loss_mse'] += gaussian_ll_to_mse(ll.item(), n_pix) * bs
+    for k in vals:
+        vals[k] /= x.shape[0]
+    vals['beta'] = beta
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return vals, grads
+
+
+def btcvae_loss(sd, hparams, x, eps, masks=None, beta=None, kl_anneal=1.0, chunk_size=200, want_grads=True):
+    """BetaTCVAE.loss (vaes.py:411-503): -ll + kl * MI + beta * TC + kl * DWKL per chunk;
+    'loss_mse' reproduces the running-sum quirk of vaes.py:490-491."""
+    beta = hparams['beta_tcvae.beta'] if beta is None else beta
+    params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
+    keys = ['loss', 'loss_ll', 'loss_mi', 'loss_tc', 'loss_dwkl']
+    vals = {k: 0.0 for k in keys}
+    vals['loss_mse'] = 0.0
+    n_pix = int(np.prod(x.shape[1:]))
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in = x[b:e]
+        x_hat, z, mu, logvar = vae_forward(params, hparams, x_in, eps[b:e])
+        t = {}
+        t['loss_ll'] = gaussian_ll(x_in, x_hat, None if masks is None else masks[b:e])
+        t['loss_mi'], t['loss_tc'], t['loss_dwkl'] = decomposed_kl(z, mu, logvar)
+        t['loss'] = -t['loss_ll'] + kl_anneal * t['loss_mi'] + beta * t['loss_tc'] + kl_anneal * t['loss_dwkl']
+        if want_grads:
+            t['loss'].backward()
+        bs = e - b
+        for k in keys:
+            vals[k] += t[k].item() * bs
+        vals['loss_mse'] += gaussian_ll_to_mse(vals['loss_ll'] / bs, n_pix) * bs
+    for k in vals:
+        vals[k] /= x.shape[0]
+    vals['beta'] = beta
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return vals, grads
+
+
+# ------------------------------------------------------------------------------------------------
 # synthetic parameters with the reference's shapes/names (torch default inits)
 # ------------------------------------------------------------------------------------------------
 
@@ -242,6 +308,12 @@ def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class
     hp['model_class'] = model_class
     hp['model_type'] = 'conv'
     hp['fit_sess_io_layers'] = False
+    if model_class == 'vae':
+        hp.update({'vae.beta': 2.0, 'vae.beta_anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
+    if model_class == 'beta-tcvae':
+        # BetaTCVAE.__init__ runs VAE.__init__, which reads vae.beta as well (vaes.py:100, 389)
+        hp.update({'beta_tcvae.beta': 5.0, 'beta_tcvae.beta_anneal_epochs': 0, 'vae.beta': 1.0,
+                   'vae.beta_anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
     if model_class == 'ps-vae':
         hp.update({'n_labels': n_labels, 'ps_vae.alpha': 1000, 'ps_vae.beta': 10,
                    'ps_vae.anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})

@@ -40,6 +40,8 @@ CAE_CASES = [
     ('ae_128x128x1_l12_b3', 1, 128, 128, 12, 3, 'ae', 0, 200),   # C2 geometry, tiny batch
     ('psvae_128x128x2_l16_b5', 2, 128, 128, 16, 5, 'ps-vae', 4, 3),  # C3 geometry, 2 chunks
     ('psvae_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'ps-vae', 3, 200),
+    ('vae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'vae', 0, 4),             # 2 chunks, beta = 2
+    ('btcvae_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'beta-tcvae', 0, 4),   # 2 chunks, beta = 5
 ]
 
 
@@ -50,6 +52,8 @@ def synth_inputs(case):
     out = {'x': x}
     if mc == 'ps-vae':
         out['labels'] = torch.randn(b, nl, generator=g)
+        out['eps'] = torch.randn(b, L, generator=g)
+    if mc in ('vae', 'beta-tcvae'):
         out['eps'] = torch.randn(b, L, generator=g)
     out['masks'] = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
     return out
@@ -88,6 +92,49 @@ def run_reference(case):
         assert abs(lo['loss'] - float(res['loss'])) < 1e-7, name
         for k, gref in go.items():
             assert torch.allclose(gref, res['grad.' + k], atol=1e-6, rtol=1e-4), (name, k)
+    elif mc in ('vae', 'beta-tcvae'):
+        from behavenet.models import VAE, BetaTCVAE
+        model = (VAE if mc == 'vae' else BetaTCVAE)(hp_ref)
+        model.load_state_dict(sd)
+        model.eval()
+        eps_all = inp['eps']
+        state = {'pos': 0}
+        orig = torch.randn_like
+
+        def fake_randn_like(t, *a, **k):
+            n = t.shape[0]
+            e = eps_all[state['pos']:state['pos'] + n]
+            state['pos'] += n
+            return e.to(t.dtype)
+        vaes.torch.randn_like = fake_randn_like
+        try:
+            with torch.no_grad():
+                state['pos'] = 0
+                x_hat, z, mu, logvar = model(inp['x'])
+            res.update(x_hat=x_hat, z=z, mu=mu, logvar=logvar)
+            model.curr_epoch = 1
+            model.zero_grad()
+            state['pos'] = 0
+            loss = model.loss({'images': inp['x'][None]}, accumulate_grad=True, chunk_size=chunk)
+        finally:
+            vaes.torch.randn_like = orig
+        for k, v in loss.items():
+            res['loss.' + k] = torch.tensor(float(v), dtype=torch.float64)
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                res['grad.' + k] = p.grad.clone()
+        # pin the restatement
+        o = co.vae_forward(sd, hp, inp['x'], inp['eps'])
+        for a, bref in zip(o, (x_hat, z, mu, logvar)):
+            assert torch.allclose(a, bref, atol=2e-5), name
+        fn = co.vae_loss if mc == 'vae' else co.btcvae_loss
+        lo, go = fn(sd, hp, inp['x'], inp['eps'], chunk_size=chunk)
+        for k in lo:
+            ref = float(res['loss.' + k])
+            assert abs(lo[k] - ref) <= 1e-5 * max(1.0, abs(ref)), (name, k, lo[k], ref)
+        for k, gref in go.items():
+            gr = res['grad.' + k]
+            assert torch.allclose(gref, gr, atol=1e-4 * float(gr.abs().max()) + 1e-7), (name, k)
     else:
         model = PSVAE(hp_ref)
         model.load_state_dict(sd)
@@ -175,11 +222,15 @@ def gen_arhmm():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for case in CAE_CASES:
+        if only and case[0] not in only:
+            continue
         res = run_reference(case)
         np.savez_compressed(os.path.join(GOLD, case[0] + '.npz'), **compact(res))
         print('wrote', case[0], {k: tuple(v.shape) for k, v in list(res.items())[:3]})
-    gen_arhmm()
+    if not only:
+        gen_arhmm()
 
 
 if __name__ == '__main__':

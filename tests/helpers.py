@@ -31,12 +31,14 @@ def golden_compare(gold, key, actual, rtol, atol, check_sum=True):
     assert abs(np.abs(flat.astype(np.float64)).sum() - sabs) <= atol * n + rtol * sabs, key
 
 
-def synth_inputs(c, h, w, L, b, n_labels=0, seed=1234):
+def synth_inputs(c, h, w, L, b, n_labels=0, seed=1234, variational=False):
     """Same draws as oracle/gen_golden.py::synth_inputs."""
     g = torch.Generator().manual_seed(seed)
     out = {'x': torch.rand(b, c, h, w, generator=g)}
     if n_labels:
         out['labels'] = torch.randn(b, n_labels, generator=g)
+        out['eps'] = torch.randn(b, L, generator=g)
+    elif variational:
         out['eps'] = torch.randn(b, L, generator=g)
     out['masks'] = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
     return out

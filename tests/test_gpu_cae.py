@@ -122,6 +122,46 @@ def test_psvae_forward_and_loss_match_reference_goldens(case, tc_mode):
         compare_grad(gold, key, p.grad, tc_mode, t, factor=4.0)
 
 
+VAE_CASES = {
+    'vae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 'vae', 4),
+    'btcvae_32x32x2_l8_b6': (2, 32, 32, 8, 6, 'beta-tcvae', 4),
+}
+
+
+@pytest.mark.parametrize('tc_mode', [0, 1])
+@pytest.mark.parametrize('case', list(VAE_CASES))
+def test_vae_family_forward_and_loss_match_reference_goldens(case, tc_mode):
+    """VAE / beta-TC-VAE (section 8f rank 4) on the same kernels: forward tuple, loss dict and every
+    parameter gradient against the goldens written by the reference classes."""
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import VAE, BetaTCVAE
+    c, h, w, L, b, mc, chunk = VAE_CASES[case]
+    hp = co.make_hparams(c, h, w, L, mc)
+    sd = co.init_state_dict(hp, seed=0)
+    model = (VAE if mc == 'vae' else BetaTCVAE)(copy.deepcopy(hp))
+    model.load_state_dict(sd)
+    model.to('cuda')
+    _lib.lib().bn_set_tensor_core_mode(tc_mode)
+    inp = synth_inputs(c, h, w, L, b, variational=True)
+    gold = load_golden(case)
+    t = tols(tc_mode)
+    x, eps = inp['x'].cuda(), inp['eps'].cuda()
+    with torch.no_grad():
+        x_hat, z, mu, logvar = model(x, eps=eps)
+    golden_compare(gold, 'x_hat', x_hat, rtol=t['xhat'], atol=t['xhat'])
+    for key, val in (('z', z), ('mu', mu), ('logvar', logvar)):
+        assert rel_err(val, gold[key]) < t['z'] * 10, key
+    model.curr_epoch = 1
+    model.zero_grad()
+    out = model.loss({'images': x[None]}, accumulate_grad=True, chunk_size=chunk, eps=eps)
+    for k in [k[5:] for k in gold if k.startswith('loss.')]:
+        ref = float(gold['loss.' + k])
+        assert abs(out[k] - ref) <= 10 * t['loss'] * max(1.0, abs(ref)), (k, out[k], ref)
+    for name, p in model.named_parameters():
+        compare_grad(gold, 'grad.' + name, p.grad, tc_mode, t, factor=4.0)
+    _lib.lib().bn_set_tensor_core_mode(1)
+
+
 @pytest.mark.parametrize('tc_mode', [0, 1])
 def test_ae_c2_batch_matches_oracle(tc_mode):
     """BASELINE config C2 geometry at a batch the CPU oracle finishes in seconds (B=24, chunks of

@@ -57,6 +57,30 @@ def test_psvae_protocol():
     assert model3.beta_vals[0] == 0 and model3.kl_anneal_vals[3] == 1
 
 
+def test_vae_family_protocol():
+    """VAE / BetaTCVAE keep the reference's constructor side effects, state_dict names, annealing
+    tables (vaes.py:52-100, 380-409) and are deep-copyable / picklable like the AE."""
+    from behavenet_b200.models import VAE, BetaTCVAE
+    for mc, cls in (('vae', VAE), ('beta-tcvae', BetaTCVAE)):
+        hp = co.make_hparams(1, 64, 48, 6, mc)
+        model = cls(copy.deepcopy(hp))
+        assert model.hparams['variational'] is True
+        assert set(model.state_dict().keys()) == set(co.init_state_dict(hp, seed=0).keys())
+        assert model.beta_vals.shape == (hp['max_n_epochs'] + 1,)
+        copy.deepcopy(model)
+        pickle.loads(pickle.dumps(model))
+        with pytest.raises(RuntimeError):           # no CPU path
+            model.loss({'images': torch.rand(1, 2, 1, 64, 48)})
+    hp = dict(co.make_hparams(1, 64, 48, 6, 'beta-tcvae'))
+    hp['beta_tcvae.beta_anneal_epochs'] = 5
+    m = BetaTCVAE(hp)
+    assert m.beta_vals[0] == 0 and m.kl_anneal_vals[4] == 1 and m.beta_vals[-1] == hp['beta_tcvae.beta']
+    hp = dict(co.make_hparams(1, 64, 48, 6, 'vae'))
+    hp['model_type'] = 'linear'
+    with pytest.raises(NotImplementedError):
+        VAE(hp)
+
+
 @pytest.mark.parametrize('key,val', [('ae_batch_norm', True), ('fit_sess_io_layers', True),
                                      ('ae_decoding_last_FF_layer', True), ('ae_padding_type', 'valid')])
 def test_unsupported_variants_raise_instead_of_falling_back(key, val):

@@ -57,6 +57,35 @@ def test_oracle_reproduces_reference_goldens(case):
             golden_compare(gold, key, g, rtol=1e-3, atol=1e-4 * scale + 1e-9)
 
 
+VAE_CASES = {
+    'vae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 'vae', 4),
+    'btcvae_32x32x2_l8_b6': (2, 32, 32, 8, 6, 'beta-tcvae', 4),
+}
+
+
+@pytest.mark.parametrize('case', list(VAE_CASES))
+def test_oracle_reproduces_reference_vae_goldens(case):
+    """VAE (vaes.py:38-208) and beta-TC-VAE (vaes.py:367-503) goldens written by the reference classes."""
+    c, h, w, L, b, mc, chunk = VAE_CASES[case]
+    gold = load_golden(case)
+    hp = co.make_hparams(c, h, w, L, mc)
+    sd = co.init_state_dict(hp, seed=0)
+    inp = synth_inputs(c, h, w, L, b, variational=True)
+    torch.set_num_threads(8)
+    out = co.vae_forward(sd, hp, inp['x'], inp['eps'])
+    for key, val in zip(('x_hat', 'z', 'mu', 'logvar'), out):
+        golden_compare(gold, key, val, rtol=1e-4, atol=2e-5)
+    fn = co.vae_loss if mc == 'vae' else co.btcvae_loss
+    loss, grads = fn(sd, hp, inp['x'], inp['eps'], chunk_size=chunk)
+    for k, v in loss.items():
+        ref = float(gold['loss.' + k])
+        assert abs(v - ref) <= 1e-5 * max(1.0, abs(ref)), k
+    for k, g in grads.items():
+        key = 'grad.' + k
+        scale = float(np.abs(gold[key + '#val'] if key + '#val' in gold else gold[key]).max())
+        golden_compare(gold, key, g, rtol=1e-3, atol=1e-4 * scale + 1e-9)
+
+
 def test_mse_closed_forms():
     x = torch.rand(5, 3)
     assert co.mse(x, x) == 0

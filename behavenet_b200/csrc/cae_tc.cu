@@ -1033,6 +1033,29 @@ __device__ __forceinline__ void tma_tile_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// ---- thread-block-cluster helpers: weight tiles are identical for every tile of a layer, so the
+// CTAs of a cluster each fetch 1/csz of them and TMA-multicast into all members' shared memory ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_tile_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
 // One MMA group = one halo window (tap offset) shared by `ncls` residue classes whose accumulators
 // sit in adjacent TMEM column blocks col0 .. col0 + ncls - 1: a single tcgen05.mma of N = ncls * NB
 // against the stacked weight tiles of those classes.  Small-N MMAs are bound by the 4 KB A-operand
@@ -1050,6 +1073,7 @@ struct HaloArgs {
   int ngroups;
   int tiles_per_frame;
   long long total_tiles;     // tiles_per_frame * frames
+  int csz;                   // cluster size (1, 2 or 4): CTAs that share the weight-tile stream
   int pos[4];                // TMEM column block of class c
   int Hm[4], Wm[4], oy0[4], ox0[4];
   HaloGroup g[HALO_MAXG];
@@ -1100,7 +1124,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(smem_u32(b_full + s), 1);
-      mbar_init(smem_u32(b_empty + s), 1);
+      mbar_init(smem_u32(b_empty + s), h.csz);      // released by the MMAs of every CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(a_full + s), 1);
@@ -1114,18 +1138,26 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const int csz = h.csz;
+  const uint32_t crank = csz > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
+  if (csz > 1) cluster_sync_all();      // every member's barriers exist before any remote arrive / copy
   const uint32_t tmem_base = *tmem_ptr;
   const int Ci = a.Ci;
   const int nchunk = Ci / BK;
   const uint32_t smem_base = smem_u32(smem);
   const long long total = h.total_tiles;
+  // tile sequence: clusters take groups of csz consecutive tiles, member r the r-th of each group, so
+  // all members run the same number of iterations (total_tiles is a multiple of csz)
+  const long long t_first = (long long)(blockIdx.x / csz) * csz + crank;
+  const long long t_step = (long long)(gridDim.x / csz) * csz;
 
   if (warp < 4) {
     // ======================= epilogue ============================================================
     float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
     const int elane = tid & 31;
     int ti = 0;
-    for (long long T = blockIdx.x; T < total; T += gridDim.x, ++ti) {
+    for (long long T = t_first; T < total; T += t_step, ++ti) {
       const int f = (int)(T / h.tiles_per_frame);
       const int blk = (int)(T - (long long)f * h.tiles_per_frame);
       const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
@@ -1162,7 +1194,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     // ======================= MMA issuer ==========================================================
     if ((tid & 31) == 0) {
       int ai = 0, bi = 0, ti = 0;
-      for (long long T = blockIdx.x; T < total; T += gridDim.x, ++ti) {
+      for (long long T = t_first; T < total; T += t_step, ++ti) {
         const int buf = PERSIST ? (ti & 1) : 0;
         if (ti >= 2) {
           mbar_wait(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
@@ -1190,7 +1222,8 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
               const uint64_t bd = make_desc_sw128(sb + k * 32);
               umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
             }
-            umma_commit(smem_u32(b_empty + stage));
+            if (csz > 1) umma_commit_mc(smem_u32(b_empty + stage), cmask);
+            else umma_commit(smem_u32(b_empty + stage));
           }
           umma_commit(smem_u32(a_empty + slot));
         }
@@ -1201,7 +1234,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   } else {
     // ======================= TMA producer: halo chunks and weight-tile groups ====================
     if ((tid & 31) == 0) {
-      int ai = 0, bi = 0;
+      int ai = 0, bi = 0, bt = 0;
       // chunk sequence number q -> (tile, chunk); the halo of chunk q + 1 is requested before the
       // weight tiles of chunk q so that it lands while chunk q is being multiplied
       auto load_halo = [&](long long T, int c, int q) {
@@ -1214,20 +1247,24 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
         mbar_expect_tx(bar, (uint32_t)HALO_ABYTES);
         tma_tile_4d(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a, bar, c * BK, bx * 8 + h.lo_x, by * 16 + h.lo_y, f);
       };
-      if ((long long)blockIdx.x < total) load_halo(blockIdx.x, 0, 0);
-      for (long long T = blockIdx.x; T < total; T += gridDim.x) {
+      if (t_first < total) load_halo(t_first, 0, 0);
+      for (long long T = t_first; T < total; T += t_step) {
         for (int c = 0; c < nchunk; ++c, ++ai) {
           // next chunk in sequence
           if (c + 1 < nchunk) load_halo(T, c + 1, ai + 1);
-          else if (T + gridDim.x < total) load_halo(T + gridDim.x, 0, ai + 1);
+          else if (T + t_step < total) load_halo(T + t_step, 0, ai + 1);
           for (int gi = 0; gi < h.ngroups; ++gi, ++bi) {
             const int stage = bi % NST;
             if (bi >= NST) mbar_wait(smem_u32(b_empty + stage), ((bi / NST) - 1) & 1);
             const uint32_t bar = smem_u32(b_full + stage);
             const HaloGroup g = h.g[gi];
             mbar_expect_tx(bar, (uint32_t)(g.ncls * S::B_TILE));
-            for (int j = 0; j < g.ncls; ++j)
-              tma_tile_2d(smem_base + stage * S::B_BYTES + j * S::B_TILE, &maps.b, bar, g.wt[j] * Ci + c * BK, 0);
+            for (int j = 0; j < g.ncls; ++j) {
+              const uint32_t dst = smem_base + stage * S::B_BYTES + j * S::B_TILE;
+              if (csz == 1) tma_tile_2d(dst, &maps.b, bar, g.wt[j] * Ci + c * BK, 0);
+              else if (((bt + j) % csz) == (int)crank) tma_tile_2d_mc(dst, &maps.b, bar, g.wt[j] * Ci + c * BK, 0, cmask);
+            }
+            bt += g.ncls;
           }
         }
       }
@@ -1236,6 +1273,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();      // no member leaves while peers may still multicast into it
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc<NCOLS>(tmem_base);
@@ -1264,7 +1302,7 @@ bool encode_tiled_4d(CUtensorMap* map, const float* p, int N, int H, int W, int 
 }
 
 template <int NB, int NST, bool PERSIST>
-int launch_halo(const HaloMaps& maps, const HaloArgs& h, cudaStream_t st) {
+int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
   using S = HaloSmem<NB, NST, PERSIST>;
   auto kern = dgrad_halo_kernel<NB, NST, PERSIST>;
   static bool configured = false;
@@ -1274,10 +1312,32 @@ int launch_halo(const HaloMaps& maps, const HaloArgs& h, cudaStream_t st) {
   }
   static_assert(2 * (S::TOTAL + 1024) <= 227 * 1024, "two CTAs per SM");
   static_assert(2 * (PERSIST ? 2 : 1) * 4 * NB <= 512, "TMEM columns of two resident CTAs");
+  // Cluster multicast of the weight tiles is implemented and parity-tested (BN_HALO_CLUSTER=2|4) but
+  // measured SLOWER on B200 (C_out=32: 128 / 135 / 213 us at cluster size 1 / 2 / 4): the weight
+  // stream is not what bounds this kernel, and the cluster couples the members' pipelines.  Default off.
+  static const int max_csz = [] { const char* e = getenv("BN_HALO_CLUSTER"); return e ? atoi(e) : 1; }();
+  int csz = 1;
+  for (int c = 4; c >= 2; c >>= 1)
+    if (c <= max_csz && h.total_tiles % c == 0) { csz = c; break; }
   long long grid = PERSIST ? 2 * 148 : h.total_tiles;
   if (grid > h.total_tiles) grid = h.total_tiles;
-  if (!PERSIST && grid > 0x7fffffffLL) return 1;
-  kern<<<(unsigned)grid, HALO_THREADS, S::TOTAL, st>>>(maps, h);
+  grid -= grid % csz;
+  if (grid <= 0 || grid > 0x7fffffffLL) return 1;
+  h.csz = csz;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(HALO_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csz;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BN_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, (const HaloArgs&)h));
   BN_LAUNCHED();
   return 0;
 }

@@ -365,6 +365,13 @@ def run_ours(args):
         return float(logZ.sum().item()), Ezz.sum(0).cpu()
     hmm_e2e = float(np.median(timed(estep_e2e, 3, 1)))
 
+    # ---------------- PS-VAE (C3): 128x128x2, 16 latents, 4 labels, 512 frames per GPU (weak scaling)
+    psvae = None
+    try:
+        psvae = bench_psvae(device, world, rank, args)
+    except Exception as exc:                     # the headline line must not depend on this extra leg
+        psvae = {'error': repr(exc)[:200]}
+
     if rank != 0:
         return
     cpu = cpu_baselines(hp) if world == 1 else None
@@ -418,11 +425,64 @@ def run_ours(args):
                                  'are the T-step serial chain and the 3-pass emission GEMM, not HBM' % peak_src},
         },
     }
+    line['psvae'] = psvae
     if cpu is not None:
         line['cpu_baseline'] = cpu['cae']
         line['arhmm']['cpu_baseline'] = cpu['arhmm']
     _OUT.write(json.dumps(line) + '\n')
     _OUT.flush()
+
+
+PSVAE_GFLOP_PER_FRAME = 2.111          # train step, 128x128x2, 16 latents
+PSVAE_BATCH_PER_GPU = 512
+
+
+def bench_psvae(device, world, rank, args):
+    """Config C3: one PSVAE.loss(accumulate_grad=True) per step on 512 frames per GPU (chunks of 200;
+    whole chunks are sharded over ranks, so every rank gets its own 512-frame batch slice)."""
+    import copy
+    from behavenet_b200.models import PSVAE
+    from oracle import cae_oracle as co          # seeded synthetic parameters only
+    np.random.seed(0)
+    hp = co.make_hparams(2, 128, 128, 16, 'ps-vae', 4)
+    model = PSVAE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.to(device)
+    model.curr_epoch = 1
+    # 600 frames per rank = three whole reference chunks of 200 per rank would change the config;
+    # keep 512 per GPU and let the chunk sharding split [200, 200, 112] x world over the ranks
+    B = PSVAE_BATCH_PER_GPU * world
+    model.data_parallel = world > 1
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 2, 128, 128, generator=g).to(device)
+    y = torch.randn(B, 4, generator=g).to(device)
+    eps = torch.randn(B, 16, generator=g).to(device)
+    data = {'images': x[None], 'labels': y[None]}
+
+    def step():
+        model.zero_grad()
+        model.invalidate_packed()
+        model.loss(data, accumulate_grad=True, eps=eps)
+
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = dist_max(e0.elapsed_time(e1), device) / steps
+    value = B / (ms * 1e-3)
+    return {'metric': 'PS-VAE train frames/sec (C3: 128x128x2, 16 latents, 4 labels, fwd+loss+bwd)',
+            'value': value, 'unit': 'frames/s', 'ms_per_step': ms, 'steps': steps, 'global_batch': B,
+            'tflops_per_gpu': value * PSVAE_GFLOP_PER_FRAME * 1e-3 / world,
+            'note': 'includes sklearn r2_score on the host and the per-chunk latent-block launches, as the '
+                    'reference loss() does; frames resident in HBM'}
 
 
 def cpu_cae_step(hp, batch, threads):

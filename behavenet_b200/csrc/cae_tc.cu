@@ -231,22 +231,12 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      float v[32];
       if (a.ksplit > 1) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
         const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
-        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, v, tile, elane);
+        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, r, nullptr, BN_ACT_NONE, tile, elane);
       } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          float x = __uint_as_float(r[q]);
-          if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q);
-          if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-          else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-          v[q] = x;
-        }
-        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
+        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
+                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane);
       }
     }
     tc_fence_before();
@@ -432,22 +422,12 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      float v[32];
       if (a.ksplit > 1) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
         const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
-        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, v, tile, elane);
+        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, r, nullptr, BN_ACT_NONE, tile, elane);
       } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          float x = __uint_as_float(r[q]);
-          if (a.bias) x += __ldg(a.bias + n0 + j * 32 + q);
-          if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-          else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-          v[q] = x;
-        }
-        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
+        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
+                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane);
       }
     }
     tc_fence_before();
@@ -757,10 +737,8 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const WgTcArgs a) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      float v[32];
-#pragma unroll
-      for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
-      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, v, tile, tid & 31);
+      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, r, nullptr, BN_ACT_NONE, tile,
+                        tid & 31);
     }
     tc_fence_before();
   } else {
@@ -892,10 +870,8 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      float v[32];
-#pragma unroll
-      for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
-      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, v, tile, tid & 31);
+      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, r, nullptr, BN_ACT_NONE, tile,
+                        tid & 31);
     }
     tc_fence_before();
   } else {
@@ -1056,6 +1032,18 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask) : "memory");
 }
 
+// per-role phase timestamps of CTA 0 (debug aid, BN_HALO_DBG=1; read back with bn_debug_halo_times)
+__device__ long long g_halo_dbg[8 * 8];
+__device__ __forceinline__ long long dbg_clock() {
+  long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+#define HALO_STAMP(tile, slot)                                                                      \
+  do {                                                                                              \
+    if (h.dbg && blockIdx.x == 0 && (tile) < 8) g_halo_dbg[(tile) * 8 + (slot)] = dbg_clock();      \
+  } while (0)
+
 // One MMA group = one halo window (tap offset) shared by `ncls` residue classes whose accumulators
 // sit in adjacent TMEM column blocks col0 .. col0 + ncls - 1: a single tcgen05.mma of N = ncls * NB
 // against the stacked weight tiles of those classes.  Small-N MMAs are bound by the 4 KB A-operand
@@ -1074,6 +1062,7 @@ struct HaloArgs {
   int tiles_per_frame;
   long long total_tiles;     // tiles_per_frame * frames
   int csz;                   // cluster size (1, 2 or 4): CTAs that share the weight-tile stream
+  int dbg;
   int pos[4];                // TMEM column block of class c
   int Hm[4], Wm[4], oy0[4], ox0[4];
   HaloGroup g[HALO_MAXG];
@@ -1163,8 +1152,10 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
       const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
       const int ym = by * 16 + (tid >> 3), xm = bx * 8 + (tid & 7);
       const int buf = PERSIST ? (ti & 1) : 0;
+      if (tid == 0) HALO_STAMP(ti, 3);
       mbar_wait(smem_u32(acc_full + buf), (ti >> 1) & 1);
       tc_fence_after();
+      if (tid == 0) HALO_STAMP(ti, 4);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
@@ -1173,22 +1164,20 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
 #pragma unroll 1
         for (int j = 0; j < NB / 32; ++j) {
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * ACC_COLS + h.pos[c] * NB + j * 32, r);
-          tmem_ld_wait();
-          float v[32];
+          if (!(h.dbg & 8)) {
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * ACC_COLS + h.pos[c] * NB + j * 32, r);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            float x = __uint_as_float(r[q]);
-            if (a.bias) x += __ldg(a.bias + j * 32 + q);
-            if (a.act == BN_ACT_LEAKY) x = x > 0.f ? x : BN_LEAK * x;
-            else if (a.act == BN_ACT_SIGMOID) x = 1.f / (1.f + expf(-x));
-            v[q] = x;
+            for (int q = 0; q < 32; ++q) r[q] = 0u;
           }
-          warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, v, tile, elane);
+          warp_store_rows32(a.out, a.dact, BN_LEAK, (rvalid && !(h.dbg & 4)) ? obase + j * 32 : -1, r,
+                            a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane);
         }
       }
       tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
       mbar_arrive(smem_u32(acc_empty + buf));
+      if (tid == 0) HALO_STAMP(ti, 5);
     }
   } else if (warp == 4) {
     // ======================= MMA issuer ==========================================================
@@ -1196,10 +1185,12 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
       int ai = 0, bi = 0, ti = 0;
       for (long long T = t_first; T < total; T += t_step, ++ti) {
         const int buf = PERSIST ? (ti & 1) : 0;
+        HALO_STAMP(ti, 0);
         if (ti >= 2) {
           mbar_wait(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
           tc_fence_after();
         }
+        HALO_STAMP(ti, 1);
         for (int c = 0; c < nchunk; ++c, ++ai) {
           const int slot = ai & 1;
           mbar_wait(smem_u32(a_full + slot), (ai >> 1) & 1);
@@ -1220,7 +1211,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
               // starts on any 128-byte row of the TMA-written halo needs no descriptor base offset
               const uint64_t ad = make_desc_sw128_sbo(arow + k * 32, HALO_W * 128);
               const uint64_t bd = make_desc_sw128(sb + k * 32);
-              umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
+              if (!(h.dbg & 2)) umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
             }
             if (csz > 1) umma_commit_mc(smem_u32(b_empty + stage), cmask);
             else umma_commit(smem_u32(b_empty + stage));
@@ -1228,6 +1219,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
           umma_commit(smem_u32(a_empty + slot));
         }
         umma_commit(smem_u32(acc_full + buf));
+        HALO_STAMP(ti, 2);
       }
     }
     __syncwarp();
@@ -1310,8 +1302,8 @@ int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  static_assert(2 * (S::TOTAL + 1024) <= 227 * 1024, "two CTAs per SM");
-  static_assert(2 * (PERSIST ? 2 : 1) * 4 * NB <= 512, "TMEM columns of two resident CTAs");
+  constexpr int CTAS_PER_SM = (2 * (S::TOTAL + 1024) <= 227 * 1024 && 2 * (PERSIST ? 2 : 1) * 4 * NB <= 512) ? 2 : 1;
+  static_assert(S::TOTAL + 1024 <= 227 * 1024, "shared memory per CTA");
   // Cluster multicast of the weight tiles is implemented and parity-tested (BN_HALO_CLUSTER=2|4) but
   // measured SLOWER on B200 (C_out=32: 128 / 135 / 213 us at cluster size 1 / 2 / 4): the weight
   // stream is not what bounds this kernel, and the cluster couples the members' pipelines.  Default off.
@@ -1319,11 +1311,13 @@ int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
   int csz = 1;
   for (int c = 4; c >= 2; c >>= 1)
     if (c <= max_csz && h.total_tiles % c == 0) { csz = c; break; }
-  long long grid = PERSIST ? 2 * 148 : h.total_tiles;
+  long long grid = PERSIST ? CTAS_PER_SM * 148 : h.total_tiles;
   if (grid > h.total_tiles) grid = h.total_tiles;
   grid -= grid % csz;
   if (grid <= 0 || grid > 0x7fffffffLL) return 1;
   h.csz = csz;
+  static const int dbg = [] { const char* e = getenv("BN_HALO_DBG"); return e ? atoi(e) : 0; }();
+  h.dbg = dbg;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -1441,6 +1435,8 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream
   h.tiles_per_frame = h.tiles_x * bn_cdiv(Hm, 16);
   h.total_tiles = (long long)h.tiles_per_frame * a.n;
   HaloMaps local = *hm;
+  static const int deep = [] { const char* e = getenv("BN_HALO_DEEP"); return e ? atoi(e) : 0; }();
+  if (a.Co == 32 && deep == 1) return launch_halo<32, 10, true>(local, h, st);      // one CTA per SM, 160 KB weight ring
   if (a.Co == 32) return launch_halo<32, 3, true>(local, h, st);
   return launch_halo<64, 2, false>(local, h, st);
 }
@@ -1458,7 +1454,9 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   if (in.sc != 1 || in.C % BK != 0 || in.sx != in.C || in.sy != (long long)in.W * in.C ||
       in.sn != (long long)in.H * in.W * in.C)
     return 1;
-  if (((uintptr_t)in.p & 15) || ((uintptr_t)out & 15) || ((uintptr_t)wt & 15) || (dact && ((uintptr_t)dact & 15))) return 1;
+  if (((uintptr_t)in.p & 15) || ((uintptr_t)out & 15) || ((uintptr_t)wt & 15) || (dact && ((uintptr_t)dact & 15)) ||
+      (bias && ((uintptr_t)bias & 15)))
+    return 1;
   const int bn = Co >= 256 ? 256 : Co;
   if (Co != 32 && Co != 64 && Co != 128 && Co != 256 && Co != 512) return 1;
   const long long M = (long long)n * maxM;
@@ -1598,3 +1596,10 @@ int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g
   return bn_launch_wgrad_reduce(partial, (int)splits, Ktot, Cs, g.Cb, g.k * g.k, g.d_fprop, grad, st);
 }
 
+
+// debug aid: phase timestamps (ns, %globaltimer) of CTA 0's first 8 tiles in the last halo-kernel launch
+// run with BN_HALO_DBG=1: per tile [mma loop top, acc buffer free, mmas issued, epi wait, acc ready, epi done]
+extern "C" int bn_debug_halo_times(long long* h_out) {
+  BN_CUDA(cudaMemcpyFromSymbol(h_out, g_halo_dbg, sizeof(long long) * 64));
+  return 0;
+}

@@ -75,39 +75,58 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Epilogue store of a 32-row x 32-column fp32 tile held one row per lane (the tcgen05.ld 32x32b
+// Epilogue of a 32-row x 32-column fp32 accumulator tile held one row per lane (the tcgen05.ld 32x32b
 // register layout).  Writing it straight from that layout makes every STG.128 touch 32 different
-// 128-byte lines (16 bytes each): the LSU serialises them and the epilogue, not the MMAs, bounds the
-// kernel.  Instead the warp transposes through a 4 KB shared-memory tile (XOR-swizzled, conflict-free
-// both ways) so that each store instruction writes four whole 128-byte rows.
-//   idx  : element offset of this lane's row segment in `out` (and `dact`), or < 0 for an invalid row
-//   dact : optional activation whose sign selects the LeakyReLU derivative (1 or leak) per element
+// 128-byte lines, and applying bias / activation there costs 32 dependent scalar loads per lane.
+// Instead the warp transposes the RAW accumulators through a 4 KB shared-memory tile (XOR-swizzled,
+// conflict-free both ways); afterwards a lane owns 4 fixed columns of 8 rows, so the bias is one
+// float4 per lane, all eight LDS / mask loads are issued before they are consumed, and each store
+// instruction writes four whole 128-byte rows.
+//   idx   : element offset of this lane's row segment in `out` (and `dact`), or < 0 for an invalid row
+//   bias  : 32 per-column biases of this tile (16-byte aligned) or nullptr
+//   act   : 0 none, 1 LeakyReLU(leak), 2 sigmoid
+//   dact  : optional activation whose sign selects the LeakyReLU derivative (1 or leak) per element
 __device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const float* __restrict__ dact, float leak,
-                                                  long long idx, const float (&v)[32], float* tile, int lane) {
+                                                  long long idx, const uint32_t (&r)[32],
+                                                  const float* __restrict__ bias, int act, float* tile, int lane) {
 #pragma unroll
   for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(tile + lane * 32 + ((c ^ (lane & 7)) << 2)) =
-        make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    *reinterpret_cast<uint4*>(tile + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+        make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
   __syncwarp();
   const int sub = lane >> 3, chunk = lane & 7;
+  const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
   const int lo = (int)(unsigned long long)idx, hi = (int)((unsigned long long)idx >> 32);
+  long long ridx[8];
+  float4 x[8], d[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + sub;
     const unsigned rlo = (unsigned)__shfl_sync(0xffffffffu, lo, row);
     const int rhi = __shfl_sync(0xffffffffu, hi, row);
-    const long long ridx = (long long)(((unsigned long long)(unsigned)rhi << 32) | rlo);
-    float4 x = *reinterpret_cast<const float4*>(tile + row * 32 + ((chunk ^ (row & 7)) << 2));
-    if (ridx >= 0) {
-      if (dact) {
-        const float4 d = __ldg(reinterpret_cast<const float4*>(dact + ridx) + chunk);
-        x.x *= d.x > 0.f ? 1.f : leak;
-        x.y *= d.y > 0.f ? 1.f : leak;
-        x.z *= d.z > 0.f ? 1.f : leak;
-        x.w *= d.w > 0.f ? 1.f : leak;
-      }
-      *(reinterpret_cast<float4*>(out + ridx) + chunk) = x;
+    ridx[i] = (long long)(((unsigned long long)(unsigned)rhi << 32) | rlo);
+    x[i] = *reinterpret_cast<const float4*>(tile + row * 32 + ((chunk ^ (row & 7)) << 2));
+  }
+  if (dact) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      d[i] = ridx[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(dact + ridx[i]) + chunk) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v[4] = {x[i].x + b4.x, x[i].y + b4.y, x[i].z + b4.z, x[i].w + b4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (act == 1) v[e] = v[e] > 0.f ? v[e] : leak * v[e];
+      else if (act == 2) v[e] = 1.f / (1.f + expf(-v[e]));
     }
+    if (dact) {
+      v[0] *= d[i].x > 0.f ? 1.f : leak;
+      v[1] *= d[i].y > 0.f ? 1.f : leak;
+      v[2] *= d[i].z > 0.f ? 1.f : leak;
+      v[3] *= d[i].w > 0.f ? 1.f : leak;
+    }
+    if (ridx[i] >= 0) *(reinterpret_cast<float4*>(out + ridx[i]) + chunk) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncwarp();
 }

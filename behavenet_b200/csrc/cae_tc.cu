@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp < 4) {
-    if (tid == 0) {
-      // ======================= TMA producer (one thread) =========================================
+    if (warp == 0) {
+      // ======================= TMA producer (warp 0: lane 0 the im2col tile, lane 1 the weights) ====
       const int f0 = (int)(m0 / HmWm);
       const int rem0 = (int)(m0 - (long long)f0 * HmWm);
       const int ym0 = rem0 / cls->Wm, xm0 = rem0 - ym0 * cls->Wm;
@@ -386,10 +386,13 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
         const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
         const uint32_t bar = smem_u32(full_bar + stage);
-        mbar_expect_tx(bar, (uint32_t)S::STAGE_BYTES);
-        tma_im2col_4d(sa, &tm.a[cls_idx], bar, c0, w0, h0, f0, (uint16_t)(cls->dx[tap] - lw),
-                      (uint16_t)(cls->dy[tap] - lh));
-        tma_tile_2d(sb, &tm.b, bar, cls->wt[tap] * Ci + c0, n0);
+        if (tid == 0) mbar_expect_tx(bar, (uint32_t)S::STAGE_BYTES);
+        __syncwarp();
+        if (tid == 0)
+          tma_im2col_4d(sa, &tm.a[cls_idx], bar, c0, w0, h0, f0, (uint16_t)(cls->dx[tap] - lw),
+                        (uint16_t)(cls->dy[tap] - lh));
+        else if (tid == 1)
+          tma_tile_2d(sb, &tm.b, bar, cls->wt[tap] * Ci + c0, n0);
       }
     }
     __syncwarp();
@@ -824,11 +827,26 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
   constexpr uint32_t LBO = SLAB, SBO = 512;
 
   if (warp < 4) {
-    if (tid == 0) {
+    if (warp == 0) {
+      // Producer warp.  A single thread issuing the <= 4 + BN/32 copies of a chunk back to back (each
+      // with its own coordinate arithmetic) was the bottleneck of this kernel, so the copies of a
+      // chunk are issued by different lanes: lane j < nslab the im2col slab j, the next BN/32 lanes
+      // the tiles of the small image.  Lane 0 posts the transaction count first.
       // valid 32-channel slabs of this M-tile (the last tile of Ktot = 25*Cb may be short)
       int nslab = (a.Ktot - kk0 + 31) / 32;
       nslab = nslab > BM / 32 ? BM / 32 : nslab;
       const uint32_t bytes = (uint32_t)(nslab * SLAB + (BN / 32) * SLAB);
+      const int lane = tid;
+      // this lane's fixed slab (filter tap, channel offset) or small-image column block
+      int my_cb0 = 0;
+      uint16_t my_dx = 0, my_dy = 0;
+      if (lane < nslab) {
+        const int akk = kk0 + 32 * lane;
+        const int tap = akk / Cb;
+        my_cb0 = akk - tap * Cb;
+        my_dx = (uint16_t)(cls->dx[tap] - tm.lw);
+        my_dy = (uint16_t)(cls->dy[tap] - tm.lh);
+      }
       for (int c = 0; c < nchunks; ++c) {
         const int stage = c % STAGES;
         if (c >= STAGES) mbar_wait(smem_u32(empty_bar + stage), ((c / STAGES) - 1) & 1);
@@ -836,20 +854,18 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
         const uint32_t sb = sa + S::A_BYTES;
         const uint32_t bar = smem_u32(full_bar + stage);
         const long long mc = mbeg + (long long)c * BK;
-        const int f = (int)(mc / HsWs);
-        const int rem = (int)(mc - (long long)f * HsWs);
-        const int ym = rem / a.Ws, xm = rem - ym * a.Ws;
-        const int w0 = tm.lw + xm * a.gs, h0 = tm.lh + ym * a.gs;
-        mbar_expect_tx(bar, bytes);
-        for (int j = 0; j < nslab; ++j) {
-          const int akk = kk0 + 32 * j;
-          const int tap = akk / Cb;
-          const int cb0 = akk - tap * Cb;
-          tma_im2col_4d(sa + j * SLAB, &tm.a, bar, cb0, w0, h0, f, (uint16_t)(cls->dx[tap] - tm.lw),
-                        (uint16_t)(cls->dy[tap] - tm.lh));
+        if (lane == 0) mbar_expect_tx(bar, bytes);
+        __syncwarp();
+        if (lane < nslab) {
+          const int f = (int)(mc / HsWs);
+          const int rem = (int)(mc - (long long)f * HsWs);
+          const int ym = rem / a.Ws, xm = rem - ym * a.Ws;
+          const int w0 = tm.lw + xm * a.gs, h0 = tm.lh + ym * a.gs;
+          tma_im2col_4d(sa + lane * SLAB, &tm.a, bar, my_cb0, w0, h0, f, my_dx, my_dy);
+        } else if (lane < nslab + BN / 32) {
+          const int j = lane - nslab;
+          tma_tile_2d(sb + j * SLAB, &tm.s, bar, n0 + 32 * j, (int)mc);
         }
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j) tma_tile_2d(sb + j * SLAB, &tm.s, bar, n0 + 32 * j, (int)mc);
       }
     }
     __syncwarp();
@@ -1225,19 +1241,23 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     __syncwarp();
   } else {
     // ======================= TMA producer: halo chunks and weight-tile groups ====================
-    if ((tid & 31) == 0) {
+    // whole warp runs the loop; lane 0 requests the halos, lane j < ncls the j-th weight tile of a group
+    {
+      const int lane = tid & 31;
       int ai = 0, bi = 0, bt = 0;
       // chunk sequence number q -> (tile, chunk); the halo of chunk q + 1 is requested before the
       // weight tiles of chunk q so that it lands while chunk q is being multiplied
       auto load_halo = [&](long long T, int c, int q) {
         const int slot = q & 1;
         if (q >= 2) mbar_wait(smem_u32(a_empty + slot), ((q >> 1) - 1) & 1);
-        const int f = (int)(T / h.tiles_per_frame);
-        const int blk = (int)(T - (long long)f * h.tiles_per_frame);
-        const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
-        const uint32_t bar = smem_u32(a_full + slot);
-        mbar_expect_tx(bar, (uint32_t)HALO_ABYTES);
-        tma_tile_4d(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a, bar, c * BK, bx * 8 + h.lo_x, by * 16 + h.lo_y, f);
+        if (lane == 0) {
+          const int f = (int)(T / h.tiles_per_frame);
+          const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+          const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+          const uint32_t bar = smem_u32(a_full + slot);
+          mbar_expect_tx(bar, (uint32_t)HALO_ABYTES);
+          tma_tile_4d(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a, bar, c * BK, bx * 8 + h.lo_x, by * 16 + h.lo_y, f);
+        }
       };
       if (t_first < total) load_halo(t_first, 0, 0);
       for (long long T = t_first; T < total; T += t_step) {
@@ -1250,11 +1270,12 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
             if (bi >= NST) mbar_wait(smem_u32(b_empty + stage), ((bi / NST) - 1) & 1);
             const uint32_t bar = smem_u32(b_full + stage);
             const HaloGroup g = h.g[gi];
-            mbar_expect_tx(bar, (uint32_t)(g.ncls * S::B_TILE));
-            for (int j = 0; j < g.ncls; ++j) {
-              const uint32_t dst = smem_base + stage * S::B_BYTES + j * S::B_TILE;
-              if (csz == 1) tma_tile_2d(dst, &maps.b, bar, g.wt[j] * Ci + c * BK, 0);
-              else if (((bt + j) % csz) == (int)crank) tma_tile_2d_mc(dst, &maps.b, bar, g.wt[j] * Ci + c * BK, 0, cmask);
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)(g.ncls * S::B_TILE));
+            __syncwarp();
+            if (lane < g.ncls) {
+              const uint32_t dst = smem_base + stage * S::B_BYTES + lane * S::B_TILE;
+              if (csz == 1) tma_tile_2d(dst, &maps.b, bar, g.wt[lane] * Ci + c * BK, 0);
+              else if (((bt + lane) % csz) == (int)crank) tma_tile_2d_mc(dst, &maps.b, bar, g.wt[lane] * Ci + c * BK, 0, cmask);
             }
             bt += g.ncls;
           }

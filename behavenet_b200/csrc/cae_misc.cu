@@ -207,22 +207,50 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(u);
 }
 
-__global__ void pack_conv_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
-                                 float* __restrict__ wf, float* __restrict__ wd,
-                                 float* __restrict__ wft, float* __restrict__ wdt) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long tot = (long long)Cs * Cb * kk;
-  if (i >= tot) return;
-  int tap = (int)(i % kk);
-  long long r = i / kk;
-  int cb = (int)(r % Cb);
-  int cs = (int)(r / Cb);
-  float v = src[i];
-  wf[((long long)tap * Cb + cb) * Cs + cs] = v;
-  wd[((long long)tap * Cs + cs) * Cb + cb] = v;
-  const float vr = round_tf32(v);
-  wft[((long long)cs * kk + tap) * Cb + cb] = vr;
-  wdt[((long long)cb * kk + tap) * Cs + cs] = vr;
+// Weight packing, src [cs][cb][tap] (torch layout, tap fastest) -> four GEMM orders.  A one-thread-
+// per-element version writes four scattered 4-byte stores per element (a 32-byte sector each); here
+// two kernels stage bricks in shared memory so that every global access is a contiguous run:
+//   pack_conv_rows_kernel : one block per cs: row (cb, tap) -> wft [cs][tap][cb], wd [tap][cs][cb]
+//   pack_conv_cols_kernel : block = 32 cs x 8 cb x all taps -> wf [tap][cb][cs], wdt [cb][tap][cs]
+__global__ void __launch_bounds__(256) pack_conv_rows_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
+                                                             float* __restrict__ wd, float* __restrict__ wft) {
+  extern __shared__ float prow[];                 // [cb][kk + 1] (odd pitch when kk is even is not needed: reads are strided by kk+1)
+  const int cs = blockIdx.x;
+  const int n = Cb * kk;
+  const float* s = src + (long long)cs * n;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int cb = i / kk, tap = i - cb * kk;
+    prow[cb * (kk + 1) + tap] = s[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int tap = i / Cb, cb = i - tap * Cb;
+    const float v = prow[cb * (kk + 1) + tap];
+    wd[((long long)tap * Cs + cs) * Cb + cb] = v;
+    wft[((long long)cs * kk + tap) * Cb + cb] = round_tf32(v);
+  }
+}
+
+constexpr int PCS = 32, PCB = 8;
+__global__ void __launch_bounds__(256) pack_conv_cols_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
+                                                             float* __restrict__ wf, float* __restrict__ wdt) {
+  extern __shared__ float brick[];                // [cs 32][PCB * kk + 1]
+  const int cs0 = blockIdx.x * PCS, cb0 = blockIdx.y * PCB;
+  const int ncb = min(PCB, Cb - cb0), ncs = min(PCS, Cs - cs0);
+  const int run = ncb * kk, pitch = PCB * kk + 1;
+  for (int i = threadIdx.x; i < ncs * run; i += 256) {
+    const int c = i / run, r = i - c * run;
+    brick[c * pitch + r] = src[((long long)(cs0 + c) * Cb + cb0) * kk + r];       // runs of ncb*kk contiguous floats
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < run * PCS; i += 256) {
+    const int r = i / PCS, c = i - r * PCS;             // c = cs fastest
+    if (c >= ncs) continue;
+    const int cbl = r / kk, tap = r - cbl * kk;
+    const float v = brick[c * pitch + r];
+    wf[((long long)tap * Cb + cb0 + cbl) * Cs + cs0 + c] = v;
+    wdt[((long long)(cb0 + cbl) * kk + tap) * Cs + cs0 + c] = round_tf32(v);
+  }
 }
 
 __global__ void pack_heads_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int L,
@@ -490,8 +518,21 @@ int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_
 
 int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd, float* wft,
                         float* wdt, cudaStream_t st) {
-  long long tot = (long long)Cs * Cb * kk;
-  pack_conv_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(src, Cs, Cb, kk, wf, wd, wft, wdt);
+  const size_t smem_rows = (size_t)Cb * (kk + 1) * sizeof(float);
+  const size_t smem_cols = (size_t)PCS * (PCB * kk + 1) * sizeof(float);
+  if (smem_rows > 200 * 1024 || smem_cols > 200 * 1024) BN_FAIL("pack_conv: layer too wide (C_big=%d, k*k=%d)", Cb, kk);
+  static size_t cfg_rows = 0, cfg_cols = 0;
+  if (smem_rows > cfg_rows) {
+    BN_CUDA(cudaFuncSetAttribute(pack_conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    cfg_rows = smem_rows;
+  }
+  if (smem_cols > cfg_cols) {
+    BN_CUDA(cudaFuncSetAttribute(pack_conv_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    cfg_cols = smem_cols;
+  }
+  pack_conv_rows_kernel<<<Cs, 256, smem_rows, st>>>(src, Cs, Cb, kk, wd, wft);
+  BN_LAUNCHED();
+  pack_conv_cols_kernel<<<dim3(bn_cdiv(Cs, PCS), bn_cdiv(Cb, PCB)), 256, smem_cols, st>>>(src, Cs, Cb, kk, wf, wdt);
   BN_LAUNCHED();
   return 0;
 }

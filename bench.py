@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 # algorithmic work
 CAE_C2_TRAIN_GFLOP_PER_FRAME = 2.078
 ARHMM_BYTES_PER_TIMESTEP = 113.0
-# dram__bytes_read + write per launch of the dominant kernel (profiles/r01_f_ncu_full.txt)
+# dram__bytes_read + write per launch (profiles/r01_g_ncu_full.txt)
+IGEMM128_KERNEL_TRAFFIC_BYTES = 72.1e6      # encoder conv2 forward: 67 MB input image read once
 HALO_KERNEL_TRAFFIC_BYTES = 144.2e6
 CAE_BATCH_PER_GPU = 256
 ARHMM_TRIALS_PER_GPU, ARHMM_T, ARHMM_K, ARHMM_D, ARHMM_LAGS = 2048, 1000, 16, 12, 2
@@ -195,11 +196,11 @@ def time_layer_kernel(model, device, side, layer, op, name, traffic_bytes, iters
 
 def time_dominant_kernel(model, device):
     """The kernel with the largest share of the step in the committed launch list
-    (profiles/r01_f_launches_summary.txt): the halo-resident tcgen05 transposed convolution of decoder
-    layer 3 (64 -> 32 channels, 32x32 -> 64x64, k5 s2, 256 frames)."""
-    return time_layer_kernel(model, device, 1, 3, 0,
-                             'dgrad_halo_kernel<32,3> (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])',
-                             HALO_KERNEL_TRAFFIC_BYTES)
+    (profiles/r01_g_launches_summary.txt: igemm_tma_kernel<128,3>, 8 launches, 10.1 %): its encoder
+    conv2 forward instance (64 -> 128 channels, 32x32 -> 16x16, k5 s2, 256 frames)."""
+    return time_layer_kernel(model, device, 0, 2, 0,
+                             'igemm_tma_kernel<128,3> (encoder conv2 forward, M=65536 N=128 K=1600)',
+                             IGEMM128_KERNEL_TRAFFIC_BYTES)
 
 
 def measure_cublas_tf32(device):
@@ -322,6 +323,9 @@ def run_ours(args):
     dom = time_dominant_kernel(model, device)
     dom2 = time_layer_kernel(model, device, 0, 1, 0,
                              'igemm_tma_kernel<64,4> (encoder conv1 forward, M=262144 N=64 K=800)', 51.7e6)
+    dom3 = time_layer_kernel(model, device, 1, 3, 0,
+                             'dgrad_halo_kernel<32,3> (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])',
+                             HALO_KERNEL_TRAFFIC_BYTES)
     cublas_tf32 = measure_cublas_tf32(device) if rank == 0 else None
 
     # ---------------- ARHMM (C4): weak scaling, 2048 trials per GPU
@@ -399,7 +403,7 @@ def run_ours(args):
                      'note': 'dominant kernel timed alone with CUDA events on the launch stream (%d '
                              'launches after warm-up); peak = TF32 dense = half of the %s bf16 burst '
                              'peak (MEASURED_PEAKS.json has no TF32 entry); traffic = dram read+write '
-                             'bytes per launch from profiles/r01_f_ncu_full.txt'
+                             'bytes per launch from profiles/r01_g_ncu_full.txt'
                              % (dom['launches'], peak_src)},
         'step_roofline': {'bound': 'tensor', 'achieved': tf, 'peak': tf32_peak_sust, 'unit': 'TFLOP/s',
                           'frac': tf / tf32_peak_sust,
@@ -407,7 +411,7 @@ def run_ours(args):
                                   'half of the %s bf16 sustained peak' % (CAE_C2_TRAIN_GFLOP_PER_FRAME, peak_src)},
         'kernel_rooflines': [{'kernel': d['kernel'], 'us': d['us'], 'tflops': d['tflops'],
                               'frac': d['tflops'] / tf32_peak_burst, 'traffic': d['traffic_bytes']}
-                             for d in (dom, dom2)],
+                             for d in (dom, dom2, dom3)],
         'cublas_tf32_tflops_here': cublas_tf32,
         'arhmm': {
             'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
@@ -421,7 +425,7 @@ def run_ours(args):
                          'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out '
                                  '+ per-trial outputs), whole E-step time (emission + scan kernels); peak %s; '
                                  'traffic = dram read+write of the dominant kernel (scan2_kernel, 0.31 of the 0.57 ms; '
-                                 'emission_tc_kernel adds 187 MB), profiles/r01_f_ncu_full.txt; the binding limits '
+                                 'emission_tc_kernel adds 187 MB), profiles/r01_g_ncu_full.txt; the binding limits '
                                  'are the T-step serial chain and the 3-pass emission GEMM, not HBM' % peak_src},
         },
     }

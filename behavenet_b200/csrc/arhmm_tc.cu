@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
     for (int i = tid; i < K + 1; i += NTHREADS) csm[i] = cg[i];
   }
   if (tid == 0) {
-    mbar_init(full_bar, 128 + L);        // 128 row owners + L halo lanes of warp 4
+    mbar_init(full_bar, 4 + (L > 0 ? 1 : 0));   // one arrival per producer warp (+ warp 4 for the halo rows)
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
     }
     fence_proxy_async();
     tc_fence_before();               // this thread's TMEM reads of the previous tile are complete
-    if (warp < 4 || halo_lane) mbar_arrive(full_bar);
+    // one mbarrier arrival per warp (128 single-thread arrivals on one shared word serialise):
+    // __syncwarp orders the lanes' writes before lane 0's releasing arrive
+    __syncwarp();
+    if ((tid & 31) == 0 && (warp < 4 || L > 0)) mbar_arrive(full_bar);
     // next tile's x rows are fetched while the tensor core works on this one
     step_tile();
     have = advance();

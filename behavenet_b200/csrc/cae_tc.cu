@@ -1135,7 +1135,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
       mbar_init(smem_u32(a_full + s), 1);
       mbar_init(smem_u32(a_empty + s), 1);
       mbar_init(smem_u32(acc_full + s), 1);
-      mbar_init(smem_u32(acc_empty + s), 128);
+      mbar_init(smem_u32(acc_empty + s), 4);        // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1192,7 +1192,8 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
         }
       }
       tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
-      mbar_arrive(smem_u32(acc_empty + buf));
+      __syncwarp();
+      if (elane == 0) mbar_arrive(smem_u32(acc_empty + buf));
       if (tid == 0) HALO_STAMP(ti, 5);
     }
   } else if (warp == 4) {

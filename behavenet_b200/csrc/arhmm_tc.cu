@@ -17,6 +17,8 @@
 // coalesced 2 KB store per chunk.  Warps 0-3 build psi, wait for the accumulator, read their TMEM
 // lane quarter back with tcgen05.ld and reduce per state; warp 4 allocates TMEM and issues the
 // MMAs.  Two CTAs per SM overlap one tile's MMAs with the other's epilogue.
+#include <stdlib.h>
+
 #include "arhmm_common.cuh"
 #include "tc_common.cuh"
 
@@ -47,7 +49,21 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 
 __host__ __device__ constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
 
+// phase timestamps of CTA 0 (debug aid, BN_EMIT_DBG=1; bn_debug_emit_times): per tile
+// [loop top, psi posted, x prefetch issued, accumulator ready, epilogue done]
+__device__ long long g_emit_dbg[16 * 8];
+__device__ __forceinline__ long long emit_clock() {
+  long long v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+  return v;
+}
+#define EMIT_STAMP(slot)                                                                              \
+  do {                                                                                                \
+    if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0 && ntile < 16) g_emit_dbg[ntile * 8 + (slot)] = emit_clock(); \
+  } while (0)
+
 struct EmitTcArgs {
+  int dbg;
   const unsigned char* blob;
   const float* x;
   const long long* offsets;
@@ -160,7 +176,9 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
   bool have = advance();
   float4 xv[DP / 4];
   if (have && (warp < 4 || halo_lane)) load_x(beg, T, t0 + my_r0, xv);
+  int ntile = 0;
   while (have) {
+    EMIT_STAMP(0);
     const long long cbeg = beg;
     const int cT = T, ct0 = t0;
     if (warp < 4 || halo_lane) scatter_x(my_r0, xv);
@@ -179,6 +197,7 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
     // __syncwarp orders the lanes' writes before lane 0's releasing arrive
     __syncwarp();
     if ((tid & 31) == 0 && (warp < 4 || L > 0)) mbar_arrive(full_bar);
+    EMIT_STAMP(1);
     // next tile's x rows are fetched while the tensor core works on this one
     step_tile();
     have = advance();
@@ -190,12 +209,14 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
         qinit += xv[c].x * xv[c].x + xv[c].y * xv[c].y + xv[c].z * xv[c].z + xv[c].w * xv[c].w;
     }
     if (have && (warp < 4 || halo_lane)) load_x(beg, T, t0 + my_r0, xv);
+    EMIT_STAMP(2);
 
     if (warp < 4) {
       // ---------------- epilogue
       const int t = ct0 + tid;
       mbar_wait(accum_bar, phase);
       tc_fence_after();
+      EMIT_STAMP(3);
       float vmax = -INFINITY;
       float vals[32];                       // K <= 32 log-likelihoods of this row
 #pragma unroll
@@ -246,6 +267,7 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
             if (k < K) og[k] = init ? 1.f : __expf(vals[k] - vmax);
         }
       }
+      EMIT_STAMP(4);
     } else if ((tid & 31) == 0) {
       // ---------------- MMA issuer
       mbar_wait(full_bar, phase);
@@ -271,6 +293,7 @@ __global__ void __launch_bounds__(NTHREADS) emission_tc_kernel(const EmitTcArgs 
       mbar_wait(accum_bar, phase);
     }
     phase ^= 1;
+    ++ntile;
   }
   tc_fence_before();
   __syncthreads();
@@ -313,6 +336,8 @@ int bn_launch_emission_tc(const unsigned char* d_blob, const float* d_x, const l
   EmitTcArgs a;
   a.blob = d_blob; a.x = d_x; a.offsets = d_offsets; a.K = K; a.D = D; a.lags = lags; a.n_trials = n_trials;
   a.Bsc = d_Bsc; a.mx = d_mx;
+  static const int dbg = [] { const char* e = getenv("BN_EMIT_DBG"); return e ? atoi(e) : 0; }();
+  a.dbg = dbg;
   switch (h.DP) {
     case 4: return launch<4>(a, h.NT, h.KT, max_T, st);
     case 8: return launch<8>(a, h.NT, h.KT, max_T, st);
@@ -324,4 +349,9 @@ int bn_launch_emission_tc(const unsigned char* d_blob, const float* d_x, const l
     case 32: return launch<32>(a, h.NT, h.KT, max_T, st);
     default: return 1;
   }
+}
+
+extern "C" int bn_debug_emit_times(long long* h_out) {
+  BN_CUDA(cudaMemcpyFromSymbol(h_out, g_emit_dbg, sizeof(long long) * 128));
+  return 0;
 }

@@ -57,8 +57,9 @@ int bn_launch_thin_dgrad(const float* small, const ConvGeom& g, const float* wd,
 
 // Shared-memory-tiled fast paths for kernel-5 / stride-2 thin layers (cae_thin.cu).  Each returns 1
 // when the geometry is not covered (caller falls back to the general kernels).
-int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* bias, float* out,
-                         const float* dact, int act, int n, cudaStream_t st);
+// wft != NULL selects the tcgen05 (TF32) form: K-major weights [c_small][(tap, c_big)]
+int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* wft, const float* bias,
+                         float* out, const float* dact, int act, int n, cudaStream_t st);
 int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                          size_t partial_floats, float* grad, cudaStream_t st);
 int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd, const float* bias, int n,

@@ -273,7 +273,8 @@ extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const floa
   for (int i = 0; i < p->nl; ++i) {
     const ConvGeom& g = p->enc[i];
     float* out = ws + L.enc_act[i + 1];
-    int thin = g.Cb <= 4 ? bn_launch_thin_fprop(in, g, pk + g.off_wf, P[g.p_b], out, nullptr, BN_ACT_LEAKY, n, st) : 1;
+    int thin = g.Cb <= 4 ? bn_launch_thin_fprop(in, g, pk + g.off_wf, g_tc_mode.load() ? pk + g.off_wft : nullptr, P[g.p_b], out, nullptr,
+                                                BN_ACT_LEAKY, n, st) : 1;
     if (thin < 0) return thin;
     if (thin > 0)
       BN_TRY(run_igemm(p, in, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, P[g.p_b], out, g.Hs, g.Ws,
@@ -349,7 +350,8 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
     BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
     float* out = pp[flip];
     flip ^= 1;
-    int thin = g.Cb <= 4 ? bn_launch_thin_fprop(big, g, pk + g.off_wf, nullptr, out, i > 0 ? small : nullptr,
+    int thin = g.Cb <= 4 ? bn_launch_thin_fprop(big, g, pk + g.off_wf, g_tc_mode.load() ? pk + g.off_wft : nullptr, nullptr, out,
+                                                i > 0 ? small : nullptr,
                                                 BN_ACT_NONE, n, st) : 1;
     if (thin < 0) return thin;
     if (thin > 0)
@@ -424,6 +426,13 @@ extern "C" int bn_cae_layer_op(bn_cae_plan* p, int side, int layer, int op, int 
     return run_wgrad(nhwc_view(d_in, g.Hb, g.Wb, g.Cb), d_in2, g, n, ws + L.partial, L.partial_floats, d_out, st);
   }
   if (fprop_form) {
+    if (g.Cb <= 4) {
+      // thin first / last layer: same routing as bn_cae_encode / bn_cae_decode_bwd (d_in is NHWC here)
+      int thin = bn_launch_thin_fprop(nhwc_view(d_in, g.Hb, g.Wb, g.Cb), g, pk + g.off_wf,
+                                      g_tc_mode.load() ? pk + g.off_wft : nullptr, bias, d_out, nullptr,
+                                      op == 0 ? BN_ACT_LEAKY : BN_ACT_NONE, n, st);
+      if (thin <= 0) return thin;
+    }
     return run_igemm(p, nhwc_view(d_in, g.Hb, g.Wb, g.Cb), pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, bias,
                      d_out, g.Hs, g.Ws, g.Cs, nullptr, tf, 1, g.Hs * g.Ws, g.s, 1, n,
                      op == 0 ? BN_ACT_LEAKY : BN_ACT_NONE, st);

@@ -10,7 +10,10 @@
 //                        (last ConvTranspose2d forward, aes.py:463-470 + losses.py:36-96)
 // Lane = feature channel in the first two (coalesced 128-byte rows per pixel, taps read by
 // broadcast LDS.128); lane = output pixel of one stride-residue class in the third.
+#include <stdlib.h>
+
 #include "cae_kernels.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -375,6 +378,177 @@ bool fast_geom(const ConvGeom& g) { return g.k == 5 && g.s == 2 && g.Cb >= 1 && 
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core form of thin_fprop (mode 1).  The FP32 kernel above is issue-bound: 25*CB FMAs per
+// output pixel and channel.  Here the 25*CB patch values of an output pixel become one row of a
+// K-major SWIZZLE_128B A tile (each thread gathers its own row from the staged patch with scalar LDS
+// and writes it as 16-byte chunks), the TF32 weights [c_small][(tap, c_big)] sit in a B tile for the
+// whole kernel, and an 8 x 32 output tile is two tcgen05.mma M-tiles (K padded to a multiple of 32).
+// Epilogue = the shared transposing store (bias, LeakyReLU, derivative mask).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t thin_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int CB>
+struct ThinTcSmem {
+  static constexpr int NKC = (25 * CB + 31) / 32;           // 32-float k-chunks
+  static constexpr int A_BYTES = 2 * NKC * 128 * 128;       // two M-tiles (8 rows x 32 pixels)
+  static constexpr int B_BYTES = NKC * 32 * 128;            // N = 32 channels
+  static constexpr int OFF_B = A_BYTES;
+  static constexpr int OFF_PATCH = OFF_B + B_BYTES;
+  static constexpr int PATCH_BYTES = 2 * CB * PROWS * PCOLS * 4;
+  static constexpr int OFF_BAR = OFF_PATCH + ((PATCH_BYTES + 15) & ~15);
+  static constexpr int TOTAL = OFF_BAR + 32;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(256) thin_fprop_tc_kernel(const ThinGeo g, const float* __restrict__ wft,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            const float* __restrict__ dact, int act, const TileIter it) {
+  using namespace bn_tc;
+  using S = ThinTcSmem<CB>;
+  constexpr int NKC = S::NKC, KTOT = 25 * CB;
+  extern __shared__ __align__(1024) unsigned char tsm[];
+  typedef float (*Patch)[PROWS][PCOLS];
+  Patch patch[2] = {reinterpret_cast<Patch>(tsm + S::OFF_PATCH),
+                    reinterpret_cast<Patch>(tsm + S::OFF_PATCH + CB * PROWS * PCOLS * 4)};
+  uint64_t* accum_bar = reinterpret_cast<uint64_t*>(tsm + S::OFF_BAR);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = blockIdx.y * 32;                          // channel group of this block
+  // B tile: rows n = channel, k-chunk kc, 16-byte chunk c at position c ^ (n & 7)
+  for (int i = tid; i < NKC * 32 * 8; i += 256) {
+    const int kc = i / 256, rem = i - kc * 256;
+    const int n = rem >> 3, c = rem & 7;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = kc * 32 + c * 4 + e;
+      v[e] = k < KTOT ? __ldg(wft + (long long)(c0 + n) * KTOT + k) : 0.f;
+    }
+    *reinterpret_cast<float4*>(tsm + S::OFF_B + kc * 4096 + n * 128 + ((c ^ (n & 7)) << 4)) =
+        make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(accum_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc<64>(smem_u32(tmem_ptr));
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t sa = smem_u32(tsm), sb = sa + S::OFF_B;
+  const int trow = tid >> 5, tcol = tid & 31;              // output pixel of this thread inside the 8 x 32 tile
+  const int mt = trow >> 2, arow = (trow & 3) * 32 + tcol; // M-tile and row inside it
+
+  long long t = blockIdx.x;
+  int f, y0, x0;
+  if (t < it.total) {
+    it.decode(t, f, y0, x0);
+    issue_patch<CB>(patch[0], g, f, y0, x0, tid);
+  }
+  cp_commit();
+  uint32_t phase = 0;
+  for (int buf = 0; t < it.total; t += gridDim.x, buf ^= 1, phase ^= 1) {
+    it.decode(t, f, y0, x0);
+    const long long tn = t + gridDim.x;
+    if (tn < it.total) {
+      int fn, yn, xn;
+      it.decode(tn, fn, yn, xn);
+      issue_patch<CB>(patch[buf ^ 1], g, fn, yn, xn, tid);
+    }
+    cp_commit();
+    cp_wait<1>();
+    __syncthreads();                   // patch[buf] landed; previous tile's epilogue tiles (aliasing A) are idle
+    // ---- this thread's im2col row: k = (ky*5 + kx)*CB + cb  <-  patch[cb][2*trow + ky][2*tcol + kx]
+    {
+      unsigned char* abase = tsm + (mt * NKC) * 16384 + arow * 128;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = kc * 32 + c * 4 + e;            // compile-time
+            if (k < KTOT) {
+              const int tap = k / CB, cb = k - tap * CB;
+              v[e] = patch[buf][cb][2 * trow + tap / 5][2 * tcol + tap % 5];
+            } else {
+              v[e] = 0.f;
+            }
+          }
+          *reinterpret_cast<float4*>(abase + kc * 16384 + ((c ^ (arow & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(128, 32);
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + m * 32, thin_desc_sw128(sa + (m * NKC + kc) * 16384 + k * 32),
+                      thin_desc_sw128(sb + kc * 4096 + k * 32), idesc, (kc | k) != 0 ? 1u : 0u);
+      umma_commit(smem_u32(accum_bar));
+    }
+    mbar_wait(smem_u32(accum_bar), phase);
+    tc_fence_after();
+    // ---- epilogue: warps 0-3 drain M-tile 0, warps 4-7 M-tile 1; the A tiles are free again
+    {
+      const int q = warp & 3, m = warp >> 2;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + m * 32, r);
+      tmem_ld_wait();
+      const int oy = y0 + m * 4 + q, ox = x0 + lane;
+      const bool valid = oy < g.Hs && ox < g.Ws;
+      const long long idx = valid ? (((long long)f * g.Hs + oy) * g.Ws + ox) * g.Cs + c0 : -1;
+      warp_store_rows32(out, dact, BN_LEAK, idx, r, bias ? bias + c0 : nullptr, act,
+                        reinterpret_cast<float*>(tsm) + warp * 1024, lane);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+template <int CB>
+static int launch_thin_fprop_tc(const ThinGeo& t, const float* wft, const float* bias, float* out, const float* dact,
+                                int act, const TileIter& it, int cgroups, cudaStream_t st) {
+  using S = ThinTcSmem<CB>;
+  auto kern = thin_fprop_tc_kernel<CB>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  // residency: 64 TMEM columns and S::TOTAL bytes per CTA
+  int per_sm = (227 * 1024) / (S::TOTAL + 1024);
+  per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);       // ~120 registers x 256 threads: two CTAs per SM
+  long long blocks = it.total < 148LL * per_sm ? it.total : 148LL * per_sm;
+  kern<<<dim3((unsigned)blocks, cgroups), 256, S::TOTAL, st>>>(t, wft, bias, out, dact, act, it);
+  BN_LAUNCHED();
+  return 0;
+}
+
 template <int CB>
 static int launch_thin_fprop(const ThinGeo& t, const float* wf, const float* bias, float* out, const float* dact,
                              int act, const TileIter& it, int cgroups, cudaStream_t st) {
@@ -391,8 +565,8 @@ static int launch_thin_fprop(const ThinGeo& t, const float* wf, const float* bia
   return 0;
 }
 
-int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* bias, float* out,
-                         const float* dact, int act, int n, cudaStream_t st) {
+int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* wft, const float* bias,
+                         float* out, const float* dact, int act, int n, cudaStream_t st) {
   if (!fast_geom(g) || n <= 0) return 1;
   ThinGeo t;
   t.big = big; t.Hs = g.Hs; t.Ws = g.Ws; t.Cs = g.Cs; t.pt = g.pt; t.pl = g.pl; t.n = n;
@@ -400,6 +574,17 @@ int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf,
   it.tiles_x = bn_cdiv(g.Ws, TW);
   it.tiles_per_frame = it.tiles_x * bn_cdiv(g.Hs, TH);
   it.total = (long long)it.tiles_per_frame * n;
+  static const bool tc_off = [] { const char* e = getenv("BN_THIN_TC"); return e && e[0] == '0'; }();
+  if (wft != nullptr && !tc_off && !((uintptr_t)out & 15) && !(dact && ((uintptr_t)dact & 15)) &&
+      !(bias && ((uintptr_t)bias & 15))) {
+    // tensor-core form (TF32): wft = K-major weights [c_small][(tap, c_big)]
+    switch (g.Cb) {
+      case 1: return launch_thin_fprop_tc<1>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
+      case 2: return launch_thin_fprop_tc<2>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
+      case 3: return launch_thin_fprop_tc<3>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
+      default: return launch_thin_fprop_tc<4>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
+    }
+  }
   switch (g.Cb) {
     case 1: return launch_thin_fprop<1>(t, wf, bias, out, dact, act, it, g.Cs / 32, st);
     case 2: return launch_thin_fprop<2>(t, wf, bias, out, dact, act, it, g.Cs / 32, st);

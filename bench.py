@@ -278,12 +278,27 @@ def run_ours(args):
     lo, hi = parallel.shard_range(B, world, rank)
     x_shard_host = x_host[lo:hi].clone().pin_memory()       # this rank's frames only
 
-    def step_e2e():
-        opt.zero_grad()
-        model.invalidate_packed()
-        xd = x_shard_host.to(device, non_blocking=True)
-        # ends with the loss readback (one D2H of the per-chunk sums)
-        model.loss({'images': xd[None], 'shard': (lo, B)}, accumulate_grad=True)
+    # End to end as a training loop would run it: every step's frames come from pinned host memory,
+    # the copy of step i+1 is issued on a side stream before the loss of step i (two device input
+    # buffers), and every loss() call ends with its device->host read of the per-chunk sums.
+    copy_stream = torch.cuda.Stream(device=device)
+    in_bufs = [torch.empty_like(x_dev[lo:hi]) for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            in_bufs[i & 1].copy_(x_shard_host, non_blocking=True)
+            in_ready[i & 1].record(copy_stream)
+
+    def run_e2e(n_steps):
+        prefetch(0)
+        for i in range(n_steps):
+            torch.cuda.current_stream().wait_event(in_ready[i & 1])
+            prefetch(i + 1)          # buffer (i+1)&1 was last read by step i-1, which has returned
+            opt.zero_grad()
+            model.invalidate_packed()
+            model.loss({'images': in_bufs[i & 1][None], 'shard': (lo, B)}, accumulate_grad=True)
+        copy_stream.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -312,8 +327,14 @@ def run_ours(args):
     # per-step distribution with an L2 flush between steps (inputs are 16.8 MB/GPU < L2)
     ms_flushed = timed(step, max(3, min(args.steps, 10)), 0, flush)
     opt_ms = timed(lambda: opt.step(), 3, 1)
-    e2e_ms = timed(step_e2e, max(3, min(args.steps, 10)), 2)
-    e2e_ms = dist_max(float(np.median(e2e_ms)), device)
+    e2e_steps = max(3, min(args.steps, 20))
+    run_e2e(2)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    run_e2e(e2e_steps)
+    torch.cuda.synchronize()
+    e2e_ms = dist_max((time.perf_counter() - t0) * 1e3 / e2e_steps, device)
 
     tf = cae_value * CAE_C2_TRAIN_GFLOP_PER_FRAME * 1e-3 / world         # TFLOP/s per GPU
     # TF32 dense peak: MEASURED_PEAKS.json has no TF32 entry; the hardware ratio to bf16 is 1/2, so
@@ -395,7 +416,11 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'e2e': {'value': B / (e2e_ms * 1e-3), 'unit': 'frames/s',
-                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 16 * world},
+                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 16 * world,
+                'steps': e2e_steps,
+                'note': 'AE.loss on frames copied from pinned host memory every step (the copy of step i+1 '
+                        'overlaps the compute of step i on a side stream; one extra prefetch is inside the '
+                        'timed region) + the per-step loss read-back; host wall clock, max over ranks'},
         'roofline': {'bound': 'tensor', 'achieved': dom['tflops'], 'peak': tf32_peak_burst,
                      'unit': 'TFLOP/s', 'frac': dom['tflops'] / tf32_peak_burst,
                      'traffic': dom['traffic_bytes'],

@@ -91,3 +91,25 @@ def test_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op, geom):
     assert torch.isfinite(tc).all()
     err = float((tc - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize('n_ch', [1, 2])
+@pytest.mark.parametrize('geom', [(32, 128, 128), (7, 64, 48)])
+@pytest.mark.parametrize('side,layer,op', [(0, 0, 0), (1, 4, 1)])
+def test_thin_layer_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op, geom, n_ch):
+    """First encoder layer forward / last decoder layer backward-data (1-2 image channels <-> 32 feature
+    channels): the tcgen05 form of thin_fprop against the fp32 form on TF32-exact data."""
+    n, h, w = geom
+    lib, model, drv, params, packed, ws, hp = _setup(n_ch=n_ch, n=n, h=h, w=w)
+    big, small = _dims(hp, side, layer)
+    g = torch.Generator().manual_seed(7 + side)
+    xb = _exact((n,) + big, g).cuda()
+    outs = []
+    for mode in (0, 1):
+        out = torch.full((n,) + small, float('nan'), device='cuda')
+        _run(lib, drv, params, packed, ws, side, layer, op, n, xb, None, out, mode)
+        outs.append(out)
+    ref, tc = outs
+    assert torch.isfinite(tc).all()
+    err = float((tc - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err

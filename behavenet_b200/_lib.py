@@ -47,6 +47,7 @@ SIGNATURES = {
     'bn_cae_workspace_bytes': (_sz, [_vp, _i]),
     'bn_cae_pack_params': (_i, [_vp, _vp, _vp, _vp]),
     'bn_cae_encode': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'bn_cae_encode_u8': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'bn_cae_decode': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     'bn_cae_decode_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'bn_cae_encode_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -79,7 +80,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.bn_abi_version() != 2:
+        if handle.bn_abi_version() != 3:
             raise NativeLibraryError('ABI version mismatch')
         _lib = handle
     return _lib

@@ -59,7 +59,8 @@ int bn_launch_thin_dgrad(const float* small, const ConvGeom& g, const float* wd,
 // when the geometry is not covered (caller falls back to the general kernels).
 // wft != NULL selects the tcgen05 (TF32) form: K-major weights [c_small][(tap, c_big)]
 int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* wft, const float* bias,
-                         float* out, const float* dact, int act, int n, cudaStream_t st);
+                         float* out, const float* dact, int act, int n, cudaStream_t st,
+                         const unsigned char* big_u8 = nullptr);   // big_u8: raw 0..255 video with big's strides
 int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                          size_t partial_floats, float* grad, cudaStream_t st);
 int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd, const float* bias, int n,
@@ -99,6 +100,7 @@ int bn_launch_decff_bwd(const float* z, const float* w, const float* dh0, int n,
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
                        const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
-                       int act, float* split_buf, size_t split_floats, cudaStream_t st);
+                       int act, float* split_buf, size_t split_floats, float* colsum, int* colsum_fused,
+                       cudaStream_t st);
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n,
                        float* partial, size_t partial_floats, float* grad, cudaStream_t st);

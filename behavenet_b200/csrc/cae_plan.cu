@@ -113,14 +113,21 @@ thread_local size_t t_split_floats = 0;
 
 int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const float* wt, int wrow,
               const float* bias, float* out, int Ho, int Wo, int Co, const float* dact, int table_idx,
-              int nclasses, int maxM, int gs, int os, int n, int act, cudaStream_t st) {
+              int nclasses, int maxM, int gs, int os, int n, int act, cudaStream_t st,
+              float* colsum = nullptr, int* colsum_fused = nullptr) {
+  // colsum (optional, [Co], accumulated into): the column sums of `out`, i.e. the bias gradient of the
+  // layer below when `out` is a gradient image; *colsum_fused says whether the kernel's epilogue
+  // took care of it (otherwise the caller runs bn_launch_colsum over the stored image)
   const TapClass* dcls = p->d_tables + table_idx;
+  if (colsum_fused) *colsum_fused = 0;
   if (g_tc_mode.load()) {
     int maxtaps = 0;
     for (int c = 0; c < nclasses; ++c) maxtaps = std::max(maxtaps, p->h_tables[table_idx + c].ntaps);
     int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, p->h_tables.data() + table_idx,
-                               nclasses, maxM, maxtaps, gs, os, n, act, t_split_buf, t_split_floats, st);
+                               nclasses, maxM, maxtaps, gs, os, n, act, t_split_buf, t_split_floats, colsum,
+                               colsum_fused, st);
     if (r <= 0) return r;
+    if (colsum_fused) *colsum_fused = 0;
   }
   return bn_launch_igemm(in, w, bias, out, Ho, Wo, Co, dact, dcls, nclasses, maxM, gs, os, n, act, st);
 }
@@ -258,9 +265,9 @@ extern "C" int bn_cae_pack_params(bn_cae_plan* p, const float* const* P, void* d
   return 0;
 }
 
-extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const float* const* P,
-                             const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream) {
-  if (!p || !d_x || !P || !d_packed || !d_ws || !d_mu) BN_FAIL("bn_cae_encode: null argument");
+static int encode_impl(bn_cae_plan* p, int n, const float* d_x, const unsigned char* d_x8, const float* const* P,
+                       const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream) {
+  if (!p || (!d_x && !d_x8) || !P || !d_packed || !d_ws || !d_mu) BN_FAIL("bn_cae_encode: null argument");
   if (p->d.n_heads == 2 && !d_logvar) BN_FAIL("bn_cae_encode: logvar output required for a variational encoder");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -269,13 +276,18 @@ extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const floa
   WsLayout L = ws_layout(p, n);
   t_split_buf = ws + L.partial;
   t_split_floats = L.partial_floats;
-  ImgView in = input_view(p, d_x);
+  ImgView in = input_view(p, d_x);     // d_x == NULL with uint8 frames: only the strides are used
   for (int i = 0; i < p->nl; ++i) {
     const ConvGeom& g = p->enc[i];
     float* out = ws + L.enc_act[i + 1];
+    const unsigned char* u8 = i == 0 ? d_x8 : nullptr;
     int thin = g.Cb <= 4 ? bn_launch_thin_fprop(in, g, pk + g.off_wf, g_tc_mode.load() ? pk + g.off_wft : nullptr, P[g.p_b], out, nullptr,
-                                                BN_ACT_LEAKY, n, st) : 1;
+                                                BN_ACT_LEAKY, n, st, u8) : 1;
     if (thin < 0) return thin;
+    if (thin > 0 && u8)
+      BN_FAIL("bn_cae_encode_u8: the uint8 frame loader exists for first layers with <= 4 input channels, "
+              "kernel 5, stride 2 and a multiple of 32 output channels (got C=%d k=%d s=%d C_out=%d)",
+              g.Cb, g.k, g.s, g.Cs);
     if (thin > 0)
       BN_TRY(run_igemm(p, in, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, P[g.p_b], out, g.Hs, g.Ws,
                        g.Cs, nullptr, p->enc_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_LEAKY, st));
@@ -286,6 +298,18 @@ extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const floa
                              p->d.n_heads == 2 ? P[n2 + 3] : nullptr, n, p->d.n_latents, p->d.n_heads,
                              p->feat_c * p->feat_h * p->feat_w, d_mu, d_logvar, st));
   return 0;
+}
+
+extern "C" int bn_cae_encode(bn_cae_plan* p, int n, const float* d_x, const float* const* P,
+                             const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream) {
+  if (!d_x) BN_FAIL("bn_cae_encode: null argument");
+  return encode_impl(p, n, d_x, nullptr, P, d_packed, d_ws, d_mu, d_logvar, stream);
+}
+
+extern "C" int bn_cae_encode_u8(bn_cae_plan* p, int n, const uint8_t* d_x, const float* const* P,
+                                const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream) {
+  if (!d_x) BN_FAIL("bn_cae_encode_u8: null argument");
+  return encode_impl(p, n, nullptr, d_x, P, d_packed, d_ws, d_mu, d_logvar, stream);
 }
 
 extern "C" int bn_cae_decode(bn_cae_plan* p, int n, const float* d_z, const float* const* P,
@@ -342,12 +366,14 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
   float* gcur = ws + L.dpre_last;
   float* pp[2] = {ws + L.gA, ws + L.gB};
   int flip = 0;
+  int bias_done = 0;   // the kernel that produced gcur already accumulated its column sums
   for (int i = p->nl - 1; i >= 0; --i) {
     const ConvGeom& g = p->dec[i];
     ImgView big = nhwc_view(gcur, g.Hb, g.Wb, g.Cb);
     const float* small = ws + L.dec_act[i];
     BN_TRY(run_wgrad(big, small, g, n, ws + L.partial, L.partial_floats, G[g.p_w], st));
-    BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
+    if (!bias_done) BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
+    bias_done = 0;
     float* out = pp[flip];
     flip ^= 1;
     int thin = g.Cb <= 4 ? bn_launch_thin_fprop(big, g, pk + g.off_wf, g_tc_mode.load() ? pk + g.off_wft : nullptr, nullptr, out,
@@ -356,7 +382,8 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
     if (thin < 0) return thin;
     if (thin > 0)
       BN_TRY(run_igemm(p, big, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, nullptr, out, g.Hs, g.Ws,
-                       g.Cs, i > 0 ? small : nullptr, p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st));
+                       g.Cs, i > 0 ? small : nullptr, p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st,
+                       i > 0 ? G[p->dec[i - 1].p_b] : nullptr, &bias_done));
     gcur = out;
   }
   BN_TRY(bn_launch_decff_bwd(ws + L.zcopy, P[n2 + 4], gcur, n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
@@ -384,18 +411,20 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
   BN_TRY(bn_launch_heads_bwd(ws + L.enc_act[p->nl], pk + p->off_heads, d_dmu, d_dlogvar, n, p->d.n_latents,
                              p->feat_c, p->feat_h, p->feat_w, gcur, G[n2], G[n2 + 1],
                              p->d.n_heads == 2 ? G[n2 + 2] : nullptr, p->d.n_heads == 2 ? G[n2 + 3] : nullptr, st));
+  int bias_done = 0;   // the kernel that produced gcur already accumulated its column sums
   for (int i = p->nl - 1; i >= 0; --i) {
     const ConvGeom& g = p->enc[i];
     ImgView big = i == 0 ? input_view(p, d_x) : nhwc_view(ws + L.enc_act[i], g.Hb, g.Wb, g.Cb);
     BN_TRY(run_wgrad(big, gcur, g, n, ws + L.partial, L.partial_floats, G[g.p_w], st));
-    BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hs * g.Ws, g.Cs, G[g.p_b], st));
+    if (!bias_done) BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hs * g.Ws, g.Cs, G[g.p_b], st));
+    bias_done = 0;
     if (i > 0) {
       float* out = pp[flip];
       flip ^= 1;
       ImgView in = nhwc_view(gcur, g.Hs, g.Ws, g.Cs);
       BN_TRY(run_igemm(p, in, pk + g.off_wd, pk + g.off_wdt, g.k * g.k * g.Cs, nullptr, out, g.Hb, g.Wb,
                        g.Cb, ws + L.enc_act[i], p->enc_d[i], g.n_dgrad, g.dgrad_maxM, 1, g.s, n,
-                       BN_ACT_NONE, st));
+                       BN_ACT_NONE, st, G[p->enc[i - 1].p_b], &bias_done));
       gcur = out;
     }
   }

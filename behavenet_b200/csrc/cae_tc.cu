@@ -74,6 +74,7 @@ struct TcArgs {
   int gs, os, n, act;
   int ksplit;             // > 1: single-class op whose k-chunks are split over grid.z
   float* split_out;       // [ksplit][M][Co] raw partial sums (bias / activation applied by the reducer)
+  float* colsum;          // optional [Co]: += column sums of the stored output (fused bias gradient)
 };
 
 template <int BN, int STAGES>
@@ -235,8 +236,10 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
         const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
         warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, r, nullptr, BN_ACT_NONE, tile, elane);
       } else {
+        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
         warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
-                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane);
+                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, a.colsum != nullptr);
+        if (a.colsum) warp_flush_colsum(a.colsum + n0 + j * 32, cacc, elane);
       }
     }
     tc_fence_before();
@@ -429,8 +432,10 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
         const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
         warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, r, nullptr, BN_ACT_NONE, tile, elane);
       } else {
+        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
         warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
-                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane);
+                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, a.colsum != nullptr);
+        if (a.colsum) warp_flush_colsum(a.colsum + n0 + j * 32, cacc, elane);
       }
     }
     tc_fence_before();
@@ -1161,6 +1166,9 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     // ======================= epilogue ============================================================
     float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
     const int elane = tid & 31;
+    float4 cacc[NB / 32];                     // fused bias gradient: this lane's 4 columns of every 32-column block
+#pragma unroll
+    for (int j = 0; j < NB / 32; ++j) cacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     int ti = 0;
     for (long long T = t_first; T < total; T += t_step, ++ti) {
       const int f = (int)(T / h.tiles_per_frame);
@@ -1177,7 +1185,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
         const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
         const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
         const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < NB / 32; ++j) {
           uint32_t r[32];
           if (!(h.dbg & 8)) {
@@ -1188,13 +1196,17 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
             for (int q = 0; q < 32; ++q) r[q] = 0u;
           }
           warp_store_rows32(a.out, a.dact, BN_LEAK, (rvalid && !(h.dbg & 4)) ? obase + j * 32 : -1, r,
-                            a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane);
+                            a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane, cacc[j], a.colsum != nullptr);
         }
       }
       tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
       __syncwarp();
       if (elane == 0) mbar_arrive(smem_u32(acc_empty + buf));
       if (tid == 0) HALO_STAMP(ti, 5);
+    }
+    if (a.colsum) {
+#pragma unroll
+      for (int j = 0; j < NB / 32; ++j) warp_flush_colsum(a.colsum + j * 32, cacc[j], elane);
     }
   } else if (warp == 4) {
     // ======================= MMA issuer ==========================================================
@@ -1359,7 +1371,7 @@ int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
 }
 
 // returns 1 when the op does not have the stride-2 four-class shape this kernel covers
-int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream_t st) {
+int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsum_fused, cudaStream_t st) {
   static const bool off = [] { const char* e = getenv("BN_HALO"); return e && e[0] == '0'; }();
   if (off || nclasses != 4 || a.gs != 1 || a.os != 2 || a.ksplit > 1) return 1;
   if (a.Co != 32 && a.Co != 64) return 1;
@@ -1460,6 +1472,8 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream
   static const int deep = [] { const char* e = getenv("BN_HALO_DEEP"); return e ? atoi(e) : 0; }();
   if (a.Co == 32 && deep == 1) return launch_halo<32, 10, true>(local, h, st);      // one CTA per SM, 160 KB weight ring
   if (a.Co == 32) return launch_halo<32, 3, true>(local, h, st);
+  h.a.colsum = nullptr;    // not persistent: see bn_launch_igemm_tc
+  if (colsum_fused) *colsum_fused = 0;
   return launch_halo<64, 2, false>(local, h, st);
 }
 
@@ -1468,7 +1482,9 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
                        const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
-                       int act, float* split_buf, size_t split_floats, cudaStream_t st) {
+                       int act, float* split_buf, size_t split_floats, float* colsum, int* colsum_fused,
+                       cudaStream_t st) {
+  if (colsum_fused) *colsum_fused = 0;
   // shapes this kernel covers: NHWC-dense input with C % 32 == 0, C_out in {32, 64, 128, 256, 512},
   // enough rows to fill the machine (the stride-5 layers with a few hundred rows stay on the
   // CUDA-core kernel until the split-K variant lands)
@@ -1499,8 +1515,15 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   a.in = in.p; a.Hi = in.H; a.Wi = in.W; a.Ci = in.C; a.wt = wt; a.wrow = wrow; a.bias = bias; a.out = out;
   a.Ho = Ho; a.Wo = Wo; a.Co = Co; a.dact = dact; a.classes = d_classes; a.gs = gs; a.os = os;
   a.n = n; a.act = act;
-  int r = try_dgrad_halo(a, h_classes, nclasses, st);
+  // the epilogue can accumulate the column sums of what it stores (split-K leaves that to the reducer)
+  a.colsum = (ksplit == 1 && !((uintptr_t)colsum & 15)) ? colsum : nullptr;
+  if (colsum_fused) *colsum_fused = a.colsum != nullptr;
+  int r = try_dgrad_halo(a, h_classes, nclasses, colsum_fused, st);
   if (r <= 0) return r;
+  // one tile per CTA below: a flush per tile makes ~10^4 same-address atomics per column, which costs
+  // more than the separate column-sum pass saves (measured); only the persistent halo kernel fuses
+  a.colsum = nullptr;
+  if (colsum_fused) *colsum_fused = 0;
   const TmaSet* tm = get_tma_set(in, wt, wrow, Co, bn, d_classes, h_classes, nclasses, gs, n);
   if (tm) {
     TmaSet local = *tm;      // copied into the kernel parameter space (__grid_constant__)

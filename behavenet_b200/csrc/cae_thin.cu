@@ -25,6 +25,9 @@ struct ThinGeo {
   ImgView big;          // thin image (C <= 4), any strides
   int Hs, Ws, Cs;       // fat image
   int pt, pl, n;
+  // raw uint8 video (0..255) with the strides of `big`; the patch loader divides by 255 on the way
+  // to shared memory (the reference does that on the host, data_generator.py:258-263)
+  const unsigned char* big8 = nullptr;
 };
 
 __device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok) {
@@ -49,10 +52,15 @@ __device__ __forceinline__ void issue_patch(float (*patch)[PROWS][PCOLS], const 
     int r = rem / PCOLS, col = rem - r * PCOLS;
     int y = 2 * y0 - g.pt + r, x = 2 * x0 - g.pl + col;
     const bool ok = (unsigned)y < (unsigned)g.big.H && (unsigned)x < (unsigned)g.big.W;
-    const float* src = ok ? g.big.p + (long long)f * g.big.sn + (long long)y * g.big.sy + (long long)x * g.big.sx +
-                                (long long)c * g.big.sc
-                          : g.big.p;
-    cp_async4(&patch[c][r][col], src, ok);
+    const long long off = ok ? (long long)f * g.big.sn + (long long)y * g.big.sy + (long long)x * g.big.sx +
+                                   (long long)c * g.big.sc
+                             : 0;
+    if (g.big8 != nullptr) {
+      // same rounding as numpy's float32(u8) / 255
+      patch[c][r][col] = ok ? __fdiv_rn((float)__ldg(g.big8 + off), 255.f) : 0.f;
+    } else {
+      cp_async4(&patch[c][r][col], g.big.p + off, ok);
+    }
   }
 }
 
@@ -566,9 +574,11 @@ static int launch_thin_fprop(const ThinGeo& t, const float* wf, const float* bia
 }
 
 int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* wft, const float* bias,
-                         float* out, const float* dact, int act, int n, cudaStream_t st) {
+                         float* out, const float* dact, int act, int n, cudaStream_t st,
+                         const unsigned char* big_u8) {
   if (!fast_geom(g) || n <= 0) return 1;
   ThinGeo t;
+  t.big8 = big_u8;
   t.big = big; t.Hs = g.Hs; t.Ws = g.Ws; t.Cs = g.Cs; t.pt = g.pt; t.pl = g.pl; t.n = n;
   TileIter it;
   it.tiles_x = bn_cdiv(g.Ws, TW);

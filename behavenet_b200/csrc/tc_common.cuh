@@ -86,9 +86,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 //   bias  : 32 per-column biases of this tile (16-byte aligned) or nullptr
 //   act   : 0 none, 1 LeakyReLU(leak), 2 sigmoid
 //   dact  : optional activation whose sign selects the LeakyReLU derivative (1 or leak) per element
+//   colacc : optional per-lane accumulator of the stored values of this lane's 4 columns (bias gradient
+//            = column sums of a gradient image, fused here instead of re-reading the image);
+//            flush with warp_flush_colsum
 __device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const float* __restrict__ dact, float leak,
                                                   long long idx, const uint32_t (&r)[32],
-                                                  const float* __restrict__ bias, int act, float* tile, int lane) {
+                                                  const float* __restrict__ bias, int act, float* tile, int lane,
+                                                  float4& colacc, bool do_colacc) {
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     *reinterpret_cast<uint4*>(tile + lane * 32 + ((c ^ (lane & 7)) << 2)) =
@@ -126,9 +130,37 @@ __device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const
       v[2] *= d[i].z > 0.f ? 1.f : leak;
       v[3] *= d[i].w > 0.f ? 1.f : leak;
     }
-    if (ridx[i] >= 0) *(reinterpret_cast<float4*>(out + ridx[i]) + chunk) = make_float4(v[0], v[1], v[2], v[3]);
+    if (ridx[i] >= 0) {
+      *(reinterpret_cast<float4*>(out + ridx[i]) + chunk) = make_float4(v[0], v[1], v[2], v[3]);
+      if (do_colacc) { colacc.x += v[0]; colacc.y += v[1]; colacc.z += v[2]; colacc.w += v[3]; }
+    }
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const float* __restrict__ dact, float leak,
+                                                  long long idx, const uint32_t (&r)[32],
+                                                  const float* __restrict__ bias, int act, float* tile, int lane) {
+  float4 unused = make_float4(0.f, 0.f, 0.f, 0.f);
+  warp_store_rows32(out, dact, leak, idx, r, bias, act, tile, lane, unused, false);
+}
+
+// colsum[4 * chunk + e] += sum over the warp's lanes with that chunk (lane & 7) of acc: two shuffle
+// steps over the row-group bits, then 8 lanes x 4 atomics per warp
+__device__ __forceinline__ void warp_flush_colsum(float* __restrict__ colsum, float4 acc, int lane) {
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane < 8) {
+    atomicAdd(colsum + 4 * lane + 0, acc.x);
+    atomicAdd(colsum + 4 * lane + 1, acc.y);
+    atomicAdd(colsum + 4 * lane + 2, acc.z);
+    atomicAdd(colsum + 4 * lane + 3, acc.w);
+  }
 }
 
 }  // namespace bn_tc

@@ -2,8 +2,8 @@
 
 ``encode_trials`` is the B200 form of the reference loop ``model.encoding(data['images'][0])`` per
 trial (eval.py:74-98): the encoder is frame-independent, so whole groups of trials go through ONE
-launch sequence, uint8 video is scaled by 1/255 on the device (data_generator.py:258-263 does it on
-the host), and the latents stay in HBM so that ``HMM.stage_device`` can feed the E-step without a
+launch sequence, uint8 video crosses PCIe as bytes and is scaled by 1/255 inside the first layer's
+patch loader (data_generator.py:258-263 does it on the host), and the latents stay in HBM so that ``HMM.stage_device`` can feed the E-step without a
 host round trip (config C5).  ``export_latents`` keeps the reference's call signature and pickle
 format for callers that want files.
 """
@@ -17,6 +17,13 @@ def _latents_of(model, frames):
         import torch
         return torch.cat([out[0], out[1]], dim=1)          # eval.py:75-76
     return out[0]
+
+
+def _u8_loader_ok(model):
+    """The first layer's uint8 loader (bn_cae_encode_u8) covers <= 4 channels, kernel 5, stride 2."""
+    hp = model.hparams
+    return (hp['ae_input_dim'][0] <= 4 and hp['ae_encoding_kernel_size'][0] == 5 and
+            hp['ae_encoding_stride_size'][0] == 2 and hp['ae_encoding_n_channels'][0] % 32 == 0)
 
 
 def encode_trials(model, trials, frames_per_launch=4096, device=None):
@@ -46,8 +53,12 @@ def encode_trials(model, trials, frames_per_launch=4096, device=None):
             for t in group:
                 t = t if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t))
                 t = t.to(device, non_blocking=True)
-                parts.append(t.float().div_(255.0) if t.dtype == torch.uint8 else t.float())
+                parts.append(t if t.dtype == torch.uint8 else t.float())
+            if len({q.dtype for q in parts}) > 1:
+                parts = [q.float().div_(255.0) if q.dtype == torch.uint8 else q for q in parts]
             x = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+            if x.dtype == torch.uint8 and not _u8_loader_ok(model):
+                x = x.float().div_(255.0)
             lat[o:o + x.shape[0]] = _latents_of(model, x)
             o += x.shape[0]
             group, gsize = [], 0

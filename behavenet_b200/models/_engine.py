@@ -133,11 +133,11 @@ class CaeDriver:
 
     # -- helpers -----------------------------------------------------------------------------
     @staticmethod
-    def _check_input(x, what, shape_tail=None):
+    def _check_input(x, what, shape_tail=None, allow_uint8=False):
         if not x.is_cuda:
             raise RuntimeError('%s must live on a CUDA device (B200 kernels only; no CPU path)' % what)
-        if x.dtype != torch.float32:
-            raise TypeError('%s must be float32, got %s' % (what, x.dtype))
+        if x.dtype != torch.float32 and not (allow_uint8 and x.dtype == torch.uint8):
+            raise TypeError('%s must be float32%s, got %s' % (what, ' or uint8' if allow_uint8 else '', x.dtype))
         if shape_tail is not None and tuple(x.shape[1:]) != tuple(shape_tail):
             raise ValueError('%s has shape %s, expected (n, %s)' % (
                 what, tuple(x.shape), ', '.join(str(s) for s in shape_tail)))
@@ -182,9 +182,11 @@ class CaeDriver:
         n = x.shape[0]
         mu = torch.empty(n, self.L, dtype=torch.float32, device=x.device)
         logvar = torch.empty(n, self.L, dtype=torch.float32, device=x.device) if want_logvar else None
-        _lib.check(_lib.lib().bn_cae_encode(
+        # raw uint8 video is scaled by 1/255 inside the first layer's loader (encode-only path)
+        name = 'bn_cae_encode_u8' if x.dtype == torch.uint8 else 'bn_cae_encode'
+        _lib.check(getattr(_lib.lib(), name)(
             self.plan(x.device), n, x.data_ptr(), self.table(params), packed.data_ptr(),
-            ws.data_ptr(), mu.data_ptr(), _lib.ptr(logvar), _lib.stream_ptr()), 'bn_cae_encode')
+            ws.data_ptr(), mu.data_ptr(), _lib.ptr(logvar), _lib.stream_ptr()), name)
         return mu, logvar
 
     def decode(self, z, params, packed, ws, want_xhat=True, target=None, mask=None, chunk_size=0,
@@ -221,6 +223,9 @@ class EncodeFn(torch.autograd.Function):
         table = list(params) + [None] * (drv.n_params - len(params))
         packed = drv.packed(rt, table, x.device)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if needs_grad and x.dtype == torch.uint8:
+            raise NotImplementedError('uint8 frames are an encode-only input (use torch.no_grad(), or pass '
+                                      'float32 frames in [0, 1] for training)')
         ws = drv.workspace(rt, x.shape[0], x.device, fresh=needs_grad)
         variational = drv.desc.n_heads == 2
         mu, logvar = drv.encode(x, table, packed, ws, variational)

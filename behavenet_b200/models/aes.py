@@ -79,7 +79,7 @@ class ConvAEEncoder(BaseModule):
         return ps
 
     def _heads(self, x):
-        x = CaeDriver._check_input(x, 'encoder input', self._driver.img)
+        x = CaeDriver._check_input(x, 'encoder input', self._driver.img, allow_uint8=True)
         if x.requires_grad:
             raise NotImplementedError('gradients with respect to input frames are not computed')
         ps = self.kernel_params()

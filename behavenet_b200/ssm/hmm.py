@@ -205,6 +205,36 @@ def _random_rotation(n, theta=None):
     return q.dot(out).dot(q.T)
 
 
+class _PinnedPool:
+    """Grow-only pinned staging buffer shared by every HMM of the process.
+
+    Allocating ~100 MB of page-locked memory costs tens of milliseconds, more than the E-step it
+    feeds; the buffer is therefore kept and reused, guarded by an event recorded after the last
+    copy that read from it."""
+    buf = None
+    event = None
+
+    @classmethod
+    def acquire(cls, n_floats):
+        import torch
+        if cls.event is not None:
+            cls.event.synchronize()
+            cls.event = None
+        if cls.buf is None or cls.buf.numel() < n_floats:
+            cls.buf = None
+            cls.buf = torch.empty(max(n_floats, 1 << 20), dtype=torch.float32).pin_memory()
+        return cls.buf
+
+    @classmethod
+    def release(cls):
+        import torch
+        cls.event = torch.cuda.Event()
+        cls.event.record()
+
+
+_STAGE_CHUNK_ROWS = 1 << 18          # rows per host-gather / H2D piece (12 MB at D = 12)
+
+
 class _Staged:
     """Trials concatenated on the device: x (total_T, D) fp32, offsets (n+1) int64."""
 
@@ -215,13 +245,25 @@ class _Staged:
         self.lengths = lens
         self.total = int(sum(lens))
         self.max_T = max(lens) if lens else 0
-        # one pass over the host arrays straight into pinned memory, then one async H2D copy
-        pinned = torch.empty((self.total, D), dtype=torch.float32).pin_memory() if self.total else \
-            torch.empty((0, D), dtype=torch.float32)
+        self.x = torch.empty((self.total, D), dtype=torch.float32, device=device)
         if self.total:
-            np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1, D) for d in datas], 0, out=pinned.numpy())
-        self.x = pinned.to(device, non_blocking=True)
-        self._pinned = pinned          # keeps the staging buffer alive until the copy has been consumed
+            # the host arrays are gathered piece by piece into pinned memory and each piece is sent
+            # as soon as it is complete, so the copy engine overlaps the host-side gather
+            pinned = _PinnedPool.acquire(self.total * D)[:self.total * D].view(self.total, D)
+            host = pinned.numpy()
+            i = o = 0
+            while i < self.n:
+                j, rows = i, 0
+                while j < self.n and (rows == 0 or rows + lens[j] <= _STAGE_CHUNK_ROWS):
+                    rows += lens[j]
+                    j += 1
+                if rows:
+                    np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1, D) for d in datas[i:j]], 0,
+                                   out=host[o:o + rows])
+                    self.x[o:o + rows].copy_(pinned[o:o + rows], non_blocking=True)
+                o += rows
+                i = j
+            _PinnedPool.release()
         off = np.zeros(self.n + 1, np.int64)
         off[1:] = np.cumsum(lens)
         self.offsets_host = off

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define BN_MAX_LAYERS 8
-#define BN_ABI_VERSION 2
+#define BN_ABI_VERSION 3
 
 int bn_abi_version(void);
 const char* bn_last_error(void);
@@ -94,6 +94,15 @@ int bn_cae_pack_params(bn_cae_plan* plan, const float* const* d_params, void* d_
  * Layer outputs are kept in the workspace for bn_cae_encode_bwd. */
 int bn_cae_encode(bn_cae_plan* plan, int n, const float* d_x, const float* const* d_params,
                   const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream);
+
+/* The same forward pass over raw uint8 video, d_x: (n, C, H, W) bytes in 0..255 as stored in the
+ * reference's HDF5 files; the first layer's loader converts with float32(v) / 255, i.e. the host-side
+ * scaling of data/data_generator.py:258-263, so the frames cross PCIe and HBM once, at one byte per
+ * pixel (the encode-only export path, fitting/eval.py:6-118).  Inference only: the workspace it
+ * leaves is not valid for bn_cae_encode_bwd.  The first layer must have <= 4 input channels,
+ * kernel 5, stride 2 and a multiple of 32 output channels (else an error is returned). */
+int bn_cae_encode_u8(bn_cae_plan* plan, int n, const uint8_t* d_x, const float* const* d_params,
+                     const void* d_packed, void* d_ws, float* d_mu, float* d_logvar, void* stream);
 
 /* ConvAEDecoder.forward (aes.py:432-488) with the reconstruction loss fused into the last layer's
  * epilogue.  d_z: (n, L).  d_xhat: (n, C, H, W) or NULL.

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), 'missing export: ' + name
         assert name in _lib.SIGNATURES, 'no ctypes signature for ' + name
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.bn_abi_version() == 2
+    assert lib.bn_abi_version() == 3
 
 
 def test_desc_struct_matches_header():

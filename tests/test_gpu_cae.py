@@ -289,3 +289,36 @@ def test_c5_encode_then_estep_pipeline():
     for i, (gam, jnt, lz) in enumerate(ao.e_step(p, xs)):
         assert np.abs(Ez[off[i]:off[i + 1]].cpu().numpy() - gam).max() < 1e-5
         assert abs(float(logZ[i]) - lz) <= 1e-6 * abs(lz) + 1e-4
+
+
+@pytest.mark.parametrize('c,h,w', [(1, 128, 128), (2, 128, 128), (1, 64, 48), (3, 32, 32)])
+@pytest.mark.parametrize('mode', [0, 1])
+def test_uint8_frames_match_float_frames(c, h, w, mode):
+    """bn_cae_encode_u8: the first layer's loader scales raw video by float32(v) / 255 (the reference's
+    host-side scaling, data_generator.py:258-263), so the latents are BIT-identical to encoding the
+    scaled float32 frames; training on uint8 frames is refused."""
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(c, h, w, 8)
+    model = AE(copy.deepcopy(hp))
+    sd = co.init_state_dict(hp, seed=1)
+    model.load_state_dict(sd)
+    model.cuda()
+    g = torch.Generator().manual_seed(11)
+    raw = torch.randint(0, 256, (37, c, h, w), generator=g, dtype=torch.uint8)
+    raw[0] = 0
+    raw[1] = 255
+    prev = _lib.lib().bn_get_tensor_core_mode()
+    _lib.lib().bn_set_tensor_core_mode(mode)
+    try:
+        with torch.no_grad():
+            z8 = model.encoding(raw.cuda())[0]
+            zf = model.encoding((raw.float() / 255.0).cuda())[0]
+        assert torch.equal(z8, zf)
+        if mode == 0:
+            ref = co.encode(sd, hp, raw.float() / 255.0)
+            assert rel_err(z8, ref) < 1e-4
+        with pytest.raises(NotImplementedError):
+            model.encoding(raw.cuda())
+    finally:
+        _lib.lib().bn_set_tensor_core_mode(prev)

@@ -19,6 +19,12 @@ def _latents_of(model, frames):
     return out[0]
 
 
+def _scale_u8(t):
+    """float32(v) / 255 with an IEEE division (a python-scalar divisor may become a reciprocal multiply)."""
+    import torch
+    return torch.div(t.to(torch.float32), torch.full((), 255.0, dtype=torch.float32, device=t.device))
+
+
 def _u8_loader_ok(model):
     """The first layer's uint8 loader (bn_cae_encode_u8) covers <= 4 channels, kernel 5, stride 2."""
     hp = model.hparams
@@ -55,10 +61,10 @@ def encode_trials(model, trials, frames_per_launch=4096, device=None):
                 t = t.to(device, non_blocking=True)
                 parts.append(t if t.dtype == torch.uint8 else t.float())
             if len({q.dtype for q in parts}) > 1:
-                parts = [q.float().div_(255.0) if q.dtype == torch.uint8 else q for q in parts]
+                parts = [_scale_u8(q) if q.dtype == torch.uint8 else q for q in parts]
             x = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
             if x.dtype == torch.uint8 and not _u8_loader_ok(model):
-                x = x.float().div_(255.0)
+                x = _scale_u8(x)
             lat[o:o + x.shape[0]] = _latents_of(model, x)
             o += x.shape[0]
             group, gsize = [], 0

@@ -219,8 +219,26 @@ def gen_arhmm():
     print('arhmm fixture written')
 
 
+def gen_split_trials():
+    """Outputs of the reference's ``split_trials`` (data/data_generator.py:42-103; the module imports the
+    absent h5py at the top, which is stubbed) for the cases tests/test_data_generator.py replays."""
+    sys.modules.setdefault('h5py', types.ModuleType('h5py'))
+    from behavenet.data.data_generator import split_trials
+    out = {}
+    cases = [(100, 0, 8, 1, 1, 0), (103, 1, 8, 1, 1, 0), (57, 5, 5, 1, 1, 1), (23, 2, 3, 2, 1, 0), (200, 7, 6, 2, 2, 2)]
+    out['cases'] = np.array(cases)
+    for i, (n, seed, tr, va, te, gap) in enumerate(cases):
+        r = split_trials(n, rng_seed=seed, train_tr=tr, val_tr=va, test_tr=te, gap_tr=gap)
+        for k in ('train', 'val', 'test'):
+            out['%d_%s' % (i, k)] = np.asarray(r[k])
+    np.savez_compressed(os.path.join(GOLD, 'split_trials.npz'), **out)
+    print('split_trials fixture written')
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ['split_trials']:
+        return gen_split_trials()
     torch.set_num_threads(8)
     only = sys.argv[1:]
     for case in CAE_CASES:
@@ -231,6 +249,7 @@ def main():
         print('wrote', case[0], {k: tuple(v.shape) for k, v in list(res.items())[:3]})
     if not only:
         gen_arhmm()
+        gen_split_trials()
 
 
 if __name__ == '__main__':

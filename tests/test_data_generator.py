@@ -1,0 +1,137 @@
+"""Input pipeline (behavenet_b200.data): the reference generator's protocol, its trial split against golden
+outputs of the reference's own ``split_trials``, epoch coverage, frame sharding; on a GPU also the pinned /
+side-stream prefetch path and the raw-uint8 hand-off to the encoder."""
+
+import numpy as np
+import pytest
+import torch
+
+from behavenet_b200.data import ArraySource, PrefetchSessionsGenerator, split_trials
+from tests.helpers import load_golden
+
+
+def _session(n_trials, seed, c=1, h=8, w=8, name='s', ragged=True):
+    rng = np.random.RandomState(seed)
+    lens = [int(rng.randint(3, 9)) if ragged else 6 for _ in range(n_trials)]
+    return ArraySource({
+        'images': [rng.randint(0, 256, (T, c, h, w)).astype(np.uint8) for T in lens],
+        'masks': [(rng.rand(T, c, h, w) > 0.2).astype(np.float32) for T in lens],
+        'labels': [rng.randn(T, 3).astype(np.float64) for T in lens],
+    }, lab='lab', expt='expt', animal='mouse', session=name)
+
+
+def test_split_trials_matches_reference_golden():
+    gold = load_golden('split_trials')
+    for i, (n, seed, tr, va, te, gap) in enumerate(gold['cases']):
+        got = split_trials(int(n), rng_seed=int(seed), train_tr=int(tr), val_tr=int(va), test_tr=int(te),
+                           gap_tr=int(gap))
+        for k in ('train', 'val', 'test'):
+            assert np.array_equal(got[k], gold['%d_%s' % (i, k)]), (i, k)
+    with pytest.raises(ValueError):
+        split_trials(5)
+
+
+def test_generator_protocol_and_epoch_coverage_cpu():
+    srcs = [_session(40, 0, name='a'), _session(23, 1, name='b')]
+    gen = PrefetchSessionsGenerator(srcs, device='cpu', rng_seed=3, depth=2)
+    assert gen.n_datasets == 2 and len(gen) == 2
+    assert gen.n_tot_batches == {'train': 32 + 16, 'val': 4 + 2, 'test': 4 + 2}
+    np.testing.assert_allclose(gen.batch_ratios, [32 / 48, 16 / 48])
+    assert gen.datasets[1].sess_str == 'lab_expt_mouse_b'
+    for epoch in range(2):
+        for dtype in ('train', 'val'):
+            gen.reset_iterators(dtype)
+            seen = [[], []]
+            for _ in range(gen.n_tot_batches[dtype]):
+                data, sess = gen.next_batch(dtype)
+                idx = int(data['batch_idx'].item())
+                seen[sess].append(idx)
+                src = srcs[sess]
+                x = data['images']
+                assert x.dtype == torch.float32 and x.shape[0] == 1 and x.shape[1] == src.trial_length(idx)
+                # reference scaling: float32(u8) / 255 on the host (data_generator.py:258-263)
+                assert np.array_equal(x[0].numpy(), src.load('images', idx).astype('float32') / 255)
+                assert np.array_equal(data['masks'][0].numpy(), src.load('masks', idx))
+                assert data['labels'].dtype == torch.float32 and tuple(data['labels'].shape[::2]) == (1, 3)
+            for s in range(2):
+                assert sorted(seen[s]) == sorted(gen.datasets[s].batch_idxs[dtype].tolist())
+            with pytest.raises(StopIteration):
+                gen.next_batch(dtype)
+    gen.close()
+
+
+def test_generator_same_order_for_same_seed_and_numpy_mode():
+    a = PrefetchSessionsGenerator([_session(30, 0), _session(20, 1)], device='cpu', rng_seed=5, as_numpy=True)
+    b = PrefetchSessionsGenerator([_session(30, 0), _session(20, 1)], device='cpu', rng_seed=5, as_numpy=True)
+    oa = [(s, d['batch_idx']) for d, s in (a.next_batch('train') for _ in range(a.n_tot_batches['train']))]
+    ob = [(s, d['batch_idx']) for d, s in (b.next_batch('train') for _ in range(b.n_tot_batches['train']))]
+    assert oa == ob and len(set(oa)) == len(oa)
+    d, s = a.next_batch('test')
+    assert isinstance(d['images'], np.ndarray) and d['images'].dtype == np.float32 and d['images'].shape[0] == 1
+    a.close()
+    b.close()
+
+
+def test_frame_sharding_partitions_every_trial():
+    from behavenet_b200 import parallel
+    src = _session(20, 2)
+    whole = PrefetchSessionsGenerator([src], device='cpu', rng_seed=1)
+    parts = []
+    for r in range(3):
+        g = PrefetchSessionsGenerator([src], device='cpu', rng_seed=1, shard_frames=True)
+        g._frame_range = (lambda T, r=r: parallel.shard_range(T, 3, r))
+        parts.append(g)
+    for _ in range(whole.n_tot_batches['train']):
+        d, _s = whole.next_batch('train')
+        T = d['images'].shape[1]
+        pieces = [p.next_batch('train')[0] for p in parts]
+        assert all(int(q['batch_idx']) == int(d['batch_idx']) for q in pieces)
+        assert [q['shard'][1] for q in pieces] == [T] * 3
+        assert torch.equal(torch.cat([q['images'] for q in pieces], 1), d['images'])
+        assert [q['shard'][0] for q in pieces] == list(np.cumsum([0] + [q['images'].shape[1] for q in pieces[:-1]]))
+    for g in parts + [whole]:
+        g.close()
+
+
+def test_worker_errors_surface_in_next_batch():
+    src = _session(20, 0)
+    src._data['masks'][int(split_trials(20)['val'][0])] = None
+    gen = PrefetchSessionsGenerator([src], device='cpu')
+    with pytest.raises(TypeError):
+        for _ in range(gen.n_tot_batches['val']):
+            gen.next_batch('val')
+    gen.close()
+
+
+@pytest.mark.gpu
+def test_prefetch_to_device_and_raw_uint8_into_encoder():
+    """Pinned staging + side-stream copies deliver the reference's values on the device; raw uint8 batches go
+    straight into the encoder's byte loader and give the same latents as the scaled float frames."""
+    import copy
+    from oracle import cae_oracle as co
+    from behavenet_b200.models import AE
+    src = _session(30, 4, c=1, h=64, w=48, ragged=True)
+    gen = PrefetchSessionsGenerator([src], device='cuda', rng_seed=2, depth=3)
+    raw = PrefetchSessionsGenerator([src], device='cuda', rng_seed=2, depth=3, raw_uint8=True)
+    hp = co.make_hparams(1, 64, 48, 6)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.cuda().eval()
+    for epoch in range(2):
+        gen.reset_iterators('train')
+        raw.reset_iterators('train')
+        for _ in range(gen.n_tot_batches['train']):
+            d, _s = gen.next_batch('train')
+            r, _s = raw.next_batch('train')
+            idx = int(d['batch_idx'].item())
+            assert int(r['batch_idx'].item()) == idx
+            assert d['images'].is_cuda and d['images'].dtype == torch.float32
+            assert r['images'].dtype == torch.uint8
+            assert np.array_equal(d['images'][0].cpu().numpy(), src.load('images', idx).astype('float32') / 255)
+            assert np.array_equal(d['masks'][0].cpu().numpy(), src.load('masks', idx))
+            with torch.no_grad():
+                zf = model.encoding(d['images'][0])[0]
+                z8 = model.encoding(r['images'][0])[0]
+            assert torch.equal(zf, z8)
+    gen.close()
+    raw.close()

@@ -222,7 +222,8 @@ class EncodeFn(torch.autograd.Function):
         drv, rt = module._driver, module._rt
         table = list(params) + [None] * (drv.n_params - len(params))
         packed = drv.packed(rt, table, x.device)
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # (grad mode is always off inside Function.forward; needs_input_grad is what tells the two apart)
+        needs_grad = any(ctx.needs_input_grad[2:])
         if needs_grad and x.dtype == torch.uint8:
             raise NotImplementedError('uint8 frames are an encode-only input (use torch.no_grad(), or pass '
                                       'float32 frames in [0, 1] for training)')
@@ -256,7 +257,7 @@ class DecodeFn(torch.autograd.Function):
         head = [None] * (2 * drv.n_layers + 4)
         table = head + list(params)
         packed = drv.packed(rt, table, z.device)
-        needs_grad = torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in params))
+        needs_grad = any(ctx.needs_input_grad[1:])     # a private workspace per graph that will be differentiated
         ws = drv.workspace(rt, z.shape[0], z.device, fresh=needs_grad)
         xhat = drv.decode(z, table, packed, ws, want_xhat=True)
         ctx.module, ctx.ws, ctx.packed, ctx.params, ctx.n = module, ws, packed, params, z.shape[0]

@@ -322,3 +322,31 @@ def test_uint8_frames_match_float_frames(c, h, w, mode):
             model.encoding(raw.cuda())
     finally:
         _lib.lib().bn_set_tensor_core_mode(prev)
+
+
+def test_interleaved_forwards_keep_their_own_activations():
+    """Two differentiable forward passes of the same batch size followed by their backward passes: each
+    graph owns its workspace, so the gradients equal those of running them one after the other."""
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 64, 48, 6)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=2))
+    model.cuda()
+    g = torch.Generator().manual_seed(5)
+    xa = torch.rand(9, 1, 64, 48, generator=g).cuda()
+    xb = torch.rand(9, 1, 64, 48, generator=g).cuda()
+
+    def grads_of(loss):
+        model.zero_grad(set_to_none=True)
+        loss.backward()
+        return {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    ga = grads_of(((model(xa)[0] - xa) ** 2).mean())
+    gb = grads_of(((model(xb)[0] - xb) ** 2).mean())
+    la = ((model(xa)[0] - xa) ** 2).mean()
+    lb = ((model(xb)[0] - xb) ** 2).mean()          # second forward before the first backward
+    ga2 = grads_of(la)
+    gb2 = grads_of(lb)
+    for k in ga:
+        assert rel_err(ga2[k], ga[k]) < 1e-5, k     # (atomic accumulation order differs run to run)
+        assert rel_err(gb2[k], gb[k]) < 1e-5, k

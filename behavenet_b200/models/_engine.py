@@ -218,12 +218,13 @@ class EncodeFn(torch.autograd.Function):
     """Differentiable ConvAEEncoder.forward: (x, *encoder params) -> mu [, logvar]."""
 
     @staticmethod
-    def forward(ctx, module, x, *params):
+    def forward(ctx, module, grad_on, x, *params):
+        # grad_on = torch.is_grad_enabled() of the caller: inside Function.forward grad mode is always
+        # off, and needs_input_grad ignores torch.no_grad()
         drv, rt = module._driver, module._rt
         table = list(params) + [None] * (drv.n_params - len(params))
         packed = drv.packed(rt, table, x.device)
-        # (grad mode is always off inside Function.forward; needs_input_grad is what tells the two apart)
-        needs_grad = any(ctx.needs_input_grad[2:])
+        needs_grad = grad_on and any(p.requires_grad for p in params)
         if needs_grad and x.dtype == torch.uint8:
             raise NotImplementedError('uint8 frames are an encode-only input (use torch.no_grad(), or pass '
                                       'float32 frames in [0, 1] for training)')
@@ -245,19 +246,20 @@ class EncodeFn(torch.autograd.Function):
         dmu = None if dmu is None else dmu.contiguous()
         dlogvar = None if dlogvar is None else dlogvar.contiguous()
         drv.encode_bwd(ctx.x, dmu, dlogvar, list(params) + pad, ctx.packed, ctx.ws, grads + pad)
-        return (None, None) + tuple(grads)
+        return (None, None, None) + tuple(grads)
 
 
 class DecodeFn(torch.autograd.Function):
     """Differentiable ConvAEDecoder.forward: (z, *decoder params) -> x_hat."""
 
     @staticmethod
-    def forward(ctx, module, z, *params):
+    def forward(ctx, module, grad_on, z, *params):
         drv, rt = module._driver, module._rt
         head = [None] * (2 * drv.n_layers + 4)
         table = head + list(params)
         packed = drv.packed(rt, table, z.device)
-        needs_grad = any(ctx.needs_input_grad[1:])     # a private workspace per graph that will be differentiated
+        # a private workspace per graph that will be differentiated
+        needs_grad = grad_on and (z.requires_grad or any(p.requires_grad for p in params))
         ws = drv.workspace(rt, z.shape[0], z.device, fresh=needs_grad)
         xhat = drv.decode(z, table, packed, ws, want_xhat=True)
         ctx.module, ctx.ws, ctx.packed, ctx.params, ctx.n = module, ws, packed, params, z.shape[0]
@@ -272,4 +274,4 @@ class DecodeFn(torch.autograd.Function):
         grads = [torch.zeros_like(p) if p.requires_grad else None for p in params]
         dz = drv.decode_bwd(ctx.n, dxhat.contiguous(), head + list(params), ctx.packed, ctx.ws,
                             head + grads, dxhat.device)
-        return (None, dz if ctx.z_needs_grad else None) + tuple(grads)
+        return (None, None, dz if ctx.z_needs_grad else None) + tuple(grads)

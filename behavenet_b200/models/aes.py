@@ -84,8 +84,8 @@ class ConvAEEncoder(BaseModule):
             raise NotImplementedError('gradients with respect to input frames are not computed')
         ps = self.kernel_params()
         if self.hparams.get('variational', False):
-            return EncodeFn.apply(self, x, *ps)
-        return EncodeFn.apply(self, x, *ps[:-2])
+            return EncodeFn.apply(self, torch.is_grad_enabled(), x, *ps)
+        return EncodeFn.apply(self, torch.is_grad_enabled(), x, *ps[:-2])
 
     def forward(self, x, dataset=None):
         """(z, pool_idx, output_size) -- or (mu, logvar, pool_idx, output_size) if variational
@@ -156,7 +156,7 @@ class ConvAEDecoder(BaseModule):
     def forward(self, x, pool_idx=None, target_output_size=None, dataset=None):
         """x_hat of shape (n, C, H, W) (reference aes.py:432-488)."""
         x = CaeDriver._check_input(x, 'decoder input', (self._driver.L,))
-        return DecodeFn.apply(self, x, *self.kernel_params())
+        return DecodeFn.apply(self, torch.is_grad_enabled(), x, *self.kernel_params())
 
 
 class AE(BaseModel):

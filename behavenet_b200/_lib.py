@@ -60,6 +60,7 @@ SIGNATURES = {
     'bn_arhmm_workspace_bytes': (_sz, [_i, _i, _i, _i64, _i, _i]),
     'bn_arhmm_estep': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     'bn_arhmm_viterbi': (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp]),
+    'bn_host_gather_rows': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i]),
     'bn_arhmm_ar_stats': (_i, [_i, _i, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/behavenet_b200.h"
@@ -1191,5 +1192,53 @@ extern "C" int bn_arhmm_ar_stats(int K, int D, int lags, const float* d_x, const
   int grid = n_trials < 296 ? n_trials : 296;
   ar_stats_kernel<<<grid, 256, smem, st>>>(a);
   BN_LAUNCHED();
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Host-side staging helper: the reference hands ssm a python list of per-trial (T_i, D) arrays
+// (arhmm_grid_search.py:170); concatenating ~10^3 of them into the pinned staging buffer with one
+// thread costs more than the E-step they feed.  Rows are copied (fp64 sources converted) by a few
+// threads, each taking a contiguous share of the bytes.
+// ------------------------------------------------------------------------------------------------
+#include <thread>
+
+extern "C" int bn_host_gather_rows(const void* const* h_src, const int64_t* h_rows, const int32_t* h_is_f64,
+                                   int n, int D, float* h_dst, int threads) {
+  if (n < 0 || D <= 0 || (n > 0 && (!h_src || !h_rows || !h_dst))) BN_FAIL("bn_host_gather_rows: bad argument");
+  std::vector<int64_t> off(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (h_rows[i] < 0 || (h_rows[i] > 0 && !h_src[i])) BN_FAIL("bn_host_gather_rows: bad trial %d", i);
+    off[i + 1] = off[i] + h_rows[i] * D;
+  }
+  const int64_t total = off[n];
+  if (total == 0) return 0;
+  int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+  if (total < (int64_t)1 << 18) nt = 1;
+  auto work = [&](int64_t lo, int64_t hi) {          // element range [lo, hi) of the destination
+    int i = (int)(std::upper_bound(off.begin(), off.end(), lo) - off.begin()) - 1;
+    for (; i < n && off[i] < hi; ++i) {
+      const int64_t a = lo > off[i] ? lo : off[i], b = hi < off[i + 1] ? hi : off[i + 1];
+      if (b <= a) continue;
+      if (h_is_f64 && h_is_f64[i]) {
+        const double* s = (const double*)h_src[i] + (a - off[i]);
+        for (int64_t k = 0; k < b - a; ++k) h_dst[a + k] = (float)s[k];
+      } else {
+        memcpy(h_dst + a, (const float*)h_src[i] + (a - off[i]), (size_t)(b - a) * sizeof(float));
+      }
+    }
+  };
+  if (nt == 1) {
+    work(0, total);
+    return 0;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (total + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t lo = t * per, hi = lo + per < total ? lo + per : total;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
   return 0;
 }

@@ -17,6 +17,8 @@ Division of labour:
     numpy, as in ssm; they consume the GPU-reduced statistics.
 """
 
+import os
+
 import numpy as np
 
 from behavenet_b200 import _lib, parallel
@@ -235,6 +237,21 @@ class _PinnedPool:
 _STAGE_CHUNK_ROWS = 1 << 18          # rows per host-gather / H2D piece (12 MB at D = 12)
 
 
+def _gather_rows(datas, lens, D, out):
+    """Concatenate per-trial (T_i, D) host arrays into ``out`` ((sum T_i, D) float32) with the library's
+    multi-threaded row gather (bn_host_gather_rows); arrays that are not C-contiguous float32 / float64
+    are converted first."""
+    keep = [d if (d.dtype == np.float32 or d.dtype == np.float64) and d.flags.c_contiguous
+            else np.ascontiguousarray(d, dtype=np.float32) for d in datas]
+    n = len(keep)
+    ptrs = np.fromiter((d.__array_interface__['data'][0] for d in keep), dtype=np.uint64, count=n)
+    rows = np.asarray(lens, dtype=np.int64)
+    f64 = np.fromiter((d.dtype == np.float64 for d in keep), dtype=np.int32, count=n)
+    _lib.check(_lib.lib().bn_host_gather_rows(
+        ptrs.ctypes.data, rows.ctypes.data, f64.ctypes.data, n, D, out.ctypes.data,
+        min(8, os.cpu_count() or 1)), 'bn_host_gather_rows')
+
+
 class _Staged:
     """Trials concatenated on the device: x (total_T, D) fp32, offsets (n+1) int64."""
 
@@ -258,8 +275,7 @@ class _Staged:
                     rows += lens[j]
                     j += 1
                 if rows:
-                    np.concatenate([np.asarray(d, dtype=np.float32).reshape(-1, D) for d in datas[i:j]], 0,
-                                   out=host[o:o + rows])
+                    _gather_rows(datas[i:j], lens[i:j], D, host[o:o + rows])
                     self.x[o:o + rows].copy_(pinned[o:o + rows], non_blocking=True)
                 o += rows
                 i = j

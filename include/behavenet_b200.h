@@ -212,6 +212,13 @@ int bn_arhmm_ar_stats(int K, int D, int lags, const float* d_x, const int64_t* d
                       int n_trials, int64_t total_T, const float* d_Ez, double* d_stats,
                       double* d_counts, void* stream);
 
+/* Host-side staging of the list of per-trial (T_i, D) arrays the reference passes to ssm
+ * (arhmm_grid_search.py:170) into one (sum T_i, D) fp32 buffer (normally pinned memory that is then
+ * copied to d_x): h_src[i] points at trial i's C-contiguous rows, fp32 or (h_is_f64[i] != 0) fp64;
+ * h_is_f64 may be NULL.  Copies with `threads` host threads.  No device work. */
+int bn_host_gather_rows(const void* const* h_src, const int64_t* h_rows, const int32_t* h_is_f64,
+                        int n, int D, float* h_dst, int threads);
+
 #ifdef __cplusplus
 }
 #endif

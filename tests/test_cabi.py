@@ -113,3 +113,24 @@ def test_argument_validation_reports_errors():
     out = C.c_void_p()
     assert lib.bn_cae_plan_create(C.byref(d), C.byref(out)) != 0
     assert b'n_layers' in lib.bn_last_error()
+
+
+def test_host_gather_rows_matches_concatenate():
+    """bn_host_gather_rows (host-only): ragged fp32 / fp64 trials, empty trials, thread counts."""
+    import ctypes as C
+    lib = _lib.lib()
+    rng = np.random.RandomState(0)
+    for D, lens, threads in [(12, [5, 0, 1000, 3, 77], 4), (3, [1], 1), (7, [40000, 1, 0, 65000, 12], 8), (5, [], 2)]:
+        arrs = [rng.randn(T, D).astype(np.float64 if i % 2 else np.float32) for i, T in enumerate(lens)]
+        n = len(arrs)
+        ptrs = np.array([a.ctypes.data for a in arrs], dtype=np.uint64)
+        rows = np.array(lens, dtype=np.int64)
+        f64 = np.array([a.dtype == np.float64 for a in arrs], dtype=np.int32)
+        out = np.full((int(sum(lens)), D), np.nan, np.float32)
+        rc = lib.bn_host_gather_rows(ptrs.ctypes.data if n else None, rows.ctypes.data if n else None,
+                                     f64.ctypes.data if n else None, n, D, out.ctypes.data if out.size else None,
+                                     threads)
+        assert rc == 0, lib.bn_last_error()
+        ref = np.concatenate([a.astype(np.float32) for a in arrs], 0) if n else np.zeros((0, D), np.float32)
+        assert np.array_equal(out, ref)
+    assert lib.bn_host_gather_rows(None, None, None, 3, 4, None, 1) < 0

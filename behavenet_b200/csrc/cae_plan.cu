@@ -205,7 +205,8 @@ extern "C" int bn_cae_plan_create(const bn_cae_desc* desc, bn_cae_plan** out) {
     H = g.Hb; W = g.Wb; C = g.Cb;
     p->dec_sz[i + 1] = (size_t)H * W * C;
   }
-  if (H != d.in_h || W != d.in_w || C != d.in_c) { delete p; BN_FAIL("decoder output (%d,%d,%d) != input (%d,%d,%d)", C, H, W, d.in_c, d.in_h, d.in_w); }
+  // (the channel counts may differ: a conditional encoder reads label images next to the frame, aes.py:129-137)
+  if (H != d.in_h || W != d.in_w) { delete p; BN_FAIL("decoder output (%d,%d) != input (%d,%d)", H, W, d.in_h, d.in_w); }
   if (C > 4) { delete p; BN_FAIL("n_input_channels=%d > 4 has no fused output-layer kernel", C); }
   p->packed_floats = off;
   p->max_act = 0;

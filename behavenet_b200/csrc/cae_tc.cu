@@ -1166,9 +1166,10 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     // ======================= epilogue ============================================================
     float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
     const int elane = tid & 31;
-    float4 cacc[NB / 32];                     // fused bias gradient: this lane's 4 columns of every 32-column block
-#pragma unroll
-    for (int j = 0; j < NB / 32; ++j) cacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // fused bias gradient (persistent variant only, where NB = 32: one flush per CTA; a flush per tile costs
+    // more in same-address atomics than the separate column-sum pass): this lane's 4 columns
+    static_assert(!PERSIST || NB == 32, "the fused column sums keep one accumulator per lane");
+    float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
     int ti = 0;
     for (long long T = t_first; T < total; T += t_step, ++ti) {
       const int f = (int)(T / h.tiles_per_frame);
@@ -1185,7 +1186,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
         const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
         const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
         const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < NB / 32; ++j) {
           uint32_t r[32];
           if (!(h.dbg & 8)) {
@@ -1196,7 +1197,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
             for (int q = 0; q < 32; ++q) r[q] = 0u;
           }
           warp_store_rows32(a.out, a.dact, BN_LEAK, (rvalid && !(h.dbg & 4)) ? obase + j * 32 : -1, r,
-                            a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane, cacc[j], a.colsum != nullptr);
+                            a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane, cacc, PERSIST && a.colsum != nullptr);
         }
       }
       tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
@@ -1204,10 +1205,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
       if (elane == 0) mbar_arrive(smem_u32(acc_empty + buf));
       if (tid == 0) HALO_STAMP(ti, 5);
     }
-    if (a.colsum) {
-#pragma unroll
-      for (int j = 0; j < NB / 32; ++j) warp_flush_colsum(a.colsum + j * 32, cacc[j], elane);
-    }
+    if (PERSIST && a.colsum) warp_flush_colsum(a.colsum, cacc, elane);
   } else if (warp == 4) {
     // ======================= MMA issuer ==========================================================
     if ((tid & 31) == 0) {

@@ -31,12 +31,14 @@ def _unsupported(hparams):
         raise NotImplementedError('max-pool encoders are not supported by the B200 kernels')
     if any(t != 'convtranspose' for t in hparams['ae_decoding_layer_type']):
         raise NotImplementedError('unpool decoders are not supported by the B200 kernels')
-    if hparams.get('model_class') == 'cond-ae' and hparams.get('conditional_encoder', False):
-        raise NotImplementedError('conditional encoders are not supported by the B200 kernels')
 
 
-def make_desc(hparams):
-    """bn_cae_desc from the reference's hparams lists (aes.py:25-36, 229-242)."""
+def make_desc(hparams, role=None):
+    """bn_cae_desc from the reference's hparams lists (aes.py:25-36, 229-242).
+
+    role='encoder': a conditional encoder sees n_labels/2 one-hot label images next to the frame's
+    channels (aes.py:129-137).  role='decoder': the decoder's FF layer reads hparams['hidden_layer_size']
+    values, which exceeds n_ae_latents when labels join the latents (ConditionalAE, aes.py:803)."""
     _unsupported(hparams)
     d = _lib.CaeDesc()
     n = len(hparams['ae_encoding_n_channels'])
@@ -45,6 +47,10 @@ def make_desc(hparams):
     d.n_layers = n
     d.in_c, d.in_h, d.in_w = [int(v) for v in hparams['ae_input_dim']]
     d.n_latents = int(hparams['n_ae_latents'])
+    if role == 'encoder' and hparams.get('model_class') == 'cond-ae' and hparams.get('conditional_encoder', False):
+        d.in_c += int(hparams['n_labels']) // 2
+    if role == 'decoder':
+        d.n_latents = int(hparams.get('hidden_layer_size', hparams['n_ae_latents']))
     d.n_heads = 2 if hparams.get('variational', False) else 1
     for i in range(n):
         d.enc_c[i] = int(hparams['ae_encoding_n_channels'][i])
@@ -106,8 +112,8 @@ class CaeDriver:
     """Binds a geometry (desc) + a list of parameters (ordered like the C parameter table, None
     for absent entries) to the C calls."""
 
-    def __init__(self, hparams):
-        self.desc = make_desc(hparams)
+    def __init__(self, hparams, role=None):
+        self.desc = make_desc(hparams, role)
         self.n_layers = self.desc.n_layers
         self.n_params = 4 * self.n_layers + 6
         self.L = self.desc.n_latents

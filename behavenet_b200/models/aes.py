@@ -18,7 +18,7 @@ from behavenet_b200 import _lib, parallel
 from behavenet_b200.models.base import BaseModule, BaseModel
 from behavenet_b200.models._engine import CaeDriver, Runtime, EncodeFn, DecodeFn
 
-__all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'load_pretrained_ae']
+__all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'ConditionalAE', 'AEMSP', 'load_pretrained_ae']
 
 
 class ConvAEEncoder(BaseModule):
@@ -41,10 +41,10 @@ class ConvAEEncoder(BaseModule):
     def build_model(self):
         """Parameter containers named like the reference's (aes.py:55-125)."""
         hp = self.hparams
-        self._driver = CaeDriver(hp)        # raises NotImplementedError for unsupported variants
+        self._driver = CaeDriver(hp, 'encoder')     # raises NotImplementedError for unsupported variants
         self._rt = Runtime()
         self.encoder = nn.ModuleList()
-        c_in = hp['ae_input_dim'][0]
+        c_in = self._driver.img[0]          # frame channels (+ label images of a conditional encoder)
         for i, c_out in enumerate(hp['ae_encoding_n_channels']):
             x0, x1 = hp['ae_encoding_x_padding'][i]
             y0, y1 = hp['ae_encoding_y_padding'][i]
@@ -116,7 +116,7 @@ class ConvAEDecoder(BaseModule):
         hp = self.hparams
         if hp.get('ae_padding_type', 'same') not in ('same', 'valid'):
             raise ValueError('"%s" is not a valid padding type' % hp['ae_padding_type'])
-        self._driver = CaeDriver(hp)
+        self._driver = CaeDriver(hp, 'decoder')
         self._rt = Runtime()
         c0, h0, w0 = hp['ae_decoding_starting_dim']
         self.FF = nn.Linear(hp['hidden_layer_size'], c0 * h0 * w0)
@@ -303,6 +303,163 @@ class AE(BaseModel):
         numel = float(np.prod(drv.img))
         loss_val = float(sse.sum().item()) / (numel * n_total)
         return {'loss': loss_val}
+
+
+def _masked_mse(pred, true, masks=None):
+    """losses.mse (reference fitting/losses.py:36-59): mean over ALL elements."""
+    d = (pred - true) ** 2
+    return torch.mean(d * masks) if masks is not None else torch.mean(d)
+
+
+class _AutogradChunkedAE(AE):
+    """AE variants whose loss has terms outside the fused encode->decode->loss pass: the conv stacks run in
+    the same kernels through ``EncodeFn`` / ``DecodeFn`` and the few small terms in between are ordinary
+    torch ops on (n, latents) tensors, chunk by chunk like the reference."""
+
+    def invalidate_packed(self):
+        self.encoding._rt.packed_key = None
+        self.decoding._rt.packed_key = None
+
+    def _chunk_loop(self, data, chunk_size, accumulate_grad, chunk_loss, keys):
+        x = data['images'][0]
+        n = x.shape[0]
+        vals = {k: 0.0 for k in keys}
+        for b in range(0, n, chunk_size):
+            e = min(b + chunk_size, n)
+            terms = chunk_loss(b, e)
+            if accumulate_grad:
+                terms[keys[0]].backward()
+            for k in keys:
+                vals[k] += terms[k].item() * (e - b)
+        return {k: v / n for k, v in vals.items()}
+
+
+class ConditionalAE(_AutogradChunkedAE):
+    """Conditional autoencoder (reference aes.py:776-903): labels are concatenated to the latents in front
+    of the decoder's FF layer; with ``conditional_encoder`` their one-hot images are extra input channels."""
+
+    def __init__(self, hparams):
+        if hparams['model_type'] == 'linear':
+            raise NotImplementedError
+        super().__init__(hparams)
+
+    def build_model(self):
+        self.hparams['hidden_layer_size'] = self.hparams['n_ae_latents'] + self.hparams['n_labels']
+        self.encoding = ConvAEEncoder(self.hparams)
+        self.decoding = ConvAEDecoder(self.hparams)
+        self._driver = self.encoding._driver
+        self._rt = Runtime()
+
+    def forward(self, x, dataset=None, labels=None, labels_2d=None, **kwargs):
+        """(x_hat, z) (aes.py:810-836)."""
+        if self.hparams['conditional_encoder']:
+            x = torch.cat((x, labels_2d), dim=1)
+        z, pool_idx, outsize = self.encoding(x, dataset=dataset)
+        y = self.decoding(torch.cat((z, labels), dim=1), pool_idx, outsize, dataset=dataset)
+        return y, z
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200):
+        """{'loss'}: masked MSE per chunk (aes.py:838-903)."""
+        x, y = data['images'][0], data['labels'][0]
+        m = data['masks'][0] if 'masks' in data else None
+        y2d = data['labels_sc'][0] if self.hparams['conditional_encoder'] else None
+
+        def chunk_loss(b, e):
+            x_hat, _ = self.forward(x[b:e], labels=y[b:e], labels_2d=None if y2d is None else y2d[b:e],
+                                    dataset=dataset)
+            return {'loss': _masked_mse(x[b:e], x_hat, None if m is None else m[b:e])}
+        return self._chunk_loop(data, chunk_size, accumulate_grad, chunk_loss, ['loss'])
+
+
+class AEMSP(_AutogradChunkedAE):
+    """Autoencoder with matrix subspace projection (reference aes.py:906-1217): a bias-free linear map of
+    the latents predicts the labels; ``U`` completes it to an orthogonal basis when the model is saved."""
+
+    def __init__(self, hparams):
+        if hparams['model_type'] == 'linear':
+            raise NotImplementedError
+        if hparams['n_ae_latents'] < hparams['n_labels']:
+            raise ValueError('AEMSP model must contain at least as many latents as labels')
+        self.n_latents = hparams['n_ae_latents']
+        self.n_labels = hparams['n_labels']
+        super().__init__(hparams)
+
+    def build_model(self):
+        self.hparams['hidden_layer_size'] = self.hparams['n_ae_latents']
+        self.encoding = ConvAEEncoder(self.hparams)
+        self.decoding = ConvAEDecoder(self.hparams)
+        self._driver = self.encoding._driver
+        self._rt = Runtime()
+        self.projection = nn.Linear(self.n_latents, self.n_labels, bias=False)
+        with torch.no_grad():
+            self.U = nn.Linear(self.n_latents, self.n_latents, bias=False)
+
+    def forward(self, x, dataset=None, **kwargs):
+        """(x_hat, z, y) (aes.py:973-995)."""
+        z, pool_idx, outsize = self.encoding(x, dataset=dataset)
+        y = self.projection(z)
+        x_hat = self.decoding(z, pool_idx, outsize, dataset=dataset)
+        return x_hat, z, y
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200):
+        """{'loss', 'loss_mse', 'loss_msp', 'labels_r2'} (aes.py:997-1077)."""
+        from sklearn.metrics import r2_score
+        x, y = data['images'][0], data['labels'][0]
+        m = data['masks'][0] if 'masks' in data else None
+        y_hats = []
+
+        def chunk_loss(b, e):
+            x_hat, z, y_hat = self.forward(x[b:e], dataset=dataset)
+            l_mse = _masked_mse(x[b:e], x_hat, None if m is None else m[b:e])
+            l_msp = _masked_mse(y[b:e], y_hat) + _masked_mse(z, torch.matmul(y_hat, self.projection.weight))
+            y_hats.append(y_hat.detach())
+            return {'loss': l_mse + self.hparams['msp.alpha'] * l_msp, 'loss_mse': l_mse, 'loss_msp': l_msp}
+        out = self._chunk_loop(data, chunk_size, accumulate_grad, chunk_loss, ['loss', 'loss_mse', 'loss_msp'])
+        out['labels_r2'] = r2_score(y.detach().cpu().numpy(), torch.cat(y_hats, 0).cpu().numpy(),
+                                    multioutput='variance_weighted')
+        return out
+
+    def save(self, filepath):
+        self.create_orthogonal_matrix()
+        super().save(filepath)
+
+    def create_orthogonal_matrix(self):
+        """U = [projection; null-space basis of the projection] (aes.py:1083-1097)."""
+        from scipy.linalg import null_space
+        M = self.projection.weight.data.detach().cpu().numpy()
+        U = np.concatenate([M, null_space(M).T], axis=0)
+        dev = self.projection.weight.device
+        with torch.no_grad():
+            self.U.weight = nn.Parameter(torch.from_numpy(U).float().to(dev), requires_grad=False)
+
+    def get_transformed_latents(self, inputs, dataset=None, as_numpy=True):
+        """Latents in the [labels | rest] basis from frames (4-D input) or latents (2-D) (aes.py:1099-1138)."""
+        if not isinstance(inputs, torch.Tensor):
+            inputs = torch.Tensor(inputs)
+        inputs = inputs.to(self.U.weight.device)
+        z = inputs if inputs.dim() == 2 else self.encoding(inputs, dataset=dataset)[0]
+        out = self.U(z)
+        return out.cpu().detach().numpy() if as_numpy else out
+
+    def get_inverse_transformed_latents(self, latents, as_numpy=True):
+        """Back to the encoder's basis (aes.py:1140-1163)."""
+        if not isinstance(latents, torch.Tensor):
+            latents = torch.Tensor(latents)
+        out = torch.matmul(latents.to(self.U.weight.device), self.U.weight)
+        return out.cpu().detach().numpy() if as_numpy else out
+
+    def sample(self, x=None, dataset=None, latents=None, labels=None, labels_2d=None):
+        """Decode user-chosen labels and/or transformed latents, the rest taken from ``x`` (aes.py:1165-1217)."""
+        if latents is None or labels is None:
+            tr = self.get_transformed_latents(x, dataset)
+        else:
+            tr = np.full((latents.shape[0], self.n_latents), np.nan)
+        if labels is not None:
+            tr[:, :self.n_labels] = labels
+        if latents is not None:
+            tr[:, self.n_labels:] = latents
+        z = self.get_inverse_transformed_latents(torch.from_numpy(np.asarray(tr)).float(), as_numpy=False)
+        return self.decoding(z.contiguous(), None, None, dataset=dataset)
 
 
 def load_pretrained_ae(model, hparams):

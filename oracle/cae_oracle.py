@@ -157,6 +157,65 @@ def ae_loss(sd, hparams, x, masks=None, chunk_size=200, want_grads=True):
 
 
 # ------------------------------------------------------------------------------------------------
+# Conditional AE / AE with matrix subspace projection (models/aes.py:776-1217)
+# ------------------------------------------------------------------------------------------------
+
+def cond_ae_forward(sd, hparams, x, labels, labels_2d=None):
+    """ConditionalAE.forward (aes.py:810-836): labels join the latents before the decoder's FF layer; with
+    ``conditional_encoder`` their one-hot images join the frames' channels."""
+    if hparams.get('conditional_encoder', False):
+        x = torch.cat((x, labels_2d), dim=1)
+    z = encode(sd, hparams, x)
+    return decode(sd, hparams, torch.cat((z, labels), dim=1)), z
+
+
+def cond_ae_loss(sd, hparams, x, labels, labels_2d=None, masks=None, chunk_size=200, want_grads=True):
+    """ConditionalAE.loss (aes.py:838-903)."""
+    params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
+    total = 0.0
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in = x[b:e]
+        x_hat, _ = cond_ae_forward(params, hparams, x_in, labels[b:e],
+                                   None if labels_2d is None else labels_2d[b:e])
+        loss = mse(x_in, x_hat, None if masks is None else masks[b:e])
+        if want_grads:
+            loss.backward()
+        total += loss.item() * (e - b)
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return {'loss': total / x.shape[0]}, grads
+
+
+def aemsp_forward(sd, hparams, x):
+    """AEMSP.forward (aes.py:973-995) -> (x_hat, z, y)."""
+    z = encode(sd, hparams, x)
+    return decode(sd, hparams, z), z, F.linear(z, sd['projection.weight'])
+
+
+def aemsp_loss(sd, hparams, x, labels, masks=None, chunk_size=200, want_grads=True):
+    """AEMSP.loss (aes.py:997-1077) without the host-side sklearn 'labels_r2' entry:
+    mse(x) + msp.alpha * (mse(labels, y_hat) + mse(z, y_hat @ P))."""
+    frozen = ('U.weight',)
+    params = {k: v.detach().clone().requires_grad_(want_grads and k not in frozen) for k, v in sd.items()}
+    vals = {'loss': 0.0, 'loss_mse': 0.0, 'loss_msp': 0.0}
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in = x[b:e]
+        x_hat, z, y_hat = aemsp_forward(params, hparams, x_in)
+        l_mse = mse(x_in, x_hat, None if masks is None else masks[b:e])
+        l_msp = mse(labels[b:e], y_hat) + mse(z, torch.matmul(y_hat, params['projection.weight']))
+        loss = l_mse + hparams['msp.alpha'] * l_msp
+        if want_grads:
+            loss.backward()
+        bs = e - b
+        vals['loss'] += loss.item() * bs
+        vals['loss_mse'] += l_mse.item() * bs
+        vals['loss_msp'] += l_msp.item() * bs
+    for k in vals:
+        vals[k] /= x.shape[0]
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return vals, grads
+
+
+# ------------------------------------------------------------------------------------------------
 # PS-VAE (models/vaes.py)
 # ------------------------------------------------------------------------------------------------
 
@@ -295,7 +354,7 @@ def btcvae_loss(sd, hparams, x, eps, masks=None, beta=None, kl_anneal=1.0, chunk
 # ------------------------------------------------------------------------------------------------
 
 def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class='ae',
-                 n_labels=0, arch=None):
+                 n_labels=0, arch=None, conditional_encoder=False):
     """hparams dict as the reference's grid-search mains assemble it (ae_grid_search.py:20-30)."""
     from behavenet_b200.models.ae_model_architecture_generator import (
         load_default_arch, get_handcrafted_dims)
@@ -317,6 +376,10 @@ def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class
     if model_class == 'ps-vae':
         hp.update({'n_labels': n_labels, 'ps_vae.alpha': 1000, 'ps_vae.beta': 10,
                    'ps_vae.anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
+    if model_class == 'cond-ae':
+        hp.update({'n_labels': n_labels, 'conditional_encoder': conditional_encoder})
+    if model_class == 'cond-ae-msp':
+        hp.update({'n_labels': n_labels, 'msp.alpha': 0.01})
     return hp
 
 
@@ -335,6 +398,9 @@ def init_state_dict(hparams, seed=0, dtype=torch.float32):
         sd[name + '.bias'] = uniform((n_bias,), 1 / math.sqrt(fan_in))
 
     c_in = hparams['ae_input_dim'][0]
+    cond = hparams.get('model_class') == 'cond-ae'
+    if cond and hparams.get('conditional_encoder', False):
+        c_in += hparams['n_labels'] // 2                 # one-hot label images join the frames (aes.py:129-137)
     for i, c in enumerate(hparams['ae_encoding_n_channels']):
         k = hparams['ae_encoding_kernel_size'][i]
         put('encoding.encoder.conv%i' % i, (c, c_in, k, k), c_in * k * k, c)
@@ -351,8 +417,13 @@ def init_state_dict(hparams, seed=0, dtype=torch.float32):
         sd['encoding.B.weight'] = q[nl:].to(dtype).contiguous()
         sd['encoding.D.weight'] = uniform((nl,), 1 / math.sqrt(nl))
         sd['encoding.D.bias'] = uniform((nl,), 1 / math.sqrt(nl))
+    if hparams.get('model_class') == 'cond-ae-msp':
+        nl = hparams['n_labels']
+        sd['projection.weight'] = uniform((nl, L), 1 / math.sqrt(L))
+        sd['U.weight'] = uniform((L, L), 1 / math.sqrt(L))
     c0, h0, w0 = hparams['ae_decoding_starting_dim']
-    put('decoding.FF', (c0 * h0 * w0, L), L, c0 * h0 * w0)
+    Ld = L + hparams['n_labels'] if cond else L           # hidden_layer_size (aes.py:803)
+    put('decoding.FF', (c0 * h0 * w0, Ld), Ld, c0 * h0 * w0)
     c_in = c0
     for i, c in enumerate(hparams['ae_decoding_n_channels']):
         k = hparams['ae_decoding_kernel_size'][i]

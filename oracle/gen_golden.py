@@ -42,6 +42,9 @@ CAE_CASES = [
     ('psvae_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'ps-vae', 3, 200),
     ('vae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'vae', 0, 4),             # 2 chunks, beta = 2
     ('btcvae_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'beta-tcvae', 0, 4),   # 2 chunks, beta = 5
+    ('condae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae', 4, 4),      # labels join the latents, 2 chunks
+    ('condae_enc_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'cond-ae+enc', 4, 4),   # + one-hot label images as channels
+    ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4),
 ]
 
 
@@ -59,10 +62,69 @@ def synth_inputs(case):
     return out
 
 
+def run_reference_cond(case):
+    """ConditionalAE / AEMSP (aes.py:776-1217) on tests.helpers.synth_cond_inputs."""
+    from behavenet.models.aes import ConditionalAE, AEMSP
+    import importlib.util          # (a plain `import tests.helpers` would find the reference's tests package)
+    spec = importlib.util.spec_from_file_location('bn_test_helpers', os.path.join(ROOT, 'tests', 'helpers.py'))
+    helpers = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(helpers)
+    synth_cond_inputs = helpers.synth_cond_inputs
+    name, c, h, w, L, b, mc, nl, chunk = case
+    cond_enc = mc.endswith('+enc')
+    mc = mc.replace('+enc', '')
+    hp = co.make_hparams(c, h, w, L, mc, nl, conditional_encoder=cond_enc)
+    sd = co.init_state_dict(hp, seed=0)
+    inp = synth_cond_inputs(c, h, w, b, nl)
+    res = {}
+    hp_ref = dict(hp)
+    hp_ref['device'] = 'cpu'
+    model = (ConditionalAE if mc == 'cond-ae' else AEMSP)(hp_ref)
+    model.load_state_dict(sd)
+    model.eval()
+    data = {'images': inp['x'][None], 'labels': inp['labels'][None], 'masks': inp['masks'][None]}
+    if cond_enc:
+        data['labels_sc'] = inp['labels_2d'][None]
+    with torch.no_grad():
+        if mc == 'cond-ae':
+            x_hat, z = model(inp['x'], labels=inp['labels'], labels_2d=inp['labels_2d'])
+        else:
+            x_hat, z, y = model(inp['x'])
+            res['y'] = y
+    res['x_hat'], res['z'] = x_hat, z
+    model.zero_grad()
+    loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+    for k, v in loss.items():
+        res['loss.' + k] = torch.tensor(float(v), dtype=torch.float64)
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            res['grad.' + k] = p.grad.clone()
+    # pin the restatement
+    if mc == 'cond-ae':
+        xo, zo = co.cond_ae_forward(sd, hp, inp['x'], inp['labels'], inp['labels_2d'])
+        lo, go = co.cond_ae_loss(sd, hp, inp['x'], inp['labels'], inp['labels_2d'] if cond_enc else None,
+                                 inp['masks'], chunk)
+    else:
+        xo, zo, yo = co.aemsp_forward(sd, hp, inp['x'])
+        assert torch.allclose(yo, res['y'], atol=1e-5), name
+        lo, go = co.aemsp_loss(sd, hp, inp['x'], inp['labels'], inp['masks'], chunk)
+    assert torch.allclose(xo, x_hat, atol=1e-6) and torch.allclose(zo, z, atol=1e-5), name
+    for k in lo:
+        ref = float(res['loss.' + k])
+        assert abs(lo[k] - ref) <= 1e-6 * max(1.0, abs(ref)), (name, k, lo[k], ref)
+    assert set(go) == {k[5:] for k in res if k.startswith('grad.')}, name
+    for k, gref in go.items():
+        gr = res['grad.' + k]
+        assert torch.allclose(gref, gr, atol=1e-4 * float(gr.abs().max()) + 1e-8), (name, k)
+    return res
+
+
 def run_reference(case):
     from behavenet.models import AE, PSVAE
     import behavenet.models.vaes as vaes
     name, c, h, w, L, b, mc, nl, chunk = case
+    if mc.startswith('cond-ae'):
+        return run_reference_cond(case)
     hp = co.make_hparams(c, h, w, L, mc, nl)
     sd = co.init_state_dict(hp, seed=0)
     inp = synth_inputs(case)

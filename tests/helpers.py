@@ -44,6 +44,21 @@ def synth_inputs(c, h, w, L, b, n_labels=0, seed=1234, variational=False):
     return out
 
 
+def synth_cond_inputs(c, h, w, b, n_labels, seed=1234):
+    """Inputs of the label-conditioned models (cond-ae, cond-ae-msp); oracle/gen_golden.py uses this too.
+    labels_2d: one one-hot image per (x, y) label pair, as data/transforms.py MakeOneHot2D produces."""
+    g = torch.Generator().manual_seed(seed)
+    out = {'x': torch.rand(b, c, h, w, generator=g), 'labels': torch.randn(b, n_labels, generator=g)}
+    n2 = n_labels // 2
+    ys = torch.randint(0, h, (b, n2), generator=g)
+    xs = torch.randint(0, w, (b, n2), generator=g)
+    l2d = torch.zeros(b, n2, h, w)
+    l2d[torch.arange(b)[:, None], torch.arange(n2)[None, :], ys, xs] = 1.0
+    out['labels_2d'] = l2d
+    out['masks'] = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
+    return out
+
+
 def rel_err(a, b):
     """max |a - b| / max |b|."""
     a = a.detach().double().cpu() if isinstance(a, torch.Tensor) else torch.as_tensor(a).double()

@@ -350,3 +350,54 @@ def test_interleaved_forwards_keep_their_own_activations():
     for k in ga:
         assert rel_err(ga2[k], ga[k]) < 1e-5, k     # (atomic accumulation order differs run to run)
         assert rel_err(gb2[k], gb[k]) < 1e-5, k
+
+
+COND_CASES = [('condae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae', 4, 4, False),
+              ('condae_enc_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'cond-ae', 4, 4, True),
+              ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4, False)]
+
+
+@pytest.mark.parametrize('case', COND_CASES, ids=[c[0] for c in COND_CASES])
+@pytest.mark.parametrize('tc_mode', [0, 1])
+def test_conditional_models_against_reference_golden(case, tc_mode):
+    """ConditionalAE (labels joined to the latents, optional label images into the encoder) and AEMSP run
+    their conv stacks in the same kernels; outputs, loss terms and every gradient against fixtures produced
+    by the reference classes (oracle/gen_golden.py)."""
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import ConditionalAE, AEMSP
+    from tests.helpers import synth_cond_inputs
+    name, c, h, w, L, b, mc, nl, chunk, cond_enc = case
+    gold = load_golden(name)
+    hp = co.make_hparams(c, h, w, L, mc, nl, conditional_encoder=cond_enc)
+    model = (ConditionalAE if mc == 'cond-ae' else AEMSP)(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.cuda()
+    inp = {k: v.cuda() for k, v in synth_cond_inputs(c, h, w, b, nl).items()}
+    t = tols(tc_mode)
+    _lib.lib().bn_set_tensor_core_mode(tc_mode)
+    with torch.no_grad():
+        if mc == 'cond-ae':
+            out = model(inp['x'], labels=inp['labels'], labels_2d=inp['labels_2d'])
+        else:
+            out = model(inp['x'])
+            assert rel_err(out[2], gold['y']) < t['z'] * 10
+    golden_compare(gold, 'x_hat', out[0], rtol=t['xhat'], atol=t['xhat'])
+    assert rel_err(out[1], gold['z']) < t['z'] * 10
+    data = {'images': inp['x'][None], 'labels': inp['labels'][None], 'masks': inp['masks'][None]}
+    if cond_enc:
+        data['labels_sc'] = inp['labels_2d'][None]
+    model.zero_grad()
+    loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+    n_terms = 0
+    for k, v in loss.items():
+        if 'loss.' + k in gold:
+            ref = float(gold['loss.' + k])
+            assert abs(v - ref) <= 10 * t['loss'] * max(1.0, abs(ref)), (k, v, ref)
+            n_terms += 1
+    assert n_terms == (1 if mc == 'cond-ae' else 4)
+    n_grads = 0
+    for k, p in model.named_parameters():
+        if p.requires_grad and p.grad is not None:
+            compare_grad(gold, 'grad.' + k, p.grad, tc_mode, t)
+            n_grads += 1
+    assert n_grads == 24 + (1 if mc == 'cond-ae-msp' else 0)

@@ -220,3 +220,34 @@ def test_world_size_2_gloo_allreduce_and_sharding():
         assert p.exitcode == 0
     assert res[0][1] and res[1][1]
     assert res[0][2] == (0, 5) and res[1][2] == (5, 10)
+
+
+def test_conditional_models_protocol_cpu():
+    """ConditionalAE / AEMSP: state_dict names and shapes of the reference (aes.py:776-1217), deep-copyable,
+    constructor errors; no kernels are launched."""
+    import copy
+    from oracle import cae_oracle as co
+    from behavenet_b200.models import ConditionalAE, AEMSP
+    hp = co.make_hparams(2, 32, 32, 8, 'cond-ae', 4, conditional_encoder=True)
+    m = ConditionalAE(copy.deepcopy(hp))
+    sd = m.state_dict()
+    assert sd['encoding.encoder.conv0.weight'].shape == (32, 2 + 2, 5, 5)       # frames + n_labels/2 label images
+    assert sd['decoding.FF.weight'].shape[1] == 8 + 4 and sd['encoding.FF.weight'].shape[0] == 8
+    assert m.hparams['hidden_layer_size'] == 12
+    copy.deepcopy(m)
+    hp = co.make_hparams(1, 64, 48, 6, 'cond-ae-msp', 3)
+    m = AEMSP(copy.deepcopy(hp))
+    assert set(m.state_dict()) == set(co.init_state_dict(hp))
+    m.create_orthogonal_matrix()
+    U = m.U.weight.detach().numpy()
+    assert not m.U.weight.requires_grad and U.shape == (6, 6)
+    P = m.projection.weight.detach().numpy()
+    assert abs(U[:3] - P).max() == 0 and abs(U[3:] @ P.T).max() < 1e-6 and abs(U[3:] @ U[3:].T - np.eye(3)).max() < 1e-6
+    bad = dict(hp)
+    bad['n_labels'] = 7
+    with pytest.raises(ValueError):
+        AEMSP(bad)
+    lin = dict(hp)
+    lin['model_type'] = 'linear'
+    with pytest.raises(NotImplementedError):
+        AEMSP(lin)

@@ -15,7 +15,7 @@ from torch import nn
 from behavenet_b200 import _lib, parallel
 from behavenet_b200.models.aes import AE, ConvAEDecoder, ConvAEEncoder
 from behavenet_b200.models.base import DiagLinear
-from behavenet_b200.models._engine import CaeDriver
+from behavenet_b200.models._engine import CaeDriver, Runtime
 
 __all__ = ['reparameterize', 'VAE', 'BetaTCVAE', 'PSVAE', 'ConvAEPSEncoder']
 
@@ -253,6 +253,62 @@ class VAE(AE):
             vals[k] /= n_total
         vals['beta'] = beta
         return vals
+
+
+class ConditionalVAE(VAE):
+    """Conditional VAE (reference vaes.py:211-364): labels are concatenated to the sampled latents in front
+    of the decoder's FF layer.  The conv stacks run through the autograd bridges of the kernels; the Gaussian
+    log-likelihood and the analytic KL are torch ops on the outputs, chunk by chunk like the reference."""
+
+    def build_model(self):
+        self.hparams['hidden_layer_size'] = self.hparams['n_ae_latents'] + self.hparams['n_labels']
+        self.encoding = ConvAEEncoder(self.hparams)
+        self.decoding = ConvAEDecoder(self.hparams)
+        self._driver = self.encoding._driver
+        self._rt = Runtime()
+
+    def invalidate_packed(self):
+        self.encoding._rt.packed_key = None
+        self.decoding._rt.packed_key = None
+
+    def forward(self, x, dataset=None, labels=None, labels_2d=None, use_mean=False, eps=None, **kwargs):
+        """(x_hat, z, mu, logvar) (vaes.py:241-280)."""
+        if self.hparams['conditional_encoder']:
+            x = torch.cat((x, labels_2d), dim=1)
+        mu, logvar, pool_idx, outsize = self.encoding(x, dataset=dataset)
+        z = mu if use_mean else reparameterize(mu, logvar, None if eps is None else eps.to(mu.device))
+        x_hat = self.decoding(torch.cat((z, labels), dim=1), pool_idx, outsize, dataset=dataset)
+        return x_hat, z, mu, logvar
+
+    def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200, eps=None):
+        """{'loss', 'loss_ll', 'loss_kl', 'loss_mse', 'beta'} (vaes.py:282-364)."""
+        x, y = data['images'][0], data['labels'][0]
+        m = data['masks'][0] if 'masks' in data else None
+        y2d = data['labels_sc'][0] if self.hparams['conditional_encoder'] else None
+        beta = self.beta_vals[self.curr_epoch]
+        n = x.shape[0]
+        n_dims = int(np.prod(x.shape[1:]))
+        vals = {'loss': 0.0, 'loss_ll': 0.0, 'loss_kl': 0.0, 'loss_mse': 0.0}
+        for b in range(0, n, chunk_size):
+            e = min(b + chunk_size, n)
+            x_hat, _, mu, logvar = self.forward(
+                x[b:e], dataset=dataset, labels=y[b:e], labels_2d=None if y2d is None else y2d[b:e],
+                eps=None if eps is None else eps[b:e])
+            d = (x[b:e] - x_hat) ** 2
+            if m is not None:
+                d = d * m[b:e]
+            ll = torch.mean(-0.5 * LN2PI * n_dims - 0.5 * d.reshape(e - b, -1).sum(1))   # losses.py:62-96, std = 1
+            kl = torch.mean(0.5 * torch.sum(logvar.exp() - logvar + mu ** 2 - 1, dim=1))  # losses.py:130-147
+            loss = -ll + beta * kl
+            if accumulate_grad:
+                loss.backward()
+            vals['loss'] += loss.item() * (e - b)
+            vals['loss_ll'] += ll.item() * (e - b)
+            vals['loss_kl'] += kl.item() * (e - b)
+            vals['loss_mse'] += (ll.item() + 0.5 * LN2PI * n_dims) * -2.0 / n_dims * (e - b)   # losses.py:99-127
+        out = {k: v / n for k, v in vals.items()}
+        out['beta'] = beta
+        return out
 
 
 class BetaTCVAE(VAE):

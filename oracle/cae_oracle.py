@@ -320,6 +320,40 @@ def vae_loss(sd, hparams, x, eps, masks=None, beta=None, chunk_size=200, want_gr
     return vals, grads
 
 
+def cond_vae_forward(sd, hparams, x, labels, eps=None, use_mean=False):
+    """ConditionalVAE.forward (vaes.py:241-280) with conditional_encoder = False (with it the reference's
+    encoder only widens its first layer for model_class 'cond-ae', aes.py:129-137)."""
+    mu, logvar = encode(sd, hparams, x)
+    z = mu if use_mean else eps * torch.exp(logvar) + mu
+    return decode(sd, hparams, torch.cat((z, labels), dim=1)), z, mu, logvar
+
+
+def cond_vae_loss(sd, hparams, x, labels, eps, masks=None, beta=None, chunk_size=200, want_grads=True):
+    """ConditionalVAE.loss (vaes.py:282-364)."""
+    beta = hparams['vae.beta'] if beta is None else beta
+    params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
+    vals = {'loss': 0.0, 'loss_ll': 0.0, 'loss_kl': 0.0, 'loss_mse': 0.0}
+    n_pix = int(np.prod(x.shape[1:]))
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_in = x[b:e]
+        x_hat, _, mu, logvar = cond_vae_forward(params, hparams, x_in, labels[b:e], eps[b:e])
+        ll = gaussian_ll(x_in, x_hat, None if masks is None else masks[b:e])
+        kl = kl_div_to_std_normal(mu, logvar)
+        loss = -ll + beta * kl
+        if want_grads:
+            loss.backward()
+        bs = e - b
+        vals['loss'] += loss.item() * bs
+        vals['loss_ll'] += ll.item() * bs
+        vals['loss_kl'] += kl.item() * bs
+        vals['loss_mse'] += gaussian_ll_to_mse(ll.item(), n_pix) * bs
+    for k in vals:
+        vals[k] /= x.shape[0]
+    vals['beta'] = beta
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return vals, grads
+
+
 def btcvae_loss(sd, hparams, x, eps, masks=None, beta=None, kl_anneal=1.0, chunk_size=200, want_grads=True):
     """BetaTCVAE.loss (vaes.py:411-503): -ll + kl * MI + beta * TC + kl * DWKL per chunk;
     'loss_mse' reproduces the running-sum quirk of vaes.py:490-491."""
@@ -378,6 +412,9 @@ def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class
                    'ps_vae.anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
     if model_class == 'cond-ae':
         hp.update({'n_labels': n_labels, 'conditional_encoder': conditional_encoder})
+    if model_class == 'cond-vae':
+        hp.update({'n_labels': n_labels, 'conditional_encoder': False, 'vae.beta': 2.0, 'vae.beta_anneal_epochs': 0,
+                   'max_n_epochs': 10, 'variational': True})
     if model_class == 'cond-ae-msp':
         hp.update({'n_labels': n_labels, 'msp.alpha': 0.01})
     return hp
@@ -398,8 +435,8 @@ def init_state_dict(hparams, seed=0, dtype=torch.float32):
         sd[name + '.bias'] = uniform((n_bias,), 1 / math.sqrt(fan_in))
 
     c_in = hparams['ae_input_dim'][0]
-    cond = hparams.get('model_class') == 'cond-ae'
-    if cond and hparams.get('conditional_encoder', False):
+    cond = hparams.get('model_class') in ('cond-ae', 'cond-vae')
+    if hparams.get('model_class') == 'cond-ae' and hparams.get('conditional_encoder', False):
         c_in += hparams['n_labels'] // 2                 # one-hot label images join the frames (aes.py:129-137)
     for i, c in enumerate(hparams['ae_encoding_n_channels']):
         k = hparams['ae_encoding_kernel_size'][i]

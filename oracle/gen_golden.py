@@ -45,6 +45,7 @@ CAE_CASES = [
     ('condae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae', 4, 4),      # labels join the latents, 2 chunks
     ('condae_enc_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'cond-ae+enc', 4, 4),   # + one-hot label images as channels
     ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4),
+    ('condvae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-vae', 4, 4),
 ]
 
 
@@ -62,9 +63,56 @@ def synth_inputs(case):
     return out
 
 
+def run_reference_cond_vae(ConditionalVAE, vaes, name, hp, hp_ref, sd, inp, chunk):
+    model = ConditionalVAE(hp_ref)
+    model.load_state_dict(sd)
+    model.eval()
+    eps_all = inp['eps']
+    state = {'pos': 0}
+    orig = torch.randn_like
+
+    def fake_randn_like(t, *a, **k):         # inject eps into reparameterize (vaes.py:33-35)
+        n = t.shape[0]
+        e = eps_all[state['pos']:state['pos'] + n]
+        state['pos'] += n
+        return e.to(t.dtype)
+    vaes.torch.randn_like = fake_randn_like
+    res = {}
+    try:
+        with torch.no_grad():
+            x_hat, z, mu, logvar = model(inp['x'], labels=inp['labels'])
+        res.update(x_hat=x_hat, z=z, mu=mu, logvar=logvar)
+        model.curr_epoch = 1
+        model.zero_grad()
+        state['pos'] = 0
+        loss = model.loss({'images': inp['x'][None], 'labels': inp['labels'][None], 'masks': inp['masks'][None]},
+                          accumulate_grad=True, chunk_size=chunk)
+    finally:
+        vaes.torch.randn_like = orig
+    for k, v in loss.items():
+        res['loss.' + k] = torch.tensor(float(v), dtype=torch.float64)
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            res['grad.' + k] = p.grad.clone()
+    o = co.cond_vae_forward(sd, hp, inp['x'], inp['labels'], inp['eps'])
+    for a, bref in zip(o, (x_hat, z, mu, logvar)):
+        assert torch.allclose(a, bref, atol=2e-5), name
+    lo, go = co.cond_vae_loss(sd, hp, inp['x'], inp['labels'], inp['eps'], inp['masks'], chunk_size=chunk)
+    for k in lo:
+        ref = float(res['loss.' + k])
+        assert abs(lo[k] - ref) <= 1e-5 * max(1.0, abs(ref)), (name, k, lo[k], ref)
+    assert set(go) == {k[5:] for k in res if k.startswith('grad.')}, name
+    for k, gref in go.items():
+        gr = res['grad.' + k]
+        assert torch.allclose(gref, gr, atol=1e-4 * float(gr.abs().max()) + 1e-7), (name, k)
+    return res
+
+
 def run_reference_cond(case):
     """ConditionalAE / AEMSP (aes.py:776-1217) on tests.helpers.synth_cond_inputs."""
     from behavenet.models.aes import ConditionalAE, AEMSP
+    from behavenet.models.vaes import ConditionalVAE
+    import behavenet.models.vaes as vaes
     import importlib.util          # (a plain `import tests.helpers` would find the reference's tests package)
     spec = importlib.util.spec_from_file_location('bn_test_helpers', os.path.join(ROOT, 'tests', 'helpers.py'))
     helpers = importlib.util.module_from_spec(spec)
@@ -75,10 +123,12 @@ def run_reference_cond(case):
     mc = mc.replace('+enc', '')
     hp = co.make_hparams(c, h, w, L, mc, nl, conditional_encoder=cond_enc)
     sd = co.init_state_dict(hp, seed=0)
-    inp = synth_cond_inputs(c, h, w, b, nl)
+    inp = synth_cond_inputs(c, h, w, b, nl, n_latents=L if mc == 'cond-vae' else 0)
     res = {}
     hp_ref = dict(hp)
     hp_ref['device'] = 'cpu'
+    if mc == 'cond-vae':
+        return run_reference_cond_vae(ConditionalVAE, vaes, name, hp, hp_ref, sd, inp, chunk)
     model = (ConditionalAE if mc == 'cond-ae' else AEMSP)(hp_ref)
     model.load_state_dict(sd)
     model.eval()
@@ -123,7 +173,7 @@ def run_reference(case):
     from behavenet.models import AE, PSVAE
     import behavenet.models.vaes as vaes
     name, c, h, w, L, b, mc, nl, chunk = case
-    if mc.startswith('cond-ae'):
+    if mc.startswith('cond-'):
         return run_reference_cond(case)
     hp = co.make_hparams(c, h, w, L, mc, nl)
     sd = co.init_state_dict(hp, seed=0)

@@ -44,7 +44,7 @@ def synth_inputs(c, h, w, L, b, n_labels=0, seed=1234, variational=False):
     return out
 
 
-def synth_cond_inputs(c, h, w, b, n_labels, seed=1234):
+def synth_cond_inputs(c, h, w, b, n_labels, seed=1234, n_latents=0):
     """Inputs of the label-conditioned models (cond-ae, cond-ae-msp); oracle/gen_golden.py uses this too.
     labels_2d: one one-hot image per (x, y) label pair, as data/transforms.py MakeOneHot2D produces."""
     g = torch.Generator().manual_seed(seed)
@@ -56,6 +56,8 @@ def synth_cond_inputs(c, h, w, b, n_labels, seed=1234):
     l2d[torch.arange(b)[:, None], torch.arange(n2)[None, :], ys, xs] = 1.0
     out['labels_2d'] = l2d
     out['masks'] = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
+    if n_latents:
+        out['eps'] = torch.randn(b, n_latents, generator=g)
     return out
 
 

@@ -354,7 +354,8 @@ def test_interleaved_forwards_keep_their_own_activations():
 
 COND_CASES = [('condae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae', 4, 4, False),
               ('condae_enc_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'cond-ae', 4, 4, True),
-              ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4, False)]
+              ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4, False),
+              ('condvae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-vae', 4, 4, False)]
 
 
 @pytest.mark.parametrize('case', COND_CASES, ids=[c[0] for c in COND_CASES])
@@ -364,20 +365,23 @@ def test_conditional_models_against_reference_golden(case, tc_mode):
     their conv stacks in the same kernels; outputs, loss terms and every gradient against fixtures produced
     by the reference classes (oracle/gen_golden.py)."""
     from behavenet_b200 import _lib
-    from behavenet_b200.models import ConditionalAE, AEMSP
+    from behavenet_b200.models import ConditionalAE, ConditionalVAE, AEMSP
     from tests.helpers import synth_cond_inputs
     name, c, h, w, L, b, mc, nl, chunk, cond_enc = case
     gold = load_golden(name)
     hp = co.make_hparams(c, h, w, L, mc, nl, conditional_encoder=cond_enc)
-    model = (ConditionalAE if mc == 'cond-ae' else AEMSP)(copy.deepcopy(hp))
+    model = {'cond-ae': ConditionalAE, 'cond-ae-msp': AEMSP, 'cond-vae': ConditionalVAE}[mc](copy.deepcopy(hp))
     model.load_state_dict(co.init_state_dict(hp, seed=0))
     model.cuda()
-    inp = {k: v.cuda() for k, v in synth_cond_inputs(c, h, w, b, nl).items()}
+    inp = {k: v.cuda() for k, v in synth_cond_inputs(c, h, w, b, nl, n_latents=L if mc == 'cond-vae' else 0).items()}
     t = tols(tc_mode)
     _lib.lib().bn_set_tensor_core_mode(tc_mode)
     with torch.no_grad():
         if mc == 'cond-ae':
             out = model(inp['x'], labels=inp['labels'], labels_2d=inp['labels_2d'])
+        elif mc == 'cond-vae':
+            out = model(inp['x'], labels=inp['labels'], eps=inp['eps'])
+            assert rel_err(out[2], gold['mu']) < t['z'] * 10 and rel_err(out[3], gold['logvar']) < t['z'] * 10
         else:
             out = model(inp['x'])
             assert rel_err(out[2], gold['y']) < t['z'] * 10
@@ -387,17 +391,21 @@ def test_conditional_models_against_reference_golden(case, tc_mode):
     if cond_enc:
         data['labels_sc'] = inp['labels_2d'][None]
     model.zero_grad()
-    loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+    if mc == 'cond-vae':
+        model.curr_epoch = 1
+        loss = model.loss(data, accumulate_grad=True, chunk_size=chunk, eps=inp['eps'])
+    else:
+        loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
     n_terms = 0
     for k, v in loss.items():
         if 'loss.' + k in gold:
             ref = float(gold['loss.' + k])
             assert abs(v - ref) <= 10 * t['loss'] * max(1.0, abs(ref)), (k, v, ref)
             n_terms += 1
-    assert n_terms == (1 if mc == 'cond-ae' else 4)
+    assert n_terms == {'cond-ae': 1, 'cond-ae-msp': 4, 'cond-vae': 5}[mc]
     n_grads = 0
     for k, p in model.named_parameters():
         if p.requires_grad and p.grad is not None:
             compare_grad(gold, 'grad.' + k, p.grad, tc_mode, t)
             n_grads += 1
-    assert n_grads == 24 + (1 if mc == 'cond-ae-msp' else 0)
+    assert n_grads == 24 + {'cond-ae': 0, 'cond-ae-msp': 1, 'cond-vae': 2}[mc]

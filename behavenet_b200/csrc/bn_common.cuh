@@ -38,6 +38,40 @@ extern std::atomic<long long> g_bn_launches;
 
 static inline int bn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A training step is ~70 dependent launches of 10-150 us kernels; with
+// plain stream order every boundary costs the drain of one grid plus the launch and per-CTA set-up
+// (barrier init, tcgen05.alloc, descriptor prefetch: ~2 us) of the next.  Kernels launched through
+// bn_launch() carry cudaLaunchAttributeProgrammaticStreamSerialization: each calls bn_pdl_trigger() first
+// (so the NEXT grid may be scheduled as soon as every CTA of this one has started and SM resources free
+// up), does its set-up, and calls bn_pdl_wait() before its first global-memory access (which returns once
+// the PREVIOUS grid has completed and flushed).  Rule: every kernel launched through bn_launch() executes
+// bn_pdl_wait() in all threads, so completion of a grid implies completion of everything before it.
+// Kernels launched with <<<>>> keep plain stream order on both sides.  BN_PDL=0 drops the attribute.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void bn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void bn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+bool bn_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t bn_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = bn_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+
 // One tile class of an implicit GEMM: a logical pixel grid (Hm x Wm per frame) whose every pixel
 // uses the same tap list.  fprop-form ops have one class; dgrad-form (transposed) ops have one
 // class per output residue (stride^2 classes).

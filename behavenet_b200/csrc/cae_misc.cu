@@ -38,6 +38,8 @@ struct ThinArgs {
 constexpr int THIN_SSE_SLOTS = 8;
 
 __global__ void __launch_bounds__(256) thin_dgrad_kernel(const ThinArgs a) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ float wsm[];
   __shared__ double sse_sm[THIN_SSE_SLOTS];
   const int t = threadIdx.x;
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(256) thin_dgrad_kernel(const ThinArgs a) {
 
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ dxhat, const float* __restrict__ xhat,
                                    float* __restrict__ dpre, int n, int C, int H, int W) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // NHWC index
   long long tot = (long long)n * C * H * W;
   if (i >= tot) return;
@@ -155,6 +159,8 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ dxhat, const float*
 __global__ void __launch_bounds__(256) colsum_wide_kernel(const float* __restrict__ x, long long M,
                                                           int C, long long rows_per_block,
                                                           float* __restrict__ out) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   __shared__ float red[8][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int c = blockIdx.x * 32 + tx;
@@ -175,6 +181,8 @@ __global__ void __launch_bounds__(256) colsum_wide_kernel(const float* __restric
 __global__ void __launch_bounds__(256) colsum_thin_kernel(const float* __restrict__ x,
                                                           long long total, int C,
                                                           float* __restrict__ out) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   // C <= 4: flat grid-stride walk, per-thread accumulators per column
   __shared__ float red[8][4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -214,6 +222,8 @@ __device__ __forceinline__ float round_tf32(float x) {
 //   pack_conv_cols_kernel : block = 32 cs x 8 cb x all taps -> wf [tap][cb][cs], wdt [cb][tap][cs]
 __global__ void __launch_bounds__(256) pack_conv_rows_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
                                                              float* __restrict__ wd, float* __restrict__ wft) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ float prow[];                 // [cb][kk + 1] (odd pitch when kk is even is not needed: reads are strided by kk+1)
   const int cs = blockIdx.x;
   const int n = Cb * kk;
@@ -234,6 +244,8 @@ __global__ void __launch_bounds__(256) pack_conv_rows_kernel(const float* __rest
 constexpr int PCS = 32, PCB = 8;
 __global__ void __launch_bounds__(256) pack_conv_cols_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
                                                              float* __restrict__ wf, float* __restrict__ wdt) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ float brick[];                // [cs 32][PCB * kk + 1]
   const int cs0 = blockIdx.x * PCS, cb0 = blockIdx.y * PCB;
   const int ncb = min(PCB, Cb - cb0), ncs = min(PCS, Cs - cs0);
@@ -255,6 +267,8 @@ __global__ void __launch_bounds__(256) pack_conv_cols_kernel(const float* __rest
 
 __global__ void pack_heads_kernel(const float* __restrict__ w0, const float* __restrict__ w1, int L,
                                   int C, int H, int W, float* __restrict__ wcat) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long F = (long long)C * H * W;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long tot = (w1 ? 2 : 1) * L * F;
@@ -280,6 +294,8 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ b1, int n, int L,
                                                         int nheads, int F, float* __restrict__ mu,
                                                         float* __restrict__ logvar) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   int warp = (blockIdx.x * 256 + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int HJ = nheads * L;
@@ -312,6 +328,8 @@ __device__ __forceinline__ float head_grad(const float* dmu, const float* dlv, i
 __global__ void heads_bwd_data_kernel(const float* __restrict__ feat, const float* __restrict__ wcat,
                                       const float* __restrict__ dmu, const float* __restrict__ dlv,
                                       int n, int L, int HJ, int F, float* __restrict__ dpre) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * F) return;
   int f = (int)(i / F);
@@ -328,6 +346,8 @@ __global__ void __launch_bounds__(256) heads_bwd_w_kernel(const float* __restric
                                                           const float* __restrict__ dlv, int n, int L, int HJ, int C, int H,
                                                           int W, int fper, float* __restrict__ gw0,
                                                           float* __restrict__ gw1) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long F = (long long)C * H * W;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)HJ * F) return;
@@ -357,6 +377,8 @@ __global__ void __launch_bounds__(256) heads_bwd_w_kernel(const float* __restric
 __global__ void __launch_bounds__(128) heads_bwd_b_kernel(const float* __restrict__ dmu, const float* __restrict__ dlv,
                                                           int n, int L, int HJ, float* __restrict__ gb0,
                                                           float* __restrict__ gb1) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   __shared__ float red[4];
   const int hj = blockIdx.x;
   float* g = hj < L ? gb0 : gb1;
@@ -384,6 +406,8 @@ __device__ __forceinline__ long long nhwc_to_chw(long long inhwc, int C, int H, 
 __global__ void decff_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w,
                                  const float* __restrict__ b, int n, int L, int C, int H, int W,
                                  float* __restrict__ h0) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long F = (long long)C * H * W;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * F) return;
@@ -402,6 +426,8 @@ template <int LMAX>
 __global__ void __launch_bounds__(256) decff_bwd_z_kernel(const float* __restrict__ w,
                                                           const float* __restrict__ dh0, int n, int L,
                                                           int C, int H, int W, int j0, float* __restrict__ dz) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   __shared__ float red[8][LMAX];
   const int f = blockIdx.x;
   const long long F = (long long)C * H * W;
@@ -435,6 +461,8 @@ __global__ void __launch_bounds__(256) decff_bwd_z_kernel(const float* __restric
 __global__ void __launch_bounds__(256) decff_bwd_w_kernel(const float* __restrict__ z, const float* __restrict__ dh0, int n,
                                                           int L, int C, int H, int W, int fper, float* __restrict__ gw,
                                                           float* __restrict__ gb) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long F = (long long)C * H * W;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over F * (L + 1)
   if (i >= F * (L + 1)) return;
@@ -485,7 +513,7 @@ int bn_launch_thin_dgrad(const float* small, const ConvGeom& g, const float* wd,
     BN_CUDA(cudaFuncSetAttribute(thin_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   long long npix = (long long)n * g.Hb * g.Wb;
-  thin_dgrad_kernel<<<bn_cdiv(npix, 256), 256, smem, st>>>(a);
+  BN_CUDA(bn_launch(thin_dgrad_kernel, dim3(bn_cdiv(npix, 256)), 256, smem, st, a));
   BN_LAUNCHED();
   return 0;
 }
@@ -494,7 +522,7 @@ int bn_launch_sigmoid_bwd(const float* dxhat, const float* xhat, float* dpre, in
                           int W, cudaStream_t st) {
   long long tot = (long long)n * C * H * W;
   if (tot == 0) return 0;
-  sigmoid_bwd_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(dxhat, xhat, dpre, n, C, H, W);
+  BN_CUDA(bn_launch(sigmoid_bwd_kernel, dim3(bn_cdiv(tot, 256)), 256, 0, st, dxhat, xhat, dpre, n, C, H, W));
   BN_LAUNCHED();
   return 0;
 }
@@ -504,13 +532,13 @@ int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_
   if (C <= 4) {
     long long total = M * C;
     int blocks = (int)min((long long)148 * 8, (total + 255) / 256);
-    colsum_thin_kernel<<<blocks, 256, 0, st>>>(x, total, C, out);
+    BN_CUDA(bn_launch(colsum_thin_kernel, dim3(blocks), 256, 0, st, x, total, C, out));
   } else {
     int gx = bn_cdiv(C, 32);
     int gy = (int)min((long long)bn_cdiv(148 * 8, gx), (M + 63) / 64);
     if (gy < 1) gy = 1;
     long long rpb = (M + gy - 1) / gy;
-    colsum_wide_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, M, C, rpb, out);
+    BN_CUDA(bn_launch(colsum_wide_kernel, dim3(gx, gy), 256, 0, st, x, M, C, rpb, out));
   }
   BN_LAUNCHED();
   return 0;
@@ -530,9 +558,9 @@ int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, flo
     BN_CUDA(cudaFuncSetAttribute(pack_conv_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     cfg_cols = smem_cols;
   }
-  pack_conv_rows_kernel<<<Cs, 256, smem_rows, st>>>(src, Cs, Cb, kk, wd, wft);
+  BN_CUDA(bn_launch(pack_conv_rows_kernel, dim3(Cs), 256, smem_rows, st, src, Cs, Cb, kk, wd, wft));
   BN_LAUNCHED();
-  pack_conv_cols_kernel<<<dim3(bn_cdiv(Cs, PCS), bn_cdiv(Cb, PCB)), 256, smem_cols, st>>>(src, Cs, Cb, kk, wf, wdt);
+  BN_CUDA(bn_launch(pack_conv_cols_kernel, dim3(bn_cdiv(Cs, PCS), bn_cdiv(Cb, PCB)), 256, smem_cols, st, src, Cs, Cb, kk, wf, wdt));
   BN_LAUNCHED();
   return 0;
 }
@@ -540,7 +568,7 @@ int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, flo
 int bn_launch_pack_heads(const float* w0, const float* w1, int L, int C, int H, int W, float* wcat,
                          cudaStream_t st) {
   long long tot = (long long)(w1 ? 2 : 1) * L * C * H * W;
-  pack_heads_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(w0, w1, L, C, H, W, wcat);
+  BN_CUDA(bn_launch(pack_heads_kernel, dim3(bn_cdiv(tot, 256)), 256, 0, st, w0, w1, L, C, H, W, wcat));
   BN_LAUNCHED();
   return 0;
 }
@@ -549,7 +577,7 @@ int bn_launch_heads_fwd(const float* feat, const float* wcat, const float* b0, c
                         int n, int L, int nheads, int F, float* mu, float* logvar, cudaStream_t st) {
   long long warps = (long long)n * nheads * L;
   if (warps == 0) return 0;
-  heads_fwd_kernel<<<bn_cdiv(warps * 32, 256), 256, 0, st>>>(feat, wcat, b0, b1, n, L, nheads, F, mu, logvar);
+  BN_CUDA(bn_launch(heads_fwd_kernel, dim3(bn_cdiv(warps * 32, 256)), 256, 0, st, feat, wcat, b0, b1, n, L, nheads, F, mu, logvar));
   BN_LAUNCHED();
   return 0;
 }
@@ -560,13 +588,13 @@ int bn_launch_heads_bwd(const float* feat, const float* wcat, const float* dmu, 
   if (n <= 0) return 0;
   int F = C * H * W;
   int HJ = dlogvar ? 2 * L : L;
-  heads_bwd_data_kernel<<<bn_cdiv((long long)n * F, 256), 256, 0, st>>>(feat, wcat, dmu, dlogvar, n, L, HJ, F, dpre_feat);
+  BN_CUDA(bn_launch(heads_bwd_data_kernel, dim3(bn_cdiv((long long)n * F, 256)), 256, 0, st, feat, wcat, dmu, dlogvar, n, L, HJ, F, dpre_feat));
   BN_LAUNCHED();
   const int fsplit = n >= 64 ? 8 : 1, fper = bn_cdiv(n, fsplit);
-  heads_bwd_w_kernel<<<dim3(bn_cdiv((long long)HJ * F, 256), fsplit), 256, 0, st>>>(feat, dmu, dlogvar, n, L, HJ, C, H, W,
-                                                                                   fper, gw0, gw1);
+  BN_CUDA(bn_launch(heads_bwd_w_kernel, dim3(bn_cdiv((long long)HJ * F, 256), fsplit), 256, 0, st, feat, dmu, dlogvar, n, L, HJ, C, H, W,
+                                                                                   fper, gw0, gw1));
   BN_LAUNCHED();
-  heads_bwd_b_kernel<<<HJ, 128, 0, st>>>(dmu, dlogvar, n, L, HJ, gb0, gb1);
+  BN_CUDA(bn_launch(heads_bwd_b_kernel, dim3(HJ), 128, 0, st, dmu, dlogvar, n, L, HJ, gb0, gb1));
   BN_LAUNCHED();
   return 0;
 }
@@ -575,7 +603,7 @@ int bn_launch_decff_fwd(const float* z, const float* w, const float* b, int n, i
                         int W, float* h0, cudaStream_t st) {
   long long tot = (long long)n * C * H * W;
   if (tot == 0) return 0;
-  decff_fwd_kernel<<<bn_cdiv(tot, 256), 256, 0, st>>>(z, w, b, n, L, C, H, W, h0);
+  BN_CUDA(bn_launch(decff_fwd_kernel, dim3(bn_cdiv(tot, 256)), 256, 0, st, z, w, b, n, L, C, H, W, h0));
   BN_LAUNCHED();
   return 0;
 }
@@ -585,18 +613,18 @@ int bn_launch_decff_bwd(const float* z, const float* w, const float* dh0, int n,
   if (n <= 0) return 0;
   if (dz) {
     if (L <= 16) {
-      decff_bwd_z_kernel<16><<<n, 256, 0, st>>>(w, dh0, n, L, C, H, W, 0, dz);
+      BN_CUDA(bn_launch(decff_bwd_z_kernel<16>, dim3(n), 256, 0, st, w, dh0, n, L, C, H, W, 0, dz));
       BN_LAUNCHED();
     } else {
       for (int j0 = 0; j0 < L; j0 += 32) {
-        decff_bwd_z_kernel<32><<<n, 256, 0, st>>>(w, dh0, n, L, C, H, W, j0, dz);
+        BN_CUDA(bn_launch(decff_bwd_z_kernel<32>, dim3(n), 256, 0, st, w, dh0, n, L, C, H, W, j0, dz));
         BN_LAUNCHED();
       }
     }
   }
   long long F = (long long)C * H * W;
   const int fsplit = n >= 64 ? 8 : 1, fper = bn_cdiv(n, fsplit);
-  decff_bwd_w_kernel<<<dim3(bn_cdiv(F * (L + 1), 256), fsplit), 256, 0, st>>>(z, dh0, n, L, C, H, W, fper, gw, gb);
+  BN_CUDA(bn_launch(decff_bwd_w_kernel, dim3(bn_cdiv(F * (L + 1), 256), fsplit), 256, 0, st, z, dh0, n, L, C, H, W, fper, gw, gb));
   BN_LAUNCHED();
   return 0;
 }

@@ -12,6 +12,11 @@ std::atomic<long long> g_bn_launches{0};
 static std::atomic<int> g_tc_mode{1};
 
 extern "C" int bn_abi_version(void) { return BN_ABI_VERSION; }
+
+bool bn_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("BN_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 extern "C" const char* bn_last_error(void) { return g_bn_err; }
 extern "C" int64_t bn_launch_count(void) { return (int64_t)g_bn_launches.load(); }
 extern "C" int bn_set_tensor_core_mode(int mode) {

@@ -375,6 +375,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgArgs a) {
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Ktot,
                                                            int Cs, int Cb, int KK, const TapClass* __restrict__ cls,
                                                            float* __restrict__ grad) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   __shared__ float tile[32][33];
   __shared__ unsigned char inv[BN_MAX_TAPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -477,7 +479,7 @@ int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, i
   int gz = 2 * 148 / (gx * gy);
   if (gz > splits / 4) gz = splits / 4;
   if (gz < 1) gz = 1;
-  wgrad_reduce_kernel<<<dim3(gx, gy, gz), 256, 0, st>>>(partial, splits, Ktot, Cs, Cb, KK, cls, grad);
+  BN_CUDA(bn_launch(wgrad_reduce_kernel, dim3(gx, gy, gz), 256, 0, st, partial, splits, Ktot, Cs, Cb, KK, cls, grad));
   BN_LAUNCHED();
   return 0;
 }

@@ -87,6 +87,8 @@ struct TcSmem {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ __align__(1024) unsigned char smem[];
   using S = TcSmem<BN, STAGES>;
   constexpr int NCOLS = BN < 32 ? 32 : BN;
@@ -282,7 +284,7 @@ int launch_tc(const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, a.ksplit > 1 ? a.ksplit : nclasses);
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(a);
+  BN_CUDA(bn_launch(kern, grid, NTHREADS, S::TOTAL, st, a));
   BN_LAUNCHED();
   return 0;
 }
@@ -324,6 +326,7 @@ __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* map
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_constant__ TmaSet tm, const TcArgs a) {
+  bn_pdl_trigger();
   extern __shared__ __align__(1024) unsigned char smem[];
   using S = TcSmem<BN, STAGES>;
   constexpr int NCOLS = BN < 32 ? 32 : BN;
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  bn_pdl_wait();     // set-up above touched only shared memory, TMEM and constant plan tables
 
   const int n0 = blockIdx.y * BN;
   const int Ci = a.Ci;
@@ -547,7 +551,7 @@ int launch_tma(const TmaSet& tm, const TcArgs& a, int nclasses, int maxM, cudaSt
     configured = true;
   }
   dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, a.ksplit > 1 ? a.ksplit : nclasses);
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(tm, a);
+  BN_CUDA(bn_launch(kern, grid, NTHREADS, S::TOTAL, st, tm, a));
   BN_LAUNCHED();
   return 0;
 }
@@ -556,6 +560,8 @@ int launch_tma(const TmaSet& tm, const TcArgs& a, int nclasses, int maxM, cudaSt
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long total, int Co,
                                      const float* __restrict__ bias, const float* __restrict__ dact, int act,
                                      float* __restrict__ out) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= total) return;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -616,6 +622,8 @@ struct WgTcArgs {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tc_kernel(const WgTcArgs a) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ __align__(1024) unsigned char smem[];
   using S = TcSmem<BN, STAGES>;
   constexpr int NCOLS = BN < 32 ? 32 : BN;
@@ -789,6 +797,7 @@ struct alignas(64) WgTmaSet {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_constant__ WgTmaSet tm, const WgTcArgs a) {
+  bn_pdl_trigger();
   extern __shared__ __align__(1024) unsigned char smem[];
   using S = TcSmem<BN, STAGES>;
   constexpr int NCOLS = BN < 32 ? 32 : BN;
@@ -818,6 +827,7 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  bn_pdl_wait();     // set-up above touched only shared memory, TMEM and constant plan tables
 
   const int HsWs = a.Hs * a.Ws;
   const long long M = (long long)a.n * HsWs;
@@ -933,7 +943,7 @@ int launch_wgrad_tma(const WgTmaSet& tm, const WgTcArgs& a, int splits, cudaStre
     configured = true;
   }
   dim3 grid(bn_cdiv(a.Ktot, BM), a.Cs / BN, splits);
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(tm, a);
+  BN_CUDA(bn_launch(kern, grid, NTHREADS, S::TOTAL, st, tm, a));
   BN_LAUNCHED();
   return 0;
 }
@@ -948,7 +958,7 @@ int launch_wgrad_tc(const WgTcArgs& a, int splits, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(bn_cdiv(a.Ktot, BM), a.Cs / BN, splits);
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(a);
+  BN_CUDA(bn_launch(kern, grid, NTHREADS, S::TOTAL, st, a));
   BN_LAUNCHED();
   return 0;
 }
@@ -1116,6 +1126,7 @@ struct HaloSmem {
 template <int NB, int NST, bool PERSIST>
 __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_constant__ HaloMaps maps,
                                                                   const __grid_constant__ HaloArgs h) {
+  bn_pdl_trigger();
   extern __shared__ __align__(1024) unsigned char smem[];
   using S = HaloSmem<NB, NST, PERSIST>;
   constexpr int ACC_COLS = 4 * NB;                   // one accumulator per class
@@ -1153,6 +1164,7 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
   if (csz > 1) cluster_sync_all();      // every member's barriers exist before any remote arrive / copy
   const uint32_t tmem_base = *tmem_ptr;
+  bn_pdl_wait();     // set-up above touched only shared memory, TMEM and constant plan tables
   const int Ci = a.Ci;
   const int nchunk = Ci / BK;
   const uint32_t smem_base = smem_u32(smem);
@@ -1356,13 +1368,15 @@ int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
   cfg.blockDim = dim3(HALO_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csz;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = bn_pdl_enabled() ? 2 : 1;
   BN_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, (const HaloArgs&)h));
   BN_LAUNCHED();
   return 0;
@@ -1541,7 +1555,7 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   }
   if (r || ksplit == 1) return r;
   const long long total = M * Co;          // fprop-form output is linear in (m, co)
-  splitk_reduce_kernel<<<bn_cdiv(total / 4, 256), 256, 0, st>>>(split_buf, ksplit, total, Co, bias, dact, act, out);
+  BN_CUDA(bn_launch(splitk_reduce_kernel, dim3(bn_cdiv(total / 4, 256)), 256, 0, st, split_buf, ksplit, total, Co, bias, dact, act, out));
   BN_LAUNCHED();
   return 0;
 }

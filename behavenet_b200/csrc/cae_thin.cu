@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const 
                                                          float* __restrict__ out,
                                                          const float* __restrict__ dact, int act,
                                                          const TileIter it) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ __align__(16) float thin_sm[];
   typedef float (*Patch)[PROWS][PCOLS];
   Patch patch[2] = {reinterpret_cast<Patch>(thin_sm), reinterpret_cast<Patch>(thin_sm + CB * PROWS * PCOLS)};
@@ -172,6 +174,8 @@ __global__ void __launch_bounds__(256) thin_fprop_kernel(const ThinGeo g, const 
 template <int CB>
 __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinGeo g, const float* __restrict__ small,
                                                          float* __restrict__ partial, const TileIter it) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   // persistent: each block walks tiles blockIdx.x, +gridDim.x, ...; lane = small-image channel
   extern __shared__ __align__(16) float thin_sm[];
   typedef float (*Patch)[PROWS][PCOLS];
@@ -270,6 +274,8 @@ constexpr int DP = DT + 2;  // input patch edge (3x3 neighbourhood)
 // PTO / PLO = parity of the crop offsets: they fix which taps belong to which class at compile time.
 template <int CB, int PTO, int PLO>
 __global__ void __launch_bounds__(256) thin_dgrad5_kernel(const Dg5Args a, int tiles_x) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int Cs = a.Cs, PS = Cs + 4;                    // padded pixel stride: conflict-free LDS.128
   float* patch = sm;                                   // [DP*DP][PS]
@@ -420,6 +426,8 @@ template <int CB>
 __global__ void __launch_bounds__(256) thin_fprop_tc_kernel(const ThinGeo g, const float* __restrict__ wft,
                                                             const float* __restrict__ bias, float* __restrict__ out,
                                                             const float* __restrict__ dact, int act, const TileIter it) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
   using namespace bn_tc;
   using S = ThinTcSmem<CB>;
   constexpr int NKC = S::NKC, KTOT = 25 * CB;
@@ -552,7 +560,7 @@ static int launch_thin_fprop_tc(const ThinGeo& t, const float* wft, const float*
   int per_sm = (227 * 1024) / (S::TOTAL + 1024);
   per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);       // ~120 registers x 256 threads: two CTAs per SM
   long long blocks = it.total < 148LL * per_sm ? it.total : 148LL * per_sm;
-  kern<<<dim3((unsigned)blocks, cgroups), 256, S::TOTAL, st>>>(t, wft, bias, out, dact, act, it);
+  BN_CUDA(bn_launch(kern, dim3((unsigned)blocks, cgroups), 256, S::TOTAL, st, t, wft, bias, out, dact, act, it));
   BN_LAUNCHED();
   return 0;
 }
@@ -568,7 +576,7 @@ static int launch_thin_fprop(const ThinGeo& t, const float* wf, const float* bia
     configured = true;
   }
   long long blocks = it.total < 2 * 148 ? it.total : 2 * 148;      // two resident blocks per SM (128 registers x 256 threads)
-  kern<<<dim3((unsigned)blocks, cgroups), 256, smem, st>>>(t, wf, bias, out, dact, act, it);
+  BN_CUDA(bn_launch(kern, dim3((unsigned)blocks, cgroups), 256, smem, st, t, wf, bias, out, dact, act, it));
   BN_LAUNCHED();
   return 0;
 }
@@ -613,7 +621,7 @@ static int launch_thin_wgrad(const ThinGeo& t, const float* small, float* partia
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<dim3(blocks, cgroups), 256, smem, st>>>(t, small, partial, it);
+  BN_CUDA(bn_launch(kern, dim3(blocks, cgroups), 256, smem, st, t, small, partial, it));
   BN_LAUNCHED();
   return 0;
 }
@@ -651,7 +659,7 @@ static int launch_dgrad5(const Dg5Args& a, dim3 grid, int tiles_x, size_t smem, 
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  kern<<<grid, 256, smem, st>>>(a, tiles_x);
+  BN_CUDA(bn_launch(kern, grid, 256, smem, st, a, tiles_x));
   BN_LAUNCHED();
   return 0;
 }

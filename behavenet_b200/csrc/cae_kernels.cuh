@@ -74,9 +74,18 @@ int bn_launch_sigmoid_bwd(const float* dxhat, const float* xhat, float* dpre, in
 
 // packing: src [cs][cb][kk] -> wf [(tap,cb)][cs], wd [(tap,cs)][cb] (fp32, exact) and the K-major
 // TF32-rounded copies wft [cs][(tap,cb)], wdt [cb][(tap,cs)] for the tensor-core kernels
-int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd, float* wft,
-                        float* wdt, cudaStream_t st);
-// encoder heads: wcat[(head, j)][i_nhwc] from W_head[j][i_chw]
+// one conv layer's weights: src [cs][cb][tap] (torch layout) -> wf / wd (fp32) and wft / wdt (TF32-rounded)
+struct PackJob {
+  const float* src;
+  float *wf, *wd, *wft, *wdt;
+  int Cs, Cb, kk;
+  int block0, nrows, gx, gy;      // filled by bn_launch_pack_all: block range of this job
+};
+struct PackJobs {
+  int n;
+  PackJob j[16];               // 2 * BN_MAX_LAYERS (include/behavenet_b200.h)
+};
+int bn_launch_pack_all(PackJobs& jobs, cudaStream_t st);
 int bn_launch_pack_heads(const float* w0, const float* w1, int L, int C, int H, int W, float* wcat,
                          cudaStream_t st);
 

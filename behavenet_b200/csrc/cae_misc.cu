@@ -217,17 +217,15 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 // Weight packing, src [cs][cb][tap] (torch layout, tap fastest) -> four GEMM orders.  A one-thread-
 // per-element version writes four scattered 4-byte stores per element (a 32-byte sector each); here
-// two kernels stage bricks in shared memory so that every global access is a contiguous run:
-//   pack_conv_rows_kernel : one block per cs: row (cb, tap) -> wft [cs][tap][cb], wd [tap][cs][cb]
-//   pack_conv_cols_kernel : block = 32 cs x 8 cb x all taps -> wf [tap][cb][cs], wdt [cb][tap][cs]
-__global__ void __launch_bounds__(256) pack_conv_rows_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
-                                                             float* __restrict__ wd, float* __restrict__ wft) {
-  bn_pdl_trigger();
-  bn_pdl_wait();
-  extern __shared__ float prow[];                 // [cb][kk + 1] (odd pitch when kk is even is not needed: reads are strided by kk+1)
-  const int cs = blockIdx.x;
+// two block bodies stage bricks in shared memory so that every global access is a contiguous run:
+//   pack_rows_block : one block per cs: row (cb, tap) -> wft [cs][tap][cb], wd [tap][cs][cb]
+//   pack_cols_block : block = 32 cs x 8 cb x all taps -> wf [tap][cb][cs], wdt [cb][tap][cs]
+// All conv layers of a plan are packed by ONE launch (pack_all_kernel): after every optimizer step
+// the step used to open with 20 small launches (32..512 blocks each, ~100 us in total).
+__device__ __forceinline__ void pack_rows_block(const PackJob& jb, int cs, float* prow) {
+  const int Cs = jb.Cs, Cb = jb.Cb, kk = jb.kk;   // prow: [cb][kk + 1]
   const int n = Cb * kk;
-  const float* s = src + (long long)cs * n;
+  const float* s = jb.src + (long long)cs * n;
   for (int i = threadIdx.x; i < n; i += 256) {
     const int cb = i / kk, tap = i - cb * kk;
     prow[cb * (kk + 1) + tap] = s[i];
@@ -236,23 +234,20 @@ __global__ void __launch_bounds__(256) pack_conv_rows_kernel(const float* __rest
   for (int i = threadIdx.x; i < n; i += 256) {
     const int tap = i / Cb, cb = i - tap * Cb;
     const float v = prow[cb * (kk + 1) + tap];
-    wd[((long long)tap * Cs + cs) * Cb + cb] = v;
-    wft[((long long)cs * kk + tap) * Cb + cb] = round_tf32(v);
+    jb.wd[((long long)tap * Cs + cs) * Cb + cb] = v;
+    jb.wft[((long long)cs * kk + tap) * Cb + cb] = round_tf32(v);
   }
 }
 
 constexpr int PCS = 32, PCB = 8;
-__global__ void __launch_bounds__(256) pack_conv_cols_kernel(const float* __restrict__ src, int Cs, int Cb, int kk,
-                                                             float* __restrict__ wf, float* __restrict__ wdt) {
-  bn_pdl_trigger();
-  bn_pdl_wait();
-  extern __shared__ float brick[];                // [cs 32][PCB * kk + 1]
-  const int cs0 = blockIdx.x * PCS, cb0 = blockIdx.y * PCB;
+__device__ __forceinline__ void pack_cols_block(const PackJob& jb, int bx, int by, float* brick) {
+  const int Cs = jb.Cs, Cb = jb.Cb, kk = jb.kk;   // brick: [cs 32][PCB * kk + 1]
+  const int cs0 = bx * PCS, cb0 = by * PCB;
   const int ncb = min(PCB, Cb - cb0), ncs = min(PCS, Cs - cs0);
   const int run = ncb * kk, pitch = PCB * kk + 1;
   for (int i = threadIdx.x; i < ncs * run; i += 256) {
     const int c = i / run, r = i - c * run;
-    brick[c * pitch + r] = src[((long long)(cs0 + c) * Cb + cb0) * kk + r];       // runs of ncb*kk contiguous floats
+    brick[c * pitch + r] = jb.src[((long long)(cs0 + c) * Cb + cb0) * kk + r];    // runs of ncb*kk contiguous floats
   }
   __syncthreads();
   for (int i = threadIdx.x; i < run * PCS; i += 256) {
@@ -260,8 +255,27 @@ __global__ void __launch_bounds__(256) pack_conv_cols_kernel(const float* __rest
     if (c >= ncs) continue;
     const int cbl = r / kk, tap = r - cbl * kk;
     const float v = brick[c * pitch + r];
-    wf[((long long)tap * Cb + cb0 + cbl) * Cs + cs0 + c] = v;
-    wdt[((long long)(cb0 + cbl) * kk + tap) * Cs + cs0 + c] = round_tf32(v);
+    jb.wf[((long long)tap * Cb + cb0 + cbl) * Cs + cs0 + c] = v;
+    jb.wdt[((long long)(cb0 + cbl) * kk + tap) * Cs + cs0 + c] = round_tf32(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackJobs jobs) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
+  extern __shared__ float pack_smem[];
+  const int b = blockIdx.x;
+  for (int q = 0; q < jobs.n; ++q) {
+    const PackJob& jb = jobs.j[q];
+    if (b >= jb.block0 && b < jb.block0 + jb.nrows) {
+      pack_rows_block(jb, b - jb.block0, pack_smem);
+      return;
+    }
+    const int c = b - jb.block0 - jb.nrows;
+    if (c >= 0 && c < jb.gx * jb.gy) {
+      pack_cols_block(jb, c % jb.gx, c / jb.gx, pack_smem);
+      return;
+    }
   }
 }
 
@@ -544,23 +558,29 @@ int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_
   return 0;
 }
 
-int bn_launch_pack_conv(const float* src, int Cs, int Cb, int kk, float* wf, float* wd, float* wft,
-                        float* wdt, cudaStream_t st) {
-  const size_t smem_rows = (size_t)Cb * (kk + 1) * sizeof(float);
-  const size_t smem_cols = (size_t)PCS * (PCB * kk + 1) * sizeof(float);
-  if (smem_rows > 200 * 1024 || smem_cols > 200 * 1024) BN_FAIL("pack_conv: layer too wide (C_big=%d, k*k=%d)", Cb, kk);
-  static size_t cfg_rows = 0, cfg_cols = 0;
-  if (smem_rows > cfg_rows) {
-    BN_CUDA(cudaFuncSetAttribute(pack_conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-    cfg_rows = smem_rows;
+int bn_launch_pack_all(PackJobs& jobs, cudaStream_t st) {
+  if (jobs.n <= 0) return 0;
+  size_t smem = 0;
+  int blocks = 0;
+  for (int q = 0; q < jobs.n; ++q) {
+    PackJob& jb = jobs.j[q];
+    const size_t smem_rows = (size_t)jb.Cb * (jb.kk + 1) * sizeof(float);
+    const size_t smem_cols = (size_t)PCS * (PCB * jb.kk + 1) * sizeof(float);
+    if (smem_rows > 200 * 1024 || smem_cols > 200 * 1024) BN_FAIL("pack: layer too wide (C_big=%d, k*k=%d)", jb.Cb, jb.kk);
+    smem = smem_rows > smem ? smem_rows : smem;
+    smem = smem_cols > smem ? smem_cols : smem;
+    jb.block0 = blocks;
+    jb.nrows = jb.Cs;
+    jb.gx = bn_cdiv(jb.Cs, PCS);
+    jb.gy = bn_cdiv(jb.Cb, PCB);
+    blocks += jb.nrows + jb.gx * jb.gy;
   }
-  if (smem_cols > cfg_cols) {
-    BN_CUDA(cudaFuncSetAttribute(pack_conv_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    cfg_cols = smem_cols;
+  static size_t cfg = 0;
+  if (smem > cfg) {
+    BN_CUDA(cudaFuncSetAttribute(pack_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg = smem;
   }
-  BN_CUDA(bn_launch(pack_conv_rows_kernel, dim3(Cs), 256, smem_rows, st, src, Cs, Cb, kk, wd, wft));
-  BN_LAUNCHED();
-  BN_CUDA(bn_launch(pack_conv_cols_kernel, dim3(bn_cdiv(Cs, PCS), bn_cdiv(Cb, PCB)), 256, smem_cols, st, src, Cs, Cb, kk, wf, wdt));
+  BN_CUDA(bn_launch(pack_all_kernel, dim3(blocks), 256, smem, st, jobs));
   BN_LAUNCHED();
   return 0;
 }

@@ -252,16 +252,20 @@ extern "C" int bn_cae_pack_params(bn_cae_plan* p, const float* const* P, void* d
   if (!p || !P || !d_packed) BN_FAIL("bn_cae_pack_params: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   float* pk = (float*)d_packed;
-  for (int i = 0; i < p->nl; ++i) {
-    const ConvGeom& g = p->enc[i];
-    if (P[g.p_w])
-      BN_TRY(bn_launch_pack_conv(P[g.p_w], g.Cs, g.Cb, g.k * g.k, pk + g.off_wf, pk + g.off_wd,
-                                 pk + g.off_wft, pk + g.off_wdt, st));
-    const ConvGeom& h = p->dec[i];
-    if (P[h.p_w])
-      BN_TRY(bn_launch_pack_conv(P[h.p_w], h.Cs, h.Cb, h.k * h.k, pk + h.off_wf, pk + h.off_wd,
-                                 pk + h.off_wft, pk + h.off_wdt, st));
-  }
+  PackJobs jobs;
+  jobs.n = 0;
+  static_assert(sizeof(jobs.j) / sizeof(jobs.j[0]) >= 2 * BN_MAX_LAYERS, "PackJobs holds every conv layer of a plan");
+  auto add = [&](const ConvGeom& g) {
+    if (!P[g.p_w]) return;
+    PackJob& jb = jobs.j[jobs.n++];
+    jb.src = P[g.p_w];
+    jb.wf = pk + g.off_wf; jb.wd = pk + g.off_wd; jb.wft = pk + g.off_wft; jb.wdt = pk + g.off_wdt;
+    jb.Cs = g.Cs; jb.Cb = g.Cb; jb.kk = g.k * g.k;
+  };
+  // widest layers first: their blocks are the long ones
+  for (int i = p->nl - 1; i >= 0; --i) add(p->enc[i]);
+  for (int i = 0; i < p->nl; ++i) add(p->dec[i]);
+  BN_TRY(bn_launch_pack_all(jobs, st));
   const int n2 = 2 * p->nl;
   if (P[n2]) {
     if (p->d.n_heads == 2 && !P[n2 + 2]) BN_FAIL("bn_cae_pack_params: logvar head weight missing");

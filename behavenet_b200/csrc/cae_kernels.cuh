@@ -44,6 +44,8 @@ size_t bn_wgrad_partial_floats(const ConvGeom& g, int n);
 // grad[((cs*Cb + cb)*KK + wt[tap])] += sum_z partial[z][(tap, cb)][cs]
 int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, int Cb, int KK,
                            const TapClass* cls, float* grad, cudaStream_t st);
+void bn_wgrad_reduce_defer_begin();
+int bn_wgrad_reduce_flush(cudaStream_t st);
 
 // out[c] += sum_m x[m*C + c]
 int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_t st);

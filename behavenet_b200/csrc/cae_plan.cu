@@ -47,6 +47,10 @@ struct WsLayout {
   size_t enc_act[BN_MAX_LAYERS + 1];
   size_t dec_act[BN_MAX_LAYERS + 1];
   size_t dpre_last, zcopy, gA, gB, partial, partial_floats, total;
+  // weight-gradient partial sums: one region per layer (the reductions of a backward call are deferred
+  // and batched), encoder and decoder calls share the space; `partial` (above) is the separate scratch of
+  // the split-K implicit GEMMs and of bn_cae_layer_op
+  size_t wg_enc[BN_MAX_LAYERS], wg_dec[BN_MAX_LAYERS], wg_floats_enc[BN_MAX_LAYERS], wg_floats_dec[BN_MAX_LAYERS];
 };
 
 WsLayout ws_layout(const bn_cae_plan* p, int n) {
@@ -65,6 +69,14 @@ WsLayout ws_layout(const bn_cae_plan* p, int n) {
     pf = std::max(pf, bn_wgrad_partial_floats(p->dec[i], n));
   }
   w.partial = o; w.partial_floats = pf; o += align64(pf);
+  size_t oe = o, od = o;
+  for (int i = 0; i < p->nl; ++i) {
+    w.wg_floats_enc[i] = bn_wgrad_partial_floats(p->enc[i], n);
+    w.wg_enc[i] = oe; oe += align64(w.wg_floats_enc[i]);
+    w.wg_floats_dec[i] = bn_wgrad_partial_floats(p->dec[i], n);
+    w.wg_dec[i] = od; od += align64(w.wg_floats_dec[i]);
+  }
+  o = std::max(oe, od);
   w.total = o;
   return w;
 }
@@ -377,11 +389,13 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
   float* pp[2] = {ws + L.gA, ws + L.gB};
   int flip = 0;
   int bias_done = 0;   // the kernel that produced gcur already accumulated its column sums
+  bn_wgrad_reduce_defer_begin();        // per-layer partial regions; all reductions in one launch below
+  const int rc = [&]() -> int {
   for (int i = p->nl - 1; i >= 0; --i) {
     const ConvGeom& g = p->dec[i];
     ImgView big = nhwc_view(gcur, g.Hb, g.Wb, g.Cb);
     const float* small = ws + L.dec_act[i];
-    BN_TRY(run_wgrad(big, small, g, n, ws + L.partial, L.partial_floats, G[g.p_w], st));
+    BN_TRY(run_wgrad(big, small, g, n, ws + L.wg_dec[i], L.wg_floats_dec[i], G[g.p_w], st));
     if (!bias_done) BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hb * g.Wb, g.Cb, G[g.p_b], st));
     bias_done = 0;
     float* out = pp[flip];
@@ -396,6 +410,11 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
                        i > 0 ? G[p->dec[i - 1].p_b] : nullptr, &bias_done));
     gcur = out;
   }
+  return 0;
+  }();
+  const int rf = bn_wgrad_reduce_flush(st);
+  if (rc) return rc;
+  if (rf) return rf;
   BN_TRY(bn_launch_decff_bwd(ws + L.zcopy, P[n2 + 4], gcur, n, p->d.n_latents, p->d.dec_c0, p->d.dec_h0,
                              p->d.dec_w0, d_dz, G[n2 + 4], G[n2 + 5], st));
   return 0;
@@ -422,10 +441,12 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
                              p->feat_c, p->feat_h, p->feat_w, gcur, G[n2], G[n2 + 1],
                              p->d.n_heads == 2 ? G[n2 + 2] : nullptr, p->d.n_heads == 2 ? G[n2 + 3] : nullptr, st));
   int bias_done = 0;   // the kernel that produced gcur already accumulated its column sums
+  bn_wgrad_reduce_defer_begin();
+  const int rc = [&]() -> int {
   for (int i = p->nl - 1; i >= 0; --i) {
     const ConvGeom& g = p->enc[i];
     ImgView big = i == 0 ? input_view(p, d_x) : nhwc_view(ws + L.enc_act[i], g.Hb, g.Wb, g.Cb);
-    BN_TRY(run_wgrad(big, gcur, g, n, ws + L.partial, L.partial_floats, G[g.p_w], st));
+    BN_TRY(run_wgrad(big, gcur, g, n, ws + L.wg_enc[i], L.wg_floats_enc[i], G[g.p_w], st));
     if (!bias_done) BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hs * g.Ws, g.Cs, G[g.p_b], st));
     bias_done = 0;
     if (i > 0) {
@@ -439,6 +460,9 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
     }
   }
   return 0;
+  }();
+  const int rf = bn_wgrad_reduce_flush(st);
+  return rc ? rc : rf;
 }
 
 // Single-layer entry point: kernel-level parity tests (tensor-core vs CUDA-core kernels on the same

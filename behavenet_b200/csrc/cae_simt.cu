@@ -372,22 +372,31 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgArgs a) {
 // and the brick is transposed through shared memory so the read-modify-write runs are 128 bytes too.
 // Few-output layers (the thin first / last layer has 800 outputs but ~300 slices) spread the slices
 // over grid.z and finish with atomicAdd; everything else is a deterministic +=.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Ktot,
-                                                           int Cs, int Cb, int KK, const TapClass* __restrict__ cls,
-                                                           float* __restrict__ grad) {
-  bn_pdl_trigger();
-  bn_pdl_wait();
-  __shared__ float tile[32][33];
-  __shared__ unsigned char inv[BN_MAX_TAPS];
+struct ReduceJob {
+  const float* partial;
+  float* grad;
+  const TapClass* cls;
+  int splits, Ktot, Cs, Cb, KK;
+  int gx, gy, gz, block0;
+};
+struct ReduceJobs {
+  int n;
+  ReduceJob j[16];            // 2 * BN_MAX_LAYERS
+};
+
+__device__ __forceinline__ void wgrad_reduce_block(const ReduceJob& jb, int bx, int by, int bz, float (*tile)[33],
+                                                   unsigned char* inv) {
+  const float* __restrict__ partial = jb.partial;
+  const int splits = jb.splits, Ktot = jb.Ktot, Cs = jb.Cs, Cb = jb.Cb, KK = jb.KK, gz = jb.gz;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < KK) inv[cls->wt[tid]] = (unsigned char)tid;
+  if (tid < KK) inv[jb.cls->wt[tid]] = (unsigned char)tid;
   __syncthreads();
-  const int cs = blockIdx.x * 32 + lane;
-  const int o0 = blockIdx.y * 32;
+  const int cs = bx * 32 + lane;
+  const int o0 = by * 32;
   const int nout = Cb * KK;
   const long long tot = (long long)Ktot * Cs;
-  const int zper = (splits + gridDim.z - 1) / gridDim.z;
-  const int z0 = blockIdx.z * zper, z1 = min(splits, z0 + zper);
+  const int zper = (splits + gz - 1) / gz;
+  const int z0 = bz * zper, z1 = min(splits, z0 + zper);
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   const float* p[4];
   bool ok[4];
@@ -420,13 +429,47 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int o = o0 + lane;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const int c = blockIdx.x * 32 + warp * 4 + r;
+    const int c = bx * 32 + warp * 4 + r;
     if (c < Cs && o < nout) {
-      float* g = grad + (long long)c * nout + o;
-      if (gridDim.z > 1) atomicAdd(g, tile[warp * 4 + r][lane]);
+      float* g = jb.grad + (long long)c * nout + o;
+      if (gz > 1) atomicAdd(g, tile[warp * 4 + r][lane]);
       else *g += tile[warp * 4 + r][lane];
     }
   }
+}
+
+// every queued reduction of one backward call in ONE launch (block ranges per job)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
+  bn_pdl_trigger();
+  bn_pdl_wait();
+  __shared__ float tile[32][33];
+  __shared__ unsigned char inv[BN_MAX_TAPS];
+  const int b = blockIdx.x;
+  for (int q = 0; q < jobs.n; ++q) {
+    const ReduceJob& jb = jobs.j[q];
+    const int l = b - jb.block0;
+    if (l >= 0 && l < jb.gx * jb.gy * jb.gz) {
+      const int bx = l % jb.gx, by = (l / jb.gx) % jb.gy, bz = l / (jb.gx * jb.gy);
+      wgrad_reduce_block(jb, bx, by, bz, tile, inv);
+      return;
+    }
+  }
+}
+
+thread_local ReduceJobs t_reduce_jobs;
+thread_local bool t_reduce_defer = false;
+
+int launch_reduce_jobs(ReduceJobs& jobs, cudaStream_t st) {
+  if (jobs.n == 0) return 0;
+  int blocks = 0;
+  for (int q = 0; q < jobs.n; ++q) {
+    jobs.j[q].block0 = blocks;
+    blocks += jobs.j[q].gx * jobs.j[q].gy * jobs.j[q].gz;
+  }
+  BN_CUDA(bn_launch(wgrad_reduce_kernel, dim3(blocks), 256, 0, st, jobs));
+  BN_LAUNCHED();
+  jobs.n = 0;
+  return 0;
 }
 
 }  // namespace
@@ -479,9 +522,30 @@ int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, i
   int gz = 2 * 148 / (gx * gy);
   if (gz > splits / 4) gz = splits / 4;
   if (gz < 1) gz = 1;
-  BN_CUDA(bn_launch(wgrad_reduce_kernel, dim3(gx, gy, gz), 256, 0, st, partial, splits, Ktot, Cs, Cb, KK, cls, grad));
-  BN_LAUNCHED();
-  return 0;
+  ReduceJob jb;
+  jb.partial = partial; jb.grad = grad; jb.cls = cls;
+  jb.splits = splits; jb.Ktot = Ktot; jb.Cs = Cs; jb.Cb = Cb; jb.KK = KK;
+  jb.gx = gx; jb.gy = gy; jb.gz = gz; jb.block0 = 0;
+  if (t_reduce_defer && t_reduce_jobs.n < (int)(sizeof(t_reduce_jobs.j) / sizeof(t_reduce_jobs.j[0]))) {
+    t_reduce_jobs.j[t_reduce_jobs.n++] = jb;       // launched by bn_wgrad_reduce_flush
+    return 0;
+  }
+  ReduceJobs one;
+  one.n = 1;
+  one.j[0] = jb;
+  return launch_reduce_jobs(one, st);
+}
+
+// Backward entry points give every layer its own partial-sum region and queue the reductions
+// (begin), then run them all in one launch (flush): ten small grids become two large ones.
+void bn_wgrad_reduce_defer_begin() {
+  t_reduce_jobs.n = 0;
+  t_reduce_defer = true;
+}
+
+int bn_wgrad_reduce_flush(cudaStream_t st) {
+  t_reduce_defer = false;
+  return launch_reduce_jobs(t_reduce_jobs, st);
 }
 
 int bn_launch_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,

@@ -103,6 +103,19 @@ def test_worker_errors_surface_in_next_batch():
     gen.close()
 
 
+def test_hdf5_source_needs_h5py():
+    """The HDF5 reader follows the reference file layout but h5py is not part of this image: it must say so
+    instead of failing later (when h5py is present this test is skipped)."""
+    from behavenet_b200.data import HDF5Source
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match='h5py'):
+            HDF5Source('/nonexistent/data.hdf5', ['images'])
+    else:
+        pytest.skip('h5py available')
+
+
 @pytest.mark.gpu
 def test_prefetch_to_device_and_raw_uint8_into_encoder():
     """Pinned staging + side-stream copies deliver the reference's values on the device; raw uint8 batches go

@@ -202,6 +202,24 @@ def _gloo_worker(rank, world, port, q):
         p.grad = torch.full_like(p, float(rank + 1))
     model._allreduce(params, sse)
     ok = ok and all(torch.all(p.grad == tot) for p in model.parameters())
+    # input pipeline under the same ranks: every rank stages only its own frames of each trial, all ranks
+    # walk the trials in the same order, and the shards tile the trial
+    import torch.distributed as dist
+    from behavenet_b200.data import ArraySource, PrefetchSessionsGenerator
+    rng = np.random.RandomState(0)
+    src = ArraySource({'images': [rng.randint(0, 256, (T, 1, 4, 4)).astype(np.uint8) for T in (5, 8, 3, 6, 7, 4, 9, 5, 6, 7)]})
+    gen = PrefetchSessionsGenerator([src], device='cpu', rng_seed=4, shard_frames=True)
+    for _ in range(gen.n_tot_batches['train']):
+        d, _s = gen.next_batch('train')
+        idx, (beg, T) = int(d['batch_idx']), d['shard']
+        n_mine = d['images'].shape[1]
+        info = torch.tensor([idx, beg, n_mine, T])
+        both = [torch.zeros_like(info) for _ in range(world)]
+        dist.all_gather(both, info, group=parallel.group())
+        ok = ok and all(int(b[0]) == idx and int(b[3]) == T == src.trial_length(idx) for b in both)
+        ok = ok and int(both[0][1]) == 0 and int(both[1][1]) == int(both[0][2]) and int(both[0][2] + both[1][2]) == T
+        ok = ok and np.array_equal(d['images'][0].numpy(), src.load('images', idx, beg, beg + n_mine).astype('float32') / 255)
+    gen.close()
     q.put((rank, ok, (lo, hi)))
     parallel.shutdown()
 

@@ -348,8 +348,9 @@ def test_interleaved_forwards_keep_their_own_activations():
     ga2 = grads_of(la)
     gb2 = grads_of(lb)
     for k in ga:
-        assert rel_err(ga2[k], ga[k]) < 1e-5, k     # (atomic accumulation order differs run to run)
-        assert rel_err(gb2[k], gb[k]) < 1e-5, k
+        # atomic accumulation order differs run to run (fp32 round-off); a shared workspace would be O(1) off
+        assert rel_err(ga2[k], ga[k]) < 1e-4, k
+        assert rel_err(gb2[k], gb[k]) < 1e-4, k
 
 
 COND_CASES = [('condae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae', 4, 4, False),

@@ -16,6 +16,9 @@ def _latents_of(model, frames):
     if model.hparams.get('model_class') == 'ps-vae':
         import torch
         return torch.cat([out[0], out[1]], dim=1)          # eval.py:75-76
+    if model.hparams.get('model_class') == 'msps-vae':
+        import torch
+        return torch.cat([out[0], out[1], out[2]], dim=1)  # vaes.py:1255-1266
     return out[0]
 
 

@@ -584,3 +584,212 @@ class PSVAE(AE):
         y_new = (y_og - self.encoding.D.bias) / self.encoding.D.weight
         latents = torch.cat([y_new, w_og], axis=1)
         return latents.cpu().detach().numpy() if as_numpy else latents
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-session PS-VAE (reference vaes.py:849-1462)
+# ------------------------------------------------------------------------------------------------
+
+def gaussian_ll(y_pred, y_mean, masks=None):
+    """Unit-variance Gaussian log-likelihood, summed over dims, averaged over the batch (reference
+    fitting/losses.py:62-96)."""
+    d = (y_pred - y_mean) ** 2
+    if masks is not None:
+        d = d * masks
+    n_dims = int(np.prod(y_pred.shape[1:]))
+    return torch.mean(-0.5 * LN2PI * n_dims - 0.5 * d.reshape(d.shape[0], -1).sum(1))
+
+
+def decomposed_kl(z, mu, logvar):
+    """(index-code MI, total correlation, dimension-wise KL) minibatch estimators (losses.py:284-372):
+    lq[j, i, l] = log q(z_j,l | x_i)."""
+    lq = -0.5 * (torch.exp(-logvar)[None] * (z[:, None] - mu[None]) ** 2 + logvar[None] + LN2PI)
+    joint = lq.sum(2)
+    log_qz = torch.logsumexp(joint, dim=1)
+    log_qz_prod = torch.logsumexp(lq, dim=1).sum(1)
+    log_pz = (-0.5 * (z ** 2 + LN2PI)).sum(1)
+    return ((torch.diagonal(joint) - log_qz).mean(), (log_qz - log_qz_prod).mean(), (log_qz_prod - log_pz).mean())
+
+
+def triplet_loss(triplet_loss_obj, z, datasets):
+    """Session-separation loss on the background latents (losses.py:402-513) for 2-4 sessions in a batch.
+
+    Every session's frames are shuffled (numpy's global generator, sessions in ascending id order) and dealt
+    into 3 * (n - 1) equal chunks: chunks (2k, 2k + 1) are the anchor / positive of the k-th other session,
+    whose negative chunk is 2 * (n - 1) + (rank of the anchor session among that session's others).  The sum
+    of the triplet terms and of the mean anchor-positive distances is divided by the reference's constant
+    (3, 6, 12)."""
+    ids = np.unique(datasets)
+    n = len(ids)
+    if n < 2 or n > 4:
+        raise NotImplementedError
+    n_chunks = 3 * (n - 1)
+    perms = [np.random.permutation(np.where(datasets == i)[0]) for i in ids]
+    m = min(len(q) // n_chunks for q in perms)
+    chunks = [[q[i::n_chunks][:m] for i in range(n_chunks)] for q in perms]
+    loss = 0
+    for x in range(n):
+        for k, y in enumerate(o for o in range(n) if o != x):
+            rank = x if x < y else x - 1
+            loss = loss + triplet_loss_obj(z[chunks[x][2 * k]], z[chunks[x][2 * k + 1]],
+                                           z[chunks[y][2 * (n - 1) + rank]])
+    for x in range(n):
+        for k in range(n - 1):
+            loss = loss + torch.pairwise_distance(z[chunks[x][2 * k]], z[chunks[x][2 * k + 1]]).mean()
+    return loss / {2: 3, 3: 6, 4: 12}[n]
+
+
+class ConvAEMSPSEncoder(ConvAEEncoder):
+    """Encoder with supervised (A), unsupervised (B) and session-background (C) subspaces (reference
+    vaes.py:1366-1462): rows of one fixed random orthogonal matrix; C carries a trainable bias."""
+
+    def __init__(self, hparams):
+        super().__init__(hparams)
+        L, nl, nb = self.hparams['n_ae_latents'], self.hparams['n_labels'], self.hparams['n_background']
+        self.A = nn.Linear(L, nl, bias=False)
+        self.B = nn.Linear(L, L - nl - nb, bias=False)
+        self.C = nn.Linear(L, nb, bias=True)
+        self.D = DiagLinear(nl, bias=True)
+        from scipy.stats import ortho_group
+        m = ortho_group.rvs(dim=L).astype('float32')
+        with torch.no_grad():
+            self.A.weight = nn.Parameter(torch.from_numpy(m[:nl, :]), requires_grad=False)
+            self.B.weight = nn.Parameter(torch.from_numpy(m[nl + nb:, :]), requires_grad=False)
+            self.C.weight = nn.Parameter(torch.from_numpy(m[nl:nl + nb, :]), requires_grad=False)
+
+    def __str__(self):
+        s = 'Encoder architecture:\n'
+        i = -1
+        for i, module in enumerate(self.encoder):
+            s += '    {:02d}: {}\n'.format(i, module)
+        s += '    {:02d}: {}\n'.format(i + 1, self.FF)
+        s += '    {:02d}: {} (to supervised latents)\n'.format(i + 1, self.A)
+        s += '    {:02d}: {} (to unsupervised latents)\n'.format(i + 1, self.B)
+        s += '    {:02d}: {} (to background latents)\n'.format(i + 1, self.C)
+        s += '    {:02d}: {} (supervised latents to labels)\n'.format(i + 1, self.D)
+        return s
+
+    def forward(self, x, dataset=None):
+        """(z_s, z_b, z, logvar, pool_idx, output_size); the conv stack and both heads run in the kernels,
+        the three small projections are torch ops on (n, latents) tensors."""
+        pre, logvar = self._heads(x)
+        return self.A(pre), self.C(pre), self.B(pre), logvar, [], []
+
+
+class MSPSVAE(PSVAE):
+    """Multi-session PS-VAE (reference vaes.py:849-1273): PS-VAE terms on the whole batch plus a triplet
+    loss that pushes the background latents of different sessions apart."""
+
+    def __init__(self, hparams):
+        if hparams['n_sessions_per_batch'] == 1:
+            raise ValueError('must choose "n_sessions_per_batch" > 1 in hparams')
+        hparams['n_background'] = hparams.get('n_background', 4)
+        super().__init__(hparams)
+        self.TripletLoss = nn.TripletMarginLoss(margin=1.0, p=2)
+
+    def build_model(self):
+        self.hparams['hidden_layer_size'] = self.hparams['n_ae_latents']
+        if self.model_type != 'conv':
+            raise NotImplementedError
+        self.encoding = ConvAEMSPSEncoder(self.hparams)
+        self.decoding = ConvAEDecoder(self.hparams)
+        self._driver = self.encoding._driver
+        self._rt = Runtime()
+
+    def invalidate_packed(self):
+        self.encoding._rt.packed_key = None
+        self.decoding._rt.packed_key = None
+
+    def forward(self, x, dataset=None, use_mean=False, eps=None, **kwargs):
+        """(x_hat, z, mu, logvar, y_hat) with mu = [z_s, z_b, z_u] (vaes.py:893-924)."""
+        z_s, z_b, z_u, logvar, pool_idx, outsize = self.encoding(x, dataset=dataset)
+        mu = torch.cat([z_s, z_b, z_u], dim=1)
+        z = mu if use_mean else reparameterize(mu, logvar, None if eps is None else eps.to(mu.device))
+        x_hat = self.decoding(z, pool_idx, outsize, dataset=dataset)
+        return x_hat, z, mu, logvar, self.encoding.D(z_s)
+
+    def loss(self, datas, dataset=None, accumulate_grad=True, chunk_size=None, eps=None):
+        """One pass over the whole batch (a dict, or a list of per-session dicts with ``dataset`` the list
+        of their session ids, which adds the triplet term) (vaes.py:926-1077)."""
+        from sklearn.metrics import r2_score
+        multi = isinstance(datas, list)
+        if multi:
+            def cat(key):
+                return torch.cat([d[key][0] for d in datas], dim=0) if key in datas[0] else None
+            x, y, m, n = cat('images'), cat('labels'), cat('masks'), cat('labels_masks')
+            sessions = np.concatenate([s * np.ones(datas[i]['images'].shape[1]) for i, s in enumerate(dataset)])
+        else:
+            x, y = datas['images'][0], datas['labels'][0]
+            m = datas['masks'][0] if 'masks' in datas else None
+            n = datas['labels_masks'][0] if 'labels_masks' in datas else None
+        nl, nb = self.hparams['n_labels'], self.hparams['n_background']
+        alpha, delta = self.hparams['ps_vae.alpha'], self.hparams['ps_vae.delta']
+        beta, kl = self.beta_vals[self.curr_epoch], self.kl_anneal_vals[self.curr_epoch]
+        x_hat, sample, mu, logvar, y_hat = self.forward(x, dataset=None, use_mean=False, eps=eps)
+        t = {}
+        t['loss_data_ll'] = gaussian_ll(x, x_hat, m)
+        t['loss_label_ll'] = gaussian_ll(y, y_hat, n)
+        t['loss_zs_kl'] = torch.mean(0.5 * torch.sum(
+            logvar[:, :nl].exp() - logvar[:, :nl] + mu[:, :nl] ** 2 - 1, dim=1))
+        t['loss_zu_mi'], t['loss_zu_tc'], t['loss_zu_dwkl'] = decomposed_kl(
+            sample[:, nl + nb:], mu[:, nl + nb:], logvar[:, nl + nb:])
+        total = (-t['loss_data_ll'] - alpha * t['loss_label_ll'] + t['loss_zs_kl'] + kl * t['loss_zu_mi']
+                 + beta * t['loss_zu_tc'] + kl * t['loss_zu_dwkl'])
+        if multi:
+            t['loss_triplet'] = triplet_loss(self.TripletLoss, mu[:, nl:nl + nb], sessions)
+            total = total + delta * t['loss_triplet']
+        if accumulate_grad:
+            total.backward()
+        out = {'loss': total.item()}
+        out.update({k: v.item() for k, v in t.items()})
+        if not multi:
+            out['loss_triplet'] = 0          # the reference keeps the zero it initialised the entry with
+        n_dims = int(np.prod(x.shape[1:]))
+        out['loss_data_mse'] = (out['loss_data_ll'] + 0.5 * LN2PI * n_dims) * -2.0 / n_dims
+        y_np, yh_np = y.detach().cpu().numpy(), y_hat.detach().cpu().numpy()
+        if n is not None:
+            keep = n.detach().cpu().numpy() == 1
+            r2 = r2_score(y_np[keep], yh_np[keep], multioutput='variance_weighted')
+        else:
+            r2 = r2_score(y_np, yh_np, multioutput='variance_weighted')
+        out.update({'alpha': alpha, 'beta': beta, 'delta': delta, 'label_r2': r2})
+        return out
+
+    def get_predicted_labels(self, x, dataset=None, use_mean=True):
+        z_s, _, _, logvar, _, _ = self.encoding(x, dataset=dataset)
+        if not use_mean:
+            z_s = reparameterize(z_s, logvar[:, :self.n_labels])
+        return self.encoding.D(z_s)
+
+    def _split(self, latents):
+        nl, nb = self.hparams['n_labels'], self.hparams['n_background']
+        return latents[:, :nl], latents[:, nl:nl + nb], latents[:, nl + nb:]
+
+    def get_transformed_latents(self, inputs, dataset=None, as_numpy=True):
+        """[labels-space supervised | background | unsupervised] from frames or latents (vaes.py:1105-1152)."""
+        if not isinstance(inputs, torch.Tensor):
+            inputs = torch.Tensor(inputs)
+        inputs = inputs.to(self.encoding.D.weight.device)
+        if inputs.dim() == 2:
+            z_s, z_b, z_u = self._split(inputs)
+        else:
+            z_s, z_b, z_u = self.encoding(inputs, dataset=dataset)[:3]
+        out = torch.cat([self.encoding.D(z_s), z_b, z_u], dim=1)
+        return out.cpu().detach().numpy() if as_numpy else out
+
+    def get_inverse_transformed_latents(self, inputs, dataset=None, as_numpy=True):
+        """Inverse of the above for 2-D inputs (vaes.py:1154-1200)."""
+        if not isinstance(inputs, torch.Tensor):
+            inputs = torch.Tensor(inputs)
+        if inputs.dim() != 2:
+            raise NotImplementedError
+        inputs = inputs.to(self.encoding.D.weight.device)
+        y, z_b, z_u = self._split(inputs)
+        z_s = torch.div(torch.sub(y, self.encoding.D.bias), self.encoding.D.weight)
+        out = torch.cat([z_s, z_b, z_u], dim=1)
+        return out.cpu().detach().numpy() if as_numpy else out
+
+    def export_latents(self, data_gen, filename=None):
+        """Latents of every trial as [z_s, z_b, z_u] (vaes.py:1202-1273), through the shared exporter."""
+        from behavenet_b200.fitting.eval import export_latents
+        return export_latents(data_gen, self, filename=filename)

@@ -284,6 +284,76 @@ def psvae_loss(sd, hparams, x, labels, eps, masks=None, labels_masks=None, alpha
 
 
 # ------------------------------------------------------------------------------------------------
+# multi-session PS-VAE (models/vaes.py:849-1273, 1366-1462; fitting/losses.py:402-513)
+# ------------------------------------------------------------------------------------------------
+
+def triplet_loss(z, datasets, margin=1.0):
+    """losses.triplet_loss with nn.TripletMarginLoss(margin=1, p=2): written out per session count the way
+    the reference enumerates its terms (anchor chunk, positive chunk, (negative session, negative chunk))."""
+    tables = {
+        2: (3, 3, [(0, 0, 1, 1, 2), (1, 0, 1, 0, 2)]),
+        3: (6, 6, [(0, 0, 1, 1, 4), (0, 2, 3, 2, 4), (1, 0, 1, 0, 4), (1, 2, 3, 2, 5), (2, 0, 1, 0, 5),
+                   (2, 2, 3, 1, 5)]),
+        4: (9, 12, [(0, 0, 1, 1, 6), (0, 2, 3, 2, 6), (0, 4, 5, 3, 6), (1, 0, 1, 0, 6), (1, 2, 3, 2, 7),
+                    (1, 4, 5, 3, 7), (2, 0, 1, 0, 7), (2, 2, 3, 1, 7), (2, 4, 5, 3, 8), (3, 0, 1, 0, 8),
+                    (3, 2, 3, 1, 8), (3, 4, 5, 2, 8)]),
+    }
+    ids = np.unique(datasets)
+    n_chunks, n_terms, terms = tables[len(ids)]
+    shuffled = [np.random.permutation(np.where(datasets == i)[0]) for i in ids]
+    m = min(len(s) // n_chunks for s in shuffled)
+    ch = [[s[i::n_chunks][:m] for i in range(n_chunks)] for s in shuffled]
+    tm = torch.nn.TripletMarginLoss(margin=margin, p=2)
+    loss = 0
+    for sa, ca, cp, sn, cn in terms:
+        loss = loss + tm(z[ch[sa][ca]], z[ch[sa][cp]], z[ch[sn][cn]])
+    for sa, ca, cp, _, _ in terms:
+        loss = loss + torch.pairwise_distance(z[ch[sa][ca]], z[ch[sa][cp]]).mean()
+    return loss / n_terms
+
+
+def msps_forward(sd, hparams, x, eps=None, use_mean=False):
+    """MSPSVAE.forward (vaes.py:893-924) -> (x_hat, z, mu, logvar, y_hat), mu = [z_s, z_b, z_u]."""
+    h = encoder_features(sd, hparams, x)
+    pre = F.linear(h, sd['encoding.FF.weight'], sd['encoding.FF.bias'])
+    z_s = F.linear(pre, sd['encoding.A.weight'])
+    z_u = F.linear(pre, sd['encoding.B.weight'])
+    z_b = F.linear(pre, sd['encoding.C.weight'], sd['encoding.C.bias'])
+    logvar = F.linear(h, sd['encoding.logvar.weight'], sd['encoding.logvar.bias'])
+    mu = torch.cat([z_s, z_b, z_u], 1)
+    z = mu if use_mean else eps * torch.exp(logvar) + mu
+    y_hat = z_s * sd['encoding.D.weight'] + sd['encoding.D.bias']
+    return decode(sd, hparams, z), z, mu, logvar, y_hat
+
+
+def msps_loss(sd, hparams, x, labels, eps, masks=None, sessions=None, want_grads=True):
+    """MSPSVAE.loss (vaes.py:926-1077) on the whole batch; ``sessions`` (per-frame session id) adds the triplet
+    term of a multi-session batch.  'label_r2' (host-side sklearn) is omitted."""
+    nl, nb = hparams['n_labels'], hparams['n_background']
+    frozen = ('encoding.A.weight', 'encoding.B.weight', 'encoding.C.weight')
+    params = {k: v.detach().clone().requires_grad_(want_grads and k not in frozen) for k, v in sd.items()}
+    x_hat, z, mu, logvar, y_hat = msps_forward(params, hparams, x, eps)
+    t = {}
+    t['loss_data_ll'] = gaussian_ll(x, x_hat, masks)
+    t['loss_label_ll'] = gaussian_ll(labels, y_hat)
+    t['loss_zs_kl'] = kl_div_to_std_normal(mu[:, :nl], logvar[:, :nl])
+    t['loss_zu_mi'], t['loss_zu_tc'], t['loss_zu_dwkl'] = decomposed_kl(
+        z[:, nl + nb:], mu[:, nl + nb:], logvar[:, nl + nb:])
+    loss = (-t['loss_data_ll'] - hparams['ps_vae.alpha'] * t['loss_label_ll'] + t['loss_zs_kl'] + t['loss_zu_mi']
+            + hparams['ps_vae.beta'] * t['loss_zu_tc'] + t['loss_zu_dwkl'])
+    if sessions is not None:
+        t['loss_triplet'] = triplet_loss(mu[:, nl:nl + nb], sessions)
+        loss = loss + hparams['ps_vae.delta'] * t['loss_triplet']
+    if want_grads:
+        loss.backward()
+    vals = {k: v.item() for k, v in t.items()}
+    vals['loss'] = loss.item()
+    vals['loss_data_mse'] = gaussian_ll_to_mse(vals['loss_data_ll'], int(np.prod(x.shape[1:])))
+    grads = {k: v.grad for k, v in params.items() if v.grad is not None} if want_grads else {}
+    return vals, grads
+
+
+# ------------------------------------------------------------------------------------------------
 # VAE / beta-TC-VAE (models/vaes.py:38-208, 367-503)
 # ------------------------------------------------------------------------------------------------
 
@@ -410,6 +480,10 @@ def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class
     if model_class == 'ps-vae':
         hp.update({'n_labels': n_labels, 'ps_vae.alpha': 1000, 'ps_vae.beta': 10,
                    'ps_vae.anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
+    if model_class == 'msps-vae':
+        hp.update({'n_labels': n_labels, 'n_background': 2, 'n_sessions_per_batch': 2, 'ps_vae.alpha': 1000,
+                   'ps_vae.beta': 10, 'ps_vae.delta': 50, 'ps_vae.anneal_epochs': 0, 'max_n_epochs': 10,
+                   'variational': True})
     if model_class == 'cond-ae':
         hp.update({'n_labels': n_labels, 'conditional_encoder': conditional_encoder})
     if model_class == 'cond-vae':
@@ -452,6 +526,15 @@ def init_state_dict(hparams, seed=0, dtype=torch.float32):
         q, _ = torch.linalg.qr(torch.randn(L, L, generator=g, dtype=torch.float64))
         sd['encoding.A.weight'] = q[:nl].to(dtype).contiguous()
         sd['encoding.B.weight'] = q[nl:].to(dtype).contiguous()
+        sd['encoding.D.weight'] = uniform((nl,), 1 / math.sqrt(nl))
+        sd['encoding.D.bias'] = uniform((nl,), 1 / math.sqrt(nl))
+    if hparams.get('model_class') == 'msps-vae':
+        nl, nb = hparams['n_labels'], hparams['n_background']
+        q, _ = torch.linalg.qr(torch.randn(L, L, generator=g, dtype=torch.float64))
+        sd['encoding.A.weight'] = q[:nl].to(dtype).contiguous()
+        sd['encoding.B.weight'] = q[nl + nb:].to(dtype).contiguous()
+        sd['encoding.C.weight'] = q[nl:nl + nb].to(dtype).contiguous()
+        sd['encoding.C.bias'] = uniform((nb,), 1 / math.sqrt(L))
         sd['encoding.D.weight'] = uniform((nl,), 1 / math.sqrt(nl))
         sd['encoding.D.bias'] = uniform((nl,), 1 / math.sqrt(nl))
     if hparams.get('model_class') == 'cond-ae-msp':

@@ -46,6 +46,7 @@ CAE_CASES = [
     ('condae_enc_32x32x2_l8_b6', 2, 32, 32, 8, 6, 'cond-ae+enc', 4, 4),   # + one-hot label images as channels
     ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4),
     ('condvae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-vae', 4, 4),
+    ('mspsvae_32x32x2_l8_b24', 2, 32, 32, 8, 24, 'msps-vae', 3, 0),   # 2 sessions x 12 frames, triplet term
 ]
 
 
@@ -105,6 +106,90 @@ def run_reference_cond_vae(ConditionalVAE, vaes, name, hp, hp_ref, sd, inp, chun
     for k, gref in go.items():
         gr = res['grad.' + k]
         assert torch.allclose(gref, gr, atol=1e-4 * float(gr.abs().max()) + 1e-7), (name, k)
+    return res
+
+
+def run_reference_msps(case):
+    """MSPSVAE (vaes.py:849-1273): forward, the single-session loss dict and the two-session loss (triplet term;
+    numpy's global generator seeded before the call, as the tests do)."""
+    from behavenet.models.vaes import MSPSVAE
+    import behavenet.models.vaes as vaes
+    import behavenet.fitting.losses as ref_losses
+    name, c, h, w, L, b, mc, nl, chunk = case
+    hp = co.make_hparams(c, h, w, L, mc, nl)
+    sd = co.init_state_dict(hp, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    inp = {'x': torch.rand(b, c, h, w, generator=g), 'labels': torch.randn(b, nl, generator=g),
+           'eps': torch.randn(b, L, generator=g)}
+    inp['masks'] = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
+    hp_ref = dict(hp)
+    hp_ref['device'] = 'cpu'
+    np.random.seed(0)
+    model = MSPSVAE(hp_ref)
+    model.load_state_dict(sd)
+    model.eval()
+    state = {'pos': 0}
+    orig = torch.randn_like
+
+    def fake_randn_like(t, *a, **k):
+        n = t.shape[0]
+        e = inp['eps'][state['pos']:state['pos'] + n]
+        state['pos'] += n
+        return e.to(t.dtype)
+    vaes.torch.randn_like = fake_randn_like
+    res = {}
+    half = b // 2
+    try:
+        with torch.no_grad():
+            x_hat, z, mu, logvar, y_hat = model(inp['x'])
+        res.update(x_hat=x_hat, z=z, mu=mu, logvar=logvar, y_hat=y_hat)
+        model.curr_epoch = 1
+        state['pos'] = 0
+        single = model.loss({'images': inp['x'][None], 'labels': inp['labels'][None], 'masks': inp['masks'][None]},
+                            accumulate_grad=False)
+        for k, v in single.items():
+            res['single.' + k] = torch.tensor(float(v), dtype=torch.float64)
+        datas = [{'images': inp['x'][None, :half], 'labels': inp['labels'][None, :half], 'masks': inp['masks'][None, :half]},
+                 {'images': inp['x'][None, half:], 'labels': inp['labels'][None, half:], 'masks': inp['masks'][None, half:]}]
+        model.zero_grad()
+        state['pos'] = 0
+        np.random.seed(7)
+        loss = model.loss(datas, dataset=[0, 1], accumulate_grad=True)
+    finally:
+        vaes.torch.randn_like = orig
+    for k, v in loss.items():
+        res['loss.' + k] = torch.tensor(float(v), dtype=torch.float64)
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            res['grad.' + k] = p.grad.clone()
+    # pin the restatement
+    o = co.msps_forward(sd, hp, inp['x'], inp['eps'])
+    for a, bref in zip(o, (x_hat, z, mu, logvar, y_hat)):
+        assert torch.allclose(a, bref, atol=2e-5), name
+    lo, _ = co.msps_loss(sd, hp, inp['x'], inp['labels'], inp['eps'], inp['masks'], want_grads=False)
+    for k in lo:
+        ref = float(res['single.' + k])
+        assert abs(lo[k] - ref) <= 1e-5 * max(1.0, abs(ref)), (name, 'single', k, lo[k], ref)
+    sessions = np.concatenate([np.zeros(half), np.ones(b - half)])
+    np.random.seed(7)
+    lo, go = co.msps_loss(sd, hp, inp['x'], inp['labels'], inp['eps'], inp['masks'], sessions=sessions)
+    for k in lo:
+        ref = float(res['loss.' + k])
+        assert abs(lo[k] - ref) <= 1e-5 * max(1.0, abs(ref)), (name, k, lo[k], ref)
+    assert set(go) == {k[5:] for k in res if k.startswith('grad.')}, (name, set(go) ^ {k[5:] for k in res if k.startswith('grad.')})
+    for k, gref in go.items():
+        gr = res['grad.' + k]
+        assert torch.allclose(gref, gr, atol=1e-4 * float(gr.abs().max()) + 1e-7), (name, k)
+    # the triplet rule for 3 and 4 sessions, against the reference function itself
+    tm = torch.nn.TripletMarginLoss(margin=1.0, p=2)
+    for ns in (2, 3, 4):
+        zz = torch.randn(40 * ns, 3, generator=g)
+        ds = np.repeat(np.arange(ns), 40)[np.random.RandomState(ns).permutation(40 * ns)]
+        np.random.seed(11)
+        a = ref_losses.triplet_loss(tm, zz, ds)
+        np.random.seed(11)
+        bb = co.triplet_loss(zz, ds)
+        assert abs(float(a) - float(bb)) < 1e-6, (ns, float(a), float(bb))
     return res
 
 
@@ -175,6 +260,8 @@ def run_reference(case):
     name, c, h, w, L, b, mc, nl, chunk = case
     if mc.startswith('cond-'):
         return run_reference_cond(case)
+    if mc == 'msps-vae':
+        return run_reference_msps(case)
     hp = co.make_hparams(c, h, w, L, mc, nl)
     sd = co.init_state_dict(hp, seed=0)
     inp = synth_inputs(case)

@@ -269,3 +269,42 @@ def test_conditional_models_protocol_cpu():
     lin['model_type'] = 'linear'
     with pytest.raises(NotImplementedError):
         AEMSP(lin)
+
+
+def test_mspsvae_protocol_and_triplet_rule_cpu():
+    """MSPSVAE (reference vaes.py:849-1462): state_dict names / frozen orthogonal A, B, C; the product's
+    general triplet rule equals the oracle's term-by-term table (itself checked against the reference's
+    losses.triplet_loss for 2-4 sessions by oracle/gen_golden.py); the small loss helpers equal the oracle's."""
+    from behavenet_b200.models import MSPSVAE
+    from behavenet_b200.models import vaes
+    np.random.seed(1)
+    hp = co.make_hparams(2, 32, 32, 8, 'msps-vae', 3)
+    m = MSPSVAE(copy.deepcopy(hp))
+    assert set(m.state_dict()) == set(co.init_state_dict(hp))
+    enc = m.encoding
+    assert not (enc.A.weight.requires_grad or enc.B.weight.requires_grad or enc.C.weight.requires_grad)
+    assert enc.C.bias.requires_grad and enc.B.weight.shape == (8 - 3 - 2, 8)
+    q = torch.cat([enc.A.weight, enc.C.weight, enc.B.weight], 0)
+    assert torch.allclose(q @ q.T, torch.eye(8), atol=1e-5)
+    copy.deepcopy(m)
+    one = dict(hp)
+    one['n_sessions_per_batch'] = 1
+    with pytest.raises(ValueError):
+        MSPSVAE(one)
+    g = torch.Generator().manual_seed(0)
+    tm = torch.nn.TripletMarginLoss(margin=1.0, p=2)
+    for ns in (2, 3, 4):
+        z = torch.randn(37 * ns, 4, generator=g)
+        ds = np.repeat(np.arange(ns) * 3, 37)[np.random.RandomState(ns).permutation(37 * ns)]
+        np.random.seed(5)
+        a = vaes.triplet_loss(tm, z, ds)
+        np.random.seed(5)
+        b = co.triplet_loss(z, ds)
+        assert abs(float(a) - float(b)) < 1e-6, ns
+    with pytest.raises(NotImplementedError):
+        vaes.triplet_loss(tm, torch.zeros(50, 2), np.repeat(np.arange(5), 10))
+    z, mu, lv = torch.randn(9, 3, generator=g), torch.randn(9, 3, generator=g), 0.1 * torch.randn(9, 3, generator=g)
+    for a, b in zip(vaes.decomposed_kl(z, mu, lv), co.decomposed_kl(z, mu, lv)):
+        assert abs(float(a) - float(b)) < 1e-6
+    x, xh, mk = torch.rand(5, 2, 4, 4, generator=g), torch.rand(5, 2, 4, 4, generator=g), (torch.rand(5, 2, 4, 4, generator=g) > 0.3).float()
+    assert abs(float(vaes.gaussian_ll(x, xh, mk)) - float(co.gaussian_ll(x, xh, mk))) < 1e-5

@@ -1,2 +1,2 @@
-from .data_generator import (ArraySource, HDF5Source, PrefetchSessionsGenerator, ConcatSessionsGenerator,  # noqa: F401
-                             split_trials)
+from .data_generator import (ArraySource, HDF5Source, PrefetchSessionsGenerator, PrefetchSessionsGeneratorMulti,  # noqa: F401
+                             ConcatSessionsGenerator, ConcatSessionsGeneratorMulti, split_trials)

@@ -181,6 +181,7 @@ class PrefetchSessionsGenerator:
         self._lock = threading.Lock()
         self._copy_stream = None
         self._div255 = None
+        self._group_size = 1                                    # trials per next_batch call (Multi: sessions per batch)
         for k in _SPLITS:
             self._streams[k] = None
 
@@ -205,7 +206,7 @@ class PrefetchSessionsGenerator:
             s = int(rng.choice(self.n_datasets, p=self.batch_ratios))
             if not left[s]:
                 continue                      # every session has train trials, so every ratio is > 0
-            plan.append((s, int(left[s].pop(0))))
+            plan.append([(s, int(left[s].pop(0)))])
             todo -= 1
         return plan
 
@@ -277,21 +278,28 @@ class PrefetchSessionsGenerator:
     def _worker(self, plan, q, stop):
         try:
             on_gpu = (not self.as_numpy) and str(self.device).startswith('cuda')
-            slots = [_PinnedSlot() for _ in range(self.depth + 2)] if on_gpu else None
-            for i, (s, idx) in enumerate(plan):
+            slots = [_PinnedSlot() for _ in range((self.depth + 2) * self._group_size)] if on_gpu else None
+            n_slot = 0
+            for group in plan:                                   # a group = the trials served by one call
                 if stop.is_set():
                     return
-                host, shard = self._load_host(s, idx)
-                if on_gpu:
-                    sample, event = self._to_device(host, slots[i % len(slots)])
-                else:
-                    sample, event = self._finish_host(host), None
-                sample['batch_idx'] = idx if self.as_numpy else _as_index(idx)
-                if self.shard_frames:
-                    sample['shard'] = shard
+                samples, sessions, events = [], [], []
+                for s, idx in group:
+                    host, shard = self._load_host(s, idx)
+                    if on_gpu:
+                        sample, event = self._to_device(host, slots[n_slot % len(slots)])
+                        n_slot += 1
+                        events.append(event)
+                    else:
+                        sample = self._finish_host(host)
+                    sample['batch_idx'] = idx if self.as_numpy else _as_index(idx)
+                    if self.shard_frames:
+                        sample['shard'] = shard
+                    samples.append(sample)
+                    sessions.append(s)
                 while not stop.is_set():
                     try:
-                        q.put((sample, s, event), timeout=0.1)
+                        q.put((samples, sessions, events), timeout=0.1)
                         break
                     except queue.Full:
                         continue
@@ -303,13 +311,16 @@ class PrefetchSessionsGenerator:
     def reset_iterators(self, dtype):
         """Start a fresh pass over ``dtype`` ('train' | 'val' | 'test' | 'all')."""
         for k in (_SPLITS if dtype == 'all' else (dtype,)):
-            self._stop(k)
-            plan = self._plan(k)
-            q = queue.Queue(maxsize=self.depth)
-            stop = threading.Event()
-            th = threading.Thread(target=self._worker, args=(plan, q, stop), daemon=True)
-            self._streams[k] = (q, stop, th)
-            th.start()
+            self._start(k, self._plan(k))
+
+    def _start(self, k, plan):
+        """(Re)start the worker that serves ``plan`` under stream key ``k``."""
+        self._stop(k)
+        q = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+        th = threading.Thread(target=self._worker, args=(plan, q, stop), daemon=True)
+        self._streams[k] = (q, stop, th)
+        th.start()
 
     def _stop(self, k):
         st = self._streams.get(k)
@@ -327,29 +338,37 @@ class PrefetchSessionsGenerator:
     def next_batch(self, dtype):
         """(sample, dataset): the next trial of ``dtype``; a new pass starts when the previous one is spent
         or none has been started (the reference builds its iterators in the constructor)."""
-        if self._streams[dtype] is None:
-            self.reset_iterators(dtype)
-        q = self._streams[dtype][0]
+        samples, sessions = self._next_group(dtype)
+        return samples[0], sessions[0]
+
+    def _next_group(self, key):
+        """The next planned group of ``key``: ([samples], [sessions]); copies are ordered before the caller's
+        stream.  Raises StopIteration when the pass is spent."""
+        if self._streams.get(key) is None:
+            self.reset_iterators(key)
+        q = self._streams[key][0]
         item = q.get()
         if item is None:
-            self._streams[dtype][2].join()
-            self._streams[dtype] = None
-            raise StopIteration('no %s trials left: call reset_iterators' % dtype)
+            self._streams[key][2].join()
+            self._streams[key] = None
+            raise StopIteration('no %s trials left: call reset_iterators' % key)
         if isinstance(item, BaseException):
-            self._streams[dtype] = None
+            self._streams[key] = None
             raise item
-        sample, s, event = item
-        if event is not None:
+        samples, sessions, events = item
+        if events:
             import torch
             cur = torch.cuda.current_stream()
-            cur.wait_event(event)
-            for v in sample.values():
-                if torch.is_tensor(v) and v.is_cuda:
-                    v.record_stream(cur)
-        return sample, s
+            for event in events:
+                cur.wait_event(event)
+            for sample in samples:
+                for v in sample.values():
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(cur)
+        return samples, sessions
 
     def close(self):
-        for k in _SPLITS:
+        for k in list(self._streams):
             self._stop(k)
 
     def __del__(self):
@@ -359,6 +378,68 @@ class PrefetchSessionsGenerator:
             pass
 
 
+class PrefetchSessionsGeneratorMulti(PrefetchSessionsGenerator):
+    """Drop-in for the reference's ``ConcatSessionsGeneratorMulti`` (data_generator.py:636-800): a training call
+    serves one trial from each of ``n_sessions_per_batch`` DIFFERENT sessions (the MSPS-VAE's triplet loss needs
+    them), as ``([samples], [sessions])``; validation / test calls serve single trials."""
+
+    def __init__(self, sources, n_sessions_per_batch=2, **kwargs):
+        if n_sessions_per_batch > 4:
+            raise NotImplementedError          # the triplet loss covers 2-4 sessions
+        if kwargs.get('as_numpy', False):
+            raise NotImplementedError
+        super().__init__(sources, **kwargs)
+        self.n_sessions_per_batch = n_sessions_per_batch
+        self._group_size = n_sessions_per_batch
+        self._single_train = self.n_tot_batches['train']
+        self.n_tot_batches['train'] = int(self.n_tot_batches['train'] / n_sessions_per_batch)
+
+    def __str__(self):
+        return 'Multi' + super().__str__()
+
+    def _plan_groups(self):
+        """Groups drawn like the reference: per slot a session ~ the renormalised ratios of the sessions not yet
+        in the group; a session found exhausted is dropped for this group; the pass ends when fewer sessions
+        than open slots remain (trials already drawn for the unfinished group are lost, as in the reference)."""
+        rng = self._order_rng
+        left = [list(rng.permutation(ds.batch_idxs['train'])) for ds in self.datasets]
+        plan = []
+        while True:
+            ratios = np.copy(self.batch_ratios)
+            group = []
+            for slot in range(self.n_sessions_per_batch):
+                while True:
+                    if np.sum(ratios > 0) < self.n_sessions_per_batch - slot:
+                        return plan
+                    s = int(rng.choice(self.n_datasets, p=ratios))
+                    ratios[s] = 0
+                    if np.sum(ratios) > 0:
+                        ratios = ratios / np.sum(ratios)
+                    if left[s]:
+                        group.append((s, int(left[s].pop(0))))
+                        break
+            plan.append(group)
+
+    def reset_iterators(self, dtype):
+        super().reset_iterators(dtype)                       # single-trial passes (val / test / train singles)
+        if dtype in ('train', 'all'):
+            self._multi_spent = False
+            self._start('train#multi', self._plan_groups())
+
+    def next_batch(self, dtype, return_multiple=True):
+        if dtype == 'train' and return_multiple:
+            if getattr(self, '_multi_spent', False):
+                return None, None                            # until reset_iterators, like the reference
+            if self._streams.get('train#multi') is None:
+                self._start('train#multi', self._plan_groups())
+            try:
+                return self._next_group('train#multi')
+            except StopIteration:
+                self._multi_spent = True
+                return None, None                            # what the reference returns when sessions run out
+        return super().next_batch(dtype)
+
+
 def _as_index(idx):
     import torch
     return torch.tensor([idx])
@@ -366,3 +447,4 @@ def _as_index(idx):
 
 # the reference's name, for ``from behavenet.data.data_generator import ConcatSessionsGenerator`` swaps
 ConcatSessionsGenerator = PrefetchSessionsGenerator
+ConcatSessionsGeneratorMulti = PrefetchSessionsGeneratorMulti

@@ -148,3 +148,39 @@ def test_prefetch_to_device_and_raw_uint8_into_encoder():
             assert torch.equal(zf, z8)
     gen.close()
     raw.close()
+
+
+def test_multi_session_generator_groups_distinct_sessions():
+    """ConcatSessionsGeneratorMulti protocol (data_generator.py:636-800): training calls return one trial from
+    each of n_sessions_per_batch different sessions, every trial at most once per pass, (None, None) when the
+    sessions run out; val / test calls return single trials."""
+    from behavenet_b200.data import PrefetchSessionsGeneratorMulti
+    srcs = [_session(30, 0, name='a'), _session(20, 1, name='b'), _session(20, 2, name='c')]
+    gen = PrefetchSessionsGeneratorMulti(srcs, n_sessions_per_batch=2, device='cpu', rng_seed=1)
+    single_total = sum(len(d.batch_idxs['train']) for d in gen.datasets)
+    assert gen.n_tot_batches['train'] == single_total // 2
+    for epoch in range(2):
+        gen.reset_iterators('train')
+        seen = [set() for _ in srcs]
+        n_groups = 0
+        while True:
+            samples, sessions = gen.next_batch('train')
+            if samples is None:
+                assert sessions is None
+                break
+            n_groups += 1
+            assert len(samples) == 2 and len(set(sessions)) == 2
+            for smp, s in zip(samples, sessions):
+                idx = int(smp['batch_idx'])
+                assert idx in set(gen.datasets[s].batch_idxs['train'].tolist()) and idx not in seen[s]
+                seen[s].add(idx)
+                assert np.array_equal(smp['images'][0].numpy(), srcs[s].load('images', idx).astype('float32') / 255)
+        assert n_groups >= 16                      # the smaller two sessions (16 train trials each) bound the pass
+        assert gen.next_batch('train') == (None, None)        # stays spent until reset_iterators
+    d, s = gen.next_batch('val')
+    assert isinstance(d, dict) and d['images'].shape[0] == 1
+    d, s = gen.next_batch('train', return_multiple=False)
+    assert isinstance(d, dict)
+    with pytest.raises(NotImplementedError):
+        PrefetchSessionsGeneratorMulti(srcs, n_sessions_per_batch=5, device='cpu')
+    gen.close()

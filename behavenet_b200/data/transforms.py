@@ -22,7 +22,8 @@ class Compose(object):
         return signal
 
     def __repr__(self):
-        return self.__class__.__name__ + '(' + ''.join('\n    {0}'.format(t) for t in self.transforms) + '\n)'
+        # the reference's string, backspaces included (transforms.py:40-45)
+        return self.__class__.__name__ + '(' + ''.join('{0}, '.format(t) for t in self.transforms) + '\b\b)'
 
 
 class Transform(object):

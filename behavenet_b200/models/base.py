@@ -14,55 +14,52 @@ from torch import nn
 __all__ = ['BaseModule', 'BaseModel', 'DiagLinear']
 
 
-class BaseModule(nn.Module):
-    """Template for encoder / decoder modules."""
+def _abstract(name):
+    """A method every concrete encoder / decoder / model has to provide."""
+    def method(self, *args, **kwargs):
+        raise NotImplementedError('%s.%s' % (type(self).__name__, name))
+    method.__name__ = name
+    return method
+
+
+class _Template(nn.Module):
+    """What the training code expects of both modules and models: hparams-style constructors that ignore
+    extra arguments, a printable architecture, ``build_model`` and ``forward``."""
 
     def __init__(self, *args, **kwargs):
         super().__init__()
 
-    def __str__(self):
-        raise NotImplementedError
+    __str__ = _abstract('__str__')
+    build_model = _abstract('build_model')
+    forward = _abstract('forward')
 
-    def build_model(self):
-        raise NotImplementedError
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError
+class BaseModule(_Template):
+    """Template for encoder / decoder modules (reference base.py:12-39)."""
+
+    def _set_trainable(self, flag):
+        for p in self.parameters():
+            p.requires_grad = flag
 
     def freeze(self):
-        for p in self.parameters():
-            p.requires_grad = False
+        self._set_trainable(False)
 
     def unfreeze(self):
-        for p in self.parameters():
-            p.requires_grad = True
+        self._set_trainable(True)
 
 
-class BaseModel(nn.Module):
-    """Template for models."""
+class BaseModel(_Template):
+    """Template for models (reference base.py:42-67)."""
 
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-
-    def __str__(self):
-        raise NotImplementedError
-
-    def build_model(self):
-        raise NotImplementedError
-
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError
-
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError
+    loss = _abstract('loss')
 
     def save(self, filepath):
-        """Save the state_dict (same file format as the reference, base.py:61-63)."""
+        """state_dict in the reference's file format (base.py:61-63)."""
         torch.save(self.state_dict(), filepath)
 
     def get_parameters(self):
-        """Parameters with gradient updates turned on (consumed by Adam, training.py:284)."""
-        return filter(lambda p: p.requires_grad, self.parameters())
+        """The trainable parameters, as an iterator (handed to Adam at training.py:284)."""
+        return (p for p in self.parameters() if p.requires_grad)
 
 
 class DiagLinear(nn.Module):

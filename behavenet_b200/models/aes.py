@@ -305,10 +305,7 @@ class AE(BaseModel):
         return {'loss': loss_val}
 
 
-def _masked_mse(pred, true, masks=None):
-    """losses.mse (reference fitting/losses.py:36-59): mean over ALL elements."""
-    d = (pred - true) ** 2
-    return torch.mean(d * masks) if masks is not None else torch.mean(d)
+from behavenet_b200.fitting.losses import mse as _masked_mse      # noqa: E402  (losses.mse, losses.py:36-59)
 
 
 class _AutogradChunkedAE(AE):

@@ -16,6 +16,8 @@ from behavenet_b200 import _lib, parallel
 from behavenet_b200.models.aes import AE, ConvAEDecoder, ConvAEEncoder
 from behavenet_b200.models.base import DiagLinear
 from behavenet_b200.models._engine import CaeDriver, Runtime
+from behavenet_b200.fitting.losses import (gaussian_ll, gaussian_ll_to_mse, kl_div_to_std_normal, decomposed_kl,  # noqa: F401
+                                           triplet_loss)
 
 __all__ = ['reparameterize', 'VAE', 'BetaTCVAE', 'PSVAE', 'ConvAEPSEncoder']
 
@@ -294,18 +296,15 @@ class ConditionalVAE(VAE):
             x_hat, _, mu, logvar = self.forward(
                 x[b:e], dataset=dataset, labels=y[b:e], labels_2d=None if y2d is None else y2d[b:e],
                 eps=None if eps is None else eps[b:e])
-            d = (x[b:e] - x_hat) ** 2
-            if m is not None:
-                d = d * m[b:e]
-            ll = torch.mean(-0.5 * LN2PI * n_dims - 0.5 * d.reshape(e - b, -1).sum(1))   # losses.py:62-96, std = 1
-            kl = torch.mean(0.5 * torch.sum(logvar.exp() - logvar + mu ** 2 - 1, dim=1))  # losses.py:130-147
+            ll = gaussian_ll(x[b:e], x_hat, None if m is None else m[b:e])
+            kl = kl_div_to_std_normal(mu, logvar)
             loss = -ll + beta * kl
             if accumulate_grad:
                 loss.backward()
             vals['loss'] += loss.item() * (e - b)
             vals['loss_ll'] += ll.item() * (e - b)
             vals['loss_kl'] += kl.item() * (e - b)
-            vals['loss_mse'] += (ll.item() + 0.5 * LN2PI * n_dims) * -2.0 / n_dims * (e - b)   # losses.py:99-127
+            vals['loss_mse'] += float(gaussian_ll_to_mse(ll.item(), n_dims)) * (e - b)
         out = {k: v / n for k, v in vals.items()}
         out['beta'] = beta
         return out
@@ -590,55 +589,6 @@ class PSVAE(AE):
 # multi-session PS-VAE (reference vaes.py:849-1462)
 # ------------------------------------------------------------------------------------------------
 
-def gaussian_ll(y_pred, y_mean, masks=None):
-    """Unit-variance Gaussian log-likelihood, summed over dims, averaged over the batch (reference
-    fitting/losses.py:62-96)."""
-    d = (y_pred - y_mean) ** 2
-    if masks is not None:
-        d = d * masks
-    n_dims = int(np.prod(y_pred.shape[1:]))
-    return torch.mean(-0.5 * LN2PI * n_dims - 0.5 * d.reshape(d.shape[0], -1).sum(1))
-
-
-def decomposed_kl(z, mu, logvar):
-    """(index-code MI, total correlation, dimension-wise KL) minibatch estimators (losses.py:284-372):
-    lq[j, i, l] = log q(z_j,l | x_i)."""
-    lq = -0.5 * (torch.exp(-logvar)[None] * (z[:, None] - mu[None]) ** 2 + logvar[None] + LN2PI)
-    joint = lq.sum(2)
-    log_qz = torch.logsumexp(joint, dim=1)
-    log_qz_prod = torch.logsumexp(lq, dim=1).sum(1)
-    log_pz = (-0.5 * (z ** 2 + LN2PI)).sum(1)
-    return ((torch.diagonal(joint) - log_qz).mean(), (log_qz - log_qz_prod).mean(), (log_qz_prod - log_pz).mean())
-
-
-def triplet_loss(triplet_loss_obj, z, datasets):
-    """Session-separation loss on the background latents (losses.py:402-513) for 2-4 sessions in a batch.
-
-    Every session's frames are shuffled (numpy's global generator, sessions in ascending id order) and dealt
-    into 3 * (n - 1) equal chunks: chunks (2k, 2k + 1) are the anchor / positive of the k-th other session,
-    whose negative chunk is 2 * (n - 1) + (rank of the anchor session among that session's others).  The sum
-    of the triplet terms and of the mean anchor-positive distances is divided by the reference's constant
-    (3, 6, 12)."""
-    ids = np.unique(datasets)
-    n = len(ids)
-    if n < 2 or n > 4:
-        raise NotImplementedError
-    n_chunks = 3 * (n - 1)
-    perms = [np.random.permutation(np.where(datasets == i)[0]) for i in ids]
-    m = min(len(q) // n_chunks for q in perms)
-    chunks = [[q[i::n_chunks][:m] for i in range(n_chunks)] for q in perms]
-    loss = 0
-    for x in range(n):
-        for k, y in enumerate(o for o in range(n) if o != x):
-            rank = x if x < y else x - 1
-            loss = loss + triplet_loss_obj(z[chunks[x][2 * k]], z[chunks[x][2 * k + 1]],
-                                           z[chunks[y][2 * (n - 1) + rank]])
-    for x in range(n):
-        for k in range(n - 1):
-            loss = loss + torch.pairwise_distance(z[chunks[x][2 * k]], z[chunks[x][2 * k + 1]]).mean()
-    return loss / {2: 3, 3: 6, 4: 12}[n]
-
-
 class ConvAEMSPSEncoder(ConvAEEncoder):
     """Encoder with supervised (A), unsupervised (B) and session-background (C) subspaces (reference
     vaes.py:1366-1462): rows of one fixed random orthogonal matrix; C carries a trainable bias."""
@@ -729,8 +679,7 @@ class MSPSVAE(PSVAE):
         t = {}
         t['loss_data_ll'] = gaussian_ll(x, x_hat, m)
         t['loss_label_ll'] = gaussian_ll(y, y_hat, n)
-        t['loss_zs_kl'] = torch.mean(0.5 * torch.sum(
-            logvar[:, :nl].exp() - logvar[:, :nl] + mu[:, :nl] ** 2 - 1, dim=1))
+        t['loss_zs_kl'] = kl_div_to_std_normal(mu[:, :nl], logvar[:, :nl])
         t['loss_zu_mi'], t['loss_zu_tc'], t['loss_zu_dwkl'] = decomposed_kl(
             sample[:, nl + nb:], mu[:, nl + nb:], logvar[:, nl + nb:])
         total = (-t['loss_data_ll'] - alpha * t['loss_label_ll'] + t['loss_zs_kl'] + kl * t['loss_zu_mi']
@@ -745,7 +694,7 @@ class MSPSVAE(PSVAE):
         if not multi:
             out['loss_triplet'] = 0          # the reference keeps the zero it initialised the entry with
         n_dims = int(np.prod(x.shape[1:]))
-        out['loss_data_mse'] = (out['loss_data_ll'] + 0.5 * LN2PI * n_dims) * -2.0 / n_dims
+        out['loss_data_mse'] = float(gaussian_ll_to_mse(out['loss_data_ll'], n_dims))
         y_np, yh_np = y.detach().cpu().numpy(), y_hat.detach().cpu().numpy()
         if n is not None:
             keep = n.detach().cpu().numpy() == 1

@@ -308,3 +308,62 @@ def test_mspsvae_protocol_and_triplet_rule_cpu():
         assert abs(float(a) - float(b)) < 1e-6
     x, xh, mk = torch.rand(5, 2, 4, 4, generator=g), torch.rand(5, 2, 4, 4, generator=g), (torch.rand(5, 2, 4, 4, generator=g) > 0.3).float()
     assert abs(float(vaes.gaussian_ll(x, xh, mk)) - float(co.gaussian_ll(x, xh, mk))) < 1e-5
+
+
+def test_loss_composition_of_autograd_path_models_with_oracle_forward():
+    """ConditionalAE / ConditionalVAE / AEMSP / MSPSVAE ``loss()`` bodies (chunking, weighting, dict keys) on
+    CPU: the model's ``forward`` is replaced by the oracle's restatement of it, everything after that is the
+    product code; values against the fixtures written by the reference classes."""
+    from behavenet_b200 import models as M
+    from tests.helpers import synth_cond_inputs
+
+    def run(mc, cls, name, c, h, w, L, b, nl, chunk, fwd, n_latents=0, **loss_kw):
+        gold = load_golden(name)
+        hp = co.make_hparams(c, h, w, L, mc, nl)
+        sd = co.init_state_dict(hp, seed=0)
+        np.random.seed(0)
+        model = cls(copy.deepcopy(hp))
+        model.load_state_dict(sd)
+        model.forward = lambda x, **kw: fwd(model, sd, hp, x, **kw)
+        inp = synth_cond_inputs(c, h, w, b, nl, n_latents=n_latents)
+        data = {'images': inp['x'][None], 'labels': inp['labels'][None], 'masks': inp['masks'][None]}
+        if 'eps' in inp:
+            loss_kw['eps'] = inp['eps']
+        model.curr_epoch = 1
+        out = model.loss(data, accumulate_grad=False, chunk_size=chunk, **loss_kw)
+        for k, v in out.items():
+            if k != 'labels_r2':
+                ref = float(gold['loss.' + k])
+                assert abs(v - ref) <= 1e-5 * max(1.0, abs(ref)), (name, k, v, ref)
+        return out
+
+    run('cond-ae', M.ConditionalAE, 'condae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 4, 4,
+        lambda m, sd, hp, x, labels=None, labels_2d=None, **kw: co.cond_ae_forward(sd, hp, x, labels, labels_2d))
+    run('cond-vae', M.ConditionalVAE, 'condvae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 4, 4,
+        lambda m, sd, hp, x, labels=None, eps=None, **kw: co.cond_vae_forward(sd, hp, x, labels, eps), n_latents=6)
+    out = run('cond-ae-msp', M.AEMSP, 'aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 3, 4,
+              lambda m, sd, hp, x, **kw: co.aemsp_forward(sd, hp, x))
+    assert set(out) == {'loss', 'loss_mse', 'loss_msp', 'labels_r2'}
+    # MSPS-VAE: its fixture uses its own input draw (oracle/gen_golden.py run_reference_msps)
+    gold = load_golden('mspsvae_32x32x2_l8_b24')
+    hp = co.make_hparams(2, 32, 32, 8, 'msps-vae', 3)
+    sd = co.init_state_dict(hp, seed=0)
+    np.random.seed(0)
+    model = M.MSPSVAE(copy.deepcopy(hp))
+    model.load_state_dict(sd)
+    model.forward = lambda x, eps=None, **kw: co.msps_forward(sd, hp, x, eps)
+    g = torch.Generator().manual_seed(1234)
+    x, y = torch.rand(24, 2, 32, 32, generator=g), torch.randn(24, 3, generator=g)
+    eps = torch.randn(24, 8, generator=g)
+    m = (torch.rand(24, 2, 32, 32, generator=g) > 0.1).float()
+    model.curr_epoch = 1
+    single = model.loss({'images': x[None], 'labels': y[None], 'masks': m[None]}, accumulate_grad=False, eps=eps)
+    datas = [{'images': x[None, :12], 'labels': y[None, :12], 'masks': m[None, :12]},
+             {'images': x[None, 12:], 'labels': y[None, 12:], 'masks': m[None, 12:]}]
+    np.random.seed(7)
+    multi = model.loss(datas, dataset=[0, 1], accumulate_grad=False, eps=eps)
+    for tag, vals in (('single.', single), ('loss.', multi)):
+        assert len(vals) == 13
+        for k, v in vals.items():
+            ref = float(gold[tag + k])
+            assert abs(v - ref) <= 1e-5 * max(1.0, abs(ref)) + (1e-3 if k == 'label_r2' else 0), (tag, k, v, ref)

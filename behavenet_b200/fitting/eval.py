@@ -109,3 +109,47 @@ def export_latents(data_generator, model, filename=None):
             pickle.dump({'latents': latents[sess], 'trials': ds.batch_idxs}, f)
         filenames.append(fname)
     return filenames
+
+
+def export_states(hparams, data_generator, model, filename=None):
+    """Most likely ARHMM state sequence of every trial, one pickle per dataset (reference eval.py:120-181):
+    ``{'states': [per-trial int arrays, gap trials empty], 'trials': dataset.batch_idxs}``.
+
+    The reference calls ``hmm.most_likely_states`` once per trial (eval.py:167); here the trials of a split are
+    collected first and decoded by ONE Viterbi launch (``HMM.most_likely_states_batch``) when the model offers
+    it -- any object with only ``most_likely_states`` (ssm's interface) is served trial by trial."""
+    import os
+    import pickle
+    states = [[np.array([]) for _ in range(ds.n_trials)] for ds in data_generator.datasets]
+    key = 'labels' if hparams['model_class'].find('label') > -1 else 'ae_latents'
+    for dtype in ['train', 'val', 'test']:
+        data_generator.reset_iterators(dtype)
+        where, trials = [], []
+        for _ in range(data_generator.n_tot_batches[dtype]):
+            data, sess = data_generator.next_batch(dtype)
+            y = data[key][0]
+            y = y[0] if isinstance(y, (list, tuple)) or (hasattr(y, 'ndim') and y.ndim == 3) else y
+            y = y.detach().cpu().numpy() if hasattr(y, 'detach') else np.asarray(y)
+            idx = data['batch_idx'].item() if hasattr(data['batch_idx'], 'item') else int(data['batch_idx'])
+            where.append((sess, idx))
+            trials.append(np.asarray(y, dtype=np.float32))
+        if not trials:
+            continue
+        if hasattr(model, 'most_likely_states_batch'):
+            decoded = model.most_likely_states_batch(trials)
+        else:
+            decoded = [model.most_likely_states(y) for y in trials]
+        for (sess, idx), z in zip(where, decoded):
+            states[sess][idx] = z
+    filenames = []
+    for sess, ds in enumerate(data_generator.datasets):
+        if filename is None:
+            sess_id = '%s_%s_%s_%s_states.pkl' % (ds.lab, ds.expt, ds.animal, ds.session)
+            fname = os.path.join(hparams['expt_dir'], 'version_%i' % hparams['version'], sess_id)
+        else:
+            fname = filename
+        print('saving states %i of %i:\n%s' % (sess + 1, data_generator.n_datasets, fname))
+        with open(fname, 'wb') as f:
+            pickle.dump({'states': states[sess], 'trials': ds.batch_idxs}, f)
+        filenames.append(fname)
+    return filenames

@@ -184,3 +184,49 @@ def test_multi_session_generator_groups_distinct_sessions():
     with pytest.raises(NotImplementedError):
         PrefetchSessionsGeneratorMulti(srcs, n_sessions_per_batch=5, device='cpu')
     gen.close()
+
+
+def test_export_states_and_latents_file_formats(tmp_path):
+    """export_states (reference eval.py:120-181): every train / val / test trial decoded, gap trials left empty,
+    the reference's pickle layout; with a batch-capable model one call per split, otherwise one per trial."""
+    import pickle
+    from behavenet_b200.fitting.eval import export_states
+    rng = np.random.RandomState(0)
+    lens = [int(rng.randint(4, 9)) for _ in range(24)]
+    src = ArraySource({'ae_latents': [rng.randn(T, 3).astype(np.float32) for T in lens]},
+                      lab='l', expt='e', animal='a', session='s')
+    gen = PrefetchSessionsGenerator([src], device='cpu', rng_seed=0,
+                                    trial_splits={'train_tr': 4, 'val_tr': 1, 'test_tr': 1, 'gap_tr': 1})
+
+    class PerTrial:
+        calls = 0
+
+        def most_likely_states(self, y):
+            PerTrial.calls += 1
+            return (np.asarray(y)[:, 0] > 0).astype(np.int64)
+
+    class Batched(PerTrial):
+        batches = 0
+
+        def most_likely_states_batch(self, ys):
+            Batched.batches += 1
+            return [(np.asarray(y)[:, 0] > 0).astype(np.int64) for y in ys]
+
+    hp = {'model_class': 'arhmm', 'expt_dir': str(tmp_path), 'version': 0}
+    for model, fname in ((PerTrial(), tmp_path / 'a.pkl'), (Batched(), tmp_path / 'b.pkl')):
+        out = export_states(hp, gen, model, filename=str(fname))
+        assert out == [str(fname)]
+        with open(fname, 'rb') as f:
+            d = pickle.load(f)
+        assert set(d) == {'states', 'trials'} and len(d['states']) == 24
+        used = np.concatenate([d['trials'][k] for k in ('train', 'val', 'test')])
+        for i in range(24):
+            if i in used:
+                assert np.array_equal(d['states'][i], (src.load('ae_latents', i)[:, 0] > 0).astype(np.int64))
+            else:
+                assert d['states'][i].size == 0                      # gap trial
+    assert PerTrial.calls == 12 and Batched.batches == 3       # 2 blocks of 4 + 1 + 1 trials (+ 3 gap trials each)
+    (tmp_path / 'version_0').mkdir()
+    out = export_states(hp, gen, Batched())
+    assert out[0].endswith('version_0/l_e_a_s_states.pkl')
+    gen.close()

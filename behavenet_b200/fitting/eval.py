@@ -153,3 +153,47 @@ def export_states(hparams, data_generator, model, filename=None):
             pickle.dump({'states': states[sess], 'trials': ds.batch_idxs}, f)
         filenames.append(fname)
     return filenames
+
+
+# model_class -> (position of the latent mean in forward()'s tuple, extra forward kwargs it understands)
+_FORWARD_LAYOUT = {
+    'ae': (1, ()),
+    'cond-ae-msp': (1, ()),
+    'vae': (1, ('use_mean',)),
+    'beta-tcvae': (1, ('use_mean',)),
+    'ps-vae': (2, ('use_mean',)),
+    'msps-vae': (2, ('use_mean',)),
+    'cond-ae': (1, ('labels', 'labels_2d')),
+    'cond-vae': (1, ('labels', 'labels_2d')),
+}
+
+
+def get_reconstruction(model, inputs, dataset=None, return_latents=False, labels=None, labels_2d=None,
+                       apply_inverse_transform=True, use_mean=True):
+    """Reconstructed frames from frames (4-D input: full forward pass) or from latents (2-D input: decoder
+    only), as numpy arrays (reference eval.py:284-376).  Latent inputs of the label-structured models are first
+    mapped back to the encoder's basis (``get_inverse_transformed_latents``) unless ``apply_inverse_transform``
+    is off; conditional models get their labels appended."""
+    import torch
+    model.eval()
+    if not isinstance(inputs, torch.Tensor):
+        inputs = torch.Tensor(inputs).to(model.hparams['device'])
+    mc = model.hparams['model_class']
+    with torch.no_grad():
+        if inputs.dim() != 2:
+            if mc not in _FORWARD_LAYOUT:
+                raise ValueError('Invalid model class %s' % mc)
+            pos, extra = _FORWARD_LAYOUT[mc]
+            offered = {'use_mean': use_mean, 'labels': labels, 'labels_2d': labels_2d}
+            out = model(inputs, dataset=dataset, **{k: offered[k] for k in extra})
+            ims_recon, latents = out[0], out[pos]
+        else:
+            if mc in ('cond-ae', 'cond-vae'):
+                inputs = torch.cat((inputs, labels), dim=1)
+            elif mc in ('cond-ae-msp', 'ps-vae', 'msps-vae') and apply_inverse_transform:
+                inputs = model.get_inverse_transformed_latents(inputs, as_numpy=False)
+            ims_recon = model.decoding(inputs.contiguous(), None, None, dataset=None)
+            latents = inputs
+    ims_recon = ims_recon.cpu().detach().numpy()
+    latents = latents.cpu().detach().numpy()
+    return (ims_recon, latents) if return_latents else ims_recon

@@ -230,3 +230,52 @@ def test_export_states_and_latents_file_formats(tmp_path):
     out = export_states(hp, gen, Batched())
     assert out[0].endswith('version_0/l_e_a_s_states.pkl')
     gen.close()
+
+
+def test_get_reconstruction_dispatch_per_model_class():
+    """get_reconstruction (reference eval.py:284-376): which element of forward()'s tuple is the latent mean and
+    which keyword arguments each model class receives; latent inputs go through the decoder only."""
+    from behavenet_b200.fitting.eval import get_reconstruction
+
+    class Mock:
+        def __init__(self, mc, arity):
+            self.hparams = {'model_class': mc, 'device': 'cpu'}
+            self.arity, self.kwargs, self.decoded = arity, None, None
+
+        def eval(self):
+            return self
+
+        def __call__(self, x, dataset=None, **kw):
+            self.kwargs = kw
+            return tuple(torch.full((x.shape[0], 2), float(i)) if i else x * 0 + 7 for i in range(self.arity))
+
+        def decoding(self, z, pool_idx, outsize, dataset=None):
+            self.decoded = z
+            return torch.zeros(z.shape[0], 1, 4, 4)
+
+        def get_inverse_transformed_latents(self, z, as_numpy=True):
+            return z + 100
+
+    x = torch.rand(3, 1, 4, 4)
+    lab, lab2d = torch.ones(3, 2), torch.ones(3, 1, 4, 4)
+    for mc, arity, pos, keys in [('ae', 2, 1, set()), ('cond-ae-msp', 3, 1, set()), ('vae', 4, 1, {'use_mean'}),
+                                 ('beta-tcvae', 4, 1, {'use_mean'}), ('ps-vae', 5, 2, {'use_mean'}),
+                                 ('msps-vae', 5, 2, {'use_mean'}), ('cond-ae', 2, 1, {'labels', 'labels_2d'}),
+                                 ('cond-vae', 4, 1, {'labels', 'labels_2d'})]:
+        m = Mock(mc, arity)
+        ims, lat = get_reconstruction(m, x, return_latents=True, labels=lab, labels_2d=lab2d)
+        assert set(m.kwargs) == keys and np.all(ims == 7) and np.all(lat == pos), mc
+        assert isinstance(get_reconstruction(m, x.numpy()), np.ndarray)
+    with pytest.raises(ValueError):
+        get_reconstruction(Mock('nope', 2), x)
+    z = torch.zeros(3, 2)
+    m = Mock('ps-vae', 5)
+    _, lat = get_reconstruction(m, z, return_latents=True)
+    assert np.all(lat == 100) and torch.all(m.decoded == 100)
+    _, lat = get_reconstruction(m, z, return_latents=True, apply_inverse_transform=False)
+    assert np.all(lat == 0)
+    m = Mock('cond-ae', 2)
+    _, lat = get_reconstruction(m, z, return_latents=True, labels=lab)
+    assert lat.shape == (3, 4) and np.all(lat[:, 2:] == 1)
+    m = Mock('ae', 2)
+    assert get_reconstruction(m, z).shape == (3, 1, 4, 4) and torch.all(m.decoded == 0)

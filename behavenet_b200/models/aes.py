@@ -227,6 +227,17 @@ class AE(BaseModel):
                 o += p.numel()
             self._rt.bufs['flat_grad'] = flat
             self._rt.bufs['flat_grad_ptrs'] = [p.grad.data_ptr() for p in missing]
+            # the decoder's parameters form one contiguous bucket of the flat buffer (they are final after
+            # bn_cae_decode_bwd, before the encoder's backward pass starts)
+            dec = {id(p) for p in self.decoding.kernel_params() if p is not None}
+            o, lo, hi, cnt = 0, None, None, 0
+            for p in missing:
+                if id(p) in dec:
+                    lo = o if lo is None else lo
+                    hi = o + p.numel()
+                    cnt += p.numel()
+                o += p.numel()
+            self._rt.bufs['flat_grad_dec'] = (lo, hi) if lo is not None and hi - lo == cnt else None
         return [None if (p is None or not p.requires_grad) else p.grad for p in params]
 
     def _shard(self, n):
@@ -235,19 +246,50 @@ class AE(BaseModel):
             return 0, n
         return parallel.shard_range(n)
 
-    def _allreduce(self, params, extra):
-        """One NCCL all-reduce of the flat gradient (+ one of the loss partial sums)."""
+    def _flat_is_live(self, params):
         flat = self._rt.bufs.get('flat_grad')
         ptrs = self._rt.bufs.get('flat_grad_ptrs')
         everything = [p for p in params if p is not None] + self._extra_trainable()
         live = [p.grad.data_ptr() for p in everything if p.requires_grad]
-        if flat is not None and ptrs == live:
-            parallel.all_reduce_sum(flat)
+        return flat is not None and ptrs == live, everything
+
+    def _allreduce_begin(self, params, which='dec'):
+        """Start the all-reduce of the decoder-side gradient bucket as soon as the decoder's backward pass
+        is enqueued: the collective runs on the communication stream underneath the encoder's backward
+        kernels ("decoder-side buckets overlap with encoder backward").  Returns a
+        handle for ``_allreduce`` or None when the gradients are not views of the flat buffer."""
+        ok, _ = self._flat_is_live(params)
+        span = self._rt.bufs.get('flat_grad_dec')
+        if not ok or span is None or not parallel.overlap_enabled():
+            return None
+        flat = self._rt.bufs['flat_grad']
+        return (parallel.all_reduce_sum_async(flat[span[0]:span[1]]), span)
+
+    def _allreduce(self, params, extra, pending=None):
+        """All-reduce(SUM) of the flat gradient -- minus the bucket already in flight -- and of the loss
+        partial sums."""
+        ok, everything = self._flat_is_live(params)
+        if ok:
+            flat = self._rt.bufs['flat_grad']
+            if pending is not None:
+                lo, hi = pending[1]
+                if lo > 0:
+                    parallel.all_reduce_sum(flat[:lo])
+                if hi < flat.numel():
+                    parallel.all_reduce_sum(flat[hi:])
+            else:
+                parallel.all_reduce_sum(flat)
         else:
+            if pending is not None:
+                pending[0].wait()
+                pending = None
+                raise RuntimeError('gradient buffers changed between the bucketed all-reduce and its completion')
             for p in everything:
                 if p.requires_grad:
                     parallel.all_reduce_sum(p.grad)
         parallel.all_reduce_sum(extra)
+        if pending is not None:
+            pending[0].wait()
 
     def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200):
         """MSE loss (+ gradients) with the reference's chunk semantics (aes.py:722-773): the batch
@@ -279,6 +321,7 @@ class AE(BaseModel):
         params = self._kernel_params()
         device = x.device
         sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
+        pending = None
         if n > 0:
             xs = x if local else x[beg:end]
             ms = None if m is None else (m if local else m[beg:end])
@@ -292,12 +335,14 @@ class AE(BaseModel):
             if accumulate_grad:
                 grads = self._grad_table(params)
                 dz = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+                if self.data_parallel and parallel.enabled():
+                    pending = self._allreduce_begin(params)
                 drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
         elif accumulate_grad:
             self._grad_table(params)
         if self.data_parallel and parallel.enabled():
             if accumulate_grad:
-                self._allreduce(params, sse)
+                self._allreduce(params, sse, pending)
             else:
                 parallel.all_reduce_sum(sse)
         numel = float(np.prod(drv.img))
@@ -318,6 +363,9 @@ class _AutogradChunkedAE(AE):
         self.decoding._rt.packed_key = None
 
     def _chunk_loop(self, data, chunk_size, accumulate_grad, chunk_loss, keys):
+        if (self.data_parallel and parallel.enabled()) or 'shard' in data:
+            raise NotImplementedError('%s has no data-parallel path (no frame sharding, no gradient all-reduce); '
+                                      'run it with one process per model' % type(self).__name__)
         x = data['images'][0]
         n = x.shape[0]
         vals = {k: 0.0 for k in keys}

@@ -34,6 +34,40 @@ def reparameterize(mu, logvar, eps=None):
     return eps * torch.exp(logvar) + mu
 
 
+
+def _latent_rows(beg, end, n_total, chunks, pre, logvar, eps_s, call, dp):
+    """Run the per-chunk latent block for every reference chunk that holds frames of this rank's
+    contiguous range [beg, end) and return this rank's rows of (mu, z, gmu_part, glogvar_part, gz_part).
+
+    The MI / TC / DWKL estimators are pairwise over a whole chunk (reference losses.py:321-341), so a rank
+    whose frames end inside a chunk needs the other ranks' (FF output, logvar, eps) rows of that chunk:
+    with ``dp`` the (n_total, 3 L) table is assembled by one all-reduce(SUM) of zero-padded rows (an
+    all-gather that also works on ragged shards and on the gloo backend; 3 L floats per frame).  Every
+    rank that shares a chunk evaluates the (tiny) block on all of its rows and keeps its own; the loss
+    sums, label predictions and D gradients of a chunk are contributed by its owner only -- the rank
+    holding the chunk's first frame -- so the later all-reduce counts them once.
+    ``call(c, b, e, owner, pre, logvar, eps, mu, z, gmu, glv, gz)`` evaluates chunk c = frames [b, e) on
+    full-batch-indexed tensors."""
+    L = pre.shape[1]
+    dev = pre.device
+    if dp:
+        full = torch.zeros(n_total, 3 * L, dtype=torch.float32, device=dev)
+        full[beg:end, :L] = pre
+        full[beg:end, L:2 * L] = logvar
+        full[beg:end, 2 * L:] = eps_s
+        parallel.all_reduce_sum(full)
+        pre_f, lv_f, eps_f = (full[:, i * L:(i + 1) * L].contiguous() for i in range(3))
+    else:
+        assert beg == 0 and end == n_total
+        pre_f, lv_f, eps_f = pre, logvar, eps_s
+    out = [torch.zeros(n_total, L, dtype=torch.float32, device=dev) for _ in range(5)]
+    for c, (b, e) in enumerate(chunks):
+        if e <= beg or b >= end:
+            continue
+        call(c, b, e, beg <= b < end, pre_f, lv_f, eps_f, *out)
+    return [o[beg:end] for o in out]
+
+
 class _LatentFn(torch.autograd.Function):
     """Differentiable PS-VAE latent block outside ``loss`` (forward / plotting helpers):
     (pre, logvar, A, B, Dw, Db, eps) -> (mu, z, y_hat).  Backward chains through the same C call
@@ -172,18 +206,17 @@ class VAE(AE):
         L = self.hparams['n_ae_latents']
         nl, alpha, beta, kl, kls = self._latent_weights()
         device = x.device
-        if self.data_parallel and parallel.enabled():
-            cb, ce = parallel.shard_range(n_chunks)      # whole chunks: the estimators are per chunk
-            my_chunks = list(range(cb, ce))
-        else:
-            my_chunks = list(range(n_chunks))
-        beg = chunks[my_chunks[0]][0] if my_chunks else 0
-        end = chunks[my_chunks[-1]][1] if my_chunks else 0
+        if 'shard' in data:
+            raise NotImplementedError("data['shard'] (rank-local staging) is only supported by AE.loss; the VAE "
+                                      'family shards the full batch itself when model.data_parallel is set')
+        dp = self.data_parallel and parallel.enabled()
+        beg, end = parallel.shard_range(n_total) if dp else (0, n_total)      # contiguous frames per rank
         n = end - beg
         params = self._kernel_params()
         sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
         terms = torch.zeros(n_chunks, 5, dtype=torch.float64, device=device)
         lib = _lib.lib()
+        pending = None
         if n > 0:
             xs = x[beg:end]
             ms = None if m is None else m[beg:end]
@@ -195,30 +228,33 @@ class VAE(AE):
             packed = drv.packed(rt, params, device)
             ws = drv.workspace(rt, n, device)
             pre, logvar = drv.encode(xs, params, packed, ws, True)
-            mu = torch.empty(n, L, device=device)
-            z = torch.empty(n, L, device=device)
-            gmu_p = torch.empty(n, L, device=device)
-            glv_p = torch.empty(n, L, device=device)
-            gz_p = torch.zeros(n, L, device=device)
-            yhat = torch.empty(max(n * nl, 1), device=device)
-            grads = self._grad_table(params) if accumulate_grad else None
+        else:
+            pre = logvar = eps_s = torch.zeros(0, L, dtype=torch.float32, device=device)
+        if n > 0 or dp:
+            eye, ones, zeros = self._identity(device)
+            yhat = torch.empty(max(chunk_size * nl, 1), device=device)
+            scratch = torch.zeros(5, dtype=torch.float64, device=device)
             lws = torch.empty(lib.bn_psvae_latent_workspace_bytes(chunk_size, L), dtype=torch.uint8, device=device)
             A = eye.data_ptr() if nl > 0 else None
             B = eye.data_ptr() if nl < L else None
-            for c in my_chunks:
-                b, e = chunks[c][0] - beg, chunks[c][1] - beg
+
+            def call(c, b, e, owner, pre_f, lv_f, eps_f, mu_f, z_f, gmu_f, glv_f, gz_f):
                 sl = slice(b, e)
                 _lib.check(lib.bn_psvae_latent(
-                    e - b, L, nl, pre[sl].data_ptr(), logvar[sl].data_ptr(), A, B,
+                    e - b, L, nl, pre_f[sl].data_ptr(), lv_f[sl].data_ptr(), A, B,
                     ones.data_ptr() if nl > 0 else None, zeros.data_ptr() if nl > 0 else None,
-                    eps_s[sl].data_ptr(), None, None, float(alpha), float(beta), float(kl), float(kls),
-                    lws.data_ptr(), mu[sl].data_ptr(), z[sl].data_ptr(), yhat.data_ptr() if nl > 0 else None,
-                    terms[c].data_ptr(), gmu_p[sl].data_ptr(), glv_p[sl].data_ptr(), gz_p[sl].data_ptr(),
-                    None, None, _lib.stream_ptr()), 'bn_psvae_latent')
+                    eps_f[sl].data_ptr(), None, None, float(alpha), float(beta), float(kl), float(kls),
+                    lws.data_ptr(), mu_f[sl].data_ptr(), z_f[sl].data_ptr(), yhat.data_ptr() if nl > 0 else None,
+                    (terms[c] if owner else scratch).data_ptr(), gmu_f[sl].data_ptr(), glv_f[sl].data_ptr(),
+                    gz_f[sl].data_ptr(), None, None, _lib.stream_ptr()), 'bn_psvae_latent')
+            mu, z, gmu_p, glv_p, gz_p = _latent_rows(beg, end, n_total, chunks, pre, logvar, eps_s, call, dp)
+        if n > 0:
+            grads = self._grad_table(params) if accumulate_grad else None
             drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms, chunk_size=chunk_size,
                        frame_offset=beg, n_total=n_total, grad_coef=1.0, sse=sse)
             if accumulate_grad:
                 gz_dec = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+                pending = self._allreduce_begin(params, 'dec') if dp else None
                 gpre = torch.empty(n, L, device=device)
                 glv = torch.empty(n, L, device=device)
                 _lib.check(lib.bn_psvae_latent_bwd(
@@ -229,9 +265,9 @@ class VAE(AE):
         elif accumulate_grad:
             self._grad_table(params)
         stats = torch.cat([sse[:, None], terms], 1)
-        if self.data_parallel and parallel.enabled():
+        if dp:
             if accumulate_grad:
-                self._allreduce(params, stats)
+                self._allreduce(params, stats, pending)
             else:
                 parallel.all_reduce_sum(stats)
         return stats.cpu().numpy(), chunks        # the one device->host read of the call
@@ -436,14 +472,13 @@ class PSVAE(AE):
         beta = self.beta_vals[self.curr_epoch]
         kl = self.kl_anneal_vals[self.curr_epoch]
         device = x.device
-        if self.data_parallel and parallel.enabled():
-            # whole chunks per rank: the pairwise estimators need a chunk's frames together
-            cb, ce = parallel.shard_range(n_chunks)
-            my_chunks = list(range(cb, ce))
-        else:
-            my_chunks = list(range(n_chunks))
-        beg = chunks[my_chunks[0]][0] if my_chunks else 0
-        end = chunks[my_chunks[-1]][1] if my_chunks else 0
+        if 'shard' in data:
+            raise NotImplementedError("data['shard'] (rank-local staging) is only supported by AE.loss; PSVAE "
+                                      'shards the full batch itself when model.data_parallel is set')
+        dp = self.data_parallel and parallel.enabled()
+        # contiguous frames per rank, balanced by frames; chunks that span ranks exchange their
+        # (FF output, logvar, eps) rows (reference losses.py:321-341)
+        beg, end = parallel.shard_range(n_total) if dp else (0, n_total)
         n = end - beg
         params = self._kernel_params()
         # per chunk: [sse_pixels] ; [label sumsq, zs_kl, mi, tc, dwkl]
@@ -451,6 +486,7 @@ class PSVAE(AE):
         terms = torch.zeros(n_chunks, 5, dtype=torch.float64, device=device)
         y_hat_all = torch.zeros(n_total, nl, dtype=torch.float32, device=device)
         lib = _lib.lib()
+        pending = None
         if n > 0:
             xs = x[beg:end]
             ms = None if m is None else m[beg:end]
@@ -461,35 +497,39 @@ class PSVAE(AE):
             packed = drv.packed(rt, params, device)
             ws = drv.workspace(rt, n, device)
             pre, logvar = drv.encode(xs, params, packed, ws, True)
-            mu = torch.empty(n, L, device=device)
-            z = torch.empty(n, L, device=device)
-            gmu_p = torch.empty(n, L, device=device)
-            glv_p = torch.empty(n, L, device=device)
-            gz_p = torch.empty(n, L, device=device)
+        else:
+            pre = logvar = eps_s = torch.zeros(0, L, dtype=torch.float32, device=device)
+        grads = self._grad_table(params) if accumulate_grad else None
+        if n > 0 or dp:
             D = enc.D
-            grads = self._grad_table(params) if accumulate_grad else None
+            scratch = torch.zeros(5, dtype=torch.float64, device=device)
+            yhat_scratch = torch.empty(chunk_size, nl, dtype=torch.float32, device=device)
             lws = torch.empty(lib.bn_psvae_latent_workspace_bytes(chunk_size, L), dtype=torch.uint8,
                               device=device)
-            for c in my_chunks:
-                b, e = chunks[c][0] - beg, chunks[c][1] - beg
+
+            def call(c, b, e, owner, pre_f, lv_f, eps_f, mu_f, z_f, gmu_f, glv_f, gz_f):
                 sl = slice(b, e)
+                own_grad = owner and accumulate_grad
                 _lib.check(lib.bn_psvae_latent(
-                    e - b, L, nl, pre[sl].data_ptr(), logvar[sl].data_ptr(), enc.A.weight.data_ptr(),
+                    e - b, L, nl, pre_f[sl].data_ptr(), lv_f[sl].data_ptr(), enc.A.weight.data_ptr(),
                     _lib.ptr(enc.B.weight) if L > nl else None, D.weight.data_ptr(), D.bias.data_ptr(),
-                    eps_s[sl].data_ptr(), y[beg + b:beg + e].data_ptr(),
-                    None if nm is None else nm[beg + b:beg + e].data_ptr(),
-                    float(alpha), float(beta), float(kl), 1.0, lws.data_ptr(), mu[sl].data_ptr(),
-                    z[sl].data_ptr(), y_hat_all[beg + b:beg + e].data_ptr(), terms[c].data_ptr(),
-                    gmu_p[sl].data_ptr(), glv_p[sl].data_ptr(), gz_p[sl].data_ptr(),
-                    D.weight.grad.data_ptr() if accumulate_grad and D.weight.requires_grad else None,
-                    D.bias.grad.data_ptr() if accumulate_grad and D.bias.requires_grad else None,
+                    eps_f[sl].data_ptr(), y[sl].data_ptr(), None if nm is None else nm[sl].data_ptr(),
+                    float(alpha), float(beta), float(kl), 1.0, lws.data_ptr(), mu_f[sl].data_ptr(),
+                    z_f[sl].data_ptr(), (y_hat_all[sl] if owner else yhat_scratch).data_ptr(),
+                    (terms[c] if owner else scratch).data_ptr(),
+                    gmu_f[sl].data_ptr(), glv_f[sl].data_ptr(), gz_f[sl].data_ptr(),
+                    D.weight.grad.data_ptr() if own_grad and D.weight.requires_grad else None,
+                    D.bias.grad.data_ptr() if own_grad and D.bias.requires_grad else None,
                     _lib.stream_ptr()), 'bn_psvae_latent')
+            mu, z, gmu_p, glv_p, gz_p = _latent_rows(beg, end, n_total, chunks, pre, logvar, eps_s, call, dp)
+        if n > 0:
             # pixel log-likelihood fused in the decoder epilogue: d(-ll)/dxhat = (xhat - x) m / len
             drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms,
                        chunk_size=chunk_size, frame_offset=beg, n_total=n_total, grad_coef=1.0,
                        sse=sse)
             if accumulate_grad:
                 gz_dec = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+                pending = self._allreduce_begin(params, 'dec') if dp else None
                 gpre = torch.empty(n, L, device=device)
                 glv = torch.empty(n, L, device=device)
                 _lib.check(lib.bn_psvae_latent_bwd(
@@ -498,12 +538,10 @@ class PSVAE(AE):
                     glv_p.data_ptr(), gz_p.data_ptr(), gpre.data_ptr(), glv.data_ptr(),
                     _lib.stream_ptr()), 'bn_psvae_latent_bwd')
                 drv.encode_bwd(xs, gpre, glv, params, packed, ws, grads)
-        elif accumulate_grad:
-            self._grad_table(params)
-        if self.data_parallel and parallel.enabled():
+        if dp:
             stats = torch.cat([sse[:, None], terms], 1)
             if accumulate_grad:
-                self._allreduce(params, stats)
+                self._allreduce(params, stats, pending)
             else:
                 parallel.all_reduce_sum(stats)
             parallel.all_reduce_sum(y_hat_all)

@@ -68,6 +68,19 @@ def all_reduce_sum(t):
     return t
 
 
+def all_reduce_sum_async(t):
+    """Start an all-reduce(SUM) and return its work handle (``.wait()`` orders the current stream after
+    it).  With NCCL the collective runs on the communicator's own stream, after the work already enqueued
+    on the current stream and concurrently with whatever is enqueued next."""
+    import torch.distributed as dist
+    return dist.all_reduce(t, group=_STATE['group'], async_op=True)
+
+
+def overlap_enabled():
+    """BN_DP_OVERLAP=0 issues the whole gradient as one all-reduce after the backward pass (A/B switch)."""
+    return _STATE['enabled'] and os.environ.get('BN_DP_OVERLAP', '1') != '0'
+
+
 def shutdown():
     import torch.distributed as dist
     if _STATE['enabled'] and dist.is_initialized():

@@ -399,7 +399,7 @@ def run_ours(args):
 
     if rank != 0:
         return
-    cpu = cpu_baselines(hp) if world == 1 else None
+    cpu = cpu_baselines() if world == 1 else None
     hbm_achieved = hmm_value / world * ARHMM_BYTES_PER_TIMESTEP / 1e9
     line = {
         'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
@@ -514,86 +514,151 @@ def bench_psvae(device, world, rank, args):
                     'reference loss() does; frames resident in HBM'}
 
 
-def cpu_cae_step(hp, batch, threads):
-    from oracle import cae_oracle as co
-    torch.set_num_threads(threads)
-    sd = co.init_state_dict(hp, seed=0)
-    x = torch.rand(batch, 1, 128, 128, generator=torch.Generator().manual_seed(0))
-    co.ae_loss(sd, hp, x[:32])                 # warm-up
-    t0 = time.perf_counter()
-    co.ae_loss(sd, hp, x)
-    return time.perf_counter() - t0
+def import_reference():
+    """The UNMODIFIED reference package from baseline/_ref (installed by baseline/install_ref.sh; git-ignored,
+    travels with gpurun).  ``commentjson`` -- imported at the top of ae_model_architecture_generator.py
+    but only used to read arch json files -- is absent from this image and is stubbed.  Returns the
+    ``behavenet.models`` module or None when the install is missing."""
+    import types
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'behavenet', 'models')):
+        return None
+    sys.modules.setdefault('commentjson', types.ModuleType('commentjson'))
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import behavenet.models as ref_models
+    return ref_models
 
 
-def cpu_baselines(hp):
-    """Oracle port of the reference paths on this box's host cores (bounded samples)."""
-    from oracle import arhmm_oracle as ao
-    cores = os.cpu_count() or 1
-    dt = cpu_cae_step(hp, 256, cores)
-    cae = {'value': 256 / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-           'sample': 'one AE.loss-equivalent step (oracle/cae_oracle.ae_loss, torch eager fp32, '
-                     'chunks 200+56) on the full 256-frame batch, after a 32-frame warm-up'}
-    p = ao.synth_params(ARHMM_K, ARHMM_D, ARHMM_LAGS, seed=0)
-    X = ao.sample_batch(p, 16, ARHMM_T, seed=0)
-    ao.e_step(p, [X[0]])                        # numba compile
-    t0 = time.perf_counter()
-    ao.e_step(p, [X[i] for i in range(16)])
-    dt = time.perf_counter() - t0
-    hm = {'value': 16 * ARHMM_T / dt, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
-          'sample': '16 of the 2048 trials x 1000 steps, oracle/arhmm_oracle.e_step (numpy emissions '
-                    '+ numba fp64 log-space messages, python loop over trials = ssm execution model)'}
-    return {'cae': cae, 'arhmm': hm}
-
-
-def run_reference(args):
-    """Reference arm: the reference's own CPU path (oracle port; the reference is pure Python /
-    PyTorch eager and /root/reference does not exist on the GPU box).  Rank 0 only."""
-    if int(os.environ.get('RANK', '0')) != 0:
-        return
+def reference_ae(device):
+    """behavenet.models.AE (reference aes.py:616-773) with the seeded parameters of the GPU arm."""
     import copy
-    from oracle import cae_oracle as co
-    cores = os.cpu_count() or 1
+    from oracle import cae_oracle as co          # seeded synthetic parameters only
+    ref_models = import_reference()
+    if ref_models is None:
+        return None, None
     hp = co.make_hparams(1, 128, 128, 12)
-    sample = 64            # frames per step: bounded sample of the 256-frame batch
-    torch.set_num_threads(cores)
-    sd = co.init_state_dict(hp, seed=0)
-    x = torch.rand(sample, 1, 128, 128, generator=torch.Generator().manual_seed(0))
-    for _ in range(args.warmup):
-        co.ae_loss(sd, hp, x)
-    steps = args.steps
+    hp_ref = copy.deepcopy(hp)
+    hp_ref['device'] = str(device)
+    model = ref_models.AE(hp_ref)
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.to(device)
+    return model, hp
+
+
+def cpu_cae_rate(batch, steps, warmup, threads):
+    """frames/s of the reference's own AE.loss(data, accumulate_grad=True) on the host cores (the oracle
+    port when baseline/_ref is missing) -> (frames/s, seconds per step, kind)."""
+    torch.set_num_threads(threads)
+    x = torch.rand(batch, 1, 128, 128, generator=torch.Generator().manual_seed(0))
+    model, hp = reference_ae('cpu')
+    if model is not None:
+        kind = 'reference'
+
+        def step():
+            model.zero_grad()
+            model.loss({'images': x[None]}, accumulate_grad=True)
+    else:
+        from oracle import cae_oracle as co
+        kind = 'port'
+        hp = co.make_hparams(1, 128, 128, 12)
+        sd = co.init_state_dict(hp, seed=0)
+
+        def step():
+            co.ae_loss(sd, hp, x)
+    for _ in range(warmup):
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        co.ae_loss(sd, hp, x)
+        step()
     dt = (time.perf_counter() - t0) / steps
-    value = sample / dt
-    # ARHMM E-step of the same reference arm: ssm's execution model (python loop over trials, fp64)
+    return batch / dt, dt, kind
+
+
+CPU_SAMPLE = {'reference': 'behavenet.models.AE.loss(accumulate_grad=True) of the unmodified reference (baseline/_ref, '
+                           'PyTorch eager fp32, all host threads) on the full 256-frame batch (chunks 200+56)',
+              'port': 'oracle/cae_oracle.ae_loss (torch eager fp32, all host threads; baseline/_ref not installed) on '
+                      'the full 256-frame batch (chunks 200+56)'}
+
+
+def cpu_arhmm_rate(reps):
     from oracle import arhmm_oracle as ao
     p = ao.synth_params(ARHMM_K, ARHMM_D, ARHMM_LAGS, seed=0)
     X = ao.sample_batch(p, 16, ARHMM_T, seed=0)
     ao.e_step(p, [X[0]])                        # numba compile
-    reps = max(1, min(steps, 5))
     t0 = time.perf_counter()
     for _ in range(reps):
         ao.e_step(p, [X[i] for i in range(16)])
-    hdt = (time.perf_counter() - t0) / reps
-    hvalue = 16 * ARHMM_T / hdt
+    dt = (time.perf_counter() - t0) / reps
+    return 16 * ARHMM_T / dt, dt
+
+
+ARHMM_CPU_SAMPLE = ('16 of the 2048 trials x 1000 steps, oracle/arhmm_oracle.e_step (numpy emissions + numba fp64 '
+                    'log-space messages, python loop over trials = ssm execution model; ssm itself is not installable)')
+
+
+def cpu_baselines():
+    """The reference paths on this box's host cores (bounded samples), rank 0 at N = 1."""
+    cores = os.cpu_count() or 1
+    v, dt, kind = cpu_cae_rate(CAE_BATCH_PER_GPU, 3, 1, cores)
+    cae = {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+           'sample': '3 steps after 1 warm-up: ' + CPU_SAMPLE[kind]}
+    hv, _ = cpu_arhmm_rate(1)
+    hm = {'value': hv, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port', 'sample': ARHMM_CPU_SAMPLE}
+    return {'cae': cae, 'arhmm': hm}
+
+
+def reference_eager_b200(device):
+    """Informational: the unmodified reference classes executed by eager PyTorch + cuDNN on this B200 (what
+    the reference itself does on a GPU; SURVEY.md section 2.1 calls it "the bar to beat"), same batch,
+    same metric, TF32 convolutions on (torch's default) and off."""
+    model, _ = reference_ae(device)
+    if model is None:
+        return {'unavailable': 'baseline/_ref not installed'}
+    x = torch.rand(CAE_BATCH_PER_GPU, 1, 128, 128, generator=torch.Generator().manual_seed(0)).to(device)
+    out = {}
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        for tag, flag in (('tf32', True), ('fp32', False)):
+            torch.backends.cudnn.allow_tf32 = flag
+
+            def step():
+                model.zero_grad()
+                model.loss({'images': x[None]}, accumulate_grad=True)
+            ms = timed(step, 10, 3)
+            out[tag] = {'frames_per_s': CAE_BATCH_PER_GPU / (float(np.median(ms)) * 1e-3), 'ms_per_step': float(np.median(ms))}
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    out['note'] = ('behavenet.models.AE.loss from baseline/_ref on cuda, eager PyTorch %s + cuDNN, 256 frames resident '
+                   'in HBM, median of 10 steps after 3 warm-ups (CUDA events)' % torch.__version__)
+    return out
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path -- behavenet.models.AE.loss from
+    baseline/_ref, eager PyTorch on all host threads -- on the GPU arm's config (full 256-frame batch,
+    chunks 200 + 56), K timed steps after W warm-ups.  Rank 0 only; other ranks exit without work."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    cores = os.cpu_count() or 1
+    value, dt, kind = cpu_cae_rate(CAE_BATCH_PER_GPU, args.steps, args.warmup, cores)
+    hvalue, hdt = cpu_arhmm_rate(max(1, min(args.steps, 3)))
     _OUT.write(json.dumps({
         'impl': 'reference',
         'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
-        'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': steps,
+        'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'C2: CAE 128x128x1, 12 latents, AE.loss fwd+bwd, default 5-layer arch; '
-                               'bounded sample of %d frames per step' % sample},
-        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                         'sample': '%d-frame steps of oracle/cae_oracle.ae_loss (torch eager fp32, all host '
-                                   'threads)' % sample},
+        'config': {'workload': 'C2: CAE 128x128x1, 12 latents, batch=256 per GPU, AE.loss fwd+bwd, '
+                               'default 5-layer arch', 'global_batch': CAE_BATCH_PER_GPU,
+                   'parallelism': 'host cores (one process)'},
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                         'sample': '%d steps after %d warm-ups: %s' % (args.steps, args.warmup, CPU_SAMPLE[kind])},
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'arhmm': {'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12)', 'value': hvalue,
                   'unit': 'timesteps/s', 'ms_per_step': hdt * 1e3, 'dtype': 'f64',
                   'cpu_baseline': {'value': hvalue, 'unit': 'timesteps/s', 'cores': 1, 'kind': 'port',
-                                   'sample': '16 of the 2048 trials x 1000 steps per step, '
-                                             'oracle/arhmm_oracle.e_step'},
+                                   'sample': ARHMM_CPU_SAMPLE},
                   'e2e': {'value': hvalue, 'unit': 'timesteps/s', 'h2d_bytes_per_step': 0,
                           'd2h_bytes_per_step': 0}},
     }) + '\n')

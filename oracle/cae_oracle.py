@@ -88,6 +88,89 @@ def n_conv_layers(hparams):
     return len(hparams['ae_encoding_n_channels'])
 
 
+# ---- optional emulation of the TF32 tensor-core arithmetic of the benchmarked path ----------------
+# The product's default compute mode multiplies TF32 operands with fp32 accumulation in the fat conv
+# layers: weights are rounded to TF32 once (cvt.rna: nearest, ties away from zero) when they are packed
+# into GEMM order; activations / upstream gradients are consumed as stored, the tensor core reading
+# only the top 19 bits (truncation).  Under ``tf32_emulation()`` the conv / transposed-conv calls below
+# reproduce exactly that operand rounding in the forward, backward-data and weight-gradient products
+# (everything else -- biases, activations, FF layers, accumulation -- stays fp32/fp64), so the
+# tensor-core path can be pinned to round-off tolerances instead of to the 1e-2-level distance between
+# TF32 and fp32 arithmetic.  The first encoder layer's weight gradient and the last decoder layer's
+# forward + weight gradient run on fp32 CUDA-core kernels in the product and stay exact here
+# (behavenet_b200/csrc/cae_thin.cu).
+_EMU = {'on': False, 'act': 'trunc'}
+
+
+class tf32_emulation:
+    def __init__(self, act='trunc'):
+        self.act = act
+
+    def __enter__(self):
+        self.prev = dict(_EMU)
+        _EMU.update(on=True, act=self.act)
+
+    def __exit__(self, *exc):
+        _EMU.update(self.prev)
+
+
+def tf32_rna(t):
+    """cvt.rna.tf32.f32: round to 10 mantissa bits, nearest, ties away from zero."""
+    f = t.detach().to(torch.float32).contiguous()
+    b = f.view(torch.int32)
+    b = (b + 0x1000) & ~0x1FFF
+    return b.view(torch.float32).to(t.dtype)
+
+
+def tf32_trunc(t):
+    """What the tensor core reads of an fp32 operand: the low 13 mantissa bits are ignored."""
+    f = t.detach().to(torch.float32).contiguous()
+    return (f.view(torch.int32) & ~0x1FFF).view(torch.float32).to(t.dtype)
+
+
+def _q_act(t):
+    return tf32_trunc(t) if _EMU['act'] == 'trunc' else tf32_rna(t)
+
+
+class _EmuConv(torch.autograd.Function):
+    """conv2d / conv_transpose2d (stride s, no padding) with TF32 operand rounding per product."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, s, transposed, q_fwd, q_dgrad, q_wgrad):
+        op = F.conv_transpose2d if transposed else F.conv2d
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (s, transposed, q_dgrad, q_wgrad)
+        xin, win = (_q_act(x), tf32_rna(w)) if q_fwd else (x.detach(), w.detach())
+        return op(xin, win, b.detach(), stride=s)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        s, transposed, q_dgrad, q_wgrad = ctx.cfg
+        op = F.conv_transpose2d if transposed else F.conv2d
+        dx = dw = None
+        with torch.enable_grad():
+            if ctx.needs_input_grad[0]:
+                xin = x.detach().requires_grad_(True)
+                y = op(xin, tf32_rna(w) if q_dgrad else w.detach(), None, stride=s)
+                dx, = torch.autograd.grad(y, xin, _q_act(dy) if q_dgrad else dy)
+            if ctx.needs_input_grad[1]:
+                win = w.detach().requires_grad_(True)
+                y = op(_q_act(x) if q_wgrad else x.detach(), win, None, stride=s)
+                dw, = torch.autograd.grad(y, win, _q_act(dy) if q_wgrad else dy)
+        db = dy.sum((0, 2, 3)) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None, None, None, None
+
+
+def _conv(x, w, b, s, layer, n_layers, transposed):
+    if not _EMU['on']:
+        return (F.conv_transpose2d if transposed else F.conv2d)(x, w, b, stride=s)
+    if transposed:      # last decoder layer: fp32 forward and weight gradient, TF32 backward-data
+        last = layer == n_layers - 1
+        return _EmuConv.apply(x, w, b, s, True, not last, True, not last)
+    return _EmuConv.apply(x, w, b, s, False, True, True, layer > 0)
+
+
 def encoder_features(sd, hparams, x, prefix='encoding.'):
     """Conv stack of ConvAEEncoder.forward (aes.py:181-214); returns flattened (N, C*H*W)."""
     for i in range(n_conv_layers(hparams)):
@@ -97,8 +180,8 @@ def encoder_features(sd, hparams, x, prefix='encoding.'):
         # symmetric: Conv2d(padding=(y0,x0)); asymmetric: ZeroPad2d((x0,x1,y0,y1)) + padding 0
         # (aes.py:141-155) -- numerically the same explicit zero pad
         x = F.pad(x, (x0, x1, y0, y1))
-        x = F.conv2d(x, sd[prefix + 'encoder.conv%i.weight' % i],
-                     sd[prefix + 'encoder.conv%i.bias' % i], stride=s)
+        x = _conv(x, sd[prefix + 'encoder.conv%i.weight' % i], sd[prefix + 'encoder.conv%i.bias' % i], s, i,
+                  n_conv_layers(hparams), False)
         x = F.leaky_relu(x, LEAK)
     return x.reshape(x.shape[0], -1)
 
@@ -123,8 +206,8 @@ def decode(sd, hparams, z, prefix='decoding.'):
         s = hparams['ae_decoding_stride_size'][i]
         # symmetric pads go in as ConvTranspose2d(padding=...), asymmetric as a crop afterwards
         # (aes.py:404-418, 467-470): both are "full transposed conv, then crop"
-        x = F.conv_transpose2d(x, sd[prefix + 'decoder.convtranspose%i.weight' % i],
-                               sd[prefix + 'decoder.convtranspose%i.bias' % i], stride=s)
+        x = _conv(x, sd[prefix + 'decoder.convtranspose%i.weight' % i],
+                  sd[prefix + 'decoder.convtranspose%i.bias' % i], s, i, n, True)
         x = x[:, :, y0:x.shape[2] - y1, x0:x.shape[3] - x1]
         x = torch.sigmoid(x) if i == n - 1 else F.leaky_relu(x, LEAK)
     return x

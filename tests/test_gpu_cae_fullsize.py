@@ -1,0 +1,220 @@
+"""Parity of the BENCHMARKED configurations at their full sizes (BASELINE.json configs 2 and 3) and of
+the data-parallel sharding, through the public model API (-> C ABI).
+
+* C2: AE 128x128x1, 12 latents, B = 256 (reference chunks 200 + 56, aes.py:751-769)
+* C3: PS-VAE 128x128x2, 16 latents, 4 labels, B = 512 (chunks 200 / 200 / 112, vaes.py:655-699)
+
+Mode 0 (fp32 CUDA-core kernels) is held to round-off against the fp32 CPU oracle.  Mode 1 (the
+default, benchmarked TF32 tensor-core path) is held to round-off against the TF32-EMULATING oracle
+(``cae_oracle.tf32_emulation``: identical operand rounding per product, fp32 accumulation), which is
+what catches a dropped tap or a mis-weighted chunk at this size -- and, per parameter, to ~2x the
+measured TF32-vs-fp32 distance (profiles/r02_parity.txt, scripts/diag_parity.py).
+"""
+
+import copy
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cae_oracle as co
+from tests.helpers import rel_err, ROOT
+
+pytestmark = pytest.mark.gpu
+
+# max|g - g_ref| / max|g_ref| bounds.  fp32 path and emulated-TF32 comparison: accumulation order only.
+BOUND_FP32 = 1e-4
+BOUND_EMU = 5e-3
+# TF32 path vs the fp32 oracle, per parameter group: ~2x the values measured on B200 for these two
+# configurations (profiles/r02_parity.txt); the distance is the conditioning of the random-init
+# network's gradient under 10-bit operands -- eager PyTorch/cuDNN-TF32 shows the same (profiles/r01_precision.txt)
+BOUND_TF32 = [
+    ('encoding.encoder.conv4', 2.0e-1),
+    ('encoding.encoder', 1.2e-1),
+    ('encoding.', 5e-2),                       # FF / logvar heads, D
+    ('decoding.FF', 5e-2),
+    ('decoding.decoder.convtranspose0', 1.2e-1),
+    ('decoding.decoder.convtranspose1', 6e-2),
+    ('decoding.decoder.convtranspose2', 3e-2),
+    ('decoding.decoder.convtranspose3', 1e-2),
+    ('decoding.decoder.convtranspose4', 2e-3),
+]
+
+
+def tf32_bound(name):
+    for prefix, b in BOUND_TF32:
+        if name.startswith(prefix):
+            return b
+    raise KeyError(name)
+
+
+def _model(cls, hp, sd, mode):
+    from behavenet_b200 import _lib
+    model = cls(copy.deepcopy(hp))
+    model.load_state_dict(sd)
+    model.cuda()
+    model.curr_epoch = 1
+    _lib.lib().bn_set_tensor_core_mode(mode)
+    return model
+
+
+@pytest.fixture(scope='module')
+def c2():
+    hp = co.make_hparams(1, 128, 128, 12)
+    sd = co.init_state_dict(hp, seed=1)
+    x = torch.rand(256, 1, 128, 128, generator=torch.Generator().manual_seed(5))
+    l32, g32 = co.ae_loss(sd, hp, x, None, chunk_size=200)
+    with co.tf32_emulation():
+        lt, gt = co.ae_loss(sd, hp, x, None, chunk_size=200)
+    xo, zo = co.ae_forward(sd, hp, x[:8])
+    return dict(hp=hp, sd=sd, x=x, l32=l32, g32=g32, lt=lt, gt=gt, xo=xo, zo=zo)
+
+
+@pytest.fixture(scope='module')
+def c3():
+    hp = co.make_hparams(2, 128, 128, 16, 'ps-vae', 4)
+    sd = co.init_state_dict(hp, seed=1)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(512, 2, 128, 128, generator=g)
+    y = torch.randn(512, 4, generator=g)
+    eps = torch.randn(512, 16, generator=g)
+    l32, g32 = co.psvae_loss(sd, hp, x, y, eps, chunk_size=200)
+    with co.tf32_emulation():
+        lt, gt = co.psvae_loss(sd, hp, x, y, eps, chunk_size=200)
+    return dict(hp=hp, sd=sd, x=x, y=y, eps=eps, l32=l32, g32=g32, lt=lt, gt=gt)
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_c2_b256_loss_and_gradients(c2, mode):
+    """BASELINE config 2 at the benchmarked batch (two reference chunks, 200 + 56 frames)."""
+    from behavenet_b200.models import AE
+    model = _model(AE, c2['hp'], c2['sd'], mode)
+    x = c2['x'].cuda()
+    with torch.no_grad():
+        xh, z = model(x[:8])
+    assert rel_err(xh, c2['xo']) < 1e-4                       # north_star: reconstructions within 1e-4
+    assert rel_err(z, c2['zo']) < (2e-5 if mode == 0 else 4e-3)
+    out = model.loss({'images': x[None]})
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    if mode == 0:
+        assert abs(out['loss'] - c2['l32']['loss']) <= 1e-5 * c2['l32']['loss']
+        for k, g in grads.items():
+            assert rel_err(g, c2['g32'][k]) < BOUND_FP32, k
+    else:
+        assert abs(out['loss'] - c2['lt']['loss']) <= 1e-5 * c2['lt']['loss']
+        assert abs(out['loss'] - c2['l32']['loss']) <= 1e-4 * c2['l32']['loss']
+        for k, g in grads.items():
+            assert rel_err(g, c2['gt'][k]) < BOUND_EMU, ('tf32-emulating oracle', k)
+            assert rel_err(g, c2['g32'][k]) < tf32_bound(k), ('fp32 oracle', k)
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_c3_b512_loss_dict_and_gradients(c3, mode):
+    """BASELINE config 3 at the benchmarked batch (three reference chunks, 200 / 200 / 112)."""
+    from behavenet_b200.models import PSVAE
+    model = _model(PSVAE, c3['hp'], c3['sd'], mode)
+    out = model.loss({'images': c3['x'].cuda()[None], 'labels': c3['y'].cuda()[None]}, eps=c3['eps'].cuda())
+    ref = c3['l32'] if mode == 0 else c3['lt']
+    for k in ['loss', 'loss_data_ll', 'loss_label_ll', 'loss_zs_kl', 'loss_zu_mi', 'loss_zu_tc', 'loss_zu_dwkl',
+              'loss_data_mse']:
+        assert abs(out[k] - ref[k]) <= 2e-5 * max(1.0, abs(ref[k])), (k, out[k], ref[k])
+    for k, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        if mode == 0:
+            assert rel_err(p.grad, c3['g32'][k]) < 4 * BOUND_FP32, k
+        else:
+            assert rel_err(p.grad, c3['gt'][k]) < BOUND_EMU, ('tf32-emulating oracle', k)
+            assert rel_err(p.grad, c3['g32'][k]) < tf32_bound(k), ('fp32 oracle', k)
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_ae_frame_shards_sum_to_the_unsharded_gradient(c2, world, mode):
+    """Data-parallel numerics on ONE GPU: loss() per contiguous frame shard with data['shard'] (what a rank
+    that stages only its own frames passes), gradients accumulated over the shards (what the all-reduce
+    sums) == the unsharded call; chunk membership and 1/len(chunk) weights follow the whole batch."""
+    from behavenet_b200 import parallel
+    from behavenet_b200.models import AE
+    x = c2['x'].cuda()
+    m = (torch.rand(x.shape, generator=torch.Generator().manual_seed(9)) > 0.1).float().cuda()
+    model = _model(AE, c2['hp'], c2['sd'], mode)
+    full = model.loss({'images': x[None], 'masks': m[None]})
+    gfull = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    total = 0.0
+    for r in range(world):
+        b, e = parallel.shard_range(x.shape[0], world, r)
+        total += model.loss({'images': x[b:e][None], 'masks': m[b:e][None], 'shard': (b, x.shape[0])})['loss']
+    assert abs(total - full['loss']) <= 1e-6 * full['loss']
+    for k, p in model.named_parameters():
+        # same kernels, different tilings / split-K partitions: fp32 summation order only
+        assert rel_err(p.grad, gfull[k]) < (2e-5 if mode == 0 else 2e-4), k
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_data_parallel_ranks_reproduce_single_process(world, tmp_path):
+    """True multi-process data parallelism (model.data_parallel = True, torch.distributed) on one GPU:
+    `world` ranks share cuda:0 over the gloo backend; each runs AE.loss and PSVAE.loss on the full batch
+    description and must end with the single-process loss dict and gradients (PS-VAE chunks span ranks:
+    B = 300, chunk 128 -> 128 / 128 / 44 over `world` contiguous frame shards)."""
+    script = os.path.join(ROOT, 'tests', 'dp_worker.py')
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT=str(_free_port()), WORLD_SIZE=str(world),
+               PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    procs = []
+    for r in range(world):
+        e = dict(env, RANK=str(r), LOCAL_RANK='0')
+        procs.append(subprocess.Popen([sys.executable, script, str(tmp_path)], env=e, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    res = [torch.load(os.path.join(str(tmp_path), 'rank%d.pt' % r)) for r in range(world)]
+    ref = torch.load(os.path.join(str(tmp_path), 'single.pt'))
+    for tag in ('ae', 'psvae'):
+        for r in range(world):
+            for k, v in ref[tag]['loss'].items():
+                assert abs(res[r][tag]['loss'][k] - v) <= 2e-5 * max(1.0, abs(v)), (tag, r, k)
+            for k, g in ref[tag]['grads'].items():
+                assert rel_err(res[r][tag]['grads'][k], g) < 3e-4, (tag, r, k)
+
+
+def test_adam_trajectory_tracks_the_fp32_oracle():
+    """20 Adam(amsgrad) steps on the C2 geometry (B = 32, chunks of 20 + 12) in the TF32 mode against the same
+    20 steps taken by the fp32 CPU oracle: the loss curves must stay together (the optimizer of
+    fitting/training.py:284-286)."""
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(1, 128, 128, 12)
+    sd = co.init_state_dict(hp, seed=3)
+    x = torch.rand(32, 1, 128, 128, generator=torch.Generator().manual_seed(11))
+    model = _model(AE, hp, sd, 1)
+    opt = torch.optim.Adam(model.get_parameters(), lr=1e-3, amsgrad=True)
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ropt = torch.optim.Adam(list(ref.values()), lr=1e-3, amsgrad=True)
+    xg = x.cuda()
+    ours, theirs = [], []
+    for step in range(20):
+        opt.zero_grad()
+        ours.append(model.loss({'images': xg[None]}, chunk_size=20)['loss'])
+        opt.step()
+        ropt.zero_grad()
+        lo, go = co.ae_loss({k: v.detach() for k, v in ref.items()}, hp, x, None, chunk_size=20)
+        for k, v in ref.items():
+            v.grad = go[k]
+        ropt.step()
+        theirs.append(lo['loss'])
+    ours, theirs = np.array(ours), np.array(theirs)
+    assert theirs[-1] < 0.9 * theirs[0]                      # the 20 steps actually train
+    assert np.abs(ours - theirs).max() <= 2e-3 * theirs[0], (ours, theirs)

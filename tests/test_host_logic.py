@@ -196,6 +196,42 @@ def _gloo_worker(rank, world, port, q):
     tot = sum(r + 1 for r in range(world))
     ok = all(torch.all(g == tot * (i + 1)) for i, g in enumerate(g for g in grads if g is not None))
     ok = ok and sse.tolist() == [sum(1.0 + r for r in range(world)), 10.0 * world]
+    # bucketed path: the decoder bucket's all-reduce starts early (after the decoder's backward pass), the
+    # rest follows -- every gradient must still be summed exactly once
+    for i, g in enumerate(g for g in grads if g is not None):
+        g.fill_(float(rank + 1) * (i + 1))
+    span = model._rt.bufs['flat_grad_dec']
+    n_dec = sum(p.numel() for p in model.decoding.parameters())
+    ok = ok and span is not None and span[1] - span[0] == n_dec and span[1] == model._rt.bufs['flat_grad'].numel()
+    pending = model._allreduce_begin(params)
+    ok = ok and pending is not None
+    model._allreduce(params, sse.clone(), pending)
+    ok = ok and all(torch.all(g == tot * (i + 1)) for i, g in enumerate(g for g in grads if g is not None))
+    # PS-VAE chunks that span ranks: every rank ends up with its own rows of a per-chunk quantity that
+    # depends on all rows of the chunk, and only a chunk's owner reports its sums
+    from behavenet_b200.models.vaes import _latent_rows
+    n_total, Lz, chunk = 23, 3, 8
+    gen_ = torch.Generator().manual_seed(1)
+    tab = torch.randn(n_total, 3 * Lz, generator=gen_)
+    chunks = [(b, min(b + chunk, n_total)) for b in range(0, n_total, chunk)]
+    beg, end = parallel.shard_range(n_total)
+    owned = []
+
+    def call(c, b, e, owner, pre_f, lv_f, eps_f, mu_f, z_f, gmu_f, glv_f, gz_f):
+        sl = slice(b, e)
+        mu_f[sl] = pre_f[sl] - pre_f[sl].mean(0, keepdim=True)           # needs the whole chunk
+        z_f[sl] = lv_f[sl] * eps_f[sl].sum()
+        if owner:
+            owned.append(c)
+    rows = _latent_rows(beg, end, n_total, chunks, tab[beg:end, :Lz].clone(), tab[beg:end, Lz:2 * Lz].clone(),
+                        tab[beg:end, 2 * Lz:].clone(), call, True)
+    want_mu = torch.cat([tab[b:e, :Lz] - tab[b:e, :Lz].mean(0, keepdim=True) for b, e in chunks])[beg:end]
+    want_z = torch.cat([tab[b:e, Lz:2 * Lz] * tab[b:e, 2 * Lz:].sum() for b, e in chunks])[beg:end]
+    ok = ok and torch.allclose(rows[0], want_mu, atol=1e-6) and torch.allclose(rows[1], want_z, atol=1e-5)
+    cnt = torch.zeros(len(chunks))
+    cnt[owned] += 1
+    parallel.all_reduce_sum(cnt)
+    ok = ok and cnt.tolist() == [1.0] * len(chunks)
     # second path: gradients that are NOT views of the flat buffer
     model.zero_grad()
     for p in model.parameters():

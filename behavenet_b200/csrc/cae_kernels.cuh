@@ -46,6 +46,10 @@ int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, i
                            const TapClass* cls, float* grad, cudaStream_t st);
 void bn_wgrad_reduce_defer_begin();
 int bn_wgrad_reduce_flush(cudaStream_t st);
+// true between bn_wgrad_reduce_defer_begin() and bn_wgrad_reduce_flush() on this thread
+bool bn_reduce_deferring();
+// queue out[c] += sum_r part[r * C + c] (r < rows) for the batched reduction launch; only while deferring
+int bn_colsum_reduce_defer(const float* part, int rows, int C, float* out);
 
 // out[c] += sum_m x[m*C + c]
 int bn_launch_colsum(const float* x, long long M, int C, float* out, cudaStream_t st);
@@ -62,9 +66,13 @@ int bn_launch_thin_dgrad(const float* small, const ConvGeom& g, const float* wd,
 // wft != NULL selects the tcgen05 (TF32) form: K-major weights [c_small][(tap, c_big)]
 int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* wft, const float* bias,
                          float* out, const float* dact, int act, int n, cudaStream_t st,
-                         const unsigned char* big_u8 = nullptr);   // big_u8: raw 0..255 video with big's strides
+                         const unsigned char* big_u8 = nullptr,    // big_u8: raw 0..255 video with big's strides
+                         float* colsum = nullptr, int* colsum_fused = nullptr);   // optional fused column sums of `out`
 int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                          size_t partial_floats, float* grad, cudaStream_t st);
+// tcgen05 (TF32) form of bn_launch_thin_wgrad (cae_thin_tc.cu); returns 1 when not applicable
+int bn_launch_thin_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
+                            size_t partial_floats, float* grad, cudaStream_t st);
 int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd, const float* bias, int n,
                           float* xhat_ws, float* xhat_user, const float* target, const float* mask,
                           int chunk_size, int frame_offset, int n_total, float grad_coef, double* sse,
@@ -112,6 +120,6 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
                        const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
                        int act, float* split_buf, size_t split_floats, float* colsum, int* colsum_fused,
-                       cudaStream_t st);
+                       float* colpart, size_t colpart_floats, cudaStream_t st);
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n,
                        float* partial, size_t partial_floats, float* grad, cudaStream_t st);

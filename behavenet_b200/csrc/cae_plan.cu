@@ -51,7 +51,25 @@ struct WsLayout {
   // and batched), encoder and decoder calls share the space; `partial` (above) is the separate scratch of
   // the split-K implicit GEMMs and of bn_cae_layer_op
   size_t wg_enc[BN_MAX_LAYERS], wg_dec[BN_MAX_LAYERS], wg_floats_enc[BN_MAX_LAYERS], wg_floats_dec[BN_MAX_LAYERS];
+  // per-CTA column-sum rows of the gradient image that layer i's backward-data kernel stores (= the bias
+  // gradient of layer i - 1), reduced in the same batched launch as the weight-gradient slices
+  size_t cp_enc[BN_MAX_LAYERS], cp_dec[BN_MAX_LAYERS], cp_floats_enc[BN_MAX_LAYERS], cp_floats_dec[BN_MAX_LAYERS];
 };
+
+// rows of the per-CTA column-sum table an implicit-GEMM launch can produce: one per (class, 128-row tile) of
+// the im2col kernels, or one per 16 x 8 block of the halo kernel
+size_t colpart_rows(const bn_cae_plan* p, int table_idx, int nclasses, int n) {
+  long long maxM = 0, maxH = 0, maxW = 0;
+  for (int c = 0; c < nclasses; ++c) {
+    const TapClass& k = p->h_tables[table_idx + c];
+    maxM = std::max(maxM, (long long)k.Hm * k.Wm);
+    maxH = std::max<long long>(maxH, k.Hm);
+    maxW = std::max<long long>(maxW, k.Wm);
+  }
+  const long long im2col = (long long)nclasses * (((long long)n * maxM + 127) / 128);
+  const long long halo = (long long)n * ((maxW + 7) / 8) * ((maxH + 15) / 16);
+  return (size_t)std::max(im2col, halo);
+}
 
 WsLayout ws_layout(const bn_cae_plan* p, int n) {
   WsLayout w;
@@ -75,6 +93,16 @@ WsLayout ws_layout(const bn_cae_plan* p, int n) {
     w.wg_enc[i] = oe; oe += align64(w.wg_floats_enc[i]);
     w.wg_floats_dec[i] = bn_wgrad_partial_floats(p->dec[i], n);
     w.wg_dec[i] = od; od += align64(w.wg_floats_dec[i]);
+  }
+  o = std::max(oe, od);
+  oe = od = o;
+  for (int i = 0; i < p->nl; ++i) {
+    // encoder layer i, backward-data (dgrad form) -> image with enc[i].Cb channels
+    w.cp_floats_enc[i] = i > 0 ? colpart_rows(p, p->enc_d[i], p->enc[i].n_dgrad, n) * p->enc[i].Cb : 0;
+    w.cp_enc[i] = oe; oe += align64(w.cp_floats_enc[i]);
+    // decoder layer i, backward-data (fprop form) -> image with dec[i].Cs channels
+    w.cp_floats_dec[i] = i > 0 ? colpart_rows(p, p->dec_f[i], 1, n) * p->dec[i].Cs : 0;
+    w.cp_dec[i] = od; od += align64(w.cp_floats_dec[i]);
   }
   o = std::max(oe, od);
   w.total = o;
@@ -131,7 +159,8 @@ thread_local size_t t_split_floats = 0;
 int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const float* wt, int wrow,
               const float* bias, float* out, int Ho, int Wo, int Co, const float* dact, int table_idx,
               int nclasses, int maxM, int gs, int os, int n, int act, cudaStream_t st,
-              float* colsum = nullptr, int* colsum_fused = nullptr) {
+              float* colsum = nullptr, int* colsum_fused = nullptr, float* colpart = nullptr,
+              size_t colpart_floats = 0) {
   // colsum (optional, [Co], accumulated into): the column sums of `out`, i.e. the bias gradient of the
   // layer below when `out` is a gradient image; *colsum_fused says whether the kernel's epilogue
   // took care of it (otherwise the caller runs bn_launch_colsum over the stored image)
@@ -142,7 +171,7 @@ int run_igemm(const bn_cae_plan* p, const ImgView& in, const float* w, const flo
     for (int c = 0; c < nclasses; ++c) maxtaps = std::max(maxtaps, p->h_tables[table_idx + c].ntaps);
     int r = bn_launch_igemm_tc(in, wt, wrow, bias, out, Ho, Wo, Co, dact, dcls, p->h_tables.data() + table_idx,
                                nclasses, maxM, maxtaps, gs, os, n, act, t_split_buf, t_split_floats, colsum,
-                               colsum_fused, st);
+                               colsum_fused, colpart, colpart_floats, st);
     if (r <= 0) return r;
     if (colsum_fused) *colsum_fused = 0;
   }
@@ -153,6 +182,10 @@ int run_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, 
               size_t partial_floats, float* grad, cudaStream_t st) {
   if (!grad) return 0;
   if (g.Cb <= 4) {
+    if (g_tc_mode.load()) {
+      int r = bn_launch_thin_wgrad_tc(big, small, g, n, partial, partial_floats, grad, st);
+      if (r <= 0) return r;
+    }
     int r = bn_launch_thin_wgrad(big, small, g, n, partial, partial_floats, grad, st);
     if (r <= 0) return r;
   }
@@ -402,12 +435,13 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
     flip ^= 1;
     int thin = g.Cb <= 4 ? bn_launch_thin_fprop(big, g, pk + g.off_wf, g_tc_mode.load() ? pk + g.off_wft : nullptr, nullptr, out,
                                                 i > 0 ? small : nullptr,
-                                                BN_ACT_NONE, n, st) : 1;
+                                                BN_ACT_NONE, n, st, nullptr, i > 0 ? G[p->dec[i - 1].p_b] : nullptr,
+                                                &bias_done) : 1;
     if (thin < 0) return thin;
     if (thin > 0)
       BN_TRY(run_igemm(p, big, pk + g.off_wf, pk + g.off_wft, g.k * g.k * g.Cb, nullptr, out, g.Hs, g.Ws,
                        g.Cs, i > 0 ? small : nullptr, p->dec_f[i], 1, g.Hs * g.Ws, g.s, 1, n, BN_ACT_NONE, st,
-                       i > 0 ? G[p->dec[i - 1].p_b] : nullptr, &bias_done));
+                       i > 0 ? G[p->dec[i - 1].p_b] : nullptr, &bias_done, ws + L.cp_dec[i], L.cp_floats_dec[i]));
     gcur = out;
   }
   return 0;
@@ -455,7 +489,7 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
       ImgView in = nhwc_view(gcur, g.Hs, g.Ws, g.Cs);
       BN_TRY(run_igemm(p, in, pk + g.off_wd, pk + g.off_wdt, g.k * g.k * g.Cs, nullptr, out, g.Hb, g.Wb,
                        g.Cb, ws + L.enc_act[i], p->enc_d[i], g.n_dgrad, g.dgrad_maxM, 1, g.s, n,
-                       BN_ACT_NONE, st, G[p->enc[i - 1].p_b], &bias_done));
+                       BN_ACT_NONE, st, G[p->enc[i - 1].p_b], &bias_done, ws + L.cp_enc[i], L.cp_floats_enc[i]));
       gcur = out;
     }
   }

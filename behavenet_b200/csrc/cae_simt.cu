@@ -10,6 +10,8 @@
 //                      Zero padding (ZeroPad2d, aes.py:149-155) and the decoder crop
 //                      (F.pad(-pad), aes.py:467-470) are folded into the gather / store indexing.
 //   wgrad_kernel     : dW[(tap,cb), cs] = sum_m big[pix(m) + off(tap), cb] * small[m, cs]
+#include <string.h>
+
 #include "cae_kernels.cuh"
 
 namespace {
@@ -378,11 +380,41 @@ struct ReduceJob {
   const TapClass* cls;
   int splits, Ktot, Cs, Cb, KK;
   int gx, gy, gz, block0;
+  int kind;                   // 0: weight-gradient slices -> torch layout; 1: column sums of a [splits][Cs] table
 };
 struct ReduceJobs {
   int n;
-  ReduceJob j[16];            // 2 * BN_MAX_LAYERS
+  ReduceJob j[32];            // 2 * BN_MAX_LAYERS weight gradients + as many bias gradients
 };
+
+// out[c] += sum_r part[r][c]: block (bx, bz) owns 32 columns and the rows bz, bz + gz, .. (8 warps interleaved)
+__device__ __forceinline__ void colsum_reduce_block(const ReduceJob& jb, int bx, int bz, float (*tile)[33]) {
+  const float* __restrict__ part = jb.partial;
+  const int rows = jb.splits, C = jb.Cs, gz = jb.gz;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = bx * 32 + tx;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    const int step = 8 * gz;
+    int r = bz * 8 + ty;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      s0 += __ldg(part + (long long)r * C + c);
+      s1 += __ldg(part + (long long)(r + step) * C + c);
+      s2 += __ldg(part + (long long)(r + 2 * step) * C + c);
+      s3 += __ldg(part + (long long)(r + 3 * step) * C + c);
+    }
+    for (; r < rows; r += step) s0 += __ldg(part + (long long)r * C + c);
+  }
+  tile[ty][tx] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += tile[i][tx];
+    if (gz > 1) atomicAdd(jb.grad + c, s);
+    else jb.grad[c] += s;
+  }
+}
 
 __device__ __forceinline__ void wgrad_reduce_block(const ReduceJob& jb, int bx, int by, int bz, float (*tile)[33],
                                                    unsigned char* inv) {
@@ -450,7 +482,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
     const int l = b - jb.block0;
     if (l >= 0 && l < jb.gx * jb.gy * jb.gz) {
       const int bx = l % jb.gx, by = (l / jb.gx) % jb.gy, bz = l / (jb.gx * jb.gy);
-      wgrad_reduce_block(jb, bx, by, bz, tile, inv);
+      if (jb.kind == 1) colsum_reduce_block(jb, bx, bz, tile);
+      else wgrad_reduce_block(jb, bx, by, bz, tile, inv);
       return;
     }
   }
@@ -525,7 +558,7 @@ int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, i
   ReduceJob jb;
   jb.partial = partial; jb.grad = grad; jb.cls = cls;
   jb.splits = splits; jb.Ktot = Ktot; jb.Cs = Cs; jb.Cb = Cb; jb.KK = KK;
-  jb.gx = gx; jb.gy = gy; jb.gz = gz; jb.block0 = 0;
+  jb.gx = gx; jb.gy = gy; jb.gz = gz; jb.block0 = 0; jb.kind = 0;
   if (t_reduce_defer && t_reduce_jobs.n < (int)(sizeof(t_reduce_jobs.j) / sizeof(t_reduce_jobs.j[0]))) {
     t_reduce_jobs.j[t_reduce_jobs.n++] = jb;       // launched by bn_wgrad_reduce_flush
     return 0;
@@ -541,6 +574,22 @@ int bn_launch_wgrad_reduce(const float* partial, int splits, int Ktot, int Cs, i
 void bn_wgrad_reduce_defer_begin() {
   t_reduce_jobs.n = 0;
   t_reduce_defer = true;
+}
+
+bool bn_reduce_deferring() {
+  return t_reduce_defer && t_reduce_jobs.n < (int)(sizeof(t_reduce_jobs.j) / sizeof(t_reduce_jobs.j[0]));
+}
+
+int bn_colsum_reduce_defer(const float* part, int rows, int C, float* out) {
+  if (!bn_reduce_deferring()) BN_FAIL("bn_colsum_reduce_defer: no batched reduction is open");
+  ReduceJob jb;
+  memset(&jb, 0, sizeof(jb));
+  jb.partial = part; jb.grad = out; jb.cls = nullptr;
+  jb.splits = rows; jb.Cs = C; jb.kind = 1;
+  jb.gx = bn_cdiv(C, 32); jb.gy = 1;
+  jb.gz = rows >= 1024 ? 16 : (rows >= 128 ? 4 : 1);
+  t_reduce_jobs.j[t_reduce_jobs.n++] = jb;
+  return 0;
 }
 
 int bn_wgrad_reduce_flush(cudaStream_t st) {

@@ -74,7 +74,9 @@ struct TcArgs {
   int gs, os, n, act;
   int ksplit;             // > 1: single-class op whose k-chunks are split over grid.z
   float* split_out;       // [ksplit][M][Co] raw partial sums (bias / activation applied by the reducer)
-  float* colsum;          // optional [Co]: += column sums of the stored output (fused bias gradient)
+  float* colsum;          // optional [Co]: += column sums of the stored output (fused bias gradient; persistent halo kernel)
+  float* colpart;         // optional [ctas][Co]: row (blockIdx.z * gridDim.x + blockIdx.x) = this CTA's column sums of
+                          // what it stored (no atomics; summed by the batched reduction kernel)
 };
 
 template <int BN, int STAGES>
@@ -118,7 +120,12 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
   const int HmWm = cls->Hm * cls->Wm;
   const long long M = (long long)a.n * HmWm;
   const long long m0 = (long long)blockIdx.x * BM;
-  if (m0 >= M) return;                         // uniform per CTA, before any TMEM allocation
+  if (m0 >= M) {                               // uniform per CTA, before any TMEM allocation
+    if (a.colpart != nullptr && a.ksplit <= 1)
+      for (int c = tid; c < BN; c += NTHREADS)
+        a.colpart[((long long)blockIdx.z * gridDim.x + blockIdx.x) * a.Co + blockIdx.y * BN + c] = 0.f;
+    return;
+  }
   if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
   tc_fence_before();
   __syncthreads();
@@ -223,7 +230,11 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
     }
     // all MMAs have retired, so the pipeline stages are free: reuse them as the transposition tiles
     float* tile = reinterpret_cast<float*>(smem) + warp * 1024;
+    float* colred = reinterpret_cast<float*>(smem) + 4 * 1024;      // [4 warps][BN] per-CTA column sums
     const int elane = tid & 31;
+    const bool want_col = a.colpart != nullptr && a.ksplit <= 1;
+    if (want_col)
+      for (int c = elane; c < BN; c += 32) colred[warp * BN + c] = 0.f;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       uint32_t r[32];
@@ -240,9 +251,15 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tc_kernel(const TcArgs a) {
       } else {
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
         warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
-                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, a.colsum != nullptr);
-        if (a.colsum) warp_flush_colsum(a.colsum + n0 + j * 32, cacc, elane);
+                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, want_col);
+        if (want_col) warp_fold_colsum(colred + warp * BN + j * 32, cacc, elane);
       }
+    }
+    if (want_col) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
+      float* dst = a.colpart + ((long long)blockIdx.z * gridDim.x + blockIdx.x) * a.Co + n0;
+      for (int c = tid; c < BN; c += NPROD)
+        dst[c] = colred[c] + colred[BN + c] + colred[2 * BN + c] + colred[3 * BN + c];
     }
     tc_fence_before();
   } else {
@@ -357,7 +374,14 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
   const int HmWm = cls->Hm * cls->Wm;
   const long long M = (long long)a.n * HmWm;
   const long long m0 = (long long)blockIdx.x * BM;
-  if (m0 >= M) return;
+  if (m0 >= M) {
+    if (a.colpart != nullptr && a.ksplit <= 1) {
+      bn_pdl_wait();
+      for (int c = tid; c < BN; c += NTHREADS)
+        a.colpart[((long long)blockIdx.z * gridDim.x + blockIdx.x) * a.Co + blockIdx.y * BN + c] = 0.f;
+    }
+    return;
+  }
   if (warp == 4) tmem_alloc<NCOLS>(smem_u32(tmem_ptr));
   tc_fence_before();
   __syncthreads();
@@ -421,7 +445,11 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
     }
     // all MMAs have retired, so the pipeline stages are free: reuse them as the transposition tiles
     float* tile = reinterpret_cast<float*>(smem) + warp * 1024;
+    float* colred = reinterpret_cast<float*>(smem) + 4 * 1024;      // [4 warps][BN] per-CTA column sums
     const int elane = tid & 31;
+    const bool want_col = a.colpart != nullptr && a.ksplit <= 1;
+    if (want_col)
+      for (int c = elane; c < BN; c += 32) colred[warp * BN + c] = 0.f;
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       uint32_t r[32];
@@ -438,9 +466,15 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
       } else {
         float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
         warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
-                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, a.colsum != nullptr);
-        if (a.colsum) warp_flush_colsum(a.colsum + n0 + j * 32, cacc, elane);
+                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, want_col);
+        if (want_col) warp_fold_colsum(colred + warp * BN + j * 32, cacc, elane);
       }
+    }
+    if (want_col) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
+      float* dst = a.colpart + ((long long)blockIdx.z * gridDim.x + blockIdx.x) * a.Co + n0;
+      for (int c = tid; c < BN; c += NPROD)
+        dst[c] = colred[c] + colred[BN + c] + colred[2 * BN + c] + colred[3 * BN + c];
     }
     tc_fence_before();
   } else {
@@ -1182,6 +1216,9 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     // more in same-address atomics than the separate column-sum pass): this lane's 4 columns
     static_assert(!PERSIST || NB == 32, "the fused column sums keep one accumulator per lane");
     float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // one-tile-per-CTA variant: per-CTA column sums go to row blockIdx.x of the partial table (no atomics)
+    float* colred = reinterpret_cast<float*>(smem + S::OFF_EPI) + 4 * 1024;      // [4 warps][NB]
+    const bool want_part = !PERSIST && a.colpart != nullptr;
     int ti = 0;
     for (long long T = t_first; T < total; T += t_step, ++ti) {
       const int f = (int)(T / h.tiles_per_frame);
@@ -1193,6 +1230,8 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
       mbar_wait(smem_u32(acc_full + buf), (ti >> 1) & 1);
       tc_fence_after();
       if (tid == 0) HALO_STAMP(ti, 4);
+      if (want_part)      // (the table aliases the weight ring: only touch it once every MMA has retired)
+        for (int c = elane; c < NB; c += 32) colred[warp * NB + c] = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const bool rvalid = ym < h.Hm[c] && xm < h.Wm[c];
@@ -1208,8 +1247,15 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
 #pragma unroll
             for (int q = 0; q < 32; ++q) r[q] = 0u;
           }
-          warp_store_rows32(a.out, a.dact, BN_LEAK, (rvalid && !(h.dbg & 4)) ? obase + j * 32 : -1, r,
-                            a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane, cacc, PERSIST && a.colsum != nullptr);
+          if (want_part) {
+            float4 pacc = make_float4(0.f, 0.f, 0.f, 0.f);
+            warp_store_rows32(a.out, a.dact, BN_LEAK, (rvalid && !(h.dbg & 4)) ? obase + j * 32 : -1, r,
+                              a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane, pacc, true);
+            warp_fold_colsum(colred + warp * NB + j * 32, pacc, elane);
+          } else {
+            warp_store_rows32(a.out, a.dact, BN_LEAK, (rvalid && !(h.dbg & 4)) ? obase + j * 32 : -1, r,
+                              a.bias ? a.bias + j * 32 : nullptr, a.act, tile, elane, cacc, PERSIST && a.colsum != nullptr);
+          }
         }
       }
       tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
@@ -1218,6 +1264,12 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
       if (tid == 0) HALO_STAMP(ti, 5);
     }
     if (PERSIST && a.colsum) warp_flush_colsum(a.colsum, cacc, elane);
+    if (want_part) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps
+      float* dst = a.colpart + (long long)blockIdx.x * a.Co;
+      for (int c = tid; c < NB; c += 128)
+        dst[c] = colred[c] + colred[NB + c] + colred[2 * NB + c] + colred[3 * NB + c];
+    }
   } else if (warp == 4) {
     // ======================= MMA issuer ==========================================================
     if ((tid & 31) == 0) {
@@ -1383,7 +1435,8 @@ int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
 }
 
 // returns 1 when the op does not have the stride-2 four-class shape this kernel covers
-int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsum_fused, cudaStream_t st) {
+int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsum_fused, float* colsum_out,
+                   float* colpart, size_t colpart_floats, cudaStream_t st) {
   static const bool off = [] { const char* e = getenv("BN_HALO"); return e && e[0] == '0'; }();
   if (off || nclasses != 4 || a.gs != 1 || a.os != 2 || a.ksplit > 1) return 1;
   if (a.Co != 32 && a.Co != 64) return 1;
@@ -1484,9 +1537,18 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsu
   static const int deep = [] { const char* e = getenv("BN_HALO_DEEP"); return e ? atoi(e) : 0; }();
   if (a.Co == 32 && deep == 1) return launch_halo<32, 10, true>(local, h, st);      // one CTA per SM, 160 KB weight ring
   if (a.Co == 32) return launch_halo<32, 3, true>(local, h, st);
-  h.a.colsum = nullptr;    // not persistent: see bn_launch_igemm_tc
+  // one tile per CTA: no atomics; the CTA's column sums become one row of the partial table
+  h.a.colsum = nullptr;
   if (colsum_fused) *colsum_fused = 0;
-  return launch_halo<64, 2, false>(local, h, st);
+  h.a.colpart = nullptr;
+  if (colsum_out && colpart && bn_reduce_deferring() && (size_t)h.total_tiles * a.Co <= colpart_floats)
+    h.a.colpart = colpart;
+  int r = launch_halo<64, 2, false>(local, h, st);
+  if (r == 0 && h.a.colpart) {
+    BN_TRY(bn_colsum_reduce_defer(colpart, (int)h.total_tiles, a.Co, colsum_out));
+    if (colsum_fused) *colsum_fused = 1;
+  }
+  return r;
 }
 
 }  // namespace
@@ -1495,7 +1557,7 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
                        const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
                        int act, float* split_buf, size_t split_floats, float* colsum, int* colsum_fused,
-                       cudaStream_t st) {
+                       float* colpart, size_t colpart_floats, cudaStream_t st) {
   if (colsum_fused) *colsum_fused = 0;
   // shapes this kernel covers: NHWC-dense input with C % 32 == 0, C_out in {32, 64, 128, 256, 512},
   // enough rows to fill the machine (the stride-5 layers with a few hundred rows stay on the
@@ -1529,12 +1591,19 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   a.n = n; a.act = act;
   // the epilogue can accumulate the column sums of what it stores (split-K leaves that to the reducer)
   a.colsum = (ksplit == 1 && !((uintptr_t)colsum & 15)) ? colsum : nullptr;
+  a.colpart = nullptr;
   if (colsum_fused) *colsum_fused = a.colsum != nullptr;
-  int r = try_dgrad_halo(a, h_classes, nclasses, colsum_fused, st);
+  int r = try_dgrad_halo(a, h_classes, nclasses, colsum_fused, a.colsum, colpart, colpart_floats, st);
   if (r <= 0) return r;
   // one tile per CTA below: a flush per tile makes ~10^4 same-address atomics per column, which costs
-  // more than the separate column-sum pass saves (measured); only the persistent halo kernel fuses
+  // more than the separate column-sum pass saves (measured).  Instead every CTA writes its column sums
+  // as one row of a partial table and the batched reduction kernel of the backward call adds them up.
+  const long long col_rows = (long long)bn_cdiv(M, BM) * nclasses;
+  const bool part = a.colsum != nullptr && colpart != nullptr && !((uintptr_t)colpart & 15) && bn_reduce_deferring() &&
+                    (size_t)col_rows * Co <= colpart_floats;
+  float* colsum_out = a.colsum;
   a.colsum = nullptr;
+  a.colpart = part ? colpart : nullptr;
   if (colsum_fused) *colsum_fused = 0;
   const TmaSet* tm = get_tma_set(in, wt, wrow, Co, bn, d_classes, h_classes, nclasses, gs, n);
   if (tm) {
@@ -1552,6 +1621,10 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
       case 128: r = launch_tc<128, 3>(a, nclasses, maxM, st); break;
       default: r = launch_tc<256, 4>(a, nclasses, maxM, st); break;
     }
+  }
+  if (r == 0 && part) {
+    BN_TRY(bn_colsum_reduce_defer(colpart, (int)col_rows, Co, colsum_out));
+    if (colsum_fused) *colsum_fused = 1;
   }
   if (r || ksplit == 1) return r;
   const long long total = M * Co;          // fprop-form output is linear in (m, co)

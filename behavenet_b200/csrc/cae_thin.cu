@@ -425,7 +425,8 @@ struct ThinTcSmem {
 template <int CB>
 __global__ void __launch_bounds__(256) thin_fprop_tc_kernel(const ThinGeo g, const float* __restrict__ wft,
                                                             const float* __restrict__ bias, float* __restrict__ out,
-                                                            const float* __restrict__ dact, int act, const TileIter it) {
+                                                            const float* __restrict__ dact, int act, const TileIter it,
+                                                            float* __restrict__ colsum) {
   bn_pdl_trigger();
   bn_pdl_wait();
   using namespace bn_tc;
@@ -473,6 +474,9 @@ __global__ void __launch_bounds__(256) thin_fprop_tc_kernel(const ThinGeo g, con
     issue_patch<CB>(patch[0], g, f, y0, x0, tid);
   }
   cp_commit();
+  // fused column sums of the stored image (the bias gradient of the layer below when `out` is a gradient
+  // image): per-lane accumulators over all tiles of this persistent CTA, one flush at the end
+  float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t phase = 0;
   for (int buf = 0; t < it.total; t += gridDim.x, buf ^= 1, phase ^= 1) {
     it.decode(t, f, y0, x0);
@@ -535,11 +539,29 @@ __global__ void __launch_bounds__(256) thin_fprop_tc_kernel(const ThinGeo g, con
       const bool valid = oy < g.Hs && ox < g.Ws;
       const long long idx = valid ? (((long long)f * g.Hs + oy) * g.Ws + ox) * g.Cs + c0 : -1;
       warp_store_rows32(out, dact, BN_LEAK, idx, r, bias ? bias + c0 : nullptr, act,
-                        reinterpret_cast<float*>(tsm) + warp * 1024, lane);
+                        reinterpret_cast<float*>(tsm) + warp * 1024, lane, cacc, colsum != nullptr);
     }
     tc_fence_before();
   }
   __syncthreads();
+  if (colsum != nullptr) {
+    float* red = reinterpret_cast<float*>(tsm);           // [8 warps][32 columns]; the A tiles are idle
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      cacc.x += __shfl_xor_sync(0xffffffffu, cacc.x, o);
+      cacc.y += __shfl_xor_sync(0xffffffffu, cacc.y, o);
+      cacc.z += __shfl_xor_sync(0xffffffffu, cacc.z, o);
+      cacc.w += __shfl_xor_sync(0xffffffffu, cacc.w, o);
+    }
+    if (lane < 8) *(reinterpret_cast<float4*>(red + warp * 32) + lane) = cacc;
+    __syncthreads();
+    if (tid < 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 32 + tid];
+      atomicAdd(colsum + c0 + tid, s);
+    }
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<64>(tmem_base);
@@ -548,7 +570,7 @@ __global__ void __launch_bounds__(256) thin_fprop_tc_kernel(const ThinGeo g, con
 
 template <int CB>
 static int launch_thin_fprop_tc(const ThinGeo& t, const float* wft, const float* bias, float* out, const float* dact,
-                                int act, const TileIter& it, int cgroups, cudaStream_t st) {
+                                int act, const TileIter& it, int cgroups, cudaStream_t st, float* colsum) {
   using S = ThinTcSmem<CB>;
   auto kern = thin_fprop_tc_kernel<CB>;
   static bool configured = false;
@@ -560,7 +582,7 @@ static int launch_thin_fprop_tc(const ThinGeo& t, const float* wft, const float*
   int per_sm = (227 * 1024) / (S::TOTAL + 1024);
   per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);       // ~120 registers x 256 threads: two CTAs per SM
   long long blocks = it.total < 148LL * per_sm ? it.total : 148LL * per_sm;
-  BN_CUDA(bn_launch(kern, dim3((unsigned)blocks, cgroups), 256, S::TOTAL, st, t, wft, bias, out, dact, act, it));
+  BN_CUDA(bn_launch(kern, dim3((unsigned)blocks, cgroups), 256, S::TOTAL, st, t, wft, bias, out, dact, act, it, colsum));
   BN_LAUNCHED();
   return 0;
 }
@@ -583,7 +605,8 @@ static int launch_thin_fprop(const ThinGeo& t, const float* wf, const float* bia
 
 int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf, const float* wft, const float* bias,
                          float* out, const float* dact, int act, int n, cudaStream_t st,
-                         const unsigned char* big_u8) {
+                         const unsigned char* big_u8, float* colsum, int* colsum_fused) {
+  if (colsum_fused) *colsum_fused = 0;
   if (!fast_geom(g) || n <= 0) return 1;
   ThinGeo t;
   t.big8 = big_u8;
@@ -596,11 +619,12 @@ int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf,
   if (wft != nullptr && !tc_off && !((uintptr_t)out & 15) && !(dact && ((uintptr_t)dact & 15)) &&
       !(bias && ((uintptr_t)bias & 15))) {
     // tensor-core form (TF32): wft = K-major weights [c_small][(tap, c_big)]
+    if (colsum_fused) *colsum_fused = colsum != nullptr;
     switch (g.Cb) {
-      case 1: return launch_thin_fprop_tc<1>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
-      case 2: return launch_thin_fprop_tc<2>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
-      case 3: return launch_thin_fprop_tc<3>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
-      default: return launch_thin_fprop_tc<4>(t, wft, bias, out, dact, act, it, g.Cs / 32, st);
+      case 1: return launch_thin_fprop_tc<1>(t, wft, bias, out, dact, act, it, g.Cs / 32, st, colsum);
+      case 2: return launch_thin_fprop_tc<2>(t, wft, bias, out, dact, act, it, g.Cs / 32, st, colsum);
+      case 3: return launch_thin_fprop_tc<3>(t, wft, bias, out, dact, act, it, g.Cs / 32, st, colsum);
+      default: return launch_thin_fprop_tc<4>(t, wft, bias, out, dact, act, it, g.Cs / 32, st, colsum);
     }
   }
   switch (g.Cb) {

@@ -163,4 +163,24 @@ __device__ __forceinline__ void warp_flush_colsum(float* __restrict__ colsum, fl
   }
 }
 
+// Per-CTA column sums without atomics: every epilogue warp folds the per-lane accumulator of one 32-column
+// block into its own row of a shared-memory table ([warps][ncols], zeroed by the warp beforehand); after the
+// warps have met, cta_store_colpart writes the CTA's sums as ONE row of a [ctas][C] partial table that the
+// batched reduction kernel (cae_simt.cu, job kind 1) adds into the bias gradient.
+__device__ __forceinline__ void warp_fold_colsum(float* __restrict__ row32, float4 acc, int lane) {
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (lane < 8) {
+    float4* p = reinterpret_cast<float4*>(row32) + lane;
+    float4 v = *p;
+    v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += acc.w;
+    *p = v;
+  }
+}
+
 }  // namespace bn_tc

@@ -59,12 +59,14 @@ def _run(lib, drv, params, packed, ws, side, layer, op, n, a, b, out, mode):
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize('geom', [(32, 128, 128), (7, 64, 48), (50, 96, 80)])
+@pytest.mark.parametrize('geom', [(32, 128, 128), (7, 64, 48), (50, 96, 80), (256, 128, 128)])
 @pytest.mark.parametrize('side,layer', [(0, 1), (0, 2), (0, 3), (0, 4), (1, 0), (1, 1), (1, 2), (1, 3)])
 @pytest.mark.parametrize('op', [0, 1, 2])
 def test_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op, geom):
     """geom = (frames, H, W): the C2 shape, the integration-test shape with ragged tiles (rows and
-    reduction lengths that are not multiples of the tile sizes), and a mid-size odd shape."""
+    reduction lengths that are not multiples of the tile sizes), a mid-size odd shape, and the C2 shape at the
+    BENCHMARKED batch of 256 frames (the split-K grids, persistent tile loops and per-CTA column-sum tables take
+    their full-size paths there)."""
     n, h, w = geom
     lib, model, drv, params, packed, ws, hp = _setup(n=n, h=h, w=w)
     big, small = _dims(hp, side, layer)
@@ -108,6 +110,33 @@ def test_thin_layer_tensor_core_kernel_matches_cuda_core_kernel(side, layer, op,
     for mode in (0, 1):
         out = torch.full((n,) + small, float('nan'), device='cuda')
         _run(lib, drv, params, packed, ws, side, layer, op, n, xb, None, out, mode)
+        outs.append(out)
+    ref, tc = outs
+    assert torch.isfinite(tc).all()
+    err = float((tc - ref).abs().max() / ref.abs().max())
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize('n_ch', [1, 2, 4])
+@pytest.mark.parametrize('geom', [(32, 128, 128), (7, 64, 48), (256, 128, 128)])
+@pytest.mark.parametrize('side,layer', [(0, 0), (1, 4)])
+def test_thin_layer_weight_gradient_tensor_core_matches_cuda_core(side, layer, geom, n_ch):
+    """Weight gradient of the first encoder / last decoder layer: the tcgen05 kernel (pixels as the GEMM
+    reduction, cae_thin_tc.cu) against the fp32 kernel on TF32-exact data, incl. ragged tiles (64x48 -> 32x24
+    feature map: 24 columns in a 32-wide tile) and the benchmarked batch."""
+    n, h, w = geom
+    if n_ch == 4 and n == 256:
+        pytest.skip('4-channel frames at the full batch add nothing over the 1/2-channel cases')
+    lib, model, drv, params, packed, ws, hp = _setup(n_ch=n_ch, n=n, h=h, w=w)
+    big, small = _dims(hp, side, layer)
+    g = torch.Generator().manual_seed(31 + side)
+    xb = _exact((n,) + big, g).cuda()
+    xs = _exact((n,) + small, g).cuda()
+    wshape = params[2 * layer].shape if side == 0 else params[2 * drv.n_layers + 6 + 2 * layer].shape
+    outs = []
+    for mode in (0, 1):
+        out = torch.zeros(wshape, device='cuda')
+        _run(lib, drv, params, packed, ws, side, layer, 2, n, xb, xs, out, mode)
         outs.append(out)
     ref, tc = outs
     assert torch.isfinite(tc).all()

@@ -78,6 +78,12 @@ int bn_launch_thin_dgrad5(const float* small, const ConvGeom& g, const float* wd
                           int chunk_size, int frame_offset, int n_total, float grad_coef, double* sse,
                           float* dpre, cudaStream_t st);
 
+// tcgen05 (TF32) form of the fused last-layer forward + loss (cae_thin_tc.cu): GEMM over all taps + col2im
+// epilogue; needs a target, writes x_hat only to the workspace copy; returns 1 when not applicable
+int bn_launch_thin_dgrad_tc(const float* small, const ConvGeom& g, const float* wdt, const float* bias, int n,
+                            float* xhat_ws, const float* target, const float* mask, int chunk_size, int frame_offset,
+                            int n_total, float grad_coef, double* sse, float* dpre, cudaStream_t st);
+
 // dpre[n,y,x,c] = dxhat[n,c,y,x] * xhat * (1 - xhat)
 int bn_launch_sigmoid_bwd(const float* dxhat, const float* xhat, float* dpre, int n, int C, int H,
                           int W, cudaStream_t st);

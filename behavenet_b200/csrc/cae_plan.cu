@@ -392,9 +392,18 @@ extern "C" int bn_cae_decode(bn_cae_plan* p, int n, const float* d_z, const floa
                      g.dgrad_maxM, 1, g.s, n, BN_ACT_LEAKY, st));
   }
   const ConvGeom& g = p->dec[p->nl - 1];
-  int fast = bn_launch_thin_dgrad5(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
-                                   d_xhat, d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
-                                   ws + L.dpre_last, st);
+  // training pass (target given, no reconstruction requested): GEMM-over-all-taps + col2im on the tensor
+  // cores; a reconstruction the caller asks for always comes from the fp32 kernel (1e-4 contract)
+  int fast = (g_tc_mode.load() && d_target && !d_xhat)
+                 ? bn_launch_thin_dgrad_tc(ws + L.dec_act[p->nl - 1], g, pk + g.off_wdt, P[g.p_b], n, ws + L.dec_act[p->nl],
+                                           d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
+                                           ws + L.dpre_last, st)
+                 : 1;
+  if (fast < 0) return fast;
+  if (fast > 0)
+    fast = bn_launch_thin_dgrad5(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
+                                 d_xhat, d_target, d_mask, chunk_size, frame_offset, n_total, grad_coef, d_sse,
+                                 ws + L.dpre_last, st);
   if (fast < 0) return fast;
   if (fast > 0)
     BN_TRY(bn_launch_thin_dgrad(ws + L.dec_act[p->nl - 1], g, pk + g.off_wd, P[g.p_b], n, ws + L.dec_act[p->nl],
@@ -505,7 +514,7 @@ extern "C" int bn_cae_layer_op(bn_cae_plan* p, int side, int layer, int op, int 
                                const float* d_in2, float* d_out, const float* const* P,
                                const void* d_packed, void* d_ws, void* stream) {
   if (!p || !d_in || !d_out || !d_packed || !d_ws) BN_FAIL("bn_cae_layer_op: null argument");
-  if (side < 0 || side > 1 || layer < 0 || layer >= p->nl || op < 0 || op > 2) BN_FAIL("bn_cae_layer_op: bad selector");
+  if (side < 0 || side > 1 || layer < 0 || layer >= p->nl || op < 0 || op > 3) BN_FAIL("bn_cae_layer_op: bad selector");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const float* pk = (const float*)d_packed;
@@ -518,6 +527,23 @@ extern "C" int bn_cae_layer_op(bn_cae_plan* p, int side, int layer, int op, int 
   const int td = side == 0 ? p->enc_d[layer] : p->dec_d[layer];
   const float* bias = (P && op == 0) ? P[g.p_b] : nullptr;
   const bool fprop_form = (side == 0 && op == 0) || (side == 1 && op == 1);
+  if (op == 3) {
+    // last decoder layer forward with the fused loss (chunks of 200 frames, gaussian-ll coefficient):
+    // d_in = small image, d_in2 = target (n, C, H, W); d_out = [x_hat (n C H W) | dL/dpre (n H W C) | sse doubles]
+    if (side != 1 || layer != p->nl - 1 || !d_in2) BN_FAIL("bn_cae_layer_op: op 3 is the last decoder layer with a target");
+    const size_t tot = (size_t)n * g.Cb * g.Hb * g.Wb;
+    double* sse = reinterpret_cast<double*>(d_out + 2 * tot);
+    const int nchunks = (n + 199) / 200;
+    BN_CUDA(cudaMemsetAsync(sse, 0, sizeof(double) * nchunks, st));
+    int fast = g_tc_mode.load() ? bn_launch_thin_dgrad_tc(d_in, g, pk + g.off_wdt, P ? P[g.p_b] : nullptr, n, d_out, d_in2,
+                                                          nullptr, 200, 0, n, 1.f, sse, d_out + tot, st)
+                                : 1;
+    if (fast > 0)
+      fast = bn_launch_thin_dgrad5(d_in, g, pk + g.off_wd, P ? P[g.p_b] : nullptr, n, d_out, nullptr, d_in2, nullptr, 200, 0,
+                                   n, 1.f, sse, d_out + tot, st);
+    if (fast > 0) BN_FAIL("bn_cae_layer_op: op 3 needs the kernel-5 / stride-2 thin output layer");
+    return fast;
+  }
   if (op == 2) {
     if (!d_in2) BN_FAIL("bn_cae_layer_op: wgrad needs both images");
     return run_wgrad(nhwc_view(d_in, g.Hb, g.Wb, g.Cb), d_in2, g, n, ws + L.partial, L.partial_floats, d_out, st);

@@ -31,7 +31,7 @@ using namespace bn_tc;
 constexpr int WT_H = 4, WT_W = 32;                 // small-pixel tile: 4 rows x 32 columns = 4 k-chunks of 32 pixels
 constexpr int WP_ROWS = 2 * (WT_H - 1) + 5;        // 11 patch rows
 constexpr int WP_COLS = 72;                        // 2*(WT_W-1)+5 = 67 used
-constexpr int WTHREADS = 256;
+
 
 struct ThinWgArgs {
   ImgView thin;            // thin image (C <= 4), any strides
@@ -50,11 +50,11 @@ struct ThinWgSmem {
   static constexpr int B_BUF = WT_H * WT_W * 128;                    // 4 x 32 pixels x 32 channels fp32 = 16 KB
   static constexpr int PATCH = CB * WP_ROWS * WP_COLS * 4;
   static constexpr int OFF_B = 2 * A_BUF;                            // multiple of 1024
-  static constexpr int OFF_PATCH = OFF_B + 2 * B_BUF;
+  static constexpr int OFF_PATCH = OFF_B + 3 * B_BUF;
   static constexpr int OFF_BAR = OFF_PATCH + ((2 * PATCH + 15) & ~15);
   // the M = 128 MMA reads 16 KB per chunk whatever ROWS is: rows >= ROWS only feed accumulator rows that
   // are never read, but their addresses must stay inside the CTA's shared-memory window
-  static constexpr int TOTAL_MIN = OFF_BAR + 64;
+  static constexpr int TOTAL_MIN = OFF_BAR + 96;
   static constexpr int A_OVERREAD_END = A_BUF + (WT_H - 1) * A_CHUNK + 16384;
   static constexpr int TOTAL = TOTAL_MIN > A_OVERREAD_END ? TOTAL_MIN : A_OVERREAD_END;
 };
@@ -92,29 +92,58 @@ __device__ __forceinline__ void tma_tile_4d2(uint32_t dst, const CUtensorMap* ma
       : "memory");
 }
 
+// Builder warps (0-7) and one control warp (8) run the tile sequence decoupled by mbarriers: the builders stage
+// the next thin patch (cp.async), gather the im2col rows of the current one into A[buf] and arrive on
+// a_full[buf]; lane 0 of the control warp streams the fat tiles (TMA, 3 stages), issues the 16 MMAs of a tile as
+// soon as its A and B have landed and commits them to ab_free, which hands the A buffer back to the builders
+// and the B stage back to the TMA.  No thread ever waits for the single-thread MMA issue inside a barrier.
+constexpr int WBUILD = 256;                       // builder threads
+constexpr int WB_STAGES = 3;
+
+template <int CB, int T0, int T1>
+__device__ __forceinline__ void build_rows(unsigned char* __restrict__ abase, const float* __restrict__ prow0,
+                                           const uint32_t (&swz)[8], int pcol) {
+  // rows (tap, cb), tap in [T0, T1): every offset below is a compile-time constant except the swizzled column
+  float v[(T1 - T0) * CB];
+#pragma unroll
+  for (int tap = T0; tap < T1; ++tap)
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb)
+      v[(tap - T0) * CB + cb] = prow0[(cb * WP_ROWS + tap / 5) * WP_COLS + tap % 5];
+#pragma unroll
+  for (int tap = T0; tap < T1; ++tap)
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) {
+      const int r = tap * CB + cb;
+      *reinterpret_cast<float*>(abase + (r >> 3) * 1024 + (r & 7) * 128 + swz[r & 7]) = v[(tap - T0) * CB + cb];
+    }
+  (void)pcol;
+}
+
 template <int CB>
-__global__ void __launch_bounds__(WTHREADS, 2) thin_wgrad_tc_kernel(const __grid_constant__ CUtensorMap fat_map,
-                                                                 const ThinWgArgs a) {
+__global__ void __launch_bounds__(WBUILD + 32, 2) thin_wgrad_tc_kernel(const __grid_constant__ CUtensorMap fat_map,
+                                                                      const ThinWgArgs a) {
   bn_pdl_trigger();
   using S = ThinWgSmem<CB>;
   constexpr int ROWS = S::ROWS;
   extern __shared__ __align__(1024) unsigned char sm[];
-  typedef float (*Patch)[WP_ROWS][WP_COLS];
-  Patch patch[2] = {reinterpret_cast<Patch>(sm + S::OFF_PATCH), reinterpret_cast<Patch>(sm + S::OFF_PATCH + S::PATCH)};
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);    // [2] TMA landed
-  uint64_t* ab_free = b_full + 2;                                     // [2] MMAs that read A / B buffer s have retired
+  float* patch[2] = {reinterpret_cast<float*>(sm + S::OFF_PATCH), reinterpret_cast<float*>(sm + S::OFF_PATCH + S::PATCH)};
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);    // [WB_STAGES] TMA landed
+  uint64_t* a_full = b_full + WB_STAGES;                              // [2] builders done (one arrival per warp)
+  uint64_t* ab_free = a_full + 2;                                     // [2] MMAs of the tile that used A[s] retired
   uint64_t* done_bar = ab_free + 2;                                   // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    for (int s = 0; s < WB_STAGES; ++s) mbar_init(smem_u32(b_full + s), 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(b_full + s), 1);
+      mbar_init(smem_u32(a_full + s), WBUILD / 32);
       mbar_init(smem_u32(ab_free + s), 1);
     }
     mbar_init(smem_u32(done_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc<32>(smem_u32(tmem_ptr));
+  if (warp == 8) tmem_alloc<32>(smem_u32(tmem_ptr));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -130,98 +159,96 @@ __global__ void __launch_bounds__(WTHREADS, 2) thin_wgrad_tc_kernel(const __grid
     y0 = ty * WT_H;
     x0 = (tt - ty * a.tiles_x) * WT_W;
   };
-  auto issue_patch = [&](Patch dst, int f, int y0, int x0) {
-    for (int i = tid; i < CB * WP_ROWS * WP_COLS; i += WTHREADS) {
-      const int c = i / (WP_ROWS * WP_COLS);
-      const int rem = i - c * WP_ROWS * WP_COLS;
-      const int r = rem / WP_COLS, col = rem - r * WP_COLS;
-      const int y = 2 * y0 - a.pt + r, x = 2 * x0 - a.pl + col;
-      const bool ok = (unsigned)y < (unsigned)a.thin.H && (unsigned)x < (unsigned)a.thin.W;
-      const long long off = ok ? (long long)f * a.thin.sn + (long long)y * a.thin.sy + (long long)x * a.thin.sx +
-                                     (long long)c * a.thin.sc
-                               : 0;
-      cp_async4z(&dst[c][r][col], a.thin.p + off, ok);
-    }
-  };
-  auto issue_fat = [&](int buf, int f, int y0, int x0) {       // one thread
-    const uint32_t bar = smem_u32(b_full + buf);
-    mbar_expect_tx2(bar, (uint32_t)S::B_BUF);
-    tma_tile_4d2(sbase + S::OFF_B + buf * S::B_BUF, &fat_map, bar, c0, x0, y0, f);
-  };
+  const long long total = a.total_tiles;
+  int n_my = 0;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) ++n_my;
 
-  long long t = blockIdx.x;
-  int f, y0, x0;
-  if (t < a.total_tiles) {
-    decode(t, f, y0, x0);
-    issue_patch(patch[0], f, y0, x0);
-    if (tid == 0) issue_fat(0, f, y0, x0);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  const int prow = (tid & 127) >> 5, pcol = tid & 31;          // this thread's pixel of the 4 x 32 tile
-  const int half = tid >> 7;                                   // taps 0..12 / 13..24
-  int it = 0;
-  for (; t < a.total_tiles; t += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const long long tn = t + gridDim.x;
-    if (tn < a.total_tiles) {
-      int fn, yn, xn;
-      decode(tn, fn, yn, xn);
-      issue_patch(patch[buf ^ 1], fn, yn, xn);                 // its last readers finished before the previous barrier
-      if (tid == 0) {
-        // fat buffer buf^1 and A buffer buf^1 were last read by the MMAs of tile it-1
-        if (it >= 1) mbar_wait(smem_u32(ab_free + (buf ^ 1)), ((it - 1) >> 1) & 1);
-        issue_fat(buf ^ 1, fn, yn, xn);
+  if (warp < 8) {
+    // ======================= builders ============================================================
+    auto issue_patch = [&](float* dst, long long t) {
+      int f, y0, x0;
+      decode(t, f, y0, x0);
+      for (int i = tid; i < CB * WP_ROWS * WP_COLS; i += WBUILD) {
+        const int c = i / (WP_ROWS * WP_COLS);
+        const int rem = i - c * WP_ROWS * WP_COLS;
+        const int r = rem / WP_COLS, col = rem - r * WP_COLS;
+        const int y = 2 * y0 - a.pt + r, x = 2 * x0 - a.pl + col;
+        const bool ok = (unsigned)y < (unsigned)a.thin.H && (unsigned)x < (unsigned)a.thin.W;
+        const long long off = ok ? (long long)f * a.thin.sn + (long long)y * a.thin.sy + (long long)x * a.thin.sx +
+                                       (long long)c * a.thin.sc
+                                 : 0;
+        cp_async4z(dst + i, a.thin.p + off, ok);
       }
-    }
+    };
+    const int prow = (tid & 127) >> 5, pcol = lane;              // this thread's pixel of the 4 x 32 tile
+    const int half = tid >> 7;                                   // taps 0..12 / 13..24
+    uint32_t swz[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) swz[q] = (uint32_t)((((pcol >> 2) ^ q) << 4) + (pcol & 3) * 4);
+    long long t = blockIdx.x;
+    if (t < total) issue_patch(patch[0], t);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();                                           // patch[buf] is complete and visible
-    // A buffer buf was last read by the MMAs of tile it-2
-    if (it >= 2) mbar_wait(smem_u32(ab_free + buf), ((it - 2) >> 1) & 1);
-    {
+    for (int it = 0; it < n_my; ++it, t += gridDim.x) {
+      const int buf = it & 1;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // patch[buf] complete; everyone left patch[buf ^ 1]
+      if (it + 1 < n_my) issue_patch(patch[buf ^ 1], t + gridDim.x);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it >= 2) mbar_wait(smem_u32(ab_free + buf), ((it - 2) >> 1) & 1);     // MMAs of tile it - 2 retired
       unsigned char* abase = sm + buf * S::A_BUF + prow * S::A_CHUNK;
-      const int tap0 = half ? 13 : 0, tap1 = half ? 25 : 13;
-#pragma unroll 1
-      for (int tap = tap0; tap < tap1; ++tap) {
-        const int ky = tap / 5, kx = tap - ky * 5;
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb) {
-          const int r = tap * CB + cb;
-          const float v = patch[buf][cb][2 * prow + ky][2 * pcol + kx];
-          *reinterpret_cast<float*>(abase + (r >> 3) * 1024 + (r & 7) * 128 + ((((pcol >> 2) ^ (r & 7))) << 4) +
-                                    (pcol & 3) * 4) = v;
-        }
-      }
+      const float* prow0 = patch[buf] + (2 * prow) * WP_COLS + 2 * pcol;
+      if (half == 0) build_rows<CB, 0, 13>(abase, prow0, swz, pcol);
+      else build_rows<CB, 13, 25>(abase, prow0, swz, pcol);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(a_full + buf));
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(smem_u32(b_full + buf), (it >> 1) & 1);
-      tc_fence_after();
+  } else {
+    // ======================= control warp: fat-tile TMA + MMA issue ==============================
+    if (lane == 0) {
+      auto issue_fat = [&](int j) {                              // j-th tile of this CTA
+        int f, y0, x0;
+        decode(blockIdx.x + (long long)j * gridDim.x, f, y0, x0);
+        const int st = j % WB_STAGES;
+        const uint32_t bar = smem_u32(b_full + st);
+        mbar_expect_tx2(bar, (uint32_t)S::B_BUF);
+        tma_tile_4d2(sbase + S::OFF_B + st * S::B_BUF, &fat_map, bar, c0, x0, y0, f);
+      };
+      for (int j = 0; j < WB_STAGES - 1 && j < n_my; ++j) issue_fat(j);
       constexpr uint32_t idesc = make_idesc(128, 32) | (1u << 16);          // A K-major, B MN-major
-      const uint32_t sa = sbase + buf * S::A_BUF, sb = sbase + S::OFF_B + buf * S::B_BUF;
+      const uint64_t ad0 = desc_k_sw128(sbase), bd0 = desc_mn_sw128(sbase + S::OFF_B, 4096, 512);
+      for (int it = 0; it < n_my; ++it) {
+        const int buf = it & 1, st = it % WB_STAGES;
+        // stage (it + 2) % 3 was read by the MMAs of tile it - 1
+        if (it + WB_STAGES - 1 < n_my) {
+          if (it >= 1) mbar_wait(smem_u32(ab_free + (buf ^ 1)), ((it - 1) >> 1) & 1);
+          issue_fat(it + WB_STAGES - 1);
+        }
+        mbar_wait(smem_u32(a_full + buf), (it >> 1) & 1);
+        mbar_wait(smem_u32(b_full + st), (it / WB_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t ad = ad0 + (uint64_t)((buf * S::A_BUF) >> 4), bd = bd0 + (uint64_t)((st * S::B_BUF) >> 4);
 #pragma unroll
-      for (int kc = 0; kc < WT_H; ++kc)
+        for (int kc = 0; kc < WT_H; ++kc)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_tf32(tmem_base, desc_k_sw128(sa + kc * S::A_CHUNK + k * 32),
-                    desc_mn_sw128(sb + kc * 4096 + k * 1024, 4096, 512), idesc, (it | kc | k) != 0 ? 1u : 0u);
-      umma_commit(smem_u32(ab_free + buf));
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base, ad + (uint64_t)((kc * S::A_CHUNK + k * 32) >> 4), bd + (uint64_t)((kc * 4096 + k * 1024) >> 4),
+                      idesc, (it | kc | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(ab_free + buf));
+      }
+      umma_commit(smem_u32(done_bar));
     }
+    __syncwarp();
   }
   // ---- epilogue: this CTA's slice [(tap, cb)][cs] of the partial buffer
-  if (tid == 0) umma_commit(smem_u32(done_bar));
   __syncthreads();
-  if (it > 0) {
+  if (n_my > 0) {
     mbar_wait(smem_u32(done_bar), 0);
     tc_fence_after();
   }
   if (warp < 4) {
-    const int lane = tid & 31;
     uint32_t r[32];
-    if (it > 0) {
+    if (n_my > 0) {
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
       tmem_ld_wait();
     } else {
@@ -235,7 +262,7 @@ __global__ void __launch_bounds__(WTHREADS, 2) thin_wgrad_tc_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc<32>(tmem_base);
   }
@@ -306,7 +333,7 @@ int launch(const CUtensorMap& map, const ThinWgArgs& a, int blocks, int cgroups,
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  BN_CUDA(bn_launch(kern, dim3(blocks, cgroups), WTHREADS, S::TOTAL, st, map, a));
+  BN_CUDA(bn_launch(kern, dim3(blocks, cgroups), WBUILD + 32, S::TOTAL, st, map, a));
   BN_LAUNCHED();
   return 0;
 }
@@ -315,6 +342,327 @@ template <int CB>
 int resident_ctas() {
   const int per = (227 * 1024) / (ThinWgSmem<CB>::TOTAL + 1024);
   return per > 3 ? 3 : (per < 1 ? 1 : per);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Last decoder layer forward (ConvTranspose2d k5 s2 into 1-4 image channels + sigmoid + fused reconstruction
+// loss, aes.py:463-470 + losses.py:36-96) as ONE small GEMM plus a col2im epilogue.
+//
+// With so few output channels the transposed convolution is cheapest the other way round: first
+//     P[(cb, tap), p] = sum_ci  W[ci][cb][tap] * small[p, ci]          (p = small pixel)
+// for ALL 25 taps at once -- D[128 x 256] (TMEM) = A[128 x 32] * B[256 x 32]^T with the 25*CB weight rows as
+// the M operand and 14 x 18 small pixels (one tiled TMA copy, zero fill outside the image, K-major rows of 32
+// channels) as the N operand, 4 MMAs per tile, every small pixel read from shared memory ONCE -- and then
+//     out[Y, X, cb] = sum over the <= 9 taps with the right parities of  P[(cb, tap), ((Y + pt - ky) / 2, (X + pl - kx) / 2)]
+// in the epilogue (768 output pixels per tile, ~6 shared-memory reads each), followed by bias, sigmoid, the
+// per-chunk sum of squared errors and dL/d(pre-sigmoid).  The FP32 kernel it replaces (thin_dgrad5_kernel)
+// spends 800*CB FMAs plus 34 LDS.128 per 100 FMAs per output quad and runs at a fifth of the HBM rate.
+// Used by the fused training pass only (bn_cae_decode with a target and no x_hat output): the reconstruction a
+// caller ASKS for is still computed by the fp32 kernel, so the 1e-4 reconstruction contract is untouched.
+// ------------------------------------------------------------------------------------------------
+constexpr int OT_H = 24, OT_W = 32;                 // output tile
+constexpr int ST_H = OT_H / 2 + 2, ST_W = OT_W / 2 + 2;   // 14 x 18 small pixels (one-pixel halo each side)
+constexpr int ST_PIX = ST_H * ST_W;                 // 252 (MMA N = 256)
+constexpr int P_STRIDE = 260;                       // floats per P row: conflict-free float4 stores per lane
+constexpr int DG_EPI_WARPS = 8;                     // epilogue warps 0-7; warp 8 TMA producer, warp 9 MMA issuer
+constexpr int DG_THREADS = (DG_EPI_WARPS + 2) * 32;
+constexpr int DG_STAGES = 3;
+constexpr int DG_BSTAGE = 256 * 128;                // 32 KB: 256 rows x 32 channels (rows >= 252 never written)
+
+struct ThinDgArgs {
+  int Hs, Ws, Hb, Wb, pt, pl, n;
+  const float* wdt;        // [cb][tap][32] TF32-rounded
+  const float* bias;
+  float* xhat_ws;          // (n, CB, Hb, Wb)
+  const float* target;     // (n, CB, Hb, Wb)
+  const float* mask;       // same or NULL
+  int chunk_size, frame_offset, n_total;
+  float coef;
+  double* sse;
+  float* dpre;             // (n, Hb, Wb, CB)
+  int tiles_x, tiles_per_frame;
+  long long total_tiles;
+};
+
+template <int CB>
+struct ThinDgSmem {
+  static constexpr int OFF_B = 16384;                                   // A: 128 rows x 128 B
+  static constexpr int OFF_P = OFF_B + DG_STAGES * DG_BSTAGE;
+  static constexpr int P_BYTES = 25 * CB * P_STRIDE * 4;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 8 * (2 * DG_STAGES + 4) + 16;
+};
+
+// PTO / PLO = parities of the crop offsets: they decide at compile time which taps feed which pixel of a
+// thread's 2 x 2 output quad, so the col2im sum is 25 shared-memory reads at constant offsets.
+template <int CB, int PTO, int PLO>
+__global__ void __launch_bounds__(DG_THREADS, 1) thin_dgrad_tc_kernel(const __grid_constant__ CUtensorMap small_map,
+                                                                       const ThinDgArgs a) {
+  bn_pdl_trigger();
+  using S = ThinDgSmem<CB>;
+  extern __shared__ __align__(1024) unsigned char sm[];
+  float* P = reinterpret_cast<float*>(sm + S::OFF_P);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);      // [DG_STAGES]
+  uint64_t* b_empty = b_full + DG_STAGES;                               // [DG_STAGES]
+  uint64_t* acc_full = b_empty + DG_STAGES;                             // [2]
+  uint64_t* acc_empty = acc_full + 2;                                   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < DG_STAGES; ++s) {
+      mbar_init(smem_u32(b_full + s), 1);
+      mbar_init(smem_u32(b_empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(acc_full + s), 1);
+      mbar_init(smem_u32(acc_empty + s), DG_EPI_WARPS);     // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == DG_EPI_WARPS + 1) tmem_alloc<512>(smem_u32(tmem_ptr));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t sbase = smem_u32(sm);
+  bn_pdl_wait();
+  // A tile: weight row (cb, tap) sits at row (tap / 7) * 32 + cb * 7 + tap % 7, so that the four TMEM lane
+  // quarters (one per epilogue warp pair) each hold a quarter of the taps; all other rows are zero
+  for (int i = tid; i < 128 * 8; i += DG_THREADS) {
+    const int row = i >> 3, c = i & 7;
+    const int w4 = row >> 5, l = row & 31;
+    const int cb = l / 7, j = l - cb * 7;
+    const int tap = 7 * w4 + j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cb < CB && tap < 25) v = __ldg(reinterpret_cast<const float4*>(a.wdt + ((long long)cb * 25 + tap) * 32) + c);
+    *reinterpret_cast<float4*>(sm + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)) = v;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const long long total = a.total_tiles;
+  auto decode = [&](long long T, int& f, int& Y0, int& X0) {
+    f = (int)(T / a.tiles_per_frame);
+    const int tt = (int)(T - (long long)f * a.tiles_per_frame);
+    const int ty = tt / a.tiles_x;
+    Y0 = ty * OT_H;
+    X0 = (tt - ty * a.tiles_x) * OT_W;
+  };
+
+  if (warp == DG_EPI_WARPS) {
+    // ======================= TMA producer ========================================================
+    if (lane == 0) {
+      int bi = 0;
+      for (long long T = blockIdx.x; T < total; T += gridDim.x, ++bi) {
+        const int stage = bi % DG_STAGES;
+        if (bi >= DG_STAGES) mbar_wait(smem_u32(b_empty + stage), ((bi / DG_STAGES) - 1) & 1);
+        int f, Y0, X0;
+        decode(T, f, Y0, X0);
+        const int sy_lo = (Y0 + a.pt - 3) >> 1, sx_lo = (X0 + a.pl - 3) >> 1;      // ceil((v - 4) / 2)
+        const uint32_t bar = smem_u32(b_full + stage);
+        mbar_expect_tx2(bar, (uint32_t)(ST_PIX * 128));
+        tma_tile_4d2(sbase + S::OFF_B + stage * DG_BSTAGE, &small_map, bar, 0, sx_lo, sy_lo, f);
+      }
+    }
+    __syncwarp();
+  } else if (warp == DG_EPI_WARPS + 1) {
+    // ======================= MMA issuer ==========================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 256);
+      const uint64_t ad0 = desc_k_sw128(sbase), bd0 = desc_k_sw128(sbase + S::OFF_B);
+      int bi = 0;
+      for (long long T = blockIdx.x; T < total; T += gridDim.x, ++bi) {
+        const int stage = bi % DG_STAGES, buf = bi & 1;
+        if (bi >= 2) {
+          mbar_wait(smem_u32(acc_empty + buf), ((bi >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(b_full + stage), (bi / DG_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t bd = bd0 + (uint64_t)((stage * DG_BSTAGE) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_tf32(tmem_base + buf * 256, ad0 + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        umma_commit(smem_u32(b_empty + stage));
+        umma_commit(smem_u32(acc_full + buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue: TMEM -> P (shared) -> col2im + sigmoid + loss ==============
+    // copy role: warp w drains TMEM lanes 32 (w & 3) .., column blocks 4 (w >> 2) .. + 3
+    const int w4 = warp & 3, chalf = warp >> 2;
+    const int cbl = lane / 7, jl = lane - cbl * 7;
+    const int my_tap = 7 * w4 + jl;
+    const bool my_valid = cbl < CB && my_tap < 25;
+    float* prow = P + (cbl * 25 + my_tap) * P_STRIDE + chalf * 128;
+    // col2im role: thread q < 192 owns the 2 x 2 output quad (qy, qx) of the 24 x 32 tile
+    const int qy = tid >> 4, qx = tid & 15;
+    const bool has_quad = tid < (OT_H / 2) * (OT_W / 2);
+    // small pixel of tap (ky, kx) for output (2 qy + py, 2 qx + px):  qy + (py + PTO - ky) / 2 + cy  (same in x), with
+    // cy = (pt - PTO) / 2 - floor((pt - 3) / 2): the distance of the quad grid from the staged tile's origin
+    const int cy = ((a.pt - PTO) >> 1) - ((a.pt - 3) >> 1), cx = ((a.pl - PLO) >> 1) - ((a.pl - 3) >> 1);
+    const float* pq = P + (qy + cy) * ST_W + (qx + cx);
+    float bias[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) bias[c] = a.bias ? __ldg(a.bias + c) : 0.f;
+    double my_sse = 0.0;
+    int cur_chunk = -1;
+    auto flush = [&]() {
+      if (a.target == nullptr || cur_chunk < 0) return;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) my_sse += __shfl_xor_sync(0xffffffffu, my_sse, o);
+      if (lane == 0 && my_sse != 0.0) atomicAdd(a.sse + cur_chunk, my_sse);
+      my_sse = 0.0;
+    };
+    int bi = 0;
+    for (long long T = blockIdx.x; T < total; T += gridDim.x, ++bi) {
+      const int buf = bi & 1;
+      int f, Y0, X0;
+      decode(T, f, Y0, X0);
+      const int chunk = (f + a.frame_offset) / a.chunk_size;
+      if (chunk != cur_chunk) {
+        flush();
+        cur_chunk = chunk;
+      }
+      const int len = min(a.chunk_size, a.n_total - chunk * a.chunk_size);
+      const float gsc = a.coef / (float)len;
+      // this thread's targets / masks, fetched before waiting for the accumulator
+      const int Yq = Y0 + 2 * qy, Xq = X0 + 2 * qx;
+      float tg[2][2][CB], mk[2][2][CB];
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+          const bool ok = has_quad && Yq + py < a.Hb && Xq + px < a.Wb;
+#pragma unroll
+          for (int c = 0; c < CB; ++c) {
+            const long long inchw = (((long long)f * CB + c) * a.Hb + Yq + py) * a.Wb + Xq + px;
+            tg[py][px][c] = (ok && a.target) ? __ldg(a.target + inchw) : 0.f;
+            mk[py][px][c] = (ok && a.mask) ? __ldg(a.mask + inchw) : 1.f;
+          }
+        }
+      mbar_wait(smem_u32(acc_full + buf), (bi >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(w4 * 32) << 16) + buf * 256 + chalf * 128 + jb * 32, r);
+        tmem_ld_wait();
+        if (my_valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(prow + jb * 32 + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(acc_empty + buf));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (has_quad) {
+        float acc[2][2][CB];
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+          for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[py][px][c] = bias[c];
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int py = (ky + PTO) & 1;                       // the quad row this tap row feeds
+          const int dy = (py + PTO - ky) / 2;                  // exact: same parity (C++ division of an even number)
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx) {
+            const int px = (kx + PLO) & 1;
+            const int dx = (px + PLO - kx) / 2;
+#pragma unroll
+            for (int c = 0; c < CB; ++c)
+              acc[py][px][c] += pq[((c * 25 + ky * 5 + kx) * P_STRIDE) + dy * ST_W + dx];
+          }
+        }
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            const int Y = Yq + py, X = Xq + px;
+            if (Y < a.Hb && X < a.Wb) {
+#pragma unroll
+              for (int c = 0; c < CB; ++c) {
+                const float v = 1.f / (1.f + expf(-acc[py][px][c]));
+                const long long inchw = (((long long)f * CB + c) * a.Hb + Y) * a.Wb + X;
+                a.xhat_ws[inchw] = v;
+                if (a.target) {
+                  const float d = v - tg[py][px][c];
+                  my_sse += (double)(d * d * mk[py][px][c]);
+                  a.dpre[(((long long)f * a.Hb + Y) * a.Wb + X) * CB + c] = gsc * d * mk[py][px][c] * v * (1.f - v);
+                }
+              }
+            }
+          }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // P is free for the next tile
+    }
+    flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == DG_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+std::vector<std::pair<MapKey, CUtensorMap>> g_dg_maps;
+
+// NHWC fp32 image (32 channels) as (C, W, H, N); box = 32 channels x 18 pixels x 14 rows, SWIZZLE_128B (K-major rows)
+bool small_map(const float* p, int n, int H, int W, int C, CUtensorMap* out) {
+  MapKey key{p, n, H, W, C};
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_dg_maps)
+    if (kv.first == key) { *out = kv.second; return true; }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)ST_W, (cuuint32_t)ST_H, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  if (g_enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (g_dg_maps.size() >= 64) g_dg_maps.clear();
+  g_dg_maps.emplace_back(key, m);
+  *out = m;
+  return true;
+}
+
+template <int CB, int PTO, int PLO>
+int launch_dg2(const CUtensorMap& map, const ThinDgArgs& a, cudaStream_t st) {
+  using S = ThinDgSmem<CB>;
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory per CTA");
+  auto kern = thin_dgrad_tc_kernel<CB, PTO, PLO>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  const long long blocks = a.total_tiles < 148 ? a.total_tiles : 148;
+  BN_CUDA(bn_launch(kern, dim3((unsigned)blocks), DG_THREADS, S::TOTAL, st, map, a));
+  BN_LAUNCHED();
+  return 0;
+}
+
+template <int CB>
+int launch_dg(const CUtensorMap& map, const ThinDgArgs& a, cudaStream_t st) {
+  switch ((a.pt & 1) * 2 + (a.pl & 1)) {
+    case 0: return launch_dg2<CB, 0, 0>(map, a, st);
+    case 1: return launch_dg2<CB, 0, 1>(map, a, st);
+    case 2: return launch_dg2<CB, 1, 0>(map, a, st);
+    default: return launch_dg2<CB, 1, 1>(map, a, st);
+  }
 }
 
 }  // namespace
@@ -358,4 +706,33 @@ int bn_launch_thin_wgrad_tc(const ImgView& big, const float* small, const ConvGe
   }
   if (r) return r;
   return bn_launch_wgrad_reduce(partial, (int)blocks, Ktot, g.Cs, g.Cb, 25, g.d_fprop, grad, st);
+}
+
+// Last decoder layer forward with the fused reconstruction loss, tensor-core form (training pass only: needs a
+// target, writes x_hat to the workspace copy).  Returns 1 when the geometry is not covered.
+int bn_launch_thin_dgrad_tc(const float* small, const ConvGeom& g, const float* wdt, const float* bias, int n,
+                            float* xhat_ws, const float* target, const float* mask, int chunk_size, int frame_offset,
+                            int n_total, float grad_coef, double* sse, float* dpre, cudaStream_t st) {
+  if (n <= 0 || target == nullptr) return 1;
+  if (!(g.k == 5 && g.s == 2 && g.Cb >= 1 && g.Cb <= 4 && g.Cs == 32)) return 1;
+  if (g.pt < 0 || g.pl < 0 || g.pt > 4 || g.pl > 4) return 1;
+  if (((uintptr_t)small & 127) || ((uintptr_t)wdt & 15) || !have_tma()) return 1;
+  static const bool off = [] { const char* e = getenv("BN_THIN_DGRAD_TC"); return e && e[0] == '0'; }();
+  if (off) return 1;
+  CUtensorMap map;
+  if (!small_map(small, n, g.Hs, g.Ws, g.Cs, &map)) return 1;
+  ThinDgArgs a;
+  a.Hs = g.Hs; a.Ws = g.Ws; a.Hb = g.Hb; a.Wb = g.Wb; a.pt = g.pt; a.pl = g.pl; a.n = n;
+  a.wdt = wdt; a.bias = bias; a.xhat_ws = xhat_ws; a.target = target; a.mask = mask;
+  a.n_total = n_total > 0 ? n_total : n; a.frame_offset = frame_offset;
+  a.chunk_size = chunk_size > 0 ? chunk_size : a.n_total; a.coef = grad_coef; a.sse = sse; a.dpre = dpre;
+  a.tiles_x = bn_cdiv(g.Wb, OT_W);
+  a.tiles_per_frame = a.tiles_x * bn_cdiv(g.Hb, OT_H);
+  a.total_tiles = (long long)a.tiles_per_frame * n;
+  switch (g.Cb) {
+    case 1: return launch_dg<1>(map, a, st);
+    case 2: return launch_dg<2>(map, a, st);
+    case 3: return launch_dg<3>(map, a, st);
+    default: return launch_dg<4>(map, a, st);
+  }
 }

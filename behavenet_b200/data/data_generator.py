@@ -73,7 +73,9 @@ class ArraySource:
         return int(self._data[self.signals[0]][idx].shape[0])
 
     def load(self, signal, idx, lo=0, hi=None):
-        return np.asarray(self._data[signal][idx][lo:hi])
+        # a fresh copy per call, like the reference's per-trial HDF5 read: in-place transforms (ZScore,
+        # Threshold, ...) run on the returned array in the worker thread and must not touch the caller's data
+        return np.array(self._data[signal][idx][lo:hi], copy=True)
 
 
 class HDF5Source:

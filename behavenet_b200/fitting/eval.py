@@ -11,14 +11,25 @@ format for callers that want files.
 import numpy as np
 
 
-def _latents_of(model, frames):
-    out = model.encoding(frames, dataset=None)
-    if model.hparams.get('model_class') == 'ps-vae':
-        import torch
-        return torch.cat([out[0], out[1]], dim=1)          # eval.py:75-76
-    if model.hparams.get('model_class') == 'msps-vae':
-        import torch
-        return torch.cat([out[0], out[1], out[2]], dim=1)  # vaes.py:1255-1266
+def _latents_of(model, frames, labels_2d=None, dataset=None):
+    """Latents of a batch of frames the way the reference's export loop forms them (eval.py:50-98): the one-hot
+    label images join the frames of a conditional encoder (51-55, 70-71, 87-88), PS-VAE / MSPS-VAE concatenate
+    their subspaces (75-76; vaes.py:1255-1266), and the latents of an AE with matrix subspace projection are
+    exported in the [labels | rest] basis ``model.U`` (79-81, 95-97)."""
+    import torch
+    mc = model.hparams.get('model_class')
+    if mc == 'cond-ae' and model.hparams.get('conditional_encoder', False):
+        if labels_2d is None:
+            raise KeyError("a conditional encoder needs data['labels_sc'] (one-hot label images) next to the frames")
+        frames = torch.cat((frames.float() if frames.dtype != torch.float32 else frames,
+                            labels_2d.to(frames.device, torch.float32)), dim=1)
+    out = model.encoding(frames.contiguous(), dataset=dataset)
+    if mc == 'ps-vae':
+        return torch.cat([out[0], out[1]], dim=1)
+    if mc == 'msps-vae':
+        return torch.cat([out[0], out[1], out[2]], dim=1)
+    if mc == 'cond-ae-msp':
+        return model.U(out[0])
     return out[0]
 
 
@@ -84,11 +95,15 @@ def encode_trials(model, trials, frames_per_launch=4096, device=None):
 
 def export_latents(data_generator, model, filename=None):
     """Reference-compatible export (eval.py:6-118): one pickle per dataset with
-    ``{'latents': [per-trial arrays, gap trials empty], 'trials': dataset.batch_idxs}``."""
+    ``{'latents': [per-trial arrays, gap trials empty], 'trials': dataset.batch_idxs}``.  The multi-session
+    PS-VAE rebuilds a single-session generator over every trial first (eval.py:33-35 -> vaes.py:1202-1273)."""
     import os
     import pickle
     import torch
+    if model.hparams.get('model_class') == 'msps-vae' and getattr(data_generator, 'n_sessions_per_batch', 1) > 1:
+        return model.export_latents(data_generator, filename=filename)
     model.eval()
+    cond_enc = model.hparams.get('model_class') == 'cond-ae' and model.hparams.get('conditional_encoder', False)
     latents = [[np.array([]) for _ in range(ds.n_trials)] for ds in data_generator.datasets]
     with torch.no_grad():
         for dtype in ['train', 'val', 'test']:
@@ -97,7 +112,9 @@ def export_latents(data_generator, model, filename=None):
                 data, sess = data_generator.next_batch(dtype)
                 y = data['images'][0]
                 idx = data['batch_idx'].item() if hasattr(data['batch_idx'], 'item') else int(data['batch_idx'])
-                latents[sess][idx] = _latents_of(model, y).cpu().numpy()
+                # (the reference walks > 200-frame trials in chunks to fit its GPU; one launch sequence here)
+                latents[sess][idx] = _latents_of(model, y, data['labels_sc'][0] if cond_enc else None,
+                                                 dataset=sess).cpu().numpy()
     filenames = []
     for sess, ds in enumerate(data_generator.datasets):
         if filename is None:
@@ -105,6 +122,7 @@ def export_latents(data_generator, model, filename=None):
             fname = os.path.join(model.hparams['expt_dir'], 'version_%i' % model.version, sess_id)
         else:
             fname = filename
+        print('saving latents %i of %i:\n%s' % (sess + 1, data_generator.n_datasets, fname))
         with open(fname, 'wb') as f:
             pickle.dump({'latents': latents[sess], 'trials': ds.batch_idxs}, f)
         filenames.append(fname)

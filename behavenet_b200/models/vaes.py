@@ -777,6 +777,17 @@ class MSPSVAE(PSVAE):
         return out.cpu().detach().numpy() if as_numpy else out
 
     def export_latents(self, data_gen, filename=None):
-        """Latents of every trial as [z_s, z_b, z_u] (vaes.py:1202-1273), through the shared exporter."""
+        """Latents of every trial as [z_s, z_b, z_u] (vaes.py:1202-1273).  Like the reference, the multi-session
+        generator (whose training calls serve groups of trials from different sessions) is replaced by a
+        single-session generator over the same sessions with every trial in the training split
+        (``n_sessions_per_batch = 1``, ``train_frac = 1``, ``trial_splits = '1;0;0;0'``), so no trial is skipped."""
+        from behavenet_b200.data.data_generator import PrefetchSessionsGenerator
         from behavenet_b200.fitting.eval import export_latents
-        return export_latents(data_gen, self, filename=filename)
+        single = PrefetchSessionsGenerator(
+            [ds.source for ds in data_gen.datasets], device=data_gen.device, rng_seed=0,
+            trial_splits={'train_tr': 1, 'val_tr': 0, 'test_tr': 0, 'gap_tr': 0}, train_frac=1.0,
+            raw_uint8=getattr(data_gen, 'raw_uint8', False), transforms=getattr(data_gen, 'transforms', None))
+        try:
+            return export_latents(single, self, filename=filename)
+        finally:
+            single.close()

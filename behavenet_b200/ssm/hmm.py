@@ -336,6 +336,7 @@ class HMM:
     def __getstate__(self):
         st = dict(self.__dict__)
         st.pop('_cache', None)
+        st.pop('_blob_cache', None)
         return st
 
     # -- ssm-style accessors --------------------------------------------------------------------
@@ -371,11 +372,20 @@ class HMM:
 
     def _stage(self, datas):
         datas = _as_list(datas)
-        # identity of the arrays + a small content fingerprint; the cache keeps the arrays alive so
-        # their ids cannot be recycled while it is valid
+        # identity of the arrays + a content fingerprint (first / middle / last row of up to 64 evenly spaced
+        # trials, plus the very first and last rows): reusing a list whose arrays were modified IN PLACE
+        # (normalised, re-scaled, ...) re-stages; the cache keeps the arrays alive so their ids cannot be
+        # recycled while it is valid.  ``clear_cache()`` drops it explicitly.
         key = tuple((id(d), d.shape[0]) for d in datas)
-        if datas and datas[0].size and datas[-1].size:
-            key += (datas[0][0].tobytes(), datas[-1][-1].tobytes())
+        if datas:
+            import zlib
+            crc = 0
+            step = max(1, len(datas) // 64)
+            for d in list(datas[::step]) + [datas[-1]]:
+                if d.size:
+                    T = d.shape[0]
+                    crc = zlib.crc32(np.ascontiguousarray(d[[0, T // 2, T - 1]]).tobytes(), crc)
+            key += (crc,)
         cache = self.__dict__.setdefault('_cache', {})
         if cache.get('key') != key:
             for d in datas:
@@ -401,21 +411,34 @@ class HMM:
         return self._run_estep(staged, True)
 
     def _blob(self, device):
+        """Device copy of the packed parameters (fp64 Cholesky whitening + TF32 hi/lo split on the host),
+        cached by parameter CONTENT: an E-step, a log-likelihood and a Viterbi pass between two M-steps share
+        one pack + one host->device copy instead of repeating both per call."""
         import torch
+        import zlib
         o = self.observations
         K, D, L = self.K, self.D, o.lags
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
+            self.init_state_distn.log_pi0 - _logsumexp(self.init_state_distn.log_pi0),
+            self.transitions.log_Ps - _logsumexp(self.transitions.log_Ps, axis=1, keepdims=True),
+            o.As, o.bs, o.Sigmas)]
+        crc = 0
+        for a in arrs:
+            crc = zlib.crc32(a.tobytes(), crc)
+        key = (K, D, L, crc, sum(a.size for a in arrs), str(device))
+        cached = self.__dict__.get('_blob_cache')
+        if cached is not None and cached[0] == key:
+            return cached[1]
         lib = _lib.lib()
         nbytes = lib.bn_arhmm_params_bytes(K, D, L)
         if nbytes == 0:
             raise _lib.NativeLibraryError(lib.bn_last_error().decode())
         host = np.zeros(nbytes, np.uint8)
-        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (
-            self.init_state_distn.log_pi0 - _logsumexp(self.init_state_distn.log_pi0),
-            self.transitions.log_Ps - _logsumexp(self.transitions.log_Ps, axis=1, keepdims=True),
-            o.As, o.bs, o.Sigmas)]
         _lib.check(lib.bn_arhmm_pack_params(K, D, L, *[a.ctypes.data for a in arrs], host.ctypes.data),
                    'bn_arhmm_pack_params')
-        return torch.from_numpy(host).to(device)
+        blob = torch.from_numpy(host).to(device)
+        self.__dict__['_blob_cache'] = (key, blob)
+        return blob
 
     def _run_estep(self, st, want_post, shard=None):
         """Run the E-step kernels over trials [shard) and return device tensors."""

@@ -139,6 +139,10 @@ int bn_cae_encode_bwd(bn_cae_plan* plan, int n, const float* d_x, const float* d
  *   op:   0 = forward (bias + the layer's activation), 1 = backward-data (no activation mask),
  *         2 = weight gradient (d_in = big image, d_in2 = small image, d_out = torch-layout gradient,
  *             ACCUMULATES)
+ *         3 = last decoder layer forward with the fused loss (side 1, layer n_layers - 1; reference chunks of
+ *             200 frames, -gaussian_ll coefficient): d_in = small image, d_in2 = target (n, C, H, W);
+ *             d_out = [x_hat (n C H W floats) | dL/d(pre-sigmoid) (n H W C floats) | per-chunk sums of squared
+ *             errors (ceil(n / 200) doubles)]
  * "big"/"small" are the conv-input-side / conv-output-side images of the layer. */
 int bn_cae_layer_op(bn_cae_plan* plan, int side, int layer, int op, int n, const float* d_in,
                     const float* d_in2, float* d_out, const float* const* d_params,

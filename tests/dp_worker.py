@@ -32,6 +32,8 @@ def main(outdir):
     rank = int(os.environ['RANK'])
     torch.cuda.set_device(0)
     assert parallel.init('gloo')
+    from behavenet_b200 import _lib
+    _lib.lib().bn_set_tensor_core_mode(0)
     g = torch.Generator().manual_seed(3)
     cases = {}
     hp = co.make_hparams(1, 64, 48, 6)

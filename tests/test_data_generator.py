@@ -2,6 +2,8 @@
 outputs of the reference's own ``split_trials``, epoch coverage, frame sharding; on a GPU also the pinned /
 side-stream prefetch path and the raw-uint8 hand-off to the encoder."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -230,6 +232,93 @@ def test_export_states_and_latents_file_formats(tmp_path):
     out = export_states(hp, gen, Batched())
     assert out[0].endswith('version_0/l_e_a_s_states.pkl')
     gen.close()
+
+
+def test_export_latents_branches_and_file_format(tmp_path):
+    """export_latents (reference eval.py:6-118) with stand-in models on the CPU: the pickle layout, gap trials left
+    empty, ``dataset=sess`` passed to the encoder, a conditional encoder fed frames + one-hot label images
+    (eval.py:51-55, 70-71), AE-MSP latents exported through ``model.U`` (eval.py:79-81), PS-VAE subspaces
+    concatenated (75-76), and the multi-session PS-VAE re-reading every trial through a single-session generator
+    (vaes.py:1202-1273)."""
+    import pickle
+    import torch
+    from behavenet_b200.fitting.eval import export_latents
+    from behavenet_b200.data import PrefetchSessionsGeneratorMulti
+    from behavenet_b200.models.vaes import MSPSVAE
+    rng = np.random.RandomState(0)
+    lens = [int(rng.randint(3, 7)) for _ in range(12)]
+
+    def source(tag):
+        return ArraySource({'images': [rng.rand(T, 1, 4, 4).astype(np.float32) for T in lens],
+                            'labels_sc': [rng.rand(T, 2, 4, 4).astype(np.float32) for T in lens]},
+                           lab='l', expt='e', animal='a', session=tag)
+    src = source('s0')
+    splits = {'train_tr': 2, 'val_tr': 1, 'test_tr': 1, 'gap_tr': 1}
+    gen = PrefetchSessionsGenerator([src], device='cpu', rng_seed=0, trial_splits=splits)
+
+    class Enc:
+        def __init__(self, outs):
+            self.outs, self.seen = outs, []
+
+        def __call__(self, x, dataset=None):
+            self.seen.append((tuple(x.shape[1:]), dataset))
+            m = x.reshape(x.shape[0], -1).mean(1, keepdim=True)
+            return tuple(m * (i + 1) for i in range(self.outs)) + ([], [])
+
+    class Model:
+        version = 0
+
+        def __init__(self, mc, outs=1, **hp):
+            self.hparams = dict(model_class=mc, expt_dir=str(tmp_path), n_ae_latents=outs, **hp)
+            self.encoding = Enc(outs)
+
+        def eval(self):
+            return self
+
+        def U(self, z):
+            return -z
+
+    def run(model, g=gen):
+        f = tmp_path / ('%s.pkl' % model.hparams['model_class'])
+        assert export_latents(g, model, filename=str(f)) == [str(f)]
+        with open(f, 'rb') as fh:
+            d = pickle.load(fh)
+        assert set(d) == {'latents', 'trials'} and len(d['latents']) == 12
+        return d
+
+    d = run(Model('ae'))
+    used = np.concatenate([d['trials'][k] for k in ('train', 'val', 'test')])
+    assert 0 < len(used) < 12
+    for i in range(12):
+        if i in used:
+            np.testing.assert_allclose(d['latents'][i][:, 0], src.load('images', i).reshape(lens[i], -1).mean(1), rtol=1e-6)
+        else:
+            assert d['latents'][i].size == 0
+    m = Model('cond-ae', conditional_encoder=True)
+    d = run(m)
+    assert all(shape == (3, 4, 4) and ds == 0 for shape, ds in m.encoding.seen)      # 1 frame + 2 label channels
+    i = int(used[0])
+    both = np.concatenate([src.load('images', i), src.load('labels_sc', i)], 1)
+    np.testing.assert_allclose(d['latents'][i][:, 0], both.reshape(lens[i], -1).mean(1), rtol=1e-6)
+    d = run(Model('cond-ae-msp'))
+    np.testing.assert_allclose(d['latents'][i][:, 0], -src.load('images', i).reshape(lens[i], -1).mean(1), rtol=1e-6)
+    d = run(Model('ps-vae', outs=2))
+    assert d['latents'][i].shape == (lens[i], 2)
+    gen.close()
+    # multi-session PS-VAE: the multi generator serves groups and skips trials; the export must not
+    srcs = [source('s0'), source('s1')]
+    multi = PrefetchSessionsGeneratorMulti(srcs, n_sessions_per_batch=2, device='cpu', rng_seed=0, trial_splits=splits)
+    msps = Model('msps-vae', outs=3)
+    msps.export_latents = lambda g, filename=None: MSPSVAE.export_latents(msps, g, filename=filename)
+    (tmp_path / 'version_0').mkdir()
+    out = export_latents(multi, msps)
+    assert [os.path.basename(f) for f in out] == ['l_e_a_s0_latents.pkl', 'l_e_a_s1_latents.pkl']
+    for f, sr in zip(out, srcs):
+        with open(f, 'rb') as fh:
+            d = pickle.load(fh)
+        assert len(d['trials']['train']) == 12 and all(a.shape == (lens[j], 3) for j, a in enumerate(d['latents']))
+        np.testing.assert_allclose(d['latents'][5][:, 1], 2 * sr.load('images', 5).reshape(lens[5], -1).mean(1), rtol=1e-6)
+    multi.close()
 
 
 def test_get_reconstruction_dispatch_per_model_class():

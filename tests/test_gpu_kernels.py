@@ -142,3 +142,34 @@ def test_thin_layer_weight_gradient_tensor_core_matches_cuda_core(side, layer, g
     assert torch.isfinite(tc).all()
     err = float((tc - ref).abs().max() / ref.abs().max())
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize('n_ch', [1, 2, 4])
+@pytest.mark.parametrize('geom', [(32, 128, 128), (7, 64, 48), (50, 96, 80), (256, 128, 128)])
+def test_output_layer_forward_with_fused_loss_tensor_core_matches_cuda_core(geom, n_ch):
+    """Last decoder layer forward + sigmoid + fused loss: the GEMM-over-all-taps + col2im kernel (cae_thin_tc.cu)
+    against the fp32 kernel on TF32-exact data: x_hat, dL/d(pre-sigmoid) and the per-chunk sums of squared
+    errors (two reference chunks at 256 frames)."""
+    n, h, w = geom
+    if n_ch == 4 and n == 256:
+        pytest.skip('4-channel frames at the full batch add nothing over the 1/2-channel cases')
+    lib, model, drv, params, packed, ws, hp = _setup(n_ch=n_ch, n=n, h=h, w=w)
+    big, small = _dims(hp, 1, 4)
+    g = torch.Generator().manual_seed(77)
+    xs = _exact((n,) + small, g).cuda()
+    target = torch.rand((n, n_ch, h, w), generator=g).cuda()
+    tot = n * n_ch * h * w
+    nchunks = (n + 199) // 200
+    outs = []
+    for mode in (0, 1):
+        out = torch.full((2 * tot + 2 * nchunks,), float('nan'), device='cuda')
+        _run(lib, drv, params, packed, ws, 1, 4, 3, n, xs, target, out, mode)
+        outs.append(out)
+    ref, tc = outs
+    assert torch.isfinite(tc[:2 * tot]).all()
+    assert float((tc[:tot] - ref[:tot]).abs().max()) < 2e-6                       # x_hat in (0, 1)
+    scale = float(ref[tot:2 * tot].abs().max())
+    assert float((tc[tot:2 * tot] - ref[tot:2 * tot]).abs().max()) < 2e-5 * scale
+    sse_ref = ref[2 * tot:].view(torch.float64)
+    sse_tc = tc[2 * tot:].view(torch.float64)
+    assert float(((sse_tc - sse_ref).abs() / sse_ref).max()) < 1e-6

@@ -1104,6 +1104,30 @@ static int launch_vit(const VitArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// side stream + events of the emission / scan overlap inside bn_arhmm_estep (per host thread and device)
+struct OverlapStreams {
+  int device;
+  cudaStream_t side;
+  cudaEvent_t start, done[8];
+};
+static OverlapStreams* overlap_streams() {
+  thread_local OverlapStreams cache[16];
+  thread_local int n_cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (int i = 0; i < n_cached; ++i)
+    if (cache[i].device == dev) return &cache[i];
+  if (n_cached >= 16) return nullptr;
+  OverlapStreams o;
+  o.device = dev;
+  if (cudaStreamCreateWithFlags(&o.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&o.start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  for (int i = 0; i < 8; ++i)
+    if (cudaEventCreateWithFlags(&o.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  cache[n_cached] = o;
+  return &cache[n_cached++];
+}
+
 extern "C" int bn_arhmm_estep(int K, int D, int lags, const void* d_blob, const float* d_x,
                               const int64_t* d_offsets, int n_trials, int64_t total_T, int max_T,
                               void* d_ws, float* d_Ez, float* d_Ezz, double* d_logZ, void* stream) {
@@ -1118,35 +1142,66 @@ extern "C" int bn_arhmm_estep(int K, int D, int lags, const void* d_blob, const 
   e.blob = (const unsigned char*)d_blob; e.x = d_x; e.offsets = (const long long*)d_offsets;
   e.K = K; e.D = D; e.lags = lags; e.J = D * (lags + 1) + 1;
   e.Bsc = (float*)(ws + w.Bsc); e.mx = (float*)(ws + w.mx); e.ll = nullptr;
-  int tc = 1;
-  if (bn_get_tensor_core_mode())
-    tc = bn_launch_emission_tc(e.blob, d_x, e.offsets, K, D, lags, n_trials, max_T, e.Bsc, e.mx, st);
-  if (tc < 0) return tc;
-  if (tc > 0) BN_TRY((launch_emission<float, 2>(e, n_trials, max_T, st)));
   static const bool legacy_scan = [] { const char* e = getenv("BN_SCAN"); return e && e[0] == '1'; }();
-  if (legacy_scan) {
-    // sequential forward-then-backward kernel (kept for A/B timing: BN_SCAN=1)
-    ScanArgs s;
-    s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
-    s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.cinv = (float*)(ws + w.beta);
-    switch (bn_round_kp(K)) {
-      case 2: return launch_scan<2>(s, st);
-      case 4: return launch_scan<4>(s, st);
-      case 8: return launch_scan<8>(s, st);
-      case 16: return launch_scan<16>(s, st);
-      default: return launch_scan<32>(s, st);
+  // Optional emission / scan overlap (BN_ESTEP_GROUPS=g > 1): the call is cut into g trial groups, the emission
+  // kernels of all groups run back to back on a side stream and the scan of group i starts on the caller's
+  // stream as soon as ITS likelihoods are written.  MEASURED SLOWER on B200 (C4: 555 / 772 / 979 / 1571 us at
+  // g = 1 / 2 / 4 / 8, profiles/r02_estep_groups.txt): the scan is a T-step dependent chain whose duration
+  // hardly depends on how many trials are in flight, so g scans cost ~g chains while the emission kernels they
+  // were meant to hide take less than one.  Default off; the switch stays for the record.
+  static const int max_groups = [] { const char* e = getenv("BN_ESTEP_GROUPS"); return e ? atoi(e) : 1; }();
+  int groups = 1;
+  if (!legacy_scan && max_groups > 1 && n_trials >= 64 * max_groups) groups = max_groups > 8 ? 8 : max_groups;
+  OverlapStreams* ov = groups > 1 ? overlap_streams() : nullptr;
+  if (groups > 1 && !ov) groups = 1;
+  if (groups > 1) {
+    BN_CUDA(cudaEventRecord(ov->start, st));
+    BN_CUDA(cudaStreamWaitEvent(ov->side, ov->start, 0));        // inputs (and the workspace's last readers) are done
+  }
+  const int per = (n_trials + groups - 1) / groups;
+  for (int g = 0; g < groups; ++g) {
+    const int g0 = g * per, gn = std::min(per, n_trials - g0);
+    if (gn <= 0) break;
+    cudaStream_t est = groups > 1 ? ov->side : st;
+    EmitArgs<float> eg = e;
+    eg.offsets = e.offsets + g0;
+    int tc = 1;
+    if (bn_get_tensor_core_mode())
+      tc = bn_launch_emission_tc(eg.blob, d_x, eg.offsets, K, D, lags, gn, max_T, eg.Bsc, eg.mx, est);
+    if (tc < 0) return tc;
+    if (tc > 0) BN_TRY((launch_emission<float, 2>(eg, gn, max_T, est)));
+    if (groups > 1) {
+      BN_CUDA(cudaEventRecord(ov->done[g], ov->side));
+      BN_CUDA(cudaStreamWaitEvent(st, ov->done[g], 0));
     }
+    if (legacy_scan) {
+      // sequential forward-then-backward kernel (kept for A/B timing: BN_SCAN=1)
+      ScanArgs s;
+      s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
+      s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.cinv = (float*)(ws + w.beta);
+      switch (bn_round_kp(K)) {
+        case 2: return launch_scan<2>(s, st);
+        case 4: return launch_scan<4>(s, st);
+        case 8: return launch_scan<8>(s, st);
+        case 16: return launch_scan<16>(s, st);
+        default: return launch_scan<32>(s, st);
+      }
+    }
+    Scan2Args s;
+    s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = eg.offsets; s.n_trials = gn; s.K = K;
+    s.Ez = d_Ez; s.Ezz = d_Ezz ? d_Ezz + (size_t)g0 * K * K : nullptr; s.logZ = d_logZ ? d_logZ + g0 : nullptr;
+    s.beta = (float*)(ws + w.beta);
+    int r;
+    switch (bn_round_kp(K)) {
+      case 2: r = launch_scan2<2>(s, st); break;
+      case 4: r = launch_scan2<4>(s, st); break;
+      case 8: r = launch_scan2<8>(s, st); break;
+      case 16: r = launch_scan2<16>(s, st); break;
+      default: r = launch_scan2<32>(s, st); break;
+    }
+    if (r) return r;
   }
-  Scan2Args s;
-  s.blob = e.blob; s.Bsc = e.Bsc; s.mx = e.mx; s.offsets = e.offsets; s.n_trials = n_trials; s.K = K;
-  s.Ez = d_Ez; s.Ezz = d_Ezz; s.logZ = d_logZ; s.beta = (float*)(ws + w.beta);
-  switch (bn_round_kp(K)) {
-    case 2: return launch_scan2<2>(s, st);
-    case 4: return launch_scan2<4>(s, st);
-    case 8: return launch_scan2<8>(s, st);
-    case 16: return launch_scan2<16>(s, st);
-    default: return launch_scan2<32>(s, st);
-  }
+  return 0;
 }
 
 extern "C" int bn_arhmm_viterbi(int K, int D, int lags, const void* d_blob, const float* d_x,

@@ -4,11 +4,15 @@
 
 Headline workload (N GPUs, weak scaling): config C2 -- CAE 128x128x1, 12 latents, 256 frames per
 GPU, one ``AE.loss(data, accumulate_grad=True)`` call per step (forward + fused MSE + backward over
-all reference chunks, plus the gradient all-reduce when N > 1), frames resident in HBM.
-The same JSON line carries an ``arhmm`` object for config C4 (K=16, lag 2, D=12, 2048 trials x 1000
-steps per GPU, one E-step per step).
+all reference chunks, plus the bucketed gradient all-reduce when N > 1), frames resident in HBM.
+The same JSON line carries: ``sustained`` (the same step for >= 2 s), ``arhmm`` (config C4: K=16, lag 2,
+D=12; weak = 2048 trials x 1000 steps per GPU, strong = 2048 trials in total), ``psvae`` (config C3, weak
+and strong), ``c5`` (config C5: 1,000,188 uint8 frames resident in HBM -> encoder -> E-step),
+``matmul_peaks_here`` (cuBLAS TF32 / bf16 measured in this run: the roofline denominators) and
+``reference_eager_b200`` (the unmodified reference on this GPU through eager PyTorch + cuDNN, informational).
 
-``--impl reference`` times the CPU oracle port of the reference path (oracle/) on the host cores.
+``--impl reference`` times the UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.sh) on
+the host cores: behavenet.models.AE.loss on the full 256-frame batch.
 """
 
 import argparse
@@ -29,9 +33,6 @@ sys.path.insert(0, ROOT)
 # algorithmic work
 CAE_C2_TRAIN_GFLOP_PER_FRAME = 2.078
 ARHMM_BYTES_PER_TIMESTEP = 113.0
-# dram__bytes_read + write per launch (profiles/r01_g_ncu_full.txt)
-IGEMM128_KERNEL_TRAFFIC_BYTES = 72.1e6      # encoder conv2 forward: 67 MB input image read once
-HALO_KERNEL_TRAFFIC_BYTES = 144.2e6
 CAE_BATCH_PER_GPU = 256
 ARHMM_TRIALS_PER_GPU, ARHMM_T, ARHMM_K, ARHMM_D, ARHMM_LAGS = 2048, 1000, 16, 12, 2
 
@@ -147,9 +148,53 @@ def timed(fn, steps, warmup, flush=None):
     return ms
 
 
-def time_layer_kernel(model, device, side, layer, op, name, traffic_bytes, iters=20):
+def timed_block(fn, steps, device):
+    """K back-to-back calls between a barrier + synchronize on both sides; ms per call, max over ranks."""
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return dist_max(e0.elapsed_time(e1), device) / steps
+
+
+def sustained(fn, seconds, device):
+    """Back-to-back calls for at least ``seconds`` of device time (the power / clock state of a long run, like
+    the sustained figure of MEASURED_PEAKS.json) -> (ms per call, calls)."""
+    torch.cuda.synchronize()
+    barrier()
+    calls, total = 0, 0.0
+    while total < seconds * 1e3:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+        calls += 20
+        # every rank must leave the loop after the same number of calls (collectives inside fn)
+        if dist_max(total, device) >= seconds * 1e3:
+            break
+    return dist_max(total, device) / calls, calls
+
+
+def kernel_traffic():
+    """dram read + write bytes per launch of the profiled kernels, from the ncu export of the CURRENT build
+    (profiles/r02_kernel_traffic.json, written by scripts/ncu_traffic.py); {} when no capture is committed."""
+    p = os.path.join(ROOT, 'profiles', 'r02_kernel_traffic.json')
+    if os.path.exists(p):
+        return json.load(open(p))
+    return {}
+
+
+def time_layer_kernel(model, device, side, layer, op, name, iters=20):
     """One layer kernel timed alone through bn_cae_layer_op (CUDA events on the launch stream, after
-    warm-up): side 0/1 = encoder/decoder layer, op 0/1 = forward / backward-data."""
+    warm-up): side 0/1 = encoder/decoder layer, op 0/1/2 = forward / backward-data / weight gradient."""
     from behavenet_b200 import _lib
     drv, rt = model._driver, model._rt
     hp = model.hparams
@@ -163,6 +208,7 @@ def time_layer_kernel(model, device, side, layer, op, name, traffic_bytes, iters
                        hp['ae_encoding_x_dim'][layer - 1]))
         cs, hs, wsm = (hp['ae_encoding_n_channels'][layer], hp['ae_encoding_y_dim'][layer],
                        hp['ae_encoding_x_dim'][layer])
+        wshape = params[2 * layer].shape
     else:
         c0, h0, w0 = hp['ae_decoding_starting_dim']
         cs, hs, wsm = ((c0, h0, w0) if layer == 0 else
@@ -170,14 +216,20 @@ def time_layer_kernel(model, device, side, layer, op, name, traffic_bytes, iters
                         hp['ae_decoding_x_dim'][layer - 1]))
         cb, hb, wb = (hp['ae_decoding_n_channels'][layer], hp['ae_decoding_y_dim'][layer],
                       hp['ae_decoding_x_dim'][layer])
+        wshape = params[2 * drv.n_layers + 6 + 2 * layer].shape
     fprop_form = (side == 0 and op == 0) or (side == 1 and op == 1)
-    src = torch.rand((n, hb, wb, cb) if fprop_form else (n, hs, wsm, cs), device=device)
-    out = torch.empty((n, hs, wsm, cs) if fprop_form else (n, hb, wb, cb), device=device)
+    big = torch.rand((n, hb, wb, cb), device=device)
+    small = torch.rand((n, hs, wsm, cs), device=device)
+    if op == 2:
+        src, src2, out = big, small, torch.zeros(wshape, device=device)
+    else:
+        src, src2 = (big if fprop_form else small), None
+        out = torch.empty((n, hs, wsm, cs) if fprop_form else (n, hb, wb, cb), device=device)
     lib = _lib.lib()
 
     def run():
-        _lib.check(lib.bn_cae_layer_op(drv.plan(device), side, layer, op, n, src.data_ptr(), None, out.data_ptr(),
-                                       drv.table(params), packed.data_ptr(), ws.data_ptr(),
+        _lib.check(lib.bn_cae_layer_op(drv.plan(device), side, layer, op, n, src.data_ptr(), _lib.ptr(src2),
+                                       out.data_ptr(), drv.table(params), packed.data_ptr(), ws.data_ptr(),
                                        _lib.stream_ptr()), 'bn_cae_layer_op')
     for _ in range(5):
         run()
@@ -190,40 +242,52 @@ def time_layer_kernel(model, device, side, layer, op, name, traffic_bytes, iters
     e1.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / iters
     gflop = 2.0 * n * hs * wsm * cs * 25 * cb * 1e-9
+    key = name.split(' ')[0]
     return {'kernel': name, 'us': us, 'gflop': gflop, 'tflops': gflop / us * 1e3, 'launches': iters,
-            'traffic_bytes': traffic_bytes}
+            'traffic_bytes': kernel_traffic().get(key)}
 
 
-def time_dominant_kernel(model, device):
-    """The kernel with the largest share of the step in the committed launch list
-    (profiles/r01_g_launches_summary.txt: igemm_tma_kernel<128,3>, 8 launches, 10.1 %): its encoder
-    conv2 forward instance (64 -> 128 channels, 32x32 -> 16x16, k5 s2, 256 frames)."""
-    return time_layer_kernel(model, device, 0, 2, 0,
-                             'igemm_tma_kernel<128,3> (encoder conv2 forward, M=65536 N=128 K=1600)',
-                             IGEMM128_KERNEL_TRAFFIC_BYTES)
-
-
-def measure_cublas_tf32(device):
-    """cuBLAS TF32 GEMM throughput on this GPU, for context next to the roofline denominator."""
+def measure_matmul_peaks(device, sustained_s=2.0):
+    """cuBLAS dense GEMM throughput on THIS GPU, measured the way MEASURED_PEAKS.json measures bf16: torch.matmul
+    8192^3, best of 10 (burst) and back to back for ``sustained_s`` seconds (sustained), for TF32 operands (the
+    MMA kind the conv kernels use) and for bf16 (cross-check against the driver's file)."""
+    out = {}
     old = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        a = torch.randn(8192, 8192, device=device)
-        b = torch.randn(8192, 8192, device=device)
-        for _ in range(3):
-            a @ b
-        torch.cuda.synchronize()
-        best = 1e9
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            a @ b
-            e1.record()
-            e1.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        return 2 * 8192 ** 3 / (best * 1e-3) * 1e-12
+        for tag, dt in (('tf32', torch.float32), ('bf16', torch.bfloat16)):
+            a = torch.randn(8192, 8192, device=device, dtype=dt)
+            b = torch.randn(8192, 8192, device=device, dtype=dt)
+            for _ in range(3):
+                a @ b
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                a @ b
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            flop = 2 * 8192 ** 3
+            out[tag + '_tflops'] = flop / (best * 1e-3) * 1e-12
+            n, tot = 0, 0.0
+            while tot < sustained_s * 1e3:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    a @ b
+                e1.record()
+                e1.synchronize()
+                tot += e0.elapsed_time(e1)
+                n += 20
+            out[tag + '_tflops_sustained'] = flop * n / (tot * 1e-3) * 1e-12
+            del a, b
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+    out['how'] = ('torch.matmul 8192^3 on this GPU in this run: best of 10 (burst) and back to back for %.0f s (sustained); '
+                  'tf32 = fp32 tensors with torch.backends.cuda.matmul.allow_tf32' % sustained_s)
+    return out
 
 
 def dist_max(value, device):
@@ -241,20 +305,11 @@ def barrier():
         dist.barrier()
 
 
-def run_ours(args):
+# ----------------------------------------------------------------------------------------------------
+# CAE C2 (headline): weak scaling, 256 frames per GPU
+# ----------------------------------------------------------------------------------------------------
+def bench_cae(args, device, world, rank, local):
     from behavenet_b200 import _lib, parallel
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    device = torch.device('cuda', local)
-    if world > 1:
-        parallel.init('nccl')
-    peaks, peak_src = measured_peaks()
-    lib = _lib.lib()
-    lib.bn_set_tensor_core_mode(1)
-
-    # ---------------- CAE (C2) : weak scaling, 256 frames per GPU
     model, hp = make_cae(device)
     model.data_parallel = world > 1
     B = CAE_BATCH_PER_GPU * world
@@ -323,7 +378,14 @@ def run_ours(args):
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    cae_value = B / (ms_per_step * 1e-3)
+    # the same step for >= 2 s: the clock / power state of a long training run
+    sus_sampler = ClockSampler(local)
+    if rank == 0:
+        sus_sampler.start()
+    sus_sampler.mark_start()
+    sus_ms, sus_calls = sustained(step, 2.0, device)
+    sus_sampler.mark_stop()
+    sus_clocks = sus_sampler.stop() if rank == 0 else None
     # per-step distribution with an L2 flush between steps (inputs are 16.8 MB/GPU < L2)
     ms_flushed = timed(step, max(3, min(args.steps, 10)), 0, flush)
     opt_ms = timed(lambda: opt.step(), 3, 1)
@@ -335,140 +397,117 @@ def run_ours(args):
     run_e2e(e2e_steps)
     torch.cuda.synchronize()
     e2e_ms = dist_max((time.perf_counter() - t0) * 1e3 / e2e_steps, device)
+    return dict(model=model, hp=hp, B=B, ms_per_step=ms_per_step, launches=launches, clocks=clocks,
+                sustained_ms=sus_ms, sustained_calls=sus_calls, sustained_clocks=sus_clocks,
+                ms_flushed=float(np.median(ms_flushed)), opt_ms=float(np.median(opt_ms)), e2e_ms=e2e_ms,
+                e2e_steps=e2e_steps, h2d=int(x_host.numel() * 4))
 
-    tf = cae_value * CAE_C2_TRAIN_GFLOP_PER_FRAME * 1e-3 / world         # TFLOP/s per GPU
-    # TF32 dense peak: MEASURED_PEAKS.json has no TF32 entry; the hardware ratio to bf16 is 1/2, so
-    # the denominator is half of the measured bf16 burst (kernel timed alone) / sustained (whole step)
-    tf32_peak_burst = peaks['bf16_tflops'] / 2.0
-    tf32_peak_sust = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']) / 2.0
-    dom = time_dominant_kernel(model, device)
-    dom2 = time_layer_kernel(model, device, 0, 1, 0,
-                             'igemm_tma_kernel<64,4> (encoder conv1 forward, M=262144 N=64 K=800)', 51.7e6)
-    dom3 = time_layer_kernel(model, device, 1, 3, 0,
-                             'dgrad_halo_kernel<32,3> (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])',
-                             HALO_KERNEL_TRAFFIC_BYTES)
-    cublas_tf32 = measure_cublas_tf32(device) if rank == 0 else None
 
-    # ---------------- ARHMM (C4): weak scaling, 2048 trials per GPU
+# ----------------------------------------------------------------------------------------------------
+# ARHMM C4: weak (2048 trials per GPU) and strong (2048 trials in total) scaling
+# ----------------------------------------------------------------------------------------------------
+def make_hmm():
     from behavenet_b200.ssm import HMM
     from oracle import arhmm_oracle as ao         # synthetic parameters / data generator only
     p = ao.synth_params(ARHMM_K, ARHMM_D, ARHMM_LAGS, seed=0)
     hmm = HMM(ARHMM_K, ARHMM_D, observations='ar', observation_kwargs={'lags': ARHMM_LAGS})
     hmm.init_state_distn.log_pi0, hmm.transitions.log_Ps = p.log_pi0, p.log_Ps
     hmm.observations.As, hmm.observations.bs, hmm.observations.Sigmas = p.As, p.bs, p.Sigmas
+    return hmm, p
+
+
+def bench_arhmm(args, device, world, rank):
+    from behavenet_b200 import _lib, parallel
+    from oracle import arhmm_oracle as ao
+    hmm, p = make_hmm()
+    out = {}
     X = ao.sample_batch(p, ARHMM_TRIALS_PER_GPU, ARHMM_T, seed=rank)
     trials = [X[i] for i in range(X.shape[0])]
+
+    def make_step(st, shard):
+        def estep():
+            Ez, Ezz, logZ = hmm._run_estep(st, True, shard)
+            if world > 1:
+                stats = torch.cat([Ezz.sum(0).double().reshape(-1), logZ.sum().reshape(1)])
+                parallel.all_reduce_sum(stats)
+        return estep
+
+    # weak: every rank owns 2048 trials
     st = hmm._stage(trials)
-    n_ts = ARHMM_TRIALS_PER_GPU * ARHMM_T
-
-    def estep():
-        Ez, Ezz, logZ = hmm._run_estep(st, True)
-        if world > 1:
-            stats = torch.cat([Ezz.sum(0).double().reshape(-1), logZ.sum().reshape(1)])
-            parallel.all_reduce_sum(stats)
-
+    step = make_step(st, None)
     for _ in range(max(3, args.warmup)):
-        estep()
-    torch.cuda.synchronize()
-    barrier()
+        step()
     h0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        estep()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    hmm_ms = dist_max(e0.elapsed_time(e1), device) / args.steps
-    hmm_launches = _lib.launch_count() - h0
-    hmm_value = n_ts * world / (hmm_ms * 1e-3)
+    ms = timed_block(step, args.steps, device)
+    out['launches'] = _lib.launch_count() - h0
+    n_ts = ARHMM_TRIALS_PER_GPU * ARHMM_T
+    out['weak_ms'] = ms
+    out['weak_value'] = n_ts * world / (ms * 1e-3)
+    # strong: the 2048 trials of BASELINE config 4 sharded over the ranks (rank 0's trials are "the" data set)
+    if world > 1:
+        lo, hi = parallel.shard_range(ARHMM_TRIALS_PER_GPU, world, rank)
+        st_s = hmm.stage_device(st.x[lo * ARHMM_T:hi * ARHMM_T].contiguous(), [ARHMM_T] * (hi - lo))
+        step_s = make_step(st_s, None)
+        for _ in range(3):
+            step_s()
+        ms_s = timed_block(step_s, args.steps, device)
+    else:
+        ms_s = ms
+    out['strong_ms'] = ms_s
+    out['strong_value'] = n_ts / (ms_s * 1e-3)
 
-    def estep_e2e():
+    # end to end from the python list of host arrays the reference hands to ssm (arhmm_grid_search.py:170):
+    # (a) what EM does -- the list is staged ONCE (gather into pinned memory + H2D), then every iteration's
+    # E-step re-uses it (hmm.py caches by identity + fingerprint) and reads its statistics back;
+    # (b) cold: staging + one E-step + read-back per call.
+    n_iter = 10
+
+    def em_like():
         hmm.clear_cache()
-        s2 = hmm._stage(trials)                       # host -> device copy of the latents
+        s2 = hmm._stage(trials)
+        tot = 0.0
+        for _ in range(n_iter):
+            Ez, Ezz, logZ = hmm._run_estep(s2, True)
+            tot += float(logZ.sum().item())
+            Ezz.sum(0).cpu()
+        return tot
+
+    def cold():
+        hmm.clear_cache()
+        s2 = hmm._stage(trials)
         Ez, Ezz, logZ = hmm._run_estep(s2, True)
         return float(logZ.sum().item()), Ezz.sum(0).cpu()
-    hmm_e2e = float(np.median(timed(estep_e2e, 3, 1)))
-
-    # ---------------- PS-VAE (C3): 128x128x2, 16 latents, 4 labels, 512 frames per GPU (weak scaling)
-    psvae = None
-    try:
-        psvae = bench_psvae(device, world, rank, args)
-    except Exception as exc:                     # the headline line must not depend on this extra leg
-        psvae = {'error': repr(exc)[:200]}
-
-    if rank != 0:
-        return
-    cpu = cpu_baselines() if world == 1 else None
-    hbm_achieved = hmm_value / world * ARHMM_BYTES_PER_TIMESTEP / 1e9
-    line = {
-        'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
-        'value': cae_value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 accumulate)' if lib.bn_get_tensor_core_mode() else 'f32',
-        'data': 'synthetic',
-        'config': {'workload': 'C2: CAE 128x128x1, 12 latents, batch=256 per GPU, AE.loss fwd+bwd, '
-                               'default 5-layer arch', 'global_batch': B,
-                   'l2': 'inputs 16.8 MB/GPU < L2; ms_per_step_l2_flushed reports the flushed timing',
-                   'parallelism': 'dp%d' % world},
-        'ms_per_step_l2_flushed': float(np.median(ms_flushed)),
-        'optimizer_step_ms': float(np.median(opt_ms)),
-        'gpu_launches': int(launches),
-        'clocks': clocks,
-        'e2e': {'value': B / (e2e_ms * 1e-3), 'unit': 'frames/s',
-                'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': 16 * world,
-                'steps': e2e_steps,
-                'note': 'AE.loss on frames copied from pinned host memory every step (the copy of step i+1 '
-                        'overlaps the compute of step i on a side stream; one extra prefetch is inside the '
-                        'timed region) + the per-step loss read-back; host wall clock, max over ranks'},
-        'roofline': {'bound': 'tensor', 'achieved': dom['tflops'], 'peak': tf32_peak_burst,
-                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / tf32_peak_burst,
-                     'traffic': dom['traffic_bytes'],
-                     'kernel': dom['kernel'], 'kernel_us': dom['us'], 'kernel_gflop': dom['gflop'],
-                     'note': 'dominant kernel timed alone with CUDA events on the launch stream (%d '
-                             'launches after warm-up); peak = TF32 dense = half of the %s bf16 burst '
-                             'peak (MEASURED_PEAKS.json has no TF32 entry); traffic = dram read+write '
-                             'bytes per launch from profiles/r01_g_ncu_full.txt'
-                             % (dom['launches'], peak_src)},
-        'step_roofline': {'bound': 'tensor', 'achieved': tf, 'peak': tf32_peak_sust, 'unit': 'TFLOP/s',
-                          'frac': tf / tf32_peak_sust,
-                          'note': 'whole step: %.3f GFLOP/frame algorithmic / step time, per GPU; peak = '
-                                  'half of the %s bf16 sustained peak' % (CAE_C2_TRAIN_GFLOP_PER_FRAME, peak_src)},
-        'kernel_rooflines': [{'kernel': d['kernel'], 'us': d['us'], 'tflops': d['tflops'],
-                              'frac': d['tflops'] / tf32_peak_burst, 'traffic': d['traffic_bytes']}
-                             for d in (dom, dom2, dom3)],
-        'cublas_tf32_tflops_here': cublas_tf32,
-        'arhmm': {
-            'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
-            'value': hmm_value, 'unit': 'timesteps/s', 'ms_per_step': hmm_ms,
-            'gpu_launches': int(hmm_launches), 'dtype': 'f32 (scaled messages), f64 log-normaliser',
-            'e2e': {'value': n_ts / (hmm_e2e * 1e-3), 'unit': 'timesteps/s',
-                    'h2d_bytes_per_step': int(n_ts * ARHMM_D * 4),
-                    'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4)},
-            'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
-                         'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'], 'traffic': 588.4e6,
-                         'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out '
-                                 '+ per-trial outputs), whole E-step time (emission + scan kernels); peak %s; '
-                                 'traffic = dram read+write of the dominant kernel (scan2_kernel, 0.31 of the 0.57 ms; '
-                                 'emission_tc_kernel adds 187 MB), profiles/r01_g_ncu_full.txt; the binding limits '
-                                 'are the T-step serial chain and the 3-pass emission GEMM, not HBM' % peak_src},
-        },
-    }
-    line['psvae'] = psvae
-    if cpu is not None:
-        line['cpu_baseline'] = cpu['cae']
-        line['arhmm']['cpu_baseline'] = cpu['arhmm']
-    _OUT.write(json.dumps(line) + '\n')
-    _OUT.flush()
+    em_like()
+    barrier()
+    t0 = time.perf_counter()
+    em_like()
+    torch.cuda.synchronize()
+    em_s = dist_max(time.perf_counter() - t0, device)
+    cold()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cold()
+    torch.cuda.synchronize()
+    cold_s = dist_max((time.perf_counter() - t0) / 3, device)
+    out['e2e_value'] = n_ts * world * n_iter / em_s
+    out['e2e_cold_value'] = n_ts * world / cold_s
+    out['e2e_iters'] = n_iter
+    out['n_ts'] = n_ts
+    return out
 
 
+# ----------------------------------------------------------------------------------------------------
+# PS-VAE C3: 128x128x2, 16 latents, 4 labels; weak (512 frames per GPU) and strong (512 frames in total)
+# ----------------------------------------------------------------------------------------------------
 PSVAE_GFLOP_PER_FRAME = 2.111          # train step, 128x128x2, 16 latents
 PSVAE_BATCH_PER_GPU = 512
 
 
 def bench_psvae(device, world, rank, args):
-    """Config C3: one PSVAE.loss(accumulate_grad=True) per step on 512 frames per GPU (chunks of 200;
-    whole chunks are sharded over ranks, so every rank gets its own 512-frame batch slice)."""
+    """One PSVAE.loss(accumulate_grad=True) per step: contiguous frame shards per rank, reference chunks of
+    200 frames that span ranks exchange their (FF output, logvar, eps) rows (one small all-reduce), one
+    bucketed gradient all-reduce."""
     import copy
     from behavenet_b200.models import PSVAE
     from oracle import cae_oracle as co          # seeded synthetic parameters only
@@ -478,40 +517,274 @@ def bench_psvae(device, world, rank, args):
     model.load_state_dict(co.init_state_dict(hp, seed=0))
     model.to(device)
     model.curr_epoch = 1
-    # 600 frames per rank = three whole reference chunks of 200 per rank would change the config;
-    # keep 512 per GPU and let the chunk sharding split [200, 200, 112] x world over the ranks
-    B = PSVAE_BATCH_PER_GPU * world
     model.data_parallel = world > 1
-    g = torch.Generator().manual_seed(1)
-    x = torch.rand(B, 2, 128, 128, generator=g).to(device)
-    y = torch.randn(B, 4, generator=g).to(device)
-    eps = torch.randn(B, 16, generator=g).to(device)
-    data = {'images': x[None], 'labels': y[None]}
-
-    def step():
-        model.zero_grad()
-        model.invalidate_packed()
-        model.loss(data, accumulate_grad=True, eps=eps)
-
     steps = max(3, min(args.steps, 10))
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    barrier()
-    ms = dist_max(e0.elapsed_time(e1), device) / steps
-    value = B / (ms * 1e-3)
+    res = {}
+    for tag, B in (('weak', PSVAE_BATCH_PER_GPU * world), ('strong', PSVAE_BATCH_PER_GPU)):
+        if tag == 'strong' and world == 1:
+            res['strong'] = dict(res['weak'])
+            break
+        g = torch.Generator().manual_seed(1)
+        x = torch.rand(B, 2, 128, 128, generator=g).to(device)
+        y = torch.randn(B, 4, generator=g).to(device)
+        eps = torch.randn(B, 16, generator=g).to(device)
+        data = {'images': x[None], 'labels': y[None]}
+
+        def step():
+            model.zero_grad()
+            model.invalidate_packed()
+            model.loss(data, accumulate_grad=True, eps=eps)
+        for _ in range(3):
+            step()
+        ms = timed_block(step, steps, device)
+        res[tag] = {'value': B / (ms * 1e-3), 'ms_per_step': ms, 'global_batch': B,
+                    'frames_per_gpu': B // world, 'tflops_per_gpu': B / (ms * 1e-3) * PSVAE_GFLOP_PER_FRAME * 1e-3 / world}
+        del x, y, eps, data
     return {'metric': 'PS-VAE train frames/sec (C3: 128x128x2, 16 latents, 4 labels, fwd+loss+bwd)',
-            'value': value, 'unit': 'frames/s', 'ms_per_step': ms, 'steps': steps, 'global_batch': B,
-            'tflops_per_gpu': value * PSVAE_GFLOP_PER_FRAME * 1e-3 / world,
-            'note': 'includes sklearn r2_score on the host and the per-chunk latent-block launches, as the '
+            'unit': 'frames/s', 'value': res['weak']['value'], 'ms_per_step': res['weak']['ms_per_step'],
+            'steps': steps, 'global_batch': res['weak']['global_batch'],
+            'tflops_per_gpu': res['weak']['tflops_per_gpu'], 'weak': res['weak'], 'strong': res['strong'],
+            'note': 'weak = 512 frames per GPU, strong = the 512-frame batch of BASELINE config 3 sharded over the '
+                    'ranks; includes sklearn r2_score on the host and the per-chunk latent-block launches, as the '
                     'reference loss() does; frames resident in HBM'}
+
+
+# ----------------------------------------------------------------------------------------------------
+# C5: encode-only export -> ARHMM E-step on device-resident latents (Musall-shape synthetic video)
+# ----------------------------------------------------------------------------------------------------
+C5_TRIALS, C5_T, C5_LATENTS = 5292, 189, 12
+C5_ENCODE_GFLOP_PER_FRAME = 0.3539        # 2-channel encoder incl. FF
+
+
+def bench_c5(device, world, rank):
+    """BASELINE config 5: 5292 trials x 189 frames of (2, 128, 128) uint8 video (= 1,000,188 frames) sharded by
+    trial over the ranks and RESIDENT in HBM as bytes; every trial goes through the encoder (uint8 -> /255 in
+    the first layer's loader, reference data_generator.py:258-263 + eval.py:6-118) and the latents stay on the
+    GPU that produced them for one ARHMM E-step (K=16, lag 2; arhmm_grid_search.py:170).  No inter-GPU traffic
+    between the stages; one all-reduce of the E-step statistics."""
+    import copy
+    from behavenet_b200 import parallel
+    from behavenet_b200.models import AE
+    from oracle import cae_oracle as co
+    hp = co.make_hparams(2, 128, 128, C5_LATENTS)
+    model = AE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.to(device)
+    model.eval()
+    lo, hi = parallel.shard_range(C5_TRIALS, world, rank)
+    n_trials = hi - lo
+    n_frames = n_trials * C5_T
+    # noise plus structure, generated on the device in slabs (a 33 GB pinned host copy would only time malloc)
+    frames = torch.empty(n_frames, 2, 128, 128, dtype=torch.uint8, device=device)
+    yy = torch.arange(128, device=device, dtype=torch.float32)[:, None]
+    xx = torch.arange(128, device=device, dtype=torch.float32)[None, :]
+    gen = torch.Generator(device=device).manual_seed(1000 + rank)
+    slab = 8192
+    for o in range(0, n_frames, slab):
+        n = min(slab, n_frames - o)
+        ph = torch.rand(n, 2, 1, 1, device=device, generator=gen) * 6.28
+        base = 110 + 70 * torch.sin(yy * 0.07 + ph) * torch.cos(xx * 0.05 + 2 * ph)
+        noise = torch.randint(0, 48, (n, 2, 128, 128), device=device, generator=gen, dtype=torch.int16)
+        frames[o:o + n] = (base + noise).clamp_(0, 255).to(torch.uint8)
+        del ph, base, noise
+    hmm, _ = make_hmm()
+    chunk = 4096
+    lat = torch.empty(n_frames, C5_LATENTS, dtype=torch.float32, device=device)
+
+    def encode():
+        with torch.no_grad():
+            for o in range(0, n_frames, chunk):
+                lat[o:o + chunk] = model.encoding(frames[o:o + chunk])[0]
+
+    def estep():
+        st = hmm.stage_device(lat, [C5_T] * n_trials)
+        Ez, Ezz, logZ = hmm.expected_states_device(st)
+        stats = torch.cat([Ezz.sum(0).double().reshape(-1), logZ.sum().reshape(1)])
+        if world > 1:
+            parallel.all_reduce_sum(stats)
+        return stats
+    encode()
+    estep()
+    enc_ms = timed_block(encode, 2, device)
+    es_ms = timed_block(estep, 5, device)
+    total_frames = C5_TRIALS * C5_T
+    enc_rate = total_frames / (enc_ms * 1e-3)
+    tfl = enc_rate * C5_ENCODE_GFLOP_PER_FRAME * 1e-3 / world
+    # end to end on a bounded sample: 64 trials of uint8 frames from pinned host memory (one byte per pixel
+    # across PCIe), encoder, E-step on their latents, statistics read back
+    ns = min(64, n_trials)
+    host = frames[:ns * C5_T].cpu().pin_memory()
+    dev_in = torch.empty_like(frames[:ns * C5_T])
+
+    def e2e():
+        dev_in.copy_(host, non_blocking=True)
+        with torch.no_grad():
+            z = model.encoding(dev_in)[0]
+        st = hmm.stage_device(z, [C5_T] * ns)
+        Ez, Ezz, logZ = hmm.expected_states_device(st)
+        return float(logZ.sum().item()), Ezz.sum(0).cpu()
+    e2e()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e()
+    torch.cuda.synchronize()
+    e2e_s = dist_max((time.perf_counter() - t0) / 3, device)
+    res = {
+        'metric': 'C5: encode-only export -> ARHMM E-step, 5292 trials x 189 frames of 2x128x128 uint8 (1,000,188 frames)',
+        'frames': total_frames, 'frames_per_gpu': n_frames, 'resident_bytes_per_gpu': int(frames.numel()),
+        'encode': {'value': enc_rate, 'unit': 'frames/s', 'ms': enc_ms, 'tflops_per_gpu': tfl},
+        'estep': {'value': total_frames / (es_ms * 1e-3), 'unit': 'timesteps/s', 'ms': es_ms},
+        'pipeline': {'value': total_frames / ((enc_ms + es_ms) * 1e-3), 'unit': 'frames/s',
+                     'note': 'encode + E-step, frames resident in HBM as uint8, latents never leave the GPU'},
+        'e2e': {'value': ns * C5_T * world / e2e_s, 'unit': 'frames/s', 'h2d_bytes_per_step': int(host.numel()),
+                'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4),
+                'sample': '%d trials (%d frames) per rank from pinned host memory per call: H2D at one byte per pixel + '
+                          'encoder + E-step + read-back; host wall clock, max over ranks' % (ns, ns * C5_T)},
+    }
+    del frames, lat, host, dev_in
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args):
+    from behavenet_b200 import _lib, parallel
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        parallel.init('nccl')
+    peaks, peak_src = measured_peaks()
+    lib = _lib.lib()
+    lib.bn_set_tensor_core_mode(1)
+
+    cae = bench_cae(args, device, world, rank, local)
+    model, hp, B = cae['model'], cae['hp'], cae['B']
+    ms_per_step = cae['ms_per_step']
+    cae_value = B / (ms_per_step * 1e-3)
+    # (kernels are timed alone BEFORE the seconds-long cuBLAS loops below heat the part up)
+    kernels = [
+        time_layer_kernel(model, device, 0, 2, 0, 'igemm_tma_kernel<128,3> (encoder conv2 forward, M=65536 N=128 K=1600)'),
+        time_layer_kernel(model, device, 0, 1, 0, 'igemm_tma_kernel<64,4> (encoder conv1 forward, M=262144 N=64 K=800)'),
+        time_layer_kernel(model, device, 0, 1, 2, 'wgrad_tma_kernel<64,4> (encoder conv1 weight gradient, 800x64 over 262144 pixels)'),
+        time_layer_kernel(model, device, 1, 3, 0, 'dgrad_halo_kernel<32,3> (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])'),
+    ]
+    dom = kernels[0]
+
+    hm = bench_arhmm(args, device, world, rank)
+    try:
+        psvae = bench_psvae(device, world, rank, args)
+    except Exception as exc:                     # the headline line must not depend on the extra legs
+        psvae = {'error': repr(exc)[:300]}
+    try:
+        c5 = bench_c5(device, world, rank)
+    except Exception as exc:
+        c5 = {'error': repr(exc)[:300]}
+    # roofline denominators: cuBLAS TF32 measured in THIS run the way MEASURED_PEAKS.json measures bf16
+    # (burst for a kernel timed alone, sustained for the step); half of the driver's bf16 figures beside it.
+    # Last, so that the 2 x 2 s of full-power GEMMs do not pre-heat the legs above.
+    mm = measure_matmul_peaks(device)
+    tf32_burst, tf32_sust = mm['tf32_tflops'], mm['tf32_tflops_sustained']
+    half_bf16_burst = peaks['bf16_tflops'] / 2.0
+    half_bf16_sust = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']) / 2.0
+    tf = cae_value * CAE_C2_TRAIN_GFLOP_PER_FRAME * 1e-3 / world         # TFLOP/s per GPU
+    tf_sus = B / (cae['sustained_ms'] * 1e-3) * CAE_C2_TRAIN_GFLOP_PER_FRAME * 1e-3 / world
+    if isinstance(c5, dict) and 'encode' in c5:
+        tfl = c5['encode']['tflops_per_gpu']
+        c5['encode']['roofline'] = {'bound': 'tensor', 'achieved': tfl, 'peak': tf32_sust, 'unit': 'TFLOP/s',
+                                    'frac': tfl / tf32_sust,
+                                    'note': '%.4f GFLOP/frame algorithmic (SURVEY 8d) / encode time; peak = cuBLAS TF32 '
+                                            'sustained measured in this run' % C5_ENCODE_GFLOP_PER_FRAME}
+    eager = None
+    if rank == 0 and world == 1:
+        try:
+            eager = reference_eager_b200(device)
+        except Exception as exc:
+            eager = {'error': repr(exc)[:300]}
+
+    if rank != 0:
+        return
+    cpu = cpu_baselines() if world == 1 else None
+    hbm_achieved = hm['weak_value'] / world * ARHMM_BYTES_PER_TIMESTEP / 1e9
+    line = {
+        'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
+        'value': cae_value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 accumulate)' if lib.bn_get_tensor_core_mode() else 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'C2: CAE 128x128x1, 12 latents, batch=256 per GPU, AE.loss fwd+bwd, '
+                               'default 5-layer arch', 'global_batch': B,
+                   'l2': 'inputs 16.8 MB/GPU < L2; ms_per_step_l2_flushed is the same step with a 256 MB L2 flush '
+                         'between steps', 'parallelism': 'dp%d' % world},
+        'ms_per_step_l2_flushed': cae['ms_flushed'],
+        'sustained': {'ms_per_step': cae['sustained_ms'], 'value': B / (cae['sustained_ms'] * 1e-3), 'unit': 'frames/s',
+                      'steps': cae['sustained_calls'], 'clocks': cae['sustained_clocks'],
+                      'note': 'the same step back to back for >= 2 s of device time (the burst figure above covers '
+                              '%d steps = %.0f ms)' % (args.steps, ms_per_step * args.steps)},
+        'optimizer_step_ms': cae['opt_ms'],
+        'gpu_launches': int(cae['launches']),
+        'clocks': cae['clocks'],
+        'e2e': {'value': B / (cae['e2e_ms'] * 1e-3), 'unit': 'frames/s',
+                'h2d_bytes_per_step': cae['h2d'], 'd2h_bytes_per_step': 16 * world,
+                'steps': cae['e2e_steps'],
+                'note': 'AE.loss on frames copied from pinned host memory every step (the copy of step i+1 '
+                        'overlaps the compute of step i on a side stream; one extra prefetch is inside the '
+                        'timed region) + the per-step loss read-back; host wall clock, max over ranks'},
+        'roofline': {'bound': 'tensor', 'achieved': dom['tflops'], 'peak': tf32_burst,
+                     'unit': 'TFLOP/s', 'frac': dom['tflops'] / tf32_burst,
+                     'frac_vs_half_bf16_burst': dom['tflops'] / half_bf16_burst,
+                     'traffic': dom['traffic_bytes'],
+                     'kernel': dom['kernel'], 'kernel_us': dom['us'], 'kernel_gflop': dom['gflop'],
+                     'note': 'dominant kernel timed alone with CUDA events on the launch stream (%d launches after '
+                             'warm-up); peak = cuBLAS TF32 8192^3 burst measured in this run (%.1f TFLOP/s; half of the %s '
+                             'bf16 burst of MEASURED_PEAKS.json would be %.1f); traffic = dram read+write bytes per '
+                             'launch from the ncu export of this build (profiles/r02_kernel_traffic.json) or null'
+                             % (dom['launches'], tf32_burst, peak_src, half_bf16_burst)},
+        'step_roofline': {'bound': 'tensor', 'achieved': tf, 'peak': tf32_sust, 'unit': 'TFLOP/s',
+                          'frac': tf / tf32_sust, 'frac_vs_half_bf16_sustained': tf / half_bf16_sust,
+                          'sustained_achieved': tf_sus, 'sustained_frac': tf_sus / tf32_sust,
+                          'note': 'whole step: %.3f GFLOP/frame algorithmic / step time, per GPU; peak = cuBLAS TF32 '
+                                  'sustained measured in this run (%.1f TFLOP/s; half of the %s bf16 sustained peak would '
+                                  'be %.1f)' % (CAE_C2_TRAIN_GFLOP_PER_FRAME, tf32_sust, peak_src, half_bf16_sust)},
+        'kernel_rooflines': [{'kernel': d['kernel'], 'us': d['us'], 'tflops': d['tflops'],
+                              'frac': d['tflops'] / tf32_burst, 'traffic': d['traffic_bytes']} for d in kernels],
+        'matmul_peaks_here': mm,
+        'reference_eager_b200': eager,
+        'arhmm': {
+            'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
+            'value': hm['weak_value'], 'unit': 'timesteps/s', 'ms_per_step': hm['weak_ms'],
+            'scaling': 'weak',
+            'strong': {'value': hm['strong_value'], 'ms_per_step': hm['strong_ms'],
+                       'note': 'the 2048 trials of BASELINE config 4 in total, sharded by trial over the ranks'},
+            'gpu_launches': int(hm['launches']), 'dtype': 'f32 (scaled messages), f64 log-normaliser',
+            'e2e': {'value': hm['e2e_value'], 'unit': 'timesteps/s',
+                    'h2d_bytes_per_step': int(hm['n_ts'] * ARHMM_D * 4 / hm['e2e_iters']),
+                    'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4),
+                    'cold_value': hm['e2e_cold_value'],
+                    'note': 'whole job (all ranks), host wall clock, max over ranks.  value = what EM does: the python '
+                            'list of 2048 host arrays per rank is staged once (pooled pinned gather + H2D) and %d '
+                            'E-steps re-use it, each reading its statistics back; cold_value = staging + ONE E-step '
+                            '+ read-back per call' % hm['e2e_iters']},
+            'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
+                         'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'],
+                         'traffic': kernel_traffic().get('arhmm_estep'),
+                         'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out + per-trial outputs), '
+                                 'whole E-step time; peak %s; traffic = dram read+write of all E-step kernels from the ncu '
+                                 'export of this build or null.  The binding limits are the T-step serial chain / '
+                                 'issue slots of the scan and the 3-pass emission GEMM, not HBM (DESIGN.md section 4)'
+                                 % peak_src},
+        },
+        'psvae': psvae,
+        'c5': c5,
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu['cae']
+        line['arhmm']['cpu_baseline'] = cpu['arhmm']
+    _OUT.write(json.dumps(line) + '\n')
+    _OUT.flush()
 
 
 def import_reference():

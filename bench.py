@@ -674,15 +674,19 @@ def run_ours(args):
     ]
     dom = kernels[0]
 
-    hm = bench_arhmm(args, device, world, rank)
-    try:
-        psvae = bench_psvae(device, world, rank, args)
-    except Exception as exc:                     # the headline line must not depend on the extra legs
-        psvae = {'error': repr(exc)[:300]}
-    try:
-        c5 = bench_c5(device, world, rank)
-    except Exception as exc:
-        c5 = {'error': repr(exc)[:300]}
+    legs = {'cae', 'arhmm', 'psvae', 'c5', 'eager', 'cpu'} if args.legs == 'all' else set(args.legs.split(','))
+    hm = bench_arhmm(args, device, world, rank) if 'arhmm' in legs else None
+    psvae = c5 = None
+    if 'psvae' in legs:
+        try:
+            psvae = bench_psvae(device, world, rank, args)
+        except Exception as exc:                     # the headline line must not depend on the extra legs
+            psvae = {'error': repr(exc)[:300]}
+    if 'c5' in legs:
+        try:
+            c5 = bench_c5(device, world, rank)
+        except Exception as exc:
+            c5 = {'error': repr(exc)[:300]}
     # roofline denominators: cuBLAS TF32 measured in THIS run the way MEASURED_PEAKS.json measures bf16
     # (burst for a kernel timed alone, sustained for the step); half of the driver's bf16 figures beside it.
     # Last, so that the 2 x 2 s of full-power GEMMs do not pre-heat the legs above.
@@ -699,7 +703,7 @@ def run_ours(args):
                                     'note': '%.4f GFLOP/frame algorithmic (SURVEY 8d) / encode time; peak = cuBLAS TF32 '
                                             'sustained measured in this run' % C5_ENCODE_GFLOP_PER_FRAME}
     eager = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and 'eager' in legs:
         try:
             eager = reference_eager_b200(device)
         except Exception as exc:
@@ -707,8 +711,8 @@ def run_ours(args):
 
     if rank != 0:
         return
-    cpu = cpu_baselines() if world == 1 else None
-    hbm_achieved = hm['weak_value'] / world * ARHMM_BYTES_PER_TIMESTEP / 1e9
+    cpu = cpu_baselines() if (world == 1 and 'cpu' in legs) else None
+    hbm_achieved = hm['weak_value'] / world * ARHMM_BYTES_PER_TIMESTEP / 1e9 if hm else None
     line = {
         'metric': 'CAE train frames/sec (C2: 128x128x1, 12 latents, fwd+loss+bwd)',
         'value': cae_value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
@@ -753,36 +757,39 @@ def run_ours(args):
                               'frac': d['tflops'] / tf32_burst, 'traffic': d['traffic_bytes']} for d in kernels],
         'matmul_peaks_here': mm,
         'reference_eager_b200': eager,
-        'arhmm': {
-            'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
-            'value': hm['weak_value'], 'unit': 'timesteps/s', 'ms_per_step': hm['weak_ms'],
-            'scaling': 'weak',
-            'strong': {'value': hm['strong_value'], 'ms_per_step': hm['strong_ms'],
-                       'note': 'the 2048 trials of BASELINE config 4 in total, sharded by trial over the ranks'},
-            'gpu_launches': int(hm['launches']), 'dtype': 'f32 (scaled messages), f64 log-normaliser',
-            'e2e': {'value': hm['e2e_value'], 'unit': 'timesteps/s',
-                    'h2d_bytes_per_step': int(hm['n_ts'] * ARHMM_D * 4 / hm['e2e_iters']),
-                    'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4),
-                    'cold_value': hm['e2e_cold_value'],
-                    'note': 'whole job (all ranks), host wall clock, max over ranks.  value = what EM does: the python '
-                            'list of 2048 host arrays per rank is staged once (pooled pinned gather + H2D) and %d '
-                            'E-steps re-use it, each reading its statistics back; cold_value = staging + ONE E-step '
-                            '+ read-back per call' % hm['e2e_iters']},
-            'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
-                         'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'],
-                         'traffic': kernel_traffic().get('arhmm_estep'),
-                         'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out + per-trial outputs), '
-                                 'whole E-step time; peak %s; traffic = dram read+write of all E-step kernels from the ncu '
-                                 'export of this build or null.  The binding limits are the T-step serial chain / '
-                                 'issue slots of the scan and the 3-pass emission GEMM, not HBM (DESIGN.md section 4)'
-                                 % peak_src},
-        },
+        'arhmm': None,
         'psvae': psvae,
         'c5': c5,
     }
+    if hm is not None:
+        line['arhmm'] = {
+        'metric': 'ARHMM E-step timesteps/sec (C4: K=16, lag 2, D=12, 2048 trials x 1000 per GPU)',
+        'value': hm['weak_value'], 'unit': 'timesteps/s', 'ms_per_step': hm['weak_ms'],
+        'scaling': 'weak',
+        'strong': {'value': hm['strong_value'], 'ms_per_step': hm['strong_ms'],
+                   'note': 'the 2048 trials of BASELINE config 4 in total, sharded by trial over the ranks'},
+        'gpu_launches': int(hm['launches']), 'dtype': 'f32 (scaled messages), f64 log-normaliser',
+        'e2e': {'value': hm['e2e_value'], 'unit': 'timesteps/s',
+                'h2d_bytes_per_step': int(hm['n_ts'] * ARHMM_D * 4 / hm['e2e_iters']),
+                'd2h_bytes_per_step': int(8 + ARHMM_K * ARHMM_K * 4),
+                'cold_value': hm['e2e_cold_value'],
+                'note': 'whole job (all ranks), host wall clock, max over ranks.  value = what EM does: the python '
+                        'list of 2048 host arrays per rank is staged once (pooled pinned gather + H2D) and %d '
+                        'E-steps re-use it, each reading its statistics back; cold_value = staging + ONE E-step '
+                        '+ read-back per call' % hm['e2e_iters']},
+        'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
+                     'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'],
+                     'traffic': kernel_traffic().get('arhmm_estep'),
+                     'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out + per-trial outputs), '
+                             'whole E-step time; peak %s; traffic = dram read+write of all E-step kernels from the ncu '
+                             'export of this build or null.  The binding limits are the T-step serial chain / '
+                             'issue slots of the scan and the 3-pass emission GEMM, not HBM (DESIGN.md section 4)'
+                             % peak_src},
+    }
     if cpu is not None:
         line['cpu_baseline'] = cpu['cae']
-        line['arhmm']['cpu_baseline'] = cpu['arhmm']
+        if line['arhmm'] is not None:
+            line['arhmm']['cpu_baseline'] = cpu['arhmm']
     _OUT.write(json.dumps(line) + '\n')
     _OUT.flush()
 
@@ -955,6 +962,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--legs', default='all', help="'all' or a comma list of cae,arhmm,psvae,c5,eager,cpu (diagnostic runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

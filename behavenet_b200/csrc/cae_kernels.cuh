@@ -70,6 +70,10 @@ int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf,
                          float* colsum = nullptr, int* colsum_fused = nullptr);   // optional fused column sums of `out`
 int bn_launch_thin_wgrad(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                          size_t partial_floats, float* grad, cudaStream_t st);
+// decoupled-role tensor-core form of bn_launch_thin_fprop (cae_thin_tc.cu); returns 1 when not applicable
+int bn_launch_thin_fprop_tc2(const ImgView& big, const unsigned char* big_u8, const ConvGeom& g, const float* wft,
+                             const float* bias, float* out, const float* dact, int act, int n, float* colsum,
+                             cudaStream_t st);
 // tcgen05 (TF32) form of bn_launch_thin_wgrad (cae_thin_tc.cu); returns 1 when not applicable
 int bn_launch_thin_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                             size_t partial_floats, float* grad, cudaStream_t st);

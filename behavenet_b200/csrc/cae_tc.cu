@@ -16,6 +16,7 @@
 // mantissa bits).
 #include <cuda.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -341,12 +342,25 @@ __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-template <int BN, int STAGES>
+// MT = M-tiles (128 output pixels each) per CTA.  The kernel is bound by L2 -> SM bandwidth (measured:
+// l1tex__m_xbar2l1tex_read_bytes / time = 10.7-14 TB/s on every im2col kernel), and every 128-pixel tile
+// re-streams the layer's whole weight slice (205 KB .. 3.3 MB) through that path; with MT = 2 one weight tile
+// feeds two accumulators, which halves the weight traffic per output pixel.
+template <int BN, int STAGES, int MT>
+struct TmaSmem {
+  static constexpr int A_BYTES = MT * BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024;
+};
+
+template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_constant__ TmaSet tm, const TcArgs a) {
   bn_pdl_trigger();
   extern __shared__ __align__(1024) unsigned char smem[];
-  using S = TcSmem<BN, STAGES>;
-  constexpr int NCOLS = BN < 32 ? 32 : BN;
+  using S = TmaSmem<BN, STAGES, MT>;
+  constexpr int NCOLS = MT * BN < 32 ? 32 : MT * BN;
+  static_assert(NCOLS <= 512 && (NCOLS & (NCOLS - 1)) == 0, "TMEM columns");
   unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -373,7 +387,7 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
   __syncthreads();
   const int HmWm = cls->Hm * cls->Wm;
   const long long M = (long long)a.n * HmWm;
-  const long long m0 = (long long)blockIdx.x * BM;
+  const long long m0 = (long long)blockIdx.x * (MT * BM);
   if (m0 >= M) {
     if (a.colpart != nullptr && a.ksplit <= 1) {
       bn_pdl_wait();
@@ -400,15 +414,23 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
     nchunks = cend > cbeg ? cend - cbeg : 0;
   }
   const uint32_t smem_base = smem_u32(smem);
+  // number of M-tiles of this CTA that hold at least one output pixel
+  const int mt_live = (M - m0 + BM - 1) / BM < MT ? (int)((M - m0 + BM - 1) / BM) : MT;
 
   if (warp < 4) {
     if (warp == 0) {
-      // ======================= TMA producer (warp 0: lane 0 the im2col tile, lane 1 the weights) ====
-      const int f0 = (int)(m0 / HmWm);
-      const int rem0 = (int)(m0 - (long long)f0 * HmWm);
-      const int ym0 = rem0 / cls->Wm, xm0 = rem0 - ym0 * cls->Wm;
+      // ======================= TMA producer (warp 0: lanes 0 .. MT-1 the im2col tiles, lane MT the weights) ====
       const int lw = tm.lw[cls_idx], lh = tm.lh[cls_idx];
-      const int w0 = lw + xm0 * a.gs, h0 = lh + ym0 * a.gs;
+      int w0 = 0, h0 = 0, f0 = 0;
+      if (tid < MT) {
+        const long long mm = m0 + (long long)tid * BM;
+        f0 = (int)(mm / HmWm);
+        const int rem0 = (int)(mm - (long long)f0 * HmWm);
+        const int ym0 = rem0 / cls->Wm, xm0 = rem0 - ym0 * cls->Wm;
+        w0 = lw + xm0 * a.gs;
+        h0 = lh + ym0 * a.gs;
+      }
+      const uint32_t tx_bytes = (uint32_t)(mt_live * BM * BK * 4 + S::B_BYTES);
       for (int c = 0; c < nchunks; ++c) {
         const int stage = c % STAGES;
         if (c >= STAGES) mbar_wait(smem_u32(empty_bar + stage), ((c / STAGES) - 1) & 1);
@@ -417,31 +439,20 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
         const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
         const uint32_t bar = smem_u32(full_bar + stage);
-        if (tid == 0) mbar_expect_tx(bar, (uint32_t)S::STAGE_BYTES);
+        if (tid == 0) mbar_expect_tx(bar, tx_bytes);
         __syncwarp();
-        if (tid == 0)
-          tma_im2col_4d(sa, &tm.a[cls_idx], bar, c0, w0, h0, f0, (uint16_t)(cls->dx[tap] - lw),
+        if (tid < mt_live)
+          tma_im2col_4d(sa + tid * (BM * BK * 4), &tm.a[cls_idx], bar, c0, w0, h0, f0, (uint16_t)(cls->dx[tap] - lw),
                         (uint16_t)(cls->dy[tap] - lh));
-        else if (tid == 1)
+        else if (tid == MT)
           tma_tile_2d(sb, &tm.b, bar, cls->wt[tap] * Ci + c0, n0);
       }
     }
     __syncwarp();
     // ======================= epilogue ============================================================
-    const long long m = m0 + tid;
-    const bool rvalid = m < M;
     if (nchunks > 0) {
       mbar_wait(smem_u32(accum_bar), 0);
       tc_fence_after();
-    }
-    long long obase = 0;
-    if (rvalid) {
-      int f = (int)(m / HmWm);
-      int rem = (int)(m - (long long)f * HmWm);
-      int ym = rem / cls->Wm;
-      int xm = rem - ym * cls->Wm;
-      int oy = cls->oy0 + a.os * ym, ox = cls->ox0 + a.os * xm;
-      obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + n0;
     }
     // all MMAs have retired, so the pipeline stages are free: reuse them as the transposition tiles
     float* tile = reinterpret_cast<float*>(smem) + warp * 1024;
@@ -451,23 +462,37 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
     if (want_col)
       for (int c = elane; c < BN; c += 32) colred[warp * BN + c] = 0.f;
 #pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
-      uint32_t r[32];
-      if (nchunks > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) r[q] = 0u;
+    for (int mt = 0; mt < mt_live; ++mt) {
+      const long long m = m0 + (long long)mt * BM + tid;
+      const bool rvalid = m < M;
+      long long obase = 0;
+      if (rvalid) {
+        int f = (int)(m / HmWm);
+        int rem = (int)(m - (long long)f * HmWm);
+        int ym = rem / cls->Wm;
+        int xm = rem - ym * cls->Wm;
+        int oy = cls->oy0 + a.os * ym, ox = cls->ox0 + a.os * xm;
+        obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + n0;
       }
-      if (a.ksplit > 1) {
-        const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
-        warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, r, nullptr, BN_ACT_NONE, tile, elane);
-      } else {
-        float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
-                          a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, want_col);
-        if (want_col) warp_fold_colsum(colred + warp * BN + j * 32, cacc, elane);
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        if (nchunks > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * BN + j * 32, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
+        if (a.ksplit > 1) {
+          const long long pidx = rvalid ? ((long long)blockIdx.z * M + m) * a.Co + n0 + j * 32 : -1;
+          warp_store_rows32(a.split_out, nullptr, BN_LEAK, pidx, r, nullptr, BN_ACT_NONE, tile, elane);
+        } else {
+          float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+          warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + j * 32 : -1, r,
+                            a.bias ? a.bias + n0 + j * 32 : nullptr, a.act, tile, elane, cacc, want_col);
+          if (want_col) warp_fold_colsum(colred + warp * BN + j * 32, cacc, elane);
+        }
       }
     }
     if (want_col) {
@@ -488,9 +513,12 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
         const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          uint64_t ad = make_desc_sw128(sa + k * 32);
-          uint64_t bd = make_desc_sw128(sb + k * 32);
-          umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
+          const uint64_t bd = make_desc_sw128(sb + k * 32);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            if (mt < mt_live)
+              umma_tf32(tmem_base + mt * BN, make_desc_sw128(sa + mt * (BM * BK * 4) + k * 32), bd, idesc,
+                        (c | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(empty_bar + stage));
       }
@@ -575,16 +603,17 @@ bool encode_tiled_2d(CUtensorMap* map, const float* p, long long rows, long long
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 int launch_tma(const TmaSet& tm, const TcArgs& a, int nclasses, int maxM, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
-  auto kern = igemm_tma_kernel<BN, STAGES>;
+  using S = TmaSmem<BN, STAGES, MT>;
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory per CTA");
+  auto kern = igemm_tma_kernel<BN, STAGES, MT>;
   static bool configured = false;
   if (!configured) {
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  dim3 grid(bn_cdiv((long long)a.n * maxM, BM), a.Co / BN, a.ksplit > 1 ? a.ksplit : nclasses);
+  dim3 grid(bn_cdiv((long long)a.n * maxM, MT * BM), a.Co / BN, a.ksplit > 1 ? a.ksplit : nclasses);
   BN_CUDA(bn_launch(kern, grid, NTHREADS, S::TOTAL, st, tm, a));
   BN_LAUNCHED();
   return 0;
@@ -829,12 +858,16 @@ struct alignas(64) WgTmaSet {
   int lw, lh;
 };
 
-template <int BN, int STAGES>
+// MT = 128-row tiles of the (tap, channel) axis per CTA: the small-image tile (the B operand) of a pixel chunk is
+// fetched once and multiplied into MT accumulators, which divides its L2 -> SM traffic by MT (this kernel, too,
+// runs at the L2 -> SM bandwidth: 1.31 GB in 122 us for encoder conv1).
+template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_constant__ WgTmaSet tm, const WgTcArgs a) {
   bn_pdl_trigger();
   extern __shared__ __align__(1024) unsigned char smem[];
-  using S = TcSmem<BN, STAGES>;
-  constexpr int NCOLS = BN < 32 ? 32 : BN;
+  using S = TmaSmem<BN, STAGES, MT>;
+  constexpr int NCOLS = MT * BN < 32 ? 32 : MT * BN;
+  static_assert(NCOLS <= 512 && (NCOLS & (NCOLS - 1)) == 0, "TMEM columns");
   unsigned char* tail = smem + STAGES * S::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -868,25 +901,25 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
   const long long mbeg = (long long)blockIdx.z * a.rows_per_split;
   const long long mend = mbeg + a.rows_per_split < M ? mbeg + a.rows_per_split : M;
   const int nchunks = mbeg < mend ? (int)((mend - mbeg + BK - 1) / BK) : 0;
-  const int kk0 = blockIdx.x * BM;
+  const int kk0 = blockIdx.x * (MT * BM);
   const int n0 = blockIdx.y * BN;
   const int Cb = a.Cb, Cs = a.Cs;
   const uint32_t smem_base = smem_u32(smem);
   constexpr uint32_t SLAB = 32 * 128;                 // 32 pixels x 32 channels
   constexpr uint32_t LBO = SLAB, SBO = 512;
+  // valid 32-channel slabs of this CTA's MT tiles (the last tile of Ktot = 25*Cb may be short) and live tiles
+  int nslab = (a.Ktot - kk0 + 31) / 32;
+  nslab = nslab > MT * (BM / 32) ? MT * (BM / 32) : nslab;
+  const int mt_live = (nslab + BM / 32 - 1) / (BM / 32);
 
   if (warp < 4) {
     if (warp == 0) {
-      // Producer warp.  A single thread issuing the <= 4 + BN/32 copies of a chunk back to back (each
-      // with its own coordinate arithmetic) was the bottleneck of this kernel, so the copies of a
-      // chunk are issued by different lanes: lane j < nslab the im2col slab j, the next BN/32 lanes
-      // the tiles of the small image.  Lane 0 posts the transaction count first.
-      // valid 32-channel slabs of this M-tile (the last tile of Ktot = 25*Cb may be short)
-      int nslab = (a.Ktot - kk0 + 31) / 32;
-      nslab = nslab > BM / 32 ? BM / 32 : nslab;
+      // Producer warp.  A single thread issuing the copies of a chunk back to back (each with its own coordinate
+      // arithmetic) was the bottleneck of this kernel, so the copies of a chunk are issued by different lanes:
+      // lane j < nslab the im2col slab j, the next BN/32 lanes the tiles of the small image.  Lane 0 posts the
+      // transaction count first.
       const uint32_t bytes = (uint32_t)(nslab * SLAB + (BN / 32) * SLAB);
       const int lane = tid;
-      // this lane's fixed slab (filter tap, channel offset) or small-image column block
       int my_cb0 = 0;
       uint16_t my_dx = 0, my_dy = 0;
       if (lane < nslab) {
@@ -922,21 +955,24 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
       mbar_wait(smem_u32(accum_bar), 0);
       tc_fence_after();
     }
-    const int kk = kk0 + tid;
-    const long long prow_idx = ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
     float* tile = reinterpret_cast<float*>(smem) + warp * 1024;      // pipeline stages are idle now
 #pragma unroll 1
-    for (int j = 0; j < BN / 32; ++j) {
-      uint32_t r[32];
-      if (nchunks > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, r);
-        tmem_ld_wait();
-      } else {
+    for (int mt = 0; mt < mt_live; ++mt) {
+      const int kk = kk0 + mt * BM + tid;
+      const long long prow_idx = ((long long)blockIdx.z * a.Ktot + kk) * Cs + n0;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        if (nchunks > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + mt * BN + j * 32, r);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) r[q] = 0u;
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
+        warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, r, nullptr, BN_ACT_NONE, tile,
+                          tid & 31);
       }
-      warp_store_rows32(a.partial, nullptr, BN_LEAK, kk < a.Ktot ? prow_idx + j * 32 : -1, r, nullptr, BN_ACT_NONE, tile,
-                        tid & 31);
     }
     tc_fence_before();
   } else {
@@ -950,9 +986,12 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
         const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          uint64_t ad = make_desc_mn_sw128(sa + k * 2 * SBO, LBO, SBO);
-          uint64_t bd = make_desc_mn_sw128(sb + k * 2 * SBO, LBO, SBO);
-          umma_tf32(tmem_base, ad, bd, idesc, (c | k) != 0 ? 1u : 0u);
+          const uint64_t bd = make_desc_mn_sw128(sb + k * 2 * SBO, LBO, SBO);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            if (mt < mt_live)
+              umma_tf32(tmem_base + mt * BN, make_desc_mn_sw128(sa + mt * (BM / 32) * SLAB + k * 2 * SBO, LBO, SBO), bd, idesc,
+                        (c | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(empty_bar + stage));
       }
@@ -967,16 +1006,17 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 int launch_wgrad_tma(const WgTmaSet& tm, const WgTcArgs& a, int splits, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
-  auto kern = wgrad_tma_kernel<BN, STAGES>;
+  using S = TmaSmem<BN, STAGES, MT>;
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory per CTA");
+  auto kern = wgrad_tma_kernel<BN, STAGES, MT>;
   static bool configured = false;
   if (!configured) {
     BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  dim3 grid(bn_cdiv(a.Ktot, BM), a.Cs / BN, splits);
+  dim3 grid(bn_cdiv(a.Ktot, MT * BM), a.Cs / BN, splits);
   BN_CUDA(bn_launch(kern, grid, NTHREADS, S::TOTAL, st, tm, a));
   BN_LAUNCHED();
   return 0;
@@ -1553,6 +1593,18 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsu
 
 }  // namespace
 
+namespace {
+// tile configuration of the TMA kernels: "stages,mtiles" from BN_WG<bn> / BN_IG<bn>, else the defaults
+struct TileCfg { int stages, mt; };
+TileCfg env_cfg(const char* name, TileCfg dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  TileCfg c = dflt;
+  if (sscanf(e, "%d,%d", &c.stages, &c.mt) != 2) return dflt;
+  return c;
+}
+}  // namespace
+
 int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float* bias, float* out,
                        int Ho, int Wo, int Co, const float* dact, const TapClass* d_classes,
                        const TapClass* h_classes, int nclasses, int maxM, int maxtaps, int gs, int os, int n,
@@ -1598,21 +1650,36 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   // one tile per CTA below: a flush per tile makes ~10^4 same-address atomics per column, which costs
   // more than the separate column-sum pass saves (measured).  Instead every CTA writes its column sums
   // as one row of a partial table and the batched reduction kernel of the backward call adds them up.
-  const long long col_rows = (long long)bn_cdiv(M, BM) * nclasses;
+  // two M-tiles per CTA (shared weight tiles) when that still fills the machine; BN_IG<co>="stages,mtiles" overrides
+  static const TileCfg ig32 = env_cfg("BN_IG32", {3, 2}), ig64 = env_cfg("BN_IG64", {2, 2}), ig128 = env_cfg("BN_IG128", {2, 2});
+  const TileCfg ig = Co == 32 ? ig32 : Co == 64 ? ig64 : Co == 128 ? ig128 : TileCfg{4, 1};
+  const TmaSet* tm = get_tma_set(in, wt, wrow, Co, bn, d_classes, h_classes, nclasses, gs, n);
+  const int MTs = (tm && ig.mt == 2 && ksplit == 1 && Co <= 128 && (long long)bn_cdiv(M, 2 * BM) * (Co / bn) * nclasses >= 148)
+                      ? 2 : 1;
+  const long long col_rows = (long long)bn_cdiv(M, MTs * BM) * nclasses;
   const bool part = a.colsum != nullptr && colpart != nullptr && !((uintptr_t)colpart & 15) && bn_reduce_deferring() &&
                     (size_t)col_rows * Co <= colpart_floats;
   float* colsum_out = a.colsum;
   a.colsum = nullptr;
   a.colpart = part ? colpart : nullptr;
   if (colsum_fused) *colsum_fused = 0;
-  const TmaSet* tm = get_tma_set(in, wt, wrow, Co, bn, d_classes, h_classes, nclasses, gs, n);
   if (tm) {
     TmaSet local = *tm;      // copied into the kernel parameter space (__grid_constant__)
-    switch (Co) {
-      case 32: r = launch_tma<32, 4>(local, a, nclasses, maxM, st); break;
-      case 64: r = launch_tma<64, 4>(local, a, nclasses, maxM, st); break;
-      case 128: r = launch_tma<128, 3>(local, a, nclasses, maxM, st); break;
-      default: r = launch_tma<256, 4>(local, a, nclasses, maxM, st); break;
+    const int code = Co * 100 + MTs * 10 + ig.stages;
+    switch (MTs == ig.mt ? code : Co * 100 + 10 + (Co == 128 ? 3 : 4)) {
+      case 3200 + 14: r = launch_tma<32, 4, 1>(local, a, nclasses, maxM, st); break;
+      case 3200 + 23: r = launch_tma<32, 3, 2>(local, a, nclasses, maxM, st); break;
+      case 6400 + 14: r = launch_tma<64, 4, 1>(local, a, nclasses, maxM, st); break;
+      case 6400 + 22: r = launch_tma<64, 2, 2>(local, a, nclasses, maxM, st); break;
+      case 6400 + 23: r = launch_tma<64, 3, 2>(local, a, nclasses, maxM, st); break;
+      case 6400 + 24: r = launch_tma<64, 4, 2>(local, a, nclasses, maxM, st); break;
+      case 12800 + 13: r = launch_tma<128, 3, 1>(local, a, nclasses, maxM, st); break;
+      case 12800 + 22: r = launch_tma<128, 2, 2>(local, a, nclasses, maxM, st); break;
+      case 12800 + 23: r = launch_tma<128, 3, 2>(local, a, nclasses, maxM, st); break;
+      case 12800 + 24: r = launch_tma<128, 4, 2>(local, a, nclasses, maxM, st); break;
+      default:
+        if (Co >= 256) r = launch_tma<256, 4, 1>(local, a, nclasses, maxM, st);
+        else BN_FAIL("igemm: no kernel instance for Co=%d stages/M-tiles code %d", Co, code);
     }
   } else {
     switch (Co) {
@@ -1666,6 +1733,28 @@ const WgTmaSet* get_wgrad_tma_set(const ImgView& big, const float* small, const 
 
 }  // namespace
 
+namespace {
+TileCfg wg_cfg(int bn) {
+  static const TileCfg c32 = env_cfg("BN_WG32", {3, 2}), c64 = env_cfg("BN_WG64", {2, 2}), c128 = env_cfg("BN_WG128", {3, 1}),
+                       c256 = env_cfg("BN_WG256", {3, 2});
+  return bn == 32 ? c32 : bn == 64 ? c64 : bn == 128 ? c128 : c256;
+}
+int wg_mtiles(int bn) { return wg_cfg(bn).mt; }
+int wg_stages(int bn, int mt) {
+  const TileCfg c = wg_cfg(bn);
+  if (c.mt == mt) return c.stages;
+  return bn == 128 ? 3 : 4;          // fell back to one M-tile (short Ktot): the single-tile defaults
+}
+int wg_ctas_per_sm(int bn, int mt) {
+  const size_t stage = (size_t)mt * 16384 + (size_t)bn * 128;
+  const size_t total = wg_stages(bn, mt) * stage + 2048;
+  int c = (int)((227 * 1024) / total);
+  const int tmem = 512 / (mt * bn < 32 ? 32 : mt * bn);
+  c = c < tmem ? c : tmem;
+  return c < 1 ? 1 : (c > 2 ? 2 : c);
+}
+}  // namespace
+
 int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g, int n, float* partial,
                        size_t partial_floats, float* grad, cudaStream_t st) {
   if (n <= 0 || grad == nullptr) return 0;
@@ -1685,10 +1774,14 @@ int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g
   const int Ktot = g.k * g.k * g.Cb;
   const long long M = (long long)n * g.Hs * g.Ws;
   if (M < 256) return 1;
-  long long tiles = (long long)bn_cdiv(Ktot, BM) * (Cs / bn);
+  // several (tap, channel) tiles per CTA share every small-image tile when the TMA path is available
+  const WgTmaSet* tm = get_wgrad_tma_set(big, small, g, n, M);
+  int MTs = tm ? wg_mtiles(bn) : 1;
+  while (MTs > 1 && Ktot <= (MTs / 2) * BM) MTs /= 2;
+  long long tiles = (long long)bn_cdiv(Ktot, MTs * BM) * (Cs / bn);
   // one full wave and no more: the CTAs are long-running (each walks its whole pixel slice), so a
   // grid that exceeds the resident slots by a handful of CTAs doubles the kernel time
-  const long long slots = 148LL * (bn == 256 ? 1 : 2);      // 192 KB of stages per CTA at BN = 256, 96 KB otherwise
+  const long long slots = 148LL * wg_ctas_per_sm(bn, MTs);
   long long splits = slots / tiles;
   if (splits < 1) splits = 1;
   long long maxs = (M + 127) / 128;
@@ -1704,14 +1797,25 @@ int bn_launch_wgrad_tc(const ImgView& big, const float* small, const ConvGeom& g
   a.Cs = Cs; a.cls = g.d_fprop; a.gs = g.s; a.n = n; a.Ktot = Ktot; a.rows_per_split = rps;
   a.partial = partial;
   int r;
-  const WgTmaSet* tm = get_wgrad_tma_set(big, small, g, n, M);
   if (tm) {
     WgTmaSet local = *tm;
-    switch (bn) {
-      case 32: r = launch_wgrad_tma<32, 4>(local, a, (int)splits, st); break;
-      case 64: r = launch_wgrad_tma<64, 4>(local, a, (int)splits, st); break;
-      case 128: r = launch_wgrad_tma<128, 3>(local, a, (int)splits, st); break;
-      default: r = launch_wgrad_tma<256, 4>(local, a, (int)splits, st); break;
+    // (stages, M-tiles) per BN: defaults are the measured-best ones (profiles/r02_tile_sweep.txt); BN_WG<bn>="s,m" overrides
+    const int cfg = MTs * 10 + wg_stages(bn, MTs);
+    switch (bn * 100 + cfg) {
+      case 3200 + 14: r = launch_wgrad_tma<32, 4, 1>(local, a, (int)splits, st); break;
+      case 3200 + 23: r = launch_wgrad_tma<32, 3, 2>(local, a, (int)splits, st); break;
+      case 6400 + 14: r = launch_wgrad_tma<64, 4, 1>(local, a, (int)splits, st); break;
+      case 6400 + 22: r = launch_wgrad_tma<64, 2, 2>(local, a, (int)splits, st); break;
+      case 6400 + 23: r = launch_wgrad_tma<64, 3, 2>(local, a, (int)splits, st); break;
+      case 6400 + 42: r = launch_wgrad_tma<64, 2, 4>(local, a, (int)splits, st); break;
+      case 6400 + 43: r = launch_wgrad_tma<64, 3, 4>(local, a, (int)splits, st); break;
+      case 12800 + 13: r = launch_wgrad_tma<128, 3, 1>(local, a, (int)splits, st); break;
+      case 12800 + 22: r = launch_wgrad_tma<128, 2, 2>(local, a, (int)splits, st); break;
+      case 12800 + 23: r = launch_wgrad_tma<128, 3, 2>(local, a, (int)splits, st); break;
+      case 12800 + 42: r = launch_wgrad_tma<128, 2, 4>(local, a, (int)splits, st); break;
+      case 25600 + 14: r = launch_wgrad_tma<256, 4, 1>(local, a, (int)splits, st); break;
+      case 25600 + 23: r = launch_wgrad_tma<256, 3, 2>(local, a, (int)splits, st); break;
+      default: BN_FAIL("wgrad: no kernel instance for BN=%d stages/M-tiles code %d", bn, cfg);
     }
     if (r) return r;
     return bn_launch_wgrad_reduce(partial, (int)splits, Ktot, Cs, g.Cb, g.k * g.k, g.d_fprop, grad, st);

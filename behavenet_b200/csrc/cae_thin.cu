@@ -620,6 +620,10 @@ int bn_launch_thin_fprop(const ImgView& big, const ConvGeom& g, const float* wf,
       !(bias && ((uintptr_t)bias & 15))) {
     // tensor-core form (TF32): wft = K-major weights [c_small][(tap, c_big)]
     if (colsum_fused) *colsum_fused = colsum != nullptr;
+    {
+      const int r2 = bn_launch_thin_fprop_tc2(big, big_u8, g, wft, bias, out, dact, act, n, colsum, st);
+      if (r2 <= 0) return r2;
+    }
     switch (g.Cb) {
       case 1: return launch_thin_fprop_tc<1>(t, wft, bias, out, dact, act, it, g.Cs / 32, st, colsum);
       case 2: return launch_thin_fprop_tc<2>(t, wft, bias, out, dact, act, it, g.Cs / 32, st, colsum);

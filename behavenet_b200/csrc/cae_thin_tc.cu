@@ -346,6 +346,255 @@ int resident_ctas() {
 
 
 // ------------------------------------------------------------------------------------------------
+// thin image -> fat image (first encoder layer forward; last decoder layer backward-data), second form.
+// Same arithmetic as thin_fprop_tc_kernel (cae_thin.cu): every output pixel's 25*CB patch values are one row of
+// a K-major A tile, the TF32 weights sit in a resident B tile, an 8 x 32-pixel tile is two M = 128 MMAs per
+// k-chunk.  There the 256 threads of a CTA gather, wait for the MMAs and run the epilogue in turn; here the
+// three jobs belong to different warps and overlap: eight builder warps (patch staging + im2col gather into a
+// double-buffered A), one control warp (MMA issue into a double-buffered accumulator) and eight epilogue warps
+// (TMEM -> bias / LeakyReLU / derivative mask -> 128-byte row stores, fused column sums).
+// ------------------------------------------------------------------------------------------------
+constexpr int FT_H = 8, FT_W = 32;                       // small-pixel tile
+constexpr int FP_ROWS = 2 * (FT_H - 1) + 5;              // 19 patch rows
+constexpr int FP_COLS = 72;
+constexpr int FW_THREADS = 17 * 32;                      // warps 0-7 builders, 8-15 epilogue, 16 control
+
+struct ThinFwArgs {
+  ImgView thin;
+  const unsigned char* thin8;      // raw 0..255 video with the strides of `thin`, or NULL
+  int Hs, Ws, Cs, pt, pl, n;
+  const float* wft;                // [c_small][(tap, c_big)] TF32-rounded
+  const float* bias;
+  float* out;
+  const float* dact;
+  int act;
+  float* colsum;
+  int tiles_x, tiles_per_frame;
+  long long total_tiles;
+};
+
+template <int CB>
+struct ThinFwSmem {
+  static constexpr int NKC = (25 * CB + 31) / 32;
+  static constexpr int NBUF = NKC <= 2 ? 2 : 1;                       // A buffers that fit next to the rest
+  static constexpr int A_TILE = 2 * NKC * 16384;
+  static constexpr int OFF_B = NBUF * A_TILE;
+  static constexpr int B_BYTES = NKC * 4096;
+  static constexpr int OFF_PATCH = OFF_B + B_BYTES;
+  static constexpr int PATCH = CB * FP_ROWS * FP_COLS * 4;
+  static constexpr int OFF_EPI = OFF_PATCH + ((2 * PATCH + 1023) & ~1023);
+  static constexpr int OFF_BAR = OFF_EPI + 8 * 4096;
+  static constexpr int TOTAL = OFF_BAR + 128;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(FW_THREADS, 1) thin_fprop_tc2_kernel(const ThinFwArgs a) {
+  bn_pdl_trigger();
+  using S = ThinFwSmem<CB>;
+  constexpr int NKC = S::NKC, KTOT = 25 * CB, NBUF = S::NBUF;
+  extern __shared__ __align__(1024) unsigned char sm[];
+  float* patch[2] = {reinterpret_cast<float*>(sm + S::OFF_PATCH), reinterpret_cast<float*>(sm + S::OFF_PATCH + S::PATCH)};
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sm + S::OFF_BAR);     // [2] builders done (8 warp arrivals)
+  uint64_t* a_free = a_full + 2;                                       // [2] MMAs that read A[s] retired
+  uint64_t* acc_full = a_free + 2;                                     // [2]
+  uint64_t* acc_free = acc_full + 2;                                   // [2] 8 epilogue-warp arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_free + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = blockIdx.y * 32;                                      // channel group of this CTA
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(a_full + s), 8);
+      mbar_init(smem_u32(a_free + s), 1);
+      mbar_init(smem_u32(acc_full + s), 1);
+      mbar_init(smem_u32(acc_free + s), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) tmem_alloc<128>(smem_u32(tmem_ptr));
+  bn_pdl_wait();
+  // resident B tile: rows n = channel, k-chunk kc, 16-byte chunk c at position c ^ (n & 7)
+  for (int i = tid; i < NKC * 32 * 8; i += FW_THREADS) {
+    const int kc = i / 256, rem = i - kc * 256;
+    const int n = rem >> 3, c = rem & 7;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = kc * 32 + c * 4 + e;
+      v[e] = k < KTOT ? __ldg(a.wft + (long long)(c0 + n) * KTOT + k) : 0.f;
+    }
+    *reinterpret_cast<float4*>(sm + S::OFF_B + kc * 4096 + n * 128 + ((c ^ (n & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t sbase = smem_u32(sm);
+  const long long total = a.total_tiles;
+  auto decode = [&](long long t, int& f, int& y0, int& x0) {
+    f = (int)(t / a.tiles_per_frame);
+    const int tt = (int)(t - (long long)f * a.tiles_per_frame);
+    const int ty = tt / a.tiles_x;
+    y0 = ty * FT_H;
+    x0 = (tt - ty * a.tiles_x) * FT_W;
+  };
+  int n_my = 0;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) ++n_my;
+
+  if (warp < 8) {
+    // ======================= builders ============================================================
+    auto issue_patch = [&](float* dst, long long t) {
+      int f, y0, x0;
+      decode(t, f, y0, x0);
+      for (int i = tid; i < CB * FP_ROWS * FP_COLS; i += 256) {
+        const int c = i / (FP_ROWS * FP_COLS);
+        const int rem = i - c * FP_ROWS * FP_COLS;
+        const int r = rem / FP_COLS, col = rem - r * FP_COLS;
+        const int y = 2 * y0 - a.pt + r, x = 2 * x0 - a.pl + col;
+        const bool ok = (unsigned)y < (unsigned)a.thin.H && (unsigned)x < (unsigned)a.thin.W;
+        const long long off = ok ? (long long)f * a.thin.sn + (long long)y * a.thin.sy + (long long)x * a.thin.sx +
+                                       (long long)c * a.thin.sc
+                                 : 0;
+        if (a.thin8 != nullptr) dst[i] = ok ? __fdiv_rn((float)__ldg(a.thin8 + off), 255.f) : 0.f;   // numpy's float32(u8) / 255
+        else cp_async4z(dst + i, a.thin.p + off, ok);
+      }
+    };
+    const int trow = tid >> 5, tcol = lane;                  // this thread's output pixel of the 8 x 32 tile
+    const int mt = trow >> 2, arow = (trow & 3) * 32 + tcol; // M-tile and row inside it
+    long long t = blockIdx.x;
+    if (n_my > 0) issue_patch(patch[0], t);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int it = 0; it < n_my; ++it, t += gridDim.x) {
+      const int pbuf = it & 1, abuf = NBUF == 2 ? (it & 1) : 0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // patch[pbuf] complete; everyone left patch[pbuf ^ 1]
+      if (it + 1 < n_my) issue_patch(patch[pbuf ^ 1], t + gridDim.x);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (it >= NBUF) mbar_wait(smem_u32(a_free + abuf), ((it - NBUF) / NBUF) & 1);
+      // this thread's im2col row: k = (ky*5 + kx)*CB + cb  <-  patch[cb][2*trow + ky][2*tcol + kx]
+      const float* p0 = patch[pbuf] + (2 * trow) * FP_COLS + 2 * tcol;
+      unsigned char* abase = sm + abuf * S::A_TILE + (mt * NKC) * 16384 + arow * 128;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = kc * 32 + c * 4 + e;                // compile-time
+            if (k < KTOT) {
+              const int tap = k / CB, cb = k - tap * CB;
+              v[e] = p0[(cb * FP_ROWS + tap / 5) * FP_COLS + tap % 5];
+            } else {
+              v[e] = 0.f;
+            }
+          }
+          *reinterpret_cast<float4*>(abase + kc * 16384 + ((c ^ (arow & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(a_full + abuf));
+    }
+  } else if (warp == 16) {
+    // ======================= control warp: MMA issue =============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, 32);
+      const uint64_t ad0 = desc_k_sw128(sbase), bd0 = desc_k_sw128(sbase + S::OFF_B);
+      for (int it = 0; it < n_my; ++it) {
+        const int abuf = NBUF == 2 ? (it & 1) : 0, cbuf = it & 1;
+        if (it >= 2) {
+          mbar_wait(smem_u32(acc_free + cbuf), ((it >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(a_full + abuf), (it / NBUF) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(tmem_base + cbuf * 64 + m * 32,
+                        ad0 + (uint64_t)((abuf * S::A_TILE + (m * NKC + kc) * 16384 + k * 32) >> 4),
+                        bd0 + (uint64_t)((kc * 4096 + k * 32) >> 4), idesc, (kc | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(a_free + abuf));
+        umma_commit(smem_u32(acc_full + cbuf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue warps ======================================================
+    const int e = warp - 8, q = e & 3, m = e >> 2;           // TMEM lane quarter (= warp % 4) and M-tile
+    float* etile = reinterpret_cast<float*>(sm + S::OFF_EPI) + e * 1024;
+    float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long t = blockIdx.x;
+    for (int it = 0; it < n_my; ++it, t += gridDim.x) {
+      const int cbuf = it & 1;
+      int f, y0, x0;
+      decode(t, f, y0, x0);
+      mbar_wait(smem_u32(acc_full + cbuf), (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + cbuf * 64 + m * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(acc_free + cbuf));
+      const int oy = y0 + m * 4 + q, ox = x0 + lane;
+      const bool valid = oy < a.Hs && ox < a.Ws;
+      const long long idx = valid ? (((long long)f * a.Hs + oy) * a.Ws + ox) * a.Cs + c0 : -1;
+      warp_store_rows32(a.out, a.dact, BN_LEAK, idx, r, a.bias ? a.bias + c0 : nullptr, a.act, etile, lane, cacc,
+                        a.colsum != nullptr);
+    }
+    if (a.colsum != nullptr) {
+      // 8 warps x 32 columns -> one atomic per column and CTA
+      float* red = reinterpret_cast<float*>(sm + S::OFF_EPI);
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        cacc.x += __shfl_xor_sync(0xffffffffu, cacc.x, o);
+        cacc.y += __shfl_xor_sync(0xffffffffu, cacc.y, o);
+        cacc.z += __shfl_xor_sync(0xffffffffu, cacc.z, o);
+        cacc.w += __shfl_xor_sync(0xffffffffu, cacc.w, o);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");          // every epilogue warp is done with its tile
+      if (lane < 8) *(reinterpret_cast<float4*>(red + e * 32) + lane) = cacc;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (e == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) sum += red[w8 * 32 + lane];
+        atomicAdd(a.colsum + c0 + lane, sum);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+template <int CB>
+int launch_fw(const ThinFwArgs& a, int cgroups, cudaStream_t st) {
+  using S = ThinFwSmem<CB>;
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory per CTA");
+  auto kern = thin_fprop_tc2_kernel<CB>;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    configured = true;
+  }
+  long long blocks = 148 / cgroups;
+  if (blocks < 1) blocks = 1;
+  if (blocks > a.total_tiles) blocks = a.total_tiles;
+  BN_CUDA(bn_launch(kern, dim3((unsigned)blocks, cgroups), FW_THREADS, S::TOTAL, st, a));
+  BN_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Last decoder layer forward (ConvTranspose2d k5 s2 into 1-4 image channels + sigmoid + fused reconstruction
 // loss, aes.py:463-470 + losses.py:36-96) as ONE small GEMM plus a col2im epilogue.
 //
@@ -734,5 +983,31 @@ int bn_launch_thin_dgrad_tc(const float* small, const ConvGeom& g, const float* 
     case 2: return launch_dg<2>(map, a, st);
     case 3: return launch_dg<3>(map, a, st);
     default: return launch_dg<4>(map, a, st);
+  }
+}
+
+// thin image -> fat image, decoupled-role tensor-core form (see thin_fprop_tc2_kernel).  Returns 1 when not
+// applicable (the caller then uses thin_fprop_tc_kernel / the fp32 kernel of cae_thin.cu).
+int bn_launch_thin_fprop_tc2(const ImgView& big, const unsigned char* big_u8, const ConvGeom& g, const float* wft,
+                             const float* bias, float* out, const float* dact, int act, int n, float* colsum,
+                             cudaStream_t st) {
+  // Measured on B200 (C2 step, same box): 2.346 ms with the single-role kernel of cae_thin.cu (two CTAs per SM
+  // overlap each other) vs 2.367 ms with this one-CTA-per-SM role split -- parity-tested, kept behind
+  // BN_THIN_FPROP_V2=1 for the record, off by default.
+  static const bool on = [] { const char* e = getenv("BN_THIN_FPROP_V2"); return e && e[0] == '1'; }();
+  if (!on || n <= 0) return 1;
+  if (!(g.k == 5 && g.s == 2 && g.Cb >= 1 && g.Cb <= 4 && g.Cs % 32 == 0)) return 1;
+  if (((uintptr_t)out & 15) || (dact && ((uintptr_t)dact & 15)) || (bias && ((uintptr_t)bias & 15))) return 1;
+  ThinFwArgs a;
+  a.thin = big; a.thin8 = big_u8; a.Hs = g.Hs; a.Ws = g.Ws; a.Cs = g.Cs; a.pt = g.pt; a.pl = g.pl; a.n = n;
+  a.wft = wft; a.bias = bias; a.out = out; a.dact = dact; a.act = act; a.colsum = colsum;
+  a.tiles_x = bn_cdiv(g.Ws, FT_W);
+  a.tiles_per_frame = a.tiles_x * bn_cdiv(g.Hs, FT_H);
+  a.total_tiles = (long long)a.tiles_per_frame * n;
+  switch (g.Cb) {
+    case 1: return launch_fw<1>(a, g.Cs / 32, st);
+    case 2: return launch_fw<2>(a, g.Cs / 32, st);
+    case 3: return launch_fw<3>(a, g.Cs / 32, st);
+    default: return launch_fw<4>(a, g.Cs / 32, st);
   }
 }

@@ -1408,6 +1408,259 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA-pair form of the halo kernel for C_out = 32 (ConvTranspose2d forward into / Conv2d backward-data out of
+// the 32-channel 64 x 64 maps): two CTAs of a cluster (the two SMs of a TPC) each own a 16 x 8 tile and issue
+// ONE tcgen05.mma.cta_group::2 per window: M = 256 (128 rows per CTA), N = ncls * 32, with the weight operand
+// SPLIT between the two CTAs (each holds N / 2 rows at the same shared-memory offset).
+//
+// Why: dbg timestamps show the one-CTA kernel waiting for data, not for the tensor pipe -- 7.2 us per tile go by
+// with every MMA switched off -- and 200 of the 246 KB a tile pulls through L2 are the layer's WEIGHTS (205 KB in
+// total), re-streamed by each of the 2048 tiles.  Split over a CTA pair the whole layer's weights are 102 KB per
+// SM: they are loaded ONCE per CTA and stay resident, the ring of weight tiles disappears, and what is left to
+// stream is the 46 KB of input halo per tile.
+//
+// Roles per CTA: warps 0-7 epilogue (own 128 accumulator rows, two classes each), warp 8 MMA issue (leader CTA only), warp 9 TMA.
+// Cross-CTA signalling: both CTAs' TMA copies complete on the LEADER's "full" barriers (cp.async.bulk.tensor
+// .cta_group::2 with the peer bit of the mbarrier address cleared), the leader's tcgen05.commit multicasts to both
+// CTAs' "empty" / "accumulator ready" barriers, and the peer's epilogue warps release an accumulator with a remote
+// mbarrier.arrive on the leader's barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address of the even CTA of a pair
+
+__device__ __forceinline__ void tma_tile_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c, int w, int h,
+                                                 int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void tma_tile_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait_cluster(bar, parity); ++it)
+    if (it > (1u << 28)) __trap();
+}
+
+constexpr int PAIR_MAXCHUNK = 2;                      // C_in <= 64: half of the layer's weights fits one SM
+struct HaloPairArgs {
+  HaloArgs h;
+  unsigned int w_off[PAIR_MAXCHUNK][HALO_MAXG];       // byte offset of (chunk, group)'s half weight tile in the W region
+  unsigned int w_bytes;                               // resident bytes per CTA
+};
+struct alignas(64) HaloPairMaps {
+  CUtensorMap a;       // NHWC input, box 32 ch x 10 px x 18 rows x 1 frame
+  CUtensorMap b16;     // K-major weights, box 32 x 16 rows
+  CUtensorMap b32;     // K-major weights, box 32 x 32 rows
+};
+constexpr int PAIR_EPI_WARPS = 8;                     // + warp 8 MMA issue, warp 9 TMA
+constexpr int PAIR_THREADS = (PAIR_EPI_WARPS + 2) * 32;
+constexpr int PAIR_SLOTS = 4;                         // halo buffers in flight: TMA latency / MMA time per chunk ~ 2-3
+struct HaloPairSmem {
+  static constexpr int W_MAX = 100 * 1024;            // 25 class-taps x 64 input channels x 16 rows x 4 B
+  static constexpr int OFF_A = W_MAX;
+  static constexpr int OFF_EPI = OFF_A + PAIR_SLOTS * HALO_ASTRIDE;
+  static constexpr int OFF_BAR = OFF_EPI + PAIR_EPI_WARPS * 4096;
+  static constexpr int TOTAL = OFF_BAR + 8 * (2 * PAIR_SLOTS + 6) + 32;
+};
+static_assert(HaloPairSmem::TOTAL <= 227 * 1024, "shared memory per CTA");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+dgrad_halo_pair_kernel(const __grid_constant__ HaloPairMaps maps, const __grid_constant__ HaloPairArgs pa) {
+  bn_pdl_trigger();
+  constexpr int NB = 32, ACC_COLS = 4 * NB, NCOLS = 2 * ACC_COLS;
+  using S = HaloPairSmem;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const HaloArgs& h = pa.h;
+  const TcArgs& a = h.a;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);   // [1]  (leader's is the one waited on)
+  uint64_t* a_full = w_full + 1;          // [PAIR_SLOTS]  leader: both CTAs' halo bytes
+  uint64_t* a_empty = a_full + PAIR_SLOTS;   // [PAIR_SLOTS]  multicast commit
+  uint64_t* acc_full = a_empty + PAIR_SLOTS; // [2]  multicast commit
+  uint64_t* acc_empty = acc_full + 2;     // [2]  leader: 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(smem_u32(w_full), 1);
+    for (int s = 0; s < PAIR_SLOTS; ++s) {
+      mbar_init(smem_u32(a_full + s), 1);
+      mbar_init(smem_u32(a_empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(acc_full + s), 1);
+      mbar_init(smem_u32(acc_empty + s), 2 * PAIR_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PAIR_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // both CTAs' barriers exist before any remote signal / copy
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  bn_pdl_wait();
+  const int Ci = a.Ci;
+  const int nchunk = Ci / BK;
+  const uint32_t smem_base = smem_u32(smem);
+  const long long total = h.total_tiles;
+  const long long npairs = (total + 1) / 2;
+  const long long p_first = blockIdx.x >> 1, p_step = gridDim.x >> 1;
+
+  if (warp < PAIR_EPI_WARPS) {
+    // ======================= epilogue (own tile, own 128 accumulator rows) =======================
+    // eight warps: warp w drains TMEM lanes 32 (w & 3) .. (its 32 pixels) of two of the four classes
+    float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
+    const int elane = tid & 31;
+    const int q = warp & 3, chalf = warp >> 2;
+    const int pix = q * 32 + elane;
+    float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t leader_acc_empty[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(leader_acc_empty[s]) : "r"(smem_u32(acc_empty + s)));
+    int ti = 0;
+    for (long long P = p_first; P < npairs; P += p_step, ++ti) {
+      const long long T = 2 * P + rank;
+      const bool tvalid = T < total;
+      const int f = (int)(T / h.tiles_per_frame);
+      const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+      const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+      const int ym = by * 16 + (pix >> 3), xm = bx * 8 + (pix & 7);
+      const int buf = ti & 1;
+      mbar_wait_cluster(smem_u32(acc_full + buf), (ti >> 1) & 1);
+      tc_fence_after();
+      // (computing the eight row offsets per lane arithmetically instead of gathering them with shuffles, and
+      // fetching both classes' accumulators before the first store, measured 8 % SLOWER: 82 vs 76 us per launch)
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * chalf + cc;
+        const bool rvalid = tvalid && ym < h.Hm[c] && xm < h.Wm[c];
+        const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
+        const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + h.pos[c] * NB, r);
+        tmem_ld_wait();
+        warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase : -1, r, a.bias, a.act, tile, elane, cacc, a.colsum != nullptr);
+      }
+      tc_fence_before();                       // this thread's TMEM reads of the buffer are complete
+      __syncwarp();
+      if (elane == 0) mbar_arrive_cluster(leader_acc_empty[buf]);
+    }
+    if (a.colsum) warp_flush_colsum(a.colsum, cacc, elane);
+  } else if (warp == PAIR_EPI_WARPS) {
+    // ======================= MMA issuer: leader CTA only =========================================
+    if (rank == 0 && (tid & 31) == 0) {
+      mbar_wait_cluster(smem_u32(w_full), 0);  // both CTAs' resident weights have landed
+      tc_fence_after();
+      int ai = 0, ti = 0;
+      for (long long P = p_first; P < npairs; P += p_step, ++ti) {
+        const int buf = ti & 1;
+        if (ti >= 2) {
+          mbar_wait_cluster(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        for (int c = 0; c < nchunk; ++c, ++ai) {
+          const int slot = ai % PAIR_SLOTS;
+          mbar_wait_cluster(smem_u32(a_full + slot), (ai / PAIR_SLOTS) & 1);
+          tc_fence_after();
+          const uint32_t abuf = smem_base + S::OFF_A + slot * HALO_ASTRIDE;
+          for (int gi = 0; gi < h.ngroups; ++gi) {
+            const HaloGroup g = h.g[gi];
+            const uint32_t idesc = make_idesc(256, g.ncls * NB);
+            const uint32_t acc = tmem_base + buf * ACC_COLS + g.col0 * NB;
+            const uint32_t arow = abuf + g.row_off * 128;
+            const uint32_t sb = smem_base + pa.w_off[c][gi];
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k)
+              umma_tf32_pair(acc, make_desc_sw128_sbo(arow + k * 32, HALO_W * 128), make_desc_sw128(sb + k * 32), idesc,
+                             (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit_pair(smem_u32(a_empty + slot));
+        }
+        umma_commit_pair(smem_u32(acc_full + buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= TMA: resident half weights once, then this CTA's halos ===============
+    const int lane = tid & 31;
+    const uint32_t leader_w_full = smem_u32(w_full) & PEER_BIT_MASK;
+    if (lane == 0) {
+      if (rank == 0) mbar_expect_tx(smem_u32(w_full), 2u * pa.w_bytes);
+    }
+    __syncwarp();
+    // one lane per (chunk, group): this CTA's half of the stacked class tiles
+    for (int i = lane; i < nchunk * h.ngroups; i += 32) {
+      const int c = i / h.ngroups, gi = i - c * h.ngroups;
+      const HaloGroup g = h.g[gi];
+      const uint32_t dst = smem_base + pa.w_off[c][gi];
+      if (g.ncls == 1) {
+        tma_tile_2d_pair(dst, &maps.b16, leader_w_full, g.wt[0] * Ci + c * BK, (int)rank * 16);
+      } else {
+        const int half = g.ncls / 2;                // whole class tiles per CTA
+        for (int j = 0; j < half; ++j)
+          tma_tile_2d_pair(dst + j * (NB * 128), &maps.b32, leader_w_full, g.wt[rank * half + j] * Ci + c * BK, 0);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t leader_a_full0 = smem_u32(a_full) & PEER_BIT_MASK;
+      int q = 0;
+      for (long long P = p_first; P < npairs; P += p_step) {
+        const long long T = 2 * P + rank;
+        // a tile past the end (odd tile count) loads frame n: out of bounds, zero fill, nothing stored
+        const int f = (int)(T / h.tiles_per_frame);
+        const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+        const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+        for (int c = 0; c < nchunk; ++c, ++q) {
+          const int slot = q % PAIR_SLOTS;
+          if (q >= PAIR_SLOTS) mbar_wait_cluster(smem_u32(a_empty + slot), ((q / PAIR_SLOTS) - 1) & 1);
+          if (rank == 0) mbar_expect_tx(smem_u32(a_full + slot), 2u * (uint32_t)HALO_ABYTES);
+          tma_tile_4d_pair(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a, leader_a_full0 + slot * 8, c * BK, bx * 8 + h.lo_x,
+                           by * 16 + h.lo_y, f);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // no CTA leaves (or frees TMEM) while its peer may still signal / read it
+  if (warp == PAIR_EPI_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS) : "memory");
+  }
+}
+
 struct HaloKey {
   const void* in;
   const void* wt;
@@ -1470,6 +1723,63 @@ int launch_halo(const HaloMaps& maps, HaloArgs& h, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = bn_pdl_enabled() ? 2 : 1;
   BN_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, (const HaloArgs&)h));
+  BN_LAUNCHED();
+  return 0;
+}
+
+struct HaloPairKey {
+  const void* in;
+  const void* wt;
+  int n, H, W, C, wrow;
+  bool operator==(const HaloPairKey& o) const {
+    return in == o.in && wt == o.wt && n == o.n && H == o.H && W == o.W && C == o.C && wrow == o.wrow;
+  }
+};
+std::vector<std::pair<HaloPairKey, HaloPairMaps>> g_halo_pair_cache;
+
+// returns 1 when not applicable
+int launch_halo_pair(const TcArgs& a, const HaloArgs& h, cudaStream_t st) {
+  HaloPairArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.h = h;
+  pa.h.csz = 2;
+  pa.h.dbg = 0;
+  const int nchunk = a.Ci / BK;
+  unsigned int off = 0;
+  for (int c = 0; c < nchunk; ++c)
+    for (int gi = 0; gi < h.ngroups; ++gi) {
+      pa.w_off[c][gi] = off;
+      off += (unsigned int)h.g[gi].ncls * 16 * 128;            // half of ncls stacked 32 x 32 tiles
+    }
+  pa.w_bytes = off;
+  if (off > (unsigned int)HaloPairSmem::W_MAX) return 1;
+  const HaloPairMaps* pm = nullptr;
+  {
+    HaloPairKey key{a.in, a.wt, a.n, a.Hi, a.Wi, a.Ci, a.wrow};
+    std::lock_guard<std::mutex> lk(g_tma_mutex);
+    for (auto& kv : g_halo_pair_cache)
+      if (kv.first == key) pm = &kv.second;
+    if (!pm) {
+      HaloPairMaps m;
+      memset(&m, 0, sizeof(m));
+      if (!encode_tiled_4d(&m.a, a.in, a.n, a.Hi, a.Wi, a.Ci, BK, HALO_W, HALO_H)) return 1;
+      if (!encode_tiled_2d(&m.b16, a.wt, a.Co, a.wrow, BK, 16, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (!encode_tiled_2d(&m.b32, a.wt, a.Co, a.wrow, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (g_halo_pair_cache.size() >= 256) g_halo_pair_cache.clear();
+      g_halo_pair_cache.emplace_back(key, m);
+      pm = &g_halo_pair_cache.back().second;
+    }
+  }
+  HaloPairMaps local = *pm;
+  auto kern = dgrad_halo_pair_kernel;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloPairSmem::TOTAL));
+    configured = true;
+  }
+  const long long npairs = (h.total_tiles + 1) / 2;
+  long long grid = 2 * (npairs < 74 ? npairs : 74);             // one CTA per SM, whole pairs
+  BN_CUDA(bn_launch(kern, dim3((unsigned)grid), PAIR_THREADS, HaloPairSmem::TOTAL, st, local, (const HaloPairArgs&)pa));
   BN_LAUNCHED();
   return 0;
 }
@@ -1573,6 +1883,12 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsu
   }
   h.tiles_per_frame = h.tiles_x * bn_cdiv(Hm, 16);
   h.total_tiles = (long long)h.tiles_per_frame * a.n;
+  // C_out = 32 with <= 64 input channels: CTA-pair kernel, the layer's weights resident (half per SM)
+  static const bool pair_off = [] { const char* e = getenv("BN_HALO_PAIR"); return e && e[0] == '0'; }();
+  if (a.Co == 32 && a.Ci <= 32 * PAIR_MAXCHUNK && !pair_off && h.total_tiles >= 2) {
+    int r = launch_halo_pair(a, h, st);
+    if (r <= 0) return r;
+  }
   HaloMaps local = *hm;
   static const int deep = [] { const char* e = getenv("BN_HALO_DEEP"); return e ? atoi(e) : 0; }();
   if (a.Co == 32 && deep == 1) return launch_halo<32, 10, true>(local, h, st);      // one CTA per SM, 160 KB weight ring

@@ -89,10 +89,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 //   colacc : optional per-lane accumulator of the stored values of this lane's 4 columns (bias gradient
 //            = column sums of a gradient image, fused here instead of re-reading the image);
 //            flush with warp_flush_colsum
-__device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const float* __restrict__ dact, float leak,
-                                                  long long idx, const uint32_t (&r)[32],
-                                                  const float* __restrict__ bias, int act, float* tile, int lane,
-                                                  float4& colacc, bool do_colacc) {
+// core of the transposing store: ridx[i] = element offset of row (4 i + (lane >> 3)) of this warp's 32-row tile in
+// `out` / `dact` (or < 0 for a row that is not stored), as the CALLER knows it -- kernels whose rows are pixels of a
+// fixed 16 x 8 block compute it arithmetically; warp_store_rows32 below gathers it from the row-per-lane value
+// with shuffles.
+__device__ __forceinline__ void warp_store_rows32_at(float* __restrict__ out, const float* __restrict__ dact, float leak,
+                                                     const long long (&ridx)[8], const uint32_t (&r)[32],
+                                                     const float* __restrict__ bias, int act, float* tile, int lane,
+                                                     float4& colacc, bool do_colacc) {
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     *reinterpret_cast<uint4*>(tile + lane * 32 + ((c ^ (lane & 7)) << 2)) =
@@ -100,15 +104,10 @@ __device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const
   __syncwarp();
   const int sub = lane >> 3, chunk = lane & 7;
   const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const int lo = (int)(unsigned long long)idx, hi = (int)((unsigned long long)idx >> 32);
-  long long ridx[8];
   float4 x[8], d[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + sub;
-    const unsigned rlo = (unsigned)__shfl_sync(0xffffffffu, lo, row);
-    const int rhi = __shfl_sync(0xffffffffu, hi, row);
-    ridx[i] = (long long)(((unsigned long long)(unsigned)rhi << 32) | rlo);
     x[i] = *reinterpret_cast<const float4*>(tile + row * 32 + ((chunk ^ (row & 7)) << 2));
   }
   if (dact) {
@@ -136,6 +135,23 @@ __device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const
     }
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const float* __restrict__ dact, float leak,
+                                                  long long idx, const uint32_t (&r)[32],
+                                                  const float* __restrict__ bias, int act, float* tile, int lane,
+                                                  float4& colacc, bool do_colacc) {
+  const int sub = lane >> 3;
+  const int lo = (int)(unsigned long long)idx, hi = (int)((unsigned long long)idx >> 32);
+  long long ridx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + sub;
+    const unsigned rlo = (unsigned)__shfl_sync(0xffffffffu, lo, row);
+    const int rhi = __shfl_sync(0xffffffffu, hi, row);
+    ridx[i] = (long long)(((unsigned long long)(unsigned)rhi << 32) | rlo);
+  }
+  warp_store_rows32_at(out, dact, leak, ridx, r, bias, act, tile, lane, colacc, do_colacc);
 }
 
 __device__ __forceinline__ void warp_store_rows32(float* __restrict__ out, const float* __restrict__ dact, float leak,

@@ -96,6 +96,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_kernel(con
   }
 }
 
+// issue rate of the pair MMA: 2000 x 4 back-to-back MMAs from the leader, all 74 CTA pairs of the chip busy
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) pair_rate_kernel(int iters, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cta_rank();
+  for (int i = tid; i < (16384 + (N / 2) * 128) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (tid == 0) {
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_ptr)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tm = tmem_ptr;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc(256, N);
+    const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t z = 0;
+        asm volatile(
+            "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+            " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
+            ::"r"(tm), "l"(desc_k(sa + k * 32)), "l"(desc_k(sb + k * 32)), "r"(idesc), "r"(1u), "r"(z) : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(&done_bar)), "h"((uint16_t)3) : "memory");
+    mbar_wait(smem_u32(&done_bar), 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  } else {
+    mbar_wait(smem_u32(&done_bar), 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(256) : "memory");
+  }
+}
+
+template <int N>
+void rate() {
+  long long* d_out;
+  cudaMalloc(&d_out, 8);
+  const size_t smem = 16384 + (N / 2) * 128;
+  cudaFuncSetAttribute(pair_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int iters = 2000;
+  pair_rate_kernel<N><<<148, 128, smem>>>(iters, d_out);
+  cudaDeviceSynchronize();
+  pair_rate_kernel<N><<<148, 128, smem>>>(iters, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  const double per = (double)cyc / (iters * 4.0);
+  printf("N=%3d: cta_group::2 M=256 K=8: %6.1f cycles per MMA (per SM: 128 x %d x 8; tensor floor %3.0f; one-CTA M=128 form measured %s) %s\n",
+         N, per, N, 128.0 * N / 256.0, N == 32 ? "44.6" : N == 64 ? "48.0" : N == 128 ? "64.0" : "128.1",
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(d_out);
+}
+
 template <int N>
 int run() {
   float *hA = (float*)malloc(256 * 32 * 4), *hB = (float*)malloc(N * 32 * 4), *hD = (float*)malloc(256 * N * 4);
@@ -132,5 +206,9 @@ int main() {
   rc |= run<64>();
   rc |= run<128>();
   rc |= run<256>();
+  rate<32>();
+  rate<64>();
+  rate<128>();
+  rate<256>();
   return rc;
 }

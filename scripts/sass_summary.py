@@ -26,7 +26,7 @@ def main():
         m = re.match(r'\s*Function : (\S+)', line)
         if m:
             fn = subprocess.run(['c++filt', m.group(1)], capture_output=True, text=True).stdout.strip()
-            fn = re.sub(r'\(.*', '', fn).replace('(anonymous namespace)::', '').replace('void ', '')
+            fn = re.sub(r'\(.*', '', fn.replace('(anonymous namespace)::', '').replace('void ', ''))
             counts[fn] = collections.Counter()
             continue
         if fn is None:

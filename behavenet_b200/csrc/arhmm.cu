@@ -751,6 +751,405 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward-backward scan, meet-in-the-middle form, SPL states per lane.
+//
+// scan2_kernel gives every state its own lane: a C4 step is 84 warp instructions for TWO trials (the
+// all-gather, the normaliser and the address arithmetic are replicated in all 16 lanes of a trial), and ncu shows
+// the kernel issue-bound (56 % issue utilisation at 3.5 warps per scheduler, 173 M warp instructions).  Here a lane
+// owns SPL consecutive states (K = 16: 4 lanes per trial, 8 trials per warp): the per-step overhead is shared by
+// SPL states, the mat-vec of a lane is SPL independent chains of KP/2 packed FMAs on the all-gathered message,
+// and the normaliser sums travel with the message as per-lane partial sums.  The mathematics (scaling, lazy
+// finalisation of gamma / xi one step late, fp64 log normaliser) is scan2_kernel's, statement for statement.
+// Needs K % SPL == 0 (a lane's states are all real or all padding; vector loads stay aligned).
+// Block = 64 threads: warp 0 forward, warp 1 backward sweeps of the same 32 / (KP / SPL) trials.
+// ------------------------------------------------------------------------------------------------
+template <int SPL>
+struct ScanInV {
+  float b[SPL];
+  float x[SPL];
+  float m;
+};
+
+template <int SPL>
+__device__ __forceinline__ void ldv_nc(const float* p, float (&v)[SPL]) {
+  if (SPL == 4) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[SPL > 2 ? 2 : 0] = q.z; v[SPL > 2 ? 3 : 1] = q.w;
+  } else {
+    const float2 q = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = q.x; v[1] = q.y;
+  }
+}
+// coherent loads: messages written by the partner warp earlier in this kernel
+template <int SPL>
+__device__ __forceinline__ void ldv_cg(const float* p, float (&v)[SPL]) {
+  if (SPL == 4) {
+    const float4 q = __ldcg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[SPL > 2 ? 2 : 0] = q.z; v[SPL > 2 ? 3 : 1] = q.w;
+  } else {
+    const float2 q = __ldcg(reinterpret_cast<const float2*>(p));
+    v[0] = q.x; v[1] = q.y;
+  }
+}
+template <int SPL>
+__device__ __forceinline__ void stv(float* p, const float (&v)[SPL]) {
+  if (SPL == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[SPL > 2 ? 2 : 0], v[SPL > 2 ? 3 : 1]);
+  else *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+
+// ring prefetch: PF inputs in flight, slot i reloaded right after it is consumed.  The trip count nmax is the
+// warp-wide maximum of the lanes' own counts n: every lane runs every iteration (steps past its own range are
+// `live = false` no-ops), so the exchange inside a step can use a plain full-mask __syncwarp().  A sub-warp mask
+// compiles to MATCH.ANY + REDUX + VOTE in front of every barrier -- measured at ~300 cycles of a 540-cycle step
+// when one warp per scheduler has nothing to hide them behind.
+template <int PF, class In, class Load, class Step>
+__device__ __forceinline__ void run_ring(int t0, int n, int dir, Load load, Step step) {
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  In q[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) q[i] = load(t0 + dir * i, i < n);
+  for (int done = 0; done < nmax; done += PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int idx = done + i;
+      if (idx < nmax) {
+        const In cur = q[i];
+        q[i] = load(t0 + dir * (idx + PF), idx + PF < n);
+        step(t0 + dir * idx, cur, idx < n);
+      }
+    }
+  }
+}
+
+template <int KP, int SPL, bool POST>
+__global__ void __launch_bounds__(64) scan4_kernel(const Scan2Args a) {
+  constexpr int LPT = KP / SPL;                    // lanes per trial
+  constexpr int GPW = 32 / LPT;                    // trials per warp
+  constexpr int H2 = KP / 2;                       // packed pairs per message
+  constexpr int STRIDE = KP + 2 * LPT + 4;         // message + two partial-sum arrays; the pad keeps LDS.128 of the groups conflict-free
+  constexpr int PF = 6;                            // prefetch depth of the first halves
+  constexpr int PF2 = 2;                           // second halves: registers go to the xi accumulators, so the
+  constexpr int PFL2 = 8;                          //   likelihood stream is pulled into L2 PFL2 steps ahead instead
+  // Few warps carry the whole problem (C4: 512), so the loads in flight, not the latency of one, bound the likelihood
+  // stream (Little: 1 TB/s x 1 us = 1 MB; PF register slots x 64 B x 4096 chains = 1.5 MB at best).  Every lane
+  // therefore also pulls its row PFFAR steps ahead into L2; the register ring then only has to cover L2 latency.
+  constexpr int PFFAR = 32;
+  static_assert(LPT >= 4 && LPT % 4 == 0, "partial sums are read as float4");
+  const BlobHeader* hd = reinterpret_cast<const BlobHeader*>(a.blob);
+  const float* Pg = reinterpret_cast<const float*>(a.blob + hd->off_P_f);     // KP x KP, zero padded
+  const float* pi0g = reinterpret_cast<const float*>(a.blob + hd->off_pi0_f);
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int lig = lane % LPT;
+  const int grp = lane / LPT;
+  const int j0 = lig * SPL;                        // first state of this lane
+  const bool is_bwd = POST && wib == 1;
+  const int trial = (POST ? blockIdx.x : blockIdx.x * 2 + wib) * GPW + grp;
+  const bool active = trial < a.n_trials;
+  const int K = a.K;
+  const bool kvalid = active && j0 < K;
+  const long long beg = active ? a.offsets[trial] : 0;
+  const int T = active ? (int)(a.offsets[trial + 1] - beg) : 0;
+  const int h = T / 2;
+
+  __shared__ __align__(16) float xch[2][2][GPW * STRIDE];
+  __shared__ float xz[POST ? GPW : 1][POST ? KP : 1][POST ? KP + 1 : 1];
+  float* xme = &xch[wib][0][grp * STRIDE];
+  int par = 0;
+  // all-gather of the lanes' SPL-float message slices inside the trial's lane group, plus the group sums of up to
+  // two scalars (per-lane partials p0, p1); double-buffered by parity (a lane is at most one step ahead of its group)
+  auto exchange = [&](const float (&mine)[SPL], float p0, float p1, bool two, float2 (&v)[H2], float& s0, float& s1) {
+    float* x = xme + par * (GPW * STRIDE);
+    stv<SPL>(x + j0, mine);
+    x[KP + lig] = p0;
+    if (two) x[KP + LPT + lig] = p1;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < KP; j += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(x + j);
+      v[j / 2] = make_float2(q.x, q.y);
+      v[j / 2 + 1] = make_float2(q.z, q.w);
+    }
+    float2 acc = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < LPT; j += 4) {
+      const float4 e = *reinterpret_cast<const float4*>(x + KP + j);
+      acc = fadd2(acc, fadd2(make_float2(e.x, e.y), make_float2(e.z, e.w)));
+      if (two) {
+        const float4 f = *reinterpret_cast<const float4*>(x + KP + LPT + j);
+        acc1 = fadd2(acc1, fadd2(make_float2(f.x, f.y), make_float2(f.z, f.w)));
+      }
+    }
+    s0 = acc.x + acc.y;
+    s1 = acc1.x + acc1.y;
+    par ^= 1;
+  };
+  // out[s] = sum_i v(i) * M[s](i): SPL independent chains of packed FMAs
+  auto dots = [&](const float2 (&v)[H2], const float2 (&M)[SPL][H2], float (&out)[SPL]) {
+    float2 acc[SPL];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) acc[s] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < H2; ++j)
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) acc[s] = ffma2(v[j], M[s][j], acc[s]);
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) out[s] = acc[s].x + acc[s].y;
+  };
+  auto lsum = [&](const float (&v)[SPL]) {
+    float r = v[0];
+#pragma unroll
+    for (int s = 1; s < SPL; ++s) r += v[s];
+    return r;
+  };
+
+  const float* Bp = a.Bsc + beg * K + j0;
+  const float* mp = a.mx + beg;
+  float* Ep = POST ? a.Ez + beg * K + j0 : nullptr;
+  float* Bt = POST ? a.beta + beg * K + j0 : nullptr;
+  typedef ScanInV<SPL> In;
+
+  if (!is_bwd) {
+    // =============================== forward group (the lane owns columns j0 .. j0+SPL-1 of P)
+    float2 Pc[SPL][H2];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s)
+#pragma unroll
+      for (int j = 0; j < H2; ++j) Pc[s][j] = make_float2(Pg[(2 * j) * KP + j0 + s], Pg[(2 * j + 1) * KP + j0 + s]);
+    double logZ = 0.0;
+    float acur[SPL], bprev[SPL];
+    float rcur = 1.f;
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) { acur[s] = 0.f; bprev[s] = 0.f; }
+    if (T > 0) {
+      if (kvalid) ldv_nc<SPL>(Bp, bprev);
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) acur[s] = pi0g[j0 + s] * bprev[s];
+      logZ = (double)__ldg(mp);
+    }
+    auto load1 = [&](int t, bool ok) {
+      In in;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) { in.b[s] = 0.f; in.x[s] = 0.f; }
+      if (kvalid && ok) ldv_nc<SPL>(Bp + (long long)t * K, in.b);
+      if (kvalid && t + PFFAR < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(Bp + (long long)(t + PFFAR) * K));
+      in.m = ok ? __ldg(mp + t) : 0.f;
+      return in;
+    };
+    auto step1 = [&](int t, const In& in, bool live) {
+      float2 v[H2];
+      float S, unused;                               // S = S_{t-1} = sum_j a_{t-1}(j)
+      exchange(acur, lsum(acur), 0.f, false, v, S, unused);
+      if (!live) return;
+      float dot[SPL];
+      dots(v, Pc, dot);
+      if (POST && kvalid) stv<SPL>(Ep + (long long)(t - 1) * K, acur);
+      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      logZ += (double)(__logf(S) + in.m);            // fp64 accumulation, off the dependent chain
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) { acur[s] = dot[s] * in.b[s] * inv; bprev[s] = in.b[s]; }
+      rcur = inv;
+    };
+    const int n1 = POST ? h : (T > 0 ? T - 1 : 0);
+    run_ring<PF, In>(1, n1, 1, load1, step1);
+    if (!POST) {
+      float2 v[H2];
+      float S, unused;
+      exchange(acur, lsum(acur), 0.f, false, v, S, unused);
+      if (T > 0) logZ += (double)__logf(S);
+      if (active && lig == 0 && a.logZ) a.logZ[trial] = logZ;
+      return;
+    }
+    __syncthreads();
+    // second half: t = h+1 .. T; finalises step t-1 into gamma_{t-1} and xi_{t-2}; t == T has no a_t
+    float2 X[SPL][H2], vprev[H2];
+#pragma unroll
+    for (int j = 0; j < H2; ++j) {
+      vprev[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) X[s][j] = make_float2(0.f, 0.f);
+    }
+    auto load2 = [&](int t, bool ok) {
+      In in;
+      const bool cur = ok && t < T;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) { in.b[s] = 0.f; in.x[s] = 0.f; }
+      if (cur && kvalid) ldv_nc<SPL>(Bp + (long long)t * K, in.b);
+      if (kvalid && t + PFL2 < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(Bp + (long long)(t + PFL2) * K));
+      in.m = cur ? __ldg(mp + t) : 0.f;
+      if (kvalid && ok) ldv_cg<SPL>(Bt + (long long)(t - 1) * K, in.x);      // beta_tilde_{t-1}
+      return in;
+    };
+    auto step2 = [&](int t, const In& in, bool live) {
+      float2 v[H2];
+      float ab[SPL];
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) ab[s] = acur[s] * in.x[s];
+      float S, G;                                    // G = sum_k a_{t-1}(k) beta_{t-1}(k)
+      exchange(acur, lsum(acur), lsum(ab), true, v, S, G);
+      if (!live) return;
+      float dot[SPL];
+      dots(v, Pc, dot);
+      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
+      float gam[SPL];
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) gam[s] = ab[s] * rG;
+      if (kvalid) stv<SPL>(Ep + (long long)(t - 1) * K, gam);
+      const float rr = rcur * rG;                    // xi_{t-2}: vprev is all-zero on the first step
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) {
+        const float w = bprev[s] * in.x[s] * rr;
+        const float2 w2 = make_float2(w, w);
+#pragma unroll
+        for (int j = 0; j < H2; ++j) X[s][j] = ffma2(vprev[j], w2, X[s][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < H2; ++j) vprev[j] = v[j];
+      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      logZ += (double)(__logf(S) + in.m);            // in.m = 0 on the last step (t == T)
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) { acur[s] = dot[s] * in.b[s] * inv; bprev[s] = in.b[s]; }
+      rcur = inv;
+    };
+    run_ring<PF2, In>(h + 1, T - h, 1, load2, step2);
+    if (active && lig == 0 && a.logZ) a.logZ[trial] = logZ;
+    __syncthreads();                                 // backward group's xi rows are in xz
+    if (kvalid && a.Ezz) {
+      float* out = a.Ezz + (long long)trial * K * K + j0;
+#pragma unroll
+      for (int i = 0; i < KP; ++i)
+        if (i < K) {
+          float o[SPL];
+#pragma unroll
+          for (int s = 0; s < SPL; ++s) {
+            const float xi = (i & 1) ? X[s][i / 2].y : X[s][i / 2].x;
+            const float pi = (i & 1) ? Pc[s][i / 2].y : Pc[s][i / 2].x;
+            o[s] = pi * (xi + xz[grp][i][j0 + s]);
+          }
+          stv<SPL>(out + (long long)i * K, o);
+        }
+    }
+  } else {
+    // =============================== backward group (the lane owns rows j0 .. j0+SPL-1 of P)
+    float2 Pr[SPL][H2];
+#pragma unroll
+    for (int s = 0; s < SPL; ++s)
+#pragma unroll
+      for (int j = 0; j < H2; ++j) Pr[s][j] = make_float2(Pg[(j0 + s) * KP + 2 * j], Pg[(j0 + s) * KP + 2 * j + 1]);
+    float beta[SPL];                                 // beta_tilde_{t+1}
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) beta[s] = 1.f;
+    if (T > 0 && kvalid) stv<SPL>(Bt + (long long)(T - 1) * K, beta);
+    auto load1 = [&](int t, bool ok) {
+      In in;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) { in.b[s] = 0.f; in.x[s] = 0.f; }
+      if (kvalid && ok) ldv_nc<SPL>(Bp + (long long)(t + 1) * K, in.b);
+      if (kvalid && t + 1 >= PFFAR) asm volatile("prefetch.global.L2 [%0];" ::"l"(Bp + (long long)(t + 1 - PFFAR) * K));
+      in.m = 0.f;
+      return in;
+    };
+    auto step1 = [&](int t, const In& in, bool live) {
+      float2 vk[H2];
+      float msg[SPL];
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) msg[s] = in.b[s] * beta[s];
+      float Dn, unused;
+      exchange(msg, lsum(msg), 0.f, false, vk, Dn, unused);
+      if (!live) return;
+      float u[SPL];
+      dots(vk, Pr, u);
+      const float rho = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) beta[s] = u[s] * rho;
+      if (kvalid) stv<SPL>(Bt + (long long)t * K, beta);
+    };
+    run_ring<PF, In>(T - 2, max(T - 1 - h, 0), -1, load1, step1);            // t = T-2 .. h
+    __syncthreads();
+    // second half: t = h-1 .. 0.  gamma_t / xi_t need G_t = sum_j a_t(j) beta_t(j), which exists only at the END of
+    // step t: it rides along with the next step's message, so step t is finalised one iteration later (t = 0 by a
+    // trailing exchange).
+    float2 X[SPL][H2], vkp[H2];
+#pragma unroll
+    for (int j = 0; j < H2; ++j) {
+      vkp[j] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) X[s][j] = make_float2(0.f, 0.f);
+    }
+    float al_p[SPL], ab_p[SPL];
+    float rho_p = 0.f;
+#pragma unroll
+    for (int s = 0; s < SPL; ++s) { al_p[s] = 0.f; ab_p[s] = 0.f; }
+    auto load2 = [&](int t, bool ok) {
+      In in;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) { in.b[s] = 0.f; in.x[s] = 0.f; }
+      if (kvalid && ok) {
+        ldv_nc<SPL>(Bp + (long long)(t + 1) * K, in.b);
+        ldv_cg<SPL>(Ep + (long long)t * K, in.x);                           // a_t stored by the forward group
+        if (t + 1 >= PFL2) asm volatile("prefetch.global.L2 [%0];" ::"l"(Bp + (long long)(t + 1 - PFL2) * K));
+      }
+      in.m = 0.f;
+      return in;
+    };
+    auto finalise = [&](int tp, float G) {
+      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
+      float gam[SPL];
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) gam[s] = ab_p[s] * rG;
+      if (kvalid) stv<SPL>(Ep + (long long)tp * K, gam);
+      const float rr = rho_p * rG;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) {
+        const float w = al_p[s] * rr;
+        const float2 w2 = make_float2(w, w);
+#pragma unroll
+        for (int j = 0; j < H2; ++j) X[s][j] = ffma2(vkp[j], w2, X[s][j]);
+      }
+    };
+    auto step2 = [&](int t, const In& in, bool live) {
+      float2 vk[H2];
+      float msg[SPL];
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) msg[s] = in.b[s] * beta[s];
+      float Dn, G;
+      exchange(msg, lsum(msg), lsum(ab_p), true, vk, Dn, G);
+      if (!live) return;
+      if (t + 1 < h) finalise(t + 1, G);
+      float u[SPL];
+      dots(vk, Pr, u);
+      rho_p = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) {
+        beta[s] = u[s] * rho_p;
+        al_p[s] = in.x[s];
+        ab_p[s] = in.x[s] * beta[s];
+      }
+#pragma unroll
+      for (int j = 0; j < H2; ++j) vkp[j] = vk[j];
+    };
+    run_ring<PF2, In>(h - 1, h, -1, load2, step2);                           // t = h-1 .. 0
+    {
+      float2 vk[H2];
+      float zero[SPL];
+#pragma unroll
+      for (int s = 0; s < SPL; ++s) zero[s] = 0.f;
+      float Dn, G;
+      exchange(zero, 0.f, lsum(ab_p), true, vk, Dn, G);
+      if (h > 0) finalise(0, G);
+    }
+#pragma unroll
+    for (int s = 0; s < SPL; ++s)
+#pragma unroll
+      for (int j = 0; j < H2; ++j) {
+        xz[grp][j0 + s][2 * j] = X[s][j].x;
+        xz[grp][j0 + s][2 * j + 1] = X[s][j].y;
+      }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Viterbi (fp64 max-sum, backward recursion like ssm.messages.viterbi)
 // ------------------------------------------------------------------------------------------------
 struct VitArgs {
@@ -1095,6 +1494,19 @@ static int launch_scan2(const Scan2Args& a, cudaStream_t st) {
   return 0;
 }
 
+// SPL-states-per-lane scan: K = 8 .. 32 with K % SPL == 0 (BN_SCAN=2 keeps the lane-per-state kernel)
+template <int KP, int SPL>
+static int launch_scan4(const Scan2Args& a, cudaStream_t st) {
+  constexpr int GPW = 32 / (KP / SPL);
+  if (a.Ez) {
+    scan4_kernel<KP, SPL, true><<<bn_cdiv(a.n_trials, GPW), 64, 0, st>>>(a);
+  } else {
+    scan4_kernel<KP, SPL, false><<<bn_cdiv(a.n_trials, 2 * GPW), 64, 0, st>>>(a);
+  }
+  BN_LAUNCHED();
+  return 0;
+}
+
 template <int KP>
 static int launch_vit(const VitArgs& a, cudaStream_t st) {
   constexpr int GPW = 32 / KP;
@@ -1192,7 +1604,23 @@ extern "C" int bn_arhmm_estep(int K, int D, int lags, const void* d_blob, const 
     s.Ez = d_Ez; s.Ezz = d_Ezz ? d_Ezz + (size_t)g0 * K * K : nullptr; s.logZ = d_logZ ? d_logZ + g0 : nullptr;
     s.beta = (float*)(ws + w.beta);
     int r;
-    switch (bn_round_kp(K)) {
+    // Measured on B200 (C4, profiles/r02_scan4.txt): the SPL-per-lane kernel executes 93 M warp instructions against
+    // scan2's 173 M but takes 484 us against 314 us -- with 0.86 warps per scheduler nothing hides the ~5 cycles per
+    // dependent instruction and the global-load latency, so issue utilisation drops from 56 % to 20 %.  The lane-per-
+    // state kernel stays the default; BN_SCAN=4 selects this one.
+    static const bool lane_per_state = [] { const char* e = getenv("BN_SCAN"); return !(e && e[0] == '4'); }();
+    const int kp = bn_round_kp(K);
+    static const int spl16 = [] { const char* e = getenv("BN_SCAN4_SPL"); return e ? atoi(e) : 4; }();
+    if (!lane_per_state && kp == 16 && K % 4 == 0 && spl16 == 4) {
+      r = launch_scan4<16, 4>(s, st);
+    } else if (!lane_per_state && kp == 16 && K % 2 == 0) {
+      r = launch_scan4<16, 2>(s, st);
+    } else if (!lane_per_state && kp == 32 && K % 2 == 0) {
+      r = launch_scan4<32, 2>(s, st);
+    } else if (!lane_per_state && kp == 8 && K % 2 == 0) {
+      r = launch_scan4<8, 2>(s, st);
+    } else
+    switch (kp) {
       case 2: r = launch_scan2<2>(s, st); break;
       case 4: r = launch_scan2<4>(s, st); break;
       case 8: r = launch_scan2<8>(s, st); break;

@@ -503,26 +503,31 @@ __global__ void __launch_bounds__(NTHREADS) igemm_tma_kernel(const __grid_consta
     }
     tc_fence_before();
   } else {
-    if ((tid & 31) == 0) {
+    {
+      // the whole warp runs the issue loop converged and one elected lane issues: descriptors stay cheap (constant
+      // high word, low word += 2 per k-step) instead of ~20 instructions of address arithmetic + ELECT / R2UR
+      // waterfall per MMA, which at >= 66 cycles per MMA out-lasted every MMA with N <= 128 (umma_window_rate.cu)
       constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t d_hi = desc_hi_sw128(1024);
+      uint32_t accflag = 0u;
       for (int c = 0; c < nchunks; ++c) {
         const int stage = c % STAGES;
         mbar_wait(smem_u32(full_bar + stage), (c / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
-        const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t a_lo = desc_lo_sw128(sa), b_lo = desc_lo_sw128(sa + S::A_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t bd = make_desc_sw128(sb + k * 32);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
             if (mt < mt_live)
-              umma_tf32(tmem_base + mt * BN, make_desc_sw128(sa + mt * (BM * BK * 4) + k * 32), bd, idesc,
-                        (c | k) != 0 ? 1u : 0u);
+              umma_tf32_elect(tmem_base + mt * BN, ((uint64_t)d_hi << 32) | (a_lo + mt * (BM * BK * 4 / 16) + 2 * k),
+                              ((uint64_t)d_hi << 32) | (b_lo + 2 * k), idesc, accflag);
+          accflag = 1u;
         }
-        umma_commit(smem_u32(empty_bar + stage));
+        umma_commit_elect(smem_u32(empty_bar + stage));
       }
-      if (nchunks > 0) umma_commit(smem_u32(accum_bar));
+      if (nchunks > 0) umma_commit_elect(smem_u32(accum_bar));
     }
     __syncwarp();
   }
@@ -976,26 +981,30 @@ __global__ void __launch_bounds__(NTHREADS) wgrad_tma_kernel(const __grid_consta
     }
     tc_fence_before();
   } else {
-    if ((tid & 31) == 0) {
+    {
+      // converged warp, one elected lane issues (see igemm_tma_kernel)
       constexpr uint32_t idesc = make_idesc_mn(BM, BN);
+      constexpr uint32_t d_hi = (((uint32_t)SBO >> 4) & 0x3FFFu) | (1u << 14) | (1u << 29);      // SWIZZLE_128B_BASE32B
+      constexpr uint32_t lbo_w = (((uint32_t)LBO >> 4) & 0x3FFFu) << 16;
+      uint32_t accflag = 0u;
       for (int c = 0; c < nchunks; ++c) {
         const int stage = c % STAGES;
         mbar_wait(smem_u32(full_bar + stage), (c / STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * S::STAGE_BYTES;
-        const uint32_t sb = sa + S::A_BYTES;
+        const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | lbo_w, b_lo = (((sa + S::A_BYTES) >> 4) & 0x3FFFu) | lbo_w;
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t bd = make_desc_mn_sw128(sb + k * 2 * SBO, LBO, SBO);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
             if (mt < mt_live)
-              umma_tf32(tmem_base + mt * BN, make_desc_mn_sw128(sa + mt * (BM / 32) * SLAB + k * 2 * SBO, LBO, SBO), bd, idesc,
-                        (c | k) != 0 ? 1u : 0u);
+              umma_tf32_elect(tmem_base + mt * BN, ((uint64_t)d_hi << 32) | (a_lo + (mt * (BM / 32) * SLAB + k * 2 * SBO) / 16),
+                              ((uint64_t)d_hi << 32) | (b_lo + (k * 2 * SBO) / 16), idesc, accflag);
+          accflag = 1u;
         }
-        umma_commit(smem_u32(empty_bar + stage));
+        umma_commit_elect(smem_u32(empty_bar + stage));
       }
-      if (nchunks > 0) umma_commit(smem_u32(accum_bar));
+      if (nchunks > 0) umma_commit_elect(smem_u32(accum_bar));
     }
     __syncwarp();
   }
@@ -1131,6 +1140,12 @@ __device__ __forceinline__ void tma_tile_2d_mc(uint32_t dst, const CUtensorMap* 
       " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y), "h"(mask)
       : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+      " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+      ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -1312,45 +1327,51 @@ __global__ void __launch_bounds__(HALO_THREADS) dgrad_halo_kernel(const __grid_c
     }
   } else if (warp == 4) {
     // ======================= MMA issuer ==========================================================
-    if ((tid & 31) == 0) {
+    {
+      // whole warp converged, one elected lane issues (see igemm_tma_kernel): constant high descriptor words, the low
+      // word of a window = halo base + row_off * 8, += 2 per k-step
+      constexpr uint32_t a_hi = desc_hi_sw128(HALO_W * 128), b_hi = desc_hi_sw128(1024);
+      const bool lane0 = (tid & 31) == 0;
       int ai = 0, bi = 0, ti = 0;
       for (long long T = t_first; T < total; T += t_step, ++ti) {
         const int buf = PERSIST ? (ti & 1) : 0;
-        HALO_STAMP(ti, 0);
+        if (lane0) HALO_STAMP(ti, 0);
         if (ti >= 2) {
           mbar_wait(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
           tc_fence_after();
         }
-        HALO_STAMP(ti, 1);
+        if (lane0) HALO_STAMP(ti, 1);
+        uint32_t accflag = 0u;
         for (int c = 0; c < nchunk; ++c, ++ai) {
           const int slot = ai & 1;
           mbar_wait(smem_u32(a_full + slot), (ai >> 1) & 1);
           tc_fence_after();
-          const uint32_t abuf = smem_base + S::OFF_A + slot * HALO_ASTRIDE;
+          const uint32_t a_lo0 = desc_lo_sw128(smem_base + S::OFF_A + slot * HALO_ASTRIDE);
           for (int gi = 0; gi < h.ngroups; ++gi, ++bi) {
             const int stage = bi % NST;
             mbar_wait(smem_u32(b_full + stage), (bi / NST) & 1);
             tc_fence_after();
-            const uint32_t sb = smem_base + stage * S::B_BYTES;
+            const uint32_t b_lo = desc_lo_sw128(smem_base + stage * S::B_BYTES);
             const HaloGroup g = h.g[gi];
             const uint32_t idesc = make_idesc(BM, g.ncls * NB);
             const uint32_t acc = tmem_base + buf * ACC_COLS + g.col0 * NB;
-            const uint32_t arow = abuf + g.row_off * 128;
+            // the 128B swizzle is a function of the shared-memory ADDRESS bits, so a window that
+            // starts on any 128-byte row of the TMA-written halo needs no descriptor base offset
+            const uint32_t a_lo = a_lo0 + (uint32_t)g.row_off * 8u;
+            if (!(h.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              // the 128B swizzle is a function of the shared-memory ADDRESS bits, so a window that
-              // starts on any 128-byte row of the TMA-written halo needs no descriptor base offset
-              const uint64_t ad = make_desc_sw128_sbo(arow + k * 32, HALO_W * 128);
-              const uint64_t bd = make_desc_sw128(sb + k * 32);
-              if (!(h.dbg & 2)) umma_tf32(acc, ad, bd, idesc, (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
+              for (int k = 0; k < BK / 8; ++k) {
+                umma_tf32_elect(acc, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, accflag);
+                accflag = 1u;
+              }
             }
-            if (csz > 1) umma_commit_mc(smem_u32(b_empty + stage), cmask);
-            else umma_commit(smem_u32(b_empty + stage));
+            if (csz > 1) umma_commit_mc_elect(smem_u32(b_empty + stage), cmask);
+            else umma_commit_elect(smem_u32(b_empty + stage));
           }
-          umma_commit(smem_u32(a_empty + slot));
+          umma_commit_elect(smem_u32(a_empty + slot));
         }
-        umma_commit(smem_u32(acc_full + buf));
-        HALO_STAMP(ti, 2);
+        umma_commit_elect(smem_u32(acc_full + buf));
+        if (lane0) HALO_STAMP(ti, 2);
       }
     }
     __syncwarp();
@@ -1451,6 +1472,23 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// elected-lane forms for a CONVERGED issuing warp (see umma_tf32_elect in tc_common.cuh): issuing from inside
+// `if (lane == 0)` costs >= 66 cycles per MMA in address arithmetic + ELECT / R2UR waterfall (scripts/ubench/
+// umma_window_rate.cu), more than the 44.6 / 48 cycles an N = 32 / 64 MMA occupies the tensor pipe
+__device__ __forceinline__ void umma_tf32_pair_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+      " @e tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar) {
+  asm volatile(
+      "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+      " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+      ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -1578,9 +1616,10 @@ dgrad_halo_pair_kernel(const __grid_constant__ HaloPairMaps maps, const __grid_c
     if (a.colsum) warp_flush_colsum(a.colsum, cacc, elane);
   } else if (warp == PAIR_EPI_WARPS) {
     // ======================= MMA issuer: leader CTA only =========================================
-    if (rank == 0 && (tid & 31) == 0) {
+    if (rank == 0) {                           // whole warp converged, one elected lane issues (see igemm_tma_kernel)
       mbar_wait_cluster(smem_u32(w_full), 0);  // both CTAs' resident weights have landed
       tc_fence_after();
+      constexpr uint32_t a_hi = desc_hi_sw128(HALO_W * 128), b_hi = desc_hi_sw128(1024);
       int ai = 0, ti = 0;
       for (long long P = p_first; P < npairs; P += p_step, ++ti) {
         const int buf = ti & 1;
@@ -1588,25 +1627,28 @@ dgrad_halo_pair_kernel(const __grid_constant__ HaloPairMaps maps, const __grid_c
           mbar_wait_cluster(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
           tc_fence_after();
         }
+        uint32_t accflag = 0u;
         for (int c = 0; c < nchunk; ++c, ++ai) {
           const int slot = ai % PAIR_SLOTS;
           mbar_wait_cluster(smem_u32(a_full + slot), (ai / PAIR_SLOTS) & 1);
           tc_fence_after();
-          const uint32_t abuf = smem_base + S::OFF_A + slot * HALO_ASTRIDE;
+          const uint32_t a_lo0 = desc_lo_sw128(smem_base + S::OFF_A + slot * HALO_ASTRIDE);
           for (int gi = 0; gi < h.ngroups; ++gi) {
             const HaloGroup g = h.g[gi];
             const uint32_t idesc = make_idesc(256, g.ncls * NB);
             const uint32_t acc = tmem_base + buf * ACC_COLS + g.col0 * NB;
-            const uint32_t arow = abuf + g.row_off * 128;
-            const uint32_t sb = smem_base + pa.w_off[c][gi];
+            const uint32_t a_lo = a_lo0 + (uint32_t)g.row_off * 8u;
+            const uint32_t b_lo = desc_lo_sw128(smem_base + pa.w_off[c][gi]);
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k)
-              umma_tf32_pair(acc, make_desc_sw128_sbo(arow + k * 32, HALO_W * 128), make_desc_sw128(sb + k * 32), idesc,
-                             (c == 0 && gi == 0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < BK / 8; ++k) {
+              umma_tf32_pair_elect(acc, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc,
+                                   accflag);
+              accflag = 1u;
+            }
           }
-          umma_commit_pair(smem_u32(a_empty + slot));
+          umma_commit_pair_elect(smem_u32(a_empty + slot));
         }
-        umma_commit_pair(smem_u32(acc_full + buf));
+        umma_commit_pair_elect(smem_u32(acc_full + buf));
       }
     }
     __syncwarp();
@@ -1780,6 +1822,313 @@ int launch_halo_pair(const TcArgs& a, const HaloArgs& h, cudaStream_t st) {
   const long long npairs = (h.total_tiles + 1) / 2;
   long long grid = 2 * (npairs < 74 ? npairs : 74);             // one CTA per SM, whole pairs
   BN_CUDA(bn_launch(kern, dim3((unsigned)grid), PAIR_THREADS, HaloPairSmem::TOTAL, st, local, (const HaloPairArgs&)pa));
+  BN_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair halo kernel for the FPROP-form stride-2 layers with 32 input and 64 output channels (encoder conv1
+// forward, decoder convtranspose3 backward-data: the two slowest launches of a C2 step).
+//
+// igemm_tma_kernel<64> fetches every input pixel once per filter tap that touches it (25 / 4 times) plus the
+// layer's weights per tile: 1.05 GB through L2 for 208 MB of HBM traffic, and it runs at exactly that L2 -> SM
+// rate (~10 TB/s, 109 us).  A stride-2 convolution is four stride-1 convolutions over the PARITY PLANES of its
+// input (in[2y'+py][2x'+px]): tap (dy, dx) reads plane (dy & 1, dx & 1) at offset ((dy - py) / 2, (dx - px) / 2),
+// which is in {-1, 0, 1}.  So a CTA owns 16 x 8 output pixels, stages the 18 x 10 halo of each parity plane with
+// ONE tiled TMA copy (the plane is a strided view of the NHWC tensor: its own tensor map), and every tap is that
+// buffer at a row offset -- 1.4 fetches per input pixel instead of 6.25.  As in dgrad_halo_pair_kernel two CTAs
+// issue one tcgen05.mma.cta_group::2 (M = 256, N = 64) with the weight operand split between them, so all 25
+// weight tiles (100 KB per SM) are loaded once and stay resident.
+// ------------------------------------------------------------------------------------------------
+constexpr int FP_MAXT = 25;
+struct FpropTap {
+  unsigned short row_off;     // window offset inside the plane halo, in pixels
+  unsigned char plane, wt;
+};
+struct FpropPairArgs {
+  TcArgs a;
+  int tiles_x, tiles_per_frame;
+  long long total_tiles;
+  int Hm, Wm, oy0, ox0;
+  int ay_min[4], ax_min[4];   // per plane: plane-space offset of the halo origin relative to the tile origin
+  int ntaps_plane[4];         // taps are sorted by plane
+  int dbg;
+  FpropTap t[FP_MAXT];
+};
+struct alignas(64) FpropPairMaps {
+  CUtensorMap a[4];    // parity planes of the NHWC input, box 32 ch x 10 px x 18 rows x 1 frame
+  CUtensorMap b32;     // K-major weights, box 32 x 32 rows
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+fprop_halo_pair_kernel(const __grid_constant__ FpropPairMaps maps, const __grid_constant__ FpropPairArgs fa) {
+  bn_pdl_trigger();
+  constexpr int NB = 64, ACC_COLS = NB, NCOLS = 2 * ACC_COLS;
+  using S = HaloPairSmem;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcArgs& a = fa.a;
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* a_full = w_full + 1;
+  uint64_t* a_empty = a_full + PAIR_SLOTS;
+  uint64_t* acc_full = a_empty + PAIR_SLOTS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(smem_u32(w_full), 1);
+    for (int s = 0; s < PAIR_SLOTS; ++s) {
+      mbar_init(smem_u32(a_full + s), 1);
+      mbar_init(smem_u32(a_empty + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(acc_full + s), 1);
+      mbar_init(smem_u32(acc_empty + s), 2 * PAIR_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PAIR_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  bn_pdl_wait();
+  const uint32_t smem_base = smem_u32(smem);
+  const long long total = fa.total_tiles;
+  const long long npairs = (total + 1) / 2;
+  const long long p_first = blockIdx.x >> 1, p_step = gridDim.x >> 1;
+#define FP_STAMP(tile, slot)                                                                        \
+  do {                                                                                              \
+    if (fa.dbg && blockIdx.x == 0 && (tile) < 8) g_halo_dbg[(tile) * 8 + (slot)] = dbg_clock();     \
+  } while (0)
+  const int ntaps = fa.ntaps_plane[0] + fa.ntaps_plane[1] + fa.ntaps_plane[2] + fa.ntaps_plane[3];
+
+  if (warp < PAIR_EPI_WARPS) {
+    // ======================= epilogue: warp w drains lanes 32 (w & 3) .. of column block w >> 2 ===
+    float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
+    const int elane = tid & 31;
+    const int q = warp & 3, chalf = warp >> 2;
+    const int pix = q * 32 + elane;
+    float4 cacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t leader_acc_empty[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(leader_acc_empty[s]) : "r"(smem_u32(acc_empty + s)));
+    const float* bias = a.bias ? a.bias + chalf * 32 : nullptr;
+    int ti = 0;
+    for (long long P = p_first; P < npairs; P += p_step, ++ti) {
+      const long long T = 2 * P + rank;
+      const bool tvalid = T < total;
+      const int f = (int)(T / fa.tiles_per_frame);
+      const int blk = (int)(T - (long long)f * fa.tiles_per_frame);
+      const int by = blk / fa.tiles_x, bx = blk - by * fa.tiles_x;
+      const int ym = by * 16 + (pix >> 3), xm = bx * 8 + (pix & 7);
+      const int buf = ti & 1;
+      mbar_wait_cluster(smem_u32(acc_full + buf), (ti >> 1) & 1);
+      tc_fence_after();
+      if (tid == 0) FP_STAMP(ti, 6);
+      const bool rvalid = tvalid && ym < fa.Hm && xm < fa.Wm;
+      const int oy = fa.oy0 + a.os * ym, ox = fa.ox0 + a.os * xm;
+      const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co + chalf * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + chalf * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();                       // the accumulator block is in registers: release it before the stores
+      __syncwarp();
+      if (elane == 0) mbar_arrive_cluster(leader_acc_empty[buf]);
+      warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase : -1, r, bias, a.act, tile, elane, cacc, a.colsum != nullptr);
+      if (tid == 0) FP_STAMP(ti, 7);
+    }
+    if (a.colsum) warp_flush_colsum(a.colsum + chalf * 32, cacc, elane);
+  } else if (warp == PAIR_EPI_WARPS) {
+    // ======================= MMA issuer: leader CTA only =========================================
+    if (rank == 0) {                           // whole warp, converged; one elected lane issues
+      mbar_wait_cluster(smem_u32(w_full), 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(256, NB);
+      constexpr uint32_t a_hi = desc_hi_sw128(HALO_W * 128), b_hi = desc_hi_sw128(1024);
+      const uint32_t b_lo0 = desc_lo_sw128(smem_base);
+      int ai = 0, ti = 0;
+      for (long long P = p_first; P < npairs; P += p_step, ++ti) {
+        const int buf = ti & 1;
+        if (ti >= 2) {
+          mbar_wait_cluster(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + buf * ACC_COLS;
+        if ((tid & 31) == 0) FP_STAMP(ti, 0);
+        int i = 0;
+        uint32_t accflag = 0u;
+#pragma unroll 1
+        for (int pl = 0; pl < 4; ++pl, ++ai) {
+          const int slot = ai % PAIR_SLOTS;
+          mbar_wait_cluster(smem_u32(a_full + slot), (ai / PAIR_SLOTS) & 1);
+          tc_fence_after();
+          if ((tid & 31) == 0) FP_STAMP(ti, 1 + pl);
+          const uint32_t a_lo0 = desc_lo_sw128(smem_base + S::OFF_A + slot * HALO_ASTRIDE);
+          const int jend = i + fa.ntaps_plane[pl];
+#pragma unroll 1
+          for (; i < jend; ++i) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)fa.t[i].row_off * 8u;       // row_off * 128 bytes >> 4
+            const uint32_t b_lo = b_lo0 + (uint32_t)i * (32 * 128 / 16);
+#pragma unroll
+            for (int kk = 0; kk < BK / 8; ++kk) {
+              umma_tf32_pair_elect(acc, ((uint64_t)a_hi << 32) | (a_lo + 2 * kk), ((uint64_t)b_hi << 32) | (b_lo + 2 * kk), idesc,
+                                   accflag);
+              accflag = 1u;
+            }
+          }
+          umma_commit_pair_elect(smem_u32(a_empty + slot));
+        }
+        umma_commit_pair_elect(smem_u32(acc_full + buf));
+        if ((tid & 31) == 0) FP_STAMP(ti, 5);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= TMA: resident half weights once, then this CTA's plane halos ==========
+    const int lane = tid & 31;
+    const uint32_t leader_w_full = smem_u32(w_full) & PEER_BIT_MASK;
+    if (lane == 0 && rank == 0) mbar_expect_tx(smem_u32(w_full), 2u * (uint32_t)ntaps * (32 * 128));
+    __syncwarp();
+    for (int i = lane; i < ntaps; i += 32)
+      tma_tile_2d_pair(smem_base + i * (32 * 128), &maps.b32, leader_w_full, fa.t[i].wt * a.Ci, (int)rank * 32);
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t leader_a_full0 = smem_u32(a_full) & PEER_BIT_MASK;
+      int q = 0;
+      for (long long P = p_first; P < npairs; P += p_step) {
+        const long long T = 2 * P + rank;
+        // a tile past the end (odd tile count) loads frame n: out of bounds, zero fill, nothing stored
+        const int f = (int)(T / fa.tiles_per_frame);
+        const int blk = (int)(T - (long long)f * fa.tiles_per_frame);
+        const int by = blk / fa.tiles_x, bx = blk - by * fa.tiles_x;
+#pragma unroll 1
+        for (int pl = 0; pl < 4; ++pl, ++q) {
+          const int slot = q % PAIR_SLOTS;
+          if (q >= PAIR_SLOTS) mbar_wait_cluster(smem_u32(a_empty + slot), ((q / PAIR_SLOTS) - 1) & 1);
+          if (rank == 0) mbar_expect_tx(smem_u32(a_full + slot), 2u * (uint32_t)HALO_ABYTES);
+          tma_tile_4d_pair(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a[pl], leader_a_full0 + slot * 8, 0,
+                           bx * 8 + fa.ax_min[pl], by * 16 + fa.ay_min[pl], f);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == PAIR_EPI_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS) : "memory");
+  }
+}
+
+struct FpropPairKey {
+  const void* in;
+  const void* wt;
+  int n, H, W, C, wrow;
+  bool operator==(const FpropPairKey& o) const {
+    return in == o.in && wt == o.wt && n == o.n && H == o.H && W == o.W && C == o.C && wrow == o.wrow;
+  }
+};
+std::vector<std::pair<FpropPairKey, FpropPairMaps>> g_fprop_pair_cache;
+
+// parity plane (py, px) of an NHWC image as a 4-D tensor map: pixel (y', x') = image pixel (2 y' + py, 2 x' + px)
+bool encode_plane_4d(CUtensorMap* map, const float* p, int N, int H, int W, int C, int py, int px, int bc, int bw, int bh) {
+  const int Hp = (H - py + 1) / 2, Wp = (W - px + 1) / 2;
+  if (Hp < 1 || Wp < 1) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)N};
+  cuuint64_t gstr[3] = {(cuuint64_t)2 * C * 4, (cuuint64_t)2 * W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(p + ((long long)py * W + px) * C), gdim, gstr,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// returns 1 when the op is not a stride-2 fprop-form layer with 32 input / 64 output channels
+int try_fprop_halo_pair(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("BN_FPROP_HALO"); return e && e[0] == '0'; }();
+  if (off || nclasses != 1 || a.gs != 2 || a.os != 1 || a.ksplit > 1) return 1;
+  if (a.Ci != BK || a.Co != 64 || !tma_available()) return 1;
+  const TapClass& k = hc[0];
+  if (k.ntaps < 4 || k.ntaps > FP_MAXT || k.Hm < 16 || k.Wm < 8) return 1;
+  FpropPairArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.a = a;
+  fa.Hm = k.Hm; fa.Wm = k.Wm; fa.oy0 = k.oy0; fa.ox0 = k.ox0;
+  int lo_y[4], lo_x[4], hi_y[4], hi_x[4];
+  for (int p = 0; p < 4; ++p) { lo_y[p] = lo_x[p] = 127; hi_y[p] = hi_x[p] = -128; }
+  auto plane_of = [](int dy, int dx) { return (dy & 1) * 2 + (dx & 1); };
+  for (int t = 0; t < k.ntaps; ++t) {
+    const int p = plane_of(k.dy[t], k.dx[t]);
+    const int ay = (k.dy[t] - (k.dy[t] & 1)) >> 1, ax = (k.dx[t] - (k.dx[t] & 1)) >> 1;
+    lo_y[p] = ay < lo_y[p] ? ay : lo_y[p]; hi_y[p] = ay > hi_y[p] ? ay : hi_y[p];
+    lo_x[p] = ax < lo_x[p] ? ax : lo_x[p]; hi_x[p] = ax > hi_x[p] ? ax : hi_x[p];
+    ++fa.ntaps_plane[p];
+  }
+  // slot order: planes with fewer taps first, so their halo buffers are released (and refilled for the next tile)
+  // as early as possible -- with one tile's planes in flight the kernel is bound by the latency of those refills
+  int cnt[4], order[4] = {0, 1, 2, 3};
+  for (int p = 0; p < 4; ++p) { cnt[p] = fa.ntaps_plane[p]; if (cnt[p] == 0) return 1; }
+  for (int i = 0; i < 4; ++i)
+    for (int j = i + 1; j < 4; ++j)
+      if (cnt[order[j]] < cnt[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+  int n = 0;
+  for (int s = 0; s < 4; ++s) {
+    const int p = order[s];
+    if (hi_y[p] - lo_y[p] > HALO_H - 16 || hi_x[p] - lo_x[p] > HALO_W - 8) return 1;
+    fa.ntaps_plane[s] = cnt[p];
+    fa.ay_min[s] = lo_y[p]; fa.ax_min[s] = lo_x[p];
+    for (int t = 0; t < k.ntaps; ++t)
+      if (plane_of(k.dy[t], k.dx[t]) == p) {
+        const int ay = (k.dy[t] - (k.dy[t] & 1)) >> 1, ax = (k.dx[t] - (k.dx[t] & 1)) >> 1;
+        fa.t[n].row_off = (unsigned short)((ay - lo_y[p]) * HALO_W + (ax - lo_x[p]));
+        fa.t[n].plane = (unsigned char)s;
+        fa.t[n].wt = k.wt[t];
+        ++n;
+      }
+  }
+  if ((size_t)n * 32 * 128 > (size_t)HaloPairSmem::W_MAX) return 1;
+  fa.tiles_x = bn_cdiv(k.Wm, 8);
+  fa.tiles_per_frame = fa.tiles_x * bn_cdiv(k.Hm, 16);
+  fa.total_tiles = (long long)fa.tiles_per_frame * a.n;
+  if (fa.total_tiles < 2) return 1;
+  static const int dbg = [] { const char* e = getenv("BN_HALO_DBG"); return e ? atoi(e) : 0; }();
+  fa.dbg = dbg;
+  const FpropPairMaps* pm = nullptr;
+  {
+    FpropPairKey key{a.in, a.wt, a.n, a.Hi, a.Wi, a.Ci, a.wrow};
+    std::lock_guard<std::mutex> lk(g_tma_mutex);
+    for (auto& kv : g_fprop_pair_cache)
+      if (kv.first == key) pm = &kv.second;
+    if (!pm) {
+      FpropPairMaps m;
+      memset(&m, 0, sizeof(m));
+      for (int s = 0; s < 4; ++s)
+        if (!encode_plane_4d(&m.a[s], a.in, a.n, a.Hi, a.Wi, a.Ci, order[s] >> 1, order[s] & 1, BK, HALO_W, HALO_H)) return 1;
+      if (!encode_tiled_2d(&m.b32, a.wt, a.Co, a.wrow, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (g_fprop_pair_cache.size() >= 256) g_fprop_pair_cache.clear();
+      g_fprop_pair_cache.emplace_back(key, m);
+      pm = &g_fprop_pair_cache.back().second;
+    }
+  }
+  FpropPairMaps local = *pm;
+  auto kern = fprop_halo_pair_kernel;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloPairSmem::TOTAL));
+    configured = true;
+  }
+  const long long npairs = (fa.total_tiles + 1) / 2;
+  long long grid = 2 * (npairs < 74 ? npairs : 74);             // one CTA per SM, whole pairs
+  BN_CUDA(bn_launch(kern, dim3((unsigned)grid), PAIR_THREADS, HaloPairSmem::TOTAL, st, local, (const FpropPairArgs&)fa));
   BN_LAUNCHED();
   return 0;
 }
@@ -1962,6 +2311,8 @@ int bn_launch_igemm_tc(const ImgView& in, const float* wt, int wrow, const float
   a.colpart = nullptr;
   if (colsum_fused) *colsum_fused = a.colsum != nullptr;
   int r = try_dgrad_halo(a, h_classes, nclasses, colsum_fused, a.colsum, colpart, colpart_floats, st);
+  if (r <= 0) return r;
+  r = try_fprop_halo_pair(a, h_classes, nclasses, st);
   if (r <= 0) return r;
   // one tile per CTA below: a flush per tile makes ~10^4 same-address atomics per column, which costs
   // more than the separate column-sum pass saves (measured).  Instead every CTA writes its column sums

@@ -70,6 +70,11 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       "{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
       " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
 }
+// high / low words of a K-major SWIZZLE_128B descriptor: successive k-steps (32 bytes) add 2 to the low word
+__device__ __forceinline__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

@@ -1490,14 +1490,30 @@ __device__ __forceinline__ void umma_commit_pair_elect(uint32_t bar) {
       " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
       ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+// Cross-CTA signalling of the pair kernels guards tensor-memory and async-proxy (TMA, tcgen05) traffic only: what a
+// barrier phase has to order is covered by tcgen05.fence::before / after_thread_sync and by the complete_tx / commit
+// mechanisms themselves.  The .release.cluster / .acquire.cluster forms used at first compile to MEMBAR.ALL + ERRBAR
+// before every remote arrive (the epilogue warps then wait for their own earlier global STOREs to drain: 10 % of the
+// stall samples) and to an L1 invalidate (CCTL.IVALL) after every wait; the default .cta-scope forms are what the
+// 2-SM GEMM pipelines of CUTLASS use for the same hand-offs.  BN_PAIR_FENCES=1 at build time restores the heavy forms.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef BN_PAIR_FENCES
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#ifdef BN_PAIR_FENCES
   asm volatile(
       "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#else
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -1697,6 +1713,211 @@ dgrad_halo_pair_kernel(const __grid_constant__ HaloPairMaps maps, const __grid_c
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                  // no CTA leaves (or frees TMEM) while its peer may still signal / read it
+  if (warp == PAIR_EPI_WARPS) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair halo kernel for C_out = 64 (ConvTranspose2d forward into / Conv2d backward-data out of the 64-channel
+// 32 x 32 maps).  The layer's weights (819 KB at 128 input channels) cannot stay resident, but split over the pair
+// every SM streams only HALF of each stacked class tile for TWO tiles' worth of MMAs (M = 256): a quarter of the
+// one-CTA kernel's weight traffic per output pixel, which is what bounds that kernel (5.7 TB/s of L2 -> SM reads,
+// 95 us for 26.8 GFLOP).  Same roles and cross-CTA signalling as dgrad_halo_pair_kernel, plus a ring of weight
+// stages whose copies (both CTAs') complete on the leader's barrier.
+// ------------------------------------------------------------------------------------------------
+constexpr int P64_WST = 6;                               // weight stages: one MMA group each, <= 16 KB per CTA
+constexpr int P64_WBYTES = 2 * 64 * 128;                 // two whole 64-row class tiles
+struct HaloPair64Smem {
+  static constexpr int OFF_A = P64_WST * P64_WBYTES;
+  static constexpr int OFF_EPI = OFF_A + PAIR_SLOTS * HALO_ASTRIDE;
+  static constexpr int OFF_BAR = OFF_EPI + PAIR_EPI_WARPS * 4096;
+  static constexpr int TOTAL = OFF_BAR + 8 * (2 * PAIR_SLOTS + 2 * P64_WST + 4) + 32;
+};
+static_assert(HaloPair64Smem::TOTAL <= 227 * 1024, "shared memory per CTA");
+struct alignas(64) HaloPair64Maps {
+  CUtensorMap a;       // NHWC input, box 32 ch x 10 px x 18 rows x 1 frame
+  CUtensorMap b32;     // K-major weights, box 32 x 32 rows
+  CUtensorMap b64;     // K-major weights, box 32 x 64 rows
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+dgrad_halo_pair64_kernel(const __grid_constant__ HaloPair64Maps maps, const __grid_constant__ HaloArgs h) {
+  bn_pdl_trigger();
+  constexpr int NB = 64, ACC_COLS = 4 * NB, NCOLS = 2 * ACC_COLS;
+  using S = HaloPair64Smem;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcArgs& a = h.a;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);   // [PAIR_SLOTS]  leader: both CTAs' halo bytes
+  uint64_t* a_empty = a_full + PAIR_SLOTS;     // multicast commit
+  uint64_t* b_full = a_empty + PAIR_SLOTS;     // [P64_WST]  leader: both CTAs' weight bytes
+  uint64_t* b_empty = b_full + P64_WST;        // multicast commit
+  uint64_t* acc_full = b_empty + P64_WST;      // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]  leader: 16 arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    for (int s = 0; s < PAIR_SLOTS; ++s) { mbar_init(smem_u32(a_full + s), 1); mbar_init(smem_u32(a_empty + s), 1); }
+    for (int s = 0; s < P64_WST; ++s) { mbar_init(smem_u32(b_full + s), 1); mbar_init(smem_u32(b_empty + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(acc_full + s), 1); mbar_init(smem_u32(acc_empty + s), 2 * PAIR_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == PAIR_EPI_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  bn_pdl_wait();
+  const int Ci = a.Ci;
+  const int nchunk = Ci / BK;
+  const uint32_t smem_base = smem_u32(smem);
+  const long long total = h.total_tiles;
+  const long long npairs = (total + 1) / 2;
+  const long long p_first = blockIdx.x >> 1, p_step = gridDim.x >> 1;
+
+  if (warp < PAIR_EPI_WARPS) {
+    // ======================= epilogue: warp w drains lanes 32 (w & 3) .. of classes 2 (w >> 2), 2 (w >> 2) + 1 ==
+    float* tile = reinterpret_cast<float*>(smem + S::OFF_EPI) + warp * 1024;
+    const int elane = tid & 31;
+    const int q = warp & 3, chalf = warp >> 2;
+    const int pix = q * 32 + elane;
+    float4 cacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+    uint32_t leader_acc_empty[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(leader_acc_empty[s]) : "r"(smem_u32(acc_empty + s)));
+    int ti = 0;
+    for (long long P = p_first; P < npairs; P += p_step, ++ti) {
+      const long long T = 2 * P + rank;
+      const bool tvalid = T < total;
+      const int f = (int)(T / h.tiles_per_frame);
+      const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+      const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+      const int ym = by * 16 + (pix >> 3), xm = bx * 8 + (pix & 7);
+      const int buf = ti & 1;
+      mbar_wait_cluster(smem_u32(acc_full + buf), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * chalf + cc;
+        const bool rvalid = tvalid && ym < h.Hm[c] && xm < h.Wm[c];
+        const int oy = h.oy0[c] + a.os * ym, ox = h.ox0[c] + a.os * xm;
+        const long long obase = (((long long)f * a.Ho + oy) * a.Wo + ox) * a.Co;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS + h.pos[c] * NB + cb * 32, r);
+          tmem_ld_wait();
+          if (cc == 1 && cb == 1) {
+            tc_fence_before();                 // the last block of this tile is in registers: release the accumulator
+            __syncwarp();
+            if (elane == 0) mbar_arrive_cluster(leader_acc_empty[buf]);
+          }
+          warp_store_rows32(a.out, a.dact, BN_LEAK, rvalid ? obase + cb * 32 : -1, r, a.bias ? a.bias + cb * 32 : nullptr, a.act,
+                            tile, elane, cacc[cb], a.colsum != nullptr);
+        }
+      }
+    }
+    if (a.colsum) {
+      warp_flush_colsum(a.colsum, cacc[0], elane);
+      warp_flush_colsum(a.colsum + 32, cacc[1], elane);
+    }
+  } else if (warp == PAIR_EPI_WARPS) {
+    // ======================= MMA issuer: leader CTA only, converged warp, one elected lane ========
+    if (rank == 0) {
+      constexpr uint32_t a_hi = desc_hi_sw128(HALO_W * 128), b_hi = desc_hi_sw128(1024);
+      int ai = 0, bi = 0, ti = 0;
+      for (long long P = p_first; P < npairs; P += p_step, ++ti) {
+        const int buf = ti & 1;
+        if (ti >= 2) {
+          mbar_wait_cluster(smem_u32(acc_empty + buf), ((ti >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        uint32_t accflag = 0u;
+        for (int c = 0; c < nchunk; ++c, ++ai) {
+          const int slot = ai % PAIR_SLOTS;
+          mbar_wait_cluster(smem_u32(a_full + slot), (ai / PAIR_SLOTS) & 1);
+          tc_fence_after();
+          const uint32_t a_lo0 = desc_lo_sw128(smem_base + S::OFF_A + slot * HALO_ASTRIDE);
+          for (int gi = 0; gi < h.ngroups; ++gi, ++bi) {
+            const int stage = bi % P64_WST;
+            mbar_wait_cluster(smem_u32(b_full + stage), (bi / P64_WST) & 1);
+            tc_fence_after();
+            const HaloGroup g = h.g[gi];
+            const uint32_t idesc = make_idesc(256, g.ncls * NB);
+            const uint32_t acc = tmem_base + buf * ACC_COLS + g.col0 * NB;
+            const uint32_t a_lo = a_lo0 + (uint32_t)g.row_off * 8u;
+            const uint32_t b_lo = desc_lo_sw128(smem_base + stage * P64_WBYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              umma_tf32_pair_elect(acc, ((uint64_t)a_hi << 32) | (a_lo + 2 * k), ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc,
+                                   accflag);
+              accflag = 1u;
+            }
+            umma_commit_pair_elect(smem_u32(b_empty + stage));
+          }
+          umma_commit_pair_elect(smem_u32(a_empty + slot));
+        }
+        umma_commit_pair_elect(smem_u32(acc_full + buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= TMA: this CTA's halos and its half of every stacked weight group =====
+    const int lane = tid & 31;
+    const uint32_t leader_a_full0 = smem_u32(a_full) & PEER_BIT_MASK;
+    const uint32_t leader_b_full0 = smem_u32(b_full) & PEER_BIT_MASK;
+    const long long my_tiles = p_first < npairs ? (npairs - p_first + p_step - 1) / p_step : 0;
+    const long long nq = my_tiles * nchunk;            // chunk sequence of this CTA
+    auto load_halo = [&](long long q) {                // whole warp calls; lane 0 issues
+      const int slot = (int)(q % PAIR_SLOTS);
+      if (q >= PAIR_SLOTS) mbar_wait_cluster(smem_u32(a_empty + slot), (uint32_t)((q / PAIR_SLOTS) - 1) & 1u);
+      if (lane == 0) {
+        const long long P = p_first + (q / nchunk) * p_step;
+        const int c = (int)(q % nchunk);
+        const long long T = 2 * P + rank;
+        // a tile past the end (odd tile count) loads frame n: out of bounds, zero fill, nothing stored
+        const int f = (int)(T / h.tiles_per_frame);
+        const int blk = (int)(T - (long long)f * h.tiles_per_frame);
+        const int by = blk / h.tiles_x, bx = blk - by * h.tiles_x;
+        if (rank == 0) mbar_expect_tx(smem_u32(a_full + slot), 2u * (uint32_t)HALO_ABYTES);
+        tma_tile_4d_pair(smem_base + S::OFF_A + slot * HALO_ASTRIDE, &maps.a, leader_a_full0 + slot * 8, c * BK, bx * 8 + h.lo_x,
+                         by * 16 + h.lo_y, f);
+      }
+    };
+    constexpr int AHEAD = 2;                           // halo chunks requested ahead of the weight stream
+    for (long long q = 0; q < AHEAD && q < nq; ++q) load_halo(q);
+    long long bi = 0;
+    for (long long q = 0; q < nq; ++q) {
+      if (q + AHEAD < nq) load_halo(q + AHEAD);
+      const int c = (int)(q % nchunk);
+      for (int gi = 0; gi < h.ngroups; ++gi, ++bi) {
+        const int stage = (int)(bi % P64_WST);
+        if (bi >= P64_WST) mbar_wait_cluster(smem_u32(b_empty + stage), (uint32_t)((bi / P64_WST) - 1) & 1u);
+        const HaloGroup g = h.g[gi];
+        const uint32_t bar = leader_b_full0 + stage * 8;
+        if (lane == 0 && rank == 0) mbar_expect_tx(smem_u32(b_full + stage), 2u * (uint32_t)g.ncls * (NB * 128 / 2));
+        __syncwarp();
+        const uint32_t dst = smem_base + stage * P64_WBYTES;
+        if (g.ncls == 1) {
+          if (lane == 0) tma_tile_2d_pair(dst, &maps.b32, bar, g.wt[0] * Ci + c * BK, (int)rank * 32);
+        } else {
+          const int half = g.ncls / 2;                 // whole class tiles per CTA
+          if (lane < half) tma_tile_2d_pair(dst + lane * (NB * 128), &maps.b64, bar, g.wt[rank * half + lane] * Ci + c * BK, 0);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
   if (warp == PAIR_EPI_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NCOLS) : "memory");
@@ -2052,6 +2273,54 @@ bool encode_plane_4d(CUtensorMap* map, const float* p, int N, int H, int W, int 
   return r == CUDA_SUCCESS;
 }
 
+struct HaloPair64Key {
+  const void* in;
+  const void* wt;
+  int n, H, W, C, wrow;
+  bool operator==(const HaloPair64Key& o) const {
+    return in == o.in && wt == o.wt && n == o.n && H == o.H && W == o.W && C == o.C && wrow == o.wrow;
+  }
+};
+std::vector<std::pair<HaloPair64Key, HaloPair64Maps>> g_halo_pair64_cache;
+
+// returns 1 when not applicable
+int launch_halo_pair64(const TcArgs& a, const HaloArgs& h, cudaStream_t st) {
+  for (int gi = 0; gi < h.ngroups; ++gi)
+    if (h.g[gi].ncls != 1 && h.g[gi].ncls != 2 && h.g[gi].ncls != 4) return 1;
+  HaloArgs hh = h;
+  hh.csz = 2;
+  hh.dbg = 0;
+  const HaloPair64Maps* pm = nullptr;
+  {
+    HaloPair64Key key{a.in, a.wt, a.n, a.Hi, a.Wi, a.Ci, a.wrow};
+    std::lock_guard<std::mutex> lk(g_tma_mutex);
+    for (auto& kv : g_halo_pair64_cache)
+      if (kv.first == key) pm = &kv.second;
+    if (!pm) {
+      HaloPair64Maps m;
+      memset(&m, 0, sizeof(m));
+      if (!encode_tiled_4d(&m.a, a.in, a.n, a.Hi, a.Wi, a.Ci, BK, HALO_W, HALO_H)) return 1;
+      if (!encode_tiled_2d(&m.b32, a.wt, a.Co, a.wrow, BK, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (!encode_tiled_2d(&m.b64, a.wt, a.Co, a.wrow, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+      if (g_halo_pair64_cache.size() >= 256) g_halo_pair64_cache.clear();
+      g_halo_pair64_cache.emplace_back(key, m);
+      pm = &g_halo_pair64_cache.back().second;
+    }
+  }
+  HaloPair64Maps local = *pm;
+  auto kern = dgrad_halo_pair64_kernel;
+  static bool configured = false;
+  if (!configured) {
+    BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloPair64Smem::TOTAL));
+    configured = true;
+  }
+  const long long npairs = (h.total_tiles + 1) / 2;
+  long long grid = 2 * (npairs < 74 ? npairs : 74);             // one CTA per SM, whole pairs
+  BN_CUDA(bn_launch(kern, dim3((unsigned)grid), PAIR_THREADS, HaloPair64Smem::TOTAL, st, local, (const HaloArgs&)hh));
+  BN_LAUNCHED();
+  return 0;
+}
+
 // returns 1 when the op is not a stride-2 fprop-form layer with 32 input / 64 output channels
 int try_fprop_halo_pair(const TcArgs& a, const TapClass* hc, int nclasses, cudaStream_t st) {
   static const bool off = [] { const char* e = getenv("BN_FPROP_HALO"); return e && e[0] == '0'; }();
@@ -2236,6 +2505,12 @@ int try_dgrad_halo(const TcArgs& a, const TapClass* hc, int nclasses, int* colsu
   static const bool pair_off = [] { const char* e = getenv("BN_HALO_PAIR"); return e && e[0] == '0'; }();
   if (a.Co == 32 && a.Ci <= 32 * PAIR_MAXCHUNK && !pair_off && h.total_tiles >= 2) {
     int r = launch_halo_pair(a, h, st);
+    if (r <= 0) return r;
+  }
+  // C_out = 64: CTA-pair kernel with the weight stream split between the two SMs (BN_HALO_PAIR64=0: one-CTA kernel)
+  static const bool pair64_off = [] { const char* e = getenv("BN_HALO_PAIR64"); return e && e[0] == '0'; }();
+  if (a.Co == 64 && !pair64_off && h.total_tiles >= 2) {
+    int r = launch_halo_pair64(a, h, st);
     if (r <= 0) return r;
   }
   HaloMaps local = *hm;

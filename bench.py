@@ -667,10 +667,12 @@ def run_ours(args):
     cae_value = B / (ms_per_step * 1e-3)
     # (kernels are timed alone BEFORE the seconds-long cuBLAS loops below heat the part up)
     kernels = [
-        time_layer_kernel(model, device, 0, 2, 0, 'igemm_tma_kernel<128,3> (encoder conv2 forward, M=65536 N=128 K=1600)'),
-        time_layer_kernel(model, device, 0, 1, 0, 'igemm_tma_kernel<64,4> (encoder conv1 forward, M=262144 N=64 K=800)'),
-        time_layer_kernel(model, device, 0, 1, 2, 'wgrad_tma_kernel<64,4> (encoder conv1 weight gradient, 800x64 over 262144 pixels)'),
-        time_layer_kernel(model, device, 1, 3, 0, 'dgrad_halo_kernel<32,3> (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])'),
+        time_layer_kernel(model, device, 0, 2, 0, 'igemm_tma_kernel<128,2,2> (encoder conv2 forward, M=65536 N=128 K=1600)'),
+        time_layer_kernel(model, device, 0, 1, 0, 'fprop_halo_pair_kernel (encoder conv1 forward, M=262144 N=64 K=800)'),
+        time_layer_kernel(model, device, 0, 1, 2, 'wgrad_tma_kernel<64,2,2> (encoder conv1 weight gradient, 800x64 over 262144 pixels)'),
+        time_layer_kernel(model, device, 1, 3, 0, 'dgrad_halo_pair_kernel (decoder convtranspose3 forward, 4 x [M=262144 N=32 K<=576])'),
+        time_layer_kernel(model, device, 1, 2, 0, 'dgrad_halo_pair64_kernel (decoder convtranspose2 forward, 4 x [M=65536 N=64 K<=1152])'),
+        time_layer_kernel(model, device, 0, 3, 0, 'igemm_tma_kernel<256,4,1> (encoder conv3 forward, M=16384 N=256 K=3200)'),
     ]
     dom = kernels[0]
 

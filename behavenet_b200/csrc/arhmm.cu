@@ -467,6 +467,8 @@ __device__ __forceinline__ void run_range(int t0, int n, int dir, Load load, Ste
 
 struct ScanIn { float b, m, x; };
 
+// (Measured and dropped: warp-uniform trip counts with full-mask __syncwarp() in place of the sub-warp mask, which
+// compiles to MATCH.ANY + REDUX + VOTE per barrier -- the early-out of dead steps costs more: 461 vs 443 us per E-step.)
 // packed fp32 pairs (sm_100 FFMA2 / FADD2): the scan is issue-bound, so two lanes per instruction
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b),
@@ -478,6 +480,14 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), ud;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
   return *reinterpret_cast<float2*>(&ud);
+}
+
+// 1 / x for a positive normal x, 0 otherwise: one MUFU + a select (the guarded __fdividef spent six instructions of
+// every step on denormal handling the scaled messages never need)
+__device__ __forceinline__ float rcp_pos(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return x > 1.1754944e-38f ? r : 0.f;
 }
 
 template <int KP, bool POST>
@@ -593,20 +603,30 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
       logZ = (double)__ldg(mp);
     }
     // first half: t = 1 .. h; stores the (unnormalised) a_{t-1}, produces a_t
-    auto load1 = [&](int t) {
+    // run_range calls load() and step() for consecutive t, so the streams are walked with running pointers
+    // (recomputing base + t * K in 64 bits was ~15 of the 53 instructions of a step)
+    const float* bl = Bp + K;                        // b_t of the next load (t = 1 ..)
+    const float* ml = mp + 1;
+    float* es = Ep;                                  // a_{t-1} / gamma_{t-1} of the next step
+    auto load1 = [&](int) {
       ScanIn in;
-      in.b = kvalid ? __ldg(Bp + t * K) : 0.f;
-      in.m = __ldg(mp + t);
+      in.b = kvalid ? __ldg(bl) : 0.f;
+      in.m = __ldg(ml);
       in.x = 0.f;
+      bl += K;
+      ++ml;
       return in;
     };
-    auto step1 = [&](int t, const ScanIn& in) {
+    auto step1 = [&](int, const ScanIn& in) {
       float2 v[H2];
       exchange(acur, v);
       float dot, S;                                  // S = S_{t-1}
       dot_sum(v, Pcol, dot, S);
-      if (POST && kvalid) Ep[(t - 1) * K] = acur;
-      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      if (POST) {
+        if (kvalid) *es = acur;
+        es += K;
+      }
+      const float inv = rcp_pos(S);
       logZ += (double)(__logf(S) + in.m);            // fp64 accumulation, off the dependent chain
       acur = dot * in.b * inv;
       rcur = inv;
@@ -631,23 +651,28 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     float2 X[H2], vprev[H2];
 #pragma unroll
     for (int j = 0; j < H2; ++j) { X[j] = make_float2(0.f, 0.f); vprev[j] = make_float2(0.f, 0.f); }
+    const float* xl = Bt + (long long)h * K;         // beta_tilde_{t-1} of the next load (t = h+1 ..)
     auto load2 = [&](int t) {
       ScanIn in;
       const bool cur = t < T;
-      in.b = (cur && kvalid) ? __ldg(Bp + t * K) : 0.f;
-      in.m = cur ? __ldg(mp + t) : 0.f;
-      in.x = kvalid ? Bt[(t - 1) * K] : 0.f;                      // beta_tilde_{t-1}(k)
+      in.b = (cur && kvalid) ? __ldg(bl) : 0.f;
+      in.m = cur ? __ldg(ml) : 0.f;
+      in.x = kvalid ? *xl : 0.f;                                  // beta_tilde_{t-1}(k)
+      bl += K;
+      ++ml;
+      xl += K;
       return in;
     };
-    auto step2 = [&](int t, const ScanIn& in) {
+    auto step2 = [&](int, const ScanIn& in) {
       float2 v[H2];
       const float ab = acur * in.x;
       float G;                                       // sum_k a_{t-1}(k) beta_{t-1}(k)
       exchange2(acur, ab, v, G);
       float dot, S;
       dot_sum(v, Pcol, dot, S);
-      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
-      if (kvalid) Ep[(t - 1) * K] = ab * rG;
+      const float rG = rcp_pos(G);
+      if (kvalid) *es = ab * rG;
+      es += K;
       const float w = bprev * in.x * rcur * rG;      // xi_{t-2}: vprev is all-zero on the first step
       const float2 w2 = make_float2(w, w);
 #pragma unroll
@@ -655,7 +680,7 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
         X[j] = ffma2(vprev[j], w2, X[j]);
         vprev[j] = v[j];
       }
-      const float inv = S > 0.f ? __fdividef(1.f, S) : 0.f;
+      const float inv = rcp_pos(S);
       logZ += (double)(__logf(S) + in.m);            // in.m = 0 on the last step (t == T)
       acur = dot * in.b * inv;
       rcur = inv;
@@ -681,20 +706,24 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
     for (int j = 0; j < H2; ++j) Prow[j] = make_float2(Pg[k * KP + 2 * j], Pg[k * KP + 2 * j + 1]);
     float beta = 1.f;                                // beta_tilde_{t+1}(j)
     if (T > 0 && kvalid) Bt[(T - 1) * K] = 1.f;
-    auto load1 = [&](int t) {
+    const float* bl = Bp + (long long)(T - 1) * K;   // b_{t+1} of the next load (t = T-2 .. 0)
+    float* bs = Bt + (long long)(T - 2) * K;         // beta_tilde_t of the next first-half step
+    auto load1 = [&](int) {
       ScanIn in;
-      in.b = kvalid ? __ldg(Bp + (t + 1) * K) : 0.f;
+      in.b = kvalid ? __ldg(bl) : 0.f;
       in.m = 0.f;
       in.x = 0.f;
+      bl -= K;
       return in;
     };
-    auto step1 = [&](int t, const ScanIn& in) {
+    auto step1 = [&](int, const ScanIn& in) {
       float2 vk[H2];
       exchange(in.b * beta, vk);
       float u, Dn;
       dot_sum(vk, Prow, u, Dn);
-      beta = u * (Dn > 0.f ? __fdividef(1.f, Dn) : 0.f);
-      if (kvalid) Bt[t * K] = beta;
+      beta = u * rcp_pos(Dn);
+      if (kvalid) *bs = beta;
+      bs -= K;
     };
     run_range<PF, ScanIn>(T - 2, max(T - 1 - h, 0), -1, load1, step1);      // t = T-2 .. h
     pair_barrier();
@@ -705,16 +734,21 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
 #pragma unroll
     for (int j = 0; j < H2; ++j) { X[j] = make_float2(0.f, 0.f); vkp[j] = make_float2(0.f, 0.f); }
     float al_p = 0.f, ab_p = 0.f, rho_p = 0.f;
-    auto load2 = [&](int t) {
+    const float* xl = Ep + (long long)(h - 1) * K;   // a_t of the next load (t = h-1 .. 0)
+    auto load2 = [&](int) {
       ScanIn in;
-      in.b = kvalid ? __ldg(Bp + (t + 1) * K) : 0.f;
+      in.b = kvalid ? __ldg(bl) : 0.f;
       in.m = 0.f;
-      in.x = kvalid ? Ep[t * K] : 0.f;                            // a_t(j) stored by the forward group
+      in.x = kvalid ? *xl : 0.f;                                  // a_t(j) stored by the forward group
+      bl -= K;
+      xl -= K;
       return in;
     };
-    auto finalise = [&](int tp, float G) {
-      const float rG = G > 0.f ? __fdividef(1.f, G) : 0.f;
-      if (kvalid) Ep[tp * K] = ab_p * rG;
+    float* gs = Ep + (long long)(h - 1) * K;         // gamma_tp of the next finalise (tp = h-1 .. 0)
+    auto finalise = [&](int, float G) {
+      const float rG = rcp_pos(G);
+      if (kvalid) *gs = ab_p * rG;
+      gs -= K;
       const float w = al_p * rho_p * rG;
       const float2 w2 = make_float2(w, w);
 #pragma unroll
@@ -727,7 +761,7 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
       if (t + 1 < h) finalise(t + 1, G);
       float u, Dn;
       dot_sum(vk, Prow, u, Dn);
-      rho_p = Dn > 0.f ? __fdividef(1.f, Dn) : 0.f;
+      rho_p = rcp_pos(Dn);
       beta = u * rho_p;
       al_p = in.x;
       ab_p = in.x * beta;

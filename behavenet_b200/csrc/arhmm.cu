@@ -490,6 +490,13 @@ __device__ __forceinline__ float rcp_pos(float x) {
   return x > 1.1754944e-38f ? r : 0.f;
 }
 
+// log2 of a positive normal x in one MUFU (the normalisers S_t are sums of scaled probabilities, >= 1e-30)
+__device__ __forceinline__ float lg2_pos(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <int KP, bool POST>
 __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan2Args a) {
   constexpr int GPW = 32 / KP;                     // trials per warp
@@ -627,7 +634,7 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
         es += K;
       }
       const float inv = rcp_pos(S);
-      logZ += (double)(__logf(S) + in.m);            // fp64 accumulation, off the dependent chain
+      logZ += (double)fmaf(lg2_pos(S), 0.69314718f, in.m);            // fp64 accumulation, off the dependent chain
       acur = dot * in.b * inv;
       rcur = inv;
       bprev = in.b;
@@ -641,7 +648,7 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
         exchange(acur, v);
         float dot, S;
         dot_sum(v, Pcol, dot, S);
-        logZ += (double)__logf(S);
+        logZ += (double)(lg2_pos(S) * 0.69314718f);
       }
       if (active && k == 0 && a.logZ) a.logZ[trial] = logZ;
       return;
@@ -681,7 +688,7 @@ __global__ void __launch_bounds__(128, KP == 32 ? 2 : 4) scan2_kernel(const Scan
         vprev[j] = v[j];
       }
       const float inv = rcp_pos(S);
-      logZ += (double)(__logf(S) + in.m);            // in.m = 0 on the last step (t == T)
+      logZ += (double)fmaf(lg2_pos(S), 0.69314718f, in.m);            // in.m = 0 on the last step (t == T)
       acur = dot * in.b * inv;
       rcur = inv;
       bprev = in.b;

@@ -8,7 +8,7 @@ python bench.py --steps 20 --warmup 5 > $out/bench_n1.json 2> $out/bench_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_cae_2steps.csv python scripts/prof_cae.py cae 2 > $out/prof_cae.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_arhmm_2steps.csv python scripts/prof_cae.py hmm 2 > $out/prof_hmm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"igemm_|wgrad_|dgrad_halo|thin_" -s 0 -c 30 -o $out/cae_full python scripts/prof_cae.py cae 1 > $out/ncu_cae.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"igemm_|wgrad_|_halo|thin_" -s 0 -c 30 -o $out/cae_full python scripts/prof_cae.py cae 1 > $out/ncu_cae.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"scan2|emission" -s 0 -c 2 -o $out/hmm_full python scripts/prof_cae.py hmm 1 > $out/ncu_hmm.log 2>&1
 ncu -i $out/cae_full.ncu-rep --page raw --csv > $out/cae_full.raw.csv 2>/dev/null
 ncu -i $out/hmm_full.ncu-rep --page raw --csv > $out/hmm_full.raw.csv 2>/dev/null

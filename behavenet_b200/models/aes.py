@@ -448,7 +448,7 @@ class AEMSP(_AutogradChunkedAE):
 
     def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200):
         """{'loss', 'loss_mse', 'loss_msp', 'labels_r2'} (aes.py:997-1077)."""
-        from sklearn.metrics import r2_score
+        from ..fitting.losses import r2_variance_weighted
         x, y = data['images'][0], data['labels'][0]
         m = data['masks'][0] if 'masks' in data else None
         y_hats = []
@@ -460,8 +460,7 @@ class AEMSP(_AutogradChunkedAE):
             y_hats.append(y_hat.detach())
             return {'loss': l_mse + self.hparams['msp.alpha'] * l_msp, 'loss_mse': l_mse, 'loss_msp': l_msp}
         out = self._chunk_loop(data, chunk_size, accumulate_grad, chunk_loss, ['loss', 'loss_mse', 'loss_msp'])
-        out['labels_r2'] = r2_score(y.detach().cpu().numpy(), torch.cat(y_hats, 0).cpu().numpy(),
-                                    multioutput='variance_weighted')
+        out['labels_r2'] = r2_variance_weighted(y.detach().cpu().numpy(), torch.cat(y_hats, 0).cpu().numpy())
         return out
 
     def save(self, filepath):

@@ -574,15 +574,14 @@ class PSVAE(AE):
         vals['alpha'] = alpha
         vals['beta'] = beta
         # variance-weighted R^2 on the host, as the reference does with sklearn (vaes.py:709-718)
-        from sklearn.metrics import r2_score
+        from ..fitting.losses import r2_variance_weighted
         y_np = y.cpu().numpy()
         yh_np = y_hat_all.cpu().numpy()
         if nm is not None:
             n_np = nm.cpu().numpy()
-            vals['label_r2'] = r2_score(y_np[n_np == 1], yh_np[n_np == 1],
-                                        multioutput='variance_weighted')
+            vals['label_r2'] = r2_variance_weighted(y_np[n_np == 1], yh_np[n_np == 1])
         else:
-            vals['label_r2'] = r2_score(y_np, yh_np, multioutput='variance_weighted')
+            vals['label_r2'] = r2_variance_weighted(y_np, yh_np)
         return vals
 
     # -- helpers used by the reference's plotting code (vaes.py:731-846); tiny tensors ----------
@@ -699,7 +698,7 @@ class MSPSVAE(PSVAE):
     def loss(self, datas, dataset=None, accumulate_grad=True, chunk_size=None, eps=None):
         """One pass over the whole batch (a dict, or a list of per-session dicts with ``dataset`` the list
         of their session ids, which adds the triplet term) (vaes.py:926-1077)."""
-        from sklearn.metrics import r2_score
+        from ..fitting.losses import r2_variance_weighted
         multi = isinstance(datas, list)
         if multi:
             def cat(key):
@@ -736,9 +735,9 @@ class MSPSVAE(PSVAE):
         y_np, yh_np = y.detach().cpu().numpy(), y_hat.detach().cpu().numpy()
         if n is not None:
             keep = n.detach().cpu().numpy() == 1
-            r2 = r2_score(y_np[keep], yh_np[keep], multioutput='variance_weighted')
+            r2 = r2_variance_weighted(y_np[keep], yh_np[keep])
         else:
-            r2 = r2_score(y_np, yh_np, multioutput='variance_weighted')
+            r2 = r2_variance_weighted(y_np, yh_np)
         out.update({'alpha': alpha, 'beta': beta, 'delta': delta, 'label_r2': r2})
         return out
 

@@ -545,7 +545,7 @@ def bench_psvae(device, world, rank, args):
             'steps': steps, 'global_batch': res['weak']['global_batch'],
             'tflops_per_gpu': res['weak']['tflops_per_gpu'], 'weak': res['weak'], 'strong': res['strong'],
             'note': 'weak = 512 frames per GPU, strong = the 512-frame batch of BASELINE config 3 sharded over the '
-                    'ranks; includes sklearn r2_score on the host and the per-chunk latent-block launches, as the '
+                    'ranks; includes the label R^2 on the host and the per-chunk latent-block launches, as the '
                     'reference loss() does; frames resident in HBM'}
 
 

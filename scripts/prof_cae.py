@@ -19,6 +19,19 @@ if what == 'cae':
         out = model.loss({'images': x[None]})
     torch.cuda.synchronize()
     print(out)
+elif what == 'psvae':
+    from behavenet_b200.models import PSVAE
+    hp = co.make_hparams(2, 128, 128, 16, 'ps-vae', 4)
+    model = PSVAE(copy.deepcopy(hp)); model.load_state_dict(co.init_state_dict(hp, seed=0)); model.cuda()
+    model.curr_epoch = 1
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(512, 2, 128, 128, generator=g).cuda()
+    y = torch.randn(512, 4, generator=g).cuda()
+    for _ in range(steps):
+        model.zero_grad()
+        out = model.loss({'images': x[None], 'labels': y[None]})
+    torch.cuda.synchronize()
+    print(out)
 else:
     import numpy as np
     from oracle import arhmm_oracle as ao

@@ -78,3 +78,24 @@ def test_triplet_loss_known_answers():
     loss = losses.triplet_loss(tl, torch.cat([x] + [t * torch.ones_like(x) for t in (t1, t2, t3)], 0), ds4)
     v1, v2, v3 = (-np.sqrt(n_dims * t ** 2) + 1 for t in (t1, t2, t3))
     assert np.isclose(loss.item(), (6 * v1 + 4 * v2 + 2 * v3) / 12, atol=1e-5)
+
+
+def test_r2_variance_weighted_matches_sklearn():
+    """label_r2 of the PS-VAE / MSP losses (reference vaes.py:709-718 calls sklearn's r2_score per loss call):
+    the validation-free restatement returns sklearn's value, including constant and perfectly predicted columns."""
+    from sklearn.metrics import r2_score
+    from behavenet_b200.fitting.losses import r2_variance_weighted
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n, m = int(rng.integers(2, 300)), int(rng.integers(1, 6))
+        y = rng.standard_normal((n, m)).astype(np.float32)
+        yh = y + rng.standard_normal((n, m)).astype(np.float32) * rng.random()
+        if trial % 7 == 0:
+            y[:, 0] = 1.5                       # constant target column: zero denominator
+        if trial % 11 == 0:
+            yh[:, 0] = y[:, 0]                  # perfect prediction: zero numerator
+        if trial % 13 == 0:
+            y[:] = 2.0                          # every denominator zero: uniform average
+        a = r2_score(y, yh, multioutput='variance_weighted')
+        b = r2_variance_weighted(y, yh)
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (trial, a, b)

@@ -460,7 +460,7 @@ def bench_arhmm(args, device, world, rank):
     # (a) what EM does -- the list is staged ONCE (gather into pinned memory + H2D), then every iteration's
     # E-step re-uses it (hmm.py caches by identity + fingerprint) and reads its statistics back;
     # (b) cold: staging + one E-step + read-back per call.
-    n_iter = 10
+    n_iter = 20                  # the reference's default number of EM iterations (configs/arhmm_jsons/arhmm_training.json:17)
 
     def em_like():
         hmm.clear_cache()

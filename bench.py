@@ -782,6 +782,7 @@ def run_ours(args):
         'roofline': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': hbm_achieved / peaks['hbm_gbs'],
                      'traffic': kernel_traffic().get('arhmm_estep'),
+                     'other_bounds': arhmm_other_bounds(hm['weak_ms'] if hm else None),
                      'note': '113 B/timestep algorithmic (48 B latents in + 64 B posteriors out + per-trial outputs), '
                              'whole E-step time; peak %s; traffic = dram read+write of all E-step kernels from the ncu '
                              'export of this build or null.  The binding limits are the T-step serial chain / '
@@ -794,6 +795,27 @@ def run_ours(args):
             line['arhmm']['cpu_baseline'] = cpu['arhmm']
     _OUT.write(json.dumps(line) + '\n')
     _OUT.flush()
+
+
+def arhmm_other_bounds(estep_ms):
+    """The limits that actually bind the E-step (SURVEY hard part 1), from the ncu export of this build
+    (profiles/r02_kernel_traffic.json, 'arhmm_estep_bounds'): the ISSUE-SLOT floor of each kernel = executed warp
+    instructions / (SMs x 4 schedulers) cycles, and the TENSOR floor of the emission GEMM = its tensor-pipe-active
+    cycles; frac = (sum of the larger floor per kernel) / measured E-step time."""
+    b = kernel_traffic().get('arhmm_estep_bounds')
+    if not b or not estep_ms:
+        return None
+    out, floor_us = {}, 0.0
+    for name, k in b.items():
+        clk_mhz = k['sm_cycles'] / k['duration_us']
+        issue_us = k['warp_instructions'] / (148 * 4) / clk_mhz
+        tensor_us = k['tensor_pipe_active_pct'] / 100.0 * k['duration_us']
+        out[name] = {'issue_slot_floor_us': issue_us, 'tensor_floor_us': tensor_us, 'ncu_duration_us': k['duration_us'],
+                     'issue_active_pct': k['issue_active_pct']}
+        floor_us += max(issue_us, tensor_us)
+    out['floor_us'] = floor_us
+    out['frac'] = floor_us / (estep_ms * 1e3)
+    return out
 
 
 def import_reference():

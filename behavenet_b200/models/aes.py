@@ -10,6 +10,8 @@ as parameter containers (so names, shapes and default initialisation are torch's
 eager fallback: inputs on the CPU raise.
 """
 
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -19,6 +21,21 @@ from behavenet_b200.models.base import BaseModule, BaseModel
 from behavenet_b200.models._engine import CaeDriver, Runtime, EncodeFn, DecodeFn
 
 __all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'ConditionalAE', 'AEMSP', 'load_pretrained_ae']
+
+
+_DP_TIMING = os.environ.get('BN_DP_TIMING', '0') == '1'
+_DP_TIMES = []
+
+
+def _dp_timing_report(ev):
+    """BN_DP_TIMING=1 (diagnostic): device time of a data-parallel AE.loss call from the end of the forward pass --
+    decoder backward | encoder backward | collectives still exposed after the last backward kernel; rank 0 prints the
+    mean of every 10 calls."""
+    _DP_TIMES.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
+    if len(_DP_TIMES) % 10 == 0 and parallel.rank() == 0:
+        import sys
+        t = np.mean(np.array(_DP_TIMES[-10:]), axis=0)
+        sys.stderr.write('[BN_DP_TIMING] decoder bwd %.3f ms, encoder bwd %.3f ms, exposed collectives %.3f ms\n' % tuple(t))
 
 
 class ConvAEEncoder(BaseModule):
@@ -287,7 +304,8 @@ class AE(BaseModel):
             for p in everything:
                 if p.requires_grad:
                     parallel.all_reduce_sum(p.grad)
-        parallel.all_reduce_sum(extra)
+        if extra is not None:
+            parallel.all_reduce_sum(extra)
         if pending is not None:
             pending[0].wait()
 
@@ -332,19 +350,39 @@ class AE(BaseModel):
             drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms,
                        chunk_size=chunk_size, frame_offset=beg, n_total=n_total,
                        grad_coef=2.0 / numel, sse=sse)
-            if accumulate_grad:
-                grads = self._grad_table(params)
-                dz = drv.decode_bwd(n, None, params, packed, ws, grads, device)
-                if self.data_parallel and parallel.enabled():
-                    pending = self._allreduce_begin(params)
-                drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
+        dp = self.data_parallel and parallel.enabled()
+        # the per-chunk loss sums are final after the forward pass: their (tiny, latency-bound) all-reduce is started
+        # here and completes under the backward pass instead of after it
+        sse_work = parallel.all_reduce_sum_async(sse) if (dp and parallel.overlap_enabled()) else None
+        timing = dp and _DP_TIMING
+        if timing:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+        if n > 0 and accumulate_grad:
+            grads = self._grad_table(params)
+            dz = drv.decode_bwd(n, None, params, packed, ws, grads, device)
+            if dp:
+                pending = self._allreduce_begin(params)
+            if timing:
+                ev[1].record()
+            drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
         elif accumulate_grad:
             self._grad_table(params)
-        if self.data_parallel and parallel.enabled():
+        if timing:
+            if not (n > 0 and accumulate_grad):
+                ev[1].record()
+            ev[2].record()
+        if dp:
             if accumulate_grad:
-                self._allreduce(params, sse, pending)
-            else:
+                self._allreduce(params, None if sse_work is not None else sse, pending)
+            elif sse_work is None:
                 parallel.all_reduce_sum(sse)
+            if sse_work is not None:
+                sse_work.wait()
+        if timing:
+            ev[3].record()
+            ev[3].synchronize()
+            _dp_timing_report(ev)
         numel = float(np.prod(drv.img))
         loss_val = float(sse.sum().item()) / (numel * n_total)
         return {'loss': loss_val}

@@ -368,6 +368,8 @@ class AE(BaseModel):
             drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
         elif accumulate_grad:
             self._grad_table(params)
+            if dp:
+                pending = self._allreduce_begin(params)      # a rank without frames issues the same collectives
         if timing:
             if not (n > 0 and accumulate_grad):
                 ev[1].record()

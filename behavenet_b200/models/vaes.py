@@ -527,6 +527,13 @@ class PSVAE(AE):
             drv.decode(z, params, packed, ws, want_xhat=False, target=xs, mask=ms,
                        chunk_size=chunk_size, frame_offset=beg, n_total=n_total, grad_coef=1.0,
                        sse=sse)
+        stats_work = None
+        if dp and parallel.overlap_enabled():
+            # every loss term and the label predictions are final after the forward pass: their all-reduces run under
+            # the backward pass (same order on every rank, also on one that owns no frames)
+            stats = torch.cat([sse[:, None], terms], 1)
+            stats_work = (parallel.all_reduce_sum_async(stats), parallel.all_reduce_sum_async(y_hat_all))
+        if n > 0:
             if accumulate_grad:
                 gz_dec = drv.decode_bwd(n, None, params, packed, ws, grads, device)
                 pending = self._allreduce_begin(params, 'dec') if dp else None
@@ -539,12 +546,19 @@ class PSVAE(AE):
                     _lib.stream_ptr()), 'bn_psvae_latent_bwd')
                 drv.encode_bwd(xs, gpre, glv, params, packed, ws, grads)
         if dp:
-            stats = torch.cat([sse[:, None], terms], 1)
+            if n == 0 and accumulate_grad:
+                pending = self._allreduce_begin(params, 'dec')
+            if stats_work is None:
+                stats = torch.cat([sse[:, None], terms], 1)
             if accumulate_grad:
-                self._allreduce(params, stats, pending)
-            else:
+                self._allreduce(params, stats if stats_work is None else None, pending)
+            elif stats_work is None:
                 parallel.all_reduce_sum(stats)
-            parallel.all_reduce_sum(y_hat_all)
+            if stats_work is None:
+                parallel.all_reduce_sum(y_hat_all)
+            else:
+                stats_work[0].wait()
+                stats_work[1].wait()
             sse, terms = stats[:, 0], stats[:, 1:]
         # ---- one device->host read, then the reference's bookkeeping (vaes.py:700-729)
         host = torch.cat([sse[:, None], terms], 1).cpu().numpy()

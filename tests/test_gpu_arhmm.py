@@ -226,3 +226,26 @@ def test_long_trials_stay_normalised():
     rng = np.random.RandomState(6)
     xs = [ao.sample(p, T, rng)[1].astype(np.float32) for T in (5000, 4097)]
     check_against_oracle(p, xs)
+
+
+@pytest.mark.parametrize('env', [{'BN_SCAN': '4'}, {'BN_EMIT': '1'}, {'BN_SCAN': '1'}])
+def test_alternative_estep_kernels_match_oracle(env):
+    """The kernels behind the diagnostic switches (SPL-states-per-lane scan, one-stage tcgen05 emission kernel,
+    three-pass scan) stay parity-green: the switches are read once per process, so each runs in its own."""
+    import os
+    import subprocess
+    import sys
+    from tests.helpers import ROOT
+    code = (
+        "import numpy as np\n"
+        "from oracle import arhmm_oracle as ao\n"
+        "from tests.test_gpu_arhmm import check_against_oracle\n"
+        "for K, D, lags in [(16, 12, 2), (32, 4, 1), (8, 8, 1)]:\n"
+        "    p = ao.synth_params(K, D, lags, seed=K + D, mix=0.05)\n"
+        "    X = ao.sample_batch(p, 6, 300, seed=1)\n"
+        "    xs = [X[i][:n] for i, n in enumerate([300, 1, 2, 17, 129, 257])]\n"
+        "    check_against_oracle(p, xs)\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=dict(os.environ, **env), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stdout[-2000:] + r.stderr[-4000:]

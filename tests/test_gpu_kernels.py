@@ -173,3 +173,19 @@ def test_output_layer_forward_with_fused_loss_tensor_core_matches_cuda_core(geom
     sse_ref = ref[2 * tot:].view(torch.float64)
     sse_tc = tc[2 * tot:].view(torch.float64)
     assert float(((sse_tc - sse_ref).abs() / sse_ref).max()) < 1e-6
+
+
+def test_one_cta_kernels_behind_the_switches_stay_green():
+    """The CTA-pair kernels take the 32- / 64-channel layers by default; the one-CTA halo and im2col kernels they
+    replaced remain the path for shapes the pair kernels do not cover (and the A/B baseline of profiles/).  Run the
+    layer-kernel parity cases of two geometries with the pair kernels switched off (switches are read once per
+    process)."""
+    import os
+    import subprocess
+    import sys
+    from tests.helpers import ROOT
+    env = dict(os.environ, BN_FPROP_HALO='0', BN_HALO_PAIR='0', BN_HALO_PAIR64='0')
+    r = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_kernels.py', '-x', '-q', '-m', 'gpu', '-k',
+                        'test_tensor_core_kernel_matches_cuda_core_kernel and (geom1 or geom2)'],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and ' passed' in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -237,6 +237,14 @@ class _PinnedPool:
 _STAGE_CHUNK_ROWS = 1 << 18          # rows per host-gather / H2D piece (12 MB at D = 12)
 
 
+def _gather_threads():
+    """Host threads of one rank's row gather: up to 8, but the ranks of a node share its cores (8 ranks x 8 threads on
+    a 32-core host made the staging of every rank slower than one rank alone)."""
+    cores = os.cpu_count() or 1
+    local = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1)
+    return max(1, min(8, cores // max(1, local)))
+
+
 def _gather_rows(datas, lens, D, out):
     """Concatenate per-trial (T_i, D) host arrays into ``out`` ((sum T_i, D) float32) with the library's
     multi-threaded row gather (bn_host_gather_rows); arrays that are not C-contiguous float32 / float64
@@ -249,7 +257,7 @@ def _gather_rows(datas, lens, D, out):
     f64 = np.fromiter((d.dtype == np.float64 for d in keep), dtype=np.int32, count=n)
     _lib.check(_lib.lib().bn_host_gather_rows(
         ptrs.ctypes.data, rows.ctypes.data, f64.ctypes.data, n, D, out.ctypes.data,
-        min(8, os.cpu_count() or 1)), 'bn_host_gather_rows')
+        _gather_threads()), 'bn_host_gather_rows')
 
 
 class _Staged:

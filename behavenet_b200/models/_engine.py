@@ -21,12 +21,10 @@ def _unsupported(hparams):
         raise NotImplementedError('only model_type="conv" has a B200 kernel path')
     if hparams.get('ae_batch_norm', False):
         raise NotImplementedError('ae_batch_norm is not supported by the B200 kernels')
-    if hparams.get('fit_sess_io_layers', False):
-        raise NotImplementedError('fit_sess_io_layers is not supported by the B200 kernels')
     if hparams.get('ae_decoding_last_FF_layer', False):
         raise NotImplementedError('ae_decoding_last_FF_layer is not supported by the B200 kernels')
-    if hparams.get('ae_padding_type', 'same') != 'same':
-        raise NotImplementedError('only ae_padding_type="same" is supported by the B200 kernels')
+    if hparams.get('ae_padding_type', 'same') not in ('same', 'valid'):
+        raise ValueError('"%s" is not a valid padding type' % hparams['ae_padding_type'])
     if any(t != 'conv' for t in hparams['ae_encoding_layer_type']):
         raise NotImplementedError('max-pool encoders are not supported by the B200 kernels')
     if any(t != 'convtranspose' for t in hparams['ae_decoding_layer_type']):
@@ -68,7 +66,29 @@ def make_desc(hparams, role=None):
         d.dec_pt[i], d.dec_pb[i] = [int(v) for v in hparams['ae_decoding_y_padding'][i]]
         d.dec_pl[i], d.dec_pr[i] = [int(v) for v in hparams['ae_decoding_x_padding'][i]]
     d.dec_c0, d.dec_h0, d.dec_w0 = [int(v) for v in hparams['ae_decoding_starting_dim']]
+    if hparams.get('ae_padding_type', 'same') == 'valid':
+        # aes.py:382-405: ConvTranspose2d(padding=(y0, x0), output_padding=target size - full size).  In the
+        # plan's terms (full transposed conv, then crop) the rows / columns that output_padding appends are a
+        # NEGATIVE crop at the bottom / right: they lie outside every tap's reach and receive the bias only.
+        h, w = d.dec_h0, d.dec_w0
+        for i in range(n):
+            if d.dec_pt[i] or d.dec_pl[i]:
+                raise ValueError("decoder layer %d: 'valid' padding comes with zero pads" % i)
+            op_y = d.dec_h[i] - ((h - 1) * d.dec_s[i] + d.dec_k[i])
+            op_x = d.dec_w[i] - ((w - 1) * d.dec_s[i] + d.dec_k[i])
+            if not (0 <= op_y < d.dec_s[i] and 0 <= op_x < d.dec_s[i]):
+                raise ValueError('decoder layer %d: output_padding (%d, %d) outside [0, stride)' % (i, op_y, op_x))
+            d.dec_pb[i], d.dec_pr[i] = -op_y, -op_x
+            h, w = d.dec_h[i], d.dec_w[i]
     return d
+
+
+def output_padding(hparams, i):
+    """(y, x) ``output_padding`` of decoder layer i under 'valid' padding (aes.py:382-403)."""
+    h0, w0 = (hparams['ae_decoding_starting_dim'][1:] if i == 0 else
+              (hparams['ae_decoding_y_dim'][i - 1], hparams['ae_decoding_x_dim'][i - 1]))
+    s, k = hparams['ae_decoding_stride_size'][i], hparams['ae_decoding_kernel_size'][i]
+    return (hparams['ae_decoding_y_dim'][i] - ((h0 - 1) * s + k), hparams['ae_decoding_x_dim'][i] - ((w0 - 1) * s + k))
 
 
 def desc_key(d):

@@ -18,7 +18,7 @@ from torch import nn
 
 from behavenet_b200 import _lib, parallel
 from behavenet_b200.models.base import BaseModule, BaseModel
-from behavenet_b200.models._engine import CaeDriver, Runtime, EncodeFn, DecodeFn
+from behavenet_b200.models._engine import CaeDriver, Runtime, EncodeFn, DecodeFn, output_padding
 
 __all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'ConditionalAE', 'AEMSP', 'load_pretrained_ae']
 
@@ -70,9 +70,15 @@ class ConvAEEncoder(BaseModule):
             else:
                 self.encoder.add_module('zero_pad%i' % i, nn.ZeroPad2d((x0, x1, y0, y1)))
                 padding = 0
-            self.encoder.add_module('conv%i' % i, nn.Conv2d(
-                in_channels=c_in, out_channels=c_out, kernel_size=hp['ae_encoding_kernel_size'][i],
-                stride=hp['ae_encoding_stride_size'][i], padding=padding))
+            def conv(c_in=c_in, c_out=c_out, i=i, padding=padding):
+                return nn.Conv2d(in_channels=c_in, out_channels=c_out, kernel_size=hp['ae_encoding_kernel_size'][i],
+                                 stride=hp['ae_encoding_stride_size'][i], padding=padding)
+            if hp.get('fit_sess_io_layers', False) and i == 0:
+                # one input layer per session, chosen by ``dataset`` (aes.py:69-80)
+                self.encoder.add_module('conv%i_sess_io_layers' % i, nn.ModuleList(
+                    [conv() for _ in range(hp['n_datasets'])]))
+            else:
+                self.encoder.add_module('conv%i' % i, conv())
             self.encoder.add_module('relu%i' % i, nn.LeakyReLU(0.05))
             c_in = c_out
         last_conv_size = c_in * hp['ae_encoding_y_dim'][-1] * hp['ae_encoding_x_dim'][-1]
@@ -80,13 +86,15 @@ class ConvAEEncoder(BaseModule):
         if hp.get('variational', False):
             self.logvar = nn.Linear(last_conv_size, hp['n_ae_latents'])
 
-    def _conv_modules(self):
-        return [m for m in self.encoder if isinstance(m, nn.Conv2d)]
+    def _conv_modules(self, dataset=None):
+        """The conv layers of one pass: ``layer[dataset]`` for a per-session module list (aes.py:207)."""
+        return [m[dataset] if isinstance(m, nn.ModuleList) else m for m in self.encoder
+                if isinstance(m, (nn.Conv2d, nn.ModuleList))]
 
-    def kernel_params(self):
+    def kernel_params(self, dataset=None):
         """Parameters in the order of the C parameter table (encoder side)."""
         ps = []
-        for m in self._conv_modules():
+        for m in self._conv_modules(dataset):
             ps += [m.weight, m.bias]
         ps += [self.FF.weight, self.FF.bias]
         if self.hparams.get('variational', False):
@@ -95,11 +103,11 @@ class ConvAEEncoder(BaseModule):
             ps += [None, None]
         return ps
 
-    def _heads(self, x):
+    def _heads(self, x, dataset=None):
         x = CaeDriver._check_input(x, 'encoder input', self._driver.img, allow_uint8=True)
         if x.requires_grad:
             raise NotImplementedError('gradients with respect to input frames are not computed')
-        ps = self.kernel_params()
+        ps = self.kernel_params(dataset)
         if self.hparams.get('variational', False):
             return EncodeFn.apply(self, torch.is_grad_enabled(), x, *ps)
         return EncodeFn.apply(self, torch.is_grad_enabled(), x, *ps[:-2])
@@ -107,7 +115,7 @@ class ConvAEEncoder(BaseModule):
     def forward(self, x, dataset=None):
         """(z, pool_idx, output_size) -- or (mu, logvar, pool_idx, output_size) if variational
         (reference aes.py:181-218).  The pool lists are empty: there is no max-pooling path."""
-        out = self._heads(x)
+        out = self._heads(x, dataset)
         if self.hparams.get('variational', False):
             return out[0], out[1], [], []
         return out, [], []
@@ -145,35 +153,48 @@ class ConvAEDecoder(BaseModule):
             x0, x1 = hp['ae_decoding_x_padding'][i]
             y0, y1 = hp['ae_decoding_y_padding'][i]
             name = 'convtranspose%i' % i
-            if x0 == x1 and y0 == y1:
+            out_pad = 0
+            if hp.get('ae_padding_type', 'same') == 'valid':
+                padding, out_pad = (y0, x0), output_padding(hp, i)      # aes.py:382-405
+                self.conv_t_pads[name] = None
+            elif x0 == x1 and y0 == y1:
                 padding = (y0, x0)
                 self.conv_t_pads[name] = None
             else:
                 padding = 0
                 self.conv_t_pads[name] = [x0, x1, y0, y1]
-            self.decoder.add_module(name, nn.ConvTranspose2d(
-                in_channels=c_in, out_channels=c_out,
-                kernel_size=(hp['ae_decoding_kernel_size'][i],) * 2,
-                stride=(hp['ae_decoding_stride_size'][i],) * 2, padding=padding, output_padding=0))
+
+            def convt(c_in=c_in, c_out=c_out, i=i, padding=padding, out_pad=out_pad):
+                return nn.ConvTranspose2d(
+                    in_channels=c_in, out_channels=c_out, kernel_size=(hp['ae_decoding_kernel_size'][i],) * 2,
+                    stride=(hp['ae_decoding_stride_size'][i],) * 2, padding=padding, output_padding=out_pad)
+            if hp.get('fit_sess_io_layers', False) and i == n - 1:
+                # one output layer per session (aes.py:298-312)
+                self.decoder.add_module(name + '_sess_io_layers', nn.ModuleList(
+                    [convt() for _ in range(hp['n_datasets'])]))
+                self.conv_t_pads[name + '_sess_io_layers'] = self.conv_t_pads[name]
+            else:
+                self.decoder.add_module(name, convt())
             if i == n - 1:
                 self.decoder.add_module('sigmoid%i' % i, nn.Sigmoid())
             else:
                 self.decoder.add_module('relu%i' % i, nn.LeakyReLU(0.05))
             c_in = c_out
 
-    def _conv_modules(self):
-        return [m for m in self.decoder if isinstance(m, nn.ConvTranspose2d)]
+    def _conv_modules(self, dataset=None):
+        return [m[dataset] if isinstance(m, nn.ModuleList) else m for m in self.decoder
+                if isinstance(m, (nn.ConvTranspose2d, nn.ModuleList))]
 
-    def kernel_params(self):
+    def kernel_params(self, dataset=None):
         ps = [self.FF.weight, self.FF.bias]
-        for m in self._conv_modules():
+        for m in self._conv_modules(dataset):
             ps += [m.weight, m.bias]
         return ps
 
     def forward(self, x, pool_idx=None, target_output_size=None, dataset=None):
         """x_hat of shape (n, C, H, W) (reference aes.py:432-488)."""
         x = CaeDriver._check_input(x, 'decoder input', (self._driver.L,))
-        return DecodeFn.apply(self, torch.is_grad_enabled(), x, *self.kernel_params())
+        return DecodeFn.apply(self, torch.is_grad_enabled(), x, *self.kernel_params(dataset))
 
 
 class AE(BaseModel):
@@ -222,8 +243,10 @@ class AE(BaseModel):
         implicitly by bumping the parameter versions)."""
         self._rt.packed_key = None
 
-    def _kernel_params(self):
-        return self.encoding.kernel_params() + self.decoding.kernel_params()
+    def _kernel_params(self, dataset=None):
+        """The C parameter table of one pass; ``dataset`` picks the session's input / output layers when the
+        model has them (``fit_sess_io_layers``)."""
+        return self.encoding.kernel_params(dataset) + self.decoding.kernel_params(dataset)
 
     def _extra_trainable(self):
         """Trainable parameters that are not in the C parameter table (PS-VAE label head)."""
@@ -246,7 +269,7 @@ class AE(BaseModel):
             self._rt.bufs['flat_grad_ptrs'] = [p.grad.data_ptr() for p in missing]
             # the decoder's parameters form one contiguous bucket of the flat buffer (they are final after
             # bn_cae_decode_bwd, before the encoder's backward pass starts)
-            dec = {id(p) for p in self.decoding.kernel_params() if p is not None}
+            dec = {id(p) for p in self.decoding.parameters()}
             o, lo, hi, cnt = 0, None, None, 0
             for p in missing:
                 if id(p) in dec:
@@ -336,7 +359,7 @@ class AE(BaseModel):
             local = False
         n_chunks = int(np.ceil(n_total / chunk_size))
         n = end - beg
-        params = self._kernel_params()
+        params = self._kernel_params(dataset)
         device = x.device
         sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
         pending = None

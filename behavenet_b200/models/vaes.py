@@ -144,7 +144,7 @@ class ConvAEPSEncoder(ConvAEEncoder):
     def forward(self, x, dataset=None):
         """(y, w, logvar, pool_idx, output_size) (reference vaes.py:1319-1363): ``logvar`` comes
         from the flattened conv features, y / w are the A / B projections of the FF output."""
-        pre, logvar = self._heads(x)
+        pre, logvar = self._heads(x, dataset)
         n_labels = self.hparams['n_labels']
         mu, _, _ = _LatentFn.apply(pre, logvar, self.A.weight, self.B.weight, self.D.weight,
                                    self.D.bias, None)
@@ -190,7 +190,7 @@ class VAE(AE):
             self._rt.bufs['eye'] = buf
         return buf
 
-    def _elbo_pass(self, data, accumulate_grad, chunk_size, eps):
+    def _elbo_pass(self, data, accumulate_grad, chunk_size, eps, dataset=None):
         """Shared fused pass of the VAE family: per reference chunk the pixel sum of squares and the
         latent terms [unused, analytic KL, MI, TC, DWKL] (sums over the chunk's frames), gradients
         accumulated into ``.grad``.  Returns (host array (n_chunks, 6), chunks)."""
@@ -212,7 +212,7 @@ class VAE(AE):
         dp = self.data_parallel and parallel.enabled()
         beg, end = parallel.shard_range(n_total) if dp else (0, n_total)      # contiguous frames per rank
         n = end - beg
-        params = self._kernel_params()
+        params = self._kernel_params(dataset)
         sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
         terms = torch.zeros(n_chunks, 5, dtype=torch.float64, device=device)
         lib = _lib.lib()
@@ -274,7 +274,7 @@ class VAE(AE):
 
     def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200, eps=None):
         """ELBO loss with the reference's chunk semantics (vaes.py:131-208); same dict of floats."""
-        host, chunks = self._elbo_pass(data, accumulate_grad, chunk_size, eps)
+        host, chunks = self._elbo_pass(data, accumulate_grad, chunk_size, eps, dataset)
         beta = self.beta_vals[self.curr_epoch]
         n_pix = float(np.prod(self._driver.img))
         n_total = chunks[-1][1]
@@ -367,7 +367,7 @@ class BetaTCVAE(VAE):
         return 0, 0.0, float(self.beta_vals[self.curr_epoch]), float(self.kl_anneal_vals[self.curr_epoch]), 0.0
 
     def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200, eps=None):
-        host, chunks = self._elbo_pass(data, accumulate_grad, chunk_size, eps)
+        host, chunks = self._elbo_pass(data, accumulate_grad, chunk_size, eps, dataset)
         beta = self.beta_vals[self.curr_epoch]
         kl = self.kl_anneal_vals[self.curr_epoch]
         n_pix = float(np.prod(self._driver.img))
@@ -480,7 +480,7 @@ class PSVAE(AE):
         # (FF output, logvar, eps) rows (reference losses.py:321-341)
         beg, end = parallel.shard_range(n_total) if dp else (0, n_total)
         n = end - beg
-        params = self._kernel_params()
+        params = self._kernel_params(dataset)
         # per chunk: [sse_pixels] ; [label sumsq, zs_kl, mi, tc, dwkl]
         sse = torch.zeros(n_chunks, dtype=torch.float64, device=device)
         terms = torch.zeros(n_chunks, 5, dtype=torch.float64, device=device)
@@ -673,7 +673,7 @@ class ConvAEMSPSEncoder(ConvAEEncoder):
     def forward(self, x, dataset=None):
         """(z_s, z_b, z, logvar, pool_idx, output_size); the conv stack and both heads run in the kernels,
         the three small projections are torch ops on (n, latents) tensors."""
-        pre, logvar = self._heads(x)
+        pre, logvar = self._heads(x, dataset)
         return self.A(pre), self.C(pre), self.B(pre), logvar, [], []
 
 

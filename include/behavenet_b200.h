@@ -49,7 +49,10 @@ int bn_get_tensor_core_mode(void);
  * Encoder layer i: Conv2d(k, stride s) with explicit zero padding (top,bottom,left,right) and
  * LeakyReLU(0.05) (aes.py:71-114, 127-163).  Decoder layer i: ConvTranspose2d(k, s), output
  * cropped by (top,bottom,left,right), LeakyReLU(0.05) except Sigmoid after the last (aes.py:283-341,
- * 361-430, 467-470). */
+ * 361-430, 467-470).  A NEGATIVE bottom / right crop (> -s) is the `output_padding` of the reference's
+ * 'valid' padding mode (aes.py:382-405): the appended rows / columns lie outside the reach of every tap
+ * and hold the bias only.  With per-session input / output layers (`fit_sess_io_layers`, aes.py:69-80,
+ * 298-312) the caller puts the chosen session's tensors into the parameter table. */
 typedef struct bn_cae_desc {
   int32_t n_layers;              /* conv layers per side, 1..BN_MAX_LAYERS */
   int32_t in_c, in_h, in_w;      /* hparams['ae_input_dim'] */

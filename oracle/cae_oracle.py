@@ -171,66 +171,86 @@ def _conv(x, w, b, s, layer, n_layers, transposed):
     return _EmuConv.apply(x, w, b, s, False, True, True, layer > 0)
 
 
-def encoder_features(sd, hparams, x, prefix='encoding.'):
+def _io_name(hparams, stem, i, n, dataset, first):
+    """Parameter-name stem of conv layer i: the first encoder layer / last decoder layer are per-session
+    module lists when ``fit_sess_io_layers`` is set (aes.py:69-80, 298-312) -- not the decoder's when it
+    ends in a feed-forward layer."""
+    io = hparams.get('fit_sess_io_layers', False) and (i == 0 if first else (
+        i == n - 1 and not hparams.get('ae_decoding_last_FF_layer', False)))
+    return '%s%i_sess_io_layers.%i' % (stem, i, dataset) if io else '%s%i' % (stem, i)
+
+
+def encoder_features(sd, hparams, x, prefix='encoding.', dataset=None):
     """Conv stack of ConvAEEncoder.forward (aes.py:181-214); returns flattened (N, C*H*W)."""
-    for i in range(n_conv_layers(hparams)):
+    n = n_conv_layers(hparams)
+    for i in range(n):
         x0, x1 = hparams['ae_encoding_x_padding'][i]
         y0, y1 = hparams['ae_encoding_y_padding'][i]
         s = hparams['ae_encoding_stride_size'][i]
         # symmetric: Conv2d(padding=(y0,x0)); asymmetric: ZeroPad2d((x0,x1,y0,y1)) + padding 0
         # (aes.py:141-155) -- numerically the same explicit zero pad
         x = F.pad(x, (x0, x1, y0, y1))
-        x = _conv(x, sd[prefix + 'encoder.conv%i.weight' % i], sd[prefix + 'encoder.conv%i.bias' % i], s, i,
-                  n_conv_layers(hparams), False)
+        name = prefix + 'encoder.' + _io_name(hparams, 'conv', i, n, dataset, True)
+        x = _conv(x, sd[name + '.weight'], sd[name + '.bias'], s, i, n, False)
         x = F.leaky_relu(x, LEAK)
     return x.reshape(x.shape[0], -1)
 
 
-def encode(sd, hparams, x, prefix='encoding.'):
+def encode(sd, hparams, x, prefix='encoding.', dataset=None):
     """ConvAEEncoder.forward -> z   (or (mu, logvar) if hparams['variational'])."""
-    h = encoder_features(sd, hparams, x, prefix)
+    h = encoder_features(sd, hparams, x, prefix, dataset)
     z = F.linear(h, sd[prefix + 'FF.weight'], sd[prefix + 'FF.bias'])
     if hparams.get('variational', False):
         return z, F.linear(h, sd[prefix + 'logvar.weight'], sd[prefix + 'logvar.bias'])
     return z
 
 
-def decode(sd, hparams, z, prefix='decoding.'):
+def decode(sd, hparams, z, prefix='decoding.', dataset=None):
     """ConvAEDecoder.forward (aes.py:432-488)."""
     c0, h0, w0 = hparams['ae_decoding_starting_dim']
     x = F.linear(z, sd[prefix + 'FF.weight'], sd[prefix + 'FF.bias']).view(-1, c0, h0, w0)
     n = len(hparams['ae_decoding_n_channels'])
+    valid = hparams.get('ae_padding_type', 'same') == 'valid'
     for i in range(n):
         x0, x1 = hparams['ae_decoding_x_padding'][i]
         y0, y1 = hparams['ae_decoding_y_padding'][i]
         s = hparams['ae_decoding_stride_size'][i]
-        # symmetric pads go in as ConvTranspose2d(padding=...), asymmetric as a crop afterwards
-        # (aes.py:404-418, 467-470): both are "full transposed conv, then crop"
-        x = _conv(x, sd[prefix + 'decoder.convtranspose%i.weight' % i],
-                  sd[prefix + 'decoder.convtranspose%i.bias' % i], s, i, n, True)
-        x = x[:, :, y0:x.shape[2] - y1, x0:x.shape[3] - x1]
+        name = prefix + 'decoder.' + _io_name(hparams, 'convtranspose', i, n, dataset, False)
+        if valid:
+            # 'valid' (aes.py:382-405): ConvTranspose2d(padding=(y0, x0), output_padding=target - full size);
+            # the rows / columns that output_padding appends receive no input, only the bias
+            x = _conv(x, sd[name + '.weight'], torch.zeros_like(sd[name + '.bias']), s, i, n, True)
+            x = x[:, :, y0:x.shape[2] - y0, x0:x.shape[3] - x0]
+            opy = hparams['ae_decoding_y_dim'][i] - x.shape[2]
+            opx = hparams['ae_decoding_x_dim'][i] - x.shape[3]
+            x = F.pad(x, (0, opx, 0, opy)) + sd[name + '.bias'].view(1, -1, 1, 1)
+        else:
+            # symmetric pads go in as ConvTranspose2d(padding=...), asymmetric as a crop afterwards
+            # (aes.py:404-418, 467-470): both are "full transposed conv, then crop"
+            x = _conv(x, sd[name + '.weight'], sd[name + '.bias'], s, i, n, True)
+            x = x[:, :, y0:x.shape[2] - y1, x0:x.shape[3] - x1]
         x = torch.sigmoid(x) if i == n - 1 else F.leaky_relu(x, LEAK)
     return x
 
 
-def ae_forward(sd, hparams, x):
+def ae_forward(sd, hparams, x, dataset=None):
     """AE.forward (aes.py:695-720) -> (x_hat, z)."""
-    z = encode(sd, hparams, x)
-    return decode(sd, hparams, z), z
+    z = encode(sd, hparams, x, dataset=dataset)
+    return decode(sd, hparams, z, dataset=dataset), z
 
 
 def _chunks(n, chunk_size):
     return [(b, min(b + chunk_size, n)) for b in range(0, n, chunk_size)]
 
 
-def ae_loss(sd, hparams, x, masks=None, chunk_size=200, want_grads=True):
+def ae_loss(sd, hparams, x, masks=None, chunk_size=200, want_grads=True, dataset=None):
     """AE.loss (aes.py:722-773): returns ({'loss': float}, {name: grad}) with the reference's
     chunk semantics (each chunk back-propagates its own mean)."""
     params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
     total = 0.0
     for b, e in _chunks(x.shape[0], chunk_size):
         x_in = x[b:e]
-        x_hat, _ = ae_forward(params, hparams, x_in)
+        x_hat, _ = ae_forward(params, hparams, x_in, dataset)
         loss = mse(x_in, x_hat, None if masks is None else masks[b:e])
         if want_grads:
             loss.backward()
@@ -541,11 +561,15 @@ def btcvae_loss(sd, hparams, x, eps, masks=None, beta=None, kl_anneal=1.0, chunk
 # ------------------------------------------------------------------------------------------------
 
 def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class='ae',
-                 n_labels=0, arch=None, conditional_encoder=False):
-    """hparams dict as the reference's grid-search mains assemble it (ae_grid_search.py:20-30)."""
+                 n_labels=0, arch=None, conditional_encoder=False, padding_type=None, n_datasets=0):
+    """hparams dict as the reference's grid-search mains assemble it (ae_grid_search.py:20-30).
+    ``padding_type='valid'`` selects the unpadded variant of the default arch; ``n_datasets > 0`` the
+    per-session input / output layers (``fit_sess_io_layers``)."""
     from behavenet_b200.models.ae_model_architecture_generator import (
         load_default_arch, get_handcrafted_dims)
     hp = load_default_arch() if arch is None else dict(arch)
+    if padding_type is not None:
+        hp['ae_padding_type'] = padding_type
     hp['ae_batch_norm'] = False
     hp['ae_input_dim'] = [n_input_channels, y_pixels, x_pixels]
     hp['n_input_channels'], hp['y_pixels'], hp['x_pixels'] = n_input_channels, y_pixels, x_pixels
@@ -553,7 +577,9 @@ def make_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents, model_class
     hp = get_handcrafted_dims(hp, symmetric=True)
     hp['model_class'] = model_class
     hp['model_type'] = 'conv'
-    hp['fit_sess_io_layers'] = False
+    hp['fit_sess_io_layers'] = n_datasets > 0
+    if n_datasets > 0:
+        hp['n_datasets'] = n_datasets
     if model_class == 'vae':
         hp.update({'vae.beta': 2.0, 'vae.beta_anneal_epochs': 0, 'max_n_epochs': 10, 'variational': True})
     if model_class == 'beta-tcvae':
@@ -595,9 +621,14 @@ def init_state_dict(hparams, seed=0, dtype=torch.float32):
     cond = hparams.get('model_class') in ('cond-ae', 'cond-vae')
     if hparams.get('model_class') == 'cond-ae' and hparams.get('conditional_encoder', False):
         c_in += hparams['n_labels'] // 2                 # one-hot label images join the frames (aes.py:129-137)
+    sess_io = hparams.get('fit_sess_io_layers', False)
     for i, c in enumerate(hparams['ae_encoding_n_channels']):
         k = hparams['ae_encoding_kernel_size'][i]
-        put('encoding.encoder.conv%i' % i, (c, c_in, k, k), c_in * k * k, c)
+        if sess_io and i == 0:      # one input layer per session (aes.py:69-80)
+            for d in range(hparams['n_datasets']):
+                put('encoding.encoder.conv0_sess_io_layers.%i' % d, (c, c_in, k, k), c_in * k * k, c)
+        else:
+            put('encoding.encoder.conv%i' % i, (c, c_in, k, k), c_in * k * k, c)
         c_in = c
     feat = c_in * hparams['ae_encoding_y_dim'][-1] * hparams['ae_encoding_x_dim'][-1]
     L = hparams['n_ae_latents']
@@ -631,6 +662,10 @@ def init_state_dict(hparams, seed=0, dtype=torch.float32):
     for i, c in enumerate(hparams['ae_decoding_n_channels']):
         k = hparams['ae_decoding_kernel_size'][i]
         # torch computes ConvTranspose2d fan_in from weight.size(1) = out channels
-        put('decoding.decoder.convtranspose%i' % i, (c_in, c, k, k), c * k * k, c)
+        if sess_io and i == len(hparams['ae_decoding_n_channels']) - 1:     # aes.py:298-312
+            for d in range(hparams['n_datasets']):
+                put('decoding.decoder.convtranspose%i_sess_io_layers.%i' % (i, d), (c_in, c, k, k), c * k * k, c)
+        else:
+            put('decoding.decoder.convtranspose%i' % i, (c_in, c, k, k), c * k * k, c)
         c_in = c
     return sd

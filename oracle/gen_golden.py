@@ -47,6 +47,12 @@ CAE_CASES = [
     ('aemsp_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-ae-msp', 3, 4),
     ('condvae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'cond-vae', 4, 4),
     ('mspsvae_32x32x2_l8_b24', 2, 32, 32, 8, 24, 'msps-vae', 3, 0),   # 2 sessions x 12 frames, triplet term
+    # architecture variants of the same classes (aes.py:69-80, 298-312, 382-405): 'valid' padding (transposed convs
+    # with output_padding) and per-session input / output layers (forward / loss with dataset = 1)
+    ('ae_valid_128x128x1_l12_b3', 1, 128, 128, 12, 3, 'ae+valid', 0, 2),
+    ('ae_valid_160x130x2_l6_b5', 2, 160, 130, 6, 5, 'ae+valid', 0, 2),
+    ('ae_io3_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'ae+io3', 0, 4),
+    ('ae_valid_io2_160x130x2_l6_b5', 2, 160, 130, 6, 5, 'ae+valid+io2', 0, 200),
 ]
 
 
@@ -254,6 +260,20 @@ def run_reference_cond(case):
     return res
 
 
+def variant_options(mc):
+    """'ae+valid+io3' -> ('ae', {'padding_type': 'valid', 'n_datasets': 3}): the make_hparams keywords of a case."""
+    mc, *flags = mc.split('+')
+    opts = {}
+    for f in flags:
+        if f == 'valid':
+            opts['padding_type'] = 'valid'
+        elif f.startswith('io'):
+            opts['n_datasets'] = int(f[2:])
+        else:
+            raise ValueError(f)
+    return mc, opts
+
+
 def run_reference(case):
     from behavenet.models import AE, PSVAE
     import behavenet.models.vaes as vaes
@@ -262,33 +282,37 @@ def run_reference(case):
         return run_reference_cond(case)
     if mc == 'msps-vae':
         return run_reference_msps(case)
-    hp = co.make_hparams(c, h, w, L, mc, nl)
+    mc, opts = variant_options(mc)
+    hp = co.make_hparams(c, h, w, L, mc, nl, **opts)
     sd = co.init_state_dict(hp, seed=0)
     inp = synth_inputs(case)
     res = {}
     hp_ref = dict(hp)
     if mc == 'ae':
+        ds = 1 if opts.get('n_datasets', 0) else None       # which session's input / output layers
         model = AE(hp_ref)
         model.load_state_dict(sd)
         model.eval()
         with torch.no_grad():
-            x_hat, z = model(inp['x'])
+            x_hat, z = model(inp['x'], dataset=ds)
         res['x_hat'], res['z'] = x_hat, z
         for tag, m in (('', None), ('_masked', inp['masks'])):
             model.zero_grad()
             data = {'images': inp['x'][None]}
             if m is not None:
                 data['masks'] = m[None]
-            loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+            loss = model.loss(data, dataset=ds or 0, accumulate_grad=True, chunk_size=chunk)
             res['loss' + tag] = torch.tensor(loss['loss'], dtype=torch.float64)
             for k, p in model.named_parameters():
-                res['grad%s.%s' % (tag, k)] = p.grad.clone()
+                if p.grad is not None:                      # the other sessions' io layers stay without gradient
+                    res['grad%s.%s' % (tag, k)] = p.grad.clone()
         # pin the restatement
-        xo, zo = co.ae_forward(sd, hp, inp['x'])
+        xo, zo = co.ae_forward(sd, hp, inp['x'], ds)
         assert torch.allclose(xo, x_hat, atol=1e-6), name
         assert torch.allclose(zo, z, atol=1e-5), name
-        lo, go = co.ae_loss(sd, hp, inp['x'], None, chunk)
+        lo, go = co.ae_loss(sd, hp, inp['x'], None, chunk, dataset=ds)
         assert abs(lo['loss'] - float(res['loss'])) < 1e-7, name
+        assert set(go) == {k[5:] for k in res if k.startswith('grad.')}, name
         for k, gref in go.items():
             assert torch.allclose(gref, res['grad.' + k], atol=1e-6, rtol=1e-4), (name, k)
     elif mc in ('vae', 'beta-tcvae'):

@@ -81,13 +81,40 @@ def test_vae_family_protocol():
         VAE(hp)
 
 
-@pytest.mark.parametrize('key,val', [('ae_batch_norm', True), ('fit_sess_io_layers', True),
-                                     ('ae_decoding_last_FF_layer', True), ('ae_padding_type', 'valid')])
+@pytest.mark.parametrize('key,val', [('ae_batch_norm', True), ('ae_decoding_last_FF_layer', True)])
 def test_unsupported_variants_raise_instead_of_falling_back(key, val):
     from behavenet_b200.models import AE
     hp = co.make_hparams(1, 32, 32, 8)
     hp[key] = val
     with pytest.raises(NotImplementedError):
+        AE(hp)
+
+
+def test_valid_padding_and_session_layers_mirror_the_reference_containers():
+    """'valid' padding: zero pads, ``output_padding`` per transposed conv as aes.py:382-405 computes it, and the
+    plan descriptor's negative bottom / right crop; ``fit_sess_io_layers``: module lists named like the
+    reference's (aes.py:69-80, 298-312), whose entries fill the parameter table by ``dataset``."""
+    from behavenet_b200.models import AE
+    hp = co.make_hparams(2, 160, 130, 6, padding_type='valid', n_datasets=2)
+    assert hp['ae_encoding_y_dim'] == [78, 37, 17, 7, 1] and hp['ae_encoding_x_dim'] == [63, 30, 13, 5, 1]
+    m = AE(hp)
+    assert set(m.state_dict()) == set(co.init_state_dict(hp))
+    convs = [l for l in m.decoding.decoder if isinstance(l, torch.nn.ConvTranspose2d)]
+    assert [c.output_padding for c in convs] == [(2, 0), (0, 0), (0, 1), (1, 0)]
+    io, io_in = list(m.decoding.decoder)[-2], list(m.encoding.encoder)[0]
+    assert isinstance(io, torch.nn.ModuleList) and len(io) == 2 and io[0].output_padding == (1, 1)
+    d = m._driver.desc
+    assert list(d.dec_pb)[:5] == [-2, 0, 0, -1, -1] and list(d.dec_pr)[:5] == [0, 0, -1, 0, -1]
+    assert list(d.dec_pt)[:5] == [0] * 5 and list(d.enc_pb)[:5] == [0] * 5
+    p0, p1 = m._kernel_params(0), m._kernel_params(1)
+    assert p0[0] is io_in[0].weight and p1[0] is io_in[1].weight
+    assert p0[-2] is io[0].weight and p1[-1] is io[1].bias
+    assert all(a is b for a, b in zip(p0[2:-2], p1[2:-2]))
+    with pytest.raises(TypeError):
+        m._kernel_params(None)
+    hp = co.make_hparams(1, 32, 32, 8)
+    hp['ae_padding_type'] = 'circular'
+    with pytest.raises(ValueError):
         AE(hp)
 
 

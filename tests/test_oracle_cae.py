@@ -57,6 +57,37 @@ def test_oracle_reproduces_reference_goldens(case):
             golden_compare(gold, key, g, rtol=1e-3, atol=1e-4 * scale + 1e-9)
 
 
+VARIANT_CASES = {     # name: (C, H, W, latents, batch, make_hparams keywords, chunk, dataset)
+    'ae_valid_128x128x1_l12_b3': (1, 128, 128, 12, 3, dict(padding_type='valid'), 2, None),
+    'ae_valid_160x130x2_l6_b5': (2, 160, 130, 6, 5, dict(padding_type='valid'), 2, None),
+    'ae_io3_64x48x1_l6_b7': (1, 64, 48, 6, 7, dict(n_datasets=3), 4, 1),
+    'ae_valid_io2_160x130x2_l6_b5': (2, 160, 130, 6, 5, dict(padding_type='valid', n_datasets=2), 200, 1),
+}
+
+
+@pytest.mark.parametrize('case', list(VARIANT_CASES))
+def test_oracle_reproduces_reference_goldens_of_arch_variants(case):
+    """'valid' padding (aes.py:382-405) and per-session input / output layers (aes.py:69-80, 298-312)."""
+    c, h, w, L, b, kw, chunk, ds = VARIANT_CASES[case]
+    gold = load_golden(case)
+    hp = co.make_hparams(c, h, w, L, 'ae', 0, **kw)
+    sd = co.init_state_dict(hp, seed=0)
+    inp = synth_inputs(c, h, w, L, b, 0)
+    torch.set_num_threads(8)
+    x_hat, z = co.ae_forward(sd, hp, inp['x'], ds)
+    golden_compare(gold, 'x_hat', x_hat, rtol=1e-5, atol=1e-6)
+    golden_compare(gold, 'z', z, rtol=1e-4, atol=1e-5)
+    for tag, m in (('', None), ('_masked', inp['masks'])):
+        loss, grads = co.ae_loss(sd, hp, inp['x'], m, chunk, dataset=ds)
+        assert abs(loss['loss'] - float(gold['loss' + tag])) < 1e-7
+        stored = {k.split('#')[0] for k in gold if k.startswith('grad%s.' % tag)}
+        assert stored == {'grad%s.%s' % (tag, k) for k in grads}      # only the chosen session's io layers
+        for k, g in grads.items():
+            key = 'grad%s.%s' % (tag, k)
+            scale = float(np.abs(gold[key + '#val'] if key + '#val' in gold else gold[key]).max())
+            golden_compare(gold, key, g, rtol=1e-4, atol=1e-5 * scale + 1e-9)
+
+
 VAE_CASES = {
     'vae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 'vae', 4),
     'btcvae_32x32x2_l8_b6': (2, 32, 32, 8, 6, 'beta-tcvae', 4),

@@ -80,25 +80,52 @@ class ArraySource:
 
 class HDF5Source:
     """One session's ``data.hdf5`` in the reference layout: group ``<signal>/trial_%04i`` per trial
-    (data_generator.py:253-303).  The file is opened once per worker thread, not once per trial."""
+    (data_generator.py:253-303).  The file is opened once per worker thread, not once per trial.
 
-    def __init__(self, path, signals, lab='', expt='', animal='', session=''):
-        try:
-            import h5py
-        except ImportError as e:
-            raise ImportError('HDF5Source needs h5py, which is not installed here') from e
-        self._h5py = h5py
+    Read through ``h5py`` when it is installed (like the reference) and through the dependency-free reader
+    ``behavenet_b200.data.hdf5_lite`` otherwise (``backend='lite'`` forces the latter); both expose the same
+    calls."""
+
+    def __init__(self, path, signals, lab='', expt='', animal='', session='', backend=None):
+        if backend not in (None, 'h5py', 'lite'):
+            raise ValueError('backend must be None, "h5py" or "lite"')
+        h5 = None
+        if backend != 'lite':
+            try:
+                import h5py as h5
+            except ImportError:
+                if backend == 'h5py':
+                    raise
+        if h5 is None:
+            from behavenet_b200.data import hdf5_lite as h5
+        self._h5 = h5
+        self.backend = 'lite' if h5.__name__.endswith('hdf5_lite') else 'h5py'
         self.path = path
         self.signals = list(signals)
         self.lab, self.expt, self.animal, self.session = lab, expt, animal, session
         self._local = threading.local()
-        with h5py.File(path, 'r', libver='latest', swmr=True) as f:
+        with h5.File(path, 'r', libver='latest', swmr=True) as f:
+            for s in self.signals:
+                if s not in f:
+                    raise KeyError('%s has no group "%s"' % (path, s))
             self.n_trials = len(f[self.signals[0]])
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop('_local')
+        st['_h5'] = self._h5.__name__
+        return st
+
+    def __setstate__(self, st):
+        import importlib
+        self.__dict__.update(st)
+        self._h5 = importlib.import_module(st['_h5'])
+        self._local = threading.local()
 
     def _file(self):
         f = getattr(self._local, 'f', None)
         if f is None:
-            f = self._local.f = self._h5py.File(self.path, 'r', libver='latest', swmr=True)
+            f = self._local.f = self._h5.File(self.path, 'r', libver='latest', swmr=True)
         return f
 
     def trial_length(self, idx):

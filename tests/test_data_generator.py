@@ -105,17 +105,21 @@ def test_worker_errors_surface_in_next_batch():
     gen.close()
 
 
-def test_hdf5_source_needs_h5py():
-    """The HDF5 reader follows the reference file layout but h5py is not part of this image: it must say so
-    instead of failing later (when h5py is present this test is skipped)."""
-    from behavenet_b200.data import HDF5Source
+def test_hdf5_source_backend_selection(tmp_path):
+    """h5py when it is installed (like the reference), the dependency-free reader otherwise; asking for h5py
+    explicitly where it is absent fails at construction, not at the first trial."""
+    from behavenet_b200.data import HDF5Source, hdf5_lite
+    path = str(tmp_path / 'data.hdf5')
+    hdf5_lite.write(path, {'images': {'trial_0000': np.zeros((3, 1, 4, 4), np.uint8)}})
     try:
         import h5py  # noqa: F401
     except ImportError:
-        with pytest.raises(ImportError, match='h5py'):
-            HDF5Source('/nonexistent/data.hdf5', ['images'])
+        assert HDF5Source(path, ['images']).backend == 'lite'
+        with pytest.raises(ImportError):
+            HDF5Source(path, ['images'], backend='h5py')
     else:
-        pytest.skip('h5py available')
+        assert HDF5Source(path, ['images']).backend == 'h5py'       # (reads a file hdf5_lite wrote)
+        assert HDF5Source(path, ['images'], backend='lite').n_trials == 1
 
 
 @pytest.mark.gpu

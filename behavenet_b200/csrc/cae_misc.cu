@@ -183,15 +183,41 @@ __global__ void __launch_bounds__(256) colsum_thin_kernel(const float* __restric
                                                           float* __restrict__ out) {
   bn_pdl_trigger();
   bn_pdl_wait();
-  // C <= 4: flat grid-stride walk, per-thread accumulators per column
+  // C <= 4: flat grid-stride walk, per-thread accumulators per column.  C in {1, 2, 4} with a 16-byte aligned
+  // image: float4 loads, element j of a vector always belongs to column j % C (no per-element 64-bit modulo,
+  // which cost ~50 instructions per load in the scalar loop: 16 us for 17 MB)
   __shared__ float red[8][4];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    float v = __ldg(x + i);
-    int c = (int)(i % C);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((C == 1 || C == 2 || C == 4) && (total & 3) == 0 && ((uintptr_t)x & 15) == 0) {
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+    const long long n4 = total >> 2;
+    long long i = first;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride),
+                   d = __ldg(x4 + i + 3 * stride);
+      acc[0] += (a.x + b.x) + (c.x + d.x);
+      acc[1] += (a.y + b.y) + (c.y + d.y);
+      acc[2] += (a.z + b.z) + (c.z + d.z);
+      acc[3] += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; i < n4; i += stride) {
+      const float4 a = __ldg(x4 + i);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    }
+    if (C == 1) { acc[0] = (acc[0] + acc[1]) + (acc[2] + acc[3]); acc[1] = acc[2] = acc[3] = 0.f; }
+    if (C == 2) { acc[0] += acc[2]; acc[1] += acc[3]; acc[2] = acc[3] = 0.f; }
+  } else {
+    int c = (int)(first % C);
+    const int cstep = (int)(stride % C);
+    for (long long i = first; i < total; i += stride) {
+      const float v = __ldg(x + i);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] += (q == c) ? v : 0.f;
+      for (int q = 0; q < 4; ++q) acc[q] += (q == c) ? v : 0.f;
+      c += cstep;
+      if (c >= C) c -= C;
+    }
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);

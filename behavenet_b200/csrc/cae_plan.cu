@@ -463,11 +463,18 @@ extern "C" int bn_cae_decode_bwd(bn_cae_plan* p, int n, const float* d_dxhat, co
   return 0;
 }
 
-extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const float* d_dmu,
-                                 const float* d_dlogvar, const float* const* P, const void* d_packed,
-                                 void* d_ws, float* const* G, void* stream) {
+namespace {
+// phase 0: the whole pass.  Phases 1 + 2 are the same launches in two calls, split where the gradients of the
+// heads and of the top conv layer are final (heads backward, top layer weight gradient + bias sums, their batched
+// reduction), so that a data-parallel caller can start the all-reduce of that bucket -- three quarters of the
+// encoder's parameters in the default architecture -- underneath phase 2 (backward-data of the top layer, then
+// every layer below).  The upstream-gradient image of the top layer stays in the workspace between the calls.
+int encode_bwd_impl(bn_cae_plan* p, int n, const float* d_x, const float* d_dmu, const float* d_dlogvar,
+                    const float* const* P, const void* d_packed, void* d_ws, float* const* G, void* stream,
+                    int phase) {
   if (!p || !d_x || !P || !d_packed || !d_ws || !G) BN_FAIL("bn_cae_encode_bwd: null argument");
   if (!d_dmu && !d_dlogvar) BN_FAIL("bn_cae_encode_bwd: no upstream gradient");
+  if (phase < 0 || phase > 2) BN_FAIL("bn_cae_encode_bwd: phase %d", phase);
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const float* pk = (const float*)d_packed;
@@ -480,18 +487,22 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
   int flip = 0;
   float* gcur = pp[flip];
   flip ^= 1;
-  BN_TRY(bn_launch_heads_bwd(ws + L.enc_act[p->nl], pk + p->off_heads, d_dmu, d_dlogvar, n, p->d.n_latents,
-                             p->feat_c, p->feat_h, p->feat_w, gcur, G[n2], G[n2 + 1],
-                             p->d.n_heads == 2 ? G[n2 + 2] : nullptr, p->d.n_heads == 2 ? G[n2 + 3] : nullptr, st));
+  if (phase != 2)
+    BN_TRY(bn_launch_heads_bwd(ws + L.enc_act[p->nl], pk + p->off_heads, d_dmu, d_dlogvar, n, p->d.n_latents,
+                               p->feat_c, p->feat_h, p->feat_w, gcur, G[n2], G[n2 + 1],
+                               p->d.n_heads == 2 ? G[n2 + 2] : nullptr, p->d.n_heads == 2 ? G[n2 + 3] : nullptr, st));
   int bias_done = 0;   // the kernel that produced gcur already accumulated its column sums
   bn_wgrad_reduce_defer_begin();
   const int rc = [&]() -> int {
   for (int i = p->nl - 1; i >= 0; --i) {
     const ConvGeom& g = p->enc[i];
     ImgView big = i == 0 ? input_view(p, d_x) : nhwc_view(ws + L.enc_act[i], g.Hb, g.Wb, g.Cb);
-    BN_TRY(run_wgrad(big, gcur, g, n, ws + L.wg_enc[i], L.wg_floats_enc[i], G[g.p_w], st));
-    if (!bias_done) BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hs * g.Ws, g.Cs, G[g.p_b], st));
+    if (!(phase == 2 && i == p->nl - 1)) {
+      BN_TRY(run_wgrad(big, gcur, g, n, ws + L.wg_enc[i], L.wg_floats_enc[i], G[g.p_w], st));
+      if (!bias_done) BN_TRY(bn_launch_colsum(gcur, (long long)n * g.Hs * g.Ws, g.Cs, G[g.p_b], st));
+    }
     bias_done = 0;
+    if (phase == 1) return 0;
     if (i > 0) {
       float* out = pp[flip];
       flip ^= 1;
@@ -506,6 +517,19 @@ extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const 
   }();
   const int rf = bn_wgrad_reduce_flush(st);
   return rc ? rc : rf;
+}
+}  // namespace
+
+extern "C" int bn_cae_encode_bwd(bn_cae_plan* p, int n, const float* d_x, const float* d_dmu,
+                                 const float* d_dlogvar, const float* const* P, const void* d_packed,
+                                 void* d_ws, float* const* G, void* stream) {
+  return encode_bwd_impl(p, n, d_x, d_dmu, d_dlogvar, P, d_packed, d_ws, G, stream, 0);
+}
+
+extern "C" int bn_cae_encode_bwd_phase(bn_cae_plan* p, int n, const float* d_x, const float* d_dmu,
+                                       const float* d_dlogvar, const float* const* P, const void* d_packed,
+                                       void* d_ws, float* const* G, void* stream, int phase) {
+  return encode_bwd_impl(p, n, d_x, d_dmu, d_dlogvar, P, d_packed, d_ws, G, stream, phase);
 }
 
 // Single-layer entry point: kernel-level parity tests (tensor-core vs CUDA-core kernels on the same

@@ -233,11 +233,13 @@ class CaeDriver:
             ws.data_ptr(), self.table(grads), _lib.ptr(dz), _lib.stream_ptr()), 'bn_cae_decode_bwd')
         return dz
 
-    def encode_bwd(self, x, dmu, dlogvar, params, packed, ws, grads):
-        _lib.check(_lib.lib().bn_cae_encode_bwd(
+    def encode_bwd(self, x, dmu, dlogvar, params, packed, ws, grads, phase=0):
+        """phase 0: the whole pass; 1: heads + top conv layer (their gradients are final afterwards); 2: the
+        layers below -- the split lets a data-parallel caller all-reduce the top bucket under phase 2."""
+        _lib.check(_lib.lib().bn_cae_encode_bwd_phase(
             self.plan(x.device), x.shape[0], x.data_ptr(), _lib.ptr(dmu), _lib.ptr(dlogvar),
             self.table(params), packed.data_ptr(), ws.data_ptr(), self.table(grads),
-            _lib.stream_ptr()), 'bn_cae_encode_bwd')
+            _lib.stream_ptr(), int(phase)), 'bn_cae_encode_bwd')
 
 
 class EncodeFn(torch.autograd.Function):

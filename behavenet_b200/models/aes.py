@@ -278,6 +278,18 @@ class AE(BaseModel):
                     cnt += p.numel()
                 o += p.numel()
             self._rt.bufs['flat_grad_dec'] = (lo, hi) if lo is not None and hi - lo == cnt else None
+            # the encoder's heads and top conv layer form the contiguous bucket right below the decoder's: they
+            # are final after phase 1 of bn_cae_encode_bwd_phase
+            n_enc = 2 * self._driver.n_layers
+            top = {id(p) for p in params[n_enc - 2:n_enc + 4] if p is not None}
+            o, lo, hi, cnt = 0, None, None, 0
+            for p in missing:
+                if id(p) in top:
+                    lo = o if lo is None else lo
+                    hi = o + p.numel()
+                    cnt += p.numel()
+                o += p.numel()
+            self._rt.bufs['flat_grad_top'] = (lo, hi) if lo is not None and hi - lo == cnt else None
         return [None if (p is None or not p.requires_grad) else p.grad for p in params]
 
     def _shard(self, n):
@@ -299,38 +311,38 @@ class AE(BaseModel):
         kernels ("decoder-side buckets overlap with encoder backward").  Returns a
         handle for ``_allreduce`` or None when the gradients are not views of the flat buffer."""
         ok, _ = self._flat_is_live(params)
-        span = self._rt.bufs.get('flat_grad_dec')
+        span = self._rt.bufs.get('flat_grad_' + which)
         if not ok or span is None or not parallel.overlap_enabled():
             return None
         flat = self._rt.bufs['flat_grad']
         return (parallel.all_reduce_sum_async(flat[span[0]:span[1]]), span)
 
     def _allreduce(self, params, extra, pending=None):
-        """All-reduce(SUM) of the flat gradient -- minus the bucket already in flight -- and of the loss
-        partial sums."""
+        """All-reduce(SUM) of the flat gradient -- minus the buckets already in flight (``pending``: one
+        ``_allreduce_begin`` handle or a list of them) -- and of the loss partial sums."""
+        if pending is not None and not isinstance(pending, list):
+            pending = [pending]
+        pending = [p for p in (pending or []) if p is not None]
         ok, everything = self._flat_is_live(params)
         if ok:
             flat = self._rt.bufs['flat_grad']
-            if pending is not None:
-                lo, hi = pending[1]
-                if lo > 0:
-                    parallel.all_reduce_sum(flat[:lo])
-                if hi < flat.numel():
-                    parallel.all_reduce_sum(flat[hi:])
-            else:
-                parallel.all_reduce_sum(flat)
+            o = 0
+            for lo, hi in sorted(span for _, span in pending) + [(flat.numel(), flat.numel())]:
+                if lo > o:
+                    parallel.all_reduce_sum(flat[o:lo])
+                o = max(o, hi)
         else:
-            if pending is not None:
-                pending[0].wait()
-                pending = None
+            if pending:
+                for work, _ in pending:
+                    work.wait()
                 raise RuntimeError('gradient buffers changed between the bucketed all-reduce and its completion')
             for p in everything:
                 if p.requires_grad:
                     parallel.all_reduce_sum(p.grad)
         if extra is not None:
             parallel.all_reduce_sum(extra)
-        if pending is not None:
-            pending[0].wait()
+        for work, _ in pending:
+            work.wait()
 
     def loss(self, data, dataset=0, accumulate_grad=True, chunk_size=200):
         """MSE loss (+ gradients) with the reference's chunk semantics (aes.py:722-773): the batch
@@ -385,14 +397,22 @@ class AE(BaseModel):
             grads = self._grad_table(params)
             dz = drv.decode_bwd(n, None, params, packed, ws, grads, device)
             if dp:
-                pending = self._allreduce_begin(params)
+                pending = [self._allreduce_begin(params)]
             if timing:
                 ev[1].record()
-            drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
+            if dp and pending[0] is not None and self._rt.bufs.get('flat_grad_top') is not None:
+                # heads + top conv layer first; their bucket is all-reduced under the layers below
+                drv.encode_bwd(xs, dz, None, params, packed, ws, grads, phase=1)
+                pending.append(self._allreduce_begin(params, 'top'))
+                drv.encode_bwd(xs, dz, None, params, packed, ws, grads, phase=2)
+            else:
+                drv.encode_bwd(xs, dz, None, params, packed, ws, grads)
         elif accumulate_grad:
             self._grad_table(params)
-            if dp:
-                pending = self._allreduce_begin(params)      # a rank without frames issues the same collectives
+            if dp:      # a rank without frames issues the same collectives
+                pending = [self._allreduce_begin(params)]
+                if pending[0] is not None and self._rt.bufs.get('flat_grad_top') is not None:
+                    pending.append(self._allreduce_begin(params, 'top'))
         if timing:
             if not (n > 0 and accumulate_grad):
                 ev[1].record()

@@ -136,6 +136,16 @@ int bn_cae_encode_bwd(bn_cae_plan* plan, int n, const float* d_x, const float* d
                       const float* d_dlogvar, const float* const* d_params, const void* d_packed,
                       void* d_ws, float* const* d_grads, void* stream);
 
+/* The same backward pass in two calls, for data-parallel callers (gradient buckets
+ * all-reduced underneath the remaining backward kernels; the reference has no counterpart, its
+ * loss.backward() at aes.py:766 is one autograd sweep).  phase 1: heads and top conv layer -- on return the
+ * gradients of encoding.FF / encoding.logvar and of the last encoding.encoder.conv layer are final on `stream`;
+ * phase 2: everything below (call it after phase 1 with the same arguments and an untouched workspace);
+ * phase 0: both, identical to bn_cae_encode_bwd. */
+int bn_cae_encode_bwd_phase(bn_cae_plan* plan, int n, const float* d_x, const float* d_dmu,
+                            const float* d_dlogvar, const float* const* d_params, const void* d_packed,
+                            void* d_ws, float* const* d_grads, void* stream, int phase);
+
 /* Run ONE layer operation of the plan on caller tensors (NHWC fp32): kernel-level parity tests of
  * the tensor-core kernels against the CUDA-core kernels, and per-kernel timing for bench.py.
  *   side: 0 = encoder layer `layer` (Conv2d), 1 = decoder layer `layer` (ConvTranspose2d)

@@ -24,6 +24,12 @@ __all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'ConditionalAE', 'AEMSP', 'lo
 
 
 _DP_TIMING = os.environ.get('BN_DP_TIMING', '0') == '1'
+# BN_DP_TOP_BUCKET=1: encoder backward in two phases (bn_cae_encode_bwd_phase), the heads + top conv layer bucket
+# (13 of the encoder's 17.5 MB) all-reduced under the layers below.  OFF by default -- measured on 8 x B200
+# (profiles/r02_zz_dp_top_bucket_n8.txt): the collectives left exposed after the last backward kernel shrink from
+# 0.12 to 0.09 ms, but the encoder's backward kernels slow down from 0.70 to 0.75 ms next to the second NCCL
+# kernel (plus one more reduction launch): 2.556 ms per step against 2.503 ms without it.
+_DP_TOP_BUCKET = os.environ.get('BN_DP_TOP_BUCKET', '0') == '1'
 _DP_TIMES = []
 
 
@@ -400,7 +406,7 @@ class AE(BaseModel):
                 pending = [self._allreduce_begin(params)]
             if timing:
                 ev[1].record()
-            if dp and pending[0] is not None and self._rt.bufs.get('flat_grad_top') is not None:
+            if dp and _DP_TOP_BUCKET and pending[0] is not None and self._rt.bufs.get('flat_grad_top') is not None:
                 # heads + top conv layer first; their bucket is all-reduced under the layers below
                 drv.encode_bwd(xs, dz, None, params, packed, ws, grads, phase=1)
                 pending.append(self._allreduce_begin(params, 'top'))
@@ -411,7 +417,7 @@ class AE(BaseModel):
             self._grad_table(params)
             if dp:      # a rank without frames issues the same collectives
                 pending = [self._allreduce_begin(params)]
-                if pending[0] is not None and self._rt.bufs.get('flat_grad_top') is not None:
+                if _DP_TOP_BUCKET and pending[0] is not None and self._rt.bufs.get('flat_grad_top') is not None:
                     pending.append(self._allreduce_begin(params, 'top'))
         if timing:
             if not (n > 0 and accumulate_grad):

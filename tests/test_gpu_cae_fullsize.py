@@ -177,15 +177,18 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_data_parallel_ranks_reproduce_single_process(world, tmp_path):
+@pytest.mark.parametrize('world,top_bucket', [(2, '0'), (3, '0'), (2, '1')])
+def test_data_parallel_ranks_reproduce_single_process(world, top_bucket, tmp_path):
     """True multi-process data parallelism (model.data_parallel = True, torch.distributed) on one GPU, fp32
     kernels (mode 0: the shards' and the full batch's arithmetic then differ in summation order only):
     `world` ranks share cuda:0 over the gloo backend; each runs AE.loss and PSVAE.loss on the full batch
     description and must end with the single-process loss dict and gradients (PS-VAE chunks span ranks:
-    B = 300, chunk 128 -> 128 / 128 / 44 over `world` contiguous frame shards)."""
+    B = 300, chunk 128 -> 128 / 128 / 44 over `world` contiguous frame shards).  ``top_bucket`` = '1': the
+    encoder's backward pass in two phases with the heads + top-layer bucket all-reduced in between
+    (BN_DP_TOP_BUCKET, off by default: measured slower on 8 x B200)."""
     script = os.path.join(ROOT, 'tests', 'dp_worker.py')
     env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT=str(_free_port()), WORLD_SIZE=str(world),
+               BN_DP_TOP_BUCKET=top_bucket,
                PYTHONPATH=ROOT + os.pathsep + os.environ.get('PYTHONPATH', ''))
     procs = []
     for r in range(world):

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, 'libbehavenet_b200.so')
-SOURCES = ['cae_plan.cu', 'cae_simt.cu', 'cae_misc.cu', 'cae_thin.cu', 'cae_thin_tc.cu', 'cae_tc.cu', 'psvae.cu', 'arhmm.cu', 'arhmm_tc.cu']
+SOURCES = ['cae_plan.cu', 'cae_simt.cu', 'cae_misc.cu', 'cae_thin.cu', 'cae_thin_tc.cu', 'cae_tc.cu', 'linae.cu', 'psvae.cu', 'arhmm.cu', 'arhmm_tc.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--use_fast_math=false']

@@ -20,7 +20,7 @@ from behavenet_b200 import _lib, parallel
 from behavenet_b200.models.base import BaseModule, BaseModel
 from behavenet_b200.models._engine import CaeDriver, Runtime, EncodeFn, DecodeFn, output_padding
 
-__all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'AE', 'ConditionalAE', 'AEMSP', 'load_pretrained_ae']
+__all__ = ['ConvAEEncoder', 'ConvAEDecoder', 'LinearAEEncoder', 'LinearAEDecoder', 'AE', 'ConditionalAE', 'AEMSP', 'load_pretrained_ae']
 
 
 _DP_TIMING = os.environ.get('BN_DP_TIMING', '0') == '1'
@@ -203,8 +203,84 @@ class ConvAEDecoder(BaseModule):
         return DecodeFn.apply(self, torch.is_grad_enabled(), x, *self.kernel_params(dataset))
 
 
+def _linear_input(x, what, n_features):
+    """Frames flattened like the reference's ``x.view(x.size(0), -1)``."""
+    if not x.is_cuda:
+        raise RuntimeError('%s must live on a CUDA device (B200 kernels only; no CPU path)' % what)
+    if x.dtype != torch.float32:
+        raise TypeError('%s must be float32, got %s' % (what, x.dtype))
+    x = x.contiguous().view(x.shape[0], -1)
+    if x.shape[1] != n_features:
+        raise ValueError('%s has %d values per frame, expected %d' % (what, x.shape[1], n_features))
+    return x
+
+
+class LinearAEEncoder(BaseModule):
+    """Linear encoder (reference aes.py:491-547): ``z = x W^T + b`` on the flattened frame."""
+
+    def __init__(self, n_latents, input_size):
+        super().__init__()
+        self.n_latents = n_latents
+        self.input_size = input_size
+        self.encoder = None
+        self.decoder = None
+        self.build_model()
+
+    def __str__(self):
+        return 'Encoder architecture:\n' + str('    {}\n'.format(self.encoder))
+
+    def build_model(self):
+        if not 1 <= self.n_latents <= 64:
+            raise NotImplementedError('the linear-AE kernels hold 1..64 latents, got %d' % self.n_latents)
+        self.encoder = nn.Linear(out_features=self.n_latents, in_features=int(np.prod(self.input_size)), bias=True)
+
+    def forward(self, x, dataset=None):
+        """(z, None, None) -- the Nones stand in for the conv encoder's pool lists (aes.py:530-547).  Inference
+        only: training goes through ``AE.loss`` (one fused pass), there is no autograd bridge for this model."""
+        P = int(np.prod(self.input_size))
+        x = _linear_input(x, 'encoder input', P)
+        z = torch.empty(x.shape[0], self.n_latents, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().bn_linae_forward(
+            x.shape[0], P, self.n_latents, x.data_ptr(), self.encoder.weight.data_ptr(), self.encoder.bias.data_ptr(),
+            None, z.data_ptr(), None, _lib.stream_ptr()), 'bn_linae_forward')
+        return z, None, None
+
+
+class LinearAEDecoder(BaseModule):
+    """Linear decoder on the encoder's transposed weights plus its own bias (reference aes.py:550-613, the form
+    ``AE.build_model`` constructs).  An independent weight matrix (``encoder=None``) has no kernel."""
+
+    def __init__(self, n_latents, output_size, encoder=None):
+        super().__init__()
+        self.n_latents = n_latents
+        self.output_size = output_size
+        self.encoder = encoder          # registered as a submodule, like the reference (state_dict lists it twice)
+        self.decoder = None
+        self.build_model()
+
+    def __str__(self):
+        return 'Decoder architecture:\n    Encoder weights transposed (plus independent bias)\n'
+
+    def build_model(self):
+        if self.encoder is None:
+            raise NotImplementedError('a linear decoder with its own weights has no B200 kernel; AE ties it to the encoder')
+        self.bias = nn.Parameter(torch.zeros(int(np.prod(self.output_size))), requires_grad=True)
+
+    def forward(self, x, dataset=None):
+        """x_hat of shape (n, C, H, W) = z W + c (aes.py:588-613); inference only, see the encoder."""
+        lin = self.encoder.encoder
+        P = int(np.prod(self.output_size))
+        z = _linear_input(x, 'decoder input', self.n_latents)
+        n = z.shape[0]
+        xhat = torch.empty((n,) + tuple(int(v) for v in self.output_size), dtype=torch.float32, device=z.device)
+        _lib.check(_lib.lib().bn_linae_decode(
+            n, P, self.n_latents, z.data_ptr(), lin.weight.data_ptr(), self.bias.data_ptr(), xhat.data_ptr(),
+            _lib.stream_ptr()), 'bn_linae_decode')
+        return xhat
+
+
 class AE(BaseModel):
-    """Convolutional autoencoder (reference aes.py:616-773)."""
+    """Convolutional (or linear) autoencoder (reference aes.py:616-773)."""
 
     def __init__(self, hparams):
         super().__init__()
@@ -231,17 +307,61 @@ class AE(BaseModel):
             self.encoding = ConvAEEncoder(self.hparams)
             self.decoding = ConvAEDecoder(self.hparams)
         elif self.model_type == 'linear':
-            raise NotImplementedError('linear autoencoders have no B200 kernel path')
+            if self.hparams.get('fit_sess_io_layers', False):
+                raise NotImplementedError
+            n_latents = self.hparams['n_ae_latents']
+            self.encoding = LinearAEEncoder(n_latents, self.img_size)
+            self.decoding = LinearAEDecoder(n_latents, self.img_size, self.encoding)
         else:
             raise ValueError('"%s" is an invalid model_type' % self.model_type)
-        self._driver = self.encoding._driver
+        self._driver = getattr(self.encoding, '_driver', None)
         self._rt = Runtime()
 
     def forward(self, x, dataset=None, **kwargs):
         """(x_hat, z) (reference aes.py:695-720)."""
+        if self.model_type == 'linear':
+            z, _, _ = self.encoding(x)
+            return self.decoding(z), z
         z, pool_idx, outsize = self.encoding(x, dataset=dataset)
         y = self.decoding(z, pool_idx, outsize, dataset=dataset)
         return y, z
+
+    def _linear_loss(self, data, accumulate_grad, chunk_size):
+        """AE.loss of the linear model (aes.py:722-773): three launches (encode, decode + masked squared error per
+        reference chunk + its gradient, encoder weight gradient), gradients accumulated into ``.grad``."""
+        enc, dec = self.encoding.encoder, self.decoding
+        L, P = self.encoding.n_latents, int(np.prod(self.img_size))
+        x = _linear_input(data['images'][0], "data['images'][0]", P)
+        m = _linear_input(data['masks'][0].to(torch.float32), "data['masks'][0]", P) if 'masks' in data else None
+        if 'shard' in data:
+            beg, n_total = int(data['shard'][0]), int(data['shard'][1])
+            xs, ms = x, m
+        else:
+            n_total = x.shape[0]
+            beg, end = self._shard(n_total)
+            xs, ms = x[beg:end], (None if m is None else m[beg:end])
+        n = xs.shape[0]
+        n_chunks = int(np.ceil(n_total / chunk_size))
+        sse = torch.zeros(n_chunks, dtype=torch.float64, device=x.device)
+        params = [enc.weight, enc.bias, dec.bias]
+        if accumulate_grad:
+            for p in params:
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p)
+        grads = [p.grad if (accumulate_grad and p.requires_grad) else None for p in params]
+        if n > 0:
+            lib = _lib.lib()
+            ws = torch.empty(max(lib.bn_linae_workspace_bytes(n, L), 16), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.bn_linae_loss(
+                n, P, L, xs.data_ptr(), _lib.ptr(ms), enc.weight.data_ptr(), enc.bias.data_ptr(), dec.bias.data_ptr(),
+                int(chunk_size), beg, n_total, ws.data_ptr(), sse.data_ptr(), _lib.ptr(grads[0]), _lib.ptr(grads[1]),
+                _lib.ptr(grads[2]), _lib.stream_ptr()), 'bn_linae_loss')
+        if self.data_parallel and parallel.enabled():
+            for g in grads:
+                if g is not None:
+                    parallel.all_reduce_sum(g)
+            parallel.all_reduce_sum(sse)
+        return {'loss': float(sse.sum().item()) / (float(P) * n_total)}
 
     # -- fused training step -----------------------------------------------------------------
     def invalidate_packed(self):
@@ -359,6 +479,8 @@ class AE(BaseModel):
         gradient computed in the last layer's epilogue -> backward kernels accumulating into
         ``.grad``.  A single device->host read of the per-chunk sums ends the call.
         """
+        if self.model_type == 'linear':
+            return self._linear_loss(data, accumulate_grad, chunk_size)
         x = data['images'][0]
         m = data['masks'][0] if 'masks' in data else None
         drv, rt = self._driver, self._rt

@@ -161,6 +161,25 @@ int bn_cae_layer_op(bn_cae_plan* plan, int side, int layer, int op, int n, const
                     const float* d_in2, float* d_out, const float* const* d_params,
                     const void* d_packed, void* d_ws, void* stream);
 
+/* Linear autoencoder (model_type 'linear': LinearAEEncoder / LinearAEDecoder aes.py:491-613 as AE.build_model
+ * ties them, aes.py:684-687): z = x W^T + b, x_hat = z W + c.  d_x (n, P) frames flattened as the reference's
+ * x.view(n, -1), d_W (L, P) = encoding.encoder.weight, d_b (L) = encoding.encoder.bias, d_c (P) = decoding.bias;
+ * 1 <= L <= 64.
+ *   bn_linae_forward: AE.forward (aes.py:714-716): d_z (n, L) and, unless NULL, d_xhat (n, P).
+ *   bn_linae_decode:  LinearAEDecoder.forward (aes.py:588-613) on caller latents d_z (n, L) -> d_xhat (n, P).
+ *   bn_linae_loss:    AE.loss (aes.py:722-773) with the reference's chunk rule: frames [frame_offset,
+ *     frame_offset + n) of a batch of n_total frames; d_sse[chunk] += sum of mask * (x_hat - x)^2 (doubles, one per
+ *     reference chunk of the WHOLE batch); gradients of sum_chunks mean(chunk) ACCUMULATE into d_gW / d_gb / d_gc
+ *     (all NULL = loss only).  d_mask (n, P) may be NULL.  d_ws: bn_linae_workspace_bytes(n, L). */
+size_t bn_linae_workspace_bytes(int n, int n_latents);
+int bn_linae_forward(int n, int n_pixels, int n_latents, const float* d_x, const float* d_W, const float* d_b,
+                     const float* d_c, float* d_z, float* d_xhat, void* stream);
+int bn_linae_decode(int n, int n_pixels, int n_latents, const float* d_z, const float* d_W, const float* d_c,
+                    float* d_xhat, void* stream);
+int bn_linae_loss(int n, int n_pixels, int n_latents, const float* d_x, const float* d_mask, const float* d_W,
+                  const float* d_b, const float* d_c, int chunk_size, int frame_offset, int n_total, void* d_ws,
+                  double* d_sse, float* d_gW, float* d_gb, float* d_gc, void* stream);
+
 /* PS-VAE latent block (vaes.py:571-601, 669-696; losses.py:130-147, 284-372), one reference chunk
  * of n frames at a time (the MI/TC/DWKL estimators are pairwise over the chunk).
  * Inputs: d_pre (n, L) = FF output, d_logvar (n, L), frozen orthogonal d_A (n_labels, L) /

@@ -239,6 +239,51 @@ def ae_forward(sd, hparams, x, dataset=None):
     return decode(sd, hparams, z, dataset=dataset), z
 
 
+# ---- linear autoencoder (models/aes.py:491-613; AE.build_model ties the decoder to the encoder, aes.py:684-687) ----
+
+def make_linear_hparams(n_input_channels, y_pixels, x_pixels, n_ae_latents):
+    """The keys AE reads for ``model_type='linear'`` (aes.py:660-687)."""
+    return {'model_class': 'ae', 'model_type': 'linear', 'n_input_channels': n_input_channels, 'y_pixels': y_pixels,
+            'x_pixels': x_pixels, 'n_ae_latents': n_ae_latents, 'fit_sess_io_layers': False}
+
+
+def init_linear_state_dict(hparams, seed=0, dtype=torch.float32):
+    """Random parameters under the reference's names.  The decoder registers the encoder module as a submodule
+    (aes.py:573), so its tensors appear a second time as ``decoding.encoder.encoder.*``."""
+    g = torch.Generator().manual_seed(seed)
+    P = hparams['n_input_channels'] * hparams['y_pixels'] * hparams['x_pixels']
+    L = hparams['n_ae_latents']
+    bound = 1 / math.sqrt(P)
+    sd = {'encoding.encoder.weight': ((torch.rand(L, P, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype),
+          'encoding.encoder.bias': ((torch.rand(L, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype),
+          'decoding.bias': (torch.rand(P, generator=g, dtype=torch.float64) * 0.5 + 0.25).to(dtype)}
+    sd['decoding.encoder.encoder.weight'] = sd['encoding.encoder.weight']
+    sd['decoding.encoder.encoder.bias'] = sd['encoding.encoder.bias']
+    return sd
+
+
+def linear_ae_forward(sd, hparams, x):
+    """AE.forward, linear branch (aes.py:714-716) -> (x_hat, z)."""
+    W, b, c = sd['encoding.encoder.weight'], sd['encoding.encoder.bias'], sd['decoding.bias']
+    z = F.linear(x.reshape(x.shape[0], -1), W, b)
+    return (F.linear(z, W.t()) + c).view(x.shape), z
+
+
+def linear_ae_loss(sd, hparams, x, masks=None, chunk_size=200, want_grads=True):
+    """AE.loss (aes.py:722-773) of the linear model; gradients under the three distinct parameter names."""
+    names = ['encoding.encoder.weight', 'encoding.encoder.bias', 'decoding.bias']
+    params = {k: sd[k].detach().clone().requires_grad_(want_grads) for k in names}
+    total = 0.0
+    for b, e in _chunks(x.shape[0], chunk_size):
+        x_hat, _ = linear_ae_forward(params, hparams, x[b:e])
+        loss = mse(x[b:e], x_hat, None if masks is None else masks[b:e])
+        if want_grads:
+            loss.backward()
+        total += loss.item() * (e - b)
+    grads = {k: v.grad for k, v in params.items()} if want_grads else {}
+    return {'loss': total / x.shape[0]}, grads
+
+
 def _chunks(n, chunk_size):
     return [(b, min(b + chunk_size, n)) for b in range(0, n, chunk_size)]
 

@@ -458,6 +458,47 @@ def gen_split_trials():
     print('split_trials fixture written')
 
 
+LINEAR_CASES = [      # (name, C, H, W, latents, batch, chunk)
+    ('linae_64x48x1_l6_b7', 1, 64, 48, 6, 7, 4),
+    ('linae_40x36x2_l20_b9', 2, 40, 36, 20, 9, 200),
+]
+
+
+def run_reference_linear(case):
+    """AE with model_type='linear' (aes.py:491-613, 684-687, 714-716): forward, loss with and without masks."""
+    from behavenet.models import AE
+    name, c, h, w, L, b, chunk = case
+    hp = co.make_linear_hparams(c, h, w, L)
+    sd = co.init_linear_state_dict(hp, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(b, c, h, w, generator=g)
+    masks = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
+    model = AE(dict(hp))
+    model.load_state_dict(sd)
+    model.eval()
+    res = {}
+    with torch.no_grad():
+        res['x_hat'], res['z'] = model(x)
+    xo, zo = co.linear_ae_forward(sd, hp, x)
+    assert torch.allclose(xo, res['x_hat'], atol=1e-6) and torch.allclose(zo, res['z'], atol=1e-6), name
+    for tag, m in (('', None), ('_masked', masks)):
+        model.zero_grad()
+        data = {'images': x[None]}
+        if m is not None:
+            data['masks'] = m[None]
+        loss = model.loss(data, accumulate_grad=True, chunk_size=chunk)
+        res['loss' + tag] = torch.tensor(loss['loss'], dtype=torch.float64)
+        grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+        for k, v in grads.items():
+            res['grad%s.%s' % (tag, k)] = v
+        lo, go = co.linear_ae_loss(sd, hp, x, m, chunk)
+        assert abs(lo['loss'] - loss['loss']) < 1e-7, name
+        assert set(go) == set(grads), (name, set(go) ^ set(grads))
+        for k, gref in go.items():
+            assert torch.allclose(gref, grads[k], atol=1e-7, rtol=1e-4), (name, k)
+    return res
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if sys.argv[1:] == ['split_trials']:
@@ -470,6 +511,12 @@ def main():
         res = run_reference(case)
         np.savez_compressed(os.path.join(GOLD, case[0] + '.npz'), **compact(res))
         print('wrote', case[0], {k: tuple(v.shape) for k, v in list(res.items())[:3]})
+    for case in LINEAR_CASES:
+        if only and case[0] not in only:
+            continue
+        res = run_reference_linear(case)
+        np.savez_compressed(os.path.join(GOLD, case[0] + '.npz'), **compact(res))
+        print('wrote', case[0])
     if not only:
         gen_arhmm()
         gen_split_trials()

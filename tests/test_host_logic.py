@@ -119,11 +119,27 @@ def test_valid_padding_and_session_layers_mirror_the_reference_containers():
 
 
 def test_invalid_model_type_and_linear():
-    from behavenet_b200.models import AE
-    hp = co.make_hparams(1, 32, 32, 8)
-    hp['model_type'] = 'linear'
+    from behavenet_b200.models import AE, LinearAEDecoder
+    hp = co.make_linear_hparams(2, 24, 20, 5)
+    model = AE(copy.deepcopy(hp))
+    # the reference's names: the decoder holds the encoder module, so its tensors are listed twice (aes.py:573)
+    assert set(model.state_dict()) == set(co.init_linear_state_dict(hp))
+    model.load_state_dict(co.init_linear_state_dict(hp))
+    assert len(list(model.get_parameters())) == 3 and model.decoding.encoder is model.encoding
+    assert 'Encoder weights transposed' in str(model)
+    with pytest.raises(RuntimeError):            # no CPU path
+        model(torch.rand(2, 2, 24, 20))
+    with pytest.raises(RuntimeError):
+        model.loss({'images': torch.rand(1, 2, 2, 24, 20)})
+    copy.deepcopy(model)
+    pickle.loads(pickle.dumps(model))
     with pytest.raises(NotImplementedError):
-        AE(hp)
+        AE(dict(hp, fit_sess_io_layers=True))
+    with pytest.raises(NotImplementedError):
+        AE(dict(hp, n_ae_latents=65))
+    with pytest.raises(NotImplementedError):
+        LinearAEDecoder(5, (2, 24, 20), None)
+    hp = co.make_hparams(1, 32, 32, 8)
     hp['model_type'] = 'bogus'
     with pytest.raises((ValueError, NotImplementedError)):
         AE(hp)

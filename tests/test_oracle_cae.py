@@ -88,6 +88,32 @@ def test_oracle_reproduces_reference_goldens_of_arch_variants(case):
             golden_compare(gold, key, g, rtol=1e-4, atol=1e-5 * scale + 1e-9)
 
 
+LINEAR_CASES = {'linae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 4), 'linae_40x36x2_l20_b9': (2, 40, 36, 20, 9, 200)}
+
+
+@pytest.mark.parametrize('case', list(LINEAR_CASES))
+def test_oracle_reproduces_reference_goldens_of_the_linear_ae(case):
+    """model_type='linear' (aes.py:491-613): decoder on the transposed encoder weights + its own bias."""
+    c, h, w, L, b, chunk = LINEAR_CASES[case]
+    gold = load_golden(case)
+    hp = co.make_linear_hparams(c, h, w, L)
+    sd = co.init_linear_state_dict(hp, seed=0)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(b, c, h, w, generator=g)
+    masks = (torch.rand(b, c, h, w, generator=g) > 0.1).float()
+    x_hat, z = co.linear_ae_forward(sd, hp, x)
+    golden_compare(gold, 'x_hat', x_hat, rtol=1e-5, atol=1e-6)
+    golden_compare(gold, 'z', z, rtol=1e-5, atol=1e-6)
+    for tag, m in (('', None), ('_masked', masks)):
+        loss, grads = co.linear_ae_loss(sd, hp, x, m, chunk)
+        assert abs(loss['loss'] - float(gold['loss' + tag])) < 1e-7
+        assert {'grad%s.%s' % (tag, k) for k in grads} == {k.split('#')[0] for k in gold if k.startswith('grad%s.' % tag)}
+        for k, gr in grads.items():
+            key = 'grad%s.%s' % (tag, k)
+            scale = float(np.abs(gold[key + '#val'] if key + '#val' in gold else gold[key]).max())
+            golden_compare(gold, key, gr, rtol=1e-4, atol=1e-6 * scale + 1e-10)
+
+
 VAE_CASES = {
     'vae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 'vae', 4),
     'btcvae_32x32x2_l8_b6': (2, 32, 32, 8, 6, 'beta-tcvae', 4),

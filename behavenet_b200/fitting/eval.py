@@ -42,6 +42,8 @@ def _scale_u8(t):
 def _u8_loader_ok(model):
     """The first layer's uint8 loader (bn_cae_encode_u8) covers <= 4 channels, kernel 5, stride 2."""
     hp = model.hparams
+    if hp.get('model_type', 'conv') != 'conv' or hp.get('ae_padding_type', 'same') != 'same':
+        return False
     return (hp['ae_input_dim'][0] <= 4 and hp['ae_encoding_kernel_size'][0] == 5 and
             hp['ae_encoding_stride_size'][0] == 2 and hp['ae_encoding_n_channels'][0] % 32 == 0)
 
@@ -51,46 +53,74 @@ def encode_trials(model, trials, frames_per_launch=4096, device=None):
 
     trials: list of (T_i, C, H, W) arrays / tensors, uint8 (0..255) or float32 (0..1), host or device.
     Returns (latents, lengths): a (sum T_i, n_latents) CUDA float32 tensor and the list of T_i.
+
+    Trials are grouped into launches of up to ``frames_per_launch`` frames.  Host trials are copied on a side
+    stream one group AHEAD of the encoder (from pinned memory the copy of group k + 1 runs under the kernels of
+    group k; pageable memory still works, without the overlap).
     """
     import torch
     if device is None:
         device = next(model.parameters()).device
+    device = torch.device(device)
     lengths = [int(t.shape[0]) for t in trials]
     total = int(sum(lengths))
     L = int(model.hparams['n_ae_latents'])
     lat = torch.empty(total, L, dtype=torch.float32, device=device)
+    groups, group, gsize = [], [], 0
+    for t in trials:
+        if gsize and gsize + t.shape[0] > frames_per_launch:
+            groups.append(group)
+            group, gsize = [], 0
+        group.append(t)
+        gsize += int(t.shape[0])
+    if group:
+        groups.append(group)
+    on_gpu = device.type == 'cuda'
+    compute = torch.cuda.current_stream(device) if on_gpu else None
+    side = torch.cuda.Stream(device) if on_gpu else None
+
+    def stage(group):
+        """Enqueue the host -> device copies of one group on the side stream; returns (frames, event)."""
+        if not on_gpu:
+            return _assemble(model, group, device), None
+        side.wait_stream(compute)            # (the group's device-resident trials were produced on `compute`)
+        with torch.cuda.stream(side):
+            x = _assemble(model, group, device)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return x, ev
+
     was_training = model.training
     model.eval()
     with torch.no_grad():
         o = 0
-        group, gsize = [], 0
-
-        def flush():
-            nonlocal o, group, gsize
-            if not group:
-                return
-            parts = []
-            for t in group:
-                t = t if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t))
-                t = t.to(device, non_blocking=True)
-                parts.append(t if t.dtype == torch.uint8 else t.float())
-            if len({q.dtype for q in parts}) > 1:
-                parts = [_scale_u8(q) if q.dtype == torch.uint8 else q for q in parts]
-            x = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
-            if x.dtype == torch.uint8 and not _u8_loader_ok(model):
-                x = _scale_u8(x)
+        staged = stage(groups[0]) if groups else None
+        for k in range(len(groups)):
+            x, ev = staged
+            staged = stage(groups[k + 1]) if k + 1 < len(groups) else None
+            if ev is not None:
+                compute.wait_event(ev)
+                x.record_stream(compute)
             lat[o:o + x.shape[0]] = _latents_of(model, x)
             o += x.shape[0]
-            group, gsize = [], 0
-
-        for t in trials:
-            if gsize and gsize + t.shape[0] > frames_per_launch:
-                flush()
-            group.append(t)
-            gsize += int(t.shape[0])
-        flush()
     model.train(was_training)
     return lat, lengths
+
+
+def _assemble(model, group, device):
+    """One launch's frames on the device: uint8 stays uint8 when the first layer can read bytes."""
+    import torch
+    parts = []
+    for t in group:
+        t = t if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t))
+        t = t.to(device, non_blocking=True)
+        parts.append(t if t.dtype == torch.uint8 else t.float())
+    if len({q.dtype for q in parts}) > 1:
+        parts = [_scale_u8(q) if q.dtype == torch.uint8 else q for q in parts]
+    x = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+    if x.dtype == torch.uint8 and not _u8_loader_ok(model):
+        x = _scale_u8(x)
+    return x
 
 
 def export_latents(data_generator, model, filename=None):

@@ -53,7 +53,7 @@ SIGNATURES = {
     'bn_cae_encode_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'bn_cae_encode_bwd_phase': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     'bn_cae_layer_op': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'bn_linae_workspace_bytes': (_sz, [_i, _i]),
+    'bn_linae_workspace_bytes': (_sz, [_i, _i, _i]),
     'bn_linae_forward': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'bn_linae_decode': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'bn_linae_loss': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

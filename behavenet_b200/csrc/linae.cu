@@ -5,11 +5,15 @@
 // The whole model is a rank-L factorisation of a (frames x pixels) matrix with L ~ 10: 2 * L flops per byte of
 // frame data, i.e. HBM-bound on streaming the frames.  Three launches per training call, each reading the
 // frames once:
-//   linae_encode_kernel      : block per frame, z = x W^T + b                      (reads x)
+//   linae_encode_kernel      : block per 1 / 2 / 4 frames, z = x W^T + b           (reads x)
 //   linae_decode_loss_kernel : thread per pixel, frames in a loop: x_hat, masked squared error per reference
-//                              chunk, g = dL/dx_hat, dc += g, dW += z^T g, dz = g W^T  (reads x [, mask])
+//                              chunk, g = dL/dx_hat (stored), dc += g, dW += z^T g  (reads x [, mask], writes g)
+//   linae_encode_kernel on g : dz = g W^T                                          (reads g)
 //   linae_encode_bwd_kernel  : thread per pixel: dW += dz^T x, db = colsum(dz)     (reads x)
-// W (L x P floats, < 1 MB) is re-read through L1 / L2.  Gradients are ACCUMULATED into the caller's tensors.
+// i.e. four launches per training call that stream 5 x (frames x pixels) floats.  W (L x P floats, < 1 MB) is
+// re-read through L1 / L2.  Gradients are ACCUMULATED into the caller's tensors.  A first version reduced dz
+// across the pixels of a block inside the decode kernel's frame loop (L warp reductions and two barriers per
+// frame): 0.24 ms for 256 frames of 128 x 128, latency-bound at 0.03 of the HBM rate.
 #include <string.h>
 
 #include "../../include/behavenet_b200.h"
@@ -23,36 +27,67 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-// z[f][l] = b[l] + sum_p x[f][p] W[l][p]; one block per frame, latents in groups of 8
+// z[f][l] = b[l] + sum_p x[f][p] W[l][p] for the F frames of a block, 16 latents per pass over the pixels (one
+// pass for L <= 16): every W value fetched (through L1 / L2: the matrix is re-read by every block) is used for F
+// frames, and the loads of two pixel steps are issued before their FMAs (the first version had one step's loads
+// outstanding per thread: 350 us for 2048 frames, latency-bound).  Also run on the gradient image (x = g, no
+// bias) for dz = g W^T.
+template <int F>
 __global__ void __launch_bounds__(256) linae_encode_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ b, float* __restrict__ z,
-                                                           int P, int L) {
+                                                           int n, int P, int L) {
   bn_pdl_trigger();
   bn_pdl_wait();
-  __shared__ float red[8][8];
-  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* xf = x + (long long)f * P;
-  for (int l0 = 0; l0 < L; l0 += 8) {
-    float acc[8];
+  __shared__ float red[8][F * 16];
+  const int f0 = blockIdx.x * F, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xf[F];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int p = tid; p < P; p += 256) {
-      const float xv = __ldg(xf + p);
+  for (int q = 0; q < F; ++q) xf[q] = x + (long long)min(f0 + q, n - 1) * P;
+  for (int l0 = 0; l0 < L; l0 += 16) {
+    const float* wr[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (l0 + j < L) acc[j] = fmaf(xv, __ldg(W + (long long)(l0 + j) * P + p), acc[j]);
+    for (int j = 0; j < 16; ++j) wr[j] = W + (long long)min(l0 + j, L - 1) * P;
+    float acc[F][16];
+#pragma unroll
+    for (int q = 0; q < F; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[q][j] = 0.f;
+    int p = tid;
+    for (; p + 256 < P; p += 512) {
+      float xa[F], xb[F], wa[16], wb[16];
+#pragma unroll
+      for (int q = 0; q < F; ++q) { xa[q] = __ldg(xf[q] + p); xb[q] = __ldg(xf[q] + p + 256); }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { wa[j] = __ldg(wr[j] + p); wb[j] = __ldg(wr[j] + p + 256); }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+#pragma unroll
+        for (int q = 0; q < F; ++q) acc[q][j] = fmaf(xb[q], wb[j], fmaf(xa[q], wa[j], acc[q][j]));
+    }
+    for (; p < P; p += 256) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float wv = __ldg(wr[j] + p);
+#pragma unroll
+        for (int q = 0; q < F; ++q) acc[q][j] = fmaf(__ldg(xf[q] + p), wv, acc[q][j]);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s = warp_sum_f(acc[j]);
-      if (lane == 0) red[warp][j] = s;
-    }
+    for (int q = 0; q < F; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float s = warp_sum_f(acc[q][j]);
+        if (lane == 0) red[warp][q * 16 + j] = s;
+      }
     __syncthreads();
-    if (tid < 8 && l0 + tid < L) {
-      float s = b ? b[l0 + tid] : 0.f;
+    if (tid < F * 16) {
+      const int q = tid >> 4, j = tid & 15;
+      if (f0 + q < n && l0 + j < L) {
+        float s = b ? b[l0 + j] : 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w][tid];
-      z[(long long)f * L + l0 + tid] = s;
+        for (int w = 0; w < 8; ++w) s += red[w][tid];
+        z[(long long)(f0 + q) * L + l0 + j] = s;
+      }
     }
     __syncthreads();
   }
@@ -65,23 +100,32 @@ struct LinDecArgs {
   const float* c;        // (P) decoder bias
   const float* z;        // (n, L)
   float* xhat;           // (n, P) or NULL
-  float* dz;             // (n, L), zero-initialised, or NULL (forward only)
+  float* g;              // (n, P) dL/dx_hat, or NULL (forward / loss only)
   float* gW;             // (L, P) accumulated, or NULL
   float* gc;             // (P) accumulated, or NULL
   double* sse;           // per reference chunk of the WHOLE batch, accumulated, or NULL
   int n, P, L, chunk_size, frame_offset, n_total, fsplit;
 };
 
-// thread = pixel, block = 256 pixels x the frames of one frame split
+#define LIN_FB 32      // frames whose latents are staged in shared memory per barrier (a multiple of 4)
+
+// thread = pixel (its W column in registers), block = 256 pixels x the frames of one frame split.  Nothing in
+// the frame loop crosses threads: the squared error is kept per thread and reduced when the reference chunk
+// changes, g goes to memory for the dz pass (the encode kernel run on g).  Per-frame constants (chunk index,
+// gradient coefficient) are staged next to the latents; the frames are walked four at a time with their x / mask
+// loads issued up front.
 template <int LMAX>
 __global__ void __launch_bounds__(256) linae_decode_loss_kernel(const LinDecArgs a) {
   bn_pdl_trigger();
   bn_pdl_wait();
-  __shared__ float zs[LMAX];
-  __shared__ float red[8][LMAX + 1];
+  __shared__ __align__(16) float zs[LIN_FB][LMAX];
+  __shared__ float coef[LIN_FB];
+  __shared__ int chunk_of[LIN_FB];
+  __shared__ float red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p = blockIdx.x * 256 + tid;
   const bool in = p < a.P;
+  const int pc = in ? p : 0;
   const int per = (a.n + a.fsplit - 1) / a.fsplit;
   const int f0 = blockIdx.y * per, f1 = min(a.n, f0 + per);
   const int L = a.L;
@@ -92,62 +136,83 @@ __global__ void __launch_bounds__(256) linae_decode_loss_kernel(const LinDecArgs
     gw[l] = 0.f;
   }
   const float cb = in ? __ldg(a.c + p) : 0.f;
-  float gcb = 0.f;
-  const bool train = a.dz != nullptr;
-  double sse_acc = 0.0;         // thread 0: squared error of the current chunk seen by this block
+  float gcb = 0.f, e2sum = 0.f;
+  const bool train = a.g != nullptr;
+  const bool want_loss = a.sse != nullptr || train;
   int cur_chunk = -1;
-  for (int f = f0; f < f1; ++f) {
-    if (tid < L) zs[tid] = a.z[(long long)f * L + tid];
+
+  auto flush_chunk = [&]() {      // block-wide: every thread takes the same branch (chunks depend on f only)
+    const float s = warp_sum_f(e2sum);
+    if (lane == 0) red[warp] = s;
     __syncthreads();
-    float xh = cb;
+    if (tid == 0 && a.sse && cur_chunk >= 0) {
+      double t = 0.0;
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l) xh = fmaf(zs[l < L ? l : 0], w[l], xh);
-    if (a.xhat && in) a.xhat[(long long)f * a.P + p] = xh;
-    if (a.sse || train) {
-      const int gf = a.frame_offset + f;
-      const int chunk = a.chunk_size > 0 ? gf / a.chunk_size : 0;
-      const int clen = a.chunk_size > 0 ? min(a.chunk_size, a.n_total - chunk * a.chunk_size) : a.n_total;
-      float err = 0.f, m = 0.f;
-      if (in) {
-        m = a.mask ? __ldg(a.mask + (long long)f * a.P + p) : 1.f;
-        err = xh - __ldg(a.x + (long long)f * a.P + p);
-      }
-      const float e2 = err * err * m;
-      // dL/dx_hat of the chunk's mean squared error (losses.mse: mean over every element, masked or not)
-      const float g = 2.f * err * m / ((float)a.P * (float)clen);
-      float s = warp_sum_f(e2);
-      if (lane == 0) red[warp][LMAX] = s;
-      if (train) {
-        gcb += g;
-#pragma unroll
-        for (int l = 0; l < LMAX; ++l) {
-          gw[l] = fmaf(zs[l < L ? l : 0], g, gw[l]);
-          const float d = warp_sum_f(g * w[l]);
-          if (lane == 0) red[warp][l] = d;
-        }
-      }
-      __syncthreads();
-      if (train && tid < L) {
-        float d = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) d += red[q][tid];
-        atomicAdd(a.dz + (long long)f * L + tid, d);
-      }
-      if (tid == 0 && a.sse) {
-        if (chunk != cur_chunk) {
-          if (cur_chunk >= 0) atomicAdd(a.sse + cur_chunk, sse_acc);
-          cur_chunk = chunk;
-          sse_acc = 0.0;
-        }
-        float t = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t += red[q][LMAX];
-        sse_acc += (double)t;
-      }
+      for (int q = 0; q < 8; ++q) t += (double)red[q];
+      atomicAdd(a.sse + cur_chunk, t);
     }
     __syncthreads();
+    e2sum = 0.f;
+  };
+
+  for (int fb = f0; fb < f1; fb += LIN_FB) {
+    const int nf = min(LIN_FB, f1 - fb);
+    __syncthreads();
+    for (int i = tid; i < LIN_FB * LMAX; i += 256) {
+      const int q = i / LMAX, l = i - q * LMAX;
+      zs[q][l] = (q < nf && l < L) ? a.z[(long long)(fb + q) * L + l] : 0.f;
+    }
+    if (tid < LIN_FB) {
+      const int gf = a.frame_offset + fb + min(tid, nf - 1);
+      const int chunk = a.chunk_size > 0 ? gf / a.chunk_size : 0;
+      const int clen = a.chunk_size > 0 ? min(a.chunk_size, a.n_total - chunk * a.chunk_size) : a.n_total;
+      chunk_of[tid] = chunk;
+      // dL/dx_hat of the chunk's mean squared error (losses.mse: mean over every element, masked or not)
+      coef[tid] = 2.f / ((float)a.P * (float)clen);
+    }
+    __syncthreads();
+    for (int q0 = 0; q0 < nf; q0 += 4) {
+      float xv[4], mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long row = (long long)(fb + min(q0 + u, nf - 1)) * a.P + pc;
+        xv[u] = want_loss ? __ldg(a.x + row) : 0.f;
+        mv[u] = (want_loss && a.mask) ? __ldg(a.mask + row) : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u;
+        if (q >= nf) break;
+        float zr[LMAX];
+#pragma unroll
+        for (int l = 0; l < LMAX; l += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&zs[q][l]);
+          zr[l] = t.x; zr[l + 1] = t.y; zr[l + 2] = t.z; zr[l + 3] = t.w;
+        }
+        float xh = cb;
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) xh = fmaf(zr[l], w[l], xh);
+        const long long row = (long long)(fb + q) * a.P + pc;
+        if (a.xhat && in) a.xhat[row] = xh;
+        if (!want_loss) continue;
+        if (chunk_of[q] != cur_chunk) {
+          if (cur_chunk >= 0) flush_chunk();
+          cur_chunk = chunk_of[q];
+        }
+        const float m = in ? mv[u] : 0.f;
+        const float err = xh - xv[u];
+        e2sum = fmaf(err * err, m, e2sum);
+        if (train) {
+          const float g = coef[q] * err * m;
+          if (in) a.g[row] = g;
+          gcb += g;
+#pragma unroll
+          for (int l = 0; l < LMAX; ++l) gw[l] = fmaf(zr[l], g, gw[l]);
+        }
+      }
+    }
   }
-  if (tid == 0 && a.sse && cur_chunk >= 0) atomicAdd(a.sse + cur_chunk, sse_acc);
+  if (want_loss && cur_chunk >= 0) flush_chunk();
   if (train && in) {
     if (a.gc) atomicAdd(a.gc + p, gcb);
     if (a.gW) {
@@ -158,31 +223,50 @@ __global__ void __launch_bounds__(256) linae_decode_loss_kernel(const LinDecArgs
   }
 }
 
-// gW[l][p] += sum_f dz[f][l] x[f][p]; gb[l] += sum_f dz[f][l] (block (0, 0))
+// gW[l][p] += sum_f dz[f][l] x[f][p]; gb[l] += sum_f dz[f][l] (blocks of pixel tile 0)
 template <int LMAX>
 __global__ void __launch_bounds__(256) linae_encode_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                                float* __restrict__ gW, float* __restrict__ gb, int n, int P,
                                                                int L, int fsplit) {
   bn_pdl_trigger();
   bn_pdl_wait();
-  __shared__ float ds[LMAX];
+  __shared__ __align__(16) float ds[LIN_FB][LMAX];
   const int tid = threadIdx.x;
   const int p = blockIdx.x * 256 + tid;
   const bool in = p < P;
+  const int pc = in ? p : 0;
   const int per = (n + fsplit - 1) / fsplit;
   const int f0 = blockIdx.y * per, f1 = min(n, f0 + per);
   float acc[LMAX];
 #pragma unroll
   for (int l = 0; l < LMAX; ++l) acc[l] = 0.f;
   float bsum = 0.f;
-  for (int f = f0; f < f1; ++f) {
-    if (tid < L) ds[tid] = dz[(long long)f * L + tid];
+  for (int fb = f0; fb < f1; fb += LIN_FB) {
+    const int nf = min(LIN_FB, f1 - fb);
     __syncthreads();
-    const float xv = in ? __ldg(x + (long long)f * P + p) : 0.f;
+    for (int i = tid; i < LIN_FB * LMAX; i += 256) {
+      const int q = i / LMAX, l = i - q * LMAX;
+      ds[q][l] = (q < nf && l < L) ? dz[(long long)(fb + q) * L + l] : 0.f;
+    }
+    __syncthreads();
+    for (int q0 = 0; q0 < LIN_FB; q0 += 4) {       // rows beyond nf hold zeros
+      if (q0 >= nf) break;
+      float xv[4];
 #pragma unroll
-    for (int l = 0; l < LMAX; ++l) acc[l] = fmaf(ds[l < L ? l : 0], xv, acc[l]);
-    if (blockIdx.x == 0 && tid < L) bsum += ds[tid];
-    __syncthreads();
+      for (int u = 0; u < 4; ++u) xv[u] = __ldg(x + (long long)(fb + min(q0 + u, nf - 1)) * P + pc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int l = 0; l < LMAX; l += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&ds[q0 + u][l]);
+          acc[l] = fmaf(t.x, xv[u], acc[l]);
+          acc[l + 1] = fmaf(t.y, xv[u], acc[l + 1]);
+          acc[l + 2] = fmaf(t.z, xv[u], acc[l + 2]);
+          acc[l + 3] = fmaf(t.w, xv[u], acc[l + 3]);
+        }
+        if (blockIdx.x == 0 && tid < L) bsum += ds[q0 + u][tid];
+      }
+    }
   }
   if (in && gW) {
 #pragma unroll
@@ -193,11 +277,23 @@ __global__ void __launch_bounds__(256) linae_encode_bwd_kernel(const float* __re
 }
 
 int frame_splits(int n, int P) {
+  // 256-pixel tiles x frame splits: ~4 blocks per SM's worth of resident work, at least 32 frames per block
   const int tiles = bn_cdiv(P, 256);
-  int fs = bn_cdiv(2 * 148, tiles);
-  if (fs > n) fs = n;
-  if (fs > 64) fs = 64;
+  int fs = bn_cdiv(6 * 148, tiles);
+  if (fs > bn_cdiv(n, LIN_FB)) fs = bn_cdiv(n, LIN_FB);
+  if (fs > 128) fs = 128;
   return fs < 1 ? 1 : fs;
+}
+
+int launch_encode(const float* x, const float* W, const float* b, float* z, int n, int P, int L, cudaStream_t st) {
+  // two frames per block (W fetches shared) once that still leaves two waves of blocks
+  if (n >= 4 * 148) {
+    BN_CUDA(bn_launch(linae_encode_kernel<2>, dim3(bn_cdiv(n, 2)), 256, 0, st, x, W, b, z, n, P, L));
+  } else {
+    BN_CUDA(bn_launch(linae_encode_kernel<1>, dim3(n), 256, 0, st, x, W, b, z, n, P, L));
+  }
+  BN_LAUNCHED();
+  return 0;
 }
 
 template <int LMAX>
@@ -217,8 +313,8 @@ int launch_encode_bwd(const float* x, const float* dz, float* gW, float* gb, int
 
 }  // namespace
 
-extern "C" size_t bn_linae_workspace_bytes(int n, int L) {
-  return n > 0 && L > 0 ? 2 * sizeof(float) * (size_t)n * L : 0;
+extern "C" size_t bn_linae_workspace_bytes(int n, int P, int L) {
+  return n > 0 && L > 0 && P > 0 ? sizeof(float) * ((size_t)2 * n * L + (size_t)n * P) : 0;
 }
 
 extern "C" int bn_linae_forward(int n, int P, int L, const float* d_x, const float* d_W, const float* d_b,
@@ -228,8 +324,7 @@ extern "C" int bn_linae_forward(int n, int P, int L, const float* d_x, const flo
   if (d_xhat && !d_c) BN_FAIL("bn_linae_forward: the decoder needs its bias");
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  BN_CUDA(bn_launch(linae_encode_kernel, dim3(n), 256, 0, st, d_x, d_W, d_b, d_z, P, L));
-  BN_LAUNCHED();
+  BN_TRY(launch_encode(d_x, d_W, d_b, d_z, n, P, L, st));
   if (!d_xhat) return 0;
   LinDecArgs a;
   memset(&a, 0, sizeof(a));
@@ -263,17 +358,17 @@ extern "C" int bn_linae_loss(int n, int P, int L, const float* d_x, const float*
   cudaStream_t st = (cudaStream_t)stream;
   float* z = (float*)d_ws;
   float* dz = z + (size_t)n * L;
-  BN_CUDA(bn_launch(linae_encode_kernel, dim3(n), 256, 0, st, d_x, d_W, d_b, z, P, L));
-  BN_LAUNCHED();
-  if (train) BN_CUDA(cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)n * L, st));
+  float* g = dz + (size_t)n * L;
+  BN_TRY(launch_encode(d_x, d_W, d_b, z, n, P, L, st));
   LinDecArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = d_x; a.mask = d_mask; a.W = d_W; a.c = d_c; a.z = z; a.dz = train ? dz : nullptr;
+  a.x = d_x; a.mask = d_mask; a.W = d_W; a.c = d_c; a.z = z; a.g = train ? g : nullptr;
   a.gW = d_gW; a.gc = d_gc; a.sse = d_sse;
   a.n = n; a.P = P; a.L = L; a.chunk_size = chunk_size; a.frame_offset = frame_offset; a.n_total = n_total;
   a.fsplit = frame_splits(n, P);
   BN_TRY(L <= 16 ? launch_decode<16>(a, st) : (L <= 32 ? launch_decode<32>(a, st) : launch_decode<64>(a, st)));
   if (!train) return 0;
+  BN_TRY(launch_encode(g, d_W, nullptr, dz, n, P, L, st));          // dz = g W^T
   const int fs = a.fsplit;
   return L <= 16 ? launch_encode_bwd<16>(d_x, dz, d_gW, d_gb, n, P, L, fs, st)
                  : (L <= 32 ? launch_encode_bwd<32>(d_x, dz, d_gW, d_gb, n, P, L, fs, st)

@@ -351,7 +351,7 @@ class AE(BaseModel):
         grads = [p.grad if (accumulate_grad and p.requires_grad) else None for p in params]
         if n > 0:
             lib = _lib.lib()
-            ws = torch.empty(max(lib.bn_linae_workspace_bytes(n, L), 16), dtype=torch.uint8, device=x.device)
+            ws = torch.empty(max(lib.bn_linae_workspace_bytes(n, P, L), 16), dtype=torch.uint8, device=x.device)
             _lib.check(lib.bn_linae_loss(
                 n, P, L, xs.data_ptr(), _lib.ptr(ms), enc.weight.data_ptr(), enc.bias.data_ptr(), dec.bias.data_ptr(),
                 int(chunk_size), beg, n_total, ws.data_ptr(), sse.data_ptr(), _lib.ptr(grads[0]), _lib.ptr(grads[1]),

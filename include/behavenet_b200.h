@@ -170,8 +170,8 @@ int bn_cae_layer_op(bn_cae_plan* plan, int side, int layer, int op, int n, const
  *   bn_linae_loss:    AE.loss (aes.py:722-773) with the reference's chunk rule: frames [frame_offset,
  *     frame_offset + n) of a batch of n_total frames; d_sse[chunk] += sum of mask * (x_hat - x)^2 (doubles, one per
  *     reference chunk of the WHOLE batch); gradients of sum_chunks mean(chunk) ACCUMULATE into d_gW / d_gb / d_gc
- *     (all NULL = loss only).  d_mask (n, P) may be NULL.  d_ws: bn_linae_workspace_bytes(n, L). */
-size_t bn_linae_workspace_bytes(int n, int n_latents);
+ *     (all NULL = loss only).  d_mask (n, P) may be NULL.  d_ws: bn_linae_workspace_bytes(n, P, L). */
+size_t bn_linae_workspace_bytes(int n, int n_pixels, int n_latents);
 int bn_linae_forward(int n, int n_pixels, int n_latents, const float* d_x, const float* d_W, const float* d_b,
                      const float* d_c, float* d_z, float* d_xhat, void* stream);
 int bn_linae_decode(int n, int n_pixels, int n_latents, const float* d_z, const float* d_W, const float* d_c,

@@ -77,7 +77,7 @@ def encode_trials(model, trials, frames_per_launch=4096, device=None):
         groups.append(group)
     on_gpu = device.type == 'cuda'
     compute = torch.cuda.current_stream(device) if on_gpu else None
-    side = torch.cuda.Stream(device) if on_gpu else None
+    side = _side_stream(device) if on_gpu else None
 
     def stage(group):
         """Enqueue the host -> device copies of one group on the side stream; returns (frames, event)."""
@@ -105,6 +105,19 @@ def encode_trials(model, trials, frames_per_launch=4096, device=None):
             o += x.shape[0]
     model.train(was_training)
     return lat, lengths
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """ONE copy stream per device for the life of the process: the caching allocator keeps a pool per stream, so a
+    fresh stream per call would re-allocate every staging buffer (measured: C5 end to end 563 k -> 376 k frames/s)."""
+    import torch
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
 
 
 def _assemble(model, group, device):

@@ -505,14 +505,14 @@ def msps_loss(sd, hparams, x, labels, eps, masks=None, sessions=None, want_grads
 # VAE / beta-TC-VAE (models/vaes.py:38-208, 367-503)
 # ------------------------------------------------------------------------------------------------
 
-def vae_forward(sd, hparams, x, eps=None, use_mean=False):
+def vae_forward(sd, hparams, x, eps=None, use_mean=False, dataset=None):
     """VAE.forward (vaes.py:102-129) -> (x_hat, z, mu, logvar); noise injected like psvae_forward."""
-    mu, logvar = encode(sd, hparams, x)
+    mu, logvar = encode(sd, hparams, x, dataset=dataset)
     z = mu if use_mean else eps * torch.exp(logvar) + mu
-    return decode(sd, hparams, z), z, mu, logvar
+    return decode(sd, hparams, z, dataset=dataset), z, mu, logvar
 
 
-def vae_loss(sd, hparams, x, eps, masks=None, beta=None, chunk_size=200, want_grads=True):
+def vae_loss(sd, hparams, x, eps, masks=None, beta=None, chunk_size=200, want_grads=True, dataset=None):
     """VAE.loss (vaes.py:131-208): -ll + beta * KL per chunk."""
     beta = hparams['vae.beta'] if beta is None else beta
     params = {k: v.detach().clone().requires_grad_(want_grads) for k, v in sd.items()}
@@ -520,7 +520,7 @@ def vae_loss(sd, hparams, x, eps, masks=None, beta=None, chunk_size=200, want_gr
     n_pix = int(np.prod(x.shape[1:]))
     for b, e in _chunks(x.shape[0], chunk_size):
         x_in = x[b:e]
-        x_hat, _, mu, logvar = vae_forward(params, hparams, x_in, eps[b:e])
+        x_hat, _, mu, logvar = vae_forward(params, hparams, x_in, eps[b:e], dataset=dataset)
         ll = gaussian_ll(x_in, x_hat, None if masks is None else masks[b:e])
         kl = kl_div_to_std_normal(mu, logvar)
         loss = -ll + beta * kl

@@ -53,11 +53,14 @@ CAE_CASES = [
     ('ae_valid_160x130x2_l6_b5', 2, 160, 130, 6, 5, 'ae+valid', 0, 2),
     ('ae_io3_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'ae+io3', 0, 4),
     ('ae_valid_io2_160x130x2_l6_b5', 2, 160, 130, 6, 5, 'ae+valid+io2', 0, 200),
+    ('psvae_valid_128x128x2_l16_b5', 2, 128, 128, 16, 5, 'ps-vae+valid', 4, 3),     # the variants reach the whole family
+    ('vae_io2_64x48x1_l6_b7', 1, 64, 48, 6, 7, 'vae+io2', 0, 4),
 ]
 
 
 def synth_inputs(case):
     name, c, h, w, L, b, mc, nl, chunk = case
+    mc = mc.split('+')[0]
     g = torch.Generator().manual_seed(1234)
     x = torch.rand(b, c, h, w, generator=g)
     out = {'x': x}
@@ -331,14 +334,15 @@ def run_reference(case):
             return e.to(t.dtype)
         vaes.torch.randn_like = fake_randn_like
         try:
+            ds = 1 if opts.get('n_datasets', 0) else None
             with torch.no_grad():
                 state['pos'] = 0
-                x_hat, z, mu, logvar = model(inp['x'])
+                x_hat, z, mu, logvar = model(inp['x'], dataset=ds)
             res.update(x_hat=x_hat, z=z, mu=mu, logvar=logvar)
             model.curr_epoch = 1
             model.zero_grad()
             state['pos'] = 0
-            loss = model.loss({'images': inp['x'][None]}, accumulate_grad=True, chunk_size=chunk)
+            loss = model.loss({'images': inp['x'][None]}, dataset=ds or 0, accumulate_grad=True, chunk_size=chunk)
         finally:
             vaes.torch.randn_like = orig
         for k, v in loss.items():
@@ -347,11 +351,14 @@ def run_reference(case):
             if p.grad is not None:
                 res['grad.' + k] = p.grad.clone()
         # pin the restatement
-        o = co.vae_forward(sd, hp, inp['x'], inp['eps'])
+        o = co.vae_forward(sd, hp, inp['x'], inp['eps'], dataset=ds)
         for a, bref in zip(o, (x_hat, z, mu, logvar)):
             assert torch.allclose(a, bref, atol=2e-5), name
-        fn = co.vae_loss if mc == 'vae' else co.btcvae_loss
-        lo, go = fn(sd, hp, inp['x'], inp['eps'], chunk_size=chunk)
+        if mc == 'vae':
+            lo, go = co.vae_loss(sd, hp, inp['x'], inp['eps'], chunk_size=chunk, dataset=ds)
+        else:
+            lo, go = co.btcvae_loss(sd, hp, inp['x'], inp['eps'], chunk_size=chunk)
+        assert set(go) == {k[5:] for k in res if k.startswith('grad.')}, name
         for k in lo:
             ref = float(res['loss.' + k])
             assert abs(lo[k] - ref) <= 1e-5 * max(1.0, abs(ref)), (name, k, lo[k], ref)

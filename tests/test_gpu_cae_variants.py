@@ -143,3 +143,84 @@ def test_valid_padding_at_a_tile_filling_batch(mode):
     errs = {k: rel_err(p.grad, g64[k]) for k, p in model.named_parameters()}
     bad = {k: e for k, e in errs.items() if not e < 2 * bound(table, k)}
     assert not bad, (bad, errs)
+
+
+def _family_grads(gold, model, tc_mode, t, loose_prefix=None):
+    bad, n_checked = [], 0
+    for name, p in model.named_parameters():
+        key = 'grad.' + name
+        if key not in gold and key + '#val' not in gold:
+            # frozen PS-VAE projections, or another session's input / output layers
+            assert (not p.requires_grad) or ('_sess_io_layers.' in name and p.grad is None), name
+            continue
+        loose = loose_prefix is not None and tc_mode == 0 and name.startswith(loose_prefix)
+        try:
+            compare_grad(gold, key, p.grad, tc_mode, t, factor=50.0 if loose else 4.0)
+        except AssertionError as e:
+            bad.append((key, str(e)[:300]))
+        n_checked += 1
+    assert not bad, bad
+    return n_checked
+
+
+@pytest.mark.parametrize('tc_mode', [0, 1])
+def test_psvae_with_valid_padding_matches_reference_golden(tc_mode):
+    """The variants reach the whole model family: PS-VAE (C3 geometry) with ae_padding_type='valid'."""
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import PSVAE
+    case = 'psvae_valid_128x128x2_l16_b5'
+    hp = co.make_hparams(2, 128, 128, 16, 'ps-vae', 4, padding_type='valid')
+    model = PSVAE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.to('cuda')
+    _lib.lib().bn_set_tensor_core_mode(tc_mode)
+    try:
+        inp = synth_inputs(2, 128, 128, 16, 5, 4)
+        gold, t = load_golden(case), tols(tc_mode)
+        x, y, eps = inp['x'].cuda(), inp['labels'].cuda(), inp['eps'].cuda()
+        with torch.no_grad():
+            x_hat, z, mu, logvar, y_hat = model(x, eps=eps)
+        golden_compare(gold, 'x_hat', x_hat, rtol=t['xhat'], atol=t['xhat'])
+        for key, val in (('z', z), ('mu', mu), ('logvar', logvar), ('y_hat', y_hat)):
+            assert rel_err(val, gold[key]) < t['z'] * 10, key
+        model.curr_epoch = 1
+        model.zero_grad()
+        out = model.loss({'images': x[None], 'labels': y[None]}, accumulate_grad=True, chunk_size=3, eps=eps)
+        for k in ['loss', 'loss_data_ll', 'loss_label_ll', 'loss_zs_kl', 'loss_zu_mi', 'loss_zu_tc', 'loss_zu_dwkl',
+                  'loss_data_mse']:
+            ref = float(gold['loss.' + k])
+            assert abs(out[k] - ref) <= 10 * t['loss'] * max(1.0, abs(ref)), (k, out[k], ref)
+        assert _family_grads(gold, model, tc_mode, t, loose_prefix='encoding.encoder') >= 26
+    finally:
+        _lib.lib().bn_set_tensor_core_mode(1)
+
+
+@pytest.mark.parametrize('tc_mode', [0, 1])
+def test_vae_with_session_layers_matches_reference_golden(tc_mode):
+    """VAE with fit_sess_io_layers: forward / loss with dataset = 1 take session 1's input and output layers."""
+    from behavenet_b200 import _lib
+    from behavenet_b200.models import VAE
+    case = 'vae_io2_64x48x1_l6_b7'
+    hp = co.make_hparams(1, 64, 48, 6, 'vae', 0, n_datasets=2)
+    model = VAE(copy.deepcopy(hp))
+    model.load_state_dict(co.init_state_dict(hp, seed=0))
+    model.to('cuda')
+    _lib.lib().bn_set_tensor_core_mode(tc_mode)
+    try:
+        inp = synth_inputs(1, 64, 48, 6, 7, variational=True)
+        gold, t = load_golden(case), tols(tc_mode)
+        x, eps = inp['x'].cuda(), inp['eps'].cuda()
+        with torch.no_grad():
+            x_hat, z, mu, logvar = model(x, dataset=1, eps=eps)
+        golden_compare(gold, 'x_hat', x_hat, rtol=t['xhat'], atol=t['xhat'])
+        for key, val in (('z', z), ('mu', mu), ('logvar', logvar)):
+            assert rel_err(val, gold[key]) < t['z'] * 10, key
+        model.curr_epoch = 1
+        model.zero_grad()
+        out = model.loss({'images': x[None]}, dataset=1, accumulate_grad=True, chunk_size=4, eps=eps)
+        for k in [k[5:] for k in gold if k.startswith('loss.')]:
+            ref = float(gold['loss.' + k])
+            assert abs(out[k] - ref) <= 10 * t['loss'] * max(1.0, abs(ref)), (k, out[k], ref)
+        assert _family_grads(gold, model, tc_mode, t) == 26
+    finally:
+        _lib.lib().bn_set_tensor_core_mode(1)

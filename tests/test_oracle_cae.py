@@ -88,6 +88,32 @@ def test_oracle_reproduces_reference_goldens_of_arch_variants(case):
             golden_compare(gold, key, g, rtol=1e-4, atol=1e-5 * scale + 1e-9)
 
 
+def test_oracle_reproduces_family_variant_goldens():
+    """PS-VAE with 'valid' padding and VAE with per-session layers (dataset = 1): loss dicts of the reference."""
+    torch.set_num_threads(8)
+    gold = load_golden('psvae_valid_128x128x2_l16_b5')
+    hp = co.make_hparams(2, 128, 128, 16, 'ps-vae', 4, padding_type='valid')
+    sd = co.init_state_dict(hp, seed=0)
+    inp = synth_inputs(2, 128, 128, 16, 5, 4)
+    out = co.psvae_forward(sd, hp, inp['x'], inp['eps'])
+    for key, val in zip(('x_hat', 'z', 'mu', 'logvar', 'y_hat'), out):
+        golden_compare(gold, key, val, rtol=1e-4, atol=2e-5)
+    loss, grads = co.psvae_loss(sd, hp, inp['x'], inp['labels'], inp['eps'], chunk_size=3)
+    for k, v in loss.items():
+        ref = float(gold['loss.' + k])
+        assert abs(v - ref) <= 1e-5 * max(1.0, abs(ref)), k
+    gold = load_golden('vae_io2_64x48x1_l6_b7')
+    hp = co.make_hparams(1, 64, 48, 6, 'vae', 0, n_datasets=2)
+    sd = co.init_state_dict(hp, seed=0)
+    inp = synth_inputs(1, 64, 48, 6, 7, variational=True)
+    loss, grads = co.vae_loss(sd, hp, inp['x'], inp['eps'], chunk_size=4, dataset=1)
+    for k in [k[5:] for k in gold if k.startswith('loss.')]:
+        ref = float(gold['loss.' + k])
+        assert abs(loss[k] - ref) <= 1e-5 * max(1.0, abs(ref)), k
+    assert {'grad.' + k for k in grads} == {k.split('#')[0] for k in gold if k.startswith('grad.')}
+    assert any('_sess_io_layers.1.' in k for k in grads) and not any('_sess_io_layers.0.' in k for k in grads)
+
+
 LINEAR_CASES = {'linae_64x48x1_l6_b7': (1, 64, 48, 6, 7, 4), 'linae_40x36x2_l20_b9': (2, 40, 36, 20, 9, 200)}
 
 

@@ -57,6 +57,11 @@ class _Reader:
     def length(self, off):
         return self.u(off, self.lsz)
 
+    def addr_bytes(self, b, o):
+        """Address field inside an already extracted message body."""
+        v = int.from_bytes(b[o:o + self.osz], 'little')
+        return None if v == (1 << (8 * self.osz)) - 1 else v + self.base
+
 
 def _parse_datatype(b):
     cls, ver = b[0] & 0x0F, b[0] >> 4
@@ -169,14 +174,6 @@ class _Object:
 
     def find(self, mtype):
         return [b for t, b in self.msgs if t == mtype]
-
-
-def _addr_bytes(self, b, o):
-    v = int.from_bytes(b[o:o + self.osz], 'little')
-    return None if v == (1 << (8 * self.osz)) - 1 else v + self.base
-
-
-_Reader.addr_bytes = _addr_bytes
 
 
 class Dataset:

@@ -268,3 +268,45 @@ def test_latest_format_structures_from_the_specification(tmp_path, dense):
         for k, a in arrays.items():
             assert f[k].shape == a.shape and f[k].dtype == a.dtype
             np.testing.assert_array_equal(f[k][()], a)
+
+
+def test_round_trip_property():
+    """Random trees (nesting, names, dtypes, ranks, empty and scalar datasets) survive write -> read."""
+    import tempfile
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    dtypes = st.sampled_from(['u1', 'i1', '<u2', '<i2', '<u4', '<i4', '<u8', '<i8', '<f4', '<f8', '>i4', '>f8'])
+    names = st.text(alphabet='abcdefghijklmnopqrstuvwxyzABC_0123456789-. é', min_size=1, max_size=12).filter(
+        lambda s: s not in ('.', '..'))
+
+    @st.composite
+    def arrays(draw):
+        dt = np.dtype(draw(dtypes))
+        shape = tuple(draw(st.lists(st.integers(0, 5), min_size=0, max_size=4)))
+        n = int(np.prod(shape, dtype=np.int64))
+        seed = draw(st.integers(0, 2 ** 31 - 1))
+        rng = np.random.RandomState(seed)
+        a = (rng.randn(n) * 100).astype(dt) if dt.kind == 'f' else rng.randint(0, 100, n).astype(dt)
+        return a.reshape(shape)
+
+    trees = st.recursive(arrays(), lambda kids: st.dictionaries(names, kids, max_size=6), max_leaves=12)
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.dictionaries(names, trees, max_size=6), st.sampled_from([0, 512]))
+    def run(tree, userblock):
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, 't.hdf5')
+            h5.write(path, tree, userblock=userblock)
+
+            def check(node, ref):
+                if isinstance(ref, dict):
+                    assert sorted(node.keys()) == sorted(ref)
+                    for k, v in ref.items():
+                        check(node[k], v)
+                else:
+                    want = ref.dtype.newbyteorder('<') if ref.dtype.byteorder == '>' else ref.dtype      # written little-endian
+                    assert node.shape == ref.shape and node.dtype == want
+                    np.testing.assert_array_equal(node[()], ref)
+            with h5.File(path) as f:
+                check(f, tree)
+    run()

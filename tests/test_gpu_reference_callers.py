@@ -166,3 +166,41 @@ def test_reference_arhmm_grid_search_body_runs_verbatim_with_the_b200_hmm(tmp_pa
     usage = np.bincount(np.concatenate(zs), minlength=K)
     assert np.array_equal(usage, np.sort(usage)[::-1])              # states re-ordered by usage (lines 201-204)
     assert np.array_equal(clone.most_likely_states(latents['train'][0]), zs[0])
+
+
+def test_reference_fit_with_the_linear_ae_on_an_hdf5_session(tmp_path):
+    """The same unmodified fit() on the linear autoencoder (model_type='linear') fed from a ``data.hdf5`` in the
+    reference's layout (``images/trial_%04i``, uint8) through HDF5Source's dependency-free reader."""
+    from behavenet_b200.data import HDF5Source, PrefetchSessionsGenerator, hdf5_lite
+    from behavenet_b200.models import AE
+    training = _import_reference_training()
+    hp = co.make_linear_hparams(1, 32, 32, 6)
+    expt_dir = str(tmp_path)
+    os.makedirs(os.path.join(expt_dir, 'version_0'))
+    hp.update({'learning_rate': 1e-3, 'l2_reg': 0.0, 'enable_early_stop': True, 'early_stop_history': 10,
+               'min_n_epochs': 1, 'max_n_epochs': 3, 'val_check_interval': 1, 'rng_seed_train': 0,
+               'expt_dir': expt_dir, 'export_latents': True, 'save_last_model': True, 'device': 'cuda'})
+    frames = _structured_frames(20, 1, 32, 32, seed=1)
+    path = os.path.join(expt_dir, 'data.hdf5')
+    hdf5_lite.write(path, {'images': {'trial_%04i' % i: f for i, f in enumerate(frames)}})
+    src = HDF5Source(path, ['images'], lab='lab', expt='expt', animal='mouse', session='s0', backend='lite')
+    gen = PrefetchSessionsGenerator([src], device='cuda', rng_seed=0,
+                                    trial_splits={'train_tr': 6, 'val_tr': 2, 'test_tr': 2, 'gap_tr': 0})
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = AE(hp)
+    model.to('cuda')
+    model.version = 0
+    exp = StubExperiment(0)
+    training.fit(hp, model, gen, exp, method='ae')
+    gen.close()
+    train_rows = [r for r in exp.rows if r.get('dataset') == -1 and 'tr_loss' in r]
+    assert len(train_rows) == 4 and all(np.isfinite(r['tr_loss']) for r in train_rows)
+    assert train_rows[-1]['tr_loss'] < train_rows[0]['tr_loss']
+    vdir = os.path.join(expt_dir, 'version_0')
+    sd = torch.load(os.path.join(vdir, 'best_val_model.pt'), map_location='cpu')
+    assert set(sd) == set(model.state_dict())
+    with open(os.path.join(vdir, 'lab_expt_mouse_s0_latents.pkl'), 'rb') as fh:
+        d = pickle.load(fh)
+    full = [z for z in d['latents'] if len(z)]
+    assert len(full) == 20 and all(z.shape == (f.shape[0], 6) for z, f in zip(d['latents'], frames))

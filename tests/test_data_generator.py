@@ -372,3 +372,39 @@ def test_get_reconstruction_dispatch_per_model_class():
     assert lat.shape == (3, 4) and np.all(lat[:, 2:] == 1)
     m = Mock('ae', 2)
     assert get_reconstruction(m, z).shape == (3, 1, 4, 4) and torch.all(m.decoded == 0)
+
+
+def test_encode_trials_groups_and_orders_on_a_mock_model():
+    """Host logic of fitting.eval.encode_trials on the CPU with a stand-in model: trials are grouped into launches of
+    at most ``frames_per_launch`` frames (a single longer trial still goes alone), uint8 groups are scaled when the
+    first layer cannot read bytes, mixed uint8 / float groups are unified, and the latents come back in trial order."""
+    import torch
+    from behavenet_b200.fitting.eval import encode_trials
+
+    class Mock(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.hparams = {'model_class': 'ae', 'model_type': 'linear', 'n_ae_latents': 3}
+            self.calls = []
+
+        def encoding(self, x, dataset=None):
+            assert x.dtype == torch.float32          # (no byte loader for this model: uint8 arrives scaled)
+            self.calls.append(int(x.shape[0]))
+            m = x.reshape(x.shape[0], -1).mean(1, keepdim=True)
+            return torch.cat([m, 2 * m, m * 0 + x.shape[0]], 1), None, None
+
+    rng = np.random.RandomState(0)
+    lens = [5, 7, 40, 3, 3, 9]
+    trials = [rng.randint(0, 256, (t, 1, 4, 4)).astype(np.uint8) for t in lens]
+    trials[4] = trials[4].astype(np.float32) / 255            # a float trial next to uint8 ones
+    model = Mock()
+    model.train()
+    lat, lengths = encode_trials(model, trials, frames_per_launch=16, device='cpu')
+    assert lengths == lens and lat.shape == (sum(lens), 3) and model.training
+    assert model.calls == [12, 40, 15]                       # [5, 7] | [40] | [3, 3, 9]
+    want = np.concatenate([t.reshape(t.shape[0], -1).astype(np.float64).mean(1) / (255 if t.dtype == np.uint8 else 1)
+                           for t in trials])
+    np.testing.assert_allclose(lat[:, 0].numpy(), want, rtol=1e-6)
+    np.testing.assert_allclose(lat[:, 1].numpy(), 2 * want, rtol=1e-6)
+    assert encode_trials(model, [], device='cpu')[0].shape == (0, 3)

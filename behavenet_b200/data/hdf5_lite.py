@@ -435,19 +435,26 @@ def _fractal_heap_links(r, heap):
         raise ValueError('bad fractal heap header at %d' % heap)
     o = heap + 5
     o += 2                                              # heap ID length
-    filt_len = r.u(o, 2); o += 2
-    flags = buf[o]; o += 1
+    filt_len = r.u(o, 2)                                # encoded length of the I/O filter pipeline
+    o += 2
+    flags = buf[o]
+    o += 1
     o += 4                                              # max size of managed objects
     o += r.lsz + r.osz                                  # next huge id, huge-object B-tree
     o += r.lsz + r.osz                                  # free space, free-space manager
     o += 4 * r.lsz                                      # managed space, allocated space, iterator offset, n objects
     o += 4 * r.lsz                                      # huge size / count, tiny size / count
-    width = r.u(o, 2); o += 2
-    start = r.length(o); o += r.lsz
-    max_direct = r.length(o); o += r.lsz
-    max_heap_bits = r.u(o, 2); o += 2
+    width = r.u(o, 2)
+    o += 2
+    start = r.length(o)                                 # starting block size
+    o += r.lsz
+    max_direct = r.length(o)
+    o += r.lsz
+    max_heap_bits = r.u(o, 2)
+    o += 2
     o += 2                                              # starting rows of the root indirect block
-    root = r.addr(o); o += r.osz
+    root = r.addr(o)
+    o += r.osz
     root_rows = r.u(o, 2)
     if filt_len:
         raise NotImplementedError('filtered fractal heap')

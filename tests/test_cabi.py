@@ -113,6 +113,20 @@ def test_argument_validation_reports_errors():
     out = C.c_void_p()
     assert lib.bn_cae_plan_create(C.byref(d), C.byref(out)) != 0
     assert b'n_layers' in lib.bn_last_error()
+    # linear autoencoder entry points: validated before any launch
+    assert lib.bn_linae_workspace_bytes(256, 16384, 12) == 4 * (2 * 256 * 12 + 256 * 16384)
+    assert lib.bn_linae_workspace_bytes(0, 16384, 12) == 0
+    fake = C.c_void_p(1 << 20)      # never dereferenced: the calls below fail on their arguments
+    assert lib.bn_linae_forward(4, 100, 65, fake, fake, fake, fake, fake, None, None) != 0
+    assert b'L=65' in lib.bn_last_error()
+    assert lib.bn_linae_forward(4, 100, 8, None, fake, fake, fake, fake, None, None) != 0
+    assert b'null argument' in lib.bn_last_error()
+    assert lib.bn_linae_loss(4, 100, 8, fake, None, fake, fake, fake, 200, 3, 6, fake, fake, None, None, None, None) != 0
+    assert b'outside the batch' in lib.bn_last_error()
+    assert lib.bn_linae_decode(0, 100, 8, fake, fake, fake, fake, None) == 0        # nothing to do
+    # two-phase encoder backward: the phase selector is checked with the other arguments
+    assert lib.bn_cae_encode_bwd_phase(fake, 4, fake, fake, None, fake, fake, fake, fake, None, 7) != 0
+    assert b'phase 7' in lib.bn_last_error()
 
 
 def test_host_gather_rows_matches_concatenate():
